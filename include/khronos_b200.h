@@ -1,0 +1,239 @@
+/*
+ * khronos_b200.h — C ABI of the B200-native active-window volumetric integrator.
+ *
+ * This is the drop-in boundary for Khronos' per-frame active-window fusion hot path. Every entry
+ * point cites the reference interface it replaces (paths relative to the Khronos checkout;
+ * "UP" = upstream MIT-SPARK/Hydra, which Khronos only calls / subclasses).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no C++/torch types. Every function returns a kb_status
+ *     (0 = ok) and never throws across the ABI; kb_last_error() gives a message for the handle.
+ *   - A handle owns all device memory of one volumetric map (TSDF + tracking + semantic layers over
+ *     an open-addressed GPU block hash) and one CUDA stream. Calls on one handle are serialised by
+ *     the caller (the reference holds mutex_, khronos/src/active_window/active_window.cpp:119);
+ *     different handles are fully concurrent (extraction workers own private maps,
+ *     khronos/src/active_window/object_extraction/object_worker_pool.cpp:130).
+ *   - Input pointers are borrowed for the duration of the call. kb_frame.memory says whether image
+ *     pointers are host (pageable or pinned) or device pointers. Outputs are caller-allocated.
+ *   - Images are row-major H x W like cv::Mat (depth CV_32FC1, label/mask/object CV_32SC1,
+ *     vertex CV_32FC3, color CV_8UC3).
+ *   - There is NO CPU fallback: kb_create fails with KB_ERR_NO_DEVICE if no CUDA device exists.
+ */
+#ifndef KHRONOS_B200_H_
+#define KHRONOS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KB_ABI_VERSION 1
+
+typedef enum kb_status {
+  KB_OK = 0,
+  KB_ERR_INVALID = 1,    /* invalid argument / configuration (reference: config::checkValid aborts) */
+  KB_ERR_CUDA = 2,       /* CUDA runtime error */
+  KB_ERR_CAPACITY = 3,   /* block pool / hash table / semantic pool exhausted */
+  KB_ERR_NO_DEVICE = 4,  /* no usable CUDA device: the product path refuses to run */
+  KB_ERR_STATE = 5       /* call order violated (e.g. non-monotonic stamps) */
+} kb_status;
+
+typedef struct kb_handle kb_handle;
+
+/* hydra::VolumetricMap::Config (UP; fields as used at
+ * khronos/src/active_window/object_extraction/mesh_object_extractor.cpp:201-211) + pool sizing. */
+typedef struct kb_map_config {
+  float voxel_size;           /* metres */
+  int32_t voxels_per_side;    /* 8 or 16 */
+  float truncation_distance;  /* metres */
+  int32_t with_semantics;
+  int32_t with_tracking;
+  int32_t max_blocks;           /* capacity of the device block pool */
+  int32_t max_semantic_blocks;  /* capacity of the lazily assigned semantic pool (0 => max_blocks) */
+} kb_map_config;
+
+enum { KB_INTERP_NEAREST = 0, KB_INTERP_BILINEAR = 1, KB_INTERP_ADAPTIVE = 2 };
+enum { KB_SEMANTICS_NONE = 0, KB_SEMANTICS_MLE = 1, KB_SEMANTICS_BINARY = 2 };
+#define KB_MAX_LABELS 64
+
+/* hydra::ProjectiveIntegrator::Config (UP; Khronos only sets num_threads,
+ * khronos_ros/config/mapper/uHumans2.yaml:80-81) + the semantic integrator choice
+ * (khronos/src/active_window/integration/object_integrator.cpp:44-48 forces BINARY). */
+typedef struct kb_integrator_config {
+  int32_t use_weight_dropoff;     /* default 1 */
+  float weight_dropoff_epsilon;   /* default -1 (negative => multiple of voxel size) */
+  int32_t use_constant_weight;    /* default 0 */
+  float max_weight;               /* default 1e5 */
+  int32_t interpolation_method;   /* default KB_INTERP_ADAPTIVE */
+  float adaptive_max_depth_difference; /* bilinear only if max-min of the 4 taps < this; default 0.2 */
+  int32_t semantic_mode;          /* KB_SEMANTICS_* */
+  int32_t num_labels;             /* MLE: total labels N (<= KB_MAX_LABELS) */
+  float label_confidence;         /* MLE: default 0.9 */
+  uint8_t label_blocked[KB_MAX_LABELS]; /* MLE: 1 => label is dynamic/invalid: canIntegrate false */
+  int32_t num_threads;            /* CPU oracle only; ignored by the GPU product */
+} kb_integrator_config;
+
+/* khronos::TrackingIntegrator::Config,
+ * khronos/include/khronos/active_window/integration/tracking_integrator.h:59-83 */
+typedef struct kb_tracking_config {
+  float temporal_buffer;           /* s, default 1 */
+  float burn_in_period;            /* s, default 1 (declared but unused by the reference) */
+  float tsdf_occupancy_threshold;  /* m; negative => multiple of voxel size; default -1.5 */
+  int32_t neighbor_connectivity;   /* 6 | 18 | 26, default 18 */
+  float temporal_window;           /* s, default 3 */
+  int32_t num_threads;             /* CPU oracle only */
+} kb_tracking_config;
+
+/* khronos::FreeSpaceMotionDetector::Config,
+ * khronos/include/khronos/active_window/motion_detection/free_space_motion_detector.h:70-95 */
+typedef struct kb_motion_config {
+  int32_t neighbor_connectivity;   /* 6 | 18 | 26, default 26 */
+  int32_t min_cluster_size;        /* default 0 */
+  int32_t max_cluster_size;        /* default 1000000 */
+  float min_separation_distance;   /* voxels, default 1 */
+  float max_range;                 /* m, default 10000 */
+  float min_z_coordinate;          /* m (sensor frame offset), default -10000 */
+  int32_t num_threads;             /* CPU oracle only */
+} kb_motion_config;
+
+/* Pinhole hydra::Camera (UP) + range limits from InputData. */
+typedef struct kb_camera {
+  int32_t width, height;
+  float fx, fy, cx, cy;
+  float min_range, max_range;
+} kb_camera;
+
+enum { KB_MEM_HOST = 0, KB_MEM_DEVICE = 1 };
+
+/* khronos::FrameData (khronos/include/khronos/active_window/data/frame_data.h:59-83) wrapping
+ * hydra::InputData (UP). */
+typedef struct kb_frame {
+  const float* depth;          /* H*W z-depth == range image for cameras; <= 0 invalid */
+  const int32_t* label;        /* H*W semantic labels, may be NULL */
+  const int32_t* mask;         /* H*W dynamic_image; non-zero pixels are not integrated near the
+                                  surface (hydra::maskNonZero, active_window.cpp:209); may be NULL */
+  const int32_t* object_image; /* H*W, BINARY mode label source (object_integrator.cpp:76-79) */
+  const uint8_t* color;        /* H*W*3 RGB, may be NULL */
+  const float* vertex_world;   /* H*W*3 world-frame vertex map; NULL => computed from depth+pose */
+  double world_T_sensor[16];   /* row-major 4x4, InputData::getSensorPose() */
+  uint64_t stamp_ns;           /* must be > 0 (0 is the reference's "never observed" sentinel) */
+  int32_t object_target_id;    /* BINARY mode: ObjectIntegrator::setFrameData target id */
+  int32_t memory;              /* KB_MEM_HOST | KB_MEM_DEVICE for the image pointers above */
+} kb_frame;
+
+typedef struct kb_frame_stats {
+  int32_t blocks_in_frustum;   /* blocks selected by the frustum test (or all allocated blocks) */
+  int32_t blocks_allocated;    /* new blocks allocated by this call */
+  int32_t blocks_updated;      /* blocks with at least one integrated voxel */
+  int32_t voxels_updated;      /* Nv: voxels with a valid measurement */
+  int32_t voxels_in_band;      /* Nb: of those, |sdf| < truncation */
+  int32_t voxels_semantic;     /* band voxels whose semantic state was updated */
+  int32_t total_blocks;        /* blocks allocated in the map after the call */
+  int32_t capacity_exceeded;   /* non-zero if a pool ran out (results incomplete) */
+} kb_frame_stats;
+
+/* ---- lifecycle -------------------------------------------------------------------------------- */
+
+/* Replaces VolumetricMap construction + ProjectiveIntegrator / TrackingIntegrator /
+ * FreeSpaceMotionDetector construction (active_window.cpp:75-98). tracking/motion may be NULL. */
+int kb_create(const kb_map_config* map, const kb_integrator_config* integrator,
+              const kb_tracking_config* tracking, const kb_motion_config* motion, int device,
+              kb_handle** out);
+int kb_destroy(kb_handle* h);
+const char* kb_last_error(const kb_handle* h);
+int kb_abi_version(void);
+
+/* Use an externally owned cudaStream_t (e.g. torch's current stream) for all work of this handle. */
+int kb_set_stream(kb_handle* h, void* cuda_stream);
+int kb_synchronize(kb_handle* h);
+
+int kb_set_camera(kb_handle* h, const kb_camera* camera);
+
+/* Spatial block-hash sharding across the GPUs of one box (new in this build): this
+ * handle only allocates/integrates blocks with owner(block) == rank. rank=0,nranks=1 = unsharded. */
+int kb_set_shard(kb_handle* h, int rank, int nranks);
+/* Owner rank of a block index under the shard hash (pure function; usable without a device). */
+int kb_block_owner(int32_t bx, int32_t by, int32_t bz, int nranks);
+
+/* ---- the hot path ----------------------------------------------------------------------------- */
+
+/* K0+K1. Replaces hydra::ProjectiveIntegrator::updateMap(data, map, allocate_blocks, mask)
+ * (call sites active_window.cpp:210, mesh_object_extractor.cpp:242) incl. the computeLabel hook
+ * (object_integrator.cpp:58-81). stats may be NULL (then no device->host sync happens). */
+int kb_integrate_frame(kb_handle* h, const kb_frame* frame, int allocate_blocks,
+                       kb_frame_stats* stats);
+
+/* K2+K3. Replaces TrackingIntegrator::updateBlocks (tracking_integrator.cpp:71-104). */
+int kb_update_tracking(kb_handle* h, uint64_t stamp_ns);
+
+/* K2r. Replaces TrackingIntegrator::resetInactive (tracking_integrator.cpp:106-131). Removed block
+ * indices (x,y,z triples, ascending) are written to removed_xyz (capacity max_removed triples). */
+int kb_reset_inactive(kb_handle* h, int32_t* removed_xyz, int32_t max_removed, int32_t* n_removed);
+
+/* ActiveWindow::finishMapping (active_window.cpp:181-183): has_active_data=false on all blocks. */
+int kb_mark_all_inactive(kb_handle* h);
+
+/* Clears the `updated` flag of all blocks (active_window.cpp:169-171). */
+int kb_clear_updated(kb_handle* h);
+
+/* M1-M4. Replaces FreeSpaceMotionDetector::processInput (free_space_motion_detector.cpp:73-103).
+ * dynamic_image_out: H*W int32 (host), 0 = static, cluster ids 1..255. n_seeds/n_clusters optional. */
+int kb_detect_motion(kb_handle* h, const kb_frame* frame, int32_t* dynamic_image_out,
+                     int32_t* n_seeds, int32_t* n_clusters);
+/* Clusters of the last kb_detect_motion call (MeasurementCluster, measurement_clusters.h:63-81):
+ * counts[c*2+0]=#pixels, counts[c*2+1]=#voxels; then flat pixel (u,v) pairs (order within a cluster
+ * unspecified, duplicates preserved as in the reference) and voxel (x,y,z) global indices (ascending
+ * z,y,x) in cluster order; bbox_min_max[c*6..] = world AABB of the cluster's vertices
+ * (writeClustersToData, free_space_motion_detector.cpp:396-397). NULL pointers are skipped. */
+int kb_get_motion_clusters(kb_handle* h, int32_t* counts, int32_t* pixels_uv, int64_t* voxels_xyz,
+                           float* bbox_min_max, int32_t* total_pixels, int32_t* total_voxels);
+
+/* E0. Replaces the dense allocation loop of MeshObjectExtractor::extractStaticObject
+ * (mesh_object_extractor.cpp:220-228): allocates all blocks in [min,max] (inclusive). */
+int kb_allocate_box(kb_handle* h, const int32_t min_block[3], const int32_t max_block[3]);
+
+/* K4. Replaces the low-confidence erase loop (mesh_object_extractor.cpp:246-264) with
+ * computeConfidence (:342-356): voxels with distance <= 0 and confidence < min_confidence get
+ * distance = +truncation. */
+int kb_scan_object_confidence(kb_handle* h, float min_confidence, int32_t min_observations,
+                              int32_t* n_erased);
+
+/* ---- mirror-back / parity export ---------------------------------------------------------------- */
+
+enum { KB_EXPORT_ALL = 0, KB_EXPORT_UPDATED = 1 };
+
+/* Block flags bits (hydra::TsdfBlock flags + TrackingBlock::has_active_data). */
+enum {
+  KB_FLAG_UPDATED = 1, KB_FLAG_MESH_UPDATED = 2, KB_FLAG_ESDF_UPDATED = 4,
+  KB_FLAG_TRACKING_UPDATED = 8, KB_FLAG_HAS_ACTIVE_DATA = 16
+};
+
+/* Caller-allocated arrays for n blocks of V = voxels_per_side^3 voxels, blocks sorted ascending by
+ * (x, y, z). Any pointer may be NULL to skip that field. This is what repopulates
+ * hydra::VolumetricMap for MeshIntegrator / cloneUpdated (active_window.cpp:223,229). */
+typedef struct kb_block_export {
+  int32_t* block_index;     /* n*3 */
+  uint8_t* block_flags;     /* n */
+  float* distance;          /* n*V  TsdfVoxel::distance */
+  float* weight;            /* n*V  TsdfVoxel::weight */
+  uint8_t* color;           /* n*V*3 */
+  uint64_t* last_observed;  /* n*V  TrackingVoxel */
+  uint64_t* last_occupied;  /* n*V */
+  uint8_t* ever_free;       /* n*V */
+  uint8_t* active;          /* n*V */
+  uint8_t* to_remove;       /* n*V */
+  uint32_t* semantic_label; /* n*V  SemanticVoxel */
+  uint8_t* semantic_empty;  /* n*V */
+  float* semantic_likelihoods; /* n*V*L (L = num_labels for MLE, 2 for BINARY) */
+} kb_block_export;
+
+int kb_num_blocks(kb_handle* h, int which, int32_t* n);
+int kb_export_blocks(kb_handle* h, int which, int32_t max_blocks, kb_block_export* out,
+                     int32_t* n_written);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* KHRONOS_B200_H_ */

@@ -1,0 +1,337 @@
+"""ctypes binding of the C ABI declared in include/khronos_b200.h.
+
+`MapHandle` is a thin, 1:1 wrapper over the C entry points (prefix ``kb_``). The struct layouts
+here must match the header exactly. The same class can drive any library exporting the same
+entry points under another prefix (the tests use this to drive the CPU oracle with ``ko_``);
+the product itself only ever loads ``libkhronos_b200.so``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+
+KB_MAX_LABELS = 64
+KB_OK = 0
+KB_ERR_NO_DEVICE = 4
+INTERP_NEAREST, INTERP_BILINEAR, INTERP_ADAPTIVE = 0, 1, 2
+SEM_NONE, SEM_MLE, SEM_BINARY = 0, 1, 2
+MEM_HOST, MEM_DEVICE = 0, 1
+EXPORT_ALL, EXPORT_UPDATED = 0, 1
+FLAG_UPDATED, FLAG_MESH_UPDATED, FLAG_ESDF_UPDATED, FLAG_TRACKING_UPDATED, FLAG_HAS_ACTIVE_DATA = 1, 2, 4, 8, 16
+
+
+class MapConfig(C.Structure):
+    _fields_ = [("voxel_size", C.c_float), ("voxels_per_side", C.c_int32),
+                ("truncation_distance", C.c_float), ("with_semantics", C.c_int32),
+                ("with_tracking", C.c_int32), ("max_blocks", C.c_int32),
+                ("max_semantic_blocks", C.c_int32)]
+
+
+class IntegratorConfig(C.Structure):
+    _fields_ = [("use_weight_dropoff", C.c_int32), ("weight_dropoff_epsilon", C.c_float),
+                ("use_constant_weight", C.c_int32), ("max_weight", C.c_float),
+                ("interpolation_method", C.c_int32), ("adaptive_max_depth_difference", C.c_float),
+                ("semantic_mode", C.c_int32), ("num_labels", C.c_int32),
+                ("label_confidence", C.c_float), ("label_blocked", C.c_uint8 * KB_MAX_LABELS),
+                ("num_threads", C.c_int32)]
+
+
+class TrackingConfig(C.Structure):
+    _fields_ = [("temporal_buffer", C.c_float), ("burn_in_period", C.c_float),
+                ("tsdf_occupancy_threshold", C.c_float), ("neighbor_connectivity", C.c_int32),
+                ("temporal_window", C.c_float), ("num_threads", C.c_int32)]
+
+
+class MotionConfig(C.Structure):
+    _fields_ = [("neighbor_connectivity", C.c_int32), ("min_cluster_size", C.c_int32),
+                ("max_cluster_size", C.c_int32), ("min_separation_distance", C.c_float),
+                ("max_range", C.c_float), ("min_z_coordinate", C.c_float),
+                ("num_threads", C.c_int32)]
+
+
+class Camera(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("fx", C.c_float), ("fy", C.c_float),
+                ("cx", C.c_float), ("cy", C.c_float), ("min_range", C.c_float),
+                ("max_range", C.c_float)]
+
+
+class Frame(C.Structure):
+    _fields_ = [("depth", C.c_void_p), ("label", C.c_void_p), ("mask", C.c_void_p),
+                ("object_image", C.c_void_p), ("color", C.c_void_p), ("vertex_world", C.c_void_p),
+                ("world_T_sensor", C.c_double * 16), ("stamp_ns", C.c_uint64),
+                ("object_target_id", C.c_int32), ("memory", C.c_int32)]
+
+
+class FrameStats(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in
+                ("blocks_in_frustum", "blocks_allocated", "blocks_updated", "voxels_updated",
+                 "voxels_in_band", "voxels_semantic", "total_blocks", "capacity_exceeded")]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class BlockExport(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in
+                ("block_index", "block_flags", "distance", "weight", "color", "last_observed",
+                 "last_occupied", "ever_free", "active", "to_remove", "semantic_label",
+                 "semantic_empty", "semantic_likelihoods")]
+
+
+# ---- defaults mirroring the reference configs ------------------------------------------------------
+
+def default_map_config(voxel_size=0.05, vps=16, trunc=0.15, with_semantics=True, with_tracking=True,
+                       max_blocks=4096, max_semantic_blocks=0) -> MapConfig:
+    """hydra::VolumetricMap::Config; values of khronos_ros/config/mapper/ground_truth.yaml:63-67."""
+    return MapConfig(voxel_size, vps, trunc, int(with_semantics), int(with_tracking), max_blocks,
+                     max_semantic_blocks)
+
+
+def default_integrator_config(semantic_mode=SEM_MLE, num_labels=20, blocked=(), num_threads=-1,
+                              interpolation=INTERP_ADAPTIVE) -> IntegratorConfig:
+    """hydra::ProjectiveIntegrator::Config defaults."""
+    c = IntegratorConfig()
+    c.use_weight_dropoff = 1
+    c.weight_dropoff_epsilon = -1.0
+    c.use_constant_weight = 0
+    c.max_weight = 1e5
+    c.interpolation_method = interpolation
+    c.adaptive_max_depth_difference = 0.2
+    c.semantic_mode = semantic_mode
+    c.num_labels = num_labels if semantic_mode == SEM_MLE else (2 if semantic_mode == SEM_BINARY else 0)
+    c.label_confidence = 0.9
+    for b in blocked:
+        c.label_blocked[b] = 1
+    c.num_threads = num_threads
+    return c
+
+
+def default_tracking_config(num_threads=-1) -> TrackingConfig:
+    """khronos::TrackingIntegrator::Config defaults (tracking_integrator.h:59-83)."""
+    return TrackingConfig(1.0, 1.0, -1.5, 18, 3.0, num_threads)
+
+
+def default_motion_config(num_threads=-1, min_cluster_size=0, max_cluster_size=1000000,
+                          min_separation_distance=1.0, connectivity=26) -> MotionConfig:
+    """khronos::FreeSpaceMotionDetector::Config defaults (free_space_motion_detector.h:70-95)."""
+    return MotionConfig(connectivity, min_cluster_size, max_cluster_size, min_separation_distance,
+                        10000.0, -10000.0, num_threads)
+
+
+class KbError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__(f"status {status}: {msg}")
+        self.status = status
+
+
+def _ptr(a) -> Optional[int]:
+    """Address of a numpy array (host) / torch tensor (device or host) / raw int, or None."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return a
+    if isinstance(a, np.ndarray):
+        assert a.flags["C_CONTIGUOUS"]
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):
+        assert a.is_contiguous()
+        return a.data_ptr()
+    raise TypeError(type(a))
+
+
+@dataclass
+class Blocks:
+    """Host copy of exported blocks (sorted by block index x,y,z)."""
+    block_index: np.ndarray
+    block_flags: np.ndarray
+    distance: np.ndarray
+    weight: np.ndarray
+    last_observed: np.ndarray
+    last_occupied: np.ndarray
+    ever_free: np.ndarray
+    active: np.ndarray
+    to_remove: np.ndarray
+    semantic_label: np.ndarray
+    semantic_empty: np.ndarray
+    semantic_likelihoods: Optional[np.ndarray] = None
+    extra: dict = field(default_factory=dict)
+
+    @property
+    def n(self):
+        return int(self.block_index.shape[0])
+
+
+class MapHandle:
+    """One volumetric map + integrators behind the C ABI (see include/khronos_b200.h)."""
+
+    def __init__(self, lib: C.CDLL, prefix: str, map_cfg: MapConfig, integ_cfg: IntegratorConfig,
+                 tracking_cfg: Optional[TrackingConfig] = None,
+                 motion_cfg: Optional[MotionConfig] = None, device: int = 0):
+        self._lib, self._p = lib, prefix
+        self.map_cfg, self.integ_cfg = map_cfg, integ_cfg
+        self.V = map_cfg.voxels_per_side ** 3
+        self.L = 0
+        if map_cfg.with_semantics:
+            self.L = {SEM_MLE: integ_cfg.num_labels, SEM_BINARY: 2}.get(integ_cfg.semantic_mode, 0)
+        self._h = C.c_void_p()
+        self._camera = None
+        st = self._fn("create")(C.byref(map_cfg), C.byref(integ_cfg),
+                                C.byref(tracking_cfg) if tracking_cfg else None,
+                                C.byref(motion_cfg) if motion_cfg else None, device, C.byref(self._h))
+        if st != KB_OK:
+            self._h = C.c_void_p()
+            raise KbError(st, "create failed (no CUDA device?)" if st == KB_ERR_NO_DEVICE else "create failed")
+
+    def _fn(self, name):
+        f = getattr(self._lib, self._p + name)
+        f.restype = C.c_int
+        return f
+
+    def _check(self, st):
+        if st != KB_OK:
+            e = getattr(self._lib, self._p + "last_error")
+            e.restype = C.c_char_p
+            raise KbError(st, (e(self._h) or b"").decode())
+
+    def close(self):
+        if self._h:
+            self._fn("destroy")(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- configuration
+    def set_camera(self, cam: Camera):
+        self._camera = cam
+        self._check(self._fn("set_camera")(self._h, C.byref(cam)))
+
+    def set_stream(self, cuda_stream: int):
+        self._check(self._fn("set_stream")(self._h, C.c_void_p(cuda_stream)))
+
+    def synchronize(self):
+        self._check(self._fn("synchronize")(self._h))
+
+    def set_shard(self, rank: int, nranks: int):
+        self._check(self._fn("set_shard")(self._h, rank, nranks))
+
+    # ---- hot path
+    @staticmethod
+    def make_frame(depth, pose, stamp_ns, label=None, mask=None, object_image=None, color=None,
+                   vertex_world=None, target_id=0, memory=MEM_HOST) -> Frame:
+        f = Frame()
+        f.depth, f.label, f.mask = _ptr(depth), _ptr(label), _ptr(mask)
+        f.object_image, f.color, f.vertex_world = _ptr(object_image), _ptr(color), _ptr(vertex_world)
+        T = np.asarray(pose, dtype=np.float64).reshape(16)
+        for i in range(16):
+            f.world_T_sensor[i] = float(T[i])
+        f.stamp_ns = int(stamp_ns)
+        f.object_target_id = int(target_id)
+        f.memory = memory
+        f._keep = (depth, label, mask, object_image, color, vertex_world)  # keep buffers alive
+        return f
+
+    def integrate_frame(self, frame: Frame, allocate_blocks=True, want_stats=True):
+        stats = FrameStats()
+        self._check(self._fn("integrate_frame")(self._h, C.byref(frame), int(allocate_blocks),
+                                                C.byref(stats) if want_stats else None))
+        return stats if want_stats else None
+
+    def update_tracking(self, stamp_ns: int):
+        self._check(self._fn("update_tracking")(self._h, C.c_uint64(int(stamp_ns))))
+
+    def reset_inactive(self, max_removed=1 << 20) -> np.ndarray:
+        n = C.c_int32(0)
+        buf = np.zeros((max_removed, 3), np.int32)
+        self._check(self._fn("reset_inactive")(self._h, C.c_void_p(buf.ctypes.data), max_removed, C.byref(n)))
+        return buf[: n.value].copy()
+
+    def mark_all_inactive(self):
+        self._check(self._fn("mark_all_inactive")(self._h))
+
+    def clear_updated(self):
+        self._check(self._fn("clear_updated")(self._h))
+
+    def detect_motion(self, frame: Frame):
+        H, W = self._camera.height, self._camera.width
+        img = np.zeros((H, W), np.int32)
+        ns, nc = C.c_int32(0), C.c_int32(0)
+        self._check(self._fn("detect_motion")(self._h, C.byref(frame), C.c_void_p(img.ctypes.data),
+                                              C.byref(ns), C.byref(nc)))
+        self._last_nc = nc.value
+        return img, ns.value, nc.value
+
+    def get_motion_clusters(self):
+        tp, tv = C.c_int32(0), C.c_int32(0)
+        f = self._fn("get_motion_clusters")
+        self._check(f(self._h, None, None, None, None, C.byref(tp), C.byref(tv)))
+        nc = getattr(self, "_last_nc", 0)
+        counts = np.zeros((max(nc, 1), 2), np.int32)
+        px = np.zeros((max(tp.value, 1), 2), np.int32)
+        vx = np.zeros((max(tv.value, 1), 3), np.int64)
+        bb = np.zeros((counts.shape[0], 6), np.float32)
+        self._check(f(self._h, C.c_void_p(counts.ctypes.data), C.c_void_p(px.ctypes.data),
+                      C.c_void_p(vx.ctypes.data), C.c_void_p(bb.ctypes.data), C.byref(tp), C.byref(tv)))
+        out, po, vo = [], 0, 0
+        for c in range(nc):
+            npx, nvx = int(counts[c, 0]), int(counts[c, 1])
+            out.append({"pixels": px[po:po + npx].copy(), "voxels": vx[vo:vo + nvx].copy(),
+                        "bbox": bb[c].copy()})
+            po += npx
+            vo += nvx
+        return out
+
+    def allocate_box(self, mn, mx):
+        a = (C.c_int32 * 3)(*[int(v) for v in mn])
+        b = (C.c_int32 * 3)(*[int(v) for v in mx])
+        self._check(self._fn("allocate_box")(self._h, a, b))
+
+    def scan_object_confidence(self, min_confidence=0.5, min_observations=10) -> int:
+        n = C.c_int32(0)
+        self._check(self._fn("scan_object_confidence")(self._h, C.c_float(min_confidence),
+                                                       int(min_observations), C.byref(n)))
+        return n.value
+
+    # ---- export
+    def num_blocks(self, which=EXPORT_ALL) -> int:
+        n = C.c_int32(0)
+        self._check(self._fn("num_blocks")(self._h, which, C.byref(n)))
+        return n.value
+
+    def export_blocks(self, which=EXPORT_ALL, likelihoods=True) -> Blocks:
+        n, V, L = self.num_blocks(which), self.V, self.L
+        b = Blocks(
+            block_index=np.zeros((n, 3), np.int32), block_flags=np.zeros(n, np.uint8),
+            distance=np.zeros((n, V), np.float32), weight=np.zeros((n, V), np.float32),
+            last_observed=np.zeros((n, V), np.uint64), last_occupied=np.zeros((n, V), np.uint64),
+            ever_free=np.zeros((n, V), np.uint8), active=np.zeros((n, V), np.uint8),
+            to_remove=np.zeros((n, V), np.uint8), semantic_label=np.zeros((n, V), np.uint32),
+            semantic_empty=np.ones((n, V), np.uint8),
+            semantic_likelihoods=np.zeros((n, V, L), np.float32) if (likelihoods and L > 0) else None)
+        ex = BlockExport()
+        for name, _ in BlockExport._fields_:
+            arr = getattr(b, name, None)
+            setattr(ex, name, arr.ctypes.data if isinstance(arr, np.ndarray) and arr.size else None)
+        nw = C.c_int32(0)
+        if n:
+            self._check(self._fn("export_blocks")(self._h, which, n, C.byref(ex), C.byref(nw)))
+            assert nw.value == n
+        return b
+
+
+def load_product_library() -> C.CDLL:
+    """Load the in-tree CUDA product library. Fails loudly if it is missing: there is no fallback."""
+    here = os.path.dirname(os.path.abspath(__file__))
+    path = os.path.join(here, "csrc", "libkhronos_b200.so")
+    if not os.path.exists(path):
+        raise ImportError(
+            f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). khronos_b200 has no CPU fallback.")
+    return C.CDLL(path, mode=C.RTLD_GLOBAL)

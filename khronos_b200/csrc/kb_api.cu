@@ -1,0 +1,724 @@
+// C ABI (include/khronos_b200.h) over the sm_100a kernels: handle lifetime, device memory, frame
+// staging, stamp <-> frame-index bookkeeping, export. Host code only; no CPU compute fallback exists:
+// every entry point that touches voxels launches a kernel, and kb_create refuses to run without a GPU.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/khronos_b200.h"
+#include "kb_kernels.cuh"
+#include "kb_motion_host.h"
+
+using namespace kb;
+
+struct kb_handle {
+  kb_map_config map{};
+  kb_integrator_config integ{};
+  kb_tracking_config trk{};
+  kb_motion_config mot{};
+  kb_camera cam{};
+  bool has_trk = false, has_mot = false, has_cam = false;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int rank = 0, nranks = 1;
+  DeviceMap dm{};
+  int L = 0;
+  float block_size = 0, mle_diag = 0, mle_off = 0, mle_init = 0;
+  unsigned long long blocked_mask = 0;
+  std::vector<uint64_t> stamps;  // frame index -> stamp; [0] = 0 ("never")
+  // host frame staging (device copies of host images)
+  float* stg_depth = nullptr;
+  int* stg_label = nullptr;
+  int* stg_mask = nullptr;
+  int* stg_object = nullptr;
+  float* stg_vertex = nullptr;
+  size_t stg_pixels = 0;
+  // counters
+  int* h_ctr = nullptr;  // pinned mirror
+  int prev_ctr[kNumCounters] = {0};
+  bool ctr_dirty = false;  // launches happened since prev_ctr was refreshed
+  // motion detection scratch + result
+  int3* d_pixel_gidx = nullptr;
+  uint8_t* d_pixel_seed = nullptr;
+  std::vector<int32_t> h_pixel_gidx;
+  std::vector<uint8_t> h_pixel_seed;
+  std::vector<float> h_depth;
+  MotionResult motion;
+  int3* d_removed = nullptr;
+  int max_removed = 0;
+  std::string err;
+};
+
+namespace {
+
+#define KB_CUDA(h, call)                                                                       \
+  do {                                                                                         \
+    cudaError_t e_ = (call);                                                                   \
+    if (e_ != cudaSuccess) {                                                                   \
+      (h)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                           \
+      return KB_ERR_CUDA;                                                                      \
+    }                                                                                          \
+  } while (0)
+
+int fail(kb_handle* h, int code, const char* msg) {
+  if (h) h->err = msg;
+  return code;
+}
+
+inline double toSeconds(uint64_t ns) { return static_cast<double>(ns) / 1e9; }
+
+template <typename T>
+cudaError_t devAlloc(T** p, size_t n, int fill_byte) {
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), std::max<size_t>(n, 1) * sizeof(T));
+  if (e != cudaSuccess) return e;
+  return cudaMemset(*p, fill_byte, std::max<size_t>(n, 1) * sizeof(T));
+}
+
+int ensureStaging(kb_handle* h, size_t pixels) {
+  if (h->stg_pixels >= pixels) return KB_OK;
+  cudaFree(h->stg_depth); cudaFree(h->stg_label); cudaFree(h->stg_mask); cudaFree(h->stg_object);
+  cudaFree(h->stg_vertex); cudaFree(h->d_pixel_gidx); cudaFree(h->d_pixel_seed);
+  KB_CUDA(h, devAlloc(&h->stg_depth, pixels, 0));
+  KB_CUDA(h, devAlloc(&h->stg_label, pixels, 0));
+  KB_CUDA(h, devAlloc(&h->stg_mask, pixels, 0));
+  KB_CUDA(h, devAlloc(&h->stg_object, pixels, 0));
+  KB_CUDA(h, devAlloc(&h->stg_vertex, pixels * 3, 0));
+  KB_CUDA(h, devAlloc(&h->d_pixel_gidx, pixels, 0));
+  KB_CUDA(h, devAlloc(&h->d_pixel_seed, pixels, 0));
+  h->stg_pixels = pixels;
+  return KB_OK;
+}
+
+// Resolves one image pointer of a frame to a device pointer (copying host images to staging).
+template <typename T>
+int stage(kb_handle* h, const T* src, T* staging, size_t count, int memory, const T** out) {
+  *out = nullptr;
+  if (!src) return KB_OK;
+  if (memory == KB_MEM_DEVICE) { *out = src; return KB_OK; }
+  KB_CUDA(h, cudaMemcpyAsync(staging, src, count * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+  *out = staging;
+  return KB_OK;
+}
+
+void poseToFloat(const double T[16], float R[9], float t[3], float Rw[9], float tw[3]) {
+  // sensor_T_world = world_T_sensor^-1 (rigid), formed in double and rounded once to float.
+  double Rd[9], td[3];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) Rd[r * 3 + c] = T[c * 4 + r];
+  for (int r = 0; r < 3; ++r) td[r] = -(Rd[r * 3 + 0] * T[3] + Rd[r * 3 + 1] * T[7] + Rd[r * 3 + 2] * T[11]);
+  for (int i = 0; i < 9; ++i) R[i] = static_cast<float>(Rd[i]);
+  for (int i = 0; i < 3; ++i) t[i] = static_cast<float>(td[i]);
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) Rw[r * 3 + c] = static_cast<float>(T[r * 4 + c]);
+    tw[r] = static_cast<float>(T[r * 4 + 3]);
+  }
+}
+
+// Frame index of a stamp (appends new stamps; stamps must not decrease while tracking is on).
+int frameIndex(kb_handle* h, uint64_t stamp, uint32_t* idx) {
+  if (stamp == 0) return fail(h, KB_ERR_INVALID, "stamp_ns must be > 0");
+  if (stamp == h->stamps.back()) { *idx = static_cast<uint32_t>(h->stamps.size() - 1); return KB_OK; }
+  if (stamp < h->stamps.back()) {
+    if (h->map.with_tracking) return fail(h, KB_ERR_STATE, "stamps must be non-decreasing when tracking is enabled");
+    *idx = static_cast<uint32_t>(h->stamps.size() - 1);
+    return KB_OK;
+  }
+  h->stamps.push_back(stamp);
+  *idx = static_cast<uint32_t>(h->stamps.size() - 1);
+  return KB_OK;
+}
+
+int readCounters(kb_handle* h) {
+  KB_CUDA(h, cudaMemcpyAsync(h->h_ctr, h->dm.counters, sizeof(int) * kNumCounters, cudaMemcpyDeviceToHost, h->stream));
+  KB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return KB_OK;
+}
+
+int slotHwm(kb_handle* h, int* n) {
+  // Upper bound on live slots without a sync: the pool capacity would do, but launching one CTA per
+  // potential slot is wasteful, so we read the high-water mark (4 B, one sync).
+  int st = readCounters(h);
+  if (st != KB_OK) return st;
+  *n = std::min(h->h_ctr[kCtrPoolHwm], h->dm.max_blocks);
+  return KB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int kb_abi_version(void) { return KB_ABI_VERSION; }
+
+const char* kb_last_error(const kb_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+int kb_block_owner(int32_t bx, int32_t by, int32_t bz, int nranks) {
+  return nranks <= 1 ? 0 : blockOwner(bx, by, bz, nranks);
+}
+
+int kb_create(const kb_map_config* map, const kb_integrator_config* integ, const kb_tracking_config* trk,
+              const kb_motion_config* mot, int device, kb_handle** out) {
+  if (!map || !integ || !out) return KB_ERR_INVALID;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
+    cudaGetLastError();
+    return KB_ERR_NO_DEVICE;  // the product path refuses to run without a GPU
+  }
+  if ((map->voxels_per_side != 8 && map->voxels_per_side != 16) || !(map->voxel_size > 0.f) ||
+      !(map->truncation_distance > 0.f) || map->max_blocks <= 0)
+    return KB_ERR_INVALID;
+  if (integ->semantic_mode == KB_SEMANTICS_MLE && (integ->num_labels < 2 || integ->num_labels > KB_MAX_LABELS))
+    return KB_ERR_INVALID;
+  if (trk && (trk->neighbor_connectivity != 6 && trk->neighbor_connectivity != 18 && trk->neighbor_connectivity != 26))
+    return KB_ERR_INVALID;
+  if (trk && (!(trk->temporal_buffer > 0.f) || !(trk->temporal_window > 0.f) || trk->tsdf_occupancy_threshold == 0.f))
+    return KB_ERR_INVALID;  // tracking_integrator.cpp:61-65
+  if (mot && (mot->neighbor_connectivity != 6 && mot->neighbor_connectivity != 18 && mot->neighbor_connectivity != 26))
+    return KB_ERR_INVALID;
+  if (mot && (mot->max_cluster_size < mot->min_cluster_size || !(mot->max_range > 0.f)))
+    return KB_ERR_INVALID;  // free_space_motion_detector.cpp:61-66
+
+  auto* h = new kb_handle();
+  h->map = *map;
+  h->integ = *integ;
+  if (trk) { h->trk = *trk; h->has_trk = true; }
+  if (mot) { h->mot = *mot; h->has_mot = true; }
+  h->device = device;
+  h->stamps.push_back(0);
+  h->block_size = map->voxel_size * static_cast<float>(map->voxels_per_side);
+  h->L = !map->with_semantics ? 0
+         : integ->semantic_mode == KB_SEMANTICS_MLE ? integ->num_labels
+         : integ->semantic_mode == KB_SEMANTICS_BINARY ? 2 : 0;
+  if (integ->semantic_mode == KB_SEMANTICS_MLE) {
+    // MLESemanticIntegrator constants (UP), formed in double, rounded once.
+    const double c = static_cast<double>(integ->label_confidence), N = static_cast<double>(integ->num_labels);
+    h->mle_diag = static_cast<float>(std::log(c));
+    h->mle_off = static_cast<float>(std::log((1.0 - c) / (N - 1.0)));
+    h->mle_init = static_cast<float>(std::log(1.0 / N));
+    for (int i = 0; i < KB_MAX_LABELS; ++i)
+      if (integ->label_blocked[i]) h->blocked_mask |= 1ull << i;
+  }
+
+  DeviceMap& m = h->dm;
+  m.vps = map->voxels_per_side;
+  m.V = m.vps * m.vps * m.vps;
+  m.max_blocks = map->max_blocks;
+  m.max_sem = h->L > 0 ? (map->max_semantic_blocks > 0 ? map->max_semantic_blocks : map->max_blocks) : 0;
+  m.Lp = h->L == 0 ? 0 : (integ->semantic_mode == KB_SEMANTICS_BINARY ? 2 : ((h->L + 3) / 4) * 4);
+  uint32_t cap = 1024;
+  while (cap < static_cast<uint32_t>(m.max_blocks) * 2u) cap <<= 1;
+  m.hash_mask = cap - 1;
+
+  int st = KB_OK;
+  auto run = [&]() -> int {
+    KB_CUDA(h, cudaSetDevice(device));
+    KB_CUDA(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    h->own_stream = true;
+    const size_t S = m.max_blocks, V = m.V;
+    KB_CUDA(h, devAlloc(&m.hash_keys, cap, 0xFF));
+    KB_CUDA(h, devAlloc(&m.hash_vals, cap, 0xFF));
+    KB_CUDA(h, devAlloc(&m.counters, kNumCounters, 0));
+    KB_CUDA(h, devAlloc(&m.free_list, S, 0));
+    KB_CUDA(h, devAlloc(&m.block_index, S, 0));
+    KB_CUDA(h, devAlloc(&m.block_flags, S, 0));
+    KB_CUDA(h, devAlloc(&m.block_sem, S, 0xFF));
+    KB_CUDA(h, devAlloc(&m.tsdf, S * V, 0));
+    if (map->with_tracking) {
+      KB_CUDA(h, devAlloc(&m.last_obs, S * V, 0));
+      KB_CUDA(h, devAlloc(&m.last_occ, S * V, 0));
+      KB_CUDA(h, devAlloc(&m.vflags, S * V, 0));
+    }
+    if (h->L > 0) {
+      const size_t Q = m.max_sem;
+      KB_CUDA(h, devAlloc(&m.sem_free_list, Q, 0));
+      KB_CUDA(h, devAlloc(&m.sem_label, Q * V, 0xFF));
+      KB_CUDA(h, devAlloc(&m.sem_lik, Q * V * m.Lp, 0));
+    }
+    KB_CUDA(h, cudaMallocHost(reinterpret_cast<void**>(&h->h_ctr), sizeof(int) * kNumCounters));
+    std::memset(h->h_ctr, 0, sizeof(int) * kNumCounters);
+    h->max_removed = m.max_blocks;
+    KB_CUDA(h, devAlloc(&h->d_removed, static_cast<size_t>(h->max_removed), 0));
+    KB_CUDA(h, cudaDeviceSynchronize());
+    return KB_OK;
+  };
+  st = run();
+  if (st != KB_OK) {
+    std::fprintf(stderr, "kb_create: %s\n", h->err.c_str());
+    kb_destroy(h);
+    return st;
+  }
+  *out = h;
+  return KB_OK;
+}
+
+int kb_destroy(kb_handle* h) {
+  if (!h) return KB_OK;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  DeviceMap& m = h->dm;
+  cudaFree(m.hash_keys); cudaFree(m.hash_vals); cudaFree(m.counters); cudaFree(m.free_list);
+  cudaFree(m.sem_free_list); cudaFree(m.block_index); cudaFree(m.block_flags); cudaFree(m.block_sem);
+  cudaFree(m.tsdf); cudaFree(m.last_obs); cudaFree(m.last_occ); cudaFree(m.vflags);
+  cudaFree(m.sem_label); cudaFree(m.sem_lik);
+  cudaFree(h->stg_depth); cudaFree(h->stg_label); cudaFree(h->stg_mask); cudaFree(h->stg_object);
+  cudaFree(h->stg_vertex); cudaFree(h->d_pixel_gidx); cudaFree(h->d_pixel_seed); cudaFree(h->d_removed);
+  if (h->h_ctr) cudaFreeHost(h->h_ctr);
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return KB_OK;
+}
+
+int kb_set_stream(kb_handle* h, void* cuda_stream) {
+  if (!h) return KB_ERR_INVALID;
+  KB_CUDA(h, cudaSetDevice(h->device));
+  KB_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (h->own_stream) cudaStreamDestroy(h->stream);
+  h->stream = static_cast<cudaStream_t>(cuda_stream);
+  h->own_stream = false;
+  return KB_OK;
+}
+
+int kb_synchronize(kb_handle* h) {
+  if (!h) return KB_ERR_INVALID;
+  KB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return KB_OK;
+}
+
+int kb_set_camera(kb_handle* h, const kb_camera* cam) {
+  if (!h || !cam || cam->width <= 1 || cam->height <= 1 || !(cam->fx > 0.f) || !(cam->fy > 0.f))
+    return fail(h, KB_ERR_INVALID, "invalid camera");
+  h->cam = *cam;
+  h->has_cam = true;
+  KB_CUDA(h, cudaSetDevice(h->device));
+  return ensureStaging(h, static_cast<size_t>(cam->width) * cam->height);
+}
+
+int kb_set_shard(kb_handle* h, int rank, int nranks) {
+  if (!h || nranks < 1 || rank < 0 || rank >= nranks) return fail(h, KB_ERR_INVALID, "invalid shard");
+  h->rank = rank;
+  h->nranks = nranks;
+  return KB_OK;
+}
+
+int kb_integrate_frame(kb_handle* h, const kb_frame* f, int allocate_blocks, kb_frame_stats* stats) {
+  if (!h || !f || !f->depth) return fail(h, KB_ERR_INVALID, "null frame");
+  if (!h->has_cam) return fail(h, KB_ERR_STATE, "kb_set_camera must be called first");
+  KB_CUDA(h, cudaSetDevice(h->device));
+  uint32_t fidx = 0;
+  int st = frameIndex(h, f->stamp_ns, &fidx);
+  if (st != KB_OK) return st;
+  if (stats && h->ctr_dirty) {
+    if ((st = readCounters(h)) != KB_OK) return st;
+    std::memcpy(h->prev_ctr, h->h_ctr, sizeof(h->prev_ctr));
+    h->ctr_dirty = false;
+  }
+
+  FrameParams p{};
+  poseToFloat(f->world_T_sensor, p.R, p.t, p.Rw, p.tw);
+  const kb_camera& c = h->cam;
+  p.W = c.width; p.H = c.height;
+  p.fx = c.fx; p.fy = c.fy; p.cx = c.cx; p.cy = c.cy;
+  p.min_range = c.min_range; p.max_range = c.max_range;
+  {
+    // Inward unit normals of the four frustum side planes (same float expressions as the oracle).
+    const float xl = (0.f - c.cx) / c.fx, xr = (static_cast<float>(c.width - 1) - c.cx) / c.fx;
+    const float yt = (0.f - c.cy) / c.fy, yb = (static_cast<float>(c.height - 1) - c.cy) / c.fy;
+    const float il = 1.f / std::sqrt(1.f + xl * xl), ir = 1.f / std::sqrt(1.f + xr * xr);
+    const float it = 1.f / std::sqrt(1.f + yt * yt), ib = 1.f / std::sqrt(1.f + yb * yb);
+    p.pl[0][0] = il;  p.pl[0][1] = -xl * il;
+    p.pl[1][0] = -ir; p.pl[1][1] = xr * ir;
+    p.pl[2][0] = it;  p.pl[2][1] = -yt * it;
+    p.pl[3][0] = -ib; p.pl[3][1] = yb * ib;
+  }
+  p.voxel_size = h->map.voxel_size;
+  p.block_size = h->block_size;
+  p.trunc = h->map.truncation_distance;
+  p.voxel_size_inv = 1.f / h->map.voxel_size;
+  p.block_size_inv = 1.f / h->block_size;
+  p.infl = h->block_size * 0.8660254f;
+  p.use_dropoff = h->integ.use_weight_dropoff;
+  p.dropoff_eps = h->integ.weight_dropoff_epsilon > 0.f ? h->integ.weight_dropoff_epsilon
+                                                       : h->integ.weight_dropoff_epsilon * -h->map.voxel_size;
+  p.constant_weight = h->integ.use_constant_weight;
+  p.max_weight = h->integ.max_weight;
+  p.interp = h->integ.interpolation_method;
+  p.adaptive_thr = h->integ.adaptive_max_depth_difference;
+  p.sem_mode = h->L > 0 ? h->integ.semantic_mode : KB_SEMANTICS_NONE;
+  p.L = h->L;
+  p.mle_diag = h->mle_diag; p.mle_off = h->mle_off; p.mle_init = h->mle_init;
+  p.blocked_mask = h->blocked_mask;
+  p.target_id = f->object_target_id;
+  p.frame_idx = fidx;
+  p.allocate = allocate_blocks ? 1 : 0;
+  p.rank = h->rank; p.nranks = h->nranks;
+  p.with_tracking = h->map.with_tracking;
+
+  const size_t px = static_cast<size_t>(c.width) * c.height;
+  if ((st = stage(h, f->depth, h->stg_depth, px, f->memory, &p.depth)) != KB_OK) return st;
+  if ((st = stage(h, f->label, h->stg_label, px, f->memory, &p.label)) != KB_OK) return st;
+  if ((st = stage(h, f->mask, h->stg_mask, px, f->memory, &p.mask)) != KB_OK) return st;
+  if ((st = stage(h, f->object_image, h->stg_object, px, f->memory, &p.object_image)) != KB_OK) return st;
+
+  int grid = 0;
+  if (allocate_blocks) {
+    const float reach = c.max_range + p.infl;
+    for (int a = 0; a < 3; ++a) {
+      p.lo[a] = static_cast<int>(std::floor((p.tw[a] - reach) * p.block_size_inv));
+      const int hi = static_cast<int>(std::floor((p.tw[a] + reach) * p.block_size_inv));
+      p.dims[a] = hi - p.lo[a] + 1;
+    }
+    grid = p.dims[0] * p.dims[1] * p.dims[2];
+  } else {
+    if ((st = slotHwm(h, &grid)) != KB_OK) return st;
+  }
+  launchIntegrate(h->dm, p, grid, h->stream);
+  KB_CUDA(h, cudaGetLastError());
+  h->ctr_dirty = true;
+
+  if (stats) {
+    if ((st = readCounters(h)) != KB_OK) return st;
+    const int* c1 = h->h_ctr;
+    const int* c0 = h->prev_ctr;
+    stats->blocks_in_frustum = c1[kCtrFrustum] - c0[kCtrFrustum];
+    stats->blocks_allocated = c1[kCtrAllocated] - c0[kCtrAllocated];
+    stats->blocks_updated = c1[kCtrBlocksUpdated] - c0[kCtrBlocksUpdated];
+    stats->voxels_updated = c1[kCtrVoxelsUpdated] - c0[kCtrVoxelsUpdated];
+    stats->voxels_in_band = c1[kCtrVoxelsBand] - c0[kCtrVoxelsBand];
+    stats->voxels_semantic = c1[kCtrVoxelsSemantic] - c0[kCtrVoxelsSemantic];
+    stats->total_blocks = c1[kCtrLiveBlocks];
+    stats->capacity_exceeded = c1[kCtrCapacityExceeded];
+    std::memcpy(h->prev_ctr, h->h_ctr, sizeof(h->prev_ctr));
+    h->ctr_dirty = false;
+    if (c1[kCtrCapacityExceeded]) return fail(h, KB_ERR_CAPACITY, "block / semantic pool exhausted");
+  }
+  return KB_OK;
+}
+
+int kb_update_tracking(kb_handle* h, uint64_t stamp_ns) {
+  if (!h) return KB_ERR_INVALID;
+  if (!h->has_trk || !h->map.with_tracking) return fail(h, KB_ERR_STATE, "tracking not configured");
+  KB_CUDA(h, cudaSetDevice(h->device));
+  uint32_t fidx = 0;
+  int st = frameIndex(h, stamp_ns, &fidx);
+  if (st != KB_OK) return st;
+  TrackingParams p{};
+  p.frame_idx = fidx;
+  p.occupancy_thr = h->trk.tsdf_occupancy_threshold < 0 ? h->trk.tsdf_occupancy_threshold * -h->map.voxel_size
+                                                        : h->trk.tsdf_occupancy_threshold;
+  p.connectivity = h->trk.neighbor_connectivity;
+  // The reference compares stamps in double seconds (tracking_integrator.cpp:238,250). Stamps are
+  // strictly increasing in the frame-index table, so each predicate is a threshold on the index.
+  const double now = toSeconds(stamp_ns);
+  const double t_active = now - h->trk.temporal_window;
+  const double t_free = now - h->trk.temporal_buffer;
+  // First frame index (>= 1) whose stamp satisfies toSeconds(stamp) >= threshold.
+  auto firstAtLeast = [&](double thr) {
+    auto it = std::partition_point(h->stamps.begin() + 1, h->stamps.end(),
+                                   [&](uint64_t s) { return toSeconds(s) < thr; });
+    return static_cast<uint32_t>(it - h->stamps.begin());
+  };
+  const uint32_t a = firstAtLeast(t_active), g = firstAtLeast(t_free);
+  p.active_min_idx = a;   // last_obs >= a  <=>  toSeconds(last_obs) >= now - window
+  p.zero_active = 0.0 >= t_active;
+  p.free_max_idx = g;     // last_occ < g   <=>  toSeconds(last_occ) < now - buffer
+  p.zero_free = 0.0 < t_free;
+  int nslots = 0;
+  if ((st = slotHwm(h, &nslots)) != KB_OK) return st;
+  launchTracking(h->dm, p, nslots, h->stream);
+  launchEverFree(h->dm, p, nslots, h->stream);
+  KB_CUDA(h, cudaGetLastError());
+  return KB_OK;
+}
+
+int kb_reset_inactive(kb_handle* h, int32_t* removed_xyz, int32_t max_removed, int32_t* n_removed) {
+  if (!h) return KB_ERR_INVALID;
+  if (!h->map.with_tracking) { if (n_removed) *n_removed = 0; return KB_OK; }  // no tracking blocks
+  KB_CUDA(h, cudaSetDevice(h->device));
+  int st, nslots = 0;
+  if ((st = slotHwm(h, &nslots)) != KB_OK) return st;
+  const int before = h->h_ctr[kCtrRemoved];
+  launchResetInactive(h->dm, nslots, h->d_removed, h->max_removed, h->stream);
+  KB_CUDA(h, cudaGetLastError());
+  if ((st = readCounters(h)) != KB_OK) return st;
+  const int n = h->h_ctr[kCtrRemoved] - before;
+  // the device appends at absolute positions [before, before+n) modulo nothing: we reset the counter
+  std::vector<int3> host(static_cast<size_t>(std::max(n, 0)));
+  if (n > 0) {
+    // removed[] was indexed by the cumulative counter; copy the window (bounded by max_removed).
+    const int lo = std::min(before, h->max_removed), hi = std::min(before + n, h->max_removed);
+    if (hi > lo) KB_CUDA(h, cudaMemcpy(host.data(), h->d_removed + lo, sizeof(int3) * (hi - lo), cudaMemcpyDeviceToHost));
+    host.resize(hi - lo);
+  }
+  // keep the cumulative counter from walking off the buffer
+  KB_CUDA(h, cudaMemsetAsync(h->dm.counters + kCtrRemoved, 0, sizeof(int), h->stream));
+  h->h_ctr[kCtrRemoved] = 0;
+  std::sort(host.begin(), host.end(), [](const int3& a, const int3& b) {
+    return a.x != b.x ? a.x < b.x : (a.y != b.y ? a.y < b.y : a.z < b.z);
+  });
+  if (n_removed) *n_removed = static_cast<int32_t>(host.size());
+  if (removed_xyz)
+    for (int i = 0; i < std::min<int>(max_removed, host.size()); ++i) {
+      removed_xyz[i * 3 + 0] = host[i].x; removed_xyz[i * 3 + 1] = host[i].y; removed_xyz[i * 3 + 2] = host[i].z;
+    }
+  return KB_OK;
+}
+
+int kb_mark_all_inactive(kb_handle* h) {
+  if (!h) return KB_ERR_INVALID;
+  KB_CUDA(h, cudaSetDevice(h->device));
+  int st, n = 0;
+  if ((st = slotHwm(h, &n)) != KB_OK) return st;
+  launchMarkAllInactive(h->dm, n, h->stream);
+  KB_CUDA(h, cudaGetLastError());
+  return KB_OK;
+}
+
+int kb_clear_updated(kb_handle* h) {
+  if (!h) return KB_ERR_INVALID;
+  KB_CUDA(h, cudaSetDevice(h->device));
+  int st, n = 0;
+  if ((st = slotHwm(h, &n)) != KB_OK) return st;
+  launchClearUpdated(h->dm, n, h->stream);
+  KB_CUDA(h, cudaGetLastError());
+  return KB_OK;
+}
+
+int kb_allocate_box(kb_handle* h, const int32_t mn[3], const int32_t mx[3]) {
+  if (!h || !mn || !mx) return KB_ERR_INVALID;
+  KB_CUDA(h, cudaSetDevice(h->device));
+  const int3 lo = make_int3(mn[0], mn[1], mn[2]);
+  const int3 dims = make_int3(mx[0] - mn[0] + 1, mx[1] - mn[1] + 1, mx[2] - mn[2] + 1);
+  if (dims.x <= 0 || dims.y <= 0 || dims.z <= 0) return KB_OK;
+  launchAllocateBox(h->dm, lo, dims, h->rank, h->nranks, h->stream);
+  KB_CUDA(h, cudaGetLastError());
+  int st = readCounters(h);
+  if (st != KB_OK) return st;
+  if (h->h_ctr[kCtrCapacityExceeded]) return fail(h, KB_ERR_CAPACITY, "block pool exhausted");
+  return KB_OK;
+}
+
+int kb_scan_object_confidence(kb_handle* h, float min_confidence, int32_t min_observations, int32_t* n_erased) {
+  if (!h) return KB_ERR_INVALID;
+  if (h->L != 2 || h->integ.semantic_mode != KB_SEMANTICS_BINARY)
+    return fail(h, KB_ERR_STATE, "kb_scan_object_confidence needs binary semantics");
+  KB_CUDA(h, cudaSetDevice(h->device));
+  int st, n = 0;
+  if ((st = slotHwm(h, &n)) != KB_OK) return st;
+  const int before = h->h_ctr[kCtrErased];
+  launchScanConfidence(h->dm, min_confidence, static_cast<float>(min_observations), h->map.truncation_distance, n, h->stream);
+  KB_CUDA(h, cudaGetLastError());
+  if ((st = readCounters(h)) != KB_OK) return st;
+  if (n_erased) *n_erased = h->h_ctr[kCtrErased] - before;
+  return KB_OK;
+}
+
+int kb_detect_motion(kb_handle* h, const kb_frame* f, int32_t* dynamic_image_out, int32_t* n_seeds, int32_t* n_clusters) {
+  if (!h || !f || !f->depth || !dynamic_image_out) return fail(h, KB_ERR_INVALID, "null argument");
+  if (!h->has_mot || !h->map.with_tracking) return fail(h, KB_ERR_STATE, "motion detector not configured");
+  if (!h->has_cam) return fail(h, KB_ERR_STATE, "kb_set_camera must be called first");
+  KB_CUDA(h, cudaSetDevice(h->device));
+  const kb_camera& c = h->cam;
+  const size_t px = static_cast<size_t>(c.width) * c.height;
+  MotionParams p{};
+  float R[9], t[3];
+  poseToFloat(f->world_T_sensor, R, t, p.Rw, p.tw);
+  p.W = c.width; p.H = c.height; p.fx = c.fx; p.fy = c.fy; p.cx = c.cx; p.cy = c.cy;
+  p.max_range = h->mot.max_range;
+  p.min_z_world = p.tw[2] + h->mot.min_z_coordinate;  // free_space_motion_detector.cpp:80
+  p.block_size = h->block_size;
+  p.block_size_inv = 1.f / h->block_size;
+  p.voxel_size_inv = 1.f / h->map.voxel_size;
+  int st;
+  if ((st = stage(h, f->depth, h->stg_depth, px, f->memory, &p.depth)) != KB_OK) return st;
+  if ((st = stage(h, f->vertex_world, h->stg_vertex, px * 3, f->memory, &p.vertex)) != KB_OK) return st;
+  p.pixel_gidx = h->d_pixel_gidx;
+  p.pixel_seed = h->d_pixel_seed;
+  if ((st = readCounters(h)) != KB_OK) return st;
+  const int seeds_before = h->h_ctr[kCtrSeeds];
+  launchMotionLookup(h->dm, p, h->stream);
+  KB_CUDA(h, cudaGetLastError());
+  if ((st = readCounters(h)) != KB_OK) return st;
+  const int seed_pixels = h->h_ctr[kCtrSeeds] - seeds_before;
+
+  std::memset(dynamic_image_out, 0, sizeof(int32_t) * px);
+  h->motion.clusters.clear();
+  h->motion.n_seeds = 0;
+  if (seed_pixels > 0) {
+    // Seeds exist: bring the per-pixel voxel keys back and cluster on the host (M2-M4 are serial,
+    // data-dependent graph walks over a handful of voxels; SURVEY §8f lists a device version as next).
+    h->h_pixel_gidx.resize(px * 3);
+    h->h_pixel_seed.resize(px);
+    KB_CUDA(h, cudaMemcpyAsync(h->h_pixel_gidx.data(), h->d_pixel_gidx, sizeof(int3) * px, cudaMemcpyDeviceToHost, h->stream));
+    KB_CUDA(h, cudaMemcpyAsync(h->h_pixel_seed.data(), h->d_pixel_seed, px, cudaMemcpyDeviceToHost, h->stream));
+    const float* depth_host = f->depth;
+    const float* vertex_host = f->vertex_world;
+    if (f->memory == KB_MEM_DEVICE) {
+      h->h_depth.resize(px);
+      KB_CUDA(h, cudaMemcpyAsync(h->h_depth.data(), f->depth, sizeof(float) * px, cudaMemcpyDeviceToHost, h->stream));
+      depth_host = h->h_depth.data();
+      vertex_host = nullptr;  // bounding boxes are recomputed from depth + pose (identical arithmetic)
+    }
+    KB_CUDA(h, cudaStreamSynchronize(h->stream));
+    MotionHostParams mp{};
+    mp.W = c.width; mp.H = c.height; mp.fx = c.fx; mp.fy = c.fy; mp.cx = c.cx; mp.cy = c.cy;
+    std::memcpy(mp.Rw, p.Rw, sizeof(mp.Rw));
+    std::memcpy(mp.tw, p.tw, sizeof(mp.tw));
+    mp.connectivity = h->mot.neighbor_connectivity;
+    mp.min_cluster_size = h->mot.min_cluster_size;
+    mp.max_cluster_size = h->mot.max_cluster_size;
+    mp.min_separation_distance = h->mot.min_separation_distance;
+    clusterMotion(mp, h->h_pixel_gidx.data(), h->h_pixel_seed.data(), depth_host, vertex_host,
+                  dynamic_image_out, &h->motion);
+  }
+  if (n_seeds) *n_seeds = h->motion.n_seeds;
+  if (n_clusters) *n_clusters = static_cast<int32_t>(h->motion.clusters.size());
+  return KB_OK;
+}
+
+int kb_get_motion_clusters(kb_handle* h, int32_t* counts, int32_t* pixels_uv, int64_t* voxels_xyz,
+                           float* bbox_min_max, int32_t* total_pixels, int32_t* total_voxels) {
+  if (!h) return KB_ERR_INVALID;
+  size_t tp = 0, tv = 0;
+  const auto& cl = h->motion.clusters;
+  for (size_t c = 0; c < cl.size(); ++c) {
+    if (counts) { counts[c * 2] = static_cast<int32_t>(cl[c].pixels.size() / 2); counts[c * 2 + 1] = static_cast<int32_t>(cl[c].voxels.size() / 3); }
+    if (pixels_uv) std::memcpy(pixels_uv + tp * 2, cl[c].pixels.data(), cl[c].pixels.size() * sizeof(int32_t));
+    if (voxels_xyz) std::memcpy(voxels_xyz + tv * 3, cl[c].voxels.data(), cl[c].voxels.size() * sizeof(int64_t));
+    if (bbox_min_max) std::memcpy(bbox_min_max + c * 6, cl[c].bbox, sizeof(float) * 6);
+    tp += cl[c].pixels.size() / 2;
+    tv += cl[c].voxels.size() / 3;
+  }
+  if (total_pixels) *total_pixels = static_cast<int32_t>(tp);
+  if (total_voxels) *total_voxels = static_cast<int32_t>(tv);
+  return KB_OK;
+}
+
+// ---- export -------------------------------------------------------------------------------------------
+
+static int collectSlots(kb_handle* h, int which, std::vector<int>* slots, std::vector<int3>* index,
+                        std::vector<uint32_t>* flags) {
+  int st, n = 0;
+  if ((st = slotHwm(h, &n)) != KB_OK) return st;
+  std::vector<int3> bi(static_cast<size_t>(n));
+  std::vector<uint32_t> bf(static_cast<size_t>(n));
+  if (n > 0) {
+    KB_CUDA(h, cudaMemcpy(bi.data(), h->dm.block_index, sizeof(int3) * n, cudaMemcpyDeviceToHost));
+    KB_CUDA(h, cudaMemcpy(bf.data(), h->dm.block_flags, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost));
+  }
+  std::vector<int> order;
+  for (int s = 0; s < n; ++s) {
+    if (!(bf[s] & kFlagAllocated)) continue;
+    if (which == KB_EXPORT_UPDATED && !(bf[s] & KB_FLAG_UPDATED)) continue;
+    order.push_back(s);
+  }
+  std::sort(order.begin(), order.end(), [&](int a, int b) {
+    const int3 &p = bi[a], &q = bi[b];
+    return p.x != q.x ? p.x < q.x : (p.y != q.y ? p.y < q.y : p.z < q.z);
+  });
+  slots->clear(); index->clear(); flags->clear();
+  for (int s : order) { slots->push_back(s); index->push_back(bi[s]); flags->push_back(bf[s]); }
+  return KB_OK;
+}
+
+int kb_num_blocks(kb_handle* h, int which, int32_t* n) {
+  if (!h || !n) return KB_ERR_INVALID;
+  KB_CUDA(h, cudaSetDevice(h->device));
+  std::vector<int> slots; std::vector<int3> index; std::vector<uint32_t> flags;
+  int st = collectSlots(h, which, &slots, &index, &flags);
+  if (st != KB_OK) return st;
+  *n = static_cast<int32_t>(slots.size());
+  return KB_OK;
+}
+
+int kb_export_blocks(kb_handle* h, int which, int32_t max_blocks, kb_block_export* out, int32_t* n_written) {
+  if (!h || !out) return KB_ERR_INVALID;
+  KB_CUDA(h, cudaSetDevice(h->device));
+  std::vector<int> slots; std::vector<int3> index; std::vector<uint32_t> flags;
+  int st = collectSlots(h, which, &slots, &index, &flags);
+  if (st != KB_OK) return st;
+  const int n = std::min<int>(max_blocks, slots.size());
+  const size_t V = h->dm.V, L = h->L;
+  for (int i = 0; i < n; ++i) {
+    if (out->block_index) { out->block_index[i * 3] = index[i].x; out->block_index[i * 3 + 1] = index[i].y; out->block_index[i * 3 + 2] = index[i].z; }
+    if (out->block_flags) out->block_flags[i] = static_cast<uint8_t>(flags[i] & kPublicFlagMask);
+  }
+  if (out->color && n) std::memset(out->color, 0, static_cast<size_t>(n) * V * 3);
+  // Gather in chunks through dense device buffers, then copy out.
+  const int chunk = 1024;
+  int* d_slots = nullptr;
+  unsigned long long* d_stamps = nullptr;
+  char* d_buf = nullptr;
+  const size_t per_block = V * (4 + 4) + V * (8 + 8 + 3) + V * (4 + 1) + V * L * 4;
+  auto cleanup = [&]() { cudaFree(d_slots); cudaFree(d_stamps); cudaFree(d_buf); };
+  auto body = [&]() -> int {
+    if (n == 0) return KB_OK;
+    KB_CUDA(h, cudaMalloc(&d_slots, sizeof(int) * n));
+    KB_CUDA(h, cudaMemcpy(d_slots, slots.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
+    KB_CUDA(h, cudaMalloc(&d_stamps, sizeof(uint64_t) * h->stamps.size()));
+    KB_CUDA(h, cudaMemcpy(d_stamps, h->stamps.data(), sizeof(uint64_t) * h->stamps.size(), cudaMemcpyHostToDevice));
+    KB_CUDA(h, cudaMalloc(&d_buf, per_block * std::min(chunk, n)));
+    for (int b0 = 0; b0 < n; b0 += chunk) {
+      const int nb = std::min(chunk, n - b0);
+      char* q = d_buf;
+      float* d_dist = reinterpret_cast<float*>(q); q += nb * V * 4;
+      float* d_w = reinterpret_cast<float*>(q); q += nb * V * 4;
+      unsigned long long* d_lo = reinterpret_cast<unsigned long long*>(q); q += nb * V * 8;
+      unsigned long long* d_lc = reinterpret_cast<unsigned long long*>(q); q += nb * V * 8;
+      uint32_t* d_lab = reinterpret_cast<uint32_t*>(q); q += nb * V * 4;
+      float* d_lik = reinterpret_cast<float*>(q); q += nb * V * L * 4;
+      uint8_t* d_ef = reinterpret_cast<uint8_t*>(q); q += nb * V;
+      uint8_t* d_ac = reinterpret_cast<uint8_t*>(q); q += nb * V;
+      uint8_t* d_tr = reinterpret_cast<uint8_t*>(q); q += nb * V;
+      uint8_t* d_em = reinterpret_cast<uint8_t*>(q); q += nb * V;
+      const size_t off = static_cast<size_t>(b0) * V;
+      if (out->distance || out->weight) {
+        launchGatherTsdf(h->dm, d_slots + b0, nb, d_dist, d_w, h->stream);
+        if (out->distance) KB_CUDA(h, cudaMemcpyAsync(out->distance + off, d_dist, nb * V * 4, cudaMemcpyDeviceToHost, h->stream));
+        if (out->weight) KB_CUDA(h, cudaMemcpyAsync(out->weight + off, d_w, nb * V * 4, cudaMemcpyDeviceToHost, h->stream));
+      }
+      const bool want_trk = out->last_observed || out->last_occupied || out->ever_free || out->active || out->to_remove;
+      if (want_trk) {
+        if (h->map.with_tracking) {
+          launchGatherTracking(h->dm, d_slots + b0, nb, d_stamps, d_lo, d_lc, d_ef, d_ac, d_tr, h->stream);
+          if (out->last_observed) KB_CUDA(h, cudaMemcpyAsync(out->last_observed + off, d_lo, nb * V * 8, cudaMemcpyDeviceToHost, h->stream));
+          if (out->last_occupied) KB_CUDA(h, cudaMemcpyAsync(out->last_occupied + off, d_lc, nb * V * 8, cudaMemcpyDeviceToHost, h->stream));
+          if (out->ever_free) KB_CUDA(h, cudaMemcpyAsync(out->ever_free + off, d_ef, nb * V, cudaMemcpyDeviceToHost, h->stream));
+          if (out->active) KB_CUDA(h, cudaMemcpyAsync(out->active + off, d_ac, nb * V, cudaMemcpyDeviceToHost, h->stream));
+          if (out->to_remove) KB_CUDA(h, cudaMemcpyAsync(out->to_remove + off, d_tr, nb * V, cudaMemcpyDeviceToHost, h->stream));
+        } else {
+          if (out->last_observed) std::memset(out->last_observed + off, 0, nb * V * 8);
+          if (out->last_occupied) std::memset(out->last_occupied + off, 0, nb * V * 8);
+          if (out->ever_free) std::memset(out->ever_free + off, 0, nb * V);
+          if (out->active) std::memset(out->active + off, 0, nb * V);
+          if (out->to_remove) std::memset(out->to_remove + off, 0, nb * V);
+        }
+      }
+      if (out->semantic_label || out->semantic_empty || out->semantic_likelihoods) {
+        if (L > 0) {
+          launchGatherSemantic(h->dm, d_slots + b0, nb, static_cast<int>(L), d_lab, d_em,
+                               out->semantic_likelihoods ? d_lik : nullptr, h->stream);
+          if (out->semantic_label) KB_CUDA(h, cudaMemcpyAsync(out->semantic_label + off, d_lab, nb * V * 4, cudaMemcpyDeviceToHost, h->stream));
+          if (out->semantic_empty) KB_CUDA(h, cudaMemcpyAsync(out->semantic_empty + off, d_em, nb * V, cudaMemcpyDeviceToHost, h->stream));
+          if (out->semantic_likelihoods) KB_CUDA(h, cudaMemcpyAsync(out->semantic_likelihoods + off * L, d_lik, nb * V * L * 4, cudaMemcpyDeviceToHost, h->stream));
+        } else {
+          if (out->semantic_label) std::memset(out->semantic_label + off, 0, nb * V * 4);
+          if (out->semantic_empty) std::memset(out->semantic_empty + off, 1, nb * V);
+        }
+      }
+      KB_CUDA(h, cudaGetLastError());
+      KB_CUDA(h, cudaStreamSynchronize(h->stream));
+    }
+    return KB_OK;
+  };
+  st = body();
+  cleanup();
+  if (st != KB_OK) return st;
+  if (n_written) *n_written = n;
+  return KB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,162 @@
+// Device-side data layout and helpers of the B200 volumetric map (sm_100a).
+//
+// HBM layout (all arrays are structure-of-arrays over a fixed pool of block slots, V = vps^3):
+//   hash_keys[H] u64, hash_vals[H] i32      open-addressed block hash (linear probing, tombstones)
+//   block_index[S] int3, block_flags[S] u32, block_sem[S] i32 (semantic slot or -1)
+//   tsdf[S][V] float2 {distance, weight}    one 8 B RMW per integrated voxel, 256 B per warp
+//   last_obs[S][V] u32, last_occ[S][V] u32  frame *indices* (1-based, 0 = never); the host keeps the
+//                                            index -> u64 stamp table, halving tracking traffic
+//   vflags[S][V] u8                         bit0 ever_free, bit1 active, bit2 to_remove
+//   sem_label[Q][V] u16 (0xFFFF = empty), sem_lik[Q][V][Lp] f32   lazily assigned semantic slots
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace kb {
+
+constexpr unsigned long long kEmptyKey = ~0ull;
+constexpr unsigned long long kTombKey = ~0ull - 1ull;
+constexpr uint32_t kFlagAllocated = 1u << 8;      // slot is live
+constexpr uint32_t kFlagEverFreePending = 1u << 9;  // tracking_updated latched by K2 for K3
+constexpr uint32_t kPublicFlagMask = 0x1Fu;
+constexpr uint16_t kSemEmpty = 0xFFFFu;
+constexpr uint8_t kVoxEverFree = 1, kVoxActive = 2, kVoxToRemove = 4;
+
+struct DeviceMap {
+  unsigned long long* hash_keys;
+  int* hash_vals;
+  uint32_t hash_mask;
+  int max_blocks, max_sem;
+  int vps, V, Lp;  // Lp = padded likelihood stride (multiple of 4 floats)
+  int* counters;   // see Counter enum
+  int* free_list;      // recycled block slots (stack)
+  int* sem_free_list;  // recycled semantic slots
+  int3* block_index;
+  uint32_t* block_flags;
+  int* block_sem;
+  float2* tsdf;
+  uint32_t* last_obs;
+  uint32_t* last_occ;
+  uint8_t* vflags;
+  uint16_t* sem_label;
+  float* sem_lik;
+};
+
+// Cumulative device counters (never reset on the hot path; the host reports differences).
+enum Counter {
+  kCtrPoolHwm = 0,     // high-water mark of block slots
+  kCtrFreeCount = 1,   // entries in free_list
+  kCtrSemHwm = 2,
+  kCtrSemFreeCount = 3,
+  kCtrLiveBlocks = 4,
+  kCtrCapacityExceeded = 5,
+  kCtrFrustum = 6,
+  kCtrAllocated = 7,
+  kCtrBlocksUpdated = 8,
+  kCtrVoxelsUpdated = 9,
+  kCtrVoxelsBand = 10,
+  kCtrVoxelsSemantic = 11,
+  kCtrSeeds = 12,
+  kCtrRemoved = 13,
+  kCtrErased = 14,
+  kNumCounters = 16
+};
+
+__host__ __device__ inline unsigned long long packKey(int x, int y, int z) {
+  const unsigned long long o = 1ull << 20, m = (1ull << 21) - 1ull;
+  return ((static_cast<unsigned long long>(x + static_cast<long long>(o)) & m)) |
+         ((static_cast<unsigned long long>(y + static_cast<long long>(o)) & m) << 21) |
+         ((static_cast<unsigned long long>(z + static_cast<long long>(o)) & m) << 42);
+}
+
+__host__ __device__ inline unsigned long long mix64(unsigned long long k) {
+  k ^= k >> 33;
+  k *= 0xff51afd7ed558ccdull;
+  k ^= k >> 33;
+  k *= 0xc4ceb9fe1a85ec53ull;
+  k ^= k >> 33;
+  return k;
+}
+
+// Shard owner of a block: upper hash bits, so it is independent of the table slot (lower bits).
+__host__ __device__ inline int blockOwner(int x, int y, int z, int nranks) {
+  return static_cast<int>((mix64(packKey(x, y, z)) >> 40) % static_cast<unsigned long long>(nranks));
+}
+
+#ifdef __CUDACC__
+__device__ inline int hashLookup(const DeviceMap& m, int x, int y, int z) {
+  const unsigned long long key = packKey(x, y, z);
+  uint32_t h = static_cast<uint32_t>(mix64(key)) & m.hash_mask;
+  for (uint32_t probe = 0; probe <= m.hash_mask; ++probe) {
+    const unsigned long long k = m.hash_keys[h];
+    if (k == key) return m.hash_vals[h];
+    if (k == kEmptyKey) return -1;
+    h = (h + 1) & m.hash_mask;
+  }
+  return -1;
+}
+
+// Pops a recycled slot or bumps the high-water mark. Returns -1 when the pool is exhausted.
+__device__ inline int allocSlot(int* counters, int ctr_hwm, int ctr_free, const int* free_list, int cap) {
+  int nfree = atomicSub(&counters[ctr_free], 1);
+  if (nfree > 0) return free_list[nfree - 1];
+  atomicAdd(&counters[ctr_free], 1);
+  const int s = atomicAdd(&counters[ctr_hwm], 1);
+  if (s >= cap) {
+    atomicSub(&counters[ctr_hwm], 1);
+    atomicExch(&counters[kCtrCapacityExceeded], 1);
+    return -1;
+  }
+  return s;
+}
+
+// Finds or inserts a block. At most one thread per key calls this in any launch. *created = 1 if new.
+__device__ inline int hashFindOrInsert(const DeviceMap& m, int x, int y, int z, int* created) {
+  const unsigned long long key = packKey(x, y, z);
+  uint32_t h = static_cast<uint32_t>(mix64(key)) & m.hash_mask;
+  *created = 0;
+  // Pass 1: is the key present? remember the first tombstone.
+  int64_t tomb = -1;
+  uint32_t hh = h;
+  for (uint32_t probe = 0; probe <= m.hash_mask; ++probe) {
+    const unsigned long long k = m.hash_keys[hh];
+    if (k == key) return m.hash_vals[hh];
+    if (k == kEmptyKey) break;
+    if (k == kTombKey && tomb < 0) tomb = hh;
+    hh = (hh + 1) & m.hash_mask;
+  }
+  const int slot = allocSlot(m.counters, kCtrPoolHwm, kCtrFreeCount, m.free_list, m.max_blocks);
+  if (slot < 0) return -1;
+  // Pass 2: claim the tombstone or the first empty entry (other keys may race for the same entry).
+  if (tomb >= 0 && atomicCAS(&m.hash_keys[tomb], kTombKey, key) == kTombKey) {
+    m.hash_vals[tomb] = slot;
+  } else {
+    hh = h;
+    bool done = false;
+    for (uint32_t probe = 0; probe <= m.hash_mask && !done; ++probe) {
+      unsigned long long k = m.hash_keys[hh];
+      if (k == kEmptyKey || k == kTombKey) {
+        if (atomicCAS(&m.hash_keys[hh], k, key) == k) {
+          m.hash_vals[hh] = slot;
+          done = true;
+          break;
+        }
+      }
+      hh = (hh + 1) & m.hash_mask;
+    }
+    if (!done) {
+      atomicExch(&m.counters[kCtrCapacityExceeded], 1);
+      return -1;
+    }
+  }
+  m.block_index[slot] = make_int3(x, y, z);
+  m.block_flags[slot] = kFlagAllocated;
+  m.block_sem[slot] = -1;
+  atomicAdd(&m.counters[kCtrLiveBlocks], 1);
+  *created = 1;
+  return slot;
+}
+#endif
+
+}  // namespace kb

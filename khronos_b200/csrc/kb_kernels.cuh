@@ -1,0 +1,78 @@
+// Kernel parameter blocks and launch wrappers (implemented in kb_kernels.cu).
+#pragma once
+
+#include "kb_device.cuh"
+
+namespace kb {
+
+// Everything one frame's K0+K1 launch needs, passed by value (constant bank).
+struct FrameParams {
+  float R[9], t[3];    // sensor_T_world (float, rounded once from the double inverse)
+  float Rw[9], tw[3];  // world_T_sensor
+  int W, H;
+  float fx, fy, cx, cy, min_range, max_range;
+  float pl[4][2];      // frustum side planes (left,right,top,bottom): {lateral coeff, z coeff}
+  float voxel_size, block_size, trunc, voxel_size_inv, block_size_inv, infl;
+  int use_dropoff;
+  float dropoff_eps;
+  int constant_weight;
+  float max_weight;
+  int interp;
+  float adaptive_thr;
+  int sem_mode, L;
+  float mle_diag, mle_off, mle_init;
+  unsigned long long blocked_mask;
+  int target_id;
+  const float* depth;
+  const int* label;
+  const int* mask;
+  const int* object_image;
+  uint32_t frame_idx;
+  int lo[3], dims[3];  // candidate block AABB (allocate mode)
+  int allocate;        // 1: enumerate AABB + frustum test + insert; 0: all live slots
+  int rank, nranks;
+  int with_tracking;
+};
+
+struct TrackingParams {
+  uint32_t frame_idx;       // current frame index ("now")
+  float occupancy_thr;      // tsdf distance below which a voxel is occupied
+  uint32_t active_min_idx;  // last_obs >= this  <=> toSeconds(last_obs) >= toSeconds(now) - window
+  int zero_active;          // the same predicate for last_obs == 0 (stamp 0)
+  uint32_t free_max_idx;    // last_occ < this   <=> toSeconds(last_occ) < toSeconds(now) - buffer
+  int zero_free;            // the same predicate for last_occ == 0
+  int connectivity;         // 6 | 18 | 26
+};
+
+struct MotionParams {
+  float Rw[9], tw[3];
+  int W, H;
+  float fx, fy, cx, cy;
+  float max_range, min_z_world;
+  float block_size, block_size_inv, voxel_size_inv;
+  const float* depth;
+  const float* vertex;  // may be null -> computed from depth
+  int3* pixel_gidx;     // out: global voxel index per pixel, x = INT_MIN if the pixel is dropped
+  uint8_t* pixel_seed;  // out: 1 if the pixel's voxel is ever-free
+};
+
+void launchIntegrate(const DeviceMap& m, const FrameParams& p, int grid, cudaStream_t s);
+void launchTracking(const DeviceMap& m, const TrackingParams& p, int n_slots, cudaStream_t s);
+void launchEverFree(const DeviceMap& m, const TrackingParams& p, int n_slots, cudaStream_t s);
+void launchResetInactive(const DeviceMap& m, int n_slots, int3* removed, int max_removed, cudaStream_t s);
+void launchMarkAllInactive(const DeviceMap& m, int n_slots, cudaStream_t s);
+void launchClearUpdated(const DeviceMap& m, int n_slots, cudaStream_t s);
+void launchMotionLookup(const DeviceMap& m, const MotionParams& p, cudaStream_t s);
+void launchAllocateBox(const DeviceMap& m, int3 lo, int3 dims, int rank, int nranks, cudaStream_t s);
+void launchScanConfidence(const DeviceMap& m, float min_conf, float min_obs, float trunc, int n_slots,
+                          cudaStream_t s);
+
+// Export gathers: slot_list[n] -> dense arrays (device), see kb_api.cu.
+void launchGatherTsdf(const DeviceMap& m, const int* slots, int n, float* dist, float* weight, cudaStream_t s);
+void launchGatherTracking(const DeviceMap& m, const int* slots, int n, const unsigned long long* stamps,
+                          unsigned long long* last_obs, unsigned long long* last_occ, uint8_t* ever_free,
+                          uint8_t* active, uint8_t* to_remove, cudaStream_t s);
+void launchGatherSemantic(const DeviceMap& m, const int* slots, int n, int L, uint32_t* label,
+                          uint8_t* empty, float* lik, cudaStream_t s);
+
+}  // namespace kb

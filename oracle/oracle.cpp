@@ -1,0 +1,709 @@
+// TEST INFRASTRUCTURE — NOT PRODUCT CODE. See oracle.hpp. PARITY UNPINNED (no reference tests).
+// Compile with -ffp-contract=off: every float expression below is evaluated op by op in fp32.
+#include "oracle.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <thread>
+
+namespace ko {
+
+namespace {
+
+inline double toSeconds(uint64_t ns) { return static_cast<double>(ns) / 1e9; }  // UP App. A.2 [M]
+
+inline int floorDiv(int64_t a, int64_t b) {
+  int64_t q = a / b, r = a % b;
+  if (r != 0 && ((r < 0) != (b < 0))) --q;
+  return static_cast<int>(q);
+}
+
+template <typename F>
+void parallelFor(int n, int num_threads, F&& fn) {
+  // Same model as hydra::IndexGetter + std::thread workers (tracking_integrator.cpp:83-90): a shared
+  // cursor hands out block indices.
+  num_threads = std::max(1, std::min(num_threads, n));
+  if (num_threads == 1) {
+    for (int i = 0; i < n; ++i) fn(i);
+    return;
+  }
+  std::atomic<int> cursor{0};
+  std::vector<std::thread> threads;
+  for (int t = 0; t < num_threads; ++t) {
+    threads.emplace_back([&]() {
+      int i;
+      while ((i = cursor.fetch_add(1)) < n) fn(i);
+    });
+  }
+  for (auto& t : threads) t.join();
+}
+
+int resolveThreads(int n) {
+  if (n > 0) return n;
+  int hc = static_cast<int>(std::thread::hardware_concurrency());
+  return hc > 0 ? hc : 1;  // ThreadNumConversion: -1 => hardware concurrency (tracking_integrator.cpp:59)
+}
+
+// spatial_hash::NeighborSearch offsets (UP App. A.1): 6 faces, +12 edges (18), +8 corners (26).
+std::vector<std::array<int, 3>> neighborOffsets(int connectivity) {
+  std::vector<std::array<int, 3>> out;
+  for (int pass = 1; pass <= 3; ++pass) {
+    if ((pass == 2 && connectivity < 18) || (pass == 3 && connectivity < 26)) break;
+    for (int dz = -1; dz <= 1; ++dz)
+      for (int dy = -1; dy <= 1; ++dy)
+        for (int dx = -1; dx <= 1; ++dx) {
+          int nz = (dx != 0) + (dy != 0) + (dz != 0);
+          if (nz == pass) out.push_back({dx, dy, dz});
+        }
+  }
+  return out;
+}
+
+}  // namespace
+
+Oracle::Oracle(const kb_map_config& map, const kb_integrator_config& integ,
+               const kb_tracking_config* trk, const kb_motion_config* mot)
+    : map_(map), integ_(integ) {
+  if (trk) { trk_ = *trk; has_trk_ = true; }
+  if (mot) { mot_ = *mot; has_mot_ = true; }
+  vps_ = map.voxels_per_side;
+  V_ = vps_ * vps_ * vps_;
+  L_ = integ.semantic_mode == KB_SEMANTICS_MLE ? integ.num_labels
+       : integ.semantic_mode == KB_SEMANTICS_BINARY ? 2 : 0;
+  if (!map.with_semantics) L_ = 0;
+  block_size_ = map.voxel_size * static_cast<float>(vps_);
+  voxel_size_inv_ = 1.f / map.voxel_size;
+  block_size_inv_ = 1.f / block_size_;
+  if (integ.semantic_mode == KB_SEMANTICS_MLE && integ.num_labels > 1) {
+    // MLESemanticIntegrator (UP App. A.8): log-likelihood matrix with diag log(c), off-diag
+    // log((1-c)/(N-1)); prior log(1/N). Constants are formed in double and rounded once to float.
+    const double c = static_cast<double>(integ.label_confidence);
+    const double N = static_cast<double>(integ.num_labels);
+    mle_diag_ = static_cast<float>(std::log(c));
+    mle_off_ = static_cast<float>(std::log((1.0 - c) / (N - 1.0)));
+    mle_init_ = static_cast<float>(std::log(1.0 / N));
+  }
+  if (vps_ != 8 && vps_ != 16) error_ = "voxels_per_side must be 8 or 16";
+  if (!(map.voxel_size > 0) || !(map.truncation_distance > 0)) error_ = "invalid map config";
+}
+
+Block* Oracle::getBlock(const Idx3& idx) const {
+  auto it = blocks_.find(idx);
+  return it == blocks_.end() ? nullptr : it->second.get();
+}
+
+Block* Oracle::allocateBlock(const Idx3& idx) {
+  auto it = blocks_.find(idx);
+  if (it != blocks_.end()) return it->second.get();
+  auto b = std::make_unique<Block>();
+  b->index = idx;
+  b->distance.assign(V_, 0.f);
+  b->weight.assign(V_, 0.f);
+  b->color.assign(3 * V_, 0);
+  if (map_.with_tracking) {
+    b->last_observed.assign(V_, 0);
+    b->last_occupied.assign(V_, 0);
+    b->ever_free.assign(V_, 0);
+    b->active.assign(V_, 0);     // TrackingVoxel::active default [L]: false
+    b->to_remove.assign(V_, 0);
+  }
+  if (L_ > 0) {
+    b->semantic_label.assign(V_, 0);
+    b->semantic_empty.assign(V_, 1);
+    b->likelihoods.assign(static_cast<size_t>(V_) * L_, 0.f);
+  }
+  Block* raw = b.get();
+  blocks_.emplace(idx, std::move(b));
+  return raw;
+}
+
+// ---- camera (hydra::Camera, UP App. A.3) -------------------------------------------------------
+
+bool Oracle::project(const float p[3], float* u, float* v) const {
+  if (p[2] <= 0.f) return false;
+  *u = cam_.fx * p[0] / p[2] + cam_.cx;
+  *v = cam_.fy * p[1] / p[2] + cam_.cy;
+  if (*u < 0.f || *u > static_cast<float>(cam_.width - 1) || *v < 0.f ||
+      *v > static_cast<float>(cam_.height - 1)) {
+    return false;
+  }
+  return true;
+}
+
+bool Oracle::pointInFrustum(const float p[3], float infl) const {
+  if (p[2] < -infl) return false;
+  const float r = std::sqrt((p[0] * p[0] + p[1] * p[1]) + p[2] * p[2]);
+  if (r < cam_.min_range - infl || r > cam_.max_range + infl) return false;
+  // Four side planes through the optical centre, inward unit normals, offset by the inflation.
+  const float xl = (0.f - cam_.cx) / cam_.fx;
+  const float xr = (static_cast<float>(cam_.width - 1) - cam_.cx) / cam_.fx;
+  const float yt = (0.f - cam_.cy) / cam_.fy;
+  const float yb = (static_cast<float>(cam_.height - 1) - cam_.cy) / cam_.fy;
+  const float il = 1.f / std::sqrt(1.f + xl * xl), ir = 1.f / std::sqrt(1.f + xr * xr);
+  const float it = 1.f / std::sqrt(1.f + yt * yt), ib = 1.f / std::sqrt(1.f + yb * yb);
+  if (il * p[0] + (-xl * il) * p[2] < -infl) return false;
+  if ((-ir) * p[0] + (xr * ir) * p[2] < -infl) return false;
+  if (it * p[1] + (-yt * it) * p[2] < -infl) return false;
+  if ((-ib) * p[1] + (yb * ib) * p[2] < -infl) return false;
+  return true;
+}
+
+// ---- interpolators (hydra ProjectionInterpolator*, UP App. A.7) ------------------------------------
+
+Oracle::Weights Oracle::computeWeights(float u, float v, const float* range) const {
+  Weights w;
+  const int W = cam_.width, H = cam_.height;
+  auto nearest = [&]() {
+    Weights n;
+    n.u = static_cast<int>(std::round(u));
+    n.v = static_cast<int>(std::round(v));
+    n.bilinear = false;
+    n.valid = n.u >= 0 && n.u < W && n.v >= 0 && n.v < H && range[n.v * W + n.u] > 0.f;
+    return n;
+  };
+  if (integ_.interpolation_method == KB_INTERP_NEAREST) return nearest();
+  const int u0 = static_cast<int>(std::floor(u)), v0 = static_cast<int>(std::floor(v));
+  const bool inside = u0 >= 0 && v0 >= 0 && u0 + 1 < W && v0 + 1 < H;
+  if (!inside) {
+    return integ_.interpolation_method == KB_INTERP_ADAPTIVE ? nearest() : w;  // bilinear: invalid
+  }
+  // Neighbour order (u,v), (u,v+1), (u+1,v), (u+1,v+1).
+  const float r0 = range[v0 * W + u0], r1 = range[(v0 + 1) * W + u0];
+  const float r2 = range[v0 * W + u0 + 1], r3 = range[(v0 + 1) * W + u0 + 1];
+  const bool all_valid = r0 > 0.f && r1 > 0.f && r2 > 0.f && r3 > 0.f;
+  if (integ_.interpolation_method == KB_INTERP_ADAPTIVE) {
+    const float mx = std::max(std::max(r0, r1), std::max(r2, r3));
+    const float mn = std::min(std::min(r0, r1), std::min(r2, r3));
+    if (!all_valid || !(mx - mn < integ_.adaptive_max_depth_difference)) return nearest();
+  } else if (!all_valid) {
+    return w;
+  }
+  const float du = u - static_cast<float>(u0), dv = v - static_cast<float>(v0);
+  w.valid = true;
+  w.bilinear = true;
+  w.u = u0;
+  w.v = v0;
+  w.w[0] = (1.f - du) * (1.f - dv);
+  w.w[1] = (1.f - du) * dv;
+  w.w[2] = du * (1.f - dv);
+  w.w[3] = du * dv;
+  return w;
+}
+
+float Oracle::interpolateRange(const float* range, const Weights& w) const {
+  const int W = cam_.width;
+  if (!w.bilinear) return range[w.v * W + w.u];
+  return ((w.w[0] * range[w.v * W + w.u] + w.w[1] * range[(w.v + 1) * W + w.u]) +
+          w.w[2] * range[w.v * W + w.u + 1]) +
+         w.w[3] * range[(w.v + 1) * W + w.u + 1];
+}
+
+int32_t Oracle::interpolateID(const int32_t* img, const Weights& w) const {
+  const int W = cam_.width;
+  if (!w.bilinear) return img[w.v * W + w.u];
+  int best = 0;  // value at the neighbour with the largest weight; ties -> lowest neighbour index
+  for (int i = 1; i < 4; ++i) {
+    if (w.w[i] > w.w[best]) best = i;
+  }
+  const int du = best >> 1, dv = best & 1;
+  return img[(w.v + dv) * W + w.u + du];
+}
+
+float Oracle::computeWeight(float depth, float sdf) const {
+  // UP App. A.6 step 4: ray density fx*fy*vs^2/z^2, optional 1/z^2, linear drop-off behind surface.
+  const float vs = map_.voxel_size;
+  float weight = (cam_.fx * cam_.fy) * (vs * vs) / (depth * depth);
+  if (!integ_.use_constant_weight) weight = weight / (depth * depth);
+  if (integ_.use_weight_dropoff) {
+    const float eps = integ_.weight_dropoff_epsilon > 0.f ? integ_.weight_dropoff_epsilon
+                                                          : integ_.weight_dropoff_epsilon * -vs;
+    if (sdf < -eps) {
+      weight = weight * ((map_.truncation_distance + sdf) / (map_.truncation_distance - eps));
+      weight = std::max(weight, 0.f);
+    }
+  }
+  return weight;
+}
+
+// ---- K0 + K1 ---------------------------------------------------------------------------------------
+
+static void invertPose(const double T[16], float R[9], float t[3], float Rw[9], float tw[3]) {
+  // sensor_T_world = world_T_sensor^-1 for a rigid transform, formed in double, rounded once to float.
+  double Rd[9], td[3];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) Rd[r * 3 + c] = T[c * 4 + r];
+  for (int r = 0; r < 3; ++r)
+    td[r] = -(Rd[r * 3 + 0] * T[3] + Rd[r * 3 + 1] * T[7] + Rd[r * 3 + 2] * T[11]);
+  for (int i = 0; i < 9; ++i) R[i] = static_cast<float>(Rd[i]);
+  for (int i = 0; i < 3; ++i) t[i] = static_cast<float>(td[i]);
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) Rw[r * 3 + c] = static_cast<float>(T[r * 4 + c]);
+    tw[r] = static_cast<float>(T[r * 4 + 3]);
+  }
+}
+
+static inline void transform(const float R[9], const float t[3], const float p[3], float out[3]) {
+  out[0] = ((R[0] * p[0] + R[1] * p[1]) + R[2] * p[2]) + t[0];
+  out[1] = ((R[3] * p[0] + R[4] * p[1]) + R[5] * p[2]) + t[1];
+  out[2] = ((R[6] * p[0] + R[7] * p[1]) + R[8] * p[2]) + t[2];
+}
+
+void Oracle::integrateFrame(const kb_frame& f, bool allocate_blocks, kb_frame_stats* stats) {
+  if (!has_cam_) { error_ = "camera not set"; return; }
+  if (f.stamp_ns == 0) { error_ = "stamp must be > 0"; return; }
+  float R[9], t[3], Rw[9], tw[3];
+  invertPose(f.world_T_sensor, R, t, Rw, tw);
+
+  std::vector<Block*> todo;
+  int n_new = 0;
+  if (allocate_blocks) {
+    // findBlocksInViewFrustum (UP App. A.5): block centres inside the frustum inflated by the block
+    // half-diagonal, within [min_range, max_range].
+    const float infl = block_size_ * 0.8660254f;
+    const float reach = cam_.max_range + infl;
+    int lo[3], hi[3];
+    for (int a = 0; a < 3; ++a) {
+      lo[a] = static_cast<int>(std::floor((tw[a] - reach) * block_size_inv_));
+      hi[a] = static_cast<int>(std::floor((tw[a] + reach) * block_size_inv_));
+    }
+    for (int bz = lo[2]; bz <= hi[2]; ++bz)
+      for (int by = lo[1]; by <= hi[1]; ++by)
+        for (int bx = lo[0]; bx <= hi[0]; ++bx) {
+          const float c[3] = {(static_cast<float>(bx) + 0.5f) * block_size_,
+                              (static_cast<float>(by) + 0.5f) * block_size_,
+                              (static_cast<float>(bz) + 0.5f) * block_size_};
+          float cC[3];
+          transform(R, t, c, cC);
+          if (!pointInFrustum(cC, infl)) continue;
+          const Idx3 idx{bx, by, bz};
+          if (!getBlock(idx)) ++n_new;
+          todo.push_back(allocateBlock(idx));
+        }
+  } else {
+    for (auto& kv : blocks_) todo.push_back(kv.second.get());
+  }
+
+  std::atomic<int> counters[4];
+  for (auto& c : counters) c = 0;
+  parallelFor(static_cast<int>(todo.size()), resolveThreads(integ_.num_threads),
+              [&](int i) { updateBlock(*todo[i], f, R, t, counters); });
+  if (stats) {
+    stats->blocks_in_frustum = static_cast<int>(todo.size());
+    stats->blocks_allocated = n_new;
+    stats->blocks_updated = counters[0];
+    stats->voxels_updated = counters[1];
+    stats->voxels_in_band = counters[2];
+    stats->voxels_semantic = counters[3];
+    stats->total_blocks = static_cast<int>(blocks_.size());
+    stats->capacity_exceeded = 0;
+  }
+}
+
+void Oracle::updateBlock(Block& b, const kb_frame& f, const float R[9], const float t[3],
+                         std::atomic<int>* counters) {
+  // ProjectiveIntegrator::updateBlock / getVoxelMeasurement / computeLabel / updateVoxel
+  // (UP App. A.6; computeLabel structure pinned by object_integrator.cpp:58-81).
+  const float vs = map_.voxel_size, trunc = map_.truncation_distance;
+  const float ox = static_cast<float>(b.index.x) * block_size_;
+  const float oy = static_cast<float>(b.index.y) * block_size_;
+  const float oz = static_cast<float>(b.index.z) * block_size_;
+  const bool binary = integ_.semantic_mode == KB_SEMANTICS_BINARY;
+  const bool has_sem = L_ > 0 && (binary ? f.object_image != nullptr : f.label != nullptr);
+  int n_valid = 0, n_band = 0, n_sem = 0;
+  for (int lin = 0; lin < V_; ++lin) {
+    const int vx = lin % vps_, vy = (lin / vps_) % vps_, vz = lin / (vps_ * vps_);
+    const float pW[3] = {ox + (static_cast<float>(vx) + 0.5f) * vs,
+                         oy + (static_cast<float>(vy) + 0.5f) * vs,
+                         oz + (static_cast<float>(vz) + 0.5f) * vs};
+    float pC[3];
+    transform(R, t, pW, pC);
+    // 1. interpolatePoint
+    float u, v;
+    if (!project(pC, &u, &v)) continue;
+    const Weights w = computeWeights(u, v, f.depth);
+    if (!w.valid) continue;
+    // 2. sdf
+    const float depth = pC[2];
+    const float sdf = interpolateRange(f.depth, w) - depth;
+    if (sdf < -trunc) continue;
+    // 3. computeLabel
+    const bool in_band = std::fabs(sdf) < trunc;
+    uint32_t label = 0;
+    bool have_label = false;
+    if (in_band) {
+      if (f.mask && interpolateID(f.mask, w) != 0) continue;
+      if (has_sem) {
+        if (binary) {
+          label = interpolateID(f.object_image, w) == f.object_target_id ? 1u : 0u;
+          have_label = true;
+        } else {
+          label = static_cast<uint32_t>(interpolateID(f.label, w));
+          // SemanticIntegrator::canIntegrate: dynamic / invalid labels are not integrated at all.
+          if (label < static_cast<uint32_t>(KB_MAX_LABELS) && integ_.label_blocked[label]) continue;
+          have_label = true;
+        }
+      }
+    }
+    // 4. weight
+    const float wm = computeWeight(depth, sdf);
+    // updateVoxel
+    const float d_old = b.distance[lin], w_old = b.weight[lin];
+    const float sdf_c = std::min(std::max(sdf, -trunc), trunc);
+    b.distance[lin] = (d_old * w_old + sdf_c * wm) / (w_old + wm);
+    b.weight[lin] = std::min(w_old + wm, integ_.max_weight);
+    if (map_.with_tracking) b.last_observed[lin] = f.stamp_ns;
+    ++n_valid;
+    if (!in_band) continue;
+    ++n_band;
+    if (have_label && label < static_cast<uint32_t>(L_)) {  // isValidLabel
+      float* lik = &b.likelihoods[static_cast<size_t>(lin) * L_];
+      if (b.semantic_empty[lin]) {
+        b.semantic_empty[lin] = 0;
+        for (int k = 0; k < L_; ++k) lik[k] = binary ? 0.f : mle_init_;
+      }
+      if (binary) {
+        lik[label] = lik[label] + 1.f;
+      } else {
+        for (int k = 0; k < L_; ++k)
+          lik[k] = lik[k] + (static_cast<uint32_t>(k) == label ? mle_diag_ : mle_off_);
+      }
+      int best = 0;
+      for (int k = 1; k < L_; ++k)
+        if (lik[k] > lik[best]) best = k;
+      b.semantic_label[lin] = static_cast<uint32_t>(best);
+      ++n_sem;
+    }
+  }
+  if (n_valid > 0) {
+    b.updated = b.mesh_updated = b.esdf_updated = b.tracking_updated = true;  // setUpdated()
+    counters[0] += 1;
+    counters[1] += n_valid;
+    counters[2] += n_band;
+    counters[3] += n_sem;
+  }
+}
+
+// ---- K2 / K3 / K2r -----------------------------------------------------------------------------------
+
+bool Oracle::voxelIsFree(const Block& b, int lin, uint64_t stamp) const {
+  // tracking_integrator.cpp:248-252 (uses temporal_buffer; burn_in_period is unused by the reference).
+  return toSeconds(b.last_occupied[lin]) < toSeconds(stamp) - trk_.temporal_buffer &&
+         b.last_observed[lin] != 0u;
+}
+
+void Oracle::updateBlockTracking(Block& b, uint64_t stamp, float thr) {
+  // tracking_integrator.cpp:133-166 + updateTrackingDuration :224-246.
+  b.tracking_updated = false;
+  bool any_active = false;
+  for (int lin = 0; lin < V_; ++lin) {
+    if (b.distance[lin] < thr) b.last_occupied[lin] = stamp;
+    const bool was_active = b.active[lin] != 0;
+    const bool now_active =
+        toSeconds(b.last_observed[lin]) >= toSeconds(stamp) - trk_.temporal_window;
+    b.active[lin] = now_active;
+    if (was_active && !now_active) b.to_remove[lin] = 1;
+    any_active = any_active || now_active;
+  }
+  b.has_active_data = any_active;
+}
+
+void Oracle::updateBlockEverFree(const Block& b, uint64_t stamp, std::vector<int>* to_set) const {
+  // tracking_integrator.cpp:168-222. The reference writes ever_free while other threads read it; the
+  // outcome is order independent because a neighbour that became ever-free during this pass
+  // necessarily satisfies voxelIsFree at this stamp. We therefore evaluate every voxel against the
+  // pre-pass flags ("neighbour ever_free OR neighbour free now") and apply the writes afterwards,
+  // which is race free and gives the identical result.
+  const auto offs = neighborOffsets(trk_.neighbor_connectivity);
+  for (int lin = 0; lin < V_; ++lin) {
+    if (b.ever_free[lin] || !voxelIsFree(b, lin, stamp)) continue;
+    const int vx = lin % vps_, vy = (lin / vps_) % vps_, vz = lin / (vps_ * vps_);
+    bool blocked = false;
+    for (const auto& o : offs) {
+      int nx = vx + o[0], ny = vy + o[1], nz = vz + o[2];
+      Idx3 nb = b.index;
+      if (nx < 0) { nx += vps_; --nb.x; } else if (nx >= vps_) { nx -= vps_; ++nb.x; }
+      if (ny < 0) { ny += vps_; --nb.y; } else if (ny >= vps_) { ny -= vps_; ++nb.y; }
+      if (nz < 0) { nz += vps_; --nb.z; } else if (nz >= vps_) { nz -= vps_; ++nb.z; }
+      const Block* nblk = (nb == b.index) ? &b : getBlock(nb);
+      if (!nblk) { blocked = true; break; }  // :198-202 missing neighbour block
+      const int nlin = nx + vps_ * (ny + vps_ * nz);
+      if (nblk->ever_free[nlin]) continue;
+      if (!voxelIsFree(*nblk, nlin, stamp)) { blocked = true; break; }
+    }
+    if (!blocked) to_set->push_back(lin);
+  }
+}
+
+void Oracle::updateTracking(uint64_t stamp) {
+  if (!has_trk_ || !map_.with_tracking) { error_ = "tracking not configured"; return; }
+  // tracking_integrator.cpp:71-104: all blocks get the tracking pass, then blocks whose TSDF was
+  // updated this frame get the ever-free pass.
+  std::vector<Block*> all, updated;
+  for (auto& kv : blocks_) {
+    all.push_back(kv.second.get());
+    if (kv.second->tracking_updated) updated.push_back(kv.second.get());
+  }
+  const float thr = trk_.tsdf_occupancy_threshold < 0
+                        ? trk_.tsdf_occupancy_threshold * -map_.voxel_size
+                        : trk_.tsdf_occupancy_threshold;
+  const int nt = resolveThreads(trk_.num_threads);
+  parallelFor(static_cast<int>(all.size()), nt, [&](int i) { updateBlockTracking(*all[i], stamp, thr); });
+  std::vector<std::vector<int>> to_set(updated.size());
+  parallelFor(static_cast<int>(updated.size()), nt,
+              [&](int i) { updateBlockEverFree(*updated[i], stamp, &to_set[i]); });
+  for (size_t i = 0; i < updated.size(); ++i)
+    for (int lin : to_set[i]) updated[i]->ever_free[lin] = 1;
+}
+
+void Oracle::resetInactive(std::vector<Idx3>* removed) {
+  // tracking_integrator.cpp:106-131.
+  std::vector<Idx3> to_erase;
+  for (auto& kv : blocks_) {
+    Block& b = *kv.second;
+    if (b.to_remove.empty()) continue;  // no tracking block
+    bool remove_block = true;
+    for (int lin = 0; lin < V_; ++lin)
+      if (!b.to_remove[lin]) { remove_block = false; break; }
+    if (!b.has_active_data || remove_block) to_erase.push_back(b.index);
+  }
+  std::sort(to_erase.begin(), to_erase.end());
+  for (const auto& i : to_erase) blocks_.erase(i);
+  if (removed) *removed = to_erase;
+}
+
+void Oracle::markAllInactive() {
+  for (auto& kv : blocks_) kv.second->has_active_data = false;  // active_window.cpp:181-183
+}
+
+void Oracle::clearUpdated() {
+  for (auto& kv : blocks_) kv.second->updated = false;  // active_window.cpp:169-171
+}
+
+// ---- M1 - M4 --------------------------------------------------------------------------------------------
+
+void Oracle::detectMotion(const kb_frame& f, int32_t* dynamic_image, int32_t* n_seeds_out,
+                          int32_t* n_clusters_out) {
+  if (!has_mot_ || !map_.with_tracking) { error_ = "motion detector not configured"; return; }
+  const int W = cam_.width, H = cam_.height;
+  float R[9], t[3], Rw[9], tw[3];
+  invertPose(f.world_T_sensor, R, t, Rw, tw);
+  std::memset(dynamic_image, 0, sizeof(int32_t) * W * H);
+  clusters_.clear();
+
+  // vertex map in the world frame (hydra parseInputPacket, UP): back-project depth, then transform.
+  const float* vertex = f.vertex_world;
+  if (!vertex) {
+    vertex_scratch_.resize(static_cast<size_t>(W) * H * 3);
+    for (int v = 0; v < H; ++v)
+      for (int u = 0; u < W; ++u) {
+        const float d = f.depth[v * W + u];
+        const float pC[3] = {(static_cast<float>(u) - cam_.cx) / cam_.fx * d,
+                             (static_cast<float>(v) - cam_.cy) / cam_.fy * d, d};
+        transform(Rw, tw, pC, &vertex_scratch_[(static_cast<size_t>(v) * W + u) * 3]);
+      }
+    vertex = vertex_scratch_.data();
+  }
+
+  // M1: setUpPointMap / setUpPointMapPart (free_space_motion_detector.cpp:105-203).
+  const float min_z_world = tw[2] + mot_.min_z_coordinate;  // :80
+  using VoxelPoints = std::unordered_map<GIdx, std::vector<Pixel>, GIdxHash>;
+  VoxelPoints point_map;  // keyed by global voxel index of *valid* voxel indices
+  std::unordered_set<GIdx, GIdxHash> seeds;
+  const int nt = std::max(1, std::min(resolveThreads(mot_.num_threads), W));
+  int u_step = W / nt;
+  if (u_step * nt < W) ++u_step;  // :112-115
+  std::mutex mtx;
+  std::vector<std::thread> threads;
+  for (int i = 0; i < nt; ++i) {
+    threads.emplace_back([&, i]() {
+      VoxelPoints local_map;
+      std::unordered_set<GIdx, GIdxHash> local_seeds;
+      const int u_start = u_step * i, u_stop = std::min(u_step * (i + 1), W);
+      for (int v = 0; v < H; ++v)
+        for (int u = u_start; u < u_stop; ++u) {
+          const float range = f.depth[v * W + u];
+          if (range <= 0.f || range > mot_.max_range) continue;  // :169-172
+          const float* p = &vertex[(static_cast<size_t>(v) * W + u) * 3];
+          if (p[2] < min_z_world) continue;  // :176-178
+          const Idx3 bi{static_cast<int>(std::floor(p[0] * block_size_inv_)),
+                        static_cast<int>(std::floor(p[1] * block_size_inv_)),
+                        static_cast<int>(std::floor(p[2] * block_size_inv_))};
+          const Block* blk = getBlock(bi);
+          if (!blk) continue;  // :180-183
+          // block->getVoxelIndex(p): floor((p - origin) * voxel_size_inv), may be out of range.
+          const int vx = static_cast<int>(std::floor((p[0] - static_cast<float>(bi.x) * block_size_) * voxel_size_inv_));
+          const int vy = static_cast<int>(std::floor((p[1] - static_cast<float>(bi.y) * block_size_) * voxel_size_inv_));
+          const int vz = static_cast<int>(std::floor((p[2] - static_cast<float>(bi.z) * block_size_) * voxel_size_inv_));
+          // The reference appends the pixel under (block, voxel_index) before the validity check
+          // (:187-196); invalid indices can never be looked up again (keyFromGlobalIndex always
+          // yields valid voxel indices, :234), so such pixels never reach a cluster. We drop them.
+          if (vx < 0 || vy < 0 || vz < 0 || vx >= vps_ || vy >= vps_ || vz >= vps_) continue;
+          const GIdx g{static_cast<int64_t>(bi.x) * vps_ + vx, static_cast<int64_t>(bi.y) * vps_ + vy,
+                       static_cast<int64_t>(bi.z) * vps_ + vz};
+          local_map[g].push_back({u, v});
+          if (blk->ever_free[vx + vps_ * (vy + vps_ * vz)]) local_seeds.insert(g);  // :197-200
+        }
+      std::lock_guard<std::mutex> lock(mtx);
+      seeds.insert(local_seeds.begin(), local_seeds.end());
+      for (auto& kv : local_map) {
+        auto& dst = point_map[kv.first];
+        dst.insert(dst.end(), kv.second.begin(), kv.second.end());
+      }
+    });
+  }
+  for (auto& th : threads) th.join();
+  if (n_seeds_out) *n_seeds_out = static_cast<int32_t>(seeds.size());
+
+  // M2: clusterDynamicVoxels (:205-272). Seeds iterate in ascending (z,y,x) — a deliberate
+  // determinisation of the reference's unordered_set order.
+  std::vector<GIdx> seed_list(seeds.begin(), seeds.end());
+  std::sort(seed_list.begin(), seed_list.end(), GIdxZyxLess());
+  const auto offs = neighborOffsets(mot_.neighbor_connectivity);
+  std::unordered_set<GIdx, GIdxHash> closed;
+  std::vector<Cluster> clusters;
+  for (const GIdx& seed : seed_list) {
+    if (closed.count(seed)) continue;
+    std::vector<GIdx> stack = {seed};
+    Cluster cluster;
+    while (!stack.empty()) {
+      const GIdx g = stack.back();
+      stack.pop_back();
+      if (closed.count(g)) continue;
+      closed.insert(g);
+      auto it = point_map.find(g);
+      if (it == point_map.end()) continue;
+      cluster.pixels.insert(cluster.pixels.end(), it->second.begin(), it->second.end());
+      cluster.voxels.insert(g);
+      for (const auto& o : offs) {
+        const GIdx n{g.x + o[0], g.y + o[1], g.z + o[2]};
+        if (seeds.count(n)) {
+          stack.push_back(n);
+        } else {
+          // Non-seed neighbour that contains points: absorbed (pixels appended once per adjacent
+          // processed seed voxel — no closed-set check in the reference, :255-265) and closed.
+          auto it2 = point_map.find(n);
+          if (it2 != point_map.end()) {
+            cluster.pixels.insert(cluster.pixels.end(), it2->second.begin(), it2->second.end());
+            cluster.voxels.insert(n);
+            closed.insert(n);
+          }
+        }
+      }
+    }
+    clusters.emplace_back(std::move(cluster));
+  }
+
+  // M3: mergeClusters (:274-322): connected components of the overlap graph merge into the lowest
+  // index. checkClusterOverlap (:345-355): Eigen integer norm() truncates sqrt to an integer.
+  const size_t C = clusters.size();
+  std::vector<std::vector<uint8_t>> overlap(C, std::vector<uint8_t>(C, 0));
+  for (size_t i = 0; i < C; ++i)
+    for (size_t j = i + 1; j < C; ++j) {
+      bool ov = false;
+      for (const GIdx& a : clusters[i].voxels) {
+        for (const GIdx& b : clusters[j].voxels) {
+          const int64_t dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;
+          const int64_t n = static_cast<int64_t>(std::sqrt(static_cast<double>(dx * dx + dy * dy + dz * dz)));
+          if (static_cast<float>(n) < mot_.min_separation_distance) { ov = true; break; }
+        }
+        if (ov) break;
+      }
+      overlap[i][j] = overlap[j][i] = ov;
+    }
+  std::vector<bool> merged(C, false), keep(C, false);
+  std::function<void(size_t, std::vector<size_t>&)> collect = [&](size_t c, std::vector<size_t>& out) {
+    for (size_t i = 0; i < C; ++i) {
+      if (merged[i]) continue;
+      if (overlap[c][i]) {
+        merged[i] = true;
+        out.push_back(i);
+        collect(i, out);
+      }
+    }
+  };
+  for (size_t cur = 0; cur < C; ++cur) {
+    if (merged[cur]) continue;
+    std::vector<size_t> conn;
+    collect(cur, conn);
+    for (size_t i : conn) {
+      if (i == cur) continue;
+      clusters[cur].pixels.insert(clusters[cur].pixels.end(), clusters[i].pixels.begin(),
+                                  clusters[i].pixels.end());
+      clusters[cur].voxels.insert(clusters[i].voxels.begin(), clusters[i].voxels.end());
+    }
+    keep[cur] = true;
+  }
+  std::vector<Cluster> kept;
+  for (size_t i = 0; i < C; ++i)
+    if (keep[i]) kept.emplace_back(std::move(clusters[i]));
+
+  // M4: applyClusterLevelFilters (:365-379) + writeClustersToData (:381-399).
+  for (auto& c : kept) {
+    const int sz = static_cast<int>(c.pixels.size());
+    if (sz < mot_.min_cluster_size || sz > mot_.max_cluster_size) continue;
+    clusters_.emplace_back(std::move(c));
+  }
+  int id = 1;
+  for (auto& c : clusters_) {
+    c.id = id;
+    bool first = true;
+    for (const Pixel& px : c.pixels) {
+      dynamic_image[px.v * W + px.u] = id;
+      const float* p = &vertex[(static_cast<size_t>(px.v) * W + px.u) * 3];
+      for (int a = 0; a < 3; ++a) {
+        c.bbox_min[a] = first ? p[a] : std::min(c.bbox_min[a], p[a]);
+        c.bbox_max[a] = first ? p[a] : std::max(c.bbox_max[a], p[a]);
+      }
+      first = false;
+    }
+    if (id < 255) ++id;  // ids saturate at 255 (:390-395)
+  }
+  if (n_clusters_out) *n_clusters_out = static_cast<int32_t>(clusters_.size());
+}
+
+// ---- E0 / K4 ----------------------------------------------------------------------------------------------
+
+void Oracle::allocateBox(const int32_t mn[3], const int32_t mx[3]) {
+  for (int x = mn[0]; x <= mx[0]; ++x)
+    for (int y = mn[1]; y <= mx[1]; ++y)
+      for (int z = mn[2]; z <= mx[2]; ++z) allocateBlock(Idx3{x, y, z});
+}
+
+int Oracle::scanObjectConfidence(float min_confidence, int min_observations) {
+  // mesh_object_extractor.cpp:246-264 with computeConfidence :342-356.
+  int erased = 0;
+  if (L_ < 2) { error_ = "scanObjectConfidence needs binary semantics"; return 0; }
+  for (auto& kv : blocks_) {
+    Block& b = *kv.second;
+    for (int lin = 0; lin < V_; ++lin) {
+      if (b.distance[lin] > 0.f) continue;
+      float conf;
+      if (b.semantic_empty[lin]) {
+        conf = 0.f;
+      } else {
+        const float total = b.likelihoods[static_cast<size_t>(lin) * L_] +
+                            b.likelihoods[static_cast<size_t>(lin) * L_ + 1];
+        conf = total < static_cast<float>(min_observations)
+                   ? -1.f
+                   : b.likelihoods[static_cast<size_t>(lin) * L_ + 1] / total;
+      }
+      if (conf < min_confidence) {
+        b.distance[lin] = map_.truncation_distance;
+        ++erased;
+      }
+    }
+  }
+  return erased;
+}
+
+std::vector<const Block*> Oracle::sortedBlocks(int which) const {
+  std::vector<const Block*> out;
+  for (auto& kv : blocks_)
+    if (which == KB_EXPORT_ALL || kv.second->updated) out.push_back(kv.second.get());
+  std::sort(out.begin(), out.end(), [](const Block* a, const Block* b) { return a->index < b->index; });
+  return out;
+}
+
+}  // namespace ko

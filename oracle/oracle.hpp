@@ -1,0 +1,151 @@
+// TEST INFRASTRUCTURE — NOT PRODUCT CODE.
+//
+// CPU oracle: a dependency-free C++17 restatement of Khronos' active-window fusion hot path. Only
+// tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may use it.
+//
+// PARITY UNPINNED: the reference ships no tests / golden vectors for this path, and the per-voxel
+// arithmetic lives in MIT-SPARK/Hydra @ main (floating, un-vendored: install/https.rosinstall:5-8),
+// which is absent from /root/reference. In-tree code (tracking_integrator.cpp,
+// free_space_motion_detector.cpp, object_integrator.cpp, mesh_object_extractor.cpp) is followed
+// line by line; upstream behaviour is restated per SURVEY.md Appendix A / docs/ORACLE_SPEC.md.
+//
+// All citations are relative to /root/reference/.
+#pragma once
+
+#include <array>
+#include <atomic>
+#include <cstdint>
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <unordered_set>
+#include <vector>
+
+#include "../include/khronos_b200.h"  // plain-C config/frame/export structs (declarations only)
+
+namespace ko {
+
+struct Idx3 {
+  int32_t x = 0, y = 0, z = 0;
+  bool operator==(const Idx3& o) const { return x == o.x && y == o.y && z == o.z; }
+  bool operator<(const Idx3& o) const {
+    return x != o.x ? x < o.x : (y != o.y ? y < o.y : z < o.z);
+  }
+};
+// spatial_hash block hash (UP): x + y*17191 + z*17191^2. Only affects iteration order.
+struct Idx3Hash {
+  size_t operator()(const Idx3& i) const {
+    return static_cast<size_t>(static_cast<int64_t>(i.x) + static_cast<int64_t>(i.y) * 17191 +
+                               static_cast<int64_t>(i.z) * 17191 * 17191);
+  }
+};
+struct GIdx {
+  int64_t x = 0, y = 0, z = 0;
+  bool operator==(const GIdx& o) const { return x == o.x && y == o.y && z == o.z; }
+};
+struct GIdxHash {
+  size_t operator()(const GIdx& i) const {
+    return static_cast<size_t>(i.x + i.y * 17191 + i.z * 17191 * 17191);
+  }
+};
+// Deterministic seed order: ascending (z, y, x).
+struct GIdxZyxLess {
+  bool operator()(const GIdx& a, const GIdx& b) const {
+    return a.z != b.z ? a.z < b.z : (a.y != b.y ? a.y < b.y : a.x < b.x);
+  }
+};
+
+struct Pixel {
+  int32_t u, v;
+};
+
+// One voxel block of all layers (hydra TsdfBlock + TrackingBlock + SemanticBlock, UP App. A.2),
+// stored SoA. Linear voxel index = x + vps*(y + vps*z).
+struct Block {
+  Idx3 index;
+  std::vector<float> distance, weight;                   // TsdfVoxel
+  std::vector<uint8_t> color;                            // 3 per voxel
+  std::vector<uint64_t> last_observed, last_occupied;    // TrackingVoxel
+  std::vector<uint8_t> ever_free, active, to_remove;
+  std::vector<uint32_t> semantic_label;                  // SemanticVoxel
+  std::vector<uint8_t> semantic_empty;
+  std::vector<float> likelihoods;                        // V * L
+  bool updated = false, mesh_updated = false, esdf_updated = false, tracking_updated = false;
+  bool has_active_data = false;
+};
+
+struct Cluster {
+  std::vector<Pixel> pixels;
+  std::unordered_set<GIdx, GIdxHash> voxels;
+  int id = 0;
+  float bbox_min[3] = {0, 0, 0}, bbox_max[3] = {0, 0, 0};
+};
+
+class Oracle {
+ public:
+  Oracle(const kb_map_config& map, const kb_integrator_config& integ, const kb_tracking_config* trk,
+         const kb_motion_config* mot);
+
+  void setCamera(const kb_camera& cam) { cam_ = cam; has_cam_ = true; }
+
+  // K0+K1: hydra::ProjectiveIntegrator::updateMap (UP; call site active_window.cpp:210).
+  void integrateFrame(const kb_frame& f, bool allocate_blocks, kb_frame_stats* stats);
+  // K2+K3: TrackingIntegrator::updateBlocks (tracking_integrator.cpp:71-104).
+  void updateTracking(uint64_t stamp_ns);
+  // K2r: TrackingIntegrator::resetInactive (tracking_integrator.cpp:106-131).
+  void resetInactive(std::vector<Idx3>* removed);
+  void markAllInactive();
+  void clearUpdated();
+  // M1-M4: FreeSpaceMotionDetector::processInput (free_space_motion_detector.cpp:73-103).
+  void detectMotion(const kb_frame& f, int32_t* dynamic_image, int32_t* n_seeds, int32_t* n_clusters);
+  const std::vector<Cluster>& clusters() const { return clusters_; }
+  // E0 / K4 (mesh_object_extractor.cpp:220-228, :246-264, :342-356).
+  void allocateBox(const int32_t mn[3], const int32_t mx[3]);
+  int scanObjectConfidence(float min_confidence, int min_observations);
+
+  std::vector<const Block*> sortedBlocks(int which) const;
+  int V() const { return V_; }
+  int L() const { return L_; }
+  bool ok() const { return error_.empty(); }
+  const std::string& error() const { return error_; }
+
+  // Exposed for known-answer unit tests.
+  struct Weights {
+    bool valid = false, bilinear = false;
+    int u = 0, v = 0;
+    float w[4] = {0, 0, 0, 0};
+  };
+  Weights computeWeights(float u, float v, const float* range) const;
+  float interpolateRange(const float* range, const Weights& w) const;
+  int32_t interpolateID(const int32_t* img, const Weights& w) const;
+  bool project(const float p_C[3], float* u, float* v) const;
+  float computeWeight(float depth, float sdf) const;
+  bool pointInFrustum(const float p_C[3], float inflation) const;
+
+ private:
+  Block* allocateBlock(const Idx3& idx);
+  Block* getBlock(const Idx3& idx) const;
+  void updateBlock(Block& b, const kb_frame& f, const float R[9], const float t[3],
+                   std::atomic<int>* counters);
+  void updateBlockTracking(Block& b, uint64_t stamp, float thr);
+  void updateBlockEverFree(const Block& b, uint64_t stamp, std::vector<int>* to_set) const;
+  bool voxelIsFree(const Block& b, int lin, uint64_t stamp) const;
+
+  kb_map_config map_;
+  kb_integrator_config integ_;
+  kb_tracking_config trk_{};
+  kb_motion_config mot_{};
+  bool has_trk_ = false, has_mot_ = false, has_cam_ = false;
+  kb_camera cam_{};
+  int vps_, V_, L_;
+  float block_size_, voxel_size_inv_, block_size_inv_;
+  float mle_diag_ = 0, mle_off_ = 0, mle_init_ = 0;
+  std::unordered_map<Idx3, std::unique_ptr<Block>, Idx3Hash> blocks_;
+  std::vector<Cluster> clusters_;
+  std::vector<float> vertex_scratch_;
+  std::string error_;
+};
+
+}  // namespace ko

@@ -1,0 +1,187 @@
+// TEST INFRASTRUCTURE — NOT PRODUCT CODE. C API of the CPU oracle, mirroring include/khronos_b200.h
+// one-to-one with a ko_ prefix so the same Python harness can drive either side.
+#include <algorithm>
+#include <cstring>
+
+#include "oracle.hpp"
+
+using ko::Oracle;
+
+struct ko_handle {
+  Oracle* o;
+  std::string last_error;
+};
+
+static int fail(ko_handle* h, int code) {
+  if (h && h->o) h->last_error = h->o->error();
+  return code;
+}
+
+extern "C" {
+
+int ko_create(const kb_map_config* map, const kb_integrator_config* integ,
+              const kb_tracking_config* trk, const kb_motion_config* mot, int /*device*/,
+              ko_handle** out) {
+  if (!map || !integ || !out) return KB_ERR_INVALID;
+  auto* h = new ko_handle{new Oracle(*map, *integ, trk, mot), ""};
+  if (!h->o->ok()) {
+    delete h->o;
+    delete h;
+    return KB_ERR_INVALID;
+  }
+  *out = h;
+  return KB_OK;
+}
+
+int ko_destroy(ko_handle* h) {
+  if (!h) return KB_OK;
+  delete h->o;
+  delete h;
+  return KB_OK;
+}
+
+const char* ko_last_error(const ko_handle* h) { return h ? h->last_error.c_str() : "null handle"; }
+int ko_abi_version(void) { return KB_ABI_VERSION; }
+int ko_set_stream(ko_handle*, void*) { return KB_OK; }
+int ko_synchronize(ko_handle*) { return KB_OK; }
+
+int ko_set_camera(ko_handle* h, const kb_camera* cam) {
+  if (!h || !cam) return KB_ERR_INVALID;
+  h->o->setCamera(*cam);
+  return KB_OK;
+}
+
+int ko_integrate_frame(ko_handle* h, const kb_frame* f, int allocate_blocks, kb_frame_stats* stats) {
+  if (!h || !f || !f->depth) return KB_ERR_INVALID;
+  h->o->integrateFrame(*f, allocate_blocks != 0, stats);
+  return h->o->ok() ? KB_OK : fail(h, KB_ERR_INVALID);
+}
+
+int ko_update_tracking(ko_handle* h, uint64_t stamp_ns) {
+  if (!h) return KB_ERR_INVALID;
+  h->o->updateTracking(stamp_ns);
+  return h->o->ok() ? KB_OK : fail(h, KB_ERR_INVALID);
+}
+
+int ko_reset_inactive(ko_handle* h, int32_t* removed_xyz, int32_t max_removed, int32_t* n_removed) {
+  if (!h) return KB_ERR_INVALID;
+  std::vector<ko::Idx3> removed;
+  h->o->resetInactive(&removed);
+  if (n_removed) *n_removed = static_cast<int32_t>(removed.size());
+  if (removed_xyz) {
+    for (int i = 0; i < std::min<int>(max_removed, removed.size()); ++i) {
+      removed_xyz[i * 3 + 0] = removed[i].x;
+      removed_xyz[i * 3 + 1] = removed[i].y;
+      removed_xyz[i * 3 + 2] = removed[i].z;
+    }
+  }
+  return KB_OK;
+}
+
+int ko_mark_all_inactive(ko_handle* h) { h->o->markAllInactive(); return KB_OK; }
+int ko_clear_updated(ko_handle* h) { h->o->clearUpdated(); return KB_OK; }
+
+int ko_detect_motion(ko_handle* h, const kb_frame* f, int32_t* dynamic_image_out, int32_t* n_seeds,
+                     int32_t* n_clusters) {
+  if (!h || !f || !dynamic_image_out) return KB_ERR_INVALID;
+  h->o->detectMotion(*f, dynamic_image_out, n_seeds, n_clusters);
+  return h->o->ok() ? KB_OK : fail(h, KB_ERR_INVALID);
+}
+
+int ko_get_motion_clusters(ko_handle* h, int32_t* counts, int32_t* pixels_uv, int64_t* voxels_xyz,
+                           float* bbox_min_max, int32_t* total_pixels, int32_t* total_voxels) {
+  if (!h) return KB_ERR_INVALID;
+  const auto& cl = h->o->clusters();
+  int tp = 0, tv = 0;
+  for (size_t c = 0; c < cl.size(); ++c) {
+    if (counts) {
+      counts[c * 2 + 0] = static_cast<int32_t>(cl[c].pixels.size());
+      counts[c * 2 + 1] = static_cast<int32_t>(cl[c].voxels.size());
+    }
+    if (pixels_uv) {
+      for (size_t i = 0; i < cl[c].pixels.size(); ++i) {
+        pixels_uv[(tp + i) * 2 + 0] = cl[c].pixels[i].u;
+        pixels_uv[(tp + i) * 2 + 1] = cl[c].pixels[i].v;
+      }
+    }
+    if (voxels_xyz) {
+      std::vector<ko::GIdx> vs(cl[c].voxels.begin(), cl[c].voxels.end());
+      std::sort(vs.begin(), vs.end(), ko::GIdxZyxLess());
+      for (size_t i = 0; i < vs.size(); ++i) {
+        voxels_xyz[(tv + i) * 3 + 0] = vs[i].x;
+        voxels_xyz[(tv + i) * 3 + 1] = vs[i].y;
+        voxels_xyz[(tv + i) * 3 + 2] = vs[i].z;
+      }
+    }
+    if (bbox_min_max) {
+      for (int a = 0; a < 3; ++a) {
+        bbox_min_max[c * 6 + a] = cl[c].bbox_min[a];
+        bbox_min_max[c * 6 + 3 + a] = cl[c].bbox_max[a];
+      }
+    }
+    tp += static_cast<int>(cl[c].pixels.size());
+    tv += static_cast<int>(cl[c].voxels.size());
+  }
+  if (total_pixels) *total_pixels = tp;
+  if (total_voxels) *total_voxels = tv;
+  return KB_OK;
+}
+
+int ko_allocate_box(ko_handle* h, const int32_t mn[3], const int32_t mx[3]) {
+  if (!h) return KB_ERR_INVALID;
+  h->o->allocateBox(mn, mx);
+  return KB_OK;
+}
+
+int ko_scan_object_confidence(ko_handle* h, float min_confidence, int32_t min_observations,
+                              int32_t* n_erased) {
+  if (!h) return KB_ERR_INVALID;
+  const int n = h->o->scanObjectConfidence(min_confidence, min_observations);
+  if (n_erased) *n_erased = n;
+  return h->o->ok() ? KB_OK : fail(h, KB_ERR_INVALID);
+}
+
+int ko_num_blocks(ko_handle* h, int which, int32_t* n) {
+  if (!h || !n) return KB_ERR_INVALID;
+  *n = static_cast<int32_t>(h->o->sortedBlocks(which).size());
+  return KB_OK;
+}
+
+int ko_export_blocks(ko_handle* h, int which, int32_t max_blocks, kb_block_export* out,
+                     int32_t* n_written) {
+  if (!h || !out) return KB_ERR_INVALID;
+  const auto blocks = h->o->sortedBlocks(which);
+  const int n = std::min<int>(max_blocks, blocks.size());
+  const size_t V = h->o->V(), L = h->o->L();
+  for (int i = 0; i < n; ++i) {
+    const ko::Block& b = *blocks[i];
+    if (out->block_index) {
+      out->block_index[i * 3 + 0] = b.index.x;
+      out->block_index[i * 3 + 1] = b.index.y;
+      out->block_index[i * 3 + 2] = b.index.z;
+    }
+    if (out->block_flags) {
+      out->block_flags[i] = (b.updated ? KB_FLAG_UPDATED : 0) | (b.mesh_updated ? KB_FLAG_MESH_UPDATED : 0) |
+                            (b.esdf_updated ? KB_FLAG_ESDF_UPDATED : 0) |
+                            (b.tracking_updated ? KB_FLAG_TRACKING_UPDATED : 0) |
+                            (b.has_active_data ? KB_FLAG_HAS_ACTIVE_DATA : 0);
+    }
+    if (out->distance) std::memcpy(out->distance + i * V, b.distance.data(), V * 4);
+    if (out->weight) std::memcpy(out->weight + i * V, b.weight.data(), V * 4);
+    if (out->color) std::memcpy(out->color + i * V * 3, b.color.data(), V * 3);
+    const bool trk = !b.last_observed.empty();
+    if (out->last_observed) trk ? (void)std::memcpy(out->last_observed + i * V, b.last_observed.data(), V * 8) : (void)std::memset(out->last_observed + i * V, 0, V * 8);
+    if (out->last_occupied) trk ? (void)std::memcpy(out->last_occupied + i * V, b.last_occupied.data(), V * 8) : (void)std::memset(out->last_occupied + i * V, 0, V * 8);
+    if (out->ever_free) trk ? (void)std::memcpy(out->ever_free + i * V, b.ever_free.data(), V) : (void)std::memset(out->ever_free + i * V, 0, V);
+    if (out->active) trk ? (void)std::memcpy(out->active + i * V, b.active.data(), V) : (void)std::memset(out->active + i * V, 0, V);
+    if (out->to_remove) trk ? (void)std::memcpy(out->to_remove + i * V, b.to_remove.data(), V) : (void)std::memset(out->to_remove + i * V, 0, V);
+    const bool sem = L > 0;
+    if (out->semantic_label) sem ? (void)std::memcpy(out->semantic_label + i * V, b.semantic_label.data(), V * 4) : (void)std::memset(out->semantic_label + i * V, 0, V * 4);
+    if (out->semantic_empty) sem ? (void)std::memcpy(out->semantic_empty + i * V, b.semantic_empty.data(), V) : (void)std::memset(out->semantic_empty + i * V, 1, V);
+    if (out->semantic_likelihoods && sem) std::memcpy(out->semantic_likelihoods + i * V * L, b.likelihoods.data(), V * L * 4);
+  }
+  if (n_written) *n_written = n;
+  return KB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,239 @@
+"""GPU parity tests proper: CUDA product (through the C ABI) vs the CPU oracle on the same seeded
+synthetic inputs. Integer outputs (labels, stamps, flags, block sets, dynamic image) must be bit-exact;
+TSDF distance / weight within 1e-4 relative (BASELINE.json north_star) — in practice they are also
+bit-exact because both sides evaluate the same fp32 expression order without FMA contraction."""
+import numpy as np
+import pytest
+
+import khronos_b200 as kb
+from khronos_b200 import capi, synthetic as syn
+import harness as hs
+
+pytestmark = pytest.mark.gpu
+
+
+def both(oracle_lib, product_lib, **kw):
+    return hs.make_handle(oracle_lib, "ko_", **kw), hs.make_handle(product_lib, "kb_", **kw)
+
+
+def room_frames(cam, n, laps=0.25, dt_ns=33_333_333, scene=None):
+    scene = scene or syn.room_scene()
+    poses, stamps = syn.orbit_trajectory(n, laps=laps, dt_ns=dt_ns)
+    return hs.render_frames(scene, cam, poses, stamps), poses, stamps
+
+
+@pytest.mark.parametrize("interp", [capi.INTERP_ADAPTIVE, capi.INTERP_NEAREST, capi.INTERP_BILINEAR])
+def test_fusion_small_stream_bit_exact(oracle_lib, product_lib, interp):
+    cam = hs.small_camera(4)
+    frames, poses, stamps = room_frames(cam, 10)
+    cfg = dict(cam=cam, integ_cfg=capi.default_integrator_config(interpolation=interp))
+    o, g = both(oracle_lib, product_lib, **cfg)
+    so = hs.run_fusion(o, frames, poses, stamps)
+    sg = hs.run_fusion(g, frames, poses, stamps)
+    assert so == sg
+    hs.assert_blocks_equal(o.export_blocks(), g.export_blocks(), exact_float=True, what=f"interp{interp}")
+
+
+def test_fusion_full_resolution_frame(oracle_lib, product_lib):
+    """BASELINE config 1/2 shape: 640x480 into a 5 cm / 16^3 map."""
+    cam = syn.make_camera()
+    frames, poses, stamps = room_frames(cam, 3, laps=0.02)
+    o, g = both(oracle_lib, product_lib, cam=cam)
+    so = hs.run_fusion(o, frames, poses, stamps)
+    sg = hs.run_fusion(g, frames, poses, stamps)
+    assert so == sg
+    assert so[0]["voxels_updated"] > 100000
+    hs.assert_blocks_equal(o.export_blocks(), g.export_blocks(), exact_float=True, what="fullres")
+
+
+def test_fusion_weight_options_and_blocked_labels(oracle_lib, product_lib):
+    cam = hs.small_camera(4)
+    frames, poses, stamps = room_frames(cam, 6)
+    ic = capi.default_integrator_config(blocked=(4, 9))
+    ic.use_constant_weight = 1
+    ic.use_weight_dropoff = 0
+    ic.max_weight = 50.0
+    o, g = both(oracle_lib, product_lib, cam=cam, integ_cfg=ic)
+    assert hs.run_fusion(o, frames, poses, stamps) == hs.run_fusion(g, frames, poses, stamps)
+    bo, bg = o.export_blocks(), g.export_blocks()
+    hs.assert_blocks_equal(bo, bg, exact_float=True, what="options")
+    assert not np.isin(bo.semantic_label[bo.semantic_empty == 0], (4, 9)).any()
+
+
+def test_integration_mask(oracle_lib, product_lib):
+    cam = hs.small_camera(4)
+    frames, poses, stamps = room_frames(cam, 4)
+    rng = np.random.default_rng(3)
+    masks = []
+    for _ in frames:
+        m = np.zeros((cam.height, cam.width), np.int32)
+        m[20:70, 30:90] = rng.integers(0, 3, size=(50, 60))
+        masks.append(m)
+    o, g = both(oracle_lib, product_lib, cam=cam)
+    assert hs.run_fusion(o, frames, poses, stamps, masks=masks) == hs.run_fusion(g, frames, poses, stamps, masks=masks)
+    hs.assert_blocks_equal(o.export_blocks(), g.export_blocks(), exact_float=True, what="mask")
+
+
+def test_no_semantics_no_tracking(oracle_lib, product_lib):
+    cam = hs.small_camera(4)
+    frames, poses, stamps = room_frames(cam, 4)
+    mc = capi.default_map_config(with_semantics=False, with_tracking=False)
+    ic = capi.default_integrator_config(semantic_mode=capi.SEM_NONE)
+    o, g = both(oracle_lib, product_lib, cam=cam, map_cfg=mc, integ_cfg=ic)
+    assert hs.run_fusion(o, frames, poses, stamps) == hs.run_fusion(g, frames, poses, stamps)
+    hs.assert_blocks_equal(o.export_blocks(), g.export_blocks(), exact_float=True, what="plain")
+
+
+def dynamic_scenario(cam):
+    """Static burn-in (> temporal_buffer) so free space becomes ever-free, then a cuboid moves through it."""
+    scene = syn.room_scene()
+    scene.mover = ((0.5, 0.5, 1.2), (8.6, 1.5, 0.9), (0.0, 2.0, 0.0), 2.0)
+    n, dt = 30, 150_000_000
+    pose = syn.look_pose((6.0, 5.0, 1.5), 0.0, np.radians(10.0))
+    poses = [pose] * n
+    stamps = [1_000_000_000 + i * dt for i in range(n)]
+    # the mover waits outside the view cone, then crosses the (by then ever-free) space in front of
+    # the camera from t = 2 s on.
+    return scene, hs.render_frames(scene, cam, poses, stamps), poses, stamps
+
+
+def test_tracking_everfree_motion(oracle_lib, product_lib):
+    cam = hs.small_camera(4)
+    scene, frames, poses, stamps = dynamic_scenario(cam)
+    mot = capi.default_motion_config(min_cluster_size=5, min_separation_distance=2.0)
+    o, g = both(oracle_lib, product_lib, cam=cam, mot_cfg=mot)
+    total_dyn = 0
+    for i, ((d, l), T, st) in enumerate(zip(frames, poses, stamps)):
+        fo, fg = o.make_frame(d, T, st, label=l), g.make_frame(d, T, st, label=l)
+        io, so_, co = o.detect_motion(fo)
+        ig, sg_, cg = g.detect_motion(fg)
+        assert (so_, co) == (sg_, cg), f"frame {i}: seeds/clusters {so_, co} vs {sg_, cg}"
+        np.testing.assert_array_equal(io, ig, err_msg=f"dynamic_image frame {i}")
+        clo, clg = o.get_motion_clusters(), g.get_motion_clusters()
+        assert len(clo) == len(clg)
+        for a, b in zip(clo, clg):
+            np.testing.assert_array_equal(a["voxels"], b["voxels"])
+            pa = a["pixels"][np.lexsort(a["pixels"].T)]
+            pb = b["pixels"][np.lexsort(b["pixels"].T)]
+            np.testing.assert_array_equal(pa, pb)
+            np.testing.assert_array_equal(a["bbox"], b["bbox"])
+        total_dyn += int((io > 0).sum())
+        fo2, fg2 = o.make_frame(d, T, st, label=l, mask=io), g.make_frame(d, T, st, label=l, mask=ig)
+        assert o.integrate_frame(fo2).as_dict() == g.integrate_frame(fg2).as_dict()
+        o.update_tracking(st)
+        g.update_tracking(st)
+    bo, bg = o.export_blocks(), g.export_blocks()
+    hs.assert_blocks_equal(bo, bg, exact_float=True, what="dynamic")
+    assert bo.ever_free.sum() > 1000, "scenario must produce ever-free space"
+    assert total_dyn > 100, "scenario must flag dynamic pixels"
+
+
+def test_reset_inactive_and_reuse(oracle_lib, product_lib):
+    cam = hs.small_camera(4)
+    # 0.5 s between frames, quarter orbit: early blocks leave the 3 s temporal window
+    frames, poses, stamps = room_frames(cam, 14, laps=0.5, dt_ns=500_000_000)
+    o, g = both(oracle_lib, product_lib, cam=cam)
+    removed_total = 0
+    for i, ((d, l), T, st) in enumerate(zip(frames, poses, stamps)):
+        for h in (o, g):
+            h.integrate_frame(h.make_frame(d, T, st, label=l))
+            h.update_tracking(st)
+        if i % 4 == 3:
+            ro, rg = o.reset_inactive(), g.reset_inactive()
+            np.testing.assert_array_equal(ro, rg)
+            removed_total += len(ro)
+            o.clear_updated(); g.clear_updated()
+            hs.assert_blocks_equal(o.export_blocks(), g.export_blocks(), exact_float=True, what=f"after reset {i}")
+    assert removed_total > 0
+    hs.assert_blocks_equal(o.export_blocks(capi.EXPORT_UPDATED), g.export_blocks(capi.EXPORT_UPDATED), exact_float=True, what="updated-only")
+    for h in (o, g):
+        h.mark_all_inactive()
+    np.testing.assert_array_equal(o.reset_inactive(), g.reset_inactive())
+    assert o.num_blocks() == g.num_blocks() == 0
+
+
+def test_object_extraction_path(oracle_lib, product_lib):
+    """K1b + E0 + K4: private vps=8 binary-semantics map, pre-allocated box, integrate without
+    allocation, low-confidence erase (mesh_object_extractor.cpp:201-264)."""
+    cam = hs.small_camera(2)
+    scene = syn.room_scene()
+    # 12 views orbiting towards the first cuboid (label 7, [2,2,0]..[3,3.5,1.2])
+    angles = np.linspace(3.45, 3.95, 12)
+    poses = [syn.look_pose((6.0 + 2.5 * np.cos(a), 5.0 + 2.5 * np.sin(a), 1.5), a, np.radians(10.0)) for a in angles]
+    stamps = [1_000_000_000 + i * 33_333_333 for i in range(12)]
+    frames = hs.render_frames(scene, cam, poses, stamps)
+    target = 7  # first cuboid's label plays the role of the object id in object_image
+    voxel = 0.04
+    mc = capi.default_map_config(voxel_size=voxel, vps=8, trunc=2 * voxel, with_semantics=True, with_tracking=False,
+                                 max_blocks=8192)
+    ic = capi.default_integrator_config(semantic_mode=capi.SEM_BINARY)
+    o, g = both(oracle_lib, product_lib, cam=cam, map_cfg=mc, integ_cfg=ic)
+    bs = voxel * 8
+    # the first cuboid (label 7): [2,2,0]..[3,3.5,1.2]; sits in view of the first poses? choose by data
+    lo = np.floor(np.array([1.5, 1.5, -0.3]) / bs).astype(int)
+    hi = np.floor(np.array([3.5, 4.0, 1.7]) / bs).astype(int)
+    seen = 0
+    for h in (o, g):
+        h.allocate_box(lo, hi)
+    assert o.num_blocks() == g.num_blocks() == int(np.prod(hi - lo + 1))
+    for (d, l), T, st in zip(frames, poses, stamps):
+        seen += int((l == target).sum())
+        so = o.integrate_frame(o.make_frame(d, T, st, object_image=l, target_id=target), allocate_blocks=False)
+        sg = g.integrate_frame(g.make_frame(d, T, st, object_image=l, target_id=target), allocate_blocks=False)
+        assert so.as_dict() == sg.as_dict()
+    hs.assert_blocks_equal(o.export_blocks(), g.export_blocks(), exact_float=True, what="object pre-scan")
+    assert seen > 1000, "the target object must be visible"
+    eo, eg = o.scan_object_confidence(0.5, 3), g.scan_object_confidence(0.5, 3)
+    assert eo == eg and eo > 0
+    hs.assert_blocks_equal(o.export_blocks(), g.export_blocks(), exact_float=True, what="object post-scan")
+
+
+@pytest.mark.parametrize("nshards", [2, 4])
+def test_block_hash_sharding_is_exact(oracle_lib, product_lib, nshards):
+    """SURVEY §4 "fake-shard" mode: S shard handles on one GPU; their union equals the unsharded map."""
+    cam = hs.small_camera(4)
+    frames, poses, stamps = room_frames(cam, 6)
+    o = hs.make_handle(oracle_lib, "ko_", cam=cam)
+    hs.run_fusion(o, frames, poses, stamps)
+    bo = o.export_blocks()
+    parts = []
+    for r in range(nshards):
+        g = hs.make_handle(product_lib, "kb_", cam=cam)
+        g.set_shard(r, nshards)
+        hs.run_fusion(g, frames, poses, stamps)
+        b = g.export_blocks()
+        for idx in b.block_index:
+            assert product_lib.kb_block_owner(int(idx[0]), int(idx[1]), int(idx[2]), nshards) == r
+        parts.append(b)
+    assert sum(p.n for p in parts) == bo.n
+    order = np.lexsort(np.concatenate([p.block_index for p in parts])[:, ::-1].T)
+    def cat(name):
+        return np.concatenate([getattr(p, name) for p in parts])[order]
+    np.testing.assert_array_equal(cat("block_index"), bo.block_index)
+    for name in ("distance", "weight"):
+        np.testing.assert_array_equal(cat(name).view(np.uint32), getattr(bo, name).view(np.uint32))
+    for name in ("last_observed", "semantic_label", "semantic_empty", "block_flags"):
+        np.testing.assert_array_equal(cat(name), getattr(bo, name))
+
+
+def test_device_resident_frames(oracle_lib, product_lib):
+    import torch
+    cam = hs.small_camera(4)
+    frames, poses, stamps = room_frames(cam, 5)
+    o, g = both(oracle_lib, product_lib, cam=cam)
+    hs.run_fusion(o, frames, poses, stamps)
+    for (d, l), T, st in zip(frames, poses, stamps):
+        dd, ll = torch.from_numpy(d).cuda(), torch.from_numpy(l).cuda()
+        torch.cuda.synchronize()
+        g.integrate_frame(g.make_frame(dd, T, st, label=ll, memory=capi.MEM_DEVICE), want_stats=False)
+    g.synchronize()
+    hs.assert_blocks_equal(o.export_blocks(), g.export_blocks(), exact_float=True, what="device frames")
+
+
+def test_capacity_error_is_reported(product_lib):
+    cam = hs.small_camera(4)
+    frames, poses, stamps = room_frames(cam, 1)
+    g = hs.make_handle(product_lib, "kb_", cam=cam, map_cfg=capi.default_map_config(max_blocks=16))
+    with pytest.raises(kb.KbError) as e:
+        hs.run_fusion(g, frames, poses, stamps)
+    assert e.value.status == 3
