@@ -1,0 +1,399 @@
+#!/usr/bin/env python
+"""bench.py — frames/s of the active-window fusion hot path (BASELINE.json metric).
+
+Workload "hall640" (BASELINE config[1]): synthetic 640x480 depth+label stream sweeping hall S2
+ into a 5 cm / 16^3-block map with MLE semantic fusion (L=20) and the tracking layer's
+last_observed written (TSDF + semantic fusion only; K2/K3/M1 off). One lap of the trajectory is
+rendered into HBM up front; a step = `--frames-per-step` consecutive frames, each one call of
+kb_integrate_frame (the C ABI the Khronos adaptor binds) with device-resident images.
+
+  value      whole-job frames/s, inputs already resident in HBM (CUDA events on the launch stream)
+  e2e        same metric with HOST (pinned) images through the same C ABI, H2D inside the timed region
+  roofline   dominant kernel (integrateKernel): algorithmic bytes per launch / mean launch duration
+  cpu_baseline  the oracle port on this box's host cores over a bounded sample of the same stream
+
+`--impl reference` times the CPU oracle port (the reference itself cannot be built here: it needs
+Hydra/spatial_hash/Eigen/OpenCV) on all host threads.
+N > 1 (torchrun): the map shards by block hash, rank 0 broadcasts each step's frames over NCCL and
+every rank integrates only the blocks it owns ("strong" scaling: total work is fixed).
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+L_LABELS = 20
+BYTES_PER_PIXEL_IN = 8  # depth f32 + label i32
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames-per-step", type=int, default=1000)
+    ap.add_argument("--lap-frames", type=int, default=5000, help="frames in one lap of the trajectory (pool in HBM)")
+    ap.add_argument("--max-blocks", type=int, default=90000)
+    ap.add_argument("--cpu-sample-frames", type=int, default=96)
+    ap.add_argument("--e2e-frames", type=int, default=512)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--small", action="store_true", help="tiny configuration for functional checks")
+    return ap.parse_args()
+
+
+def workload(args):
+    from khronos_b200 import synthetic as syn
+    if args.small:
+        cam = syn.make_camera(160, 120, 80.0, 80.0)
+        scene = syn.hall_scene(L_LABELS, size=(20.0, 16.0, 6.0))
+        poses, stamps = syn.sweep_trajectory(args.lap_frames, size=(20.0, 16.0), margin=4.0, lanes=3, yaw_turns=6.0)
+    else:
+        cam = syn.make_camera()
+        scene = syn.hall_scene(L_LABELS)
+        poses, stamps = syn.sweep_trajectory(args.lap_frames)
+    return cam, scene, poses, stamps
+
+
+def algorithmic_bytes(nv, nsem, nblk, pixels, lp=20):
+    """Byte model: per integrated voxel 8 B read + 8 B write of {distance, weight} and a
+    4 B last_observed write; per semantic update Lp*4 B read + write of the likelihood row and a 2 B
+    label read + write; the frame's depth + label images once; 16 B of hash/index per visited block."""
+    return nv * (8 + 8 + 4) + nsem * (2 * 4 * lp + 4) + pixels * BYTES_PER_PIXEL_IN + nblk * 16
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 6:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def map_configs(args):
+    from khronos_b200 import capi
+    mc = capi.default_map_config(voxel_size=0.05, vps=16, trunc=0.15, with_semantics=True, with_tracking=True,
+                                 max_blocks=args.max_blocks if not args.small else 8192,
+                                 max_semantic_blocks=0)
+    ic = capi.default_integrator_config(semantic_mode=capi.SEM_MLE, num_labels=L_LABELS)
+    return mc, ic
+
+
+def run_cpu(args, cam, frames_host, poses, stamps, n_frames, threads=-1):
+    """Times the oracle port on host cores over frames [0, n_frames). Returns (fps, cores, seconds)."""
+    from khronos_b200 import capi
+    lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "liboracle.so"))
+    mc, ic = map_configs(args)
+    ic.num_threads = threads
+    h = capi.MapHandle(lib, "ko_", mc, ic, capi.default_tracking_config(), None)
+    h.set_camera(cam)
+    fr = [h.make_frame(frames_host[0][i], poses[i], stamps[i], label=frames_host[1][i]) for i in range(n_frames)]
+    t0 = time.perf_counter()
+    for f in fr:
+        h.integrate_frame(f, want_stats=False)
+    dt = time.perf_counter() - t0
+    cores = os.cpu_count() if threads <= 0 else threads
+    h.close()
+    return n_frames / dt, cores, dt
+
+
+def main_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port; the real binary is unbuildable
+    here) on all host threads, each step a bounded sample of the same stream."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from khronos_b200 import synthetic as syn
+    cam, scene, poses, stamps = workload(args)
+    per_step = max(4, min(32, args.cpu_sample_frames // 3))
+    n = per_step * (args.steps + args.warmup)
+    stride = max(1, len(poses) // n)
+    sel = [(i * stride) % len(poses) for i in range(n)]
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    d, l = syn.render_stream(scene, cam, [poses[i] for i in sel], [stamps[i] for i in sel], device=dev, dtype=torch.float32)
+    d, l = d.cpu().numpy(), l.cpu().numpy()
+    from khronos_b200 import capi
+    lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "liboracle.so"))
+    mc, ic = map_configs(args)
+    h = capi.MapHandle(lib, "ko_", mc, ic, capi.default_tracking_config(), None)
+    h.set_camera(cam)
+    # stamps must increase along the sampled sequence
+    fr = [h.make_frame(d[k], poses[i], 1_000_000_000 + k * 33_333_333, label=l[k]) for k, i in enumerate(sel)]
+    for f in fr[: per_step * args.warmup]:
+        h.integrate_frame(f, want_stats=False)
+    t0 = time.perf_counter()
+    for f in fr[per_step * args.warmup:]:
+        h.integrate_frame(f, want_stats=False)
+    dt = time.perf_counter() - t0
+    fps = per_step * args.steps / dt
+    out = {
+        "impl": "reference", "metric": "rgbd_frames_per_sec_integrated", "value": fps, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "hall640" if not args.small else "hall160-small", "image": [cam.width, cam.height],
+                   "voxel_size": 0.05, "voxels_per_side": 16, "semantics": "MLE L=20",
+                   "frames_per_step": per_step},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+                         "sample": f"{per_step} frames/step, every {stride}th frame of the lap, oracle port "
+                                   f"(reference needs Hydra/Eigen/OpenCV: unbuildable here)"},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return main_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import khronos_b200 as kb
+    from khronos_b200 import capi, synthetic as syn
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    F, K, Wm = args.frames_per_step, args.steps, args.warmup
+    if args.small:
+        F = min(F, 64)
+        args.lap_frames = min(args.lap_frames, 256)
+
+    cam, scene, poses, stamps = workload(args)
+    lap = len(poses)
+    P = cam.width * cam.height
+    # ---- inputs into HBM (rank 0 renders; N>1: other ranks receive each step's frames by broadcast)
+    t_render = time.perf_counter()
+    if rank == 0:
+        depth, label = syn.render_stream(scene, cam, poses, stamps, device=dev, dtype=torch.float32)
+    else:
+        depth = label = None
+    torch.cuda.synchronize()
+    t_render = time.perf_counter() - t_render
+    if world > 1:
+        rx = [(torch.empty((F, cam.height, cam.width), dtype=torch.float32, device=dev),
+               torch.empty((F, cam.height, cam.width), dtype=torch.int32, device=dev)) for _ in range(2)]
+
+    mc, ic = map_configs(args)
+    h = kb.create_map(mc, ic, capi.default_tracking_config(), None, device=local_rank)
+    h.set_camera(cam)
+    if world > 1:
+        h.set_shard(rank, world)
+    stream = torch.cuda.Stream(device=dev)
+    h.set_stream(stream.cuda_stream)
+
+    def frame_index(step, j):
+        return (step * F + j) % lap
+
+    def stamp_of(step, j):
+        g = step * F + j
+        return 1_000_000_000 + g * 33_333_333
+
+    def make_step_frames(step, dbuf, lbuf, base):
+        """Frame structs of one step pointing into (dbuf, lbuf) at frame offset base+j."""
+        out = []
+        for j in range(F):
+            i = frame_index(step, j)
+            k = i if base is None else base + j
+            f = h.make_frame(dbuf[k].data_ptr(), poses[i], stamp_of(step, j), label=lbuf[k].data_ptr(),
+                             memory=capi.MEM_DEVICE)
+            out.append(f)
+        return out
+
+    integrate = h._fn("integrate_frame")
+    hptr = h._h
+
+    def run_step(step, sample_events=None):
+        if world > 1:
+            db, lb = rx[step % 2]
+            if rank == 0:
+                idx = torch.tensor([frame_index(step, j) for j in range(F)], device=dev)
+                db.copy_(depth.index_select(0, idx))
+                lb.copy_(label.index_select(0, idx))
+            dist.broadcast(db, 0)
+            dist.broadcast(lb, 0)
+            stream.wait_stream(torch.cuda.current_stream())
+            frames = make_step_frames(step, db, lb, 0)
+        else:
+            frames = make_step_frames(step, depth, label, None)
+        with torch.cuda.stream(stream):
+            for j, f in enumerate(frames):
+                if sample_events is not None and j % 16 == 8:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(stream)
+                    st = integrate(hptr, ctypes.byref(f), 1, None)
+                    e1.record(stream)
+                    sample_events.append((e0, e1))
+                else:
+                    st = integrate(hptr, ctypes.byref(f), 1, None)
+                if st != 0:
+                    raise RuntimeError(f"kb_integrate_frame failed: {st}")
+        if world > 1:
+            torch.cuda.current_stream().wait_stream(stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for s in range(Wm):
+        run_step(s)
+    barrier()
+    tot0 = h.get_totals()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    samples = []
+    wall0 = time.perf_counter()
+    ev0.record(stream)
+    for s in range(Wm, Wm + K):
+        run_step(s, samples)
+    ev1.record(stream)
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop() if rank == 0 else None
+    gpu_ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        # the device-timed region excludes nothing: broadcasts run on torch's stream between the
+        # recorded events' stream work, so use the barrier-bracketed wall time, max over ranks
+        t = torch.tensor([wall * 1e3], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        gpu_ms = float(t.item())
+    tot1 = h.get_totals()
+
+    def delta(name):
+        return (getattr(tot1, name) - getattr(tot0, name)) & 0xFFFFFFFF
+
+    n_frames = K * F
+    nv, nsem, nblk = delta("voxels_updated"), delta("voxels_semantic"), delta("blocks_in_frustum")
+    if world > 1:
+        t = torch.tensor([nv, nsem, nblk], device=dev, dtype=torch.float64)
+        dist.all_reduce(t)
+        nv_all, nsem_all, nblk_all = [float(x) for x in t.tolist()]
+    else:
+        nv_all, nsem_all, nblk_all = float(nv), float(nsem), float(nblk)
+    fps = n_frames / (gpu_ms * 1e-3)
+    kern_ms = [a.elapsed_time(b) for a, b in samples]
+    kern_us = float(np.mean(kern_ms) * 1e3) if kern_ms else None
+    bytes_per_launch = algorithmic_bytes(nv, nsem, nblk, n_frames * P) / n_frames  # this rank's launches
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = bytes_per_launch / (kern_us * 1e-6) / 1e9 if kern_us else None
+
+    # ---- e2e: host (pinned) images through the same C ABI, H2D inside the timed region (rank-local)
+    e2e = None
+    if not args.no_e2e and world == 1:
+        n_e = min(args.e2e_frames, lap)
+        hd = torch.empty((n_e, cam.height, cam.width), dtype=torch.float32, pin_memory=True)
+        hl = torch.empty((n_e, cam.height, cam.width), dtype=torch.int32, pin_memory=True)
+        base_step = Wm + K
+        idx = [frame_index(base_step, j) for j in range(n_e)]
+        hd.copy_(depth[idx[0]:idx[0] + n_e] if idx[-1] == idx[0] + n_e - 1 else depth[torch.tensor(idx, device=dev)])
+        hl.copy_(label[idx[0]:idx[0] + n_e] if idx[-1] == idx[0] + n_e - 1 else label[torch.tensor(idx, device=dev)])
+        torch.cuda.synchronize()
+        frames = [h.make_frame(hd[j].data_ptr(), poses[idx[j]], stamp_of(base_step, j), label=hl[j].data_ptr(),
+                               memory=capi.MEM_HOST) for j in range(n_e)]
+        stats = capi.FrameStats()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for j, f in enumerate(frames):
+            last = j == n_e - 1
+            st = integrate(hptr, ctypes.byref(f), 1, ctypes.byref(stats) if last else None)  # D2H of the result
+            if st != 0:
+                raise RuntimeError(f"kb_integrate_frame (host) failed: {st}")
+        h.synchronize()
+        dt = time.perf_counter() - t0
+        e2e = {"value": n_e / dt, "unit": "frames/s", "h2d_bytes_per_step": n_e * P * BYTES_PER_PIXEL_IN,
+               "d2h_bytes_per_step": ctypes.sizeof(capi.FrameStats) + 64, "frames_per_step": n_e,
+               "note": "host pinned depth+label -> kb_integrate_frame(KB_MEM_HOST); stats read back at step end"}
+
+    # ---- CPU baseline on a bounded sample of the same stream (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        n_c = min(args.cpu_sample_frames, lap)
+        fh = (depth[:n_c].cpu().numpy(), label[:n_c].cpu().numpy())
+        cfps, cores, secs = run_cpu(args, cam, fh, poses, stamps, n_c)
+        cpu = {"value": cfps, "unit": "frames/s", "cores": cores, "kind": "port",
+               "sample": f"first {n_c} frames of the lap into an empty map, oracle port, {secs:.1f}s"}
+
+    if rank == 0:
+        total = h.get_totals()
+        out = {
+            "metric": "rgbd_frames_per_sec_integrated", "value": fps, "unit": "frames/s", "n_gpus": world,
+            "steps": K, "warmup": Wm, "ms_per_step": gpu_ms / K, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "hall640" if not args.small else "hall160-small",
+                       "image": [cam.width, cam.height], "voxel_size": 0.05, "voxels_per_side": 16,
+                       "truncation": 0.15, "semantics": f"MLE L={L_LABELS}", "frames_per_step": F,
+                       "lap_frames": lap, "live_blocks_rank0": total.total_blocks,
+                       "l2": "inputs larger than L2: each step streams %.1f GB of frames" % (F * P * 8 / 1e9),
+                       "parallelism": "block-hash shard x%d, NCCL frame broadcast" % world if world > 1 else "single GPU",
+                       "render_s": round(t_render, 1)},
+            "per_frame": {"voxels_updated": nv_all / n_frames, "voxels_semantic": nsem_all / n_frames,
+                          "blocks_visited": nblk_all / n_frames},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "kernel": "integrateKernel<16>", "launch_us": kern_us,
+                         "algorithmic_bytes_per_launch": bytes_per_launch,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)"},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": n_frames, "clocks": clocks,
+            "wall_s_timed": wall,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

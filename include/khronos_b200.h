@@ -165,6 +165,12 @@ int kb_block_owner(int32_t bx, int32_t by, int32_t bz, int nranks);
 int kb_integrate_frame(kb_handle* h, const kb_frame* frame, int allocate_blocks,
                        kb_frame_stats* stats);
 
+/* Cumulative counters since kb_create (same fields as kb_frame_stats, summed over all frames;
+ * total_blocks = live blocks now; the 32-bit sums wrap modulo 2^32 — difference them as uint32).
+ * One 64 B device->host read + stream sync. Used for metrics
+ * (SURVEY.md §5 "C-ABI returns counters") and for the bench's byte model. */
+int kb_get_totals(kb_handle* h, kb_frame_stats* totals);
+
 /* K2+K3. Replaces TrackingIntegrator::updateBlocks (tracking_integrator.cpp:71-104). */
 int kb_update_tracking(kb_handle* h, uint64_t stamp_ns);
 

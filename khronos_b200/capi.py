@@ -244,6 +244,11 @@ class MapHandle:
                                                 C.byref(stats) if want_stats else None))
         return stats if want_stats else None
 
+    def get_totals(self) -> FrameStats:
+        t = FrameStats()
+        self._check(self._fn("get_totals")(self._h, C.byref(t)))
+        return t
+
     def update_tracking(self, stamp_ns: int):
         self._check(self._fn("update_tracking")(self._h, C.c_uint64(int(stamp_ns))))
 

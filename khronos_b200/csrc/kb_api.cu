@@ -383,18 +383,35 @@ int kb_integrate_frame(kb_handle* h, const kb_frame* f, int allocate_blocks, kb_
     if ((st = readCounters(h)) != KB_OK) return st;
     const int* c1 = h->h_ctr;
     const int* c0 = h->prev_ctr;
-    stats->blocks_in_frustum = c1[kCtrFrustum] - c0[kCtrFrustum];
-    stats->blocks_allocated = c1[kCtrAllocated] - c0[kCtrAllocated];
-    stats->blocks_updated = c1[kCtrBlocksUpdated] - c0[kCtrBlocksUpdated];
-    stats->voxels_updated = c1[kCtrVoxelsUpdated] - c0[kCtrVoxelsUpdated];
-    stats->voxels_in_band = c1[kCtrVoxelsBand] - c0[kCtrVoxelsBand];
-    stats->voxels_semantic = c1[kCtrVoxelsSemantic] - c0[kCtrVoxelsSemantic];
+    stats->blocks_in_frustum = static_cast<int32_t>(static_cast<uint32_t>(c1[kCtrFrustum]) - static_cast<uint32_t>(c0[kCtrFrustum]));
+    stats->blocks_allocated = static_cast<int32_t>(static_cast<uint32_t>(c1[kCtrAllocated]) - static_cast<uint32_t>(c0[kCtrAllocated]));
+    stats->blocks_updated = static_cast<int32_t>(static_cast<uint32_t>(c1[kCtrBlocksUpdated]) - static_cast<uint32_t>(c0[kCtrBlocksUpdated]));
+    stats->voxels_updated = static_cast<int32_t>(static_cast<uint32_t>(c1[kCtrVoxelsUpdated]) - static_cast<uint32_t>(c0[kCtrVoxelsUpdated]));
+    stats->voxels_in_band = static_cast<int32_t>(static_cast<uint32_t>(c1[kCtrVoxelsBand]) - static_cast<uint32_t>(c0[kCtrVoxelsBand]));
+    stats->voxels_semantic = static_cast<int32_t>(static_cast<uint32_t>(c1[kCtrVoxelsSemantic]) - static_cast<uint32_t>(c0[kCtrVoxelsSemantic]));
     stats->total_blocks = c1[kCtrLiveBlocks];
     stats->capacity_exceeded = c1[kCtrCapacityExceeded];
     std::memcpy(h->prev_ctr, h->h_ctr, sizeof(h->prev_ctr));
     h->ctr_dirty = false;
     if (c1[kCtrCapacityExceeded]) return fail(h, KB_ERR_CAPACITY, "block / semantic pool exhausted");
   }
+  return KB_OK;
+}
+
+int kb_get_totals(kb_handle* h, kb_frame_stats* t) {
+  if (!h || !t) return KB_ERR_INVALID;
+  KB_CUDA(h, cudaSetDevice(h->device));
+  int st = readCounters(h);
+  if (st != KB_OK) return st;
+  const int* c = h->h_ctr;
+  t->blocks_in_frustum = c[kCtrFrustum];
+  t->blocks_allocated = c[kCtrAllocated];
+  t->blocks_updated = c[kCtrBlocksUpdated];
+  t->voxels_updated = c[kCtrVoxelsUpdated];
+  t->voxels_in_band = c[kCtrVoxelsBand];
+  t->voxels_semantic = c[kCtrVoxelsSemantic];
+  t->total_blocks = c[kCtrLiveBlocks];
+  t->capacity_exceeded = c[kCtrCapacityExceeded];
   return KB_OK;
 }
 

@@ -112,7 +112,8 @@ Block* Oracle::allocateBlock(const Idx3& idx) {
   if (L_ > 0) {
     b->semantic_label.assign(V_, 0);
     b->semantic_empty.assign(V_, 1);
-    b->likelihoods.assign(static_cast<size_t>(V_) * L_, 0.f);
+    // likelihoods are sized on the block's first semantic update (hydra sizes each voxel's VectorXf
+    // on its first update, App. A.8) — keeps block allocation cheap like the reference.
   }
   Block* raw = b.get();
   blocks_.emplace(idx, std::move(b));
@@ -358,6 +359,7 @@ void Oracle::updateBlock(Block& b, const kb_frame& f, const float R[9], const fl
     if (!in_band) continue;
     ++n_band;
     if (have_label && label < static_cast<uint32_t>(L_)) {  // isValidLabel
+      if (b.likelihoods.empty()) b.likelihoods.assign(static_cast<size_t>(V_) * L_, 0.f);
       float* lik = &b.likelihoods[static_cast<size_t>(lin) * L_];
       if (b.semantic_empty[lin]) {
         b.semantic_empty[lin] = 0;
@@ -680,7 +682,7 @@ int Oracle::scanObjectConfidence(float min_confidence, int min_observations) {
     for (int lin = 0; lin < V_; ++lin) {
       if (b.distance[lin] > 0.f) continue;
       float conf;
-      if (b.semantic_empty[lin]) {
+      if (b.semantic_empty[lin] || b.likelihoods.empty()) {
         conf = 0.f;
       } else {
         const float total = b.likelihoods[static_cast<size_t>(lin) * L_] +

@@ -10,6 +10,7 @@ using ko::Oracle;
 struct ko_handle {
   Oracle* o;
   std::string last_error;
+  kb_frame_stats totals{};
 };
 
 static int fail(ko_handle* h, int code) {
@@ -23,7 +24,7 @@ int ko_create(const kb_map_config* map, const kb_integrator_config* integ,
               const kb_tracking_config* trk, const kb_motion_config* mot, int /*device*/,
               ko_handle** out) {
   if (!map || !integ || !out) return KB_ERR_INVALID;
-  auto* h = new ko_handle{new Oracle(*map, *integ, trk, mot), ""};
+  auto* h = new ko_handle{new Oracle(*map, *integ, trk, mot), "", {}};
   if (!h->o->ok()) {
     delete h->o;
     delete h;
@@ -53,8 +54,23 @@ int ko_set_camera(ko_handle* h, const kb_camera* cam) {
 
 int ko_integrate_frame(ko_handle* h, const kb_frame* f, int allocate_blocks, kb_frame_stats* stats) {
   if (!h || !f || !f->depth) return KB_ERR_INVALID;
-  h->o->integrateFrame(*f, allocate_blocks != 0, stats);
+  kb_frame_stats local{};
+  h->o->integrateFrame(*f, allocate_blocks != 0, &local);
+  h->totals.blocks_in_frustum += local.blocks_in_frustum;
+  h->totals.blocks_allocated += local.blocks_allocated;
+  h->totals.blocks_updated += local.blocks_updated;
+  h->totals.voxels_updated += local.voxels_updated;
+  h->totals.voxels_in_band += local.voxels_in_band;
+  h->totals.voxels_semantic += local.voxels_semantic;
+  if (stats) *stats = local;
   return h->o->ok() ? KB_OK : fail(h, KB_ERR_INVALID);
+}
+
+int ko_get_totals(ko_handle* h, kb_frame_stats* t) {
+  if (!h || !t) return KB_ERR_INVALID;
+  *t = h->totals;
+  t->total_blocks = static_cast<int32_t>(h->o->sortedBlocks(KB_EXPORT_ALL).size());
+  return KB_OK;
 }
 
 int ko_update_tracking(ko_handle* h, uint64_t stamp_ns) {
@@ -178,7 +194,10 @@ int ko_export_blocks(ko_handle* h, int which, int32_t max_blocks, kb_block_expor
     const bool sem = L > 0;
     if (out->semantic_label) sem ? (void)std::memcpy(out->semantic_label + i * V, b.semantic_label.data(), V * 4) : (void)std::memset(out->semantic_label + i * V, 0, V * 4);
     if (out->semantic_empty) sem ? (void)std::memcpy(out->semantic_empty + i * V, b.semantic_empty.data(), V) : (void)std::memset(out->semantic_empty + i * V, 1, V);
-    if (out->semantic_likelihoods && sem) std::memcpy(out->semantic_likelihoods + i * V * L, b.likelihoods.data(), V * L * 4);
+    if (out->semantic_likelihoods && sem) {
+      if (b.likelihoods.empty()) std::memset(out->semantic_likelihoods + i * V * L, 0, V * L * 4);
+      else std::memcpy(out->semantic_likelihoods + i * V * L, b.likelihoods.data(), V * L * 4);
+    }
   }
   if (n_written) *n_written = n;
   return KB_OK;
