@@ -1,0 +1,264 @@
+// Host-side C++ mirror of the reference's integrator / plugin interfaces over the C ABI
+// (include/khronos_b200.h). Header-only; compiles against real Hydra/Khronos headers with
+// -DKB_HAVE_HYDRA, or against hydra_stub.h (this container: no Hydra/Eigen/OpenCV/ROS).
+//
+// Class <-> reference interface it stands in for (paths relative to the Khronos checkout):
+//   GpuVolumetricMap          hydra::VolumetricMap as owned by ActiveWindow (active_window.h:166-170)
+//   GpuProjectiveIntegrator   hydra::ProjectiveIntegrator::updateMap(data, map, allocate, mask)
+//                             (call sites active_window.cpp:210, mesh_object_extractor.cpp:242)
+//   GpuObjectIntegrator       khronos::ObjectIntegrator (integration/object_integrator.h:51-74)
+//   GpuTrackingIntegrator     khronos::TrackingIntegrator::updateBlocks / resetInactive
+//                             (integration/tracking_integrator.h:96,102)
+//   GpuFreeSpaceMotionDetector khronos::FreeSpaceMotionDetector::processInput
+//                             (motion_detection/free_space_motion_detector.h:121; base motion_detector.h:62)
+//   mirrorBack                repopulates a host hydra::VolumetricMap for MeshIntegrator::generateMesh /
+//                             cloneUpdated (active_window.cpp:223,229)
+// Error behaviour follows the reference: configuration errors throw at construction
+// (config::checkValid), the per-frame path never throws — failures are logged and the frame skipped.
+#pragma once
+
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/khronos_b200.h"
+
+#ifdef KB_HAVE_HYDRA
+#include <hydra/input/input_data.h>
+#include <hydra/reconstruction/volumetric_map.h>
+#include <khronos/active_window/data/frame_data.h>
+#else
+#include "hydra_stub.h"
+namespace khronos {
+struct Pixel { int u, v; };
+struct MeasurementCluster {  // khronos/include/khronos/active_window/data/measurement_clusters.h:63-81
+  std::vector<Pixel> pixels;
+  float bbox_min[3], bbox_max[3];
+  std::vector<std::array<int64_t, 3>> voxels;
+  int id = 0;
+};
+struct FrameData {  // khronos/include/khronos/active_window/data/frame_data.h:59-83
+  hydra::InputData input;
+  std::vector<MeasurementCluster> dynamic_clusters;
+  cv::Mat dynamic_image;  // CV_32SC1
+  std::vector<MeasurementCluster> semantic_clusters;
+  cv::Mat object_image;   // CV_32SC1
+};
+}  // namespace khronos
+#endif
+
+namespace khronos_b200 {
+
+inline void check(int status, kb_handle* h, const char* what) {
+  if (status != KB_OK) throw std::runtime_error(std::string(what) + ": " + (h ? kb_last_error(h) : "kb error"));
+}
+
+// One GPU-resident map + its integrators (handle-based: extraction workers each own one).
+class GpuVolumetricMap {
+ public:
+  GpuVolumetricMap(const hydra::VolumetricMap::Config& map, const kb_integrator_config& integ,
+                   const kb_tracking_config* tracking, const kb_motion_config* motion, int max_blocks,
+                   int device = 0)
+      : config(map) {
+    kb_map_config mc{};
+    mc.voxel_size = map.voxel_size;
+    mc.voxels_per_side = map.voxels_per_side;
+    mc.truncation_distance = map.truncation_distance;
+    mc.with_semantics = map.with_semantics;
+    mc.with_tracking = map.with_tracking;
+    mc.max_blocks = max_blocks;
+    num_labels_ = !map.with_semantics ? 0 : integ.semantic_mode == KB_SEMANTICS_MLE ? integ.num_labels
+                  : integ.semantic_mode == KB_SEMANTICS_BINARY ? 2 : 0;
+    const int st = kb_create(&mc, &integ, tracking, motion, device, &h_);
+    if (st != KB_OK) throw std::runtime_error("kb_create failed (status " + std::to_string(st) + "): no GPU or invalid config");
+  }
+  ~GpuVolumetricMap() { kb_destroy(h_); }
+  GpuVolumetricMap(const GpuVolumetricMap&) = delete;
+  GpuVolumetricMap& operator=(const GpuVolumetricMap&) = delete;
+
+  kb_handle* handle() const { return h_; }
+  int numLabels() const { return num_labels_; }
+  void setSensor(const hydra::Camera& c) {
+    kb_camera cam{c.width, c.height, c.fx, c.fy, c.cx, c.cy, c.min_range, c.max_range};
+    check(kb_set_camera(h_, &cam), h_, "kb_set_camera");
+  }
+  const hydra::VolumetricMap::Config config;
+
+ private:
+  kb_handle* h_ = nullptr;
+  int num_labels_ = 0;
+};
+
+inline kb_frame makeFrame(const hydra::InputData& data, const cv::Mat* mask, const cv::Mat* object_image,
+                          int target_id) {
+  kb_frame f{};
+  f.depth = data.range_image.empty() ? data.depth_image.ptr<float>() : data.range_image.ptr<float>();
+  f.label = data.label_image.empty() ? nullptr : data.label_image.ptr<int32_t>();
+  f.mask = (mask && !mask->empty()) ? mask->ptr<int32_t>() : nullptr;
+  f.object_image = (object_image && !object_image->empty()) ? object_image->ptr<int32_t>() : nullptr;
+  f.color = nullptr;
+  f.vertex_world = data.vertex_map.empty() ? nullptr : data.vertex_map.ptr<float>();
+  const auto T = data.getSensorPose();
+#ifdef KB_HAVE_HYDRA
+  for (int r = 0; r < 4; ++r)
+    for (int c = 0; c < 4; ++c) f.world_T_sensor[r * 4 + c] = T.matrix()(r, c);
+#else
+  std::memcpy(f.world_T_sensor, T.m, sizeof(T.m));
+#endif
+  f.stamp_ns = data.timestamp_ns;
+  f.object_target_id = target_id;
+  f.memory = KB_MEM_HOST;
+  return f;
+}
+
+// hydra::ProjectiveIntegrator stand-in. dynamic_image may be passed directly as the mask: the kernel
+// tests "!= 0", which is hydra::maskNonZero fused (active_window.cpp:209).
+class GpuProjectiveIntegrator {
+ public:
+  virtual ~GpuProjectiveIntegrator() = default;
+  virtual void updateMap(const hydra::InputData& data, GpuVolumetricMap& map, bool allocate_blocks = true,
+                         const cv::Mat& integration_mask = cv::Mat()) const {
+    kb_frame f = makeFrame(data, &integration_mask, objectImage(), targetId());
+    map.setSensor(data.getSensor());
+    const int st = kb_integrate_frame(map.handle(), &f, allocate_blocks ? 1 : 0, nullptr);
+    if (st != KB_OK) std::fprintf(stderr, "[GpuProjectiveIntegrator] frame skipped: %s\n", kb_last_error(map.handle()));
+  }
+
+ protected:
+  virtual const cv::Mat* objectImage() const { return nullptr; }
+  virtual int targetId() const { return 0; }
+};
+
+// khronos::ObjectIntegrator: binary semantics with label = (object_image == target id). The map
+// handed to updateMap must have been created with KB_SEMANTICS_BINARY (forceBinaryIntegrator,
+// object_integrator.cpp:44-48).
+class GpuObjectIntegrator : public GpuProjectiveIntegrator {
+ public:
+  void setFrameData(khronos::FrameData* frame_data, int target_object_id) {
+    current_data_ = frame_data;
+    current_object_id_ = target_object_id;
+  }
+
+ protected:
+  const cv::Mat* objectImage() const override { return current_data_ ? &current_data_->object_image : nullptr; }
+  int targetId() const override { return current_object_id_; }
+
+ private:
+  khronos::FrameData* current_data_ = nullptr;
+  int current_object_id_ = -1;
+};
+
+class GpuTrackingIntegrator {
+ public:
+  void updateBlocks(const khronos::FrameData& data, GpuVolumetricMap& map) const {
+    const int st = kb_update_tracking(map.handle(), data.input.timestamp_ns);
+    if (st != KB_OK) std::fprintf(stderr, "[GpuTrackingIntegrator] %s\n", kb_last_error(map.handle()));
+  }
+  void resetInactive(GpuVolumetricMap& map, hydra::BlockIndices* removed = nullptr) const {
+    int32_t n = 0;
+    std::vector<int32_t> buf(static_cast<size_t>(3) * (1 << 20));
+    if (kb_reset_inactive(map.handle(), buf.data(), 1 << 20, &n) != KB_OK) return;
+    if (removed)
+      for (int i = 0; i < n; ++i) removed->push_back({buf[3 * i], buf[3 * i + 1], buf[3 * i + 2]});
+  }
+};
+
+// khronos::MotionDetector plugin (type string "GpuFreeSpaceMotionDetector" when registered with
+// config_utilities). Fills dynamic_image (CV_32SC1) and dynamic_clusters.
+class GpuFreeSpaceMotionDetector {
+ public:
+  void processInput(GpuVolumetricMap& map, khronos::FrameData& data) const {
+    kb_frame f = makeFrame(data.input, nullptr, nullptr, 0);
+    map.setSensor(data.input.getSensor());
+    int32_t n_seeds = 0, n_clusters = 0;
+    if (data.dynamic_image.empty()) data.dynamic_image = cv::Mat(data.input.depth_image.rows, data.input.depth_image.cols, 4);
+    if (kb_detect_motion(map.handle(), &f, data.dynamic_image.ptr<int32_t>(), &n_seeds, &n_clusters) != KB_OK) {
+      std::fprintf(stderr, "[GpuFreeSpaceMotionDetector] %s\n", kb_last_error(map.handle()));
+      return;
+    }
+    data.dynamic_clusters.clear();
+    if (n_clusters == 0) return;
+    int32_t tp = 0, tv = 0;
+    kb_get_motion_clusters(map.handle(), nullptr, nullptr, nullptr, nullptr, &tp, &tv);
+    std::vector<int32_t> counts(2 * n_clusters), px(2 * static_cast<size_t>(tp));
+    std::vector<int64_t> vx(3 * static_cast<size_t>(tv));
+    std::vector<float> bb(6 * n_clusters);
+    kb_get_motion_clusters(map.handle(), counts.data(), px.data(), vx.data(), bb.data(), &tp, &tv);
+    size_t po = 0, vo = 0;
+    for (int c = 0; c < n_clusters; ++c) {
+      khronos::MeasurementCluster cl;
+      cl.id = c + 1 < 255 ? c + 1 : 255;
+      for (int i = 0; i < counts[2 * c]; ++i, ++po) cl.pixels.push_back({px[2 * po], px[2 * po + 1]});
+#ifndef KB_HAVE_HYDRA
+      for (int i = 0; i < counts[2 * c + 1]; ++i, ++vo) cl.voxels.push_back({vx[3 * vo], vx[3 * vo + 1], vx[3 * vo + 2]});
+      std::memcpy(cl.bbox_min, &bb[6 * c], 12);
+      std::memcpy(cl.bbox_max, &bb[6 * c + 3], 12);
+#else
+      for (int i = 0; i < counts[2 * c + 1]; ++i, ++vo) cl.voxels.emplace(vx[3 * vo], vx[3 * vo + 1], vx[3 * vo + 2]);
+      cl.bounding_box = khronos::BoundingBox(khronos::Point(bb[6 * c], bb[6 * c + 1], bb[6 * c + 2]),
+                                             khronos::Point(bb[6 * c + 3], bb[6 * c + 4], bb[6 * c + 5]));
+#endif
+      data.dynamic_clusters.push_back(std::move(cl));
+    }
+  }
+};
+
+// K4 wrapper for MeshObjectExtractor::extractStaticObject (mesh_object_extractor.cpp:246-264).
+inline int eraseLowConfidence(GpuVolumetricMap& map, float min_confidence, int min_observations) {
+  int32_t n = 0;
+  check(kb_scan_object_confidence(map.handle(), min_confidence, min_observations, &n), map.handle(), "kb_scan_object_confidence");
+  return n;
+}
+
+#ifndef KB_HAVE_HYDRA
+// Repopulates the host map from the device (updated blocks only at output ticks, everything for
+// parity dumps). With real Hydra the same loop writes through TsdfLayer::allocateBlock / getVoxel.
+inline void mirrorBack(GpuVolumetricMap& gmap, hydra::VolumetricMap& host, bool updated_only) {
+  kb_handle* h = gmap.handle();
+  int32_t n = 0;
+  const int which = updated_only ? KB_EXPORT_UPDATED : KB_EXPORT_ALL;
+  check(kb_num_blocks(h, which, &n), h, "kb_num_blocks");
+  if (n == 0) return;
+  const size_t V = host.numVoxels(), L = static_cast<size_t>(gmap.numLabels());
+  std::vector<int32_t> index(3 * static_cast<size_t>(n));
+  std::vector<uint8_t> flags(n), ef(n * V), ac(n * V), tr(n * V), se(n * V);
+  std::vector<float> dist(n * V), weight(n * V), lik(n * V * L);
+  std::vector<uint64_t> lo(n * V), lc(n * V);
+  std::vector<uint32_t> sl(n * V);
+  kb_block_export ex{};
+  ex.block_index = index.data(); ex.block_flags = flags.data(); ex.distance = dist.data(); ex.weight = weight.data();
+  ex.last_observed = lo.data(); ex.last_occupied = lc.data(); ex.ever_free = ef.data(); ex.active = ac.data();
+  ex.to_remove = tr.data(); ex.semantic_label = sl.data(); ex.semantic_empty = se.data();
+  ex.semantic_likelihoods = L ? lik.data() : nullptr;
+  int32_t nw = 0;
+  check(kb_export_blocks(h, which, n, &ex, &nw), h, "kb_export_blocks");
+  for (int b = 0; b < nw; ++b) {
+    const hydra::BlockIndex bi{index[3 * b], index[3 * b + 1], index[3 * b + 2]};
+    auto tb = host.getTsdfLayer().allocateBlock(bi, V);
+    tb->updated = flags[b] & KB_FLAG_UPDATED; tb->mesh_updated = flags[b] & KB_FLAG_MESH_UPDATED;
+    tb->esdf_updated = flags[b] & KB_FLAG_ESDF_UPDATED; tb->tracking_updated = flags[b] & KB_FLAG_TRACKING_UPDATED;
+    for (size_t i = 0; i < V; ++i) { tb->voxels[i].distance = dist[b * V + i]; tb->voxels[i].weight = weight[b * V + i]; }
+    if (auto* tl = host.getTrackingLayer()) {
+      auto kb_ = tl->allocateBlock(bi, V);
+      kb_->has_active_data = flags[b] & KB_FLAG_HAS_ACTIVE_DATA;
+      for (size_t i = 0; i < V; ++i) {
+        auto& v = kb_->voxels[i];
+        v.last_observed = lo[b * V + i]; v.last_occupied = lc[b * V + i];
+        v.ever_free = ef[b * V + i]; v.active = ac[b * V + i]; v.to_remove = tr[b * V + i];
+      }
+    }
+    if (auto* slayer = host.getSemanticLayer()) {
+      auto sb = slayer->allocateBlock(bi, V);
+      for (size_t i = 0; i < V; ++i) {
+        auto& v = sb->voxels[i];
+        v.empty = se[b * V + i]; v.semantic_label = sl[b * V + i];
+        if (!v.empty) v.semantic_likelihoods.assign(lik.begin() + (b * V + i) * L, lik.begin() + (b * V + i + 1) * L);
+      }
+    }
+  }
+}
+#endif
+
+}  // namespace khronos_b200

@@ -1,0 +1,48 @@
+// Compile-and-link check of the host adaptor against the stub Hydra types. With a GPU present it also
+// runs one flat-wall frame through GpuProjectiveIntegrator + GpuTrackingIntegrator + mirrorBack and
+// prints a few voxel values that tests/test_host_adaptor.py compares with the oracle.
+#include <cstdio>
+#include <cstdlib>
+
+#include "../../khronos_b200/host/khronos_gpu_adaptor.h"
+
+int main(int argc, char** argv) {
+  using namespace khronos_b200;
+  hydra::VolumetricMap::Config mc;
+  mc.voxel_size = 0.1f; mc.voxels_per_side = 8; mc.truncation_distance = 0.3f;
+  mc.with_semantics = true; mc.with_tracking = true;
+  kb_integrator_config ic{};
+  ic.use_weight_dropoff = 1; ic.weight_dropoff_epsilon = -1.f; ic.max_weight = 1e5f;
+  ic.interpolation_method = KB_INTERP_NEAREST; ic.adaptive_max_depth_difference = 0.2f;
+  ic.semantic_mode = KB_SEMANTICS_MLE; ic.num_labels = 5; ic.label_confidence = 0.9f;
+  kb_tracking_config tc{1.f, 1.f, -1.5f, 18, 3.f, 1};
+  kb_motion_config mo{26, 0, 1000000, 1.f, 10000.f, -10000.f, 1};
+  khronos::FrameData frame;
+  auto& in = frame.input;
+  in.sensor = hydra::Camera{64, 48, 32.f, 32.f, 31.5f, 23.5f, 0.1f, 3.f};
+  in.timestamp_ns = 1000000000ull;
+  in.depth_image = cv::Mat(48, 64, 4);
+  in.range_image = cv::Mat(48, 64, 4);
+  in.label_image = cv::Mat(48, 64, 4);
+  for (int i = 0; i < 48 * 64; ++i) { in.depth_image.ptr<float>()[i] = 2.f; in.range_image.ptr<float>()[i] = 2.f; in.label_image.ptr<int32_t>()[i] = 3; }
+  try {
+    GpuVolumetricMap gmap(mc, ic, &tc, &mo, 4096);
+    GpuProjectiveIntegrator integrator;
+    GpuTrackingIntegrator tracking;
+    GpuFreeSpaceMotionDetector detector;
+    detector.processInput(gmap, frame);
+    integrator.updateMap(frame.input, gmap, true, frame.dynamic_image);
+    tracking.updateBlocks(frame, gmap);
+    hydra::VolumetricMap host(mc);
+    mirrorBack(gmap, host, false);
+    auto blk = host.getTsdfLayer().getBlockPtr({0, 0, 2});
+    if (!blk) { std::printf("missing block\n"); return 2; }
+    const auto& v = blk->getVoxel(0 + 8 * (0 + 8 * 3));
+    std::printf("blocks=%zu distance=%.9g weight=%.9g label=%u\n", host.getTsdfLayer().numBlocks(), v.distance, v.weight,
+                host.getSemanticLayer()->getBlockPtr({0, 0, 2})->getVoxel(0 + 8 * (0 + 8 * 3)).semantic_label);
+  } catch (const std::exception& e) {
+    std::printf("no-gpu: %s\n", e.what());
+    return argc > 1 ? 1 : 0;  // pass any argument to require a GPU
+  }
+  return 0;
+}
