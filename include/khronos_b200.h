@@ -165,6 +165,18 @@ int kb_block_owner(int32_t bx, int32_t by, int32_t bz, int nranks);
 int kb_integrate_frame(kb_handle* h, const kb_frame* frame, int allocate_blocks,
                        kb_frame_stats* stats);
 
+/* Batched K0+K1 for streams that are available ahead of time — replay / benchmarking and the object
+ * extractor's loop "for each semantic frame: integrator.updateMap(...)" (mesh_object_extractor.cpp
+ * :239-243). Results are identical to calling kb_integrate_frame on each frame in order; internally up
+ * to 32 frames are fused per kernel launch with the voxel state held in registers. stats (optional)
+ * receives the sums over the n frames. */
+int kb_integrate_frames(kb_handle* h, const kb_frame* frames, int32_t n_frames, int allocate_blocks,
+                        kb_frame_stats* stats);
+
+/* Enables (default) / disables the conservative per-(block, frame) depth culling. Results do not
+ * depend on this switch; it exists so tests can prove that. */
+int kb_set_culling(kb_handle* h, int enabled);
+
 /* Cumulative counters since kb_create (same fields as kb_frame_stats, summed over all frames;
  * total_blocks = live blocks now; the 32-bit sums wrap modulo 2^32 — difference them as uint32).
  * One 64 B device->host read + stream sync. Used for metrics

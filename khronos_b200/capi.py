@@ -244,6 +244,18 @@ class MapHandle:
                                                 C.byref(stats) if want_stats else None))
         return stats if want_stats else None
 
+    def integrate_frames(self, frames, allocate_blocks=True, want_stats=True):
+        """kb_integrate_frames: identical to integrating the frames one by one, fused on the GPU."""
+        arr = (Frame * len(frames))(*frames)
+        arr._keep = frames
+        stats = FrameStats()
+        self._check(self._fn("integrate_frames")(self._h, arr, len(frames), int(allocate_blocks),
+                                                 C.byref(stats) if want_stats else None))
+        return stats if want_stats else None
+
+    def set_culling(self, enabled: bool):
+        self._check(self._fn("set_culling")(self._h, int(enabled)))
+
     def get_totals(self) -> FrameStats:
         t = FrameStats()
         self._check(self._fn("get_totals")(self._h, C.byref(t)))

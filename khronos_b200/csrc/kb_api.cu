@@ -2,6 +2,7 @@
 // staging, stamp <-> frame-index bookkeeping, export. Host code only; no CPU compute fallback exists:
 // every entry point that touches voxels launches a kernel, and kb_create refuses to run without a GPU.
 #include <algorithm>
+#include <climits>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -30,13 +31,29 @@ struct kb_handle {
   float block_size = 0, mle_diag = 0, mle_off = 0, mle_init = 0;
   unsigned long long blocked_mask = 0;
   std::vector<uint64_t> stamps;  // frame index -> stamp; [0] = 0 ("never")
-  // host frame staging (device copies of host images)
+  // host frame staging: 2 sets x kMaxBatch frames (device copies of host images), filled on the copy
+  // stream so that the H2D of batch i+1 overlaps the kernels of batch i
   float* stg_depth = nullptr;
   int* stg_label = nullptr;
   int* stg_mask = nullptr;
   int* stg_object = nullptr;
   float* stg_vertex = nullptr;
-  size_t stg_pixels = 0;
+  float* mot_depth = nullptr;
+  size_t stg_pixels = 0, mot_pixels = 0;
+  int stg_set = 0;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t stg_ready[2] = {nullptr, nullptr}, stg_consumed[2] = {nullptr, nullptr};
+  // batched integration
+  BatchParams batch{};
+  float* tile_max = nullptr;
+  int* work_slots = nullptr;
+  uint32_t* work_masks = nullptr;
+  uint32_t* work_upd = nullptr;
+  int parity = 0;
+  bool cull = true;
+  int fuse_grid = 0;
+  bool hwm_dirty = true;
+  int hwm_cached = 0;
   // counters
   int* h_ctr = nullptr;  // pinned mirror
   int prev_ctr[kNumCounters] = {0};
@@ -81,15 +98,23 @@ cudaError_t devAlloc(T** p, size_t n, int fill_byte) {
 int ensureStaging(kb_handle* h, size_t pixels) {
   if (h->stg_pixels >= pixels) return KB_OK;
   cudaFree(h->stg_depth); cudaFree(h->stg_label); cudaFree(h->stg_mask); cudaFree(h->stg_object);
-  cudaFree(h->stg_vertex); cudaFree(h->d_pixel_gidx); cudaFree(h->d_pixel_seed);
-  KB_CUDA(h, devAlloc(&h->stg_depth, pixels, 0));
-  KB_CUDA(h, devAlloc(&h->stg_label, pixels, 0));
-  KB_CUDA(h, devAlloc(&h->stg_mask, pixels, 0));
-  KB_CUDA(h, devAlloc(&h->stg_object, pixels, 0));
+  const size_t n = pixels * kMaxBatch * 2;
+  KB_CUDA(h, devAlloc(&h->stg_depth, n, 0));
+  KB_CUDA(h, devAlloc(&h->stg_label, n, 0));
+  KB_CUDA(h, devAlloc(&h->stg_mask, n, 0));
+  KB_CUDA(h, devAlloc(&h->stg_object, n, 0));
+  h->stg_pixels = pixels;
+  return KB_OK;
+}
+
+int ensureMotionBuffers(kb_handle* h, size_t pixels) {
+  if (h->mot_pixels >= pixels) return KB_OK;
+  cudaFree(h->mot_depth); cudaFree(h->stg_vertex); cudaFree(h->d_pixel_gidx); cudaFree(h->d_pixel_seed);
+  KB_CUDA(h, devAlloc(&h->mot_depth, pixels, 0));
   KB_CUDA(h, devAlloc(&h->stg_vertex, pixels * 3, 0));
   KB_CUDA(h, devAlloc(&h->d_pixel_gidx, pixels, 0));
   KB_CUDA(h, devAlloc(&h->d_pixel_seed, pixels, 0));
-  h->stg_pixels = pixels;
+  h->mot_pixels = pixels;
   return KB_OK;
 }
 
@@ -240,6 +265,19 @@ int kb_create(const kb_map_config* map, const kb_integrator_config* integ, const
     }
     KB_CUDA(h, cudaMallocHost(reinterpret_cast<void**>(&h->h_ctr), sizeof(int) * kNumCounters));
     std::memset(h->h_ctr, 0, sizeof(int) * kNumCounters);
+    KB_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      KB_CUDA(h, cudaEventCreateWithFlags(&h->stg_ready[i], cudaEventDisableTiming));
+      KB_CUDA(h, cudaEventCreateWithFlags(&h->stg_consumed[i], cudaEventDisableTiming));
+    }
+    KB_CUDA(h, devAlloc(&h->work_slots, S, 0));
+    KB_CUDA(h, devAlloc(&h->work_masks, S, 0));
+    KB_CUDA(h, devAlloc(&h->work_upd, S, 0));
+    {
+      cudaDeviceProp prop{};
+      KB_CUDA(h, cudaGetDeviceProperties(&prop, device));
+      h->fuse_grid = prop.multiProcessorCount * 8;  // persistent CTAs; idle ones exit immediately
+    }
     h->max_removed = m.max_blocks;
     KB_CUDA(h, devAlloc(&h->d_removed, static_cast<size_t>(h->max_removed), 0));
     KB_CUDA(h, cudaDeviceSynchronize());
@@ -266,6 +304,12 @@ int kb_destroy(kb_handle* h) {
   cudaFree(m.sem_label); cudaFree(m.sem_lik);
   cudaFree(h->stg_depth); cudaFree(h->stg_label); cudaFree(h->stg_mask); cudaFree(h->stg_object);
   cudaFree(h->stg_vertex); cudaFree(h->d_pixel_gidx); cudaFree(h->d_pixel_seed); cudaFree(h->d_removed);
+  cudaFree(h->mot_depth); cudaFree(h->tile_max); cudaFree(h->work_slots); cudaFree(h->work_masks); cudaFree(h->work_upd);
+  for (int i = 0; i < 2; ++i) {
+    if (h->stg_ready[i]) cudaEventDestroy(h->stg_ready[i]);
+    if (h->stg_consumed[i]) cudaEventDestroy(h->stg_consumed[i]);
+  }
+  if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
   if (h->h_ctr) cudaFreeHost(h->h_ctr);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -291,35 +335,13 @@ int kb_synchronize(kb_handle* h) {
 int kb_set_camera(kb_handle* h, const kb_camera* cam) {
   if (!h || !cam || cam->width <= 1 || cam->height <= 1 || !(cam->fx > 0.f) || !(cam->fy > 0.f))
     return fail(h, KB_ERR_INVALID, "invalid camera");
+  KB_CUDA(h, cudaSetDevice(h->device));
+  const bool same = h->has_cam && std::memcmp(&h->cam, cam, sizeof(kb_camera)) == 0;
   h->cam = *cam;
   h->has_cam = true;
-  KB_CUDA(h, cudaSetDevice(h->device));
-  return ensureStaging(h, static_cast<size_t>(cam->width) * cam->height);
-}
-
-int kb_set_shard(kb_handle* h, int rank, int nranks) {
-  if (!h || nranks < 1 || rank < 0 || rank >= nranks) return fail(h, KB_ERR_INVALID, "invalid shard");
-  h->rank = rank;
-  h->nranks = nranks;
-  return KB_OK;
-}
-
-int kb_integrate_frame(kb_handle* h, const kb_frame* f, int allocate_blocks, kb_frame_stats* stats) {
-  if (!h || !f || !f->depth) return fail(h, KB_ERR_INVALID, "null frame");
-  if (!h->has_cam) return fail(h, KB_ERR_STATE, "kb_set_camera must be called first");
-  KB_CUDA(h, cudaSetDevice(h->device));
-  uint32_t fidx = 0;
-  int st = frameIndex(h, f->stamp_ns, &fidx);
-  if (st != KB_OK) return st;
-  if (stats && h->ctr_dirty) {
-    if ((st = readCounters(h)) != KB_OK) return st;
-    std::memcpy(h->prev_ctr, h->h_ctr, sizeof(h->prev_ctr));
-    h->ctr_dirty = false;
-  }
-
-  FrameParams p{};
-  poseToFloat(f->world_T_sensor, p.R, p.t, p.Rw, p.tw);
+  if (same) return KB_OK;
   const kb_camera& c = h->cam;
+  BatchParams& p = h->batch;
   p.W = c.width; p.H = c.height;
   p.fx = c.fx; p.fy = c.fy; p.cx = c.cx; p.cy = c.cy;
   p.min_range = c.min_range; p.max_range = c.max_range;
@@ -337,8 +359,6 @@ int kb_integrate_frame(kb_handle* h, const kb_frame* f, int allocate_blocks, kb_
   p.voxel_size = h->map.voxel_size;
   p.block_size = h->block_size;
   p.trunc = h->map.truncation_distance;
-  p.voxel_size_inv = 1.f / h->map.voxel_size;
-  p.block_size_inv = 1.f / h->block_size;
   p.infl = h->block_size * 0.8660254f;
   p.use_dropoff = h->integ.use_weight_dropoff;
   p.dropoff_eps = h->integ.weight_dropoff_epsilon > 0.f ? h->integ.weight_dropoff_epsilon
@@ -351,44 +371,149 @@ int kb_integrate_frame(kb_handle* h, const kb_frame* f, int allocate_blocks, kb_
   p.L = h->L;
   p.mle_diag = h->mle_diag; p.mle_off = h->mle_off; p.mle_init = h->mle_init;
   p.blocked_mask = h->blocked_mask;
-  p.target_id = f->object_target_id;
-  p.frame_idx = fidx;
-  p.allocate = allocate_blocks ? 1 : 0;
-  p.rank = h->rank; p.nranks = h->nranks;
   p.with_tracking = h->map.with_tracking;
+  p.tiles_x = (c.width + 15) / 16;
+  p.tiles_y = (c.height + 15) / 16;
+  p.work_slots = h->work_slots;
+  p.work_masks = h->work_masks;
+  p.work_upd = h->work_upd;
+  p.max_work = h->dm.max_blocks;
+  cudaFree(h->tile_max);
+  h->tile_max = nullptr;
+  KB_CUDA(h, devAlloc(&h->tile_max, static_cast<size_t>(p.tiles_x) * p.tiles_y * kMaxBatch, 0));
+  return ensureMotionBuffers(h, static_cast<size_t>(c.width) * c.height);
+}
 
+int kb_set_culling(kb_handle* h, int enabled) {
+  if (!h) return KB_ERR_INVALID;
+  h->cull = enabled != 0;
+  return KB_OK;
+}
+
+int kb_set_shard(kb_handle* h, int rank, int nranks) {
+  if (!h || nranks < 1 || rank < 0 || rank >= nranks) return fail(h, KB_ERR_INVALID, "invalid shard");
+  h->rank = rank;
+  h->nranks = nranks;
+  return KB_OK;
+}
+
+// Fuses up to kMaxBatch frames with one K0 + one K1 launch (plus one tile-max launch when culling).
+static int integrateBatch(kb_handle* h, const kb_frame* frames, int n, int allocate_blocks) {
+  const kb_camera& c = h->cam;
   const size_t px = static_cast<size_t>(c.width) * c.height;
-  if ((st = stage(h, f->depth, h->stg_depth, px, f->memory, &p.depth)) != KB_OK) return st;
-  if ((st = stage(h, f->label, h->stg_label, px, f->memory, &p.label)) != KB_OK) return st;
-  if ((st = stage(h, f->mask, h->stg_mask, px, f->memory, &p.mask)) != KB_OK) return st;
-  if ((st = stage(h, f->object_image, h->stg_object, px, f->memory, &p.object_image)) != KB_OK) return st;
+  BatchParams& p = h->batch;  // persistent: camera / integrator fields are filled by kb_set_camera
+  p.n_frames = n;
+  p.allocate = allocate_blocks ? 1 : 0;
+  p.rank = h->rank;
+  p.nranks = h->nranks;
+  p.parity = h->parity;
+  h->parity ^= 1;
+  p.cull = h->cull ? 1 : 0;
 
-  int grid = 0;
-  if (allocate_blocks) {
-    const float reach = c.max_range + p.infl;
-    for (int a = 0; a < 3; ++a) {
-      p.lo[a] = static_cast<int>(std::floor((p.tw[a] - reach) * p.block_size_inv));
-      const int hi = static_cast<int>(std::floor((p.tw[a] + reach) * p.block_size_inv));
-      p.dims[a] = hi - p.lo[a] + 1;
-    }
-    grid = p.dims[0] * p.dims[1] * p.dims[2];
-  } else {
-    if ((st = slotHwm(h, &grid)) != KB_OK) return st;
+  // ---- stage host images (double-buffered, on the copy stream so they overlap the previous batch)
+  bool any_host = false;
+  for (int b = 0; b < n; ++b) any_host |= frames[b].memory != KB_MEM_DEVICE;
+  const int set = h->stg_set;
+  if (any_host) {
+    int st = ensureStaging(h, px);
+    if (st != KB_OK) return st;
+    h->stg_set ^= 1;
+    // wait until the kernels that last read this staging set are done
+    KB_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->stg_consumed[set], 0));
   }
-  launchIntegrate(h->dm, p, grid, h->stream);
+  int lo[3] = {INT32_MAX, INT32_MAX, INT32_MAX}, hi[3] = {INT32_MIN, INT32_MIN, INT32_MIN};
+  for (int b = 0; b < n; ++b) {
+    const kb_frame& f = frames[b];
+    FrameView& v = p.f[b];
+    float Rw[9], tw[3];
+    poseToFloat(f.world_T_sensor, v.R, v.t, Rw, tw);
+    uint32_t fidx = 0;
+    int st = frameIndex(h, f.stamp_ns, &fidx);
+    if (st != KB_OK) return st;
+    v.frame_idx = fidx;
+    v.target_id = f.object_target_id;
+    if (f.memory == KB_MEM_DEVICE) {
+      v.depth = f.depth; v.label = f.label; v.mask = f.mask; v.object_image = f.object_image;
+    } else {
+      const size_t off = (static_cast<size_t>(set) * kMaxBatch + b) * px;
+      auto up = [&](const void* src, void* dst, size_t bytes) -> int {
+        KB_CUDA(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->copy_stream));
+        return KB_OK;
+      };
+      v.depth = h->stg_depth + off;
+      if ((st = up(f.depth, h->stg_depth + off, px * 4)) != KB_OK) return st;
+      v.label = v.mask = v.object_image = nullptr;
+      if (f.label) { v.label = h->stg_label + off; if ((st = up(f.label, h->stg_label + off, px * 4)) != KB_OK) return st; }
+      if (f.mask) { v.mask = h->stg_mask + off; if ((st = up(f.mask, h->stg_mask + off, px * 4)) != KB_OK) return st; }
+      if (f.object_image) { v.object_image = h->stg_object + off; if ((st = up(f.object_image, h->stg_object + off, px * 4)) != KB_OK) return st; }
+    }
+    v.tile_max = h->tile_max + static_cast<size_t>(b) * p.tiles_x * p.tiles_y;
+    if (allocate_blocks) {
+      const float reach = c.max_range + p.infl;
+      const float inv = 1.f / h->block_size;
+      for (int a = 0; a < 3; ++a) {
+        lo[a] = std::min(lo[a], static_cast<int>(std::floor((tw[a] - reach) * inv)));
+        hi[a] = std::max(hi[a], static_cast<int>(std::floor((tw[a] + reach) * inv)));
+      }
+    }
+  }
+  if (any_host) {
+    KB_CUDA(h, cudaEventRecord(h->stg_ready[set], h->copy_stream));
+    KB_CUDA(h, cudaStreamWaitEvent(h->stream, h->stg_ready[set], 0));
+  }
+  if (allocate_blocks) {
+    for (int a = 0; a < 3; ++a) { p.lo[a] = lo[a]; p.dims[a] = hi[a] - lo[a] + 1; }
+    h->hwm_dirty = true;
+  } else {
+    if (h->hwm_dirty) {
+      int st, nslots = 0;
+      if ((st = slotHwm(h, &nslots)) != KB_OK) return st;
+      h->hwm_cached = nslots;
+      h->hwm_dirty = false;
+    }
+    p.n_slots = h->hwm_cached;
+  }
+  if (p.cull) launchTileMax(p, h->stream);
+  launchSelectBlocks(h->dm, p, h->stream);
+  launchFuse(h->dm, p, h->fuse_grid, h->stream);
   KB_CUDA(h, cudaGetLastError());
+  if (any_host) {
+    KB_CUDA(h, cudaEventRecord(h->stg_consumed[set], h->stream));
+    // KB_MEM_HOST buffers are borrowed only for the duration of the call: wait for the copies (the
+    // kernels keep running asynchronously and overlap the next call's copies).
+    KB_CUDA(h, cudaStreamSynchronize(h->copy_stream));
+  }
   h->ctr_dirty = true;
+  return KB_OK;
+}
 
+int kb_integrate_frames(kb_handle* h, const kb_frame* frames, int32_t n_frames, int allocate_blocks,
+                        kb_frame_stats* stats) {
+  if (!h || !frames || n_frames < 0) return fail(h, KB_ERR_INVALID, "null frames");
+  if (!h->has_cam) return fail(h, KB_ERR_STATE, "kb_set_camera must be called first");
+  for (int i = 0; i < n_frames; ++i)
+    if (!frames[i].depth) return fail(h, KB_ERR_INVALID, "frame without depth image");
+  KB_CUDA(h, cudaSetDevice(h->device));
+  int st;
+  if (stats && h->ctr_dirty) {
+    if ((st = readCounters(h)) != KB_OK) return st;
+    std::memcpy(h->prev_ctr, h->h_ctr, sizeof(h->prev_ctr));
+    h->ctr_dirty = false;
+  }
+  for (int i = 0; i < n_frames; i += kMaxBatch) {
+    if ((st = integrateBatch(h, frames + i, std::min(kMaxBatch, n_frames - i), allocate_blocks)) != KB_OK) return st;
+  }
   if (stats) {
     if ((st = readCounters(h)) != KB_OK) return st;
     const int* c1 = h->h_ctr;
     const int* c0 = h->prev_ctr;
-    stats->blocks_in_frustum = static_cast<int32_t>(static_cast<uint32_t>(c1[kCtrFrustum]) - static_cast<uint32_t>(c0[kCtrFrustum]));
-    stats->blocks_allocated = static_cast<int32_t>(static_cast<uint32_t>(c1[kCtrAllocated]) - static_cast<uint32_t>(c0[kCtrAllocated]));
-    stats->blocks_updated = static_cast<int32_t>(static_cast<uint32_t>(c1[kCtrBlocksUpdated]) - static_cast<uint32_t>(c0[kCtrBlocksUpdated]));
-    stats->voxels_updated = static_cast<int32_t>(static_cast<uint32_t>(c1[kCtrVoxelsUpdated]) - static_cast<uint32_t>(c0[kCtrVoxelsUpdated]));
-    stats->voxels_in_band = static_cast<int32_t>(static_cast<uint32_t>(c1[kCtrVoxelsBand]) - static_cast<uint32_t>(c0[kCtrVoxelsBand]));
-    stats->voxels_semantic = static_cast<int32_t>(static_cast<uint32_t>(c1[kCtrVoxelsSemantic]) - static_cast<uint32_t>(c0[kCtrVoxelsSemantic]));
+    auto d = [&](int k) { return static_cast<int32_t>(static_cast<uint32_t>(c1[k]) - static_cast<uint32_t>(c0[k])); };
+    stats->blocks_in_frustum = d(kCtrFrustum);
+    stats->blocks_allocated = d(kCtrAllocated);
+    stats->blocks_updated = d(kCtrBlocksUpdated);
+    stats->voxels_updated = d(kCtrVoxelsUpdated);
+    stats->voxels_in_band = d(kCtrVoxelsBand);
+    stats->voxels_semantic = d(kCtrVoxelsSemantic);
     stats->total_blocks = c1[kCtrLiveBlocks];
     stats->capacity_exceeded = c1[kCtrCapacityExceeded];
     std::memcpy(h->prev_ctr, h->h_ctr, sizeof(h->prev_ctr));
@@ -396,6 +521,10 @@ int kb_integrate_frame(kb_handle* h, const kb_frame* f, int allocate_blocks, kb_
     if (c1[kCtrCapacityExceeded]) return fail(h, KB_ERR_CAPACITY, "block / semantic pool exhausted");
   }
   return KB_OK;
+}
+
+int kb_integrate_frame(kb_handle* h, const kb_frame* f, int allocate_blocks, kb_frame_stats* stats) {
+  return kb_integrate_frames(h, f, f ? 1 : 0, allocate_blocks, stats);
 }
 
 int kb_get_totals(kb_handle* h, kb_frame_stats* t) {
@@ -550,7 +679,7 @@ int kb_detect_motion(kb_handle* h, const kb_frame* f, int32_t* dynamic_image_out
   p.block_size_inv = 1.f / h->block_size;
   p.voxel_size_inv = 1.f / h->map.voxel_size;
   int st;
-  if ((st = stage(h, f->depth, h->stg_depth, px, f->memory, &p.depth)) != KB_OK) return st;
+  if ((st = stage(h, f->depth, h->mot_depth, px, f->memory, &p.depth)) != KB_OK) return st;
   if ((st = stage(h, f->vertex_world, h->stg_vertex, px * 3, f->memory, &p.vertex)) != KB_OK) return st;
   p.pixel_gidx = h->d_pixel_gidx;
   p.pixel_seed = h->d_pixel_seed;

@@ -60,7 +60,10 @@ enum Counter {
   kCtrSeeds = 12,
   kCtrRemoved = 13,
   kCtrErased = 14,
-  kNumCounters = 16
+  kCtrWork0 = 15,  // two work-list counters used alternately by consecutive batches
+  kCtrWork1 = 16,
+  kCtrFramesCulled = 17,
+  kNumCounters = 24
 };
 
 __host__ __device__ inline unsigned long long packKey(int x, int y, int z) {

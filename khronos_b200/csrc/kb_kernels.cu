@@ -2,13 +2,18 @@
 // Compile with -fmad=false: the per-voxel arithmetic must round exactly like the fp32 reference
 // (no FMA contraction), integer outputs (labels, indices, flags) are bit-exact by construction.
 //
-//   K0+K1  integrateKernel      frustum test + block hash insert + projective TSDF/semantic fusion
+//   K0     selectBlocksKernel   per batch: frustum test (+ conservative depth culling), block hash
+//                               insert, semantic slot assignment, compaction into a work list
+//   K1     fuseKernel           persistent CTAs over (block, z-slab) items: projective TSDF + semantic
+//                               fusion of up to 32 frames with the voxel state held in registers
 //   K2     trackingKernel       per-voxel last_occupied / active / to_remove, block has_active_data
 //   K3     everFreeKernel       ever-free labelling with 6/18/26 neighbourhood across blocks
 //   K2r    resetInactiveKernel  block removal + slot recycling
 //   M1     motionLookupKernel   per-pixel endpoint voxel lookup + ever-free seed test
 //   K4     scanConfidenceKernel object-extraction low-confidence erase
 #include <limits.h>
+
+#include <algorithm>
 
 #include "../../include/khronos_b200.h"
 #include "kb_kernels.cuh"
@@ -27,7 +32,7 @@ __device__ __forceinline__ void xform(const float* R, const float* t, float x, f
 }
 
 // hydra::Camera::pointIsInViewFrustum restated (oracle.cpp pointInFrustum): z, range and 4 planes.
-__device__ __forceinline__ bool inFrustum(const FrameParams& p, float x, float y, float z) {
+__device__ __forceinline__ bool inFrustum(const BatchParams& p, float x, float y, float z) {
   const float infl = p.infl;
   if (z < -infl) return false;
   const float r = sqrtf((x * x + y * y) + z * z);
@@ -45,24 +50,24 @@ struct Taps {
   float w0, w1, w2, w3;
 };
 
-__device__ __forceinline__ Taps nearestTaps(const FrameParams& p, float u, float v) {
+__device__ __forceinline__ Taps nearestTaps(const BatchParams& p, const float* __restrict__ depth, float u, float v) {
   Taps t;
   t.bilinear = false;
   t.u = static_cast<int>(roundf(u));
   t.v = static_cast<int>(roundf(v));
   t.w0 = t.w1 = t.w2 = t.w3 = 0.f;
-  t.valid = t.u >= 0 && t.u < p.W && t.v >= 0 && t.v < p.H && __ldg(&p.depth[t.v * p.W + t.u]) > 0.f;
+  t.valid = t.u >= 0 && t.u < p.W && t.v >= 0 && t.v < p.H && __ldg(&depth[t.v * p.W + t.u]) > 0.f;
   return t;
 }
 
 // ProjectionInterpolator{Nearest,Bilinear,Adaptive}::computeWeights (UP).
 // Returns the interpolated range through `range` when valid.
-__device__ __forceinline__ Taps computeTaps(const FrameParams& p, float u, float v, float& range) {
+__device__ __forceinline__ Taps computeTaps(const BatchParams& p, const float* __restrict__ depth, float u, float v, float& range) {
   Taps t;
   t.valid = false;
   if (p.interp == KB_INTERP_NEAREST) {
-    t = nearestTaps(p, u, v);
-    if (t.valid) range = __ldg(&p.depth[t.v * p.W + t.u]);
+    t = nearestTaps(p, depth, u, v);
+    if (t.valid) range = __ldg(&depth[t.v * p.W + t.u]);
     return t;
   }
   const int u0 = static_cast<int>(floorf(u)), v0 = static_cast<int>(floorf(v));
@@ -70,7 +75,7 @@ __device__ __forceinline__ Taps computeTaps(const FrameParams& p, float u, float
   bool use_nearest = !inside;
   float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
   if (inside) {
-    const float* row0 = p.depth + v0 * p.W + u0;
+    const float* row0 = depth + v0 * p.W + u0;
     r0 = __ldg(row0);
     r2 = __ldg(row0 + 1);
     r1 = __ldg(row0 + p.W);
@@ -87,8 +92,8 @@ __device__ __forceinline__ Taps computeTaps(const FrameParams& p, float u, float
     return t;
   }
   if (use_nearest) {
-    t = nearestTaps(p, u, v);
-    if (t.valid) range = __ldg(&p.depth[t.v * p.W + t.u]);
+    t = nearestTaps(p, depth, u, v);
+    if (t.valid) range = __ldg(&depth[t.v * p.W + t.u]);
     return t;
   }
   const float du = u - static_cast<float>(u0), dv = v - static_cast<float>(v0);
@@ -106,7 +111,7 @@ __device__ __forceinline__ Taps computeTaps(const FrameParams& p, float u, float
 
 // interpolateID: value at the tap with the largest weight, ties -> lowest tap index
 // (taps ordered (u,v), (u,v+1), (u+1,v), (u+1,v+1)).
-__device__ __forceinline__ int tapID(const FrameParams& p, const int* __restrict__ img, const Taps& t) {
+__device__ __forceinline__ int tapID(const BatchParams& p, const int* __restrict__ img, const Taps& t) {
   int du = 0, dv = 0;
   if (t.bilinear) {
     int best = 0;
@@ -120,7 +125,7 @@ __device__ __forceinline__ int tapID(const FrameParams& p, const int* __restrict
   return __ldg(&img[(t.v + dv) * p.W + t.u + du]);
 }
 
-__device__ __forceinline__ float measurementWeight(const FrameParams& p, float depth, float sdf) {
+__device__ __forceinline__ float measurementWeight(const BatchParams& p, float depth, float sdf) {
   float w = (p.fx * p.fy) * (p.voxel_size * p.voxel_size) / (depth * depth);
   if (!p.constant_weight) w = w / (depth * depth);
   if (p.use_dropoff && sdf < -p.dropoff_eps) {
@@ -136,185 +141,284 @@ __device__ __forceinline__ int warpSum(int v) {
   return v;
 }
 
-// One CTA per voxel block. Thread 0 does K0 (frustum test, shard filter, hash find-or-insert), then
-// all 256 threads fuse the block's voxels: thread (x,y) walks z so every warp touches 32 consecutive
-// voxels (256 B of float2 TSDF) per step. Semantic updates run in a second phase after the CTA knows
-// whether the block needs a semantic slot.
-template <int VPS>
-__global__ void __launch_bounds__(kThreads) integrateKernel(const DeviceMap m, const __grid_constant__ FrameParams p) {
-  constexpr int V = VPS * VPS * VPS;
-  constexpr int ITERS = V / kThreads;
-  __shared__ int s_slot, s_sem;
-  __shared__ int s_bidx[3];
-  __shared__ int s_cnt[3];
-  __shared__ uint8_t s_lab[V];  // pending semantic label per voxel, 0xFF = none
-  const int tid = threadIdx.x;
-
-  if (tid == 0) {
-    int slot = -1, bx = 0, by = 0, bz = 0;
-    if (p.allocate) {
-      int c = blockIdx.x;
-      bx = p.lo[0] + c % p.dims[0];
-      c /= p.dims[0];
-      by = p.lo[1] + c % p.dims[1];
-      bz = p.lo[2] + c / p.dims[1];
-      const float cx = (static_cast<float>(bx) + 0.5f) * p.block_size;
-      const float cy = (static_cast<float>(by) + 0.5f) * p.block_size;
-      const float cz = (static_cast<float>(bz) + 0.5f) * p.block_size;
-      float x, y, z;
-      xform(p.R, p.t, cx, cy, cz, x, y, z);
-      if (inFrustum(p, x, y, z) && (p.nranks == 1 || blockOwner(bx, by, bz, p.nranks) == p.rank)) {
-        int created = 0;
-        slot = hashFindOrInsert(m, bx, by, bz, &created);
-        if (slot >= 0) {
-          atomicAdd(&m.counters[kCtrFrustum], 1);
-          if (created) atomicAdd(&m.counters[kCtrAllocated], 1);
-        }
-      }
-    } else {
-      slot = blockIdx.x;
-      if (!(m.block_flags[slot] & kFlagAllocated)) {
-        slot = -1;
-      } else {
-        const int3 bi = m.block_index[slot];
-        bx = bi.x; by = bi.y; bz = bi.z;
-        atomicAdd(&m.counters[kCtrFrustum], 1);
-      }
-    }
-    s_slot = slot;
-    s_sem = slot >= 0 ? m.block_sem[slot] : -1;
-    s_bidx[0] = bx; s_bidx[1] = by; s_bidx[2] = bz;
-    s_cnt[0] = s_cnt[1] = s_cnt[2] = 0;
-  }
-  __syncthreads();
-  const int slot = s_slot;
-  if (slot < 0) return;
-
-  const float ox = static_cast<float>(s_bidx[0]) * p.block_size;
-  const float oy = static_cast<float>(s_bidx[1]) * p.block_size;
-  const float oz = static_cast<float>(s_bidx[2]) * p.block_size;
-  float2* __restrict__ tsdf = m.tsdf + static_cast<size_t>(slot) * V;
-  uint32_t* __restrict__ last_obs = m.last_obs + static_cast<size_t>(slot) * V;
-  const bool binary = p.sem_mode == KB_SEMANTICS_BINARY;
-  const bool has_sem = p.L > 0 && (binary ? p.object_image != nullptr : p.label != nullptr);
-
-  int n_valid = 0, n_band = 0, n_sem = 0;
-  int sem_pending = 0;
-
-#pragma unroll 2
-  for (int it = 0; it < ITERS; ++it) {
-    const int lin = tid + it * kThreads;
-    s_lab[lin] = 0xFF;
-    const int vx = lin % VPS, vy = (lin / VPS) % VPS, vz = lin / (VPS * VPS);
-    const float wx = ox + (static_cast<float>(vx) + 0.5f) * p.voxel_size;
-    const float wy = oy + (static_cast<float>(vy) + 0.5f) * p.voxel_size;
-    const float wz = oz + (static_cast<float>(vz) + 0.5f) * p.voxel_size;
-    float x, y, z;
-    xform(p.R, p.t, wx, wy, wz, x, y, z);
-    if (z <= 0.f) continue;
-    const float u = p.fx * x / z + p.cx;
-    const float v = p.fy * y / z + p.cy;
-    if (u < 0.f || u > static_cast<float>(p.W - 1) || v < 0.f || v > static_cast<float>(p.H - 1)) continue;
-    float range = 0.f;
-    const Taps taps = computeTaps(p, u, v, range);
-    if (!taps.valid) continue;
-    const float sdf = range - z;
-    if (sdf < -p.trunc) continue;
-    const bool in_band = fabsf(sdf) < p.trunc;
-    uint32_t label = 0;
-    bool have_label = false;
-    if (in_band) {
-      if (p.mask != nullptr && tapID(p, p.mask, taps) != 0) continue;
-      if (has_sem) {
-        if (binary) {
-          label = tapID(p, p.object_image, taps) == p.target_id ? 1u : 0u;
-        } else {
-          label = static_cast<uint32_t>(tapID(p, p.label, taps));
-          if (label < static_cast<uint32_t>(KB_MAX_LABELS) && ((p.blocked_mask >> label) & 1ull)) continue;
-        }
-        have_label = true;
-      }
-    }
-    const float wm = measurementWeight(p, z, sdf);
-    const float2 old = tsdf[lin];
-    const float sdf_c = fminf(fmaxf(sdf, -p.trunc), p.trunc);
-    float2 upd;
-    upd.x = (old.x * old.y + sdf_c * wm) / (old.y + wm);
-    upd.y = fminf(old.y + wm, p.max_weight);
-    tsdf[lin] = upd;
-    if (p.with_tracking) last_obs[lin] = p.frame_idx;
-    ++n_valid;
-    if (in_band) {
-      ++n_band;
-      if (have_label && label < static_cast<uint32_t>(p.L)) {
-        sem_pending = 1;
-        s_lab[lin] = static_cast<uint8_t>(label);
-      }
-    }
-  }
-
-  // ---- phase B: semantic fusion (lazy semantic slot) ----
-  const int any_sem = __syncthreads_or(sem_pending != 0);
-  if (any_sem) {
-    if (tid == 0 && s_sem < 0) {
-      const int q = allocSlot(m.counters, kCtrSemHwm, kCtrSemFreeCount, m.sem_free_list, m.max_sem);
-      s_sem = q;
-      m.block_sem[slot] = q;
-    }
-    __syncthreads();
-    const int sem = s_sem;
-    if (sem >= 0 && sem_pending) {
-      uint16_t* __restrict__ slabel = m.sem_label + static_cast<size_t>(sem) * V;
-      float* __restrict__ slik = m.sem_lik + static_cast<size_t>(sem) * V * m.Lp;
-      for (int it = 0; it < ITERS; ++it) {
-        const int lin = tid + it * kThreads;
-        const uint32_t label = s_lab[lin];
-        if (label == 0xFFu) continue;
-        const bool empty = slabel[lin] == kSemEmpty;
-        int best = 0;
-        if (binary) {
-          float2* lk = reinterpret_cast<float2*>(slik + static_cast<size_t>(lin) * 2);
-          float2 c = empty ? make_float2(0.f, 0.f) : *lk;
-          if (label) c.y = c.y + 1.f; else c.x = c.x + 1.f;
-          *lk = c;
-          best = c.y > c.x ? 1 : 0;
-        } else {
-          float4* lk = reinterpret_cast<float4*>(slik + static_cast<size_t>(lin) * m.Lp);
-          float bestv = 0.f;
-          for (int k4 = 0; k4 < m.Lp; k4 += 4) {
-            float4 c = empty ? make_float4(p.mle_init, p.mle_init, p.mle_init, p.mle_init) : lk[k4 >> 2];
-            float* cf = reinterpret_cast<float*>(&c);
+// ---- per-frame 16x16 tile maxima of the depth image (input of the conservative block culling) -------
+constexpr int kTile = 16;
+__global__ void __launch_bounds__(256) tileMaxKernel(const __grid_constant__ BatchParams p) {
+  const int b = blockIdx.y;
+  const int tx = blockIdx.x % p.tiles_x, ty = blockIdx.x / p.tiles_x;
+  const int u = tx * kTile + (threadIdx.x & 15), v = ty * kTile + (threadIdx.x >> 4);
+  float d = 0.f;
+  if (u < p.W && v < p.H) d = __ldg(&p.f[b].depth[v * p.W + u]);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int k = k4 + j;
-              if (k < p.L) {
-                cf[j] = cf[j] + (static_cast<uint32_t>(k) == label ? p.mle_diag : p.mle_off);
-                if (k == 0 || cf[j] > bestv) { bestv = cf[j]; best = k; }
-              }
+  for (int o = 16; o > 0; o >>= 1) d = fmaxf(d, __shfl_xor_sync(0xffffffffu, d, o));
+  __shared__ float s[8];
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = d;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = s[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, s[i]);
+    const_cast<float*>(p.f[b].tile_max)[blockIdx.x] = m;
+  }
+}
+
+// True if NO voxel of the block can receive a valid measurement from frame b, so the whole
+// (block, frame) pair can be skipped without changing any result (SURVEY §7 hard part 4): either the
+// block projects entirely outside the image, or every depth pixel its voxels could tap is invalid, or
+// every voxel lies more than the truncation distance behind the farthest of those depths
+// (sdf < -trunc). Uses margins (1 mm, 2 px) far above the fp32 rounding of the per-voxel arithmetic.
+__device__ __forceinline__ bool blockCulled(const BatchParams& p, const FrameView& f, float ox, float oy, float oz) {
+  const float lo = 0.5f * p.voxel_size, hi = p.block_size - 0.5f * p.voxel_size;
+  float zmin = 3.0e38f, umin = 3.0e38f, umax = -3.0e38f, vmin = 3.0e38f, vmax = -3.0e38f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    float x, y, z;
+    xform(f.R, f.t, ox + ((c & 1) ? hi : lo), oy + ((c & 2) ? hi : lo), oz + ((c & 4) ? hi : lo), x, y, z);
+    if (z < 1e-2f) return false;  // block reaches behind / near the camera plane: keep
+    const float u = p.fx * x / z + p.cx, v = p.fy * y / z + p.cy;
+    zmin = fminf(zmin, z);
+    umin = fminf(umin, u); umax = fmaxf(umax, u);
+    vmin = fminf(vmin, v); vmax = fmaxf(vmax, v);
+  }
+  if (umax < -0.5f || vmax < -0.5f || umin > static_cast<float>(p.W - 1) + 0.5f || vmin > static_cast<float>(p.H - 1) + 0.5f)
+    return true;  // projects entirely outside the image
+  const int u0 = max(static_cast<int>(floorf(umin)) - 2, 0), u1 = min(static_cast<int>(floorf(umax)) + 3, p.W - 1);
+  const int v0 = max(static_cast<int>(floorf(vmin)) - 2, 0), v1 = min(static_cast<int>(floorf(vmax)) + 3, p.H - 1);
+  const int tx0 = u0 / kTile, tx1 = u1 / kTile, ty0 = v0 / kTile, ty1 = v1 / kTile;
+  if ((tx1 - tx0 + 1) * (ty1 - ty0 + 1) > 96) return false;  // large footprint (near block): keep
+  float dmax = 0.f;
+  for (int ty = ty0; ty <= ty1; ++ty)
+    for (int tx = tx0; tx <= tx1; ++tx) dmax = fmaxf(dmax, __ldg(&f.tile_max[ty * p.tiles_x + tx]));
+  if (!(dmax > 0.f)) return true;                 // no valid depth anywhere in the footprint
+  return zmin - p.trunc - 1e-3f > dmax;           // everything is beyond the truncation band
+}
+
+// ---- K0: block selection for a batch of frames ---------------------------------------------------------
+// One thread per candidate block of the batch's AABB (allocate mode; hydra findBlocksInViewFrustum,
+// SURVEY App. A.5) or per pool slot (allocate == 0: all allocated blocks, mesh_object_extractor.cpp:242).
+__global__ void __launch_bounds__(128) selectBlocksKernel(const DeviceMap m, const __grid_constant__ BatchParams p) {
+  const int c0 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c0 == 0) m.counters[kCtrWork0 + (p.parity ^ 1)] = 0;  // the next batch's work counter
+  int slot = -1, bx = 0, by = 0, bz = 0;
+  uint32_t mask = 0;
+  int created = 0;
+  if (p.allocate) {
+    if (c0 >= p.dims[0] * p.dims[1] * p.dims[2]) return;
+    int c = c0;
+    bx = p.lo[0] + c % p.dims[0];
+    c /= p.dims[0];
+    by = p.lo[1] + c % p.dims[1];
+    bz = p.lo[2] + c / p.dims[1];
+    const float cx = (static_cast<float>(bx) + 0.5f) * p.block_size;
+    const float cy = (static_cast<float>(by) + 0.5f) * p.block_size;
+    const float cz = (static_cast<float>(bz) + 0.5f) * p.block_size;
+    for (int b = 0; b < p.n_frames; ++b) {
+      float x, y, z;
+      xform(p.f[b].R, p.f[b].t, cx, cy, cz, x, y, z);
+      if (inFrustum(p, x, y, z)) mask |= 1u << b;
+    }
+    if (!mask) return;
+    if (p.nranks > 1 && blockOwner(bx, by, bz, p.nranks) != p.rank) return;
+    slot = hashFindOrInsert(m, bx, by, bz, &created);
+    if (slot < 0) return;
+  } else {
+    if (c0 >= p.n_slots || !(m.block_flags[c0] & kFlagAllocated)) return;
+    slot = c0;
+    const int3 bi = m.block_index[slot];
+    bx = bi.x; by = bi.y; bz = bi.z;
+    mask = p.n_frames >= 32 ? 0xffffffffu : ((1u << p.n_frames) - 1u);
+  }
+  atomicAdd(&m.counters[kCtrFrustum], __popc(mask));
+  if (created) atomicAdd(&m.counters[kCtrAllocated], 1);
+  if (p.cull) {
+    const float ox = static_cast<float>(bx) * p.block_size, oy = static_cast<float>(by) * p.block_size,
+                oz = static_cast<float>(bz) * p.block_size;
+    uint32_t rem = mask;
+    while (rem) {
+      const int b = __ffs(rem) - 1;
+      rem &= rem - 1;
+      if (blockCulled(p, p.f[b], ox, oy, oz)) mask &= ~(1u << b);
+    }
+    if (!mask) return;
+  }
+  // Blocks that may receive measurements get their semantic slot here (one thread per block, so no
+  // allocation race inside the fuse kernel); never-measured blocks cost no semantic memory.
+  if (p.L > 0 && m.block_sem[slot] < 0) {
+    m.block_sem[slot] = allocSlot(m.counters, kCtrSemHwm, kCtrSemFreeCount, m.sem_free_list, m.max_sem);
+  }
+  const int i = atomicAdd(&m.counters[kCtrWork0 + p.parity], 1);
+  if (i < p.max_work) {
+    p.work_slots[i] = slot;
+    p.work_masks[i] = mask;
+    p.work_upd[i] = 0;
+  } else {
+    atomicExch(&m.counters[kCtrCapacityExceeded], 1);
+  }
+}
+
+// ---- K1: projective TSDF + semantic fusion ----------------------------------------------------------------
+// Persistent CTAs stride over work items = (selected block, z-slab). Thread (x, y) of the 16x16 slab
+// face owns NV voxels stacked in z and keeps their {distance, weight, last_observed} in registers
+// while it walks the frames of the batch in order, so a voxel's TSDF is read and written once per
+// batch, warp accesses are 256 B coalesced, and the NV independent gather chains give ILP.
+// ProjectiveIntegrator::updateBlock / getVoxelMeasurement / computeLabel / updateVoxel (UP App. A.6;
+// computeLabel structure pinned by khronos/src/active_window/integration/object_integrator.cpp:58-81).
+template <int VPS>
+__global__ void __launch_bounds__(kThreads) fuseKernel(const DeviceMap m, const __grid_constant__ BatchParams p) {
+  constexpr int V = VPS * VPS * VPS;
+  constexpr int PARTS = VPS == 16 ? 4 : 1;
+  constexpr int NV = V / PARTS / kThreads;  // voxels per thread: 4 (16^3) or 2 (8^3)
+  __shared__ int s_cnt[3];
+  __shared__ uint32_t s_upd;
+  const int tid = threadIdx.x;
+  const int n_items = min(m.counters[kCtrWork0 + p.parity], p.max_work) * PARTS;
+  const bool binary = p.sem_mode == KB_SEMANTICS_BINARY;
+
+  for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+    const int wi = w / PARTS, part = w % PARTS;
+    const int slot = p.work_slots[wi];
+    const uint32_t fmask = p.work_masks[wi];
+    const int3 bi = m.block_index[slot];
+    const int sem = p.L > 0 ? m.block_sem[slot] : -1;
+    if (tid == 0) { s_cnt[0] = s_cnt[1] = s_cnt[2] = 0; s_upd = 0; }
+    __syncthreads();
+
+    const float ox = static_cast<float>(bi.x) * p.block_size;
+    const float oy = static_cast<float>(bi.y) * p.block_size;
+    const float oz = static_cast<float>(bi.z) * p.block_size;
+    float2* __restrict__ tsdf = m.tsdf + static_cast<size_t>(slot) * V;
+    float wx[NV], wy[NV], wz[NV];
+    float2 st[NV];
+    uint32_t lobs[NV];
+    uint32_t have = 0, touched = 0;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int lin = part * (V / PARTS) + k * kThreads + tid;
+      const int vx = lin % VPS, vy = (lin / VPS) % VPS, vz = lin / (VPS * VPS);
+      wx[k] = ox + (static_cast<float>(vx) + 0.5f) * p.voxel_size;
+      wy[k] = oy + (static_cast<float>(vy) + 0.5f) * p.voxel_size;
+      wz[k] = oz + (static_cast<float>(vz) + 0.5f) * p.voxel_size;
+      st[k] = make_float2(0.f, 0.f);
+      lobs[k] = 0;
+    }
+    int n_valid = 0, n_band = 0, n_sem = 0;
+    uint32_t upd_frames = 0;
+
+    uint32_t rem = fmask;
+    while (rem) {
+      const int b = __ffs(rem) - 1;
+      rem &= rem - 1;
+      const FrameView& f = p.f[b];
+      const bool has_sem = sem >= 0 && (binary ? f.object_image != nullptr : f.label != nullptr);
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        float x, y, z;
+        xform(f.R, f.t, wx[k], wy[k], wz[k], x, y, z);
+        if (z <= 0.f) continue;
+        const float u = p.fx * x / z + p.cx;
+        const float v = p.fy * y / z + p.cy;
+        if (u < 0.f || u > static_cast<float>(p.W - 1) || v < 0.f || v > static_cast<float>(p.H - 1)) continue;
+        float range = 0.f;
+        const Taps taps = computeTaps(p, f.depth, u, v, range);
+        if (!taps.valid) continue;
+        const float sdf = range - z;
+        if (sdf < -p.trunc) continue;
+        const bool in_band = fabsf(sdf) < p.trunc;
+        uint32_t label = 0;
+        bool have_label = false;
+        if (in_band) {
+          if (f.mask != nullptr && tapID(p, f.mask, taps) != 0) continue;
+          if (p.L > 0 && (binary ? f.object_image != nullptr : f.label != nullptr)) {
+            if (binary) {
+              label = tapID(p, f.object_image, taps) == f.target_id ? 1u : 0u;
+            } else {
+              label = static_cast<uint32_t>(tapID(p, f.label, taps));
+              if (label < static_cast<uint32_t>(KB_MAX_LABELS) && ((p.blocked_mask >> label) & 1ull)) continue;
             }
-            lk[k4 >> 2] = c;
+            have_label = true;
           }
         }
-        slabel[lin] = static_cast<uint16_t>(best);
-        ++n_sem;
+        const float wm = measurementWeight(p, z, sdf);
+        const int lin = part * (V / PARTS) + k * kThreads + tid;
+        if (!((have >> k) & 1u)) { st[k] = tsdf[lin]; have |= 1u << k; }
+        const float sdf_c = fminf(fmaxf(sdf, -p.trunc), p.trunc);
+        const float2 old = st[k];
+        st[k].x = (old.x * old.y + sdf_c * wm) / (old.y + wm);
+        st[k].y = fminf(old.y + wm, p.max_weight);
+        lobs[k] = f.frame_idx;
+        touched |= 1u << k;
+        upd_frames |= 1u << b;
+        ++n_valid;
+        if (!in_band) continue;
+        ++n_band;
+        if (has_sem && have_label && label < static_cast<uint32_t>(p.L)) {
+          // SemanticIntegrator::updateLikelihoods (UP App. A.8) on the voxel's likelihood row
+          uint16_t* __restrict__ slabel = m.sem_label + static_cast<size_t>(sem) * V;
+          const bool empty = slabel[lin] == kSemEmpty;
+          int best = 0;
+          if (binary) {
+            float2* lk = reinterpret_cast<float2*>(m.sem_lik + (static_cast<size_t>(sem) * V + lin) * 2);
+            float2 c = empty ? make_float2(0.f, 0.f) : *lk;
+            if (label) c.y = c.y + 1.f; else c.x = c.x + 1.f;
+            *lk = c;
+            best = c.y > c.x ? 1 : 0;
+          } else {
+            float4* lk = reinterpret_cast<float4*>(m.sem_lik + (static_cast<size_t>(sem) * V + lin) * m.Lp);
+            float bestv = 0.f;
+            for (int k4 = 0; k4 < m.Lp; k4 += 4) {
+              float4 c = empty ? make_float4(p.mle_init, p.mle_init, p.mle_init, p.mle_init) : lk[k4 >> 2];
+              float* cf = reinterpret_cast<float*>(&c);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int kk = k4 + j;
+                if (kk < p.L) {
+                  cf[j] = cf[j] + (static_cast<uint32_t>(kk) == label ? p.mle_diag : p.mle_off);
+                  if (kk == 0 || cf[j] > bestv) { bestv = cf[j]; best = kk; }
+                }
+              }
+              lk[k4 >> 2] = c;
+            }
+          }
+          slabel[lin] = static_cast<uint16_t>(best);
+          ++n_sem;
+        }
       }
     }
-  }
 
-  // ---- block flags + counters ----
-  const int wv = warpSum(n_valid), wb = warpSum(n_band), ws = warpSum(n_sem);
-  if ((tid & 31) == 0 && wv) {
-    atomicAdd(&s_cnt[0], wv);
-    if (wb) atomicAdd(&s_cnt[1], wb);
-    if (ws) atomicAdd(&s_cnt[2], ws);
-  }
-  __syncthreads();
-  if (tid == 0 && s_cnt[0] > 0) {
-    m.block_flags[slot] |= KB_FLAG_UPDATED | KB_FLAG_MESH_UPDATED | KB_FLAG_ESDF_UPDATED | KB_FLAG_TRACKING_UPDATED;
-    atomicAdd(&m.counters[kCtrBlocksUpdated], 1);
-    atomicAdd(&m.counters[kCtrVoxelsUpdated], s_cnt[0]);
-    if (s_cnt[1]) atomicAdd(&m.counters[kCtrVoxelsBand], s_cnt[1]);
-    if (s_cnt[2]) atomicAdd(&m.counters[kCtrVoxelsSemantic], s_cnt[2]);
+    // ---- write the voxel state back once, then block flags + counters ----
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      if ((touched >> k) & 1u) {
+        const int lin = part * (V / PARTS) + k * kThreads + tid;
+        tsdf[lin] = st[k];
+        if (p.with_tracking) m.last_obs[static_cast<size_t>(slot) * V + lin] = lobs[k];
+      }
+    }
+    const int wv = warpSum(n_valid);
+    if (wv) {  // warp-uniform
+      const int wb = warpSum(n_band), ws = warpSum(n_sem);
+      uint32_t uf = upd_frames;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) uf |= __shfl_xor_sync(0xffffffffu, uf, o);
+      if ((tid & 31) == 0) {
+        atomicAdd(&s_cnt[0], wv);
+        if (wb) atomicAdd(&s_cnt[1], wb);
+        if (ws) atomicAdd(&s_cnt[2], ws);
+        atomicOr(&s_upd, uf);
+      }
+    }
+    __syncthreads();
+    if (tid == 0 && s_cnt[0] > 0) {
+      atomicOr(&m.block_flags[slot], static_cast<uint32_t>(KB_FLAG_UPDATED | KB_FLAG_MESH_UPDATED | KB_FLAG_ESDF_UPDATED | KB_FLAG_TRACKING_UPDATED));
+      // blocks_updated counts (block, frame) pairs once even though several z-slabs report them
+      const uint32_t prev = atomicOr(&p.work_upd[wi], s_upd);
+      const int fresh = __popc(s_upd & ~prev);
+      if (fresh) atomicAdd(&m.counters[kCtrBlocksUpdated], fresh);
+      atomicAdd(&m.counters[kCtrVoxelsUpdated], s_cnt[0]);
+      if (s_cnt[1]) atomicAdd(&m.counters[kCtrVoxelsBand], s_cnt[1]);
+      if (s_cnt[2]) atomicAdd(&m.counters[kCtrVoxelsSemantic], s_cnt[2]);
+    }
+    __syncthreads();
   }
 }
 
@@ -580,10 +684,18 @@ __global__ void gatherSemanticKernel(const DeviceMap m, const int* slots, int L,
 
 }  // namespace
 
-void launchIntegrate(const DeviceMap& m, const FrameParams& p, int grid, cudaStream_t s) {
+void launchTileMax(const BatchParams& p, cudaStream_t s) {
+  dim3 grid(p.tiles_x * p.tiles_y, p.n_frames);
+  tileMaxKernel<<<grid, 256, 0, s>>>(p);
+}
+void launchSelectBlocks(const DeviceMap& m, const BatchParams& p, cudaStream_t s) {
+  const int n = p.allocate ? p.dims[0] * p.dims[1] * p.dims[2] : p.n_slots;
+  selectBlocksKernel<<<(std::max(n, 1) + 127) / 128, 128, 0, s>>>(m, p);
+}
+void launchFuse(const DeviceMap& m, const BatchParams& p, int grid, cudaStream_t s) {
   if (grid <= 0) return;
-  if (m.vps == 16) integrateKernel<16><<<grid, kThreads, 0, s>>>(m, p);
-  else integrateKernel<8><<<grid, kThreads, 0, s>>>(m, p);
+  if (m.vps == 16) fuseKernel<16><<<grid, kThreads, 0, s>>>(m, p);
+  else fuseKernel<8><<<grid, kThreads, 0, s>>>(m, p);
 }
 void launchTracking(const DeviceMap& m, const TrackingParams& p, int n, cudaStream_t s) {
   if (n > 0) trackingKernel<<<n, kThreads, 0, s>>>(m, p);

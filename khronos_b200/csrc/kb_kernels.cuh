@@ -5,14 +5,26 @@
 
 namespace kb {
 
-// Everything one frame's K0+K1 launch needs, passed by value (constant bank).
-struct FrameParams {
-  float R[9], t[3];    // sensor_T_world (float, rounded once from the double inverse)
-  float Rw[9], tw[3];  // world_T_sensor
+constexpr int kMaxBatch = 32;  // frames fused per launch pair (bits of the per-block frame mask)
+
+// Per-frame part of a batch (pose, image pointers, frame index).
+struct FrameView {
+  float R[9], t[3];  // sensor_T_world (float, rounded once from the double inverse)
+  const float* depth;
+  const int* label;
+  const int* mask;
+  const int* object_image;
+  const float* tile_max;  // per-frame 16x16 tile maxima of depth (conservative block culling), or null
+  uint32_t frame_idx;
+  int target_id;
+};
+
+// Everything one batch's K0 (select) + K1 (fuse) launches need, passed by value (constant bank).
+struct BatchParams {
   int W, H;
   float fx, fy, cx, cy, min_range, max_range;
-  float pl[4][2];      // frustum side planes (left,right,top,bottom): {lateral coeff, z coeff}
-  float voxel_size, block_size, trunc, voxel_size_inv, block_size_inv, infl;
+  float pl[4][2];  // frustum side planes (left,right,top,bottom): {lateral coeff, z coeff}
+  float voxel_size, block_size, trunc, infl;
   int use_dropoff;
   float dropoff_eps;
   int constant_weight;
@@ -22,16 +34,20 @@ struct FrameParams {
   int sem_mode, L;
   float mle_diag, mle_off, mle_init;
   unsigned long long blocked_mask;
-  int target_id;
-  const float* depth;
-  const int* label;
-  const int* mask;
-  const int* object_image;
-  uint32_t frame_idx;
-  int lo[3], dims[3];  // candidate block AABB (allocate mode)
+  int lo[3], dims[3];  // union candidate block AABB of the batch (allocate mode)
   int allocate;        // 1: enumerate AABB + frustum test + insert; 0: all live slots
+  int n_slots;         // allocate == 0: number of pool slots to scan
   int rank, nranks;
   int with_tracking;
+  int n_frames;
+  int parity;          // which of the two work-list counters this batch uses
+  int cull;            // 1: use tile_max culling
+  int tiles_x, tiles_y;
+  int* work_slots;     // [max_work] selected block slots
+  uint32_t* work_masks;  // [max_work] bit b set: block is processed for frame b of the batch
+  uint32_t* work_upd;    // [max_work] bit b set: some voxel of the block was updated by frame b
+  int max_work;
+  FrameView f[kMaxBatch];
 };
 
 struct TrackingParams {
@@ -56,7 +72,9 @@ struct MotionParams {
   uint8_t* pixel_seed;  // out: 1 if the pixel's voxel is ever-free
 };
 
-void launchIntegrate(const DeviceMap& m, const FrameParams& p, int grid, cudaStream_t s);
+void launchTileMax(const BatchParams& p, cudaStream_t s);
+void launchSelectBlocks(const DeviceMap& m, const BatchParams& p, cudaStream_t s);
+void launchFuse(const DeviceMap& m, const BatchParams& p, int grid, cudaStream_t s);
 void launchTracking(const DeviceMap& m, const TrackingParams& p, int n_slots, cudaStream_t s);
 void launchEverFree(const DeviceMap& m, const TrackingParams& p, int n_slots, cudaStream_t s);
 void launchResetInactive(const DeviceMap& m, int n_slots, int3* removed, int max_removed, cudaStream_t s);

@@ -66,6 +66,24 @@ int ko_integrate_frame(ko_handle* h, const kb_frame* f, int allocate_blocks, kb_
   return h->o->ok() ? KB_OK : fail(h, KB_ERR_INVALID);
 }
 
+int ko_integrate_frames(ko_handle* h, const kb_frame* frames, int32_t n, int allocate_blocks, kb_frame_stats* stats) {
+  if (!h || !frames) return KB_ERR_INVALID;
+  kb_frame_stats sum{};
+  for (int i = 0; i < n; ++i) {
+    kb_frame_stats s{};
+    const int st = ko_integrate_frame(h, frames + i, allocate_blocks, &s);
+    if (st != KB_OK) return st;
+    sum.blocks_in_frustum += s.blocks_in_frustum; sum.blocks_allocated += s.blocks_allocated;
+    sum.blocks_updated += s.blocks_updated; sum.voxels_updated += s.voxels_updated;
+    sum.voxels_in_band += s.voxels_in_band; sum.voxels_semantic += s.voxels_semantic;
+    sum.total_blocks = s.total_blocks;
+  }
+  if (stats) *stats = sum;
+  return KB_OK;
+}
+
+int ko_set_culling(ko_handle*, int) { return KB_OK; }
+
 int ko_get_totals(ko_handle* h, kb_frame_stats* t) {
   if (!h || !t) return KB_ERR_INVALID;
   *t = h->totals;

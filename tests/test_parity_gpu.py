@@ -237,3 +237,57 @@ def test_capacity_error_is_reported(product_lib):
     with pytest.raises(kb.KbError) as e:
         hs.run_fusion(g, frames, poses, stamps)
     assert e.value.status == 3
+
+
+@pytest.mark.parametrize("batch", [3, 32, 37])
+def test_batched_integration_equals_sequential(oracle_lib, product_lib, batch):
+    """kb_integrate_frames fuses up to 32 frames per launch with voxel state in registers; the result
+    must be identical to frame-by-frame integration (oracle runs strictly sequentially)."""
+    cam = hs.small_camera(4)
+    frames, poses, stamps = room_frames(cam, 40, laps=0.4)
+    o, g = both(oracle_lib, product_lib, cam=cam)
+    so = hs.run_fusion(o, frames, poses, stamps)
+    tot = {k: 0 for k in so[0]}
+    for i in range(0, len(frames), batch):
+        fr = [g.make_frame(d, T, st, label=l) for (d, l), T, st in zip(frames[i:i + batch], poses[i:i + batch], stamps[i:i + batch])]
+        s = g.integrate_frames(fr).as_dict()
+        want = {k: sum(x[k] for x in so[i:i + batch]) for k in s}
+        want["total_blocks"] = so[min(i + batch, len(so)) - 1]["total_blocks"]
+        assert s == want, (i, s, want)
+    hs.assert_blocks_equal(o.export_blocks(), g.export_blocks(), exact_float=True, what=f"batch{batch}")
+
+
+def test_culling_does_not_change_results(oracle_lib, product_lib):
+    """The conservative (block, frame) depth culling may only skip work that could not have produced a
+    valid measurement: maps with culling on and off are identical (hall scene: most blocks cull)."""
+    cam = hs.small_camera(4)
+    scene = syn.hall_scene(size=(20.0, 16.0, 6.0))
+    poses, stamps = syn.sweep_trajectory(24, size=(20.0, 16.0), margin=4.0, lanes=2, yaw_turns=1.5)
+    frames = hs.render_frames(scene, cam, poses, stamps)
+    o = hs.make_handle(oracle_lib, "ko_", cam=cam)
+    so = hs.run_fusion(o, frames, poses, stamps)
+    bo = o.export_blocks()
+    for cull in (True, False):
+        g = hs.make_handle(product_lib, "kb_", cam=cam)
+        g.set_culling(cull)
+        sg = hs.run_fusion(g, frames, poses, stamps)
+        assert sg == so
+        hs.assert_blocks_equal(bo, g.export_blocks(), exact_float=True, what=f"cull={cull}")
+
+
+def test_pinned_host_frames_overlap_path(oracle_lib, product_lib):
+    """KB_MEM_HOST frames go through the double-buffered copy stream; many back-to-back calls without
+    stats must still integrate every frame exactly once and in order."""
+    import torch
+    cam = hs.small_camera(4)
+    frames, poses, stamps = room_frames(cam, 70, laps=0.5)
+    o, g = both(oracle_lib, product_lib, cam=cam)
+    hs.run_fusion(o, frames, poses, stamps)
+    hd = torch.from_numpy(np.stack([f[0] for f in frames])).pin_memory()
+    hl = torch.from_numpy(np.stack([f[1] for f in frames])).pin_memory()
+    fr = [g.make_frame(hd[i].data_ptr(), poses[i], stamps[i], label=hl[i].data_ptr()) for i in range(len(frames))]
+    for i in range(0, 20):
+        g.integrate_frame(fr[i], want_stats=False)
+    g.integrate_frames(fr[20:], want_stats=False)
+    g.synchronize()
+    hs.assert_blocks_equal(o.export_blocks(), g.export_blocks(), exact_float=True, what="pinned")
