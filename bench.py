@@ -311,6 +311,7 @@ def main():
         run_step(s)
     barrier()
     tot0 = h.get_totals()
+    dbg0 = h.get_debug_counters()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -332,6 +333,8 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         gpu_ms = float(t.item())
     tot1 = h.get_totals()
+    dbg1 = h.get_debug_counters()
+    pairs = int((int(dbg1[17]) - int(dbg0[17])) & 0xFFFFFFFF)
 
     def delta(name):
         return (getattr(tot1, name) - getattr(tot0, name)) & 0xFFFFFFFF
@@ -410,7 +413,8 @@ def main():
                        "parallelism": "block-hash shard x%d, NCCL frame broadcast" % world if world > 1 else "single GPU",
                        "render_s": round(t_render, 1)},
             "per_frame": {"voxels_updated": nv_all / n_frames, "voxels_semantic": nsem_all / n_frames,
-                          "blocks_visited": nblk_all / n_frames},
+                          "blocks_visited": nblk_all / n_frames,
+                          "block_frame_pairs_after_k0_culling_rank0": pairs / n_frames},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": None,
                          "kernel": "fuseKernel<16> (+ its tileMax/selectBlocks prologue; one launch triple per %d frames)" % B,

@@ -173,6 +173,10 @@ int kb_integrate_frame(kb_handle* h, const kb_frame* frame, int allocate_blocks,
 int kb_integrate_frames(kb_handle* h, const kb_frame* frames, int32_t n_frames, int allocate_blocks,
                         kb_frame_stats* stats);
 
+/* Raw cumulative device counters (diagnostics; layout = enum Counter in csrc/kb_device.cuh). Writes
+ * min(n, available) values. Index 17 = (block, frame) pairs that survived K0 culling. */
+int kb_get_debug_counters(kb_handle* h, int32_t* out, int32_t n);
+
 /* Enables (default) / disables the conservative per-(block, frame) depth culling. Results do not
  * depend on this switch; it exists so tests can prove that. */
 int kb_set_culling(kb_handle* h, int enabled);

@@ -253,6 +253,11 @@ class MapHandle:
                                                  C.byref(stats) if want_stats else None))
         return stats if want_stats else None
 
+    def get_debug_counters(self, n=24) -> np.ndarray:
+        out = np.zeros(n, np.int32)
+        self._check(self._fn("get_debug_counters")(self._h, C.c_void_p(out.ctypes.data), n))
+        return out
+
     def set_culling(self, enabled: bool):
         self._check(self._fn("set_culling")(self._h, int(enabled)))
 

@@ -46,6 +46,7 @@ struct kb_handle {
   // batched integration
   BatchParams batch{};
   float* tile_max = nullptr;
+  size_t tile_stride = 0;
   int* work_slots = nullptr;
   uint32_t* work_masks = nullptr;
   uint32_t* work_upd = nullptr;
@@ -276,7 +277,7 @@ int kb_create(const kb_map_config* map, const kb_integrator_config* integ, const
     {
       cudaDeviceProp prop{};
       KB_CUDA(h, cudaGetDeviceProperties(&prop, device));
-      h->fuse_grid = prop.multiProcessorCount * 8;  // persistent CTAs; idle ones exit immediately
+      h->fuse_grid = prop.multiProcessorCount * 8;  // persistent 128-thread CTAs (independent warps)
     }
     h->max_removed = m.max_blocks;
     KB_CUDA(h, devAlloc(&h->d_removed, static_cast<size_t>(h->max_removed), 0));
@@ -372,16 +373,28 @@ int kb_set_camera(kb_handle* h, const kb_camera* cam) {
   p.mle_diag = h->mle_diag; p.mle_off = h->mle_off; p.mle_init = h->mle_init;
   p.blocked_mask = h->blocked_mask;
   p.with_tracking = h->map.with_tracking;
-  p.tiles_x = (c.width + 15) / 16;
-  p.tiles_y = (c.height + 15) / 16;
+  p.tiles8_x = (c.width + 7) / 8;
+  p.tiles8_y = (c.height + 7) / 8;
+  p.tiles16_x = (p.tiles8_x + 1) / 2;
+  p.tiles16_y = (p.tiles8_y + 1) / 2;
+  h->tile_stride = static_cast<size_t>(p.tiles8_x) * p.tiles8_y + static_cast<size_t>(p.tiles16_x) * p.tiles16_y;
   p.work_slots = h->work_slots;
   p.work_masks = h->work_masks;
   p.work_upd = h->work_upd;
   p.max_work = h->dm.max_blocks;
   cudaFree(h->tile_max);
   h->tile_max = nullptr;
-  KB_CUDA(h, devAlloc(&h->tile_max, static_cast<size_t>(p.tiles_x) * p.tiles_y * kMaxBatch, 0));
+  KB_CUDA(h, devAlloc(&h->tile_max, h->tile_stride * kMaxBatch, 0));
   return ensureMotionBuffers(h, static_cast<size_t>(c.width) * c.height);
+}
+
+int kb_get_debug_counters(kb_handle* h, int32_t* out, int32_t n) {
+  if (!h || !out) return KB_ERR_INVALID;
+  KB_CUDA(h, cudaSetDevice(h->device));
+  int st = readCounters(h);
+  if (st != KB_OK) return st;
+  for (int i = 0; i < std::min<int>(n, kNumCounters); ++i) out[i] = h->h_ctr[i];
+  return KB_OK;
 }
 
 int kb_set_culling(kb_handle* h, int enabled) {
@@ -447,7 +460,8 @@ static int integrateBatch(kb_handle* h, const kb_frame* frames, int n, int alloc
       if (f.mask) { v.mask = h->stg_mask + off; if ((st = up(f.mask, h->stg_mask + off, px * 4)) != KB_OK) return st; }
       if (f.object_image) { v.object_image = h->stg_object + off; if ((st = up(f.object_image, h->stg_object + off, px * 4)) != KB_OK) return st; }
     }
-    v.tile_max = h->tile_max + static_cast<size_t>(b) * p.tiles_x * p.tiles_y;
+    v.tile8 = h->tile_max + static_cast<size_t>(b) * h->tile_stride;
+    v.tile16 = v.tile8 + static_cast<size_t>(p.tiles8_x) * p.tiles8_y;
     if (allocate_blocks) {
       const float reach = c.max_range + p.infl;
       const float inv = 1.f / h->block_size;

@@ -62,7 +62,7 @@ enum Counter {
   kCtrErased = 14,
   kCtrWork0 = 15,  // two work-list counters used alternately by consecutive batches
   kCtrWork1 = 16,
-  kCtrFramesCulled = 17,
+  kCtrPairs = 17,  // (block, frame) pairs that survived K0 culling
   kNumCounters = 24
 };
 

@@ -23,6 +23,7 @@ namespace kb {
 namespace {
 
 constexpr int kThreads = 256;
+constexpr int kFuseThreads = 128;  // 4 independent warps per CTA
 
 __device__ __forceinline__ void xform(const float* R, const float* t, float x, float y, float z,
                                       float& ox, float& oy, float& oz) {
@@ -141,64 +142,98 @@ __device__ __forceinline__ int warpSum(int v) {
   return v;
 }
 
-// ---- per-frame 16x16 tile maxima of the depth image (input of the conservative block culling) -------
-constexpr int kTile = 16;
+// ---- per-frame tile maxima of the depth image (input of the conservative culling) ---------------------
+// Two levels: 8x8-pixel tiles (work-item culling in K1) and 16x16-pixel tiles (block culling in K0).
+// One warp reduces an 8-row x 32-column strip: coalesced row reads, vertical max in registers,
+// horizontal max over 8-lane groups by shuffles -> four 8x8 maxima per warp.
 __global__ void __launch_bounds__(256) tileMaxKernel(const __grid_constant__ BatchParams p) {
   const int b = blockIdx.y;
-  const int tx = blockIdx.x % p.tiles_x, ty = blockIdx.x / p.tiles_x;
-  const int u = tx * kTile + (threadIdx.x & 15), v = ty * kTile + (threadIdx.x >> 4);
+  const int warps_x = (p.W + 31) / 32;
+  const int warp = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (warp >= warps_x * p.tiles8_y) return;
+  const int ty = warp / warps_x, wx = warp % warps_x;
+  const int u = wx * 32 + lane;
+  const float* __restrict__ depth = p.f[b].depth;
   float d = 0.f;
-  if (u < p.W && v < p.H) d = __ldg(&p.f[b].depth[v * p.W + u]);
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) d = fmaxf(d, __shfl_xor_sync(0xffffffffu, d, o));
-  __shared__ float s[8];
-  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = d;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float m = s[0];
-#pragma unroll
-    for (int i = 1; i < 8; ++i) m = fmaxf(m, s[i]);
-    const_cast<float*>(p.f[b].tile_max)[blockIdx.x] = m;
+  for (int r = 0; r < 8; ++r) {
+    const int v = ty * 8 + r;
+    if (u < p.W && v < p.H) d = fmaxf(d, __ldg(&depth[v * p.W + u]));
   }
+  d = fmaxf(d, __shfl_xor_sync(0xffffffffu, d, 1));
+  d = fmaxf(d, __shfl_xor_sync(0xffffffffu, d, 2));
+  d = fmaxf(d, __shfl_xor_sync(0xffffffffu, d, 4));
+  const int tx = wx * 4 + (lane >> 3);
+  if ((lane & 7) == 0 && tx < p.tiles8_x) p.f[b].tile8[ty * p.tiles8_x + tx] = d;
 }
 
-// True if NO voxel of the block can receive a valid measurement from frame b, so the whole
-// (block, frame) pair can be skipped without changing any result (SURVEY §7 hard part 4): either the
-// block projects entirely outside the image, or every depth pixel its voxels could tap is invalid, or
-// every voxel lies more than the truncation distance behind the farthest of those depths
-// (sdf < -trunc). Uses margins (1 mm, 2 px) far above the fp32 rounding of the per-voxel arithmetic.
-__device__ __forceinline__ bool blockCulled(const BatchParams& p, const FrameView& f, float ox, float oy, float oz) {
-  const float lo = 0.5f * p.voxel_size, hi = p.block_size - 0.5f * p.voxel_size;
-  float zmin = 3.0e38f, umin = 3.0e38f, umax = -3.0e38f, vmin = 3.0e38f, vmax = -3.0e38f;
+__global__ void __launch_bounds__(256) tileMax16Kernel(const __grid_constant__ BatchParams p) {
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= p.tiles16_x * p.tiles16_y) return;
+  const int tx = t % p.tiles16_x, ty = t / p.tiles16_x;
+  float d = 0.f;
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    float x, y, z;
-    xform(f.R, f.t, ox + ((c & 1) ? hi : lo), oy + ((c & 2) ? hi : lo), oz + ((c & 4) ? hi : lo), x, y, z);
-    if (z < 1e-2f) return false;  // block reaches behind / near the camera plane: keep
-    const float u = p.fx * x / z + p.cx, v = p.fy * y / z + p.cy;
-    zmin = fminf(zmin, z);
-    umin = fminf(umin, u); umax = fmaxf(umax, u);
-    vmin = fminf(vmin, v); vmax = fmaxf(vmax, v);
+  for (int j = 0; j < 2; ++j)
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int x = tx * 2 + i, y = ty * 2 + j;
+      if (x < p.tiles8_x && y < p.tiles8_y) d = fmaxf(d, p.f[b].tile8[y * p.tiles8_x + x]);
+    }
+  p.f[b].tile16[t] = d;
+}
+
+// Conservative culling test for an axis-aligned box of voxel centres [lo, hi] (world frame) against
+// frame f: true if NO voxel centre inside the box can receive a valid measurement, so skipping the
+// (box, frame) pair cannot change any result (SURVEY §7 hard part 4): the box projects entirely outside
+// the image, or every depth pixel its voxels could tap is invalid, or every voxel lies more than the
+// truncation distance behind the farthest of those depths (sdf < -trunc). Margins (1 mm, 2 px) are far
+// above the fp32 rounding of the per-voxel arithmetic. Executed by a full warp: lanes 0-7 project
+// the corners, all lanes scan the tile rectangle. Returns the same value in every lane.
+__device__ __forceinline__ bool boxCulledWarp(const BatchParams& p, const FrameView& f, const float* __restrict__ tiles,
+                                              int tiles_x, int tile_shift, float lox, float loy, float loz,
+                                              float hix, float hiy, float hiz, int lane) {
+  const int c = lane & 7;
+  float x, y, z;
+  xform(f.R, f.t, (c & 1) ? hix : lox, (c & 2) ? hiy : loy, (c & 4) ? hiz : loz, x, y, z);
+  const bool behind = z < 1e-2f;
+  const float zs = behind ? 1.f : z;
+  float u = p.fx * x / zs + p.cx, v = p.fy * y / zs + p.cy;
+  float zmin = z, umin = u, umax = u, vmin = v, vmax = v;
+#pragma unroll
+  for (int o = 1; o < 8; o <<= 1) {
+    zmin = fminf(zmin, __shfl_xor_sync(0xffffffffu, zmin, o));
+    umin = fminf(umin, __shfl_xor_sync(0xffffffffu, umin, o));
+    umax = fmaxf(umax, __shfl_xor_sync(0xffffffffu, umax, o));
+    vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+    vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
   }
+  if (__any_sync(0xffffffffu, behind)) return false;  // box reaches behind / near the camera plane: keep
   if (umax < -0.5f || vmax < -0.5f || umin > static_cast<float>(p.W - 1) + 0.5f || vmin > static_cast<float>(p.H - 1) + 0.5f)
     return true;  // projects entirely outside the image
   const int u0 = max(static_cast<int>(floorf(umin)) - 2, 0), u1 = min(static_cast<int>(floorf(umax)) + 3, p.W - 1);
   const int v0 = max(static_cast<int>(floorf(vmin)) - 2, 0), v1 = min(static_cast<int>(floorf(vmax)) + 3, p.H - 1);
-  const int tx0 = u0 / kTile, tx1 = u1 / kTile, ty0 = v0 / kTile, ty1 = v1 / kTile;
-  if ((tx1 - tx0 + 1) * (ty1 - ty0 + 1) > 96) return false;  // large footprint (near block): keep
+  const int tx0 = u0 >> tile_shift, ty0 = v0 >> tile_shift;
+  const int nx = (u1 >> tile_shift) - tx0 + 1, ny = (v1 >> tile_shift) - ty0 + 1;
+  const int n = nx * ny;
+  if (n > 512) return false;  // huge footprint (box right in front of the camera): keep
   float dmax = 0.f;
-  for (int ty = ty0; ty <= ty1; ++ty)
-    for (int tx = tx0; tx <= tx1; ++tx) dmax = fmaxf(dmax, __ldg(&f.tile_max[ty * p.tiles_x + tx]));
-  if (!(dmax > 0.f)) return true;                 // no valid depth anywhere in the footprint
-  return zmin - p.trunc - 1e-3f > dmax;           // everything is beyond the truncation band
+  for (int i = lane; i < n; i += 32) dmax = fmaxf(dmax, __ldg(&tiles[(ty0 + i / nx) * tiles_x + tx0 + i % nx]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) dmax = fmaxf(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+  if (!(dmax > 0.f)) return true;       // no valid depth anywhere in the footprint
+  return zmin - p.trunc - 1e-3f > dmax;  // everything is beyond the truncation band
 }
 
 // ---- K0: block selection for a batch of frames ---------------------------------------------------------
-// One thread per candidate block of the batch's AABB (allocate mode; hydra findBlocksInViewFrustum,
+// One WARP per candidate block of the batch's AABB (allocate mode; hydra findBlocksInViewFrustum,
 // SURVEY App. A.5) or per pool slot (allocate == 0: all allocated blocks, mesh_object_extractor.cpp:242).
+// Lane b evaluates frame b of the batch: frustum test -> ballot -> 32-bit frame mask.
 __global__ void __launch_bounds__(128) selectBlocksKernel(const DeviceMap m, const __grid_constant__ BatchParams p) {
-  const int c0 = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c0 == 0) m.counters[kCtrWork0 + (p.parity ^ 1)] = 0;  // the next batch's work counter
+  const int c0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (c0 == 0 && lane == 0) m.counters[kCtrWork0 + (p.parity ^ 1)] = 0;  // the next batch's work counter
   int slot = -1, bx = 0, by = 0, bz = 0;
   uint32_t mask = 0;
   int created = 0;
@@ -212,14 +247,17 @@ __global__ void __launch_bounds__(128) selectBlocksKernel(const DeviceMap m, con
     const float cx = (static_cast<float>(bx) + 0.5f) * p.block_size;
     const float cy = (static_cast<float>(by) + 0.5f) * p.block_size;
     const float cz = (static_cast<float>(bz) + 0.5f) * p.block_size;
-    for (int b = 0; b < p.n_frames; ++b) {
+    bool in = false;
+    if (lane < p.n_frames) {
       float x, y, z;
-      xform(p.f[b].R, p.f[b].t, cx, cy, cz, x, y, z);
-      if (inFrustum(p, x, y, z)) mask |= 1u << b;
+      xform(p.f[lane].R, p.f[lane].t, cx, cy, cz, x, y, z);
+      in = inFrustum(p, x, y, z);
     }
+    mask = __ballot_sync(0xffffffffu, in);
     if (!mask) return;
     if (p.nranks > 1 && blockOwner(bx, by, bz, p.nranks) != p.rank) return;
-    slot = hashFindOrInsert(m, bx, by, bz, &created);
+    if (lane == 0) slot = hashFindOrInsert(m, bx, by, bz, &created);
+    slot = __shfl_sync(0xffffffffu, slot, 0);
     if (slot < 0) return;
   } else {
     if (c0 >= p.n_slots || !(m.block_flags[c0] & kFlagAllocated)) return;
@@ -228,24 +266,30 @@ __global__ void __launch_bounds__(128) selectBlocksKernel(const DeviceMap m, con
     bx = bi.x; by = bi.y; bz = bi.z;
     mask = p.n_frames >= 32 ? 0xffffffffu : ((1u << p.n_frames) - 1u);
   }
-  atomicAdd(&m.counters[kCtrFrustum], __popc(mask));
-  if (created) atomicAdd(&m.counters[kCtrAllocated], 1);
+  if (lane == 0) {
+    atomicAdd(&m.counters[kCtrFrustum], __popc(mask));
+    if (created) atomicAdd(&m.counters[kCtrAllocated], 1);
+  }
   if (p.cull) {
     const float ox = static_cast<float>(bx) * p.block_size, oy = static_cast<float>(by) * p.block_size,
                 oz = static_cast<float>(bz) * p.block_size;
+    const float lo = 0.5f * p.voxel_size, hi = p.block_size - 0.5f * p.voxel_size;
     uint32_t rem = mask;
     while (rem) {
       const int b = __ffs(rem) - 1;
       rem &= rem - 1;
-      if (blockCulled(p, p.f[b], ox, oy, oz)) mask &= ~(1u << b);
+      if (boxCulledWarp(p, p.f[b], p.f[b].tile16, p.tiles16_x, 4, ox + lo, oy + lo, oz + lo, ox + hi, oy + hi, oz + hi, lane))
+        mask &= ~(1u << b);
     }
     if (!mask) return;
   }
+  if (lane != 0) return;
   // Blocks that may receive measurements get their semantic slot here (one thread per block, so no
   // allocation race inside the fuse kernel); never-measured blocks cost no semantic memory.
   if (p.L > 0 && m.block_sem[slot] < 0) {
     m.block_sem[slot] = allocSlot(m.counters, kCtrSemHwm, kCtrSemFreeCount, m.sem_free_list, m.max_sem);
   }
+  atomicAdd(&m.counters[kCtrPairs], __popc(mask));
   const int i = atomicAdd(&m.counters[kCtrWork0 + p.parity], 1);
   if (i < p.max_work) {
     p.work_slots[i] = slot;
@@ -257,63 +301,73 @@ __global__ void __launch_bounds__(128) selectBlocksKernel(const DeviceMap m, con
 }
 
 // ---- K1: projective TSDF + semantic fusion ----------------------------------------------------------------
-// Persistent CTAs stride over work items = (selected block, z-slab). Thread (x, y) of the 16x16 slab
-// face owns NV voxels stacked in z and keeps their {distance, weight, last_observed} in registers
-// while it walks the frames of the batch in order, so a voxel's TSDF is read and written once per
-// batch, warp accesses are 256 B coalesced, and the NV independent gather chains give ILP.
+// Persistent warps stride over work items = (selected block, 4x8x4-voxel box). Lane (x, y) of the 4x8
+// box face owns the 4 voxels stacked in z and keeps their {distance, weight, last_observed} in registers
+// while the warp walks the frames of the batch in order: a voxel's TSDF is read and written once per
+// batch, the four gather chains per lane are independent (ILP), every warp access covers whole 32 B
+// sectors, and the compact box keeps a warp's image taps in one small neighbourhood. Warps never
+// synchronise with each other (no shared memory, no CTA barrier). Each (item, frame) pair is first
+// tested by the conservative box culling against the 8x8 tile maxima.
 // ProjectiveIntegrator::updateBlock / getVoxelMeasurement / computeLabel / updateVoxel (UP App. A.6;
 // computeLabel structure pinned by khronos/src/active_window/integration/object_integrator.cpp:58-81).
 template <int VPS>
-__global__ void __launch_bounds__(kThreads) fuseKernel(const DeviceMap m, const __grid_constant__ BatchParams p) {
+__global__ void __launch_bounds__(kFuseThreads, 8) fuseKernel(const DeviceMap m, const __grid_constant__ BatchParams p) {
   constexpr int V = VPS * VPS * VPS;
-  constexpr int PARTS = VPS == 16 ? 4 : 1;
-  constexpr int NV = V / PARTS / kThreads;  // voxels per thread: 4 (16^3) or 2 (8^3)
-  __shared__ int s_cnt[3];
-  __shared__ uint32_t s_upd;
-  const int tid = threadIdx.x;
-  const int n_items = min(m.counters[kCtrWork0 + p.parity], p.max_work) * PARTS;
+  constexpr int NV = 4;                          // voxels per lane (stacked in z)
+  constexpr int IX = VPS / 4, IY = VPS / 8, IZ = VPS / NV;
+  constexpr int ITEMS = IX * IY * IZ;            // 32 (16^3) or 4 (8^3) items of 128 voxels per block
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * kFuseThreads + threadIdx.x) >> 5;
+  const int n_warps = (gridDim.x * kFuseThreads) >> 5;
+  const int n_items = min(m.counters[kCtrWork0 + p.parity], p.max_work) * ITEMS;
   const bool binary = p.sem_mode == KB_SEMANTICS_BINARY;
+  int n_valid = 0, n_band = 0, n_sem = 0;
 
-  for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
-    const int wi = w / PARTS, part = w % PARTS;
+  for (int w = warp; w < n_items; w += n_warps) {
+    const int wi = w / ITEMS, it = w % ITEMS;
     const int slot = p.work_slots[wi];
     const uint32_t fmask = p.work_masks[wi];
     const int3 bi = m.block_index[slot];
     const int sem = p.L > 0 ? m.block_sem[slot] : -1;
-    if (tid == 0) { s_cnt[0] = s_cnt[1] = s_cnt[2] = 0; s_upd = 0; }
-    __syncthreads();
+    const int x0 = (it % IX) * 4, y0 = ((it / IX) % IY) * 8, z0 = (it / (IX * IY)) * NV;
+    const int vx = x0 + (lane & 3), vy = y0 + (lane >> 2);
+    const int lin0 = vx + VPS * (vy + VPS * z0);  // voxel k of this lane: lin0 + k*VPS*VPS
 
     const float ox = static_cast<float>(bi.x) * p.block_size;
     const float oy = static_cast<float>(bi.y) * p.block_size;
     const float oz = static_cast<float>(bi.z) * p.block_size;
     float2* __restrict__ tsdf = m.tsdf + static_cast<size_t>(slot) * V;
-    float wx[NV], wy[NV], wz[NV];
+    const float wx = ox + (static_cast<float>(vx) + 0.5f) * p.voxel_size;
+    const float wy = oy + (static_cast<float>(vy) + 0.5f) * p.voxel_size;
+    float wz[NV];
     float2 st[NV];
     uint32_t lobs[NV];
-    uint32_t have = 0, touched = 0;
+    uint32_t have = 0, touched = 0, upd_frames = 0;
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
-      const int lin = part * (V / PARTS) + k * kThreads + tid;
-      const int vx = lin % VPS, vy = (lin / VPS) % VPS, vz = lin / (VPS * VPS);
-      wx[k] = ox + (static_cast<float>(vx) + 0.5f) * p.voxel_size;
-      wy[k] = oy + (static_cast<float>(vy) + 0.5f) * p.voxel_size;
-      wz[k] = oz + (static_cast<float>(vz) + 0.5f) * p.voxel_size;
+      wz[k] = oz + (static_cast<float>(z0 + k) + 0.5f) * p.voxel_size;
       st[k] = make_float2(0.f, 0.f);
       lobs[k] = 0;
     }
-    int n_valid = 0, n_band = 0, n_sem = 0;
-    uint32_t upd_frames = 0;
+    // box of this item's voxel centres (for culling)
+    const float blx = ox + (static_cast<float>(x0) + 0.5f) * p.voxel_size, bhx = ox + (static_cast<float>(x0 + 3) + 0.5f) * p.voxel_size;
+    const float bly = oy + (static_cast<float>(y0) + 0.5f) * p.voxel_size, bhy = oy + (static_cast<float>(y0 + 7) + 0.5f) * p.voxel_size;
+    const float blz = oz + (static_cast<float>(z0) + 0.5f) * p.voxel_size, bhz = oz + (static_cast<float>(z0 + NV - 1) + 0.5f) * p.voxel_size;
 
     uint32_t rem = fmask;
     while (rem) {
       const int b = __ffs(rem) - 1;
       rem &= rem - 1;
       const FrameView& f = p.f[b];
-      const bool has_sem = sem >= 0 && (binary ? f.object_image != nullptr : f.label != nullptr);
+      if (p.cull && boxCulledWarp(p, f, f.tile8, p.tiles8_x, 3, blx, bly, blz, bhx, bhy, bhz, lane)) continue;
+      const bool has_label_img = p.L > 0 && (binary ? f.object_image != nullptr : f.label != nullptr);
+      // p_C = ((R0*x + R1*y) + R2*z) + t: the (x, y) partial sums are shared by the lane's 4 voxels
+      const float ax = f.R[0] * wx + f.R[1] * wy, ay = f.R[3] * wx + f.R[4] * wy, az = f.R[6] * wx + f.R[7] * wy;
 #pragma unroll
       for (int k = 0; k < NV; ++k) {
-        float x, y, z;
-        xform(f.R, f.t, wx[k], wy[k], wz[k], x, y, z);
+        const float x = (ax + f.R[2] * wz[k]) + f.t[0];
+        const float y = (ay + f.R[5] * wz[k]) + f.t[1];
+        const float z = (az + f.R[8] * wz[k]) + f.t[2];
         if (z <= 0.f) continue;
         const float u = p.fx * x / z + p.cx;
         const float v = p.fy * y / z + p.cy;
@@ -325,21 +379,19 @@ __global__ void __launch_bounds__(kThreads) fuseKernel(const DeviceMap m, const 
         if (sdf < -p.trunc) continue;
         const bool in_band = fabsf(sdf) < p.trunc;
         uint32_t label = 0;
-        bool have_label = false;
         if (in_band) {
           if (f.mask != nullptr && tapID(p, f.mask, taps) != 0) continue;
-          if (p.L > 0 && (binary ? f.object_image != nullptr : f.label != nullptr)) {
+          if (has_label_img) {
             if (binary) {
               label = tapID(p, f.object_image, taps) == f.target_id ? 1u : 0u;
             } else {
               label = static_cast<uint32_t>(tapID(p, f.label, taps));
               if (label < static_cast<uint32_t>(KB_MAX_LABELS) && ((p.blocked_mask >> label) & 1ull)) continue;
             }
-            have_label = true;
           }
         }
         const float wm = measurementWeight(p, z, sdf);
-        const int lin = part * (V / PARTS) + k * kThreads + tid;
+        const int lin = lin0 + k * VPS * VPS;
         if (!((have >> k) & 1u)) { st[k] = tsdf[lin]; have |= 1u << k; }
         const float sdf_c = fminf(fmaxf(sdf, -p.trunc), p.trunc);
         const float2 old = st[k];
@@ -351,7 +403,7 @@ __global__ void __launch_bounds__(kThreads) fuseKernel(const DeviceMap m, const 
         ++n_valid;
         if (!in_band) continue;
         ++n_band;
-        if (has_sem && have_label && label < static_cast<uint32_t>(p.L)) {
+        if (sem >= 0 && has_label_img && label < static_cast<uint32_t>(p.L)) {
           // SemanticIntegrator::updateLikelihoods (UP App. A.8) on the voxel's likelihood row
           uint16_t* __restrict__ slabel = m.sem_label + static_cast<size_t>(sem) * V;
           const bool empty = slabel[lin] == kSemEmpty;
@@ -385,40 +437,40 @@ __global__ void __launch_bounds__(kThreads) fuseKernel(const DeviceMap m, const 
       }
     }
 
-    // ---- write the voxel state back once, then block flags + counters ----
+    // ---- write the voxel state back once; block flags + per-(block, frame) update bookkeeping ----
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
       if ((touched >> k) & 1u) {
-        const int lin = part * (V / PARTS) + k * kThreads + tid;
+        const int lin = lin0 + k * VPS * VPS;
         tsdf[lin] = st[k];
         if (p.with_tracking) m.last_obs[static_cast<size_t>(slot) * V + lin] = lobs[k];
       }
     }
-    const int wv = warpSum(n_valid);
-    if (wv) {  // warp-uniform
-      const int wb = warpSum(n_band), ws = warpSum(n_sem);
-      uint32_t uf = upd_frames;
+    if (__any_sync(0xffffffffu, touched != 0)) {
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) uf |= __shfl_xor_sync(0xffffffffu, uf, o);
-      if ((tid & 31) == 0) {
-        atomicAdd(&s_cnt[0], wv);
-        if (wb) atomicAdd(&s_cnt[1], wb);
-        if (ws) atomicAdd(&s_cnt[2], ws);
-        atomicOr(&s_upd, uf);
+      for (int o = 16; o > 0; o >>= 1) upd_frames |= __shfl_xor_sync(0xffffffffu, upd_frames, o);
+      if (lane == 0) {
+        const uint32_t all = KB_FLAG_UPDATED | KB_FLAG_MESH_UPDATED | KB_FLAG_ESDF_UPDATED | KB_FLAG_TRACKING_UPDATED;
+        if ((m.block_flags[slot] & all) != all) atomicOr(&m.block_flags[slot], all);
+        // blocks_updated counts (block, frame) pairs once even though several items report them
+        if ((p.work_upd[wi] & upd_frames) != upd_frames) {
+          const uint32_t prev = atomicOr(&p.work_upd[wi], upd_frames);
+          const int fresh = __popc(upd_frames & ~prev);
+          if (fresh) atomicAdd(&m.counters[kCtrBlocksUpdated], fresh);
+        }
       }
     }
-    __syncthreads();
-    if (tid == 0 && s_cnt[0] > 0) {
-      atomicOr(&m.block_flags[slot], static_cast<uint32_t>(KB_FLAG_UPDATED | KB_FLAG_MESH_UPDATED | KB_FLAG_ESDF_UPDATED | KB_FLAG_TRACKING_UPDATED));
-      // blocks_updated counts (block, frame) pairs once even though several z-slabs report them
-      const uint32_t prev = atomicOr(&p.work_upd[wi], s_upd);
-      const int fresh = __popc(s_upd & ~prev);
-      if (fresh) atomicAdd(&m.counters[kCtrBlocksUpdated], fresh);
-      atomicAdd(&m.counters[kCtrVoxelsUpdated], s_cnt[0]);
-      if (s_cnt[1]) atomicAdd(&m.counters[kCtrVoxelsBand], s_cnt[1]);
-      if (s_cnt[2]) atomicAdd(&m.counters[kCtrVoxelsSemantic], s_cnt[2]);
+  }
+  // ---- counters: one atomic set per warp for the whole launch ----
+  n_valid = warpSum(n_valid);
+  if (n_valid) {
+    n_band = warpSum(n_band);
+    n_sem = warpSum(n_sem);
+    if (lane == 0) {
+      atomicAdd(&m.counters[kCtrVoxelsUpdated], n_valid);
+      if (n_band) atomicAdd(&m.counters[kCtrVoxelsBand], n_band);
+      if (n_sem) atomicAdd(&m.counters[kCtrVoxelsSemantic], n_sem);
     }
-    __syncthreads();
   }
 }
 
@@ -685,17 +737,18 @@ __global__ void gatherSemanticKernel(const DeviceMap m, const int* slots, int L,
 }  // namespace
 
 void launchTileMax(const BatchParams& p, cudaStream_t s) {
-  dim3 grid(p.tiles_x * p.tiles_y, p.n_frames);
-  tileMaxKernel<<<grid, 256, 0, s>>>(p);
+  const int warps = ((p.W + 31) / 32) * p.tiles8_y;
+  tileMaxKernel<<<dim3((warps + 7) / 8, p.n_frames), 256, 0, s>>>(p);
+  tileMax16Kernel<<<dim3((p.tiles16_x * p.tiles16_y + 255) / 256, p.n_frames), 256, 0, s>>>(p);
 }
 void launchSelectBlocks(const DeviceMap& m, const BatchParams& p, cudaStream_t s) {
   const int n = p.allocate ? p.dims[0] * p.dims[1] * p.dims[2] : p.n_slots;
-  selectBlocksKernel<<<(std::max(n, 1) + 127) / 128, 128, 0, s>>>(m, p);
+  selectBlocksKernel<<<(std::max(n, 1) + 3) / 4, 128, 0, s>>>(m, p);  // one warp per candidate
 }
 void launchFuse(const DeviceMap& m, const BatchParams& p, int grid, cudaStream_t s) {
   if (grid <= 0) return;
-  if (m.vps == 16) fuseKernel<16><<<grid, kThreads, 0, s>>>(m, p);
-  else fuseKernel<8><<<grid, kThreads, 0, s>>>(m, p);
+  if (m.vps == 16) fuseKernel<16><<<grid, kFuseThreads, 0, s>>>(m, p);
+  else fuseKernel<8><<<grid, kFuseThreads, 0, s>>>(m, p);
 }
 void launchTracking(const DeviceMap& m, const TrackingParams& p, int n, cudaStream_t s) {
   if (n > 0) trackingKernel<<<n, kThreads, 0, s>>>(m, p);

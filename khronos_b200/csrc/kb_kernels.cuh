@@ -14,7 +14,8 @@ struct FrameView {
   const int* label;
   const int* mask;
   const int* object_image;
-  const float* tile_max;  // per-frame 16x16 tile maxima of depth (conservative block culling), or null
+  float* tile8;   // per-frame 8x8-pixel tile maxima of depth (K1 work-item culling)
+  float* tile16;  // per-frame 16x16-pixel tile maxima (K0 block culling)
   uint32_t frame_idx;
   int target_id;
 };
@@ -41,8 +42,8 @@ struct BatchParams {
   int with_tracking;
   int n_frames;
   int parity;          // which of the two work-list counters this batch uses
-  int cull;            // 1: use tile_max culling
-  int tiles_x, tiles_y;
+  int cull;            // 1: conservative depth culling enabled
+  int tiles8_x, tiles8_y, tiles16_x, tiles16_y;
   int* work_slots;     // [max_work] selected block slots
   uint32_t* work_masks;  // [max_work] bit b set: block is processed for frame b of the batch
   uint32_t* work_upd;    // [max_work] bit b set: some voxel of the block was updated by frame b

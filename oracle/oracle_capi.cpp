@@ -83,6 +83,7 @@ int ko_integrate_frames(ko_handle* h, const kb_frame* frames, int32_t n, int all
 }
 
 int ko_set_culling(ko_handle*, int) { return KB_OK; }
+int ko_get_debug_counters(ko_handle*, int32_t* out, int32_t n) { for (int i = 0; i < n; ++i) out[i] = 0; return KB_OK; }
 
 int ko_get_totals(ko_handle* h, kb_frame_stats* t) {
   if (!h || !t) return KB_ERR_INVALID;
