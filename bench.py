@@ -277,16 +277,23 @@ def main():
     else:
         prebuilt = {s: make_step_batches(s, depth, label, None) for s in range(Wm + K)}
 
+    buf_free = [torch.cuda.Event(), torch.cuda.Event()] if world > 1 else None  # rx[b] no longer read by kernels
+
     def run_step(step, sample_events=None):
         if world > 1:
-            db, lb = rx[step % 2]
+            # double-buffered: the broadcast of step s+1 (torch's stream) overlaps the fusion of step s
+            # (the handle's stream); rx[b] is overwritten only after the kernels of step s-2 are done
+            bsel = step % 2
+            db, lb = rx[bsel]
+            cur = torch.cuda.current_stream()
+            cur.wait_event(buf_free[bsel])
             if rank == 0:
                 idx = torch.tensor([frame_index(step, j) for j in range(F)], device=dev)
-                db.copy_(depth.index_select(0, idx))
-                lb.copy_(label.index_select(0, idx))
+                torch.index_select(depth, 0, idx, out=db)
+                torch.index_select(label, 0, idx, out=lb)
             dist.broadcast(db, 0)
             dist.broadcast(lb, 0)
-            stream.wait_stream(torch.cuda.current_stream())
+            stream.wait_stream(cur)
         with torch.cuda.stream(stream):
             for j, (arr, n) in enumerate(prebuilt[step]):
                 if sample_events is not None and j % 4 == 2:
@@ -299,8 +306,8 @@ def main():
                     st = integrate_n(hptr, arr, n, 1, None)
                 if st != 0:
                     raise RuntimeError(f"kb_integrate_frames failed: {st}")
-        if world > 1:
-            torch.cuda.current_stream().wait_stream(stream)
+            if world > 1:
+                buf_free[step % 2].record(stream)
 
     def barrier():
         if world > 1:

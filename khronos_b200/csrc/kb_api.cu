@@ -50,7 +50,15 @@ struct kb_handle {
   int* work_slots = nullptr;
   uint32_t* work_masks = nullptr;
   uint32_t* work_upd = nullptr;
+  uint32_t* item_fmask = nullptr;
+  int cull_grid = 0;
   int parity = 0;
+  // lazy tracking
+  TrackEval pass{};           // state of the last tracking pass
+  float trk_cfg_thr = 0.f;    // occupancy threshold in metres
+  uint64_t last_pass_stamp = 0;
+  int* pending = nullptr;     // ever-free work list
+  int everfree_grid = 0;
   bool cull = true;
   int fuse_grid = 0;
   bool hwm_dirty = true;
@@ -155,6 +163,19 @@ int frameIndex(kb_handle* h, uint64_t stamp, uint32_t* idx) {
   }
   h->stamps.push_back(stamp);
   *idx = static_cast<uint32_t>(h->stamps.size() - 1);
+  DeviceMap& m = h->dm;
+  if (m.next_pass && static_cast<int>(h->stamps.size()) + 2 > m.frame_capacity) {
+    // grow the per-frame-index tables of the lazy tracking
+    const int cap = m.frame_capacity * 2;
+    uint32_t *np = nullptr, *am = nullptr;
+    KB_CUDA(h, cudaStreamSynchronize(h->stream));
+    KB_CUDA(h, devAlloc(&np, static_cast<size_t>(cap), 0));
+    KB_CUDA(h, devAlloc(&am, static_cast<size_t>(cap), 0));
+    KB_CUDA(h, cudaMemcpy(np, m.next_pass, sizeof(uint32_t) * m.frame_capacity, cudaMemcpyDeviceToDevice));
+    KB_CUDA(h, cudaMemcpy(am, m.act_min, sizeof(uint32_t) * m.frame_capacity, cudaMemcpyDeviceToDevice));
+    cudaFree(m.next_pass); cudaFree(m.act_min);
+    m.next_pass = np; m.act_min = am; m.frame_capacity = cap;
+  }
   return KB_OK;
 }
 
@@ -212,6 +233,10 @@ int kb_create(const kb_map_config* map, const kb_integrator_config* integ, const
   h->map = *map;
   h->integ = *integ;
   if (trk) { h->trk = *trk; h->has_trk = true; }
+  {
+    const float cfg = trk ? trk->tsdf_occupancy_threshold : -1.5f;  // tracking_integrator.h:72
+    h->trk_cfg_thr = cfg < 0 ? cfg * -map->voxel_size : cfg;        // tracking_integrator.cpp:136-138
+  }
   if (mot) { h->mot = *mot; h->has_mot = true; }
   h->device = device;
   h->stamps.push_back(0);
@@ -257,6 +282,11 @@ int kb_create(const kb_map_config* map, const kb_integrator_config* integ, const
       KB_CUDA(h, devAlloc(&m.last_obs, S * V, 0));
       KB_CUDA(h, devAlloc(&m.last_occ, S * V, 0));
       KB_CUDA(h, devAlloc(&m.vflags, S * V, 0));
+      KB_CUDA(h, devAlloc(&m.born_frame, S, 0));
+      m.frame_capacity = 1 << 20;
+      KB_CUDA(h, devAlloc(&m.next_pass, static_cast<size_t>(m.frame_capacity), 0));
+      KB_CUDA(h, devAlloc(&m.act_min, static_cast<size_t>(m.frame_capacity), 0));
+      KB_CUDA(h, devAlloc(&h->pending, S, 0));
     }
     if (h->L > 0) {
       const size_t Q = m.max_sem;
@@ -274,10 +304,14 @@ int kb_create(const kb_map_config* map, const kb_integrator_config* integ, const
     KB_CUDA(h, devAlloc(&h->work_slots, S, 0));
     KB_CUDA(h, devAlloc(&h->work_masks, S, 0));
     KB_CUDA(h, devAlloc(&h->work_upd, S, 0));
+    h->batch.items_per_block = m.V / 128;
+    KB_CUDA(h, devAlloc(&h->item_fmask, S * h->batch.items_per_block, 0));
     {
       cudaDeviceProp prop{};
       KB_CUDA(h, cudaGetDeviceProperties(&prop, device));
-      h->fuse_grid = prop.multiProcessorCount * 8;  // persistent 128-thread CTAs (independent warps)
+      h->everfree_grid = prop.multiProcessorCount * 4;
+      h->cull_grid = prop.multiProcessorCount * 4;
+      h->fuse_grid = prop.multiProcessorCount * fuseBlocksPerSm(m.vps);  // persistent CTAs of independent warps
     }
     h->max_removed = m.max_blocks;
     KB_CUDA(h, devAlloc(&h->d_removed, static_cast<size_t>(h->max_removed), 0));
@@ -302,10 +336,11 @@ int kb_destroy(kb_handle* h) {
   cudaFree(m.hash_keys); cudaFree(m.hash_vals); cudaFree(m.counters); cudaFree(m.free_list);
   cudaFree(m.sem_free_list); cudaFree(m.block_index); cudaFree(m.block_flags); cudaFree(m.block_sem);
   cudaFree(m.tsdf); cudaFree(m.last_obs); cudaFree(m.last_occ); cudaFree(m.vflags);
+  cudaFree(m.born_frame); cudaFree(m.next_pass); cudaFree(m.act_min); cudaFree(h->pending);
   cudaFree(m.sem_label); cudaFree(m.sem_lik);
   cudaFree(h->stg_depth); cudaFree(h->stg_label); cudaFree(h->stg_mask); cudaFree(h->stg_object);
   cudaFree(h->stg_vertex); cudaFree(h->d_pixel_gidx); cudaFree(h->d_pixel_seed); cudaFree(h->d_removed);
-  cudaFree(h->mot_depth); cudaFree(h->tile_max); cudaFree(h->work_slots); cudaFree(h->work_masks); cudaFree(h->work_upd);
+  cudaFree(h->mot_depth); cudaFree(h->tile_max); cudaFree(h->work_slots); cudaFree(h->work_masks); cudaFree(h->work_upd); cudaFree(h->item_fmask);
   for (int i = 0; i < 2; ++i) {
     if (h->stg_ready[i]) cudaEventDestroy(h->stg_ready[i]);
     if (h->stg_consumed[i]) cudaEventDestroy(h->stg_consumed[i]);
@@ -373,6 +408,7 @@ int kb_set_camera(kb_handle* h, const kb_camera* cam) {
   p.mle_diag = h->mle_diag; p.mle_off = h->mle_off; p.mle_init = h->mle_init;
   p.blocked_mask = h->blocked_mask;
   p.with_tracking = h->map.with_tracking;
+  p.occ_thr = h->trk_cfg_thr;
   p.tiles8_x = (c.width + 7) / 8;
   p.tiles8_y = (c.height + 7) / 8;
   p.tiles16_x = (p.tiles8_x + 1) / 2;
@@ -381,6 +417,7 @@ int kb_set_camera(kb_handle* h, const kb_camera* cam) {
   p.work_slots = h->work_slots;
   p.work_masks = h->work_masks;
   p.work_upd = h->work_upd;
+  p.item_fmask = h->item_fmask;
   p.max_work = h->dm.max_blocks;
   cudaFree(h->tile_max);
   h->tile_max = nullptr;
@@ -422,6 +459,7 @@ static int integrateBatch(kb_handle* h, const kb_frame* frames, int n, int alloc
   p.parity = h->parity;
   h->parity ^= 1;
   p.cull = h->cull ? 1 : 0;
+  p.trk = h->pass;
 
   // ---- stage host images (double-buffered, on the copy stream so they overlap the previous batch)
   bool any_host = false;
@@ -440,6 +478,8 @@ static int integrateBatch(kb_handle* h, const kb_frame* frames, int n, int alloc
     FrameView& v = p.f[b];
     float Rw[9], tw[3];
     poseToFloat(f.world_T_sensor, v.R, v.t, Rw, tw);
+    if (h->map.with_tracking && f.stamp_ns <= h->last_pass_stamp)
+      return fail(h, KB_ERR_STATE, "frames must be newer than the last kb_update_tracking stamp");
     uint32_t fidx = 0;
     int st = frameIndex(h, f.stamp_ns, &fidx);
     if (st != KB_OK) return st;
@@ -488,7 +528,7 @@ static int integrateBatch(kb_handle* h, const kb_frame* frames, int n, int alloc
     p.n_slots = h->hwm_cached;
   }
   if (p.cull) launchTileMax(p, h->stream);
-  launchSelectBlocks(h->dm, p, h->stream);
+  launchSelectBlocks(h->dm, p, h->cull_grid, h->stream);
   launchFuse(h->dm, p, h->fuse_grid, h->stream);
   KB_CUDA(h, cudaGetLastError());
   if (any_host) {
@@ -562,35 +602,41 @@ int kb_update_tracking(kb_handle* h, uint64_t stamp_ns) {
   if (!h) return KB_ERR_INVALID;
   if (!h->has_trk || !h->map.with_tracking) return fail(h, KB_ERR_STATE, "tracking not configured");
   KB_CUDA(h, cudaSetDevice(h->device));
+  if (stamp_ns <= h->last_pass_stamp) return fail(h, KB_ERR_STATE, "tracking stamps must increase");
   uint32_t fidx = 0;
   int st = frameIndex(h, stamp_ns, &fidx);
   if (st != KB_OK) return st;
-  TrackingParams p{};
-  p.frame_idx = fidx;
-  p.occupancy_thr = h->trk.tsdf_occupancy_threshold < 0 ? h->trk.tsdf_occupancy_threshold * -h->map.voxel_size
-                                                        : h->trk.tsdf_occupancy_threshold;
-  p.connectivity = h->trk.neighbor_connectivity;
   // The reference compares stamps in double seconds (tracking_integrator.cpp:238,250). Stamps are
   // strictly increasing in the frame-index table, so each predicate is a threshold on the index.
   const double now = toSeconds(stamp_ns);
   const double t_active = now - h->trk.temporal_window;
   const double t_free = now - h->trk.temporal_buffer;
-  // First frame index (>= 1) whose stamp satisfies toSeconds(stamp) >= threshold.
-  auto firstAtLeast = [&](double thr) {
+  auto firstAtLeast = [&](double thr) {  // first frame index (>= 1) with toSeconds(stamp) >= thr
     auto it = std::partition_point(h->stamps.begin() + 1, h->stamps.end(),
                                    [&](uint64_t s) { return toSeconds(s) < thr; });
     return static_cast<uint32_t>(it - h->stamps.begin());
   };
-  const uint32_t a = firstAtLeast(t_active), g = firstAtLeast(t_free);
-  p.active_min_idx = a;   // last_obs >= a  <=>  toSeconds(last_obs) >= now - window
-  p.zero_active = 0.0 >= t_active;
-  p.free_max_idx = g;     // last_occ < g   <=>  toSeconds(last_occ) < now - buffer
-  p.zero_free = 0.0 < t_free;
-  int nslots = 0;
-  if ((st = slotHwm(h, &nslots)) != KB_OK) return st;
-  launchTracking(h->dm, p, nslots, h->stream);
-  launchEverFree(h->dm, p, nslots, h->stream);
+  TrackingParams p{};
+  p.prev_pass = h->pass.k_last;
+  p.ev.k_last = fidx;
+  p.ev.act_min = firstAtLeast(t_active);  // last_obs >= act_min <=> toSeconds(last_obs) >= now - window
+  // a never-observed voxel (stamp 0) is "active" at pass k iff 0.0 >= toSeconds(stamp_k) - window; the
+  // passes for which that holds are a prefix of the (increasing) stamp table
+  {
+    auto it = std::partition_point(h->stamps.begin() + 1, h->stamps.end(), [&](uint64_t s) {
+      return 0.0 >= toSeconds(s) - h->trk.temporal_window;
+    });
+    p.ev.zero_max = static_cast<uint32_t>(it - h->stamps.begin()) - 1;
+  }
+  p.ev.free_max = firstAtLeast(t_free);   // last_occ < free_max <=> toSeconds(last_occ) < now - buffer
+  p.ev.zero_free = 0.0 < t_free;
+  p.connectivity = h->trk.neighbor_connectivity;
+  p.n_slots = h->dm.max_blocks;
+  p.pending = h->pending;
+  launchTrackingPass(h->dm, p, h->everfree_grid, h->stream);
   KB_CUDA(h, cudaGetLastError());
+  h->pass = p.ev;
+  h->last_pass_stamp = stamp_ns;
   return KB_OK;
 }
 
@@ -600,25 +646,17 @@ int kb_reset_inactive(kb_handle* h, int32_t* removed_xyz, int32_t max_removed, i
   KB_CUDA(h, cudaSetDevice(h->device));
   int st, nslots = 0;
   if ((st = slotHwm(h, &nslots)) != KB_OK) return st;
-  const int before = h->h_ctr[kCtrRemoved];
-  launchResetInactive(h->dm, nslots, h->d_removed, h->max_removed, h->stream);
+  KB_CUDA(h, cudaMemsetAsync(h->dm.counters + kCtrRemoved, 0, sizeof(int), h->stream));
+  launchResetInactive(h->dm, h->pass, nslots, h->d_removed, h->max_removed, h->stream);
   KB_CUDA(h, cudaGetLastError());
   if ((st = readCounters(h)) != KB_OK) return st;
-  const int n = h->h_ctr[kCtrRemoved] - before;
-  // the device appends at absolute positions [before, before+n) modulo nothing: we reset the counter
+  const int n = std::min(h->h_ctr[kCtrRemoved], h->max_removed);
   std::vector<int3> host(static_cast<size_t>(std::max(n, 0)));
-  if (n > 0) {
-    // removed[] was indexed by the cumulative counter; copy the window (bounded by max_removed).
-    const int lo = std::min(before, h->max_removed), hi = std::min(before + n, h->max_removed);
-    if (hi > lo) KB_CUDA(h, cudaMemcpy(host.data(), h->d_removed + lo, sizeof(int3) * (hi - lo), cudaMemcpyDeviceToHost));
-    host.resize(hi - lo);
-  }
-  // keep the cumulative counter from walking off the buffer
-  KB_CUDA(h, cudaMemsetAsync(h->dm.counters + kCtrRemoved, 0, sizeof(int), h->stream));
-  h->h_ctr[kCtrRemoved] = 0;
+  if (n > 0) KB_CUDA(h, cudaMemcpy(host.data(), h->d_removed, sizeof(int3) * n, cudaMemcpyDeviceToHost));
   std::sort(host.begin(), host.end(), [](const int3& a, const int3& b) {
     return a.x != b.x ? a.x < b.x : (a.y != b.y ? a.y < b.y : a.z < b.z);
   });
+  h->hwm_dirty = true;
   if (n_removed) *n_removed = static_cast<int32_t>(host.size());
   if (removed_xyz)
     for (int i = 0; i < std::min<int>(max_removed, host.size()); ++i) {
@@ -653,7 +691,11 @@ int kb_allocate_box(kb_handle* h, const int32_t mn[3], const int32_t mx[3]) {
   const int3 lo = make_int3(mn[0], mn[1], mn[2]);
   const int3 dims = make_int3(mx[0] - mn[0] + 1, mx[1] - mn[1] + 1, mx[2] - mn[2] + 1);
   if (dims.x <= 0 || dims.y <= 0 || dims.z <= 0) return KB_OK;
-  launchAllocateBox(h->dm, lo, dims, h->rank, h->nranks, h->stream);
+  // blocks allocated now are seen by tracking passes with a frame index >= born
+  const uint32_t last_idx = static_cast<uint32_t>(h->stamps.size() - 1);
+  const uint32_t born = std::max(last_idx, h->pass.k_last + 1);
+  launchAllocateBox(h->dm, lo, dims, h->rank, h->nranks, born, h->stream);
+  h->hwm_dirty = true;
   KB_CUDA(h, cudaGetLastError());
   int st = readCounters(h);
   if (st != KB_OK) return st;
@@ -665,6 +707,8 @@ int kb_scan_object_confidence(kb_handle* h, float min_confidence, int32_t min_ob
   if (!h) return KB_ERR_INVALID;
   if (h->L != 2 || h->integ.semantic_mode != KB_SEMANTICS_BINARY)
     return fail(h, KB_ERR_STATE, "kb_scan_object_confidence needs binary semantics");
+  if (h->map.with_tracking)
+    return fail(h, KB_ERR_STATE, "kb_scan_object_confidence is for tracking-less extraction maps (mesh_object_extractor.cpp:210)");
   KB_CUDA(h, cudaSetDevice(h->device));
   int st, n = 0;
   if ((st = slotHwm(h, &n)) != KB_OK) return st;
@@ -812,7 +856,7 @@ int kb_export_blocks(kb_handle* h, int which, int32_t max_blocks, kb_block_expor
   int* d_slots = nullptr;
   unsigned long long* d_stamps = nullptr;
   char* d_buf = nullptr;
-  const size_t per_block = V * (4 + 4) + V * (8 + 8 + 3) + V * (4 + 1) + V * L * 4;
+  const size_t per_block = V * (4 + 4) + V * (8 + 8 + 3) + V * (4 + 1) + V * L * 4 + 16;
   auto cleanup = [&]() { cudaFree(d_slots); cudaFree(d_stamps); cudaFree(d_buf); };
   auto body = [&]() -> int {
     if (n == 0) return KB_OK;
@@ -834,16 +878,26 @@ int kb_export_blocks(kb_handle* h, int which, int32_t max_blocks, kb_block_expor
       uint8_t* d_ac = reinterpret_cast<uint8_t*>(q); q += nb * V;
       uint8_t* d_tr = reinterpret_cast<uint8_t*>(q); q += nb * V;
       uint8_t* d_em = reinterpret_cast<uint8_t*>(q); q += nb * V;
+      uint8_t* d_ba = reinterpret_cast<uint8_t*>(q); q += nb;
       const size_t off = static_cast<size_t>(b0) * V;
       if (out->distance || out->weight) {
         launchGatherTsdf(h->dm, d_slots + b0, nb, d_dist, d_w, h->stream);
         if (out->distance) KB_CUDA(h, cudaMemcpyAsync(out->distance + off, d_dist, nb * V * 4, cudaMemcpyDeviceToHost, h->stream));
         if (out->weight) KB_CUDA(h, cudaMemcpyAsync(out->weight + off, d_w, nb * V * 4, cudaMemcpyDeviceToHost, h->stream));
       }
-      const bool want_trk = out->last_observed || out->last_occupied || out->ever_free || out->active || out->to_remove;
+      const bool want_trk = out->last_observed || out->last_occupied || out->ever_free || out->active ||
+                            out->to_remove || out->block_flags;
       if (want_trk) {
         if (h->map.with_tracking) {
-          launchGatherTracking(h->dm, d_slots + b0, nb, d_stamps, d_lo, d_lc, d_ef, d_ac, d_tr, h->stream);
+          launchGatherTracking(h->dm, h->pass, d_slots + b0, nb, d_stamps, d_lo, d_lc, d_ef, d_ac, d_tr, d_ba, h->stream);
+          if (out->block_flags) {
+            std::vector<uint8_t> ba(nb);
+            KB_CUDA(h, cudaMemcpyAsync(ba.data(), d_ba, nb, cudaMemcpyDeviceToHost, h->stream));
+            KB_CUDA(h, cudaStreamSynchronize(h->stream));
+            for (int i = 0; i < nb; ++i)
+              out->block_flags[b0 + i] = static_cast<uint8_t>((out->block_flags[b0 + i] & ~KB_FLAG_HAS_ACTIVE_DATA) |
+                                                              (ba[i] ? KB_FLAG_HAS_ACTIVE_DATA : 0));
+          }
           if (out->last_observed) KB_CUDA(h, cudaMemcpyAsync(out->last_observed + off, d_lo, nb * V * 8, cudaMemcpyDeviceToHost, h->stream));
           if (out->last_occupied) KB_CUDA(h, cudaMemcpyAsync(out->last_occupied + off, d_lc, nb * V * 8, cudaMemcpyDeviceToHost, h->stream));
           if (out->ever_free) KB_CUDA(h, cudaMemcpyAsync(out->ever_free + off, d_ef, nb * V, cudaMemcpyDeviceToHost, h->stream));

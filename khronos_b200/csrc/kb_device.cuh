@@ -21,7 +21,13 @@ constexpr uint32_t kFlagAllocated = 1u << 8;      // slot is live
 constexpr uint32_t kFlagEverFreePending = 1u << 9;  // tracking_updated latched by K2 for K3
 constexpr uint32_t kPublicFlagMask = 0x1Fu;
 constexpr uint16_t kSemEmpty = 0xFFFFu;
+// vflags bits. The tracking state is kept *lazily* (SURVEY §7 hard part 3): kVoxActive / kVoxToRemove hold
+// the values as of the voxel's last write by K1 (the end of its previous observation epoch); the values
+// the reference's per-frame all-block pass would have produced are derived on demand by evalTracking().
 constexpr uint8_t kVoxEverFree = 1, kVoxActive = 2, kVoxToRemove = 4;
+constexpr uint8_t kVoxNotOccupied = 8;  // distance >= occupancy threshold after the last write (0 = occupied,
+                                        // which is also the state of a fresh voxel: distance 0 < thr)
+constexpr uint32_t kFlagInactiveOverride = 1u << 10;  // kb_mark_all_inactive until the next tracking pass
 
 struct DeviceMap {
   unsigned long long* hash_keys;
@@ -39,6 +45,10 @@ struct DeviceMap {
   uint32_t* last_obs;
   uint32_t* last_occ;
   uint8_t* vflags;
+  uint32_t* born_frame;  // [S] frame index at which the block was allocated
+  uint32_t* next_pass;   // [frame idx] index of the first tracking pass at or after that frame (0 = none yet)
+  uint32_t* act_min;     // [frame idx of a pass] smallest last_observed index that is 'active' at that pass
+  int frame_capacity;
   uint16_t* sem_label;
   float* sem_lik;
 };
@@ -63,6 +73,8 @@ enum Counter {
   kCtrWork0 = 15,  // two work-list counters used alternately by consecutive batches
   kCtrWork1 = 16,
   kCtrPairs = 17,  // (block, frame) pairs that survived K0 culling
+  kCtrPending = 18,  // ever-free work list length of the current tracking pass
+  kCtrFetch = 19,    // dynamic work cursor of the fuse kernel
   kNumCounters = 24
 };
 
@@ -115,7 +127,7 @@ __device__ inline int allocSlot(int* counters, int ctr_hwm, int ctr_free, const 
 }
 
 // Finds or inserts a block. At most one thread per key calls this in any launch. *created = 1 if new.
-__device__ inline int hashFindOrInsert(const DeviceMap& m, int x, int y, int z, int* created) {
+__device__ inline int hashFindOrInsert(const DeviceMap& m, int x, int y, int z, uint32_t born, int* created) {
   const unsigned long long key = packKey(x, y, z);
   uint32_t h = static_cast<uint32_t>(mix64(key)) & m.hash_mask;
   *created = 0;
@@ -156,9 +168,44 @@ __device__ inline int hashFindOrInsert(const DeviceMap& m, int x, int y, int z, 
   m.block_index[slot] = make_int3(x, y, z);
   m.block_flags[slot] = kFlagAllocated;
   m.block_sem[slot] = -1;
+  if (m.born_frame) m.born_frame[slot] = born;
   atomicAdd(&m.counters[kCtrLiveBlocks], 1);
   *created = 1;
   return slot;
+}
+
+// Parameters of the lazy tracking evaluation: the state of "the last tracking pass" (frame index k_last).
+struct TrackEval {
+  uint32_t k_last;      // frame index of the most recent tracking pass (0: none yet)
+  uint32_t act_min;     // last_observed >= act_min  <=> active at pass k_last (double-seconds compare, host)
+  uint32_t zero_max;    // a never-observed voxel (stamp 0) counts as active at pass k iff k <= zero_max
+  uint32_t free_max;    // last_occupied < free_max  <=> toSeconds(last_occ) < toSeconds(now) - temporal_buffer
+  int zero_free;        // the same predicate for last_occupied == 0
+};
+
+// Values the reference's brute-force pass (tracking_integrator.cpp:133-166,224-246) would hold for a
+// voxel right after pass k_last, derived from the lazily kept state (see kb_kernels.cu, fuseKernel).
+__device__ __forceinline__ void evalTracking(const DeviceMap& m, const TrackEval& t, uint32_t born, uint32_t o,
+                                             uint32_t c_stored, uint8_t f, uint32_t* last_occ, bool* active,
+                                             bool* to_remove) {
+  const uint32_t e = o > born ? o : born;
+  const bool has_pass = t.k_last != 0 && t.k_last >= e;  // a pass saw the voxel in its current epoch
+  *last_occ = (has_pass && !(f & kVoxNotOccupied)) ? t.k_last : c_stored;
+  bool act = (f & kVoxActive) != 0, rem = (f & kVoxToRemove) != 0;
+  if (has_pass) {
+    const bool act_last = o == 0 ? (t.k_last <= t.zero_max) : (o >= t.act_min);
+    if (!act_last && !rem) {
+      bool was = act;
+      if (!was) {
+        const uint32_t first = m.next_pass[e];
+        was = o == 0 ? (first <= t.zero_max) : (o >= m.act_min[first]);
+      }
+      rem = was;
+    }
+    act = act_last;
+  }
+  *active = act;
+  *to_remove = rem;
 }
 #endif
 

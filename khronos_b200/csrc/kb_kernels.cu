@@ -6,7 +6,8 @@
 //                               insert, semantic slot assignment, compaction into a work list
 //   K1     fuseKernel           persistent CTAs over (block, z-slab) items: projective TSDF + semantic
 //                               fusion of up to 32 frames with the voxel state held in registers
-//   K2     trackingKernel       per-voxel last_occupied / active / to_remove, block has_active_data
+//   K2     trackingPassKernel   lazy tracking pass: O(blocks) bookkeeping; per-voxel last_occupied / active /
+//                               to_remove are derived on demand (evalTracking) instead of rewritten per frame
 //   K3     everFreeKernel       ever-free labelling with 6/18/26 neighbourhood across blocks
 //   K2r    resetInactiveKernel  block removal + slot recycling
 //   M1     motionLookupKernel   per-pixel endpoint voxel lookup + ever-free seed test
@@ -233,7 +234,10 @@ __device__ __forceinline__ bool boxCulledWarp(const BatchParams& p, const FrameV
 __global__ void __launch_bounds__(128) selectBlocksKernel(const DeviceMap m, const __grid_constant__ BatchParams p) {
   const int c0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (c0 == 0 && lane == 0) m.counters[kCtrWork0 + (p.parity ^ 1)] = 0;  // the next batch's work counter
+  if (c0 == 0 && lane == 0) {  // reset the next batch's work counter and this batch's fetch cursor
+    m.counters[kCtrWork0 + (p.parity ^ 1)] = 0;
+    m.counters[kCtrFetch] = 0;
+  }
   int slot = -1, bx = 0, by = 0, bz = 0;
   uint32_t mask = 0;
   int created = 0;
@@ -256,7 +260,7 @@ __global__ void __launch_bounds__(128) selectBlocksKernel(const DeviceMap m, con
     mask = __ballot_sync(0xffffffffu, in);
     if (!mask) return;
     if (p.nranks > 1 && blockOwner(bx, by, bz, p.nranks) != p.rank) return;
-    if (lane == 0) slot = hashFindOrInsert(m, bx, by, bz, &created);
+    if (lane == 0) slot = hashFindOrInsert(m, bx, by, bz, p.f[__ffs(mask) - 1].frame_idx, &created);
     slot = __shfl_sync(0xffffffffu, slot, 0);
     if (slot < 0) return;
   } else {
@@ -283,91 +287,203 @@ __global__ void __launch_bounds__(128) selectBlocksKernel(const DeviceMap m, con
     }
     if (!mask) return;
   }
-  if (lane != 0) return;
-  // Blocks that may receive measurements get their semantic slot here (one thread per block, so no
-  // allocation race inside the fuse kernel); never-measured blocks cost no semantic memory.
-  if (p.L > 0 && m.block_sem[slot] < 0) {
-    m.block_sem[slot] = allocSlot(m.counters, kCtrSemHwm, kCtrSemFreeCount, m.sem_free_list, m.max_sem);
+  int i = 0;
+  if (lane == 0) {
+    // Blocks that may receive measurements get their semantic slot here (one thread per block, so no
+    // allocation race inside the fuse kernel); never-measured blocks cost no semantic memory.
+    if (p.L > 0 && m.block_sem[slot] < 0) {
+      m.block_sem[slot] = allocSlot(m.counters, kCtrSemHwm, kCtrSemFreeCount, m.sem_free_list, m.max_sem);
+    }
+    atomicAdd(&m.counters[kCtrPairs], __popc(mask));
+    i = atomicAdd(&m.counters[kCtrWork0 + p.parity], 1);
+    if (i < p.max_work) {
+      p.work_slots[i] = slot;
+      p.work_masks[i] = mask;
+      p.work_upd[i] = 0;
+    } else {
+      atomicExch(&m.counters[kCtrCapacityExceeded], 1);
+    }
   }
-  atomicAdd(&m.counters[kCtrPairs], __popc(mask));
-  const int i = atomicAdd(&m.counters[kCtrWork0 + p.parity], 1);
-  if (i < p.max_work) {
-    p.work_slots[i] = slot;
-    p.work_masks[i] = mask;
-    p.work_upd[i] = 0;
-  } else {
-    atomicExch(&m.counters[kCtrCapacityExceeded], 1);
+  i = __shfl_sync(0xffffffffu, i, 0);
+  // per-item frame masks: all of the block's frames without culling, else filled by itemCullKernel
+  if (i < p.max_work && lane < p.items_per_block) p.item_fmask[static_cast<size_t>(i) * p.items_per_block + lane] = p.cull ? 0u : mask;
+}
+
+// ---- K0b: work-item culling --------------------------------------------------------------------------------
+// Box of voxel centres of work item `it` of a block (4x8x4 voxels; x fastest).
+template <int VPS>
+__device__ __forceinline__ void itemOrigin(int it, int& x0, int& y0, int& z0) {
+  constexpr int IX = VPS / 4, IY = VPS / 8;
+  x0 = (it % IX) * 4;
+  y0 = ((it / IX) % IY) * 8;
+  z0 = (it / (IX * IY)) * 4;
+}
+
+// Scalar version of boxCulledWarp for one lane (one work item): same conservative rule, 8x8 tiles.
+__device__ __forceinline__ bool boxCulledLane(const BatchParams& p, const FrameView& f, float lox, float loy,
+                                              float loz, float hix, float hiy, float hiz) {
+  float zmin = 3.0e38f, umin = 3.0e38f, umax = -3.0e38f, vmin = 3.0e38f, vmax = -3.0e38f;
+#pragma unroll 1
+  for (int c = 0; c < 8; ++c) {
+    float x, y, z;
+    xform(f.R, f.t, (c & 1) ? hix : lox, (c & 2) ? hiy : loy, (c & 4) ? hiz : loz, x, y, z);
+    if (z < 1e-2f) return false;  // reaches behind / near the camera plane: keep
+    const float u = p.fx * x / z + p.cx, v = p.fy * y / z + p.cy;
+    zmin = fminf(zmin, z);
+    umin = fminf(umin, u); umax = fmaxf(umax, u);
+    vmin = fminf(vmin, v); vmax = fmaxf(vmax, v);
+  }
+  if (umax < -0.5f || vmax < -0.5f || umin > static_cast<float>(p.W - 1) + 0.5f || vmin > static_cast<float>(p.H - 1) + 0.5f)
+    return true;
+  const int u0 = max(static_cast<int>(floorf(umin)) - 2, 0), u1 = min(static_cast<int>(floorf(umax)) + 3, p.W - 1);
+  const int v0 = max(static_cast<int>(floorf(vmin)) - 2, 0), v1 = min(static_cast<int>(floorf(vmax)) + 3, p.H - 1);
+  const int tx0 = u0 >> 3, tx1 = u1 >> 3, ty0 = v0 >> 3, ty1 = v1 >> 3;
+  if ((tx1 - tx0 + 1) * (ty1 - ty0 + 1) > 400) return false;  // huge footprint: keep
+  float dmax = 0.f;
+  for (int ty = ty0; ty <= ty1; ++ty) {
+    const float* __restrict__ row = f.tile8 + ty * p.tiles8_x;
+    for (int tx = tx0; tx <= tx1; ++tx) dmax = fmaxf(dmax, __ldg(&row[tx]));
+  }
+  if (!(dmax > 0.f)) return true;
+  return zmin - p.trunc - 1e-3f > dmax;
+}
+
+// One warp per (work block, chunk of kCullChunk frames); lane = work item of the block. Fills
+// item_fmask[block][item] with the frames for which the item may receive a measurement.
+constexpr int kCullChunk = 4;
+template <int VPS>
+__global__ void __launch_bounds__(128) itemCullKernel(const DeviceMap m, const __grid_constant__ BatchParams p) {
+  constexpr int ITEMS = (VPS / 4) * (VPS / 8) * (VPS / 4);
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int n_warps = (gridDim.x * blockDim.x) >> 5;
+  const int chunks = (p.n_frames + kCullChunk - 1) / kCullChunk;
+  const int n = min(m.counters[kCtrWork0 + p.parity], p.max_work) * chunks;
+  for (int w = warp; w < n; w += n_warps) {
+    const int wi = w / chunks, ch = w % chunks;
+    const uint32_t bmask = p.work_masks[wi] & (((kCullChunk >= 32 ? 0u : (1u << kCullChunk)) - 1u) << (ch * kCullChunk));
+    if (!bmask || lane >= ITEMS) continue;
+    const int3 bi = m.block_index[p.work_slots[wi]];
+    int x0, y0, z0;
+    itemOrigin<VPS>(lane, x0, y0, z0);
+    const float ox = static_cast<float>(bi.x) * p.block_size, oy = static_cast<float>(bi.y) * p.block_size,
+                oz = static_cast<float>(bi.z) * p.block_size;
+    const float lx = ox + (static_cast<float>(x0) + 0.5f) * p.voxel_size, hx = ox + (static_cast<float>(x0 + 3) + 0.5f) * p.voxel_size;
+    const float ly = oy + (static_cast<float>(y0) + 0.5f) * p.voxel_size, hy = oy + (static_cast<float>(y0 + 7) + 0.5f) * p.voxel_size;
+    const float lz = oz + (static_cast<float>(z0) + 0.5f) * p.voxel_size, hz = oz + (static_cast<float>(z0 + 3) + 0.5f) * p.voxel_size;
+    uint32_t keep = 0, rem = bmask;
+    while (rem) {
+      const int b = __ffs(rem) - 1;
+      rem &= rem - 1;
+      if (!boxCulledLane(p, p.f[b], lx, ly, lz, hx, hy, hz)) keep |= 1u << b;
+    }
+    if (keep) atomicOr(&p.item_fmask[static_cast<size_t>(wi) * ITEMS + lane], keep);
   }
 }
 
 // ---- K1: projective TSDF + semantic fusion ----------------------------------------------------------------
-// Persistent warps stride over work items = (selected block, 4x8x4-voxel box). Lane (x, y) of the 4x8
-// box face owns the 4 voxels stacked in z and keeps their {distance, weight, last_observed} in registers
-// while the warp walks the frames of the batch in order: a voxel's TSDF is read and written once per
-// batch, the four gather chains per lane are independent (ILP), every warp access covers whole 32 B
-// sectors, and the compact box keeps a warp's image taps in one small neighbourhood. Warps never
-// synchronise with each other (no shared memory, no CTA barrier). Each (item, frame) pair is first
-// tested by the conservative box culling against the 8x8 tile maxima.
+// SemanticIntegrator::updateLikelihoods (UP App. A.8) on one voxel's likelihood row. Out of line: it is
+// the rarely taken, instruction-heavy tail of the voxel update and must not be replicated per voxel slot.
+__device__ __noinline__ void semanticUpdate(float* __restrict__ row, uint16_t* __restrict__ slabel, int Lp, int L,
+                                            uint32_t label, int binary, float mle_init, float mle_diag, float mle_off) {
+  const bool empty = *slabel == kSemEmpty;
+  int best = 0;
+  if (binary) {
+    float2* lk = reinterpret_cast<float2*>(row);
+    float2 c = empty ? make_float2(0.f, 0.f) : *lk;
+    if (label) c.y = c.y + 1.f; else c.x = c.x + 1.f;
+    *lk = c;
+    best = c.y > c.x ? 1 : 0;
+  } else {
+    float4* lk = reinterpret_cast<float4*>(row);
+    float bestv = 0.f;
+    for (int k4 = 0; k4 < Lp; k4 += 4) {
+      float4 c = empty ? make_float4(mle_init, mle_init, mle_init, mle_init) : lk[k4 >> 2];
+      float* cf = reinterpret_cast<float*>(&c);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int kk = k4 + j;
+        if (kk < L) {
+          cf[j] = cf[j] + (static_cast<uint32_t>(kk) == label ? mle_diag : mle_off);
+          if (kk == 0 || cf[j] > bestv) { bestv = cf[j]; best = kk; }
+        }
+      }
+      lk[k4 >> 2] = c;
+    }
+  }
+  *slabel = static_cast<uint16_t>(best);
+}
+
+// Lazy tracking fold (see evalTracking): what the tracking passes since the voxel's last write would have
+// done to it. Returns the flag byte to carry (ever_free, active, to_remove); refreshes last_occupied.
+__device__ __noinline__ uint32_t trackingFold(const DeviceMap m, const TrackEval t, uint32_t born, size_t gi) {
+  const uint8_t fl = m.vflags[gi];
+  const uint32_t c_stored = m.last_occ[gi];
+  uint32_t c_true;
+  bool act, rem;
+  evalTracking(m, t, born, m.last_obs[gi], c_stored, fl, &c_true, &act, &rem);
+  if (c_true != c_stored) m.last_occ[gi] = c_true;
+  return (fl & kVoxEverFree) | (act ? kVoxActive : 0) | (rem ? kVoxToRemove : 0);
+}
+
+// Persistent warps fetch work items = (selected block, 4x8x4-voxel box) from a shared cursor. Lane (x, y) of
+// the 4x8 box face owns the 4 voxels stacked in z; their {distance, weight, last_observed, flags} live in
+// shared memory (per-lane slots, no bank conflicts) while the warp walks the item's surviving frames in
+// order, so a voxel's TSDF is read and written once per batch and every warp access covers whole 32 B
+// sectors. Warps never synchronise with each other. The voxel loop is deliberately NOT unrolled: the body
+// is ~1 k SASS instructions and replicating it blew the instruction cache (profiles/r1_v3_*).
 // ProjectiveIntegrator::updateBlock / getVoxelMeasurement / computeLabel / updateVoxel (UP App. A.6;
 // computeLabel structure pinned by khronos/src/active_window/integration/object_integrator.cpp:58-81).
 template <int VPS>
-__global__ void __launch_bounds__(kFuseThreads, 8) fuseKernel(const DeviceMap m, const __grid_constant__ BatchParams p) {
+__global__ void __launch_bounds__(kFuseThreads) fuseKernel(const DeviceMap m, const __grid_constant__ BatchParams p) {
   constexpr int V = VPS * VPS * VPS;
   constexpr int NV = 4;                          // voxels per lane (stacked in z)
-  constexpr int IX = VPS / 4, IY = VPS / 8, IZ = VPS / NV;
-  constexpr int ITEMS = IX * IY * IZ;            // 32 (16^3) or 4 (8^3) items of 128 voxels per block
+  constexpr int ITEMS = (VPS / 4) * (VPS / 8) * (VPS / NV);  // 32 (16^3) or 4 (8^3) items of 128 voxels
+  __shared__ float2 s_st[NV][kFuseThreads];
+  __shared__ uint32_t s_lobs[NV][kFuseThreads];
+  __shared__ uint8_t s_vfl[NV][kFuseThreads];
   const int lane = threadIdx.x & 31;
-  const int warp = (blockIdx.x * kFuseThreads + threadIdx.x) >> 5;
-  const int n_warps = (gridDim.x * kFuseThreads) >> 5;
   const int n_items = min(m.counters[kCtrWork0 + p.parity], p.max_work) * ITEMS;
   const bool binary = p.sem_mode == KB_SEMANTICS_BINARY;
   int n_valid = 0, n_band = 0, n_sem = 0;
 
-  for (int w = warp; w < n_items; w += n_warps) {
+  for (;;) {
+    int w = 0;
+    if (lane == 0) w = atomicAdd(&m.counters[kCtrFetch], 1);
+    w = __shfl_sync(0xffffffffu, w, 0);
+    if (w >= n_items) break;
+    const uint32_t fmask = p.item_fmask[w];
+    if (!fmask) continue;
     const int wi = w / ITEMS, it = w % ITEMS;
     const int slot = p.work_slots[wi];
-    const uint32_t fmask = p.work_masks[wi];
     const int3 bi = m.block_index[slot];
     const int sem = p.L > 0 ? m.block_sem[slot] : -1;
-    const int x0 = (it % IX) * 4, y0 = ((it / IX) % IY) * 8, z0 = (it / (IX * IY)) * NV;
+    int x0, y0, z0;
+    itemOrigin<VPS>(it, x0, y0, z0);
     const int vx = x0 + (lane & 3), vy = y0 + (lane >> 2);
     const int lin0 = vx + VPS * (vy + VPS * z0);  // voxel k of this lane: lin0 + k*VPS*VPS
-
-    const float ox = static_cast<float>(bi.x) * p.block_size;
-    const float oy = static_cast<float>(bi.y) * p.block_size;
+    const size_t base = static_cast<size_t>(slot) * V;
+    float2* __restrict__ tsdf = m.tsdf + base;
+    const float wx = static_cast<float>(bi.x) * p.block_size + (static_cast<float>(vx) + 0.5f) * p.voxel_size;
+    const float wy = static_cast<float>(bi.y) * p.block_size + (static_cast<float>(vy) + 0.5f) * p.voxel_size;
     const float oz = static_cast<float>(bi.z) * p.block_size;
-    float2* __restrict__ tsdf = m.tsdf + static_cast<size_t>(slot) * V;
-    const float wx = ox + (static_cast<float>(vx) + 0.5f) * p.voxel_size;
-    const float wy = oy + (static_cast<float>(vy) + 0.5f) * p.voxel_size;
-    float wz[NV];
-    float2 st[NV];
-    uint32_t lobs[NV];
+    const uint32_t born = p.with_tracking ? m.born_frame[slot] : 0u;
     uint32_t have = 0, touched = 0, upd_frames = 0;
-#pragma unroll
-    for (int k = 0; k < NV; ++k) {
-      wz[k] = oz + (static_cast<float>(z0 + k) + 0.5f) * p.voxel_size;
-      st[k] = make_float2(0.f, 0.f);
-      lobs[k] = 0;
-    }
-    // box of this item's voxel centres (for culling)
-    const float blx = ox + (static_cast<float>(x0) + 0.5f) * p.voxel_size, bhx = ox + (static_cast<float>(x0 + 3) + 0.5f) * p.voxel_size;
-    const float bly = oy + (static_cast<float>(y0) + 0.5f) * p.voxel_size, bhy = oy + (static_cast<float>(y0 + 7) + 0.5f) * p.voxel_size;
-    const float blz = oz + (static_cast<float>(z0) + 0.5f) * p.voxel_size, bhz = oz + (static_cast<float>(z0 + NV - 1) + 0.5f) * p.voxel_size;
 
     uint32_t rem = fmask;
     while (rem) {
       const int b = __ffs(rem) - 1;
       rem &= rem - 1;
       const FrameView& f = p.f[b];
-      if (p.cull && boxCulledWarp(p, f, f.tile8, p.tiles8_x, 3, blx, bly, blz, bhx, bhy, bhz, lane)) continue;
       const bool has_label_img = p.L > 0 && (binary ? f.object_image != nullptr : f.label != nullptr);
       // p_C = ((R0*x + R1*y) + R2*z) + t: the (x, y) partial sums are shared by the lane's 4 voxels
       const float ax = f.R[0] * wx + f.R[1] * wy, ay = f.R[3] * wx + f.R[4] * wy, az = f.R[6] * wx + f.R[7] * wy;
-#pragma unroll
+#pragma unroll 1
       for (int k = 0; k < NV; ++k) {
-        const float x = (ax + f.R[2] * wz[k]) + f.t[0];
-        const float y = (ay + f.R[5] * wz[k]) + f.t[1];
-        const float z = (az + f.R[8] * wz[k]) + f.t[2];
+        const float wz = oz + (static_cast<float>(z0 + k) + 0.5f) * p.voxel_size;
+        const float x = (ax + f.R[2] * wz) + f.t[0];
+        const float y = (ay + f.R[5] * wz) + f.t[1];
+        const float z = (az + f.R[8] * wz) + f.t[2];
         if (z <= 0.f) continue;
         const float u = p.fx * x / z + p.cx;
         const float v = p.fy * y / z + p.cy;
@@ -392,46 +508,28 @@ __global__ void __launch_bounds__(kFuseThreads, 8) fuseKernel(const DeviceMap m,
         }
         const float wm = measurementWeight(p, z, sdf);
         const int lin = lin0 + k * VPS * VPS;
-        if (!((have >> k) & 1u)) { st[k] = tsdf[lin]; have |= 1u << k; }
+        float2 old;
+        if (!((have >> k) & 1u)) {
+          old = tsdf[lin];
+          have |= 1u << k;
+          s_vfl[k][threadIdx.x] = p.with_tracking ? static_cast<uint8_t>(trackingFold(m, p.trk, born, base + lin)) : uint8_t(0);
+        } else {
+          old = s_st[k][threadIdx.x];
+        }
         const float sdf_c = fminf(fmaxf(sdf, -p.trunc), p.trunc);
-        const float2 old = st[k];
-        st[k].x = (old.x * old.y + sdf_c * wm) / (old.y + wm);
-        st[k].y = fminf(old.y + wm, p.max_weight);
-        lobs[k] = f.frame_idx;
+        float2 upd;
+        upd.x = (old.x * old.y + sdf_c * wm) / (old.y + wm);
+        upd.y = fminf(old.y + wm, p.max_weight);
+        s_st[k][threadIdx.x] = upd;
+        s_lobs[k][threadIdx.x] = f.frame_idx;
         touched |= 1u << k;
         upd_frames |= 1u << b;
         ++n_valid;
         if (!in_band) continue;
         ++n_band;
         if (sem >= 0 && has_label_img && label < static_cast<uint32_t>(p.L)) {
-          // SemanticIntegrator::updateLikelihoods (UP App. A.8) on the voxel's likelihood row
-          uint16_t* __restrict__ slabel = m.sem_label + static_cast<size_t>(sem) * V;
-          const bool empty = slabel[lin] == kSemEmpty;
-          int best = 0;
-          if (binary) {
-            float2* lk = reinterpret_cast<float2*>(m.sem_lik + (static_cast<size_t>(sem) * V + lin) * 2);
-            float2 c = empty ? make_float2(0.f, 0.f) : *lk;
-            if (label) c.y = c.y + 1.f; else c.x = c.x + 1.f;
-            *lk = c;
-            best = c.y > c.x ? 1 : 0;
-          } else {
-            float4* lk = reinterpret_cast<float4*>(m.sem_lik + (static_cast<size_t>(sem) * V + lin) * m.Lp);
-            float bestv = 0.f;
-            for (int k4 = 0; k4 < m.Lp; k4 += 4) {
-              float4 c = empty ? make_float4(p.mle_init, p.mle_init, p.mle_init, p.mle_init) : lk[k4 >> 2];
-              float* cf = reinterpret_cast<float*>(&c);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const int kk = k4 + j;
-                if (kk < p.L) {
-                  cf[j] = cf[j] + (static_cast<uint32_t>(kk) == label ? p.mle_diag : p.mle_off);
-                  if (kk == 0 || cf[j] > bestv) { bestv = cf[j]; best = kk; }
-                }
-              }
-              lk[k4 >> 2] = c;
-            }
-          }
-          slabel[lin] = static_cast<uint16_t>(best);
+          const size_t si = static_cast<size_t>(sem) * V + lin;
+          semanticUpdate(m.sem_lik + si * m.Lp, m.sem_label + si, m.Lp, p.L, label, binary ? 1 : 0, p.mle_init, p.mle_diag, p.mle_off);
           ++n_sem;
         }
       }
@@ -442,8 +540,12 @@ __global__ void __launch_bounds__(kFuseThreads, 8) fuseKernel(const DeviceMap m,
     for (int k = 0; k < NV; ++k) {
       if ((touched >> k) & 1u) {
         const int lin = lin0 + k * VPS * VPS;
-        tsdf[lin] = st[k];
-        if (p.with_tracking) m.last_obs[static_cast<size_t>(slot) * V + lin] = lobs[k];
+        const float2 st = s_st[k][threadIdx.x];
+        tsdf[lin] = st;
+        if (p.with_tracking) {
+          m.last_obs[base + lin] = s_lobs[k][threadIdx.x];
+          m.vflags[base + lin] = s_vfl[k][threadIdx.x] | (st.x < p.occ_thr ? 0 : kVoxNotOccupied);
+        }
       }
     }
     if (__any_sync(0xffffffffu, touched != 0)) {
@@ -474,105 +576,104 @@ __global__ void __launch_bounds__(kFuseThreads, 8) fuseKernel(const DeviceMap m,
   }
 }
 
-// ---- K2: TrackingIntegrator::updateBlockTracking (tracking_integrator.cpp:133-166, :224-246) --------
-__global__ void __launch_bounds__(kThreads) trackingKernel(const DeviceMap m, const TrackingParams p) {
-  const int slot = blockIdx.x;
+// ---- K2 (lazy): TrackingIntegrator::updateBlockTracking (tracking_integrator.cpp:133-166,224-246) ------
+// The reference rewrites last_occupied / active / to_remove of EVERY voxel of EVERY allocated block each
+// frame (~10 GB/frame at 50 k blocks). All three are pure functions of (distance, last_observed, the
+// pass history), so the pass itself only (1) records the pass in two small per-frame-index tables,
+// (2) latches tracking_updated into the ever-free work list and clears it, (3) clears the
+// finishMapping override. Per-voxel values are derived by evalTracking() when someone needs them
+// (K1 when it rewrites a voxel, K3, K2r, export) — bit-identical to the brute-force pass
+// (tests/test_parity_gpu.py, tests/test_golden.py).
+__global__ void trackingPassKernel(const DeviceMap m, const TrackingParams p) {
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot == 0) {
+    for (uint32_t i = p.prev_pass + 1; i <= p.ev.k_last; ++i) m.next_pass[i] = p.ev.k_last;
+    m.act_min[p.ev.k_last] = p.ev.act_min;
+  }
+  if (slot >= p.n_slots) return;
   const uint32_t flags = m.block_flags[slot];
   if (!(flags & kFlagAllocated)) return;
-  const int V = m.V;
-  const float2* __restrict__ tsdf = m.tsdf + static_cast<size_t>(slot) * V;
-  const uint32_t* __restrict__ last_obs = m.last_obs + static_cast<size_t>(slot) * V;
-  uint32_t* __restrict__ last_occ = m.last_occ + static_cast<size_t>(slot) * V;
-  uint8_t* __restrict__ vf = m.vflags + static_cast<size_t>(slot) * V;
-  int any_active = 0;
-  for (int lin = threadIdx.x; lin < V; lin += kThreads) {
-    if (tsdf[lin].x < p.occupancy_thr) last_occ[lin] = p.frame_idx;
-    const uint32_t lo = last_obs[lin];
-    const bool now_active = lo == 0 ? (p.zero_active != 0) : (lo >= p.active_min_idx);
-    uint8_t f = vf[lin];
-    const bool was_active = f & kVoxActive;
-    uint8_t nf = (f & ~kVoxActive) | (now_active ? kVoxActive : 0);
-    if (was_active && !now_active) nf |= kVoxToRemove;
-    if (nf != f) vf[lin] = nf;
-    any_active |= now_active;
-  }
-  any_active = __syncthreads_or(any_active);
-  if (threadIdx.x == 0) {
-    uint32_t f = flags & ~(static_cast<uint32_t>(KB_FLAG_TRACKING_UPDATED) | KB_FLAG_HAS_ACTIVE_DATA | kFlagEverFreePending);
-    if (flags & KB_FLAG_TRACKING_UPDATED) f |= kFlagEverFreePending;  // latch for K3
-    if (any_active) f |= KB_FLAG_HAS_ACTIVE_DATA;
-    m.block_flags[slot] = f;
-  }
+  uint32_t f = flags & ~(static_cast<uint32_t>(KB_FLAG_TRACKING_UPDATED) | kFlagInactiveOverride);
+  if (flags & KB_FLAG_TRACKING_UPDATED) p.pending[atomicAdd(&m.counters[kCtrPending], 1)] = slot;
+  if (f != flags) m.block_flags[slot] = f;
 }
 
 // ---- K3: TrackingIntegrator::updateBlockEverFree (tracking_integrator.cpp:168-222) ------------------
 // "free(v)" = ever_free(v) || voxelIsFree(v). Neighbours set ever_free concurrently, but a voxel set
 // in this pass necessarily satisfies voxelIsFree, so the predicate is stable under the race.
-__device__ __forceinline__ bool voxelFreeOrEverFree(const DeviceMap& m, const TrackingParams& p, size_t idx) {
-  if (m.vflags[idx] & kVoxEverFree) return true;
-  const uint32_t lo = m.last_obs[idx];
-  if (lo == 0) return false;
+// During a pass every voxel of an existing block has been seen by it, so last_occupied is "now" for
+// occupied voxels and the stored value otherwise.
+__device__ __forceinline__ bool voxelFreeNow(const DeviceMap& m, const TrackEval& t, size_t idx, uint8_t f) {
+  if (f & kVoxEverFree) return true;
+  if (!(f & kVoxNotOccupied)) return false;  // occupied => last_occupied == now (also: never observed)
   const uint32_t oc = m.last_occ[idx];
-  return oc == 0 ? (p.zero_free != 0) : (oc < p.free_max_idx);
+  return oc == 0 ? (t.zero_free != 0) : (oc < t.free_max);
 }
 
 __global__ void __launch_bounds__(kThreads) everFreeKernel(const DeviceMap m, const TrackingParams p) {
-  const int slot = blockIdx.x;
   __shared__ int s_nbr[27];
-  const uint32_t flags = m.block_flags[slot];
-  if (!(flags & kFlagAllocated) || !(flags & kFlagEverFreePending)) return;
+  const int n = m.counters[kCtrPending];
   const int vps = m.vps, V = m.V;
-  if (threadIdx.x < 27) {
-    const int3 bi = m.block_index[slot];
-    const int dx = threadIdx.x % 3 - 1, dy = (threadIdx.x / 3) % 3 - 1, dz = threadIdx.x / 9 - 1;
-    s_nbr[threadIdx.x] = (dx == 0 && dy == 0 && dz == 0) ? slot : hashLookup(m, bi.x + dx, bi.y + dy, bi.z + dz);
-  }
-  __syncthreads();
-  const size_t base = static_cast<size_t>(slot) * V;
-  for (int lin = threadIdx.x; lin < V; lin += kThreads) {
-    const uint8_t f = m.vflags[base + lin];
-    if (f & kVoxEverFree) continue;
-    {
-      const uint32_t lo = m.last_obs[base + lin];
-      if (lo == 0) continue;
-      const uint32_t oc = m.last_occ[base + lin];
-      const bool is_free = oc == 0 ? (p.zero_free != 0) : (oc < p.free_max_idx);
-      if (!is_free) continue;
+  for (int w = blockIdx.x; w < n; w += gridDim.x) {
+    const int slot = p.pending[w];
+    __syncthreads();
+    if (threadIdx.x < 27) {
+      const int3 bi = m.block_index[slot];
+      const int dx = threadIdx.x % 3 - 1, dy = (threadIdx.x / 3) % 3 - 1, dz = threadIdx.x / 9 - 1;
+      s_nbr[threadIdx.x] = (dx == 0 && dy == 0 && dz == 0) ? slot : hashLookup(m, bi.x + dx, bi.y + dy, bi.z + dz);
     }
-    const int vx = lin % vps, vy = (lin / vps) % vps, vz = lin / (vps * vps);
-    bool blocked = false;
-    for (int dz = -1; dz <= 1 && !blocked; ++dz)
-      for (int dy = -1; dy <= 1 && !blocked; ++dy)
-        for (int dx = -1; dx <= 1; ++dx) {
-          const int nnz = (dx != 0) + (dy != 0) + (dz != 0);
-          if (nnz == 0 || (p.connectivity == 6 && nnz > 1) || (p.connectivity == 18 && nnz > 2)) continue;
-          int nx = vx + dx, ny = vy + dy, nz = vz + dz;
-          int bx = 1, by = 1, bz = 1;
-          if (nx < 0) { nx += vps; bx = 0; } else if (nx >= vps) { nx -= vps; bx = 2; }
-          if (ny < 0) { ny += vps; by = 0; } else if (ny >= vps) { ny -= vps; by = 2; }
-          if (nz < 0) { nz += vps; bz = 0; } else if (nz >= vps) { nz -= vps; bz = 2; }
-          const int ns = s_nbr[bx + 3 * by + 9 * bz];
-          if (ns < 0) { blocked = true; break; }
-          const size_t nidx = static_cast<size_t>(ns) * V + (nx + vps * (ny + vps * nz));
-          if (!voxelFreeOrEverFree(m, p, nidx)) { blocked = true; break; }
-        }
-    if (!blocked) m.vflags[base + lin] = f | kVoxEverFree;
+    __syncthreads();
+    const size_t base = static_cast<size_t>(slot) * V;
+    for (int lin = threadIdx.x; lin < V; lin += kThreads) {
+      const uint8_t f = m.vflags[base + lin];
+      if ((f & kVoxEverFree) || !voxelFreeNow(m, p.ev, base + lin, f)) continue;
+      const int vx = lin % vps, vy = (lin / vps) % vps, vz = lin / (vps * vps);
+      bool blocked = false;
+      for (int dz = -1; dz <= 1 && !blocked; ++dz)
+        for (int dy = -1; dy <= 1 && !blocked; ++dy)
+          for (int dx = -1; dx <= 1; ++dx) {
+            const int nnz = (dx != 0) + (dy != 0) + (dz != 0);
+            if (nnz == 0 || (p.connectivity == 6 && nnz > 1) || (p.connectivity == 18 && nnz > 2)) continue;
+            int nx = vx + dx, ny = vy + dy, nz = vz + dz;
+            int bx = 1, by = 1, bz = 1;
+            if (nx < 0) { nx += vps; bx = 0; } else if (nx >= vps) { nx -= vps; bx = 2; }
+            if (ny < 0) { ny += vps; by = 0; } else if (ny >= vps) { ny -= vps; by = 2; }
+            if (nz < 0) { nz += vps; bz = 0; } else if (nz >= vps) { nz -= vps; bz = 2; }
+            const int ns = s_nbr[bx + 3 * by + 9 * bz];
+            if (ns < 0) { blocked = true; break; }  // missing neighbour block (:198-202)
+            const size_t nidx = static_cast<size_t>(ns) * V + (nx + vps * (ny + vps * nz));
+            if (!voxelFreeNow(m, p.ev, nidx, m.vflags[nidx])) { blocked = true; break; }
+          }
+      if (!blocked) m.vflags[base + lin] = f | kVoxEverFree;
+    }
   }
-  __syncthreads();
-  if (threadIdx.x == 0) m.block_flags[slot] = flags & ~kFlagEverFreePending;
 }
 
+// Resets the ever-free work counter after K3 (separate tiny launch: K3's CTAs all read it).
+__global__ void resetPendingKernel(const DeviceMap m) { m.counters[kCtrPending] = 0; }
+
 // ---- K2r: TrackingIntegrator::resetInactive (tracking_integrator.cpp:106-131) -----------------------
-__global__ void __launch_bounds__(kThreads) resetInactiveKernel(const DeviceMap m, int3* removed, int max_removed) {
+__global__ void __launch_bounds__(kThreads) resetInactiveKernel(const DeviceMap m, const TrackEval ev, int3* removed, int max_removed) {
   const int slot = blockIdx.x;
   const uint32_t flags = m.block_flags[slot];
   if (!(flags & kFlagAllocated)) return;
   const int V = m.V;
   const size_t base = static_cast<size_t>(slot) * V;
-  int all_remove = 1;
-  for (int lin = threadIdx.x; lin < V; lin += kThreads) all_remove &= (m.vflags[base + lin] & kVoxToRemove) ? 1 : 0;
+  const uint32_t born = m.born_frame[slot];
+  int all_remove = 1, any_active = 0;
+  for (int lin = threadIdx.x; lin < V; lin += kThreads) {
+    uint32_t c;
+    bool act, rem;
+    evalTracking(m, ev, born, m.last_obs[base + lin], m.last_occ[base + lin], m.vflags[base + lin], &c, &act, &rem);
+    all_remove &= rem ? 1 : 0;
+    any_active |= act ? 1 : 0;
+  }
   all_remove = __syncthreads_and(all_remove);
-  if ((flags & KB_FLAG_HAS_ACTIVE_DATA) && !all_remove) return;
+  any_active = __syncthreads_or(any_active);
+  // has_active_data: set by the last pass that saw the block; false before any pass and after finishMapping
+  const bool seen = ev.k_last != 0 && ev.k_last >= born;
+  const bool has_active = seen && any_active && !(flags & kFlagInactiveOverride);
+  if (has_active && !all_remove) return;
   // Remove: scrub the slot so that a later allocation starts from the default voxel state.
   const int sem = m.block_sem[slot];
   for (int lin = threadIdx.x; lin < V; lin += kThreads) {
@@ -604,7 +705,7 @@ __global__ void __launch_bounds__(kThreads) resetInactiveKernel(const DeviceMap 
 
 __global__ void markAllInactiveKernel(const DeviceMap m, int n) {
   const int slot = blockIdx.x * blockDim.x + threadIdx.x;
-  if (slot < n && (m.block_flags[slot] & kFlagAllocated)) m.block_flags[slot] &= ~static_cast<uint32_t>(KB_FLAG_HAS_ACTIVE_DATA);
+  if (slot < n && (m.block_flags[slot] & kFlagAllocated)) m.block_flags[slot] |= kFlagInactiveOverride;
 }
 
 __global__ void clearUpdatedKernel(const DeviceMap m, int n) {
@@ -654,7 +755,7 @@ __global__ void motionLookupKernel(const DeviceMap m, const __grid_constant__ Mo
 }
 
 // ---- E0: dense allocation (mesh_object_extractor.cpp:220-228) ----------------------------------------
-__global__ void allocateBoxKernel(const DeviceMap m, int3 lo, int3 dims, int rank, int nranks) {
+__global__ void allocateBoxKernel(const DeviceMap m, int3 lo, int3 dims, int rank, int nranks, uint32_t born) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= dims.x * dims.y * dims.z) return;
   const int bx = lo.x + c % dims.x;
@@ -662,7 +763,7 @@ __global__ void allocateBoxKernel(const DeviceMap m, int3 lo, int3 dims, int ran
   const int by = lo.y + c % dims.y, bz = lo.z + c / dims.y;
   if (nranks > 1 && blockOwner(bx, by, bz, nranks) != rank) return;
   int created;
-  hashFindOrInsert(m, bx, by, bz, &created);
+  hashFindOrInsert(m, bx, by, bz, born, &created);
 }
 
 // ---- K4: low-confidence erase (mesh_object_extractor.cpp:246-264, computeConfidence :342-356) -------
@@ -701,18 +802,31 @@ __global__ void gatherTsdfKernel(const DeviceMap m, const int* slots, float* dis
   }
 }
 
-__global__ void gatherTrackingKernel(const DeviceMap m, const int* slots, const unsigned long long* stamps,
-                                     unsigned long long* last_obs, unsigned long long* last_occ,
-                                     uint8_t* ever_free, uint8_t* active, uint8_t* to_remove) {
+__global__ void gatherTrackingKernel(const DeviceMap m, const TrackEval ev, const int* slots,
+                                     const unsigned long long* stamps, unsigned long long* last_obs,
+                                     unsigned long long* last_occ, uint8_t* ever_free, uint8_t* active,
+                                     uint8_t* to_remove, uint8_t* block_active) {
   const int V = m.V, slot = slots[blockIdx.x];
+  const uint32_t born = m.born_frame[slot];
+  int any_active = 0;
   for (int lin = threadIdx.x; lin < V; lin += blockDim.x) {
     const size_t src = static_cast<size_t>(slot) * V + lin, dst = static_cast<size_t>(blockIdx.x) * V + lin;
-    last_obs[dst] = stamps[m.last_obs[src]];
-    last_occ[dst] = stamps[m.last_occ[src]];
     const uint8_t f = m.vflags[src];
+    const uint32_t o = m.last_obs[src];
+    uint32_t c;
+    bool act, rem;
+    evalTracking(m, ev, born, o, m.last_occ[src], f, &c, &act, &rem);
+    last_obs[dst] = stamps[o];
+    last_occ[dst] = stamps[c];
     ever_free[dst] = (f & kVoxEverFree) ? 1 : 0;
-    active[dst] = (f & kVoxActive) ? 1 : 0;
-    to_remove[dst] = (f & kVoxToRemove) ? 1 : 0;
+    active[dst] = act ? 1 : 0;
+    to_remove[dst] = rem ? 1 : 0;
+    any_active |= act ? 1 : 0;
+  }
+  any_active = __syncthreads_or(any_active);
+  if (threadIdx.x == 0) {
+    const bool seen = ev.k_last != 0 && ev.k_last >= born;
+    block_active[blockIdx.x] = (seen && any_active && !(m.block_flags[slot] & kFlagInactiveOverride)) ? 1 : 0;
   }
 }
 
@@ -741,23 +855,32 @@ void launchTileMax(const BatchParams& p, cudaStream_t s) {
   tileMaxKernel<<<dim3((warps + 7) / 8, p.n_frames), 256, 0, s>>>(p);
   tileMax16Kernel<<<dim3((p.tiles16_x * p.tiles16_y + 255) / 256, p.n_frames), 256, 0, s>>>(p);
 }
-void launchSelectBlocks(const DeviceMap& m, const BatchParams& p, cudaStream_t s) {
+void launchSelectBlocks(const DeviceMap& m, const BatchParams& p, int cull_grid, cudaStream_t s) {
   const int n = p.allocate ? p.dims[0] * p.dims[1] * p.dims[2] : p.n_slots;
   selectBlocksKernel<<<(std::max(n, 1) + 3) / 4, 128, 0, s>>>(m, p);  // one warp per candidate
+  if (p.cull) {
+    if (m.vps == 16) itemCullKernel<16><<<cull_grid, 128, 0, s>>>(m, p);
+    else itemCullKernel<8><<<cull_grid, 128, 0, s>>>(m, p);
+  }
+}
+int fuseBlocksPerSm(int vps) {
+  int n = 0;
+  if (vps == 16) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fuseKernel<16>, kFuseThreads, 0);
+  else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fuseKernel<8>, kFuseThreads, 0);
+  return n > 0 ? n : 4;
 }
 void launchFuse(const DeviceMap& m, const BatchParams& p, int grid, cudaStream_t s) {
   if (grid <= 0) return;
   if (m.vps == 16) fuseKernel<16><<<grid, kFuseThreads, 0, s>>>(m, p);
   else fuseKernel<8><<<grid, kFuseThreads, 0, s>>>(m, p);
 }
-void launchTracking(const DeviceMap& m, const TrackingParams& p, int n, cudaStream_t s) {
-  if (n > 0) trackingKernel<<<n, kThreads, 0, s>>>(m, p);
+void launchTrackingPass(const DeviceMap& m, const TrackingParams& p, int everfree_grid, cudaStream_t s) {
+  trackingPassKernel<<<(std::max(p.n_slots, 1) + 255) / 256, 256, 0, s>>>(m, p);
+  everFreeKernel<<<everfree_grid, kThreads, 0, s>>>(m, p);
+  resetPendingKernel<<<1, 1, 0, s>>>(m);
 }
-void launchEverFree(const DeviceMap& m, const TrackingParams& p, int n, cudaStream_t s) {
-  if (n > 0) everFreeKernel<<<n, kThreads, 0, s>>>(m, p);
-}
-void launchResetInactive(const DeviceMap& m, int n, int3* removed, int max_removed, cudaStream_t s) {
-  if (n > 0) resetInactiveKernel<<<n, kThreads, 0, s>>>(m, removed, max_removed);
+void launchResetInactive(const DeviceMap& m, const TrackEval& ev, int n, int3* removed, int max_removed, cudaStream_t s) {
+  if (n > 0) resetInactiveKernel<<<n, kThreads, 0, s>>>(m, ev, removed, max_removed);
 }
 void launchMarkAllInactive(const DeviceMap& m, int n, cudaStream_t s) {
   if (n > 0) markAllInactiveKernel<<<(n + 255) / 256, 256, 0, s>>>(m, n);
@@ -769,9 +892,9 @@ void launchMotionLookup(const DeviceMap& m, const MotionParams& p, cudaStream_t 
   const int n = p.W * p.H;
   motionLookupKernel<<<(n + 255) / 256, 256, 0, s>>>(m, p);
 }
-void launchAllocateBox(const DeviceMap& m, int3 lo, int3 dims, int rank, int nranks, cudaStream_t s) {
+void launchAllocateBox(const DeviceMap& m, int3 lo, int3 dims, int rank, int nranks, uint32_t born, cudaStream_t s) {
   const int n = dims.x * dims.y * dims.z;
-  if (n > 0) allocateBoxKernel<<<(n + 127) / 128, 128, 0, s>>>(m, lo, dims, rank, nranks);
+  if (n > 0) allocateBoxKernel<<<(n + 127) / 128, 128, 0, s>>>(m, lo, dims, rank, nranks, born);
 }
 void launchScanConfidence(const DeviceMap& m, float min_conf, float min_obs, float trunc, int n, cudaStream_t s) {
   if (n > 0) scanConfidenceKernel<<<n, kThreads, 0, s>>>(m, min_conf, min_obs, trunc);
@@ -779,10 +902,11 @@ void launchScanConfidence(const DeviceMap& m, float min_conf, float min_obs, flo
 void launchGatherTsdf(const DeviceMap& m, const int* slots, int n, float* dist, float* weight, cudaStream_t s) {
   if (n > 0) gatherTsdfKernel<<<n, 256, 0, s>>>(m, slots, dist, weight);
 }
-void launchGatherTracking(const DeviceMap& m, const int* slots, int n, const unsigned long long* stamps,
-                          unsigned long long* last_obs, unsigned long long* last_occ, uint8_t* ever_free,
-                          uint8_t* active, uint8_t* to_remove, cudaStream_t s) {
-  if (n > 0) gatherTrackingKernel<<<n, 256, 0, s>>>(m, slots, stamps, last_obs, last_occ, ever_free, active, to_remove);
+void launchGatherTracking(const DeviceMap& m, const TrackEval& ev, const int* slots, int n,
+                          const unsigned long long* stamps, unsigned long long* last_obs,
+                          unsigned long long* last_occ, uint8_t* ever_free, uint8_t* active, uint8_t* to_remove,
+                          uint8_t* block_active, cudaStream_t s) {
+  if (n > 0) gatherTrackingKernel<<<n, 256, 0, s>>>(m, ev, slots, stamps, last_obs, last_occ, ever_free, active, to_remove, block_active);
 }
 void launchGatherSemantic(const DeviceMap& m, const int* slots, int n, int L, uint32_t* label, uint8_t* empty,
                           float* lik, cudaStream_t s) {

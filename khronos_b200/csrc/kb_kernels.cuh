@@ -40,6 +40,8 @@ struct BatchParams {
   int n_slots;         // allocate == 0: number of pool slots to scan
   int rank, nranks;
   int with_tracking;
+  TrackEval trk;       // lazy tracking: state of the last tracking pass (K1 folds it in when it rewrites a voxel)
+  float occ_thr;       // tsdf distance below which a voxel is occupied
   int n_frames;
   int parity;          // which of the two work-list counters this batch uses
   int cull;            // 1: conservative depth culling enabled
@@ -47,18 +49,18 @@ struct BatchParams {
   int* work_slots;     // [max_work] selected block slots
   uint32_t* work_masks;  // [max_work] bit b set: block is processed for frame b of the batch
   uint32_t* work_upd;    // [max_work] bit b set: some voxel of the block was updated by frame b
+  uint32_t* item_fmask;  // [max_work * items_per_block] frames (bits) for which the item survived culling
+  int items_per_block;   // 32 (16^3 blocks) or 4 (8^3): 128-voxel work items
   int max_work;
   FrameView f[kMaxBatch];
 };
 
 struct TrackingParams {
-  uint32_t frame_idx;       // current frame index ("now")
-  float occupancy_thr;      // tsdf distance below which a voxel is occupied
-  uint32_t active_min_idx;  // last_obs >= this  <=> toSeconds(last_obs) >= toSeconds(now) - window
-  int zero_active;          // the same predicate for last_obs == 0 (stamp 0)
-  uint32_t free_max_idx;    // last_occ < this   <=> toSeconds(last_occ) < toSeconds(now) - buffer
-  int zero_free;            // the same predicate for last_occ == 0
+  TrackEval ev;             // state of this pass (k_last = this pass)
+  uint32_t prev_pass;       // frame index of the previous pass (next_pass[] is filled for (prev, k_last])
   int connectivity;         // 6 | 18 | 26
+  int n_slots;              // pool slots to scan
+  int* pending;             // [max_blocks] ever-free work list (slots whose TSDF was updated since the last pass)
 };
 
 struct MotionParams {
@@ -74,23 +76,24 @@ struct MotionParams {
 };
 
 void launchTileMax(const BatchParams& p, cudaStream_t s);
-void launchSelectBlocks(const DeviceMap& m, const BatchParams& p, cudaStream_t s);
+void launchSelectBlocks(const DeviceMap& m, const BatchParams& p, int cull_grid, cudaStream_t s);
 void launchFuse(const DeviceMap& m, const BatchParams& p, int grid, cudaStream_t s);
-void launchTracking(const DeviceMap& m, const TrackingParams& p, int n_slots, cudaStream_t s);
-void launchEverFree(const DeviceMap& m, const TrackingParams& p, int n_slots, cudaStream_t s);
-void launchResetInactive(const DeviceMap& m, int n_slots, int3* removed, int max_removed, cudaStream_t s);
+int fuseBlocksPerSm(int vps);  // resident 128-thread CTAs per SM (occupancy API)
+void launchTrackingPass(const DeviceMap& m, const TrackingParams& p, int everfree_grid, cudaStream_t s);
+void launchResetInactive(const DeviceMap& m, const TrackEval& ev, int n_slots, int3* removed, int max_removed, cudaStream_t s);
 void launchMarkAllInactive(const DeviceMap& m, int n_slots, cudaStream_t s);
 void launchClearUpdated(const DeviceMap& m, int n_slots, cudaStream_t s);
 void launchMotionLookup(const DeviceMap& m, const MotionParams& p, cudaStream_t s);
-void launchAllocateBox(const DeviceMap& m, int3 lo, int3 dims, int rank, int nranks, cudaStream_t s);
+void launchAllocateBox(const DeviceMap& m, int3 lo, int3 dims, int rank, int nranks, uint32_t born, cudaStream_t s);
 void launchScanConfidence(const DeviceMap& m, float min_conf, float min_obs, float trunc, int n_slots,
                           cudaStream_t s);
 
 // Export gathers: slot_list[n] -> dense arrays (device), see kb_api.cu.
 void launchGatherTsdf(const DeviceMap& m, const int* slots, int n, float* dist, float* weight, cudaStream_t s);
-void launchGatherTracking(const DeviceMap& m, const int* slots, int n, const unsigned long long* stamps,
-                          unsigned long long* last_obs, unsigned long long* last_occ, uint8_t* ever_free,
-                          uint8_t* active, uint8_t* to_remove, cudaStream_t s);
+void launchGatherTracking(const DeviceMap& m, const TrackEval& ev, const int* slots, int n,
+                          const unsigned long long* stamps, unsigned long long* last_obs,
+                          unsigned long long* last_occ, uint8_t* ever_free, uint8_t* active, uint8_t* to_remove,
+                          uint8_t* block_active, cudaStream_t s);
 void launchGatherSemantic(const DeviceMap& m, const int* slots, int n, int L, uint32_t* label,
                           uint8_t* empty, float* lik, cudaStream_t s);
 

@@ -291,3 +291,63 @@ def test_pinned_host_frames_overlap_path(oracle_lib, product_lib):
     g.integrate_frames(fr[20:], want_stats=False)
     g.synchronize()
     hs.assert_blocks_equal(o.export_blocks(), g.export_blocks(), exact_float=True, what="pinned")
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_lazy_tracking_random_schedules(oracle_lib, product_lib, seed):
+    """The product keeps tracking state lazily (O(blocks) per pass instead of the reference's all-voxel
+    rewrite). Irregular schedules — several integrations between passes, passes without integration, time
+    jumps beyond the temporal window, re-observation after deactivation, block removal and re-allocation —
+    must still give exactly the brute-force oracle's last_occupied / active / to_remove / ever_free /
+    has_active_data."""
+    rng = np.random.default_rng(100 + seed)
+    cam = hs.small_camera(8)
+    scene = syn.room_scene()
+    n = 36
+    poses, _ = syn.orbit_trajectory(n, laps=0.6)
+    frames = hs.render_frames(scene, cam, poses, [0] * n)
+    o, g = both(oracle_lib, product_lib, cam=cam)
+    t = 500_000_000  # start below temporal_window so the "stamp 0 is active" quirk is exercised
+    i = 0
+    checks = 0
+    while i < n:
+        k = int(rng.integers(1, 4))  # integrate 1..3 frames
+        batch = []
+        for _ in range(k):
+            if i >= n:
+                break
+            t += int(rng.choice([40_000_000, 150_000_000, 600_000_000]))
+            batch.append((i, t))
+            i += 1
+        for h in (o, g):
+            fr = [h.make_frame(frames[j][0], poses[j], st, label=frames[j][1]) for j, st in batch]
+            if len(fr) > 1 and rng.integers(0, 2) == 0 and h is g:
+                h.integrate_frames(fr, want_stats=False)
+            else:
+                for f in fr:
+                    h.integrate_frame(f, want_stats=False)
+        ev = rng.integers(0, 10)
+        if ev < 7:          # normal paired pass
+            for h in (o, g):
+                h.update_tracking(t)
+        elif ev == 7:       # pass after a long silence (> temporal_window), then another one right after
+            t += 3_500_000_000
+            for h in (o, g):
+                h.update_tracking(t)
+            t += 10_000_000
+            for h in (o, g):
+                h.update_tracking(t)
+        # ev 8, 9: no pass this round
+        if rng.integers(0, 4) == 0:
+            ro, rg = o.reset_inactive(), g.reset_inactive()
+            np.testing.assert_array_equal(ro, rg)
+        if rng.integers(0, 3) == 0:
+            hs.assert_blocks_equal(o.export_blocks(), g.export_blocks(), exact_float=True, what=f"seed{seed} frame{i}")
+            checks += 1
+    hs.assert_blocks_equal(o.export_blocks(), g.export_blocks(), exact_float=True, what=f"seed{seed} final")
+    for h in (o, g):
+        h.mark_all_inactive()
+    bo, bg = o.export_blocks(), g.export_blocks()
+    np.testing.assert_array_equal(bo.block_flags, bg.block_flags)
+    np.testing.assert_array_equal(o.reset_inactive(), g.reset_inactive())
+    assert checks > 2
