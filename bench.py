@@ -379,7 +379,7 @@ def main():
         hl.copy_(label[idx[0]:idx[0] + n_e] if idx[-1] == idx[0] + n_e - 1 else label[torch.tensor(idx, device=dev)])
         torch.cuda.synchronize()
         frames = [h.make_frame(hd[j].data_ptr(), poses[idx[j]], stamp_of(base_step, j), label=hl[j].data_ptr(),
-                               memory=capi.MEM_HOST) for j in range(n_e)]
+                               memory=capi.MEM_HOST_ASYNC) for j in range(n_e)]
         calls = [((capi.Frame * len(frames[j0:j0 + B]))(*frames[j0:j0 + B]), len(frames[j0:j0 + B])) for j0 in range(0, n_e, B)]
         stats = capi.FrameStats()
         torch.cuda.synchronize()
@@ -393,7 +393,7 @@ def main():
         dt = time.perf_counter() - t0
         e2e = {"value": n_e / dt, "unit": "frames/s", "h2d_bytes_per_step": n_e * P * BYTES_PER_PIXEL_IN,
                "d2h_bytes_per_step": ctypes.sizeof(capi.FrameStats) + 64, "frames_per_step": n_e,
-               "note": "host pinned depth+label -> kb_integrate_frames(KB_MEM_HOST, %d frames/call); stats read back at step end" % B}
+               "note": "host pinned depth+label ring -> kb_integrate_frames(KB_MEM_HOST_ASYNC, %d frames/call); stats read back at step end" % B}
 
     # ---- CPU baseline on a bounded sample of the same stream (rank 0, N=1 only)
     cpu = None

@@ -105,7 +105,10 @@ typedef struct kb_camera {
   float min_range, max_range;
 } kb_camera;
 
-enum { KB_MEM_HOST = 0, KB_MEM_DEVICE = 1 };
+/* KB_MEM_HOST: host images, borrowed until the call returns. KB_MEM_DEVICE: device pointers, used in place.
+ * KB_MEM_HOST_ASYNC: pinned host images the caller keeps valid and unmodified until kb_synchronize() (or
+ * a later call that returns stats) — the H2D copies of consecutive calls then run back to back. */
+enum { KB_MEM_HOST = 0, KB_MEM_DEVICE = 1, KB_MEM_HOST_ASYNC = 2 };
 
 /* khronos::FrameData (khronos/include/khronos/active_window/data/frame_data.h:59-83) wrapping
  * hydra::InputData (UP). */
@@ -120,7 +123,7 @@ typedef struct kb_frame {
   double world_T_sensor[16];   /* row-major 4x4, InputData::getSensorPose() */
   uint64_t stamp_ns;           /* must be > 0 (0 is the reference's "never observed" sentinel) */
   int32_t object_target_id;    /* BINARY mode: ObjectIntegrator::setFrameData target id */
-  int32_t memory;              /* KB_MEM_HOST | KB_MEM_DEVICE for the image pointers above */
+  int32_t memory;              /* KB_MEM_HOST | KB_MEM_DEVICE | KB_MEM_HOST_ASYNC for the image pointers */
 } kb_frame;
 
 typedef struct kb_frame_stats {

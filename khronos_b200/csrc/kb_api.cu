@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/khronos_b200.h"
@@ -364,6 +365,7 @@ int kb_set_stream(kb_handle* h, void* cuda_stream) {
 
 int kb_synchronize(kb_handle* h) {
   if (!h) return KB_ERR_INVALID;
+  KB_CUDA(h, cudaStreamSynchronize(h->copy_stream));
   KB_CUDA(h, cudaStreamSynchronize(h->stream));
   return KB_OK;
 }
@@ -489,16 +491,10 @@ static int integrateBatch(kb_handle* h, const kb_frame* frames, int n, int alloc
       v.depth = f.depth; v.label = f.label; v.mask = f.mask; v.object_image = f.object_image;
     } else {
       const size_t off = (static_cast<size_t>(set) * kMaxBatch + b) * px;
-      auto up = [&](const void* src, void* dst, size_t bytes) -> int {
-        KB_CUDA(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->copy_stream));
-        return KB_OK;
-      };
       v.depth = h->stg_depth + off;
-      if ((st = up(f.depth, h->stg_depth + off, px * 4)) != KB_OK) return st;
-      v.label = v.mask = v.object_image = nullptr;
-      if (f.label) { v.label = h->stg_label + off; if ((st = up(f.label, h->stg_label + off, px * 4)) != KB_OK) return st; }
-      if (f.mask) { v.mask = h->stg_mask + off; if ((st = up(f.mask, h->stg_mask + off, px * 4)) != KB_OK) return st; }
-      if (f.object_image) { v.object_image = h->stg_object + off; if ((st = up(f.object_image, h->stg_object + off, px * 4)) != KB_OK) return st; }
+      v.label = f.label ? h->stg_label + off : nullptr;
+      v.mask = f.mask ? h->stg_mask + off : nullptr;
+      v.object_image = f.object_image ? h->stg_object + off : nullptr;
     }
     v.tile8 = h->tile_max + static_cast<size_t>(b) * h->tile_stride;
     v.tile16 = v.tile8 + static_cast<size_t>(p.tiles8_x) * p.tiles8_y;
@@ -512,6 +508,27 @@ static int integrateBatch(kb_handle* h, const kb_frame* frames, int n, int alloc
     }
   }
   if (any_host) {
+    // H2D staging. Runs of frames whose host images are contiguous in memory (a ring buffer / video
+    // tensor) are coalesced into one copy per image kind; separate cv::Mat buffers copy one by one.
+    auto copyKind = [&](auto member, auto* staging) -> int {
+      using T = std::remove_pointer_t<decltype(staging)>;
+      int b = 0;
+      while (b < n) {
+        const T* src = (frames[b].memory == KB_MEM_DEVICE) ? nullptr : static_cast<const T*>(frames[b].*member);
+        if (!src) { ++b; continue; }
+        int e = b + 1;
+        while (e < n && frames[e].memory != KB_MEM_DEVICE && static_cast<const T*>(frames[e].*member) == src + static_cast<size_t>(e - b) * px) ++e;
+        T* dst = staging + (static_cast<size_t>(set) * kMaxBatch + b) * px;
+        KB_CUDA(h, cudaMemcpyAsync(dst, src, static_cast<size_t>(e - b) * px * sizeof(T), cudaMemcpyHostToDevice, h->copy_stream));
+        b = e;
+      }
+      return KB_OK;
+    };
+    int cst;
+    if ((cst = copyKind(&kb_frame::depth, h->stg_depth)) != KB_OK) return cst;
+    if ((cst = copyKind(&kb_frame::label, h->stg_label)) != KB_OK) return cst;
+    if ((cst = copyKind(&kb_frame::mask, h->stg_mask)) != KB_OK) return cst;
+    if ((cst = copyKind(&kb_frame::object_image, h->stg_object)) != KB_OK) return cst;
     KB_CUDA(h, cudaEventRecord(h->stg_ready[set], h->copy_stream));
     KB_CUDA(h, cudaStreamWaitEvent(h->stream, h->stg_ready[set], 0));
   }
@@ -534,8 +551,11 @@ static int integrateBatch(kb_handle* h, const kb_frame* frames, int n, int alloc
   if (any_host) {
     KB_CUDA(h, cudaEventRecord(h->stg_consumed[set], h->stream));
     // KB_MEM_HOST buffers are borrowed only for the duration of the call: wait for the copies (the
-    // kernels keep running asynchronously and overlap the next call's copies).
-    KB_CUDA(h, cudaStreamSynchronize(h->copy_stream));
+    // kernels keep running asynchronously and overlap the next call's copies). KB_MEM_HOST_ASYNC
+    // callers keep their (pinned) buffers valid until kb_synchronize, so the copy engine never idles.
+    bool must_wait = false;
+    for (int b = 0; b < n; ++b) must_wait |= frames[b].memory == KB_MEM_HOST;
+    if (must_wait) KB_CUDA(h, cudaStreamSynchronize(h->copy_stream));
   }
   h->ctr_dirty = true;
   return KB_OK;

@@ -285,10 +285,12 @@ def test_pinned_host_frames_overlap_path(oracle_lib, product_lib):
     hs.run_fusion(o, frames, poses, stamps)
     hd = torch.from_numpy(np.stack([f[0] for f in frames])).pin_memory()
     hl = torch.from_numpy(np.stack([f[1] for f in frames])).pin_memory()
-    fr = [g.make_frame(hd[i].data_ptr(), poses[i], stamps[i], label=hl[i].data_ptr()) for i in range(len(frames))]
+    fr = [g.make_frame(hd[i].data_ptr(), poses[i], stamps[i], label=hl[i].data_ptr(),
+                       memory=capi.MEM_HOST if i < 40 else capi.MEM_HOST_ASYNC) for i in range(len(frames))]
     for i in range(0, 20):
-        g.integrate_frame(fr[i], want_stats=False)
-    g.integrate_frames(fr[20:], want_stats=False)
+        g.integrate_frame(fr[i], want_stats=False)       # borrowed per call
+    g.integrate_frames(fr[20:40], want_stats=False)      # contiguous run -> coalesced copies
+    g.integrate_frames(fr[40:], want_stats=False)        # caller-kept pinned buffers, copies not awaited
     g.synchronize()
     hs.assert_blocks_equal(o.export_blocks(), g.export_blocks(), exact_float=True, what="pinned")
 
