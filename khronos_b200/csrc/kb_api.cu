@@ -311,8 +311,8 @@ int kb_create(const kb_map_config* map, const kb_integrator_config* integ, const
       cudaDeviceProp prop{};
       KB_CUDA(h, cudaGetDeviceProperties(&prop, device));
       h->everfree_grid = prop.multiProcessorCount * 4;
-      h->cull_grid = prop.multiProcessorCount * 4;
-      h->fuse_grid = prop.multiProcessorCount * fuseBlocksPerSm(m.vps);  // persistent CTAs of independent warps
+      h->cull_grid = prop.multiProcessorCount * 8;
+      h->fuse_grid = prop.multiProcessorCount * fuseBlocksPerSm(m.vps, m.Lp);  // persistent CTAs of independent warps
     }
     h->max_removed = m.max_blocks;
     KB_CUDA(h, devAlloc(&h->d_removed, static_cast<size_t>(h->max_removed), 0));

@@ -342,6 +342,7 @@ __device__ __forceinline__ bool boxCulledLane(const BatchParams& p, const FrameV
   float dmax = 0.f;
   for (int ty = ty0; ty <= ty1; ++ty) {
     const float* __restrict__ row = f.tile8 + ty * p.tiles8_x;
+#pragma unroll 4
     for (int tx = tx0; tx <= tx1; ++tx) dmax = fmaxf(dmax, __ldg(&row[tx]));
   }
   if (!(dmax > 0.f)) return true;
@@ -350,7 +351,7 @@ __device__ __forceinline__ bool boxCulledLane(const BatchParams& p, const FrameV
 
 // One warp per (work block, chunk of kCullChunk frames); lane = work item of the block. Fills
 // item_fmask[block][item] with the frames for which the item may receive a measurement.
-constexpr int kCullChunk = 4;
+constexpr int kCullChunk = 1;
 template <int VPS>
 __global__ void __launch_bounds__(128) itemCullKernel(const DeviceMap m, const __grid_constant__ BatchParams p) {
   constexpr int ITEMS = (VPS / 4) * (VPS / 8) * (VPS / 4);
@@ -382,38 +383,6 @@ __global__ void __launch_bounds__(128) itemCullKernel(const DeviceMap m, const _
 }
 
 // ---- K1: projective TSDF + semantic fusion ----------------------------------------------------------------
-// SemanticIntegrator::updateLikelihoods (UP App. A.8) on one voxel's likelihood row. Out of line: it is
-// the rarely taken, instruction-heavy tail of the voxel update and must not be replicated per voxel slot.
-__device__ __noinline__ void semanticUpdate(float* __restrict__ row, uint16_t* __restrict__ slabel, int Lp, int L,
-                                            uint32_t label, int binary, float mle_init, float mle_diag, float mle_off) {
-  const bool empty = *slabel == kSemEmpty;
-  int best = 0;
-  if (binary) {
-    float2* lk = reinterpret_cast<float2*>(row);
-    float2 c = empty ? make_float2(0.f, 0.f) : *lk;
-    if (label) c.y = c.y + 1.f; else c.x = c.x + 1.f;
-    *lk = c;
-    best = c.y > c.x ? 1 : 0;
-  } else {
-    float4* lk = reinterpret_cast<float4*>(row);
-    float bestv = 0.f;
-    for (int k4 = 0; k4 < Lp; k4 += 4) {
-      float4 c = empty ? make_float4(mle_init, mle_init, mle_init, mle_init) : lk[k4 >> 2];
-      float* cf = reinterpret_cast<float*>(&c);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int kk = k4 + j;
-        if (kk < L) {
-          cf[j] = cf[j] + (static_cast<uint32_t>(kk) == label ? mle_diag : mle_off);
-          if (kk == 0 || cf[j] > bestv) { bestv = cf[j]; best = kk; }
-        }
-      }
-      lk[k4 >> 2] = c;
-    }
-  }
-  *slabel = static_cast<uint16_t>(best);
-}
-
 // Lazy tracking fold (see evalTracking): what the tracking passes since the voxel's last write would have
 // done to it. Returns the flag byte to carry (ever_free, active, to_remove); refreshes last_occupied.
 __device__ __noinline__ uint32_t trackingFold(const DeviceMap m, const TrackEval t, uint32_t born, size_t gi) {
@@ -426,25 +395,26 @@ __device__ __noinline__ uint32_t trackingFold(const DeviceMap m, const TrackEval
   return (fl & kVoxEverFree) | (act ? kVoxActive : 0) | (rem ? kVoxToRemove : 0);
 }
 
-// Persistent warps fetch work items = (selected block, 4x8x4-voxel box) from a shared cursor. Lane (x, y) of
-// the 4x8 box face owns the 4 voxels stacked in z; their {distance, weight, last_observed, flags} live in
-// shared memory (per-lane slots, no bank conflicts) while the warp walks the item's surviving frames in
-// order, so a voxel's TSDF is read and written once per batch and every warp access covers whole 32 B
-// sectors. Warps never synchronise with each other. The voxel loop is deliberately NOT unrolled: the body
-// is ~1 k SASS instructions and replicating it blew the instruction cache (profiles/r1_v3_*).
+// Persistent warps fetch work items from a shared cursor. An item = one z-layer (4x8 voxels, one per lane) of
+// a 4x8x4 box that survived culling, together with the box's frame mask. The lane keeps its voxel's
+// {distance, weight, last_observed, flags} in registers and its semantic likelihood row in shared memory
+// (transposed [label][thread]: conflict free) while the warp walks the surviving frames in order: TSDF and
+// likelihoods are read and written once per batch, every warp access covers whole 32 B sectors, and the
+// serial dependency chain per item is one voxel deep, so ~25 k items per batch balance over the SMs.
+// Warps never synchronise with each other.
 // ProjectiveIntegrator::updateBlock / getVoxelMeasurement / computeLabel / updateVoxel (UP App. A.6;
-// computeLabel structure pinned by khronos/src/active_window/integration/object_integrator.cpp:58-81).
+// computeLabel structure pinned by khronos/src/active_window/integration/object_integrator.cpp:58-81);
+// SemanticIntegrator::updateLikelihoods (UP App. A.8).
 template <int VPS>
 __global__ void __launch_bounds__(kFuseThreads) fuseKernel(const DeviceMap m, const __grid_constant__ BatchParams p) {
   constexpr int V = VPS * VPS * VPS;
-  constexpr int NV = 4;                          // voxels per lane (stacked in z)
-  constexpr int ITEMS = (VPS / 4) * (VPS / 8) * (VPS / NV);  // 32 (16^3) or 4 (8^3) items of 128 voxels
-  __shared__ float2 s_st[NV][kFuseThreads];
-  __shared__ uint32_t s_lobs[NV][kFuseThreads];
-  __shared__ uint8_t s_vfl[NV][kFuseThreads];
+  constexpr int NK = 4;                                      // z-layers per culling box
+  constexpr int BOXES = (VPS / 4) * (VPS / 8) * (VPS / NK);  // 32 (16^3) or 4 (8^3) boxes of 128 voxels
+  extern __shared__ float s_rows[];                          // [Lp][kFuseThreads] likelihood rows
   const int lane = threadIdx.x & 31;
-  const int n_items = min(m.counters[kCtrWork0 + p.parity], p.max_work) * ITEMS;
+  const int n_items = min(m.counters[kCtrWork0 + p.parity], p.max_work) * BOXES * NK;
   const bool binary = p.sem_mode == KB_SEMANTICS_BINARY;
+  const int L = p.L;
   int n_valid = 0, n_band = 0, n_sem = 0;
 
   for (;;) {
@@ -452,109 +422,134 @@ __global__ void __launch_bounds__(kFuseThreads) fuseKernel(const DeviceMap m, co
     if (lane == 0) w = atomicAdd(&m.counters[kCtrFetch], 1);
     w = __shfl_sync(0xffffffffu, w, 0);
     if (w >= n_items) break;
-    const uint32_t fmask = p.item_fmask[w];
+    const int box = w / NK, k = w % NK;
+    const uint32_t fmask = p.item_fmask[box];
     if (!fmask) continue;
-    const int wi = w / ITEMS, it = w % ITEMS;
+    const int wi = box / BOXES, it = box % BOXES;
     const int slot = p.work_slots[wi];
     const int3 bi = m.block_index[slot];
-    const int sem = p.L > 0 ? m.block_sem[slot] : -1;
+    const int sem = L > 0 ? m.block_sem[slot] : -1;
     int x0, y0, z0;
     itemOrigin<VPS>(it, x0, y0, z0);
-    const int vx = x0 + (lane & 3), vy = y0 + (lane >> 2);
-    const int lin0 = vx + VPS * (vy + VPS * z0);  // voxel k of this lane: lin0 + k*VPS*VPS
-    const size_t base = static_cast<size_t>(slot) * V;
-    float2* __restrict__ tsdf = m.tsdf + base;
+    const int vx = x0 + (lane & 3), vy = y0 + (lane >> 2), vz = z0 + k;
+    const int lin = vx + VPS * (vy + VPS * vz);
+    const size_t gi = static_cast<size_t>(slot) * V + lin;
     const float wx = static_cast<float>(bi.x) * p.block_size + (static_cast<float>(vx) + 0.5f) * p.voxel_size;
     const float wy = static_cast<float>(bi.y) * p.block_size + (static_cast<float>(vy) + 0.5f) * p.voxel_size;
-    const float oz = static_cast<float>(bi.z) * p.block_size;
-    const uint32_t born = p.with_tracking ? m.born_frame[slot] : 0u;
-    uint32_t have = 0, touched = 0, upd_frames = 0;
+    const float wz = static_cast<float>(bi.z) * p.block_size + (static_cast<float>(vz) + 0.5f) * p.voxel_size;
+    float2 st = make_float2(0.f, 0.f);
+    uint32_t lobs = 0, vfl = 0, upd_frames = 0;
+    bool have = false, row_resident = false;
+    int best_label = 0;
 
     uint32_t rem = fmask;
     while (rem) {
       const int b = __ffs(rem) - 1;
       rem &= rem - 1;
       const FrameView& f = p.f[b];
-      const bool has_label_img = p.L > 0 && (binary ? f.object_image != nullptr : f.label != nullptr);
-      // p_C = ((R0*x + R1*y) + R2*z) + t: the (x, y) partial sums are shared by the lane's 4 voxels
-      const float ax = f.R[0] * wx + f.R[1] * wy, ay = f.R[3] * wx + f.R[4] * wy, az = f.R[6] * wx + f.R[7] * wy;
-#pragma unroll 1
-      for (int k = 0; k < NV; ++k) {
-        const float wz = oz + (static_cast<float>(z0 + k) + 0.5f) * p.voxel_size;
-        const float x = (ax + f.R[2] * wz) + f.t[0];
-        const float y = (ay + f.R[5] * wz) + f.t[1];
-        const float z = (az + f.R[8] * wz) + f.t[2];
-        if (z <= 0.f) continue;
-        const float u = p.fx * x / z + p.cx;
-        const float v = p.fy * y / z + p.cy;
-        if (u < 0.f || u > static_cast<float>(p.W - 1) || v < 0.f || v > static_cast<float>(p.H - 1)) continue;
-        float range = 0.f;
-        const Taps taps = computeTaps(p, f.depth, u, v, range);
-        if (!taps.valid) continue;
-        const float sdf = range - z;
-        if (sdf < -p.trunc) continue;
-        const bool in_band = fabsf(sdf) < p.trunc;
-        uint32_t label = 0;
-        if (in_band) {
-          if (f.mask != nullptr && tapID(p, f.mask, taps) != 0) continue;
-          if (has_label_img) {
-            if (binary) {
-              label = tapID(p, f.object_image, taps) == f.target_id ? 1u : 0u;
-            } else {
-              label = static_cast<uint32_t>(tapID(p, f.label, taps));
-              if (label < static_cast<uint32_t>(KB_MAX_LABELS) && ((p.blocked_mask >> label) & 1ull)) continue;
+      const bool has_label_img = L > 0 && (binary ? f.object_image != nullptr : f.label != nullptr);
+      float x, y, z;
+      xform(f.R, f.t, wx, wy, wz, x, y, z);
+      if (z <= 0.f) continue;
+      const float u = p.fx * x / z + p.cx;
+      const float v = p.fy * y / z + p.cy;
+      if (u < 0.f || u > static_cast<float>(p.W - 1) || v < 0.f || v > static_cast<float>(p.H - 1)) continue;
+      float range = 0.f;
+      const Taps taps = computeTaps(p, f.depth, u, v, range);
+      if (!taps.valid) continue;
+      const float sdf = range - z;
+      if (sdf < -p.trunc) continue;
+      const bool in_band = fabsf(sdf) < p.trunc;
+      uint32_t label = 0;
+      if (in_band) {
+        if (f.mask != nullptr && tapID(p, f.mask, taps) != 0) continue;
+        if (has_label_img) {
+          if (binary) {
+            label = tapID(p, f.object_image, taps) == f.target_id ? 1u : 0u;
+          } else {
+            label = static_cast<uint32_t>(tapID(p, f.label, taps));
+            if (label < static_cast<uint32_t>(KB_MAX_LABELS) && ((p.blocked_mask >> label) & 1ull)) continue;
+          }
+        }
+      }
+      const float wm = measurementWeight(p, z, sdf);
+      if (!have) {
+        st = m.tsdf[gi];
+        have = true;
+        if (p.with_tracking) vfl = trackingFold(m, p.trk, m.born_frame[slot], gi);
+      }
+      const float sdf_c = fminf(fmaxf(sdf, -p.trunc), p.trunc);
+      const float2 old = st;
+      st.x = (old.x * old.y + sdf_c * wm) / (old.y + wm);
+      st.y = fminf(old.y + wm, p.max_weight);
+      lobs = f.frame_idx;
+      upd_frames |= 1u << b;
+      ++n_valid;
+      if (!in_band) continue;
+      ++n_band;
+      if (sem >= 0 && has_label_img && label < static_cast<uint32_t>(L)) {
+        const size_t si = static_cast<size_t>(sem) * V + lin;
+        if (!row_resident) {  // bring the voxel's likelihood row on chip (or start it)
+          row_resident = true;
+          const bool empty = m.sem_label[si] == kSemEmpty;
+          if (binary) {
+            const float2 c = empty ? make_float2(0.f, 0.f) : *reinterpret_cast<const float2*>(m.sem_lik + si * 2);
+            s_rows[threadIdx.x] = c.x;
+            s_rows[kFuseThreads + threadIdx.x] = c.y;
+          } else {
+            const float4* __restrict__ lk = reinterpret_cast<const float4*>(m.sem_lik + si * m.Lp);
+            for (int k4 = 0; k4 < m.Lp; k4 += 4) {
+              const float4 c = empty ? make_float4(p.mle_init, p.mle_init, p.mle_init, p.mle_init) : lk[k4 >> 2];
+              s_rows[(k4 + 0) * kFuseThreads + threadIdx.x] = c.x;
+              s_rows[(k4 + 1) * kFuseThreads + threadIdx.x] = c.y;
+              s_rows[(k4 + 2) * kFuseThreads + threadIdx.x] = c.z;
+              s_rows[(k4 + 3) * kFuseThreads + threadIdx.x] = c.w;
             }
           }
         }
-        const float wm = measurementWeight(p, z, sdf);
-        const int lin = lin0 + k * VPS * VPS;
-        float2 old;
-        if (!((have >> k) & 1u)) {
-          old = tsdf[lin];
-          have |= 1u << k;
-          s_vfl[k][threadIdx.x] = p.with_tracking ? static_cast<uint8_t>(trackingFold(m, p.trk, born, base + lin)) : uint8_t(0);
+        if (binary) {
+          const float c = s_rows[label * kFuseThreads + threadIdx.x] + 1.f;
+          s_rows[label * kFuseThreads + threadIdx.x] = c;
+          best_label = s_rows[kFuseThreads + threadIdx.x] > s_rows[threadIdx.x] ? 1 : 0;
         } else {
-          old = s_st[k][threadIdx.x];
+          float bestv = 0.f;
+          for (int kk = 0; kk < L; ++kk) {
+            const float c = s_rows[kk * kFuseThreads + threadIdx.x] + (static_cast<uint32_t>(kk) == label ? p.mle_diag : p.mle_off);
+            s_rows[kk * kFuseThreads + threadIdx.x] = c;
+            if (kk == 0 || c > bestv) { bestv = c; best_label = kk; }
+          }
         }
-        const float sdf_c = fminf(fmaxf(sdf, -p.trunc), p.trunc);
-        float2 upd;
-        upd.x = (old.x * old.y + sdf_c * wm) / (old.y + wm);
-        upd.y = fminf(old.y + wm, p.max_weight);
-        s_st[k][threadIdx.x] = upd;
-        s_lobs[k][threadIdx.x] = f.frame_idx;
-        touched |= 1u << k;
-        upd_frames |= 1u << b;
-        ++n_valid;
-        if (!in_band) continue;
-        ++n_band;
-        if (sem >= 0 && has_label_img && label < static_cast<uint32_t>(p.L)) {
-          const size_t si = static_cast<size_t>(sem) * V + lin;
-          semanticUpdate(m.sem_lik + si * m.Lp, m.sem_label + si, m.Lp, p.L, label, binary ? 1 : 0, p.mle_init, p.mle_diag, p.mle_off);
-          ++n_sem;
-        }
+        ++n_sem;
       }
     }
 
-    // ---- write the voxel state back once; block flags + per-(block, frame) update bookkeeping ----
-#pragma unroll
-    for (int k = 0; k < NV; ++k) {
-      if ((touched >> k) & 1u) {
-        const int lin = lin0 + k * VPS * VPS;
-        const float2 st = s_st[k][threadIdx.x];
-        tsdf[lin] = st;
-        if (p.with_tracking) {
-          m.last_obs[base + lin] = s_lobs[k][threadIdx.x];
-          m.vflags[base + lin] = s_vfl[k][threadIdx.x] | (st.x < p.occ_thr ? 0 : kVoxNotOccupied);
+    // ---- write the voxel back once; block flags + per-(block, frame) update bookkeeping ----
+    if (have) {
+      m.tsdf[gi] = st;
+      if (p.with_tracking) {
+        m.last_obs[gi] = lobs;
+        m.vflags[gi] = static_cast<uint8_t>(vfl | (st.x < p.occ_thr ? 0 : kVoxNotOccupied));
+      }
+      if (row_resident) {
+        const size_t si = static_cast<size_t>(sem) * V + lin;
+        if (binary) {
+          *reinterpret_cast<float2*>(m.sem_lik + si * 2) = make_float2(s_rows[threadIdx.x], s_rows[kFuseThreads + threadIdx.x]);
+        } else {
+          float4* __restrict__ lk = reinterpret_cast<float4*>(m.sem_lik + si * m.Lp);
+          for (int k4 = 0; k4 < m.Lp; k4 += 4)
+            lk[k4 >> 2] = make_float4(s_rows[(k4 + 0) * kFuseThreads + threadIdx.x], s_rows[(k4 + 1) * kFuseThreads + threadIdx.x],
+                                      s_rows[(k4 + 2) * kFuseThreads + threadIdx.x], s_rows[(k4 + 3) * kFuseThreads + threadIdx.x]);
         }
+        m.sem_label[si] = static_cast<uint16_t>(best_label);
       }
     }
-    if (__any_sync(0xffffffffu, touched != 0)) {
+    if (__any_sync(0xffffffffu, have)) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) upd_frames |= __shfl_xor_sync(0xffffffffu, upd_frames, o);
       if (lane == 0) {
         const uint32_t all = KB_FLAG_UPDATED | KB_FLAG_MESH_UPDATED | KB_FLAG_ESDF_UPDATED | KB_FLAG_TRACKING_UPDATED;
         if ((m.block_flags[slot] & all) != all) atomicOr(&m.block_flags[slot], all);
-        // blocks_updated counts (block, frame) pairs once even though several items report them
+        // blocks_updated counts (block, frame) pairs once even though many items report them
         if ((p.work_upd[wi] & upd_frames) != upd_frames) {
           const uint32_t prev = atomicOr(&p.work_upd[wi], upd_frames);
           const int fresh = __popc(upd_frames & ~prev);
@@ -863,16 +858,18 @@ void launchSelectBlocks(const DeviceMap& m, const BatchParams& p, int cull_grid,
     else itemCullKernel<8><<<cull_grid, 128, 0, s>>>(m, p);
   }
 }
-int fuseBlocksPerSm(int vps) {
+static size_t fuseSmemBytes(int Lp) { return static_cast<size_t>(std::max(Lp, 2)) * kFuseThreads * sizeof(float); }
+int fuseBlocksPerSm(int vps, int Lp) {
   int n = 0;
-  if (vps == 16) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fuseKernel<16>, kFuseThreads, 0);
-  else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fuseKernel<8>, kFuseThreads, 0);
+  if (vps == 16) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fuseKernel<16>, kFuseThreads, fuseSmemBytes(Lp));
+  else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fuseKernel<8>, kFuseThreads, fuseSmemBytes(Lp));
   return n > 0 ? n : 4;
 }
 void launchFuse(const DeviceMap& m, const BatchParams& p, int grid, cudaStream_t s) {
   if (grid <= 0) return;
-  if (m.vps == 16) fuseKernel<16><<<grid, kFuseThreads, 0, s>>>(m, p);
-  else fuseKernel<8><<<grid, kFuseThreads, 0, s>>>(m, p);
+  const size_t smem = fuseSmemBytes(m.Lp);
+  if (m.vps == 16) fuseKernel<16><<<grid, kFuseThreads, smem, s>>>(m, p);
+  else fuseKernel<8><<<grid, kFuseThreads, smem, s>>>(m, p);
 }
 void launchTrackingPass(const DeviceMap& m, const TrackingParams& p, int everfree_grid, cudaStream_t s) {
   trackingPassKernel<<<(std::max(p.n_slots, 1) + 255) / 256, 256, 0, s>>>(m, p);

@@ -78,7 +78,7 @@ struct MotionParams {
 void launchTileMax(const BatchParams& p, cudaStream_t s);
 void launchSelectBlocks(const DeviceMap& m, const BatchParams& p, int cull_grid, cudaStream_t s);
 void launchFuse(const DeviceMap& m, const BatchParams& p, int grid, cudaStream_t s);
-int fuseBlocksPerSm(int vps);  // resident 128-thread CTAs per SM (occupancy API)
+int fuseBlocksPerSm(int vps, int Lp);  // resident 128-thread CTAs per SM (occupancy API)
 void launchTrackingPass(const DeviceMap& m, const TrackingParams& p, int everfree_grid, cudaStream_t s);
 void launchResetInactive(const DeviceMap& m, const TrackEval& ev, int n_slots, int3* removed, int max_removed, cudaStream_t s);
 void launchMarkAllInactive(const DeviceMap& m, int n_slots, cudaStream_t s);

@@ -126,7 +126,7 @@ def _slab(o, d, bmin, bmax):
 
 
 def render(scene: Scene, cam: Camera, pose: np.ndarray, t_s: float = 0.0, device="cpu",
-           dtype=torch.float64):
+           dtype=torch.float64, extra_cuboid=None):
     """Returns (depth f32 HxW, label i32 HxW). depth = z-depth in metres, 0 where out of
     [min_range, max_range] (the normalised InputData depth/range image)."""
     W, H = cam.width, cam.height
@@ -160,6 +160,9 @@ def render(scene: Scene, cam: Camera, pose: np.ndarray, t_s: float = 0.0, device
         hs = np.asarray(size, dtype=np.float64) / 2
         cubs = np.concatenate([cubs, np.concatenate([c - hs, c + hs])[None, :]], axis=0)
         labels = np.concatenate([labels, np.array([scene.num_labels - 1], np.int32)])
+    if extra_cuboid is not None:  # per-frame scripted object (label L-1), (6,) min xyz max xyz
+        cubs = np.concatenate([cubs, np.asarray(extra_cuboid, dtype=np.float64)[None, :]], axis=0)
+        labels = np.concatenate([labels, np.array([scene.num_labels - 1], np.int32)])
     if len(cubs):
         cb = torch.as_tensor(cubs, device=dev, dtype=dtype)
         tnear, tfar_c, _, _ = _slab(o, d, cb[:, :3], cb[:, 3:])
@@ -178,13 +181,32 @@ def render(scene: Scene, cam: Camera, pose: np.ndarray, t_s: float = 0.0, device
             label.reshape(H, W).to(torch.int32).contiguous())
 
 
-def render_stream(scene, cam, poses, stamps, device="cpu", dtype=torch.float64):
+def companion_cuboids(poses, start_frame=60, distance=2.2, size=(1.05, 1.05, 1.6), sway=0.8, period=120):
+    """Config 3 dynamic object: an axis-aligned box that stays `distance` metres in front of the camera
+    (swaying sideways), appearing after `start_frame` frames of burn-in. At 2.2 m a 1.05 x 1.6 m face covers
+    roughly 20 % of a 640x480 / f=320 image. Returns a list of (6,) cuboids or None per frame."""
+    out = []
+    for i, T in enumerate(poses):
+        if i < start_frame:
+            out.append(None)
+            continue
+        T = np.asarray(T)
+        lateral = sway * math.sin(2.0 * math.pi * (i - start_frame) / period)
+        c = T[:3, 3] + T[:3, 2] * distance + T[:3, 0] * lateral
+        c[2] = size[2] / 2 + 0.05
+        h = np.asarray(size) / 2
+        out.append(np.concatenate([c - h, c + h]))
+    return out
+
+
+def render_stream(scene, cam, poses, stamps, device="cpu", dtype=torch.float64, extra=None):
     """Renders all frames; returns depth (N,H,W) f32 and label (N,H,W) i32 tensors on `device`."""
     n = len(poses)
     depth = torch.empty((n, cam.height, cam.width), dtype=torch.float32, device=device)
     label = torch.empty((n, cam.height, cam.width), dtype=torch.int32, device=device)
     t0 = stamps[0]
     for i, (T, st) in enumerate(zip(poses, stamps)):
-        d, l = render(scene, cam, T, (st - t0) * 1e-9, device=device, dtype=dtype)
+        d, l = render(scene, cam, T, (st - t0) * 1e-9, device=device, dtype=dtype,
+                      extra_cuboid=None if extra is None else extra[i])
         depth[i], label[i] = d, l
     return depth, label
