@@ -180,8 +180,8 @@ int kb_integrate_frames(kb_handle* h, const kb_frame* frames, int32_t n_frames, 
  * min(n, available) values. Index 17 = (block, frame) pairs that survived K0 culling. */
 int kb_get_debug_counters(kb_handle* h, int32_t* out, int32_t n);
 
-/* Enables (default) / disables the conservative per-(block, frame) depth culling. Results do not
- * depend on this switch; it exists so tests can prove that. */
+/* 1 (default): conservative per-(block, frame) depth culling for calls with >= 4 frames; 0: never; 2: always.
+ * Results do not depend on this switch; it exists so tests can prove that. */
 int kb_set_culling(kb_handle* h, int enabled);
 
 /* Cumulative counters since kb_create (same fields as kb_frame_stats, summed over all frames;

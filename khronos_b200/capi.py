@@ -258,7 +258,8 @@ class MapHandle:
         self._check(self._fn("get_debug_counters")(self._h, C.c_void_p(out.ctypes.data), n))
         return out
 
-    def set_culling(self, enabled: bool):
+    def set_culling(self, enabled):
+        """0 = off, 1/True = default (calls with >= 4 frames), 2 = always."""
         self._check(self._fn("set_culling")(self._h, int(enabled)))
 
     def get_totals(self) -> FrameStats:

@@ -61,6 +61,7 @@ struct kb_handle {
   int* pending = nullptr;     // ever-free work list
   int everfree_grid = 0;
   bool cull = true;
+  bool cull_forced = false;  // kb_set_culling(2): cull even single frames (tests)
   int fuse_grid = 0;
   bool hwm_dirty = true;
   int hwm_cached = 0;
@@ -439,6 +440,7 @@ int kb_get_debug_counters(kb_handle* h, int32_t* out, int32_t n) {
 int kb_set_culling(kb_handle* h, int enabled) {
   if (!h) return KB_ERR_INVALID;
   h->cull = enabled != 0;
+  h->cull_forced = enabled == 2;
   return KB_OK;
 }
 
@@ -460,7 +462,9 @@ static int integrateBatch(kb_handle* h, const kb_frame* frames, int n, int alloc
   p.nranks = h->nranks;
   p.parity = h->parity;
   h->parity ^= 1;
-  p.cull = h->cull ? 1 : 0;
+  // the culling stages cost ~3 extra launches: they pay off once a few frames share them
+  p.cull = (h->cull && (n >= 4 || h->cull_forced)) ? 1 : 0;
+  p.layers_per_item = n >= 8 ? 1 : 4;
   p.trk = h->pass;
 
   // ---- stage host images (double-buffered, on the copy stream so they overlap the previous batch)

@@ -144,87 +144,84 @@ __device__ __forceinline__ int warpSum(int v) {
 }
 
 // ---- per-frame tile maxima of the depth image (input of the conservative culling) ---------------------
-// Two levels: 8x8-pixel tiles (work-item culling in K1) and 16x16-pixel tiles (block culling in K0).
-// One warp reduces an 8-row x 32-column strip: coalesced row reads, vertical max in registers,
-// horizontal max over 8-lane groups by shuffles -> four 8x8 maxima per warp.
+// Two levels: 8x8-pixel tiles (box culling in K0b) and 16x16-pixel tiles (block culling in K0).
+// One warp reduces a 16-row x 32-column strip: coalesced row reads, vertical max in registers,
+// horizontal max over 8-/16-lane groups by shuffles -> eight 8x8 and two 16x16 maxima per warp.
 __global__ void __launch_bounds__(256) tileMaxKernel(const __grid_constant__ BatchParams p) {
   const int b = blockIdx.y;
   const int warps_x = (p.W + 31) / 32;
   const int warp = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (warp >= warps_x * p.tiles8_y) return;
-  const int ty = warp / warps_x, wx = warp % warps_x;
+  if (warp >= warps_x * p.tiles16_y) return;
+  const int ty16 = warp / warps_x, wx = warp % warps_x;
   const int u = wx * 32 + lane;
   const float* __restrict__ depth = p.f[b].depth;
-  float d = 0.f;
+  float d[2] = {0.f, 0.f};
 #pragma unroll
-  for (int r = 0; r < 8; ++r) {
-    const int v = ty * 8 + r;
-    if (u < p.W && v < p.H) d = fmaxf(d, __ldg(&depth[v * p.W + u]));
+  for (int r = 0; r < 16; ++r) {
+    const int v = ty16 * 16 + r;
+    if (u < p.W && v < p.H) d[r >> 3] = fmaxf(d[r >> 3], __ldg(&depth[v * p.W + u]));
   }
-  d = fmaxf(d, __shfl_xor_sync(0xffffffffu, d, 1));
-  d = fmaxf(d, __shfl_xor_sync(0xffffffffu, d, 2));
-  d = fmaxf(d, __shfl_xor_sync(0xffffffffu, d, 4));
-  const int tx = wx * 4 + (lane >> 3);
-  if ((lane & 7) == 0 && tx < p.tiles8_x) p.f[b].tile8[ty * p.tiles8_x + tx] = d;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    d[h] = fmaxf(d[h], __shfl_xor_sync(0xffffffffu, d[h], 1));
+    d[h] = fmaxf(d[h], __shfl_xor_sync(0xffffffffu, d[h], 2));
+    d[h] = fmaxf(d[h], __shfl_xor_sync(0xffffffffu, d[h], 4));
+    const int tx = wx * 4 + (lane >> 3), ty = ty16 * 2 + h;
+    if ((lane & 7) == 0 && tx < p.tiles8_x && ty < p.tiles8_y) p.f[b].tile8[ty * p.tiles8_x + tx] = d[h];
+  }
+  float m16 = fmaxf(d[0], d[1]);
+  m16 = fmaxf(m16, __shfl_xor_sync(0xffffffffu, m16, 8));
+  const int tx16 = wx * 2 + (lane >> 4);
+  if ((lane & 15) == 0 && tx16 < p.tiles16_x) p.f[b].tile16[ty16 * p.tiles16_x + tx16] = m16;
 }
 
-__global__ void __launch_bounds__(256) tileMax16Kernel(const __grid_constant__ BatchParams p) {
-  const int b = blockIdx.y;
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= p.tiles16_x * p.tiles16_y) return;
-  const int tx = t % p.tiles16_x, ty = t / p.tiles16_x;
-  float d = 0.f;
-#pragma unroll
-  for (int j = 0; j < 2; ++j)
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int x = tx * 2 + i, y = ty * 2 + j;
-      if (x < p.tiles8_x && y < p.tiles8_y) d = fmaxf(d, p.f[b].tile8[y * p.tiles8_x + x]);
-    }
-  p.f[b].tile16[t] = d;
+// Conservative culling rule for an axis-aligned box of voxel centres [lo, hi] (world frame) against frame
+// f: a (box, frame) pair is skipped only if NO voxel centre inside the box can receive a valid measurement,
+// so skipping cannot change any result (SURVEY §7 hard part 4): the box projects entirely outside the
+// image, or every depth pixel its voxels could tap is invalid, or every voxel lies more than the truncation
+// distance behind the farthest of those depths (sdf < -trunc). Margins (1 mm, 2 px) are far above the fp32
+// rounding of the per-voxel arithmetic.
+
+// ---- culling helpers (lane-serial) ----------------------------------------------------------------------------
+// Box of voxel centres of work item `it` of a block (4x8x4 voxels; x fastest).
+template <int VPS>
+__device__ __forceinline__ void itemOrigin(int it, int& x0, int& y0, int& z0) {
+  constexpr int IX = VPS / 4, IY = VPS / 8;
+  x0 = (it % IX) * 4;
+  y0 = ((it / IX) % IY) * 8;
+  z0 = (it / (IX * IY)) * 4;
 }
 
-// Conservative culling test for an axis-aligned box of voxel centres [lo, hi] (world frame) against
-// frame f: true if NO voxel centre inside the box can receive a valid measurement, so skipping the
-// (box, frame) pair cannot change any result (SURVEY §7 hard part 4): the box projects entirely outside
-// the image, or every depth pixel its voxels could tap is invalid, or every voxel lies more than the
-// truncation distance behind the farthest of those depths (sdf < -trunc). Margins (1 mm, 2 px) are far
-// above the fp32 rounding of the per-voxel arithmetic. Executed by a full warp: lanes 0-7 project
-// the corners, all lanes scan the tile rectangle. Returns the same value in every lane.
-__device__ __forceinline__ bool boxCulledWarp(const BatchParams& p, const FrameView& f, const float* __restrict__ tiles,
+// One lane tests one box: 8 corner projections, then the tile-maximum rectangle they span.
+__device__ __forceinline__ bool boxCulledLane(const BatchParams& p, const FrameView& f, const float* __restrict__ tiles,
                                               int tiles_x, int tile_shift, float lox, float loy, float loz,
-                                              float hix, float hiy, float hiz, int lane) {
-  const int c = lane & 7;
-  float x, y, z;
-  xform(f.R, f.t, (c & 1) ? hix : lox, (c & 2) ? hiy : loy, (c & 4) ? hiz : loz, x, y, z);
-  const bool behind = z < 1e-2f;
-  const float zs = behind ? 1.f : z;
-  float u = p.fx * x / zs + p.cx, v = p.fy * y / zs + p.cy;
-  float zmin = z, umin = u, umax = u, vmin = v, vmax = v;
-#pragma unroll
-  for (int o = 1; o < 8; o <<= 1) {
-    zmin = fminf(zmin, __shfl_xor_sync(0xffffffffu, zmin, o));
-    umin = fminf(umin, __shfl_xor_sync(0xffffffffu, umin, o));
-    umax = fmaxf(umax, __shfl_xor_sync(0xffffffffu, umax, o));
-    vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
-    vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+                                              float hix, float hiy, float hiz) {
+  float zmin = 3.0e38f, umin = 3.0e38f, umax = -3.0e38f, vmin = 3.0e38f, vmax = -3.0e38f;
+#pragma unroll 1
+  for (int c = 0; c < 8; ++c) {
+    float x, y, z;
+    xform(f.R, f.t, (c & 1) ? hix : lox, (c & 2) ? hiy : loy, (c & 4) ? hiz : loz, x, y, z);
+    if (z < 1e-2f) return false;  // reaches behind / near the camera plane: keep
+    const float u = p.fx * x / z + p.cx, v = p.fy * y / z + p.cy;
+    zmin = fminf(zmin, z);
+    umin = fminf(umin, u); umax = fmaxf(umax, u);
+    vmin = fminf(vmin, v); vmax = fmaxf(vmax, v);
   }
-  if (__any_sync(0xffffffffu, behind)) return false;  // box reaches behind / near the camera plane: keep
   if (umax < -0.5f || vmax < -0.5f || umin > static_cast<float>(p.W - 1) + 0.5f || vmin > static_cast<float>(p.H - 1) + 0.5f)
-    return true;  // projects entirely outside the image
+    return true;
   const int u0 = max(static_cast<int>(floorf(umin)) - 2, 0), u1 = min(static_cast<int>(floorf(umax)) + 3, p.W - 1);
   const int v0 = max(static_cast<int>(floorf(vmin)) - 2, 0), v1 = min(static_cast<int>(floorf(vmax)) + 3, p.H - 1);
-  const int tx0 = u0 >> tile_shift, ty0 = v0 >> tile_shift;
-  const int nx = (u1 >> tile_shift) - tx0 + 1, ny = (v1 >> tile_shift) - ty0 + 1;
-  const int n = nx * ny;
-  if (n > 512) return false;  // huge footprint (box right in front of the camera): keep
+  const int tx0 = u0 >> tile_shift, tx1 = u1 >> tile_shift, ty0 = v0 >> tile_shift, ty1 = v1 >> tile_shift;
+  if ((tx1 - tx0 + 1) * (ty1 - ty0 + 1) > 400) return false;  // huge footprint: keep
   float dmax = 0.f;
-  for (int i = lane; i < n; i += 32) dmax = fmaxf(dmax, __ldg(&tiles[(ty0 + i / nx) * tiles_x + tx0 + i % nx]));
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) dmax = fmaxf(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
-  if (!(dmax > 0.f)) return true;       // no valid depth anywhere in the footprint
-  return zmin - p.trunc - 1e-3f > dmax;  // everything is beyond the truncation band
+  for (int ty = ty0; ty <= ty1; ++ty) {
+    const float* __restrict__ row = tiles + ty * tiles_x;
+#pragma unroll 4
+    for (int tx = tx0; tx <= tx1; ++tx) dmax = fmaxf(dmax, __ldg(&row[tx]));
+  }
+  if (!(dmax > 0.f)) return true;
+  return zmin - p.trunc - 1e-3f > dmax;
 }
 
 // ---- K0: block selection for a batch of frames ---------------------------------------------------------
@@ -275,16 +272,14 @@ __global__ void __launch_bounds__(128) selectBlocksKernel(const DeviceMap m, con
     if (created) atomicAdd(&m.counters[kCtrAllocated], 1);
   }
   if (p.cull) {
+    // block-level culling, lane = frame: each lane tests the whole block against its own frame
     const float ox = static_cast<float>(bx) * p.block_size, oy = static_cast<float>(by) * p.block_size,
                 oz = static_cast<float>(bz) * p.block_size;
     const float lo = 0.5f * p.voxel_size, hi = p.block_size - 0.5f * p.voxel_size;
-    uint32_t rem = mask;
-    while (rem) {
-      const int b = __ffs(rem) - 1;
-      rem &= rem - 1;
-      if (boxCulledWarp(p, p.f[b], p.f[b].tile16, p.tiles16_x, 4, ox + lo, oy + lo, oz + lo, ox + hi, oy + hi, oz + hi, lane))
-        mask &= ~(1u << b);
-    }
+    bool keep = false;
+    if ((mask >> lane) & 1u)
+      keep = !boxCulledLane(p, p.f[lane], p.f[lane].tile16, p.tiles16_x, 4, ox + lo, oy + lo, oz + lo, ox + hi, oy + hi, oz + hi);
+    mask = __ballot_sync(0xffffffffu, keep);
     if (!mask) return;
   }
   int i = 0;
@@ -310,45 +305,6 @@ __global__ void __launch_bounds__(128) selectBlocksKernel(const DeviceMap m, con
 }
 
 // ---- K0b: work-item culling --------------------------------------------------------------------------------
-// Box of voxel centres of work item `it` of a block (4x8x4 voxels; x fastest).
-template <int VPS>
-__device__ __forceinline__ void itemOrigin(int it, int& x0, int& y0, int& z0) {
-  constexpr int IX = VPS / 4, IY = VPS / 8;
-  x0 = (it % IX) * 4;
-  y0 = ((it / IX) % IY) * 8;
-  z0 = (it / (IX * IY)) * 4;
-}
-
-// Scalar version of boxCulledWarp for one lane (one work item): same conservative rule, 8x8 tiles.
-__device__ __forceinline__ bool boxCulledLane(const BatchParams& p, const FrameView& f, float lox, float loy,
-                                              float loz, float hix, float hiy, float hiz) {
-  float zmin = 3.0e38f, umin = 3.0e38f, umax = -3.0e38f, vmin = 3.0e38f, vmax = -3.0e38f;
-#pragma unroll 1
-  for (int c = 0; c < 8; ++c) {
-    float x, y, z;
-    xform(f.R, f.t, (c & 1) ? hix : lox, (c & 2) ? hiy : loy, (c & 4) ? hiz : loz, x, y, z);
-    if (z < 1e-2f) return false;  // reaches behind / near the camera plane: keep
-    const float u = p.fx * x / z + p.cx, v = p.fy * y / z + p.cy;
-    zmin = fminf(zmin, z);
-    umin = fminf(umin, u); umax = fmaxf(umax, u);
-    vmin = fminf(vmin, v); vmax = fmaxf(vmax, v);
-  }
-  if (umax < -0.5f || vmax < -0.5f || umin > static_cast<float>(p.W - 1) + 0.5f || vmin > static_cast<float>(p.H - 1) + 0.5f)
-    return true;
-  const int u0 = max(static_cast<int>(floorf(umin)) - 2, 0), u1 = min(static_cast<int>(floorf(umax)) + 3, p.W - 1);
-  const int v0 = max(static_cast<int>(floorf(vmin)) - 2, 0), v1 = min(static_cast<int>(floorf(vmax)) + 3, p.H - 1);
-  const int tx0 = u0 >> 3, tx1 = u1 >> 3, ty0 = v0 >> 3, ty1 = v1 >> 3;
-  if ((tx1 - tx0 + 1) * (ty1 - ty0 + 1) > 400) return false;  // huge footprint: keep
-  float dmax = 0.f;
-  for (int ty = ty0; ty <= ty1; ++ty) {
-    const float* __restrict__ row = f.tile8 + ty * p.tiles8_x;
-#pragma unroll 4
-    for (int tx = tx0; tx <= tx1; ++tx) dmax = fmaxf(dmax, __ldg(&row[tx]));
-  }
-  if (!(dmax > 0.f)) return true;
-  return zmin - p.trunc - 1e-3f > dmax;
-}
-
 // One warp per (work block, chunk of kCullChunk frames); lane = work item of the block. Fills
 // item_fmask[block][item] with the frames for which the item may receive a measurement.
 constexpr int kCullChunk = 1;
@@ -376,7 +332,7 @@ __global__ void __launch_bounds__(128) itemCullKernel(const DeviceMap m, const _
     while (rem) {
       const int b = __ffs(rem) - 1;
       rem &= rem - 1;
-      if (!boxCulledLane(p, p.f[b], lx, ly, lz, hx, hy, hz)) keep |= 1u << b;
+      if (!boxCulledLane(p, p.f[b], p.f[b].tile8, p.tiles8_x, 3, lx, ly, lz, hx, hy, hz)) keep |= 1u << b;
     }
     if (keep) atomicOr(&p.item_fmask[static_cast<size_t>(wi) * ITEMS + lane], keep);
   }
@@ -412,7 +368,10 @@ __global__ void __launch_bounds__(kFuseThreads) fuseKernel(const DeviceMap m, co
   constexpr int BOXES = (VPS / 4) * (VPS / 8) * (VPS / NK);  // 32 (16^3) or 4 (8^3) boxes of 128 voxels
   extern __shared__ float s_rows[];                          // [Lp][kFuseThreads] likelihood rows
   const int lane = threadIdx.x & 31;
-  const int n_items = min(m.counters[kCtrWork0 + p.parity], p.max_work) * BOXES * NK;
+  // Short batches have little work per voxel, so an item then covers all NK layers of its box (amortising the
+  // fetch); long batches use one layer per item for balance.
+  const int lpi = p.layers_per_item, ipb = NK / lpi;  // layers per item, items per box
+  const int n_items = min(m.counters[kCtrWork0 + p.parity], p.max_work) * BOXES * ipb;
   const bool binary = p.sem_mode == KB_SEMANTICS_BINARY;
   const int L = p.L;
   int n_valid = 0, n_band = 0, n_sem = 0;
@@ -422,7 +381,7 @@ __global__ void __launch_bounds__(kFuseThreads) fuseKernel(const DeviceMap m, co
     if (lane == 0) w = atomicAdd(&m.counters[kCtrFetch], 1);
     w = __shfl_sync(0xffffffffu, w, 0);
     if (w >= n_items) break;
-    const int box = w / NK, k = w % NK;
+    const int box = w / ipb;
     const uint32_t fmask = p.item_fmask[box];
     if (!fmask) continue;
     const int wi = box / BOXES, it = box % BOXES;
@@ -431,6 +390,10 @@ __global__ void __launch_bounds__(kFuseThreads) fuseKernel(const DeviceMap m, co
     const int sem = L > 0 ? m.block_sem[slot] : -1;
     int x0, y0, z0;
     itemOrigin<VPS>(it, x0, y0, z0);
+    uint32_t upd_all = 0;
+    bool any_have = false;
+#pragma unroll 1
+    for (int k = (w % ipb) * lpi; k < (w % ipb) * lpi + lpi; ++k) {
     const int vx = x0 + (lane & 3), vy = y0 + (lane >> 2), vz = z0 + k;
     const int lin = vx + VPS * (vy + VPS * vz);
     const size_t gi = static_cast<size_t>(slot) * V + lin;
@@ -543,7 +506,11 @@ __global__ void __launch_bounds__(kFuseThreads) fuseKernel(const DeviceMap m, co
         m.sem_label[si] = static_cast<uint16_t>(best_label);
       }
     }
-    if (__any_sync(0xffffffffu, have)) {
+    upd_all |= upd_frames;
+    any_have |= have;
+    }  // layers of the item
+    if (__any_sync(0xffffffffu, any_have)) {
+      uint32_t upd_frames = upd_all;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) upd_frames |= __shfl_xor_sync(0xffffffffu, upd_frames, o);
       if (lane == 0) {
@@ -846,9 +813,8 @@ __global__ void gatherSemanticKernel(const DeviceMap m, const int* slots, int L,
 }  // namespace
 
 void launchTileMax(const BatchParams& p, cudaStream_t s) {
-  const int warps = ((p.W + 31) / 32) * p.tiles8_y;
+  const int warps = ((p.W + 31) / 32) * p.tiles16_y;
   tileMaxKernel<<<dim3((warps + 7) / 8, p.n_frames), 256, 0, s>>>(p);
-  tileMax16Kernel<<<dim3((p.tiles16_x * p.tiles16_y + 255) / 256, p.n_frames), 256, 0, s>>>(p);
 }
 void launchSelectBlocks(const DeviceMap& m, const BatchParams& p, int cull_grid, cudaStream_t s) {
   const int n = p.allocate ? p.dims[0] * p.dims[1] * p.dims[2] : p.n_slots;

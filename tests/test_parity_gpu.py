@@ -267,7 +267,7 @@ def test_culling_does_not_change_results(oracle_lib, product_lib):
     o = hs.make_handle(oracle_lib, "ko_", cam=cam)
     so = hs.run_fusion(o, frames, poses, stamps)
     bo = o.export_blocks()
-    for cull in (True, False):
+    for cull in (2, 0):  # 2 = cull even single-frame calls, 0 = never
         g = hs.make_handle(product_lib, "kb_", cam=cam)
         g.set_culling(cull)
         sg = hs.run_fusion(g, frames, poses, stamps)
