@@ -110,6 +110,11 @@ typedef struct kb_camera {
  * a later call that returns stats) — the H2D copies of consecutive calls then run back to back. */
 enum { KB_MEM_HOST = 0, KB_MEM_DEVICE = 1, KB_MEM_HOST_ASYNC = 2 };
 
+/* Pass as kb_frame.mask to integrate with the dynamic image of the most recent kb_detect_motion call, which is
+ * still resident on the device (saves the H2D copy of the mask in the per-frame pipeline
+ * detect -> integrate -> track, active_window.cpp:127,209-210). */
+#define KB_MASK_LAST_DETECTION ((const int32_t*)(uintptr_t)1)
+
 /* khronos::FrameData (khronos/include/khronos/active_window/data/frame_data.h:59-83) wrapping
  * hydra::InputData (UP). */
 typedef struct kb_frame {

@@ -20,6 +20,7 @@ KB_ERR_NO_DEVICE = 4
 INTERP_NEAREST, INTERP_BILINEAR, INTERP_ADAPTIVE = 0, 1, 2
 SEM_NONE, SEM_MLE, SEM_BINARY = 0, 1, 2
 MEM_HOST, MEM_DEVICE, MEM_HOST_ASYNC = 0, 1, 2
+MASK_LAST_DETECTION = 1  # kb_frame.mask sentinel: reuse the device-resident dynamic image of the last detection
 EXPORT_ALL, EXPORT_UPDATED = 0, 1
 FLAG_UPDATED, FLAG_MESH_UPDATED, FLAG_ESDF_UPDATED, FLAG_TRACKING_UPDATED, FLAG_HAS_ACTIVE_DATA = 1, 2, 4, 8, 16
 

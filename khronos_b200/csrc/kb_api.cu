@@ -12,6 +12,7 @@
 
 #include "../../include/khronos_b200.h"
 #include "kb_kernels.cuh"
+#include "kb_motion_device.cuh"
 #include "kb_motion_host.h"
 
 using namespace kb;
@@ -76,6 +77,12 @@ struct kb_handle {
   std::vector<uint8_t> h_pixel_seed;
   std::vector<float> h_depth;
   MotionResult motion;
+  MotionTable mt{};            // device clustering table (M2-M4)
+  int32_t* d_dynamic = nullptr;  // device copy of the last dynamic image (usable as KB_MASK_LAST_DETECTION)
+  int* h_mscal = nullptr;      // pinned mirror of the clustering scalars
+  bool motion_stale = false;   // cluster lists of the last detection not yet built on the host
+  MotionHostParams motion_hp{};
+  bool motion_have_image = false;
   int3* d_removed = nullptr;
   int max_removed = 0;
   std::string err;
@@ -120,11 +127,32 @@ int ensureStaging(kb_handle* h, size_t pixels) {
 
 int ensureMotionBuffers(kb_handle* h, size_t pixels) {
   if (h->mot_pixels >= pixels) return KB_OK;
+  MotionTable& t = h->mt;
   cudaFree(h->mot_depth); cudaFree(h->stg_vertex); cudaFree(h->d_pixel_gidx); cudaFree(h->d_pixel_seed);
+  cudaFree(h->d_dynamic);
+  cudaFree(t.keys); cudaFree(t.count); cudaFree(t.flags); cudaFree(t.deg); cudaFree(t.parent); cudaFree(t.pix_total);
+  cudaFree(t.min_seed); cudaFree(t.cluster_id); cudaFree(t.roots); cudaFree(t.scalars); cudaFree(t.pix_slot);
   KB_CUDA(h, devAlloc(&h->mot_depth, pixels, 0));
   KB_CUDA(h, devAlloc(&h->stg_vertex, pixels * 3, 0));
   KB_CUDA(h, devAlloc(&h->d_pixel_gidx, pixels, 0));
   KB_CUDA(h, devAlloc(&h->d_pixel_seed, pixels, 0));
+  KB_CUDA(h, devAlloc(&h->d_dynamic, pixels, 0));
+  uint32_t cap = 1024;
+  while (cap < 2 * pixels) cap <<= 1;
+  t.mask = cap - 1;
+  t.max_roots = 4096;
+  KB_CUDA(h, devAlloc(&t.keys, cap, 0xFF));
+  KB_CUDA(h, devAlloc(&t.count, cap, 0));
+  KB_CUDA(h, devAlloc(&t.flags, cap, 0));
+  KB_CUDA(h, devAlloc(&t.deg, cap, 0));
+  KB_CUDA(h, devAlloc(&t.parent, cap, 0));
+  KB_CUDA(h, devAlloc(&t.pix_total, cap, 0));
+  KB_CUDA(h, devAlloc(&t.min_seed, cap, 0xFF));
+  KB_CUDA(h, devAlloc(&t.cluster_id, cap, 0));
+  KB_CUDA(h, devAlloc(&t.roots, static_cast<size_t>(t.max_roots), 0));
+  KB_CUDA(h, devAlloc(&t.scalars, static_cast<size_t>(kMsCount), 0));
+  KB_CUDA(h, devAlloc(&t.pix_slot, pixels, 0xFF));
+  if (!h->h_mscal) KB_CUDA(h, cudaMallocHost(reinterpret_cast<void**>(&h->h_mscal), sizeof(int) * kMsCount));
   h->mot_pixels = pixels;
   return KB_OK;
 }
@@ -193,6 +221,25 @@ int slotHwm(kb_handle* h, int* n) {
   int st = readCounters(h);
   if (st != KB_OK) return st;
   *n = std::min(h->h_ctr[kCtrPoolHwm], h->dm.max_blocks);
+  return KB_OK;
+}
+
+// Host M2-M4 on the per-pixel voxel keys of the last M1 launch (slow path: cluster lists on demand, separation
+// distance <= 0, caller-supplied vertex maps, pathological cluster counts).
+int buildMotionClustersOnHost(kb_handle* h, const float* vertex_world_host, int32_t* image_out) {
+  const size_t px = static_cast<size_t>(h->cam.width) * h->cam.height;
+  h->h_pixel_gidx.resize(px * 3);
+  h->h_pixel_seed.resize(px);
+  h->h_depth.resize(px);
+  KB_CUDA(h, cudaMemcpyAsync(h->h_pixel_gidx.data(), h->d_pixel_gidx, sizeof(int3) * px, cudaMemcpyDeviceToHost, h->stream));
+  KB_CUDA(h, cudaMemcpyAsync(h->h_pixel_seed.data(), h->d_pixel_seed, px, cudaMemcpyDeviceToHost, h->stream));
+  KB_CUDA(h, cudaMemcpyAsync(h->h_depth.data(), h->mot_depth, sizeof(float) * px, cudaMemcpyDeviceToHost, h->stream));
+  KB_CUDA(h, cudaStreamSynchronize(h->stream));
+  std::vector<int32_t> scratch;
+  if (!image_out) { scratch.assign(px, 0); image_out = scratch.data(); }
+  clusterMotion(h->motion_hp, h->h_pixel_gidx.data(), h->h_pixel_seed.data(), h->h_depth.data(), vertex_world_host,
+                image_out, &h->motion);
+  h->motion_stale = false;
   return KB_OK;
 }
 
@@ -342,6 +389,10 @@ int kb_destroy(kb_handle* h) {
   cudaFree(m.sem_label); cudaFree(m.sem_lik);
   cudaFree(h->stg_depth); cudaFree(h->stg_label); cudaFree(h->stg_mask); cudaFree(h->stg_object);
   cudaFree(h->stg_vertex); cudaFree(h->d_pixel_gidx); cudaFree(h->d_pixel_seed); cudaFree(h->d_removed);
+  cudaFree(h->d_dynamic);
+  { MotionTable& t = h->mt; cudaFree(t.keys); cudaFree(t.count); cudaFree(t.flags); cudaFree(t.deg); cudaFree(t.parent);
+    cudaFree(t.pix_total); cudaFree(t.min_seed); cudaFree(t.cluster_id); cudaFree(t.roots); cudaFree(t.scalars); cudaFree(t.pix_slot); }
+  if (h->h_mscal) cudaFreeHost(h->h_mscal);
   cudaFree(h->mot_depth); cudaFree(h->tile_max); cudaFree(h->work_slots); cudaFree(h->work_masks); cudaFree(h->work_upd); cudaFree(h->item_fmask);
   for (int i = 0; i < 2; ++i) {
     if (h->stg_ready[i]) cudaEventDestroy(h->stg_ready[i]);
@@ -500,6 +551,8 @@ static int integrateBatch(kb_handle* h, const kb_frame* frames, int n, int alloc
       v.mask = f.mask ? h->stg_mask + off : nullptr;
       v.object_image = f.object_image ? h->stg_object + off : nullptr;
     }
+    if (f.mask == KB_MASK_LAST_DETECTION)  // dynamic image of the last kb_detect_motion, still on the device
+      v.mask = h->motion_have_image ? h->d_dynamic : nullptr;
     v.tile8 = h->tile_max + static_cast<size_t>(b) * h->tile_stride;
     v.tile16 = v.tile8 + static_cast<size_t>(p.tiles8_x) * p.tiles8_y;
     if (allocate_blocks) {
@@ -519,9 +572,9 @@ static int integrateBatch(kb_handle* h, const kb_frame* frames, int n, int alloc
       int b = 0;
       while (b < n) {
         const T* src = (frames[b].memory == KB_MEM_DEVICE) ? nullptr : static_cast<const T*>(frames[b].*member);
-        if (!src) { ++b; continue; }
+        if (!src || static_cast<const void*>(src) == static_cast<const void*>(KB_MASK_LAST_DETECTION)) { ++b; continue; }
         int e = b + 1;
-        while (e < n && frames[e].memory != KB_MEM_DEVICE && static_cast<const T*>(frames[e].*member) == src + static_cast<size_t>(e - b) * px) ++e;
+        while (e < n && frames[e].memory != KB_MEM_DEVICE && static_cast<const T*>(frames[e].*member) == src + static_cast<size_t>(e - b) * px) ++e;  // contiguous run
         T* dst = staging + (static_cast<size_t>(set) * kMaxBatch + b) * px;
         KB_CUDA(h, cudaMemcpyAsync(dst, src, static_cast<size_t>(e - b) * px * sizeof(T), cudaMemcpyHostToDevice, h->copy_stream));
         b = e;
@@ -765,33 +818,21 @@ int kb_detect_motion(kb_handle* h, const kb_frame* f, int32_t* dynamic_image_out
   if ((st = stage(h, f->vertex_world, h->stg_vertex, px * 3, f->memory, &p.vertex)) != KB_OK) return st;
   p.pixel_gidx = h->d_pixel_gidx;
   p.pixel_seed = h->d_pixel_seed;
-  if ((st = readCounters(h)) != KB_OK) return st;
-  const int seeds_before = h->h_ctr[kCtrSeeds];
+  KB_CUDA(h, cudaMemsetAsync(h->dm.counters + kCtrSeeds, 0, sizeof(int), h->stream));
   launchMotionLookup(h->dm, p, h->stream);
   KB_CUDA(h, cudaGetLastError());
-  if ((st = readCounters(h)) != KB_OK) return st;
-  const int seed_pixels = h->h_ctr[kCtrSeeds] - seeds_before;
+  if ((st = readCounters(h)) != KB_OK) return st;  // one 4 B round trip: are there any seeds at all?
+  const int seed_pixels = h->h_ctr[kCtrSeeds];
 
-  std::memset(dynamic_image_out, 0, sizeof(int32_t) * px);
   h->motion.clusters.clear();
   h->motion.n_seeds = 0;
-  if (seed_pixels > 0) {
-    // Seeds exist: bring the per-pixel voxel keys back and cluster on the host (M2-M4 are serial,
-    // data-dependent graph walks over a handful of voxels; SURVEY §8f lists a device version as next).
-    h->h_pixel_gidx.resize(px * 3);
-    h->h_pixel_seed.resize(px);
-    KB_CUDA(h, cudaMemcpyAsync(h->h_pixel_gidx.data(), h->d_pixel_gidx, sizeof(int3) * px, cudaMemcpyDeviceToHost, h->stream));
-    KB_CUDA(h, cudaMemcpyAsync(h->h_pixel_seed.data(), h->d_pixel_seed, px, cudaMemcpyDeviceToHost, h->stream));
-    const float* depth_host = f->depth;
-    const float* vertex_host = f->vertex_world;
-    if (f->memory == KB_MEM_DEVICE) {
-      h->h_depth.resize(px);
-      KB_CUDA(h, cudaMemcpyAsync(h->h_depth.data(), f->depth, sizeof(float) * px, cudaMemcpyDeviceToHost, h->stream));
-      depth_host = h->h_depth.data();
-      vertex_host = nullptr;  // bounding boxes are recomputed from depth + pose (identical arithmetic)
-    }
-    KB_CUDA(h, cudaStreamSynchronize(h->stream));
-    MotionHostParams mp{};
+  h->motion_stale = false;
+  h->motion_have_image = false;
+  int n_clusters_out = 0;
+  if (seed_pixels == 0) {
+    std::memset(dynamic_image_out, 0, sizeof(int32_t) * px);
+  } else {
+    MotionHostParams& mp = h->motion_hp;
     mp.W = c.width; mp.H = c.height; mp.fx = c.fx; mp.fy = c.fy; mp.cx = c.cx; mp.cy = c.cy;
     std::memcpy(mp.Rw, p.Rw, sizeof(mp.Rw));
     std::memcpy(mp.tw, p.tw, sizeof(mp.tw));
@@ -799,17 +840,49 @@ int kb_detect_motion(kb_handle* h, const kb_frame* f, int32_t* dynamic_image_out
     mp.min_cluster_size = h->mot.min_cluster_size;
     mp.max_cluster_size = h->mot.max_cluster_size;
     mp.min_separation_distance = h->mot.min_separation_distance;
-    clusterMotion(mp, h->h_pixel_gidx.data(), h->h_pixel_seed.data(), depth_host, vertex_host,
-                  dynamic_image_out, &h->motion);
+    // keep the depth image on the device for lazily built cluster lists (bounding boxes)
+    if (f->memory == KB_MEM_DEVICE && p.depth != h->mot_depth)
+      KB_CUDA(h, cudaMemcpyAsync(h->mot_depth, p.depth, sizeof(float) * px, cudaMemcpyDeviceToDevice, h->stream));
+    bool device_path = h->mot.min_separation_distance > 0.f && f->vertex_world == nullptr;
+    if (device_path) {
+      // M2-M4 on the device: connected components over the voxels that contain points
+      const int D = static_cast<int>(std::ceil(h->mot.min_separation_distance));
+      launchMotionClustering(h->mt, h->d_pixel_gidx, h->d_pixel_seed, static_cast<int>(px), h->mot.neighbor_connectivity,
+                             D, h->mot.min_cluster_size, h->mot.max_cluster_size, h->d_dynamic, h->stream);
+      KB_CUDA(h, cudaGetLastError());
+      KB_CUDA(h, cudaMemcpyAsync(h->h_mscal, h->mt.scalars, sizeof(int) * kMsCount, cudaMemcpyDeviceToHost, h->stream));
+      KB_CUDA(h, cudaMemcpyAsync(dynamic_image_out, h->d_dynamic, sizeof(int32_t) * px, cudaMemcpyDeviceToHost, h->stream));
+      KB_CUDA(h, cudaStreamSynchronize(h->stream));
+      if (h->h_mscal[kMsRoots] > h->mt.max_roots) {
+        device_path = false;  // pathological number of clusters: fall through to the host path
+      } else {
+        h->motion.n_seeds = h->h_mscal[kMsSeeds];
+        n_clusters_out = h->h_mscal[kMsClusters];
+        h->motion_stale = n_clusters_out > 0;  // cluster lists are built on demand (kb_get_motion_clusters)
+        h->motion_have_image = true;
+      }
+    }
+    if (!device_path) {
+      std::memset(dynamic_image_out, 0, sizeof(int32_t) * px);
+      if ((st = buildMotionClustersOnHost(h, f->memory == KB_MEM_DEVICE ? nullptr : f->vertex_world, dynamic_image_out)) != KB_OK) return st;
+      n_clusters_out = static_cast<int>(h->motion.clusters.size());
+      KB_CUDA(h, cudaMemcpyAsync(h->d_dynamic, dynamic_image_out, sizeof(int32_t) * px, cudaMemcpyHostToDevice, h->stream));
+      h->motion_have_image = true;
+    }
   }
   if (n_seeds) *n_seeds = h->motion.n_seeds;
-  if (n_clusters) *n_clusters = static_cast<int32_t>(h->motion.clusters.size());
+  if (n_clusters) *n_clusters = n_clusters_out;
   return KB_OK;
 }
 
 int kb_get_motion_clusters(kb_handle* h, int32_t* counts, int32_t* pixels_uv, int64_t* voxels_xyz,
                            float* bbox_min_max, int32_t* total_pixels, int32_t* total_voxels) {
   if (!h) return KB_ERR_INVALID;
+  if (h->motion_stale) {
+    KB_CUDA(h, cudaSetDevice(h->device));
+    const int st = buildMotionClustersOnHost(h, nullptr, nullptr);
+    if (st != KB_OK) return st;
+  }
   size_t tp = 0, tv = 0;
   const auto& cl = h->motion.clusters;
   for (size_t c = 0; c < cl.size(); ++c) {

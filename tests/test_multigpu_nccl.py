@@ -38,7 +38,7 @@ def _worker(rank, world, port, q):
             label.copy_(torch.from_numpy(np.stack([f[1] for f in fr])))
         kd.broadcast_frames(depth, label, src=0)   # NCCL over NVLink
         torch.cuda.synchronize()
-        h = hs.make_handle(kb.lib(), "kb_", cam=cam)
+        h = hs.make_handle(kb.lib(), "kb_", cam=cam, device=rank)  # the map lives on this rank's GPU
         h.set_shard(rank, world)
         frames = [h.make_frame(depth[i].data_ptr(), poses[i], stamps[i], label=label[i].data_ptr(), memory=capi.MEM_DEVICE)
                   for i in range(n)]
@@ -64,11 +64,9 @@ def _worker(rank, world, port, q):
                 ok = ok and (np.concatenate([g[k] for g in gathered])[order] == getattr(bo, k)).all()
             q.put(("ok" if ok else "mismatch", [len(g["block_index"]) for g in gathered], bo.n))
     except Exception as e:  # pragma: no cover
-        if rank == 0:
-            q.put(("error: %r" % (e,), [], 0))
-        raise
-    finally:
-        dist.destroy_process_group()
+        q.put(("error on rank %d: %r" % (rank, e), [], 0))  # any rank reports, so the parent never waits in vain
+        os._exit(1)  # do not linger in a half-dead NCCL communicator
+    dist.destroy_process_group()
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
@@ -78,11 +76,16 @@ def test_two_gpu_sharded_fusion_matches_oracle():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29700 + (os.getpid() % 200)
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q), daemon=True) for r in range(world)]
     for p in procs:
         p.start()
-    status, sizes, n = q.get(timeout=300)
-    for p in procs:
-        p.join(timeout=60)
+    try:
+        status, sizes, n = q.get(timeout=240)
+    finally:
+        for p in procs:
+            p.join(timeout=20)
+        for p in procs:  # never leave a rank stuck in a collective behind
+            if p.is_alive():
+                p.kill()
     assert status == "ok", status
     assert sum(sizes) == n and min(sizes) > 0.25 * n

@@ -52,22 +52,25 @@ def _worker(rank, world, port, q):
                   and abs(checksum.item() - float(b.distance.astype(np.float64).sum())) < 1e-6)
             q.put(("ok" if ok else "mismatch", [len(p) for p in parts], b.n))
     except Exception as e:  # pragma: no cover
-        if rank == 0:
-            q.put(("error: %r" % (e,), [], 0))
-        raise
-    finally:
-        dist.destroy_process_group()
+        q.put(("error on rank %d: %r" % (rank, e), [], 0))
+        os._exit(1)
+    dist.destroy_process_group()
 
 
 def test_world_size_2_gloo_sharded_fusion():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29500 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q), daemon=True) for r in range(2)]
     for p in procs:
         p.start()
-    status, sizes, n = q.get(timeout=180)
-    for p in procs:
-        p.join(timeout=60)
+    try:
+        status, sizes, n = q.get(timeout=180)
+    finally:
+        for p in procs:
+            p.join(timeout=20)
+        for p in procs:
+            if p.is_alive():
+                p.kill()
     assert status == "ok", status
     assert sum(sizes) == n and min(sizes) > 0.25 * n

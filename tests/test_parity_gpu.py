@@ -97,10 +97,14 @@ def dynamic_scenario(cam):
     return scene, hs.render_frames(scene, cam, poses, stamps), poses, stamps
 
 
-def test_tracking_everfree_motion(oracle_lib, product_lib):
+@pytest.mark.parametrize("sep", [2.0, 1.0, 0.0])
+def test_tracking_everfree_motion(oracle_lib, product_lib, sep):
+    """Per-frame pipeline detect -> integrate(mask) -> track. sep > 0 runs M2-M4 on the device (connected
+    components; D = ceil(sep) = 2 merges near clusters, 1 only shared voxels), sep = 0 the host path. The
+    product integrates with the device-resident dynamic image (KB_MASK_LAST_DETECTION)."""
     cam = hs.small_camera(4)
     scene, frames, poses, stamps = dynamic_scenario(cam)
-    mot = capi.default_motion_config(min_cluster_size=5, min_separation_distance=2.0)
+    mot = capi.default_motion_config(min_cluster_size=5, min_separation_distance=sep)
     o, g = both(oracle_lib, product_lib, cam=cam, mot_cfg=mot)
     total_dyn = 0
     for i, ((d, l), T, st) in enumerate(zip(frames, poses, stamps)):
@@ -118,7 +122,8 @@ def test_tracking_everfree_motion(oracle_lib, product_lib):
             np.testing.assert_array_equal(pa, pb)
             np.testing.assert_array_equal(a["bbox"], b["bbox"])
         total_dyn += int((io > 0).sum())
-        fo2, fg2 = o.make_frame(d, T, st, label=l, mask=io), g.make_frame(d, T, st, label=l, mask=ig)
+        fo2 = o.make_frame(d, T, st, label=l, mask=io)
+        fg2 = g.make_frame(d, T, st, label=l, mask=capi.MASK_LAST_DETECTION if i % 2 else ig)
         assert o.integrate_frame(fo2).as_dict() == g.integrate_frame(fg2).as_dict()
         o.update_tracking(st)
         g.update_tracking(st)
@@ -353,3 +358,71 @@ def test_lazy_tracking_random_schedules(oracle_lib, product_lib, seed):
     np.testing.assert_array_equal(bo.block_flags, bg.block_flags)
     np.testing.assert_array_equal(o.reset_inactive(), g.reset_inactive())
     assert checks > 2
+
+
+def test_config4_shape_1280x720_2cm(oracle_lib, product_lib):
+    """BASELINE config[3] shapes: 1280x720, fx=fy=640, 2 cm voxels (0.32 m blocks), trunc 0.06 — range limited
+    to 2 m so the CPU oracle and the export stay small."""
+    cam = syn.make_camera(1280, 720, 640.0, 640.0, max_range=2.0)
+    scene = syn.room_scene()
+    poses = [syn.look_pose((3.6, 3.4, 1.2), 3.9 + 0.02 * i, np.radians(12.0)) for i in range(2)]
+    stamps = [1_000_000_000 + i * 33_333_333 for i in range(2)]
+    frames = hs.render_frames(scene, cam, poses, stamps)
+    mc = capi.default_map_config(voxel_size=0.02, vps=16, trunc=0.06, max_blocks=8192)
+    o, g = both(oracle_lib, product_lib, cam=cam, map_cfg=mc)
+    so = hs.run_fusion(o, frames, poses, stamps)
+    fr = [g.make_frame(d, T, st, label=l) for (d, l), T, st in zip(frames, poses, stamps)]
+    sg = g.integrate_frames(fr).as_dict()
+    assert sg["voxels_updated"] == sum(s["voxels_updated"] for s in so) > 100000
+    assert sg["blocks_in_frustum"] == sum(s["blocks_in_frustum"] for s in so)
+    bo, bg = o.export_blocks(likelihoods=False), g.export_blocks(likelihoods=False)
+    hs.assert_blocks_equal(bo, bg, exact_float=True, what="config4")
+
+
+def test_config5_tesse_shapes_pipeline(oracle_lib, product_lib):
+    """BASELINE config[4] shapes: 720x480, fx=fy=415.692, cx=360, cy=240 (khronos_eval/config/ground_truth/
+    tesse_cd_office_dynamic_objects.yaml:18-21), voxel 0.1 / trunc 0.2 / 16^3 (uHumans2.yaml:45-49), motion
+    detector min_cluster 500 px / separation 2 / 26-nbr (uHumans2.yaml:53-56): detect -> integrate -> track per
+    frame, reset_inactive at the output cadence, then the object-extraction path (vps 8, binary) on the same frames."""
+    cam = syn.make_camera(720, 480, 415.692, 415.692, cx=360.0, cy=240.0)
+    scene = syn.room_scene()
+    scene.mover = ((0.7, 0.7, 1.4), (8.4, 1.2, 0.9), (0.0, 2.5, 0.0), 1.6)
+    n, dt = 14, 200_000_000
+    pose = syn.look_pose((6.0, 5.0, 1.5), 0.0, np.radians(10.0))
+    poses, stamps = [pose] * n, [1_000_000_000 + i * dt for i in range(n)]
+    frames = hs.render_frames(scene, cam, poses, stamps)
+    mc = capi.default_map_config(voxel_size=0.1, vps=16, trunc=0.2)
+    mot = capi.default_motion_config(min_cluster_size=500, min_separation_distance=2.0)
+    o, g = both(oracle_lib, product_lib, cam=cam, map_cfg=mc, mot_cfg=mot)
+    flagged = 0
+    for i, ((d, l), T, st) in enumerate(zip(frames, poses, stamps)):
+        io, so_, co = o.detect_motion(o.make_frame(d, T, st, label=l))
+        ig, sg_, cg = g.detect_motion(g.make_frame(d, T, st, label=l))
+        assert (so_, co) == (sg_, cg)
+        np.testing.assert_array_equal(io, ig)
+        flagged += int((io > 0).sum())
+        o.integrate_frame(o.make_frame(d, T, st, label=l, mask=io), want_stats=False)
+        g.integrate_frame(g.make_frame(d, T, st, label=l, mask=capi.MASK_LAST_DETECTION), want_stats=False)
+        o.update_tracking(st)
+        g.update_tracking(st)
+        if i % 2 == 1:  # min_output_separation 0.4 s (uHumans2.yaml:38)
+            np.testing.assert_array_equal(o.reset_inactive(), g.reset_inactive())
+            o.clear_updated(); g.clear_updated()
+    assert flagged > 500
+    hs.assert_blocks_equal(o.export_blocks(), g.export_blocks(), exact_float=True, what="config5 window")
+    # object extraction on the same frames: the second cuboid (label 8) as the tracked object
+    target = 8
+    voxel = 0.05
+    emc = capi.default_map_config(voxel_size=voxel, vps=8, trunc=2 * voxel, with_tracking=False, max_blocks=16384)
+    eic = capi.default_integrator_config(semantic_mode=capi.SEM_BINARY)
+    eo, eg = both(oracle_lib, product_lib, cam=cam, map_cfg=emc, integ_cfg=eic)
+    lo = np.floor(np.array([8.0, 1.0, -0.3]) / (voxel * 8)).astype(int)
+    hi = np.floor(np.array([10.5, 3.0, 1.4]) / (voxel * 8)).astype(int)
+    for h in (eo, eg):
+        h.allocate_box(lo, hi)
+    for (d, l), T, st in zip(frames, poses, stamps):
+        eo.integrate_frame(eo.make_frame(d, T, st, object_image=l, target_id=target), allocate_blocks=False, want_stats=False)
+    eg.integrate_frames([eg.make_frame(d, T, st, object_image=l, target_id=target) for (d, l), T, st in zip(frames, poses, stamps)],
+                        allocate_blocks=False, want_stats=False)
+    assert eo.scan_object_confidence(0.5, 10) == eg.scan_object_confidence(0.5, 10) > 0
+    hs.assert_blocks_equal(eo.export_blocks(), eg.export_blocks(), exact_float=True, what="config5 object")
