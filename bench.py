@@ -51,9 +51,10 @@ def parse_args():
     ap.add_argument("--no-cull", action="store_true", help="disable the conservative depth culling (results identical)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--small", action="store_true", help="tiny configuration for functional checks")
-    ap.add_argument("--workload", default="hall640", choices=["hall640", "dynamic"],
-                    help="hall640 = BASELINE config[1] (fusion only, the headline); dynamic = config[2]: the same "
-                         "per-frame pipeline as ActiveWindow::spinOnce with motion detection + tracking")
+    ap.add_argument("--workload", default="hall640", choices=["hall640", "hall1280", "dynamic"],
+                    help="hall640 = BASELINE config[1] (fusion only, the headline, used for every --gpus N); hall1280 = "
+                         "config[3] shapes (1280x720, 2 cm voxels: ~20x the voxel work per frame) for the sharded "
+                         "scaling study; dynamic = config[2]: per-frame pipeline with motion detection + tracking")
     return ap.parse_args()
 
 
@@ -63,6 +64,10 @@ def workload(args):
         cam = syn.make_camera(160, 120, 80.0, 80.0)
         scene = syn.hall_scene(L_LABELS, size=(20.0, 16.0, 6.0))
         poses, stamps = syn.sweep_trajectory(args.lap_frames, size=(20.0, 16.0), margin=4.0, lanes=3, yaw_turns=6.0)
+    elif args.workload == "hall1280":
+        cam = syn.make_camera(1280, 720, 640.0, 640.0)
+        scene = syn.hall_scene(L_LABELS, size=(30.0, 20.0, 6.0))
+        poses, stamps = syn.sweep_trajectory(args.lap_frames, size=(30.0, 20.0), margin=5.0, lanes=3, yaw_turns=10.0)
     else:
         cam = syn.make_camera()
         scene = syn.hall_scene(L_LABELS)
@@ -115,9 +120,15 @@ class ClockSampler:
 
 def map_configs(args):
     from khronos_b200 import capi
-    mc = capi.default_map_config(voxel_size=0.05, vps=16, trunc=0.15, with_semantics=True, with_tracking=True,
-                                 max_blocks=args.max_blocks if not args.small else 8192,
-                                 max_semantic_blocks=0)
+    vs, tr = (0.02, 0.06) if args.workload == "hall1280" else (0.05, 0.15)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    mb = args.max_blocks if not args.small else 8192
+    msem = 0
+    if args.workload == "hall1280" and not args.small:
+        mb = max(args.max_blocks, 420000) // world + 20000   # block-hash shard: 1/N of the map per GPU
+        msem = mb // 2
+    mc = capi.default_map_config(voxel_size=vs, vps=16, trunc=tr, with_semantics=True, with_tracking=True,
+                                 max_blocks=mb, max_semantic_blocks=msem)
     ic = capi.default_integrator_config(semantic_mode=capi.SEM_MLE, num_labels=L_LABELS)
     return mc, ic
 
@@ -224,19 +235,23 @@ def main_dynamic(args):
     h = kb.create_map(mc, ic, capi.default_tracking_config(), mot, device=0)
     h.set_camera(cam)
     flagged = []
+    img_host = torch.zeros((cam.height, cam.width), dtype=torch.int32, pin_memory=True)  # FrameData::dynamic_image
+    img_ptr = ctypes.c_void_p(img_host.data_ptr())
+    detect = h._fn("detect_motion")
+    hptr = h._h
 
     def run_frame(i):
         f = h.make_frame(depth[i].data_ptr(), poses[i], stamps[i], label=label[i].data_ptr(), memory=capi.MEM_DEVICE)
-        img, ns, nc = h.detect_motion(f)
-        mask = None
-        if nc:
-            mask = torch.from_numpy(img).to(dev, non_blocking=False)
-            f = h.make_frame(depth[i].data_ptr(), poses[i], stamps[i], label=label[i].data_ptr(), mask=mask.data_ptr(),
-                             memory=capi.MEM_DEVICE)
-            f._mask_keep = mask
+        ns, nc = ctypes.c_int32(0), ctypes.c_int32(0)
+        st = detect(hptr, ctypes.byref(f), img_ptr, ctypes.byref(ns), ctypes.byref(nc))  # dynamic image -> pinned host
+        if st != 0:
+            raise RuntimeError(f"kb_detect_motion failed: {st}")
+        if nc.value:  # integrate with the device-resident dynamic image of this detection
+            f = h.make_frame(depth[i].data_ptr(), poses[i], stamps[i], label=label[i].data_ptr(),
+                             mask=capi.MASK_LAST_DETECTION, memory=capi.MEM_DEVICE)
         h.integrate_frame(f, want_stats=False)
         h.update_tracking(stamps[i])
-        return float((img > 0).mean())
+        return nc.value
 
     for i in range(Wm * F):
         run_frame(i)
@@ -246,7 +261,8 @@ def main_dynamic(args):
     sampler.start()
     t0 = time.perf_counter()
     for i in range(Wm * F, n):
-        flagged.append(run_frame(i))
+        nc = run_frame(i)
+        flagged.append(float((img_host > 0).float().mean()) if (nc and i % 10 == 0) else (None if nc else 0.0))
     h.synchronize()
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
@@ -260,8 +276,8 @@ def main_dynamic(args):
                    "voxel_size": 0.05, "voxels_per_side": 16, "semantics": f"MLE L={L_LABELS}", "frames_per_step": F,
                    "pipeline": "kb_detect_motion + kb_integrate_frame(mask) + kb_update_tracking per frame",
                    "live_blocks": tot.total_blocks},
-        "per_frame": {"flagged_pixel_fraction_mean": float(np.mean(flagged)),
-                      "flagged_pixel_fraction_after_burn_in": float(np.mean([x for x in flagged if x > 0] or [0]))},
+        "per_frame": {"frames_with_clusters": int(sum(1 for x in flagged if x is None or x > 0)),
+                      "flagged_pixel_fraction_when_dynamic": float(np.mean([x for x in flagged if x] or [0]))},
         "roofline": None, "cpu_baseline": None, "e2e": None, "gpu_launches": 8 * K * F, "clocks": clocks,
     }
     print(json.dumps(out))
@@ -444,25 +460,36 @@ def main():
     e2e = None
     if not args.no_e2e and world == 1:
         n_e = min(args.e2e_frames, lap)
-        hd = torch.empty((n_e, cam.height, cam.width), dtype=torch.float32, pin_memory=True)
-        hl = torch.empty((n_e, cam.height, cam.width), dtype=torch.int32, pin_memory=True)
-        base_step = Wm + K
-        idx = [frame_index(base_step, j) for j in range(n_e)]
-        hd.copy_(depth[idx[0]:idx[0] + n_e] if idx[-1] == idx[0] + n_e - 1 else depth[torch.tensor(idx, device=dev)])
-        hl.copy_(label[idx[0]:idx[0] + n_e] if idx[-1] == idx[0] + n_e - 1 else label[torch.tensor(idx, device=dev)])
-        torch.cuda.synchronize()
-        frames = [h.make_frame(hd[j].data_ptr(), poses[idx[j]], stamp_of(base_step, j), label=hl[j].data_ptr(),
+
+        def host_window(step):
+            """Pinned host copies of the n_e frames that follow `step`, plus the kb_integrate_frames calls."""
+            idx = [frame_index(step, j) for j in range(n_e)]
+            it = torch.tensor(idx, device=dev)
+            hd = torch.empty((n_e, cam.height, cam.width), dtype=torch.float32, pin_memory=True)
+            hl = torch.empty((n_e, cam.height, cam.width), dtype=torch.int32, pin_memory=True)
+            hd.copy_(depth.index_select(0, it))
+            hl.copy_(label.index_select(0, it))
+            torch.cuda.synchronize()
+            fr = [h.make_frame(hd[j].data_ptr(), poses[idx[j]], stamp_of(step, j), label=hl[j].data_ptr(),
                                memory=capi.MEM_HOST_ASYNC) for j in range(n_e)]
-        calls = [((capi.Frame * len(frames[j0:j0 + B]))(*frames[j0:j0 + B]), len(frames[j0:j0 + B])) for j0 in range(0, n_e, B)]
-        stats = capi.FrameStats()
+            calls = [((capi.Frame * len(fr[j0:j0 + B]))(*fr[j0:j0 + B]), len(fr[j0:j0 + B])) for j0 in range(0, n_e, B)]
+            return calls, (hd, hl)
+
+        def run_window(calls):
+            stats = capi.FrameStats()
+            for j, (arr, n) in enumerate(calls):
+                last = j == len(calls) - 1
+                st = integrate_n(hptr, arr, n, 1, ctypes.byref(stats) if last else None)  # D2H of the result
+                if st != 0:
+                    raise RuntimeError(f"kb_integrate_frames (host) failed: {st}")
+            h.synchronize()
+
+        warm, keep0 = host_window(Wm + K)        # untimed: the library allocates its staging buffers here
+        timed, keep1 = host_window(Wm + K + 1)
+        run_window(warm)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        for j, (arr, n) in enumerate(calls):
-            last = j == len(calls) - 1
-            st = integrate_n(hptr, arr, n, 1, ctypes.byref(stats) if last else None)  # D2H of the result
-            if st != 0:
-                raise RuntimeError(f"kb_integrate_frames (host) failed: {st}")
-        h.synchronize()
+        run_window(timed)
         dt = time.perf_counter() - t0
         e2e = {"value": n_e / dt, "unit": "frames/s", "h2d_bytes_per_step": n_e * P * BYTES_PER_PIXEL_IN,
                "d2h_bytes_per_step": ctypes.sizeof(capi.FrameStats) + 64, "frames_per_step": n_e,
@@ -485,9 +512,9 @@ def main():
             "metric": "rgbd_frames_per_sec_integrated", "value": fps, "unit": "frames/s", "n_gpus": world,
             "steps": K, "warmup": Wm, "ms_per_step": gpu_ms / K, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "hall640" if not args.small else "hall160-small",
-                       "image": [cam.width, cam.height], "voxel_size": 0.05, "voxels_per_side": 16,
-                       "truncation": 0.15, "semantics": f"MLE L={L_LABELS}", "frames_per_step": F, "frames_per_call": B,
+            "config": {"workload": args.workload if not args.small else "hall160-small",
+                       "image": [cam.width, cam.height], "voxel_size": mc.voxel_size, "voxels_per_side": 16,
+                       "truncation": mc.truncation_distance, "semantics": f"MLE L={L_LABELS}", "frames_per_step": F, "frames_per_call": B,
                        "lap_frames": lap, "live_blocks_rank0": total.total_blocks,
                        "l2": "inputs larger than L2: each step streams %.1f GB of frames" % (F * P * 8 / 1e9),
                        "parallelism": "block-hash shard x%d, NCCL frame broadcast" % world if world > 1 else "single GPU",
