@@ -210,7 +210,7 @@ def main_reference(args):
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(out))
+    emit(out)
 
 
 def main_dynamic(args):
@@ -280,11 +280,32 @@ def main_dynamic(args):
                       "flagged_pixel_fraction_when_dynamic": float(np.mean([x for x in flagged if x] or [0]))},
         "roofline": None, "cpu_baseline": None, "e2e": None, "gpu_launches": 8 * K * F, "clocks": clocks,
     }
-    print(json.dumps(out))
+    emit(out)
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Libraries (NCCL, torch) print banners on fd 1; the contract is ONE JSON line on stdout. Everything is routed
+    to stderr until emit() restores the real stdout for the result line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(obj), flush=True)
 
 
 def main():
     args = parse_args()
+    quiet_stdout()
     if args.impl == "reference":
         return main_reference(args)
     if args.workload == "dynamic":
@@ -321,8 +342,9 @@ def main():
     torch.cuda.synchronize()
     t_render = time.perf_counter() - t_render
     if world > 1:
-        rx = [(torch.empty((F, cam.height, cam.width), dtype=torch.float32, device=dev),
-               torch.empty((F, cam.height, cam.width), dtype=torch.int32, device=dev)) for _ in range(2)]
+        # one packed receive buffer per step: [F, 2, H, W] int32 = (depth bits, label) -> a single broadcast
+        rxp = [torch.empty((F, 2, cam.height, cam.width), dtype=torch.int32, device=dev) for _ in range(2)]
+        rx = [(b[:, 0].view(torch.float32), b[:, 1]) for b in rxp]
 
     mc, ic = map_configs(args)
     h = kb.create_map(mc, ic, capi.default_tracking_config(), None, device=local_rank)
@@ -378,10 +400,9 @@ def main():
             cur.wait_event(buf_free[bsel])
             if rank == 0:
                 idx = torch.tensor([frame_index(step, j) for j in range(F)], device=dev)
-                torch.index_select(depth, 0, idx, out=db)
-                torch.index_select(label, 0, idx, out=lb)
-            dist.broadcast(db, 0)
-            dist.broadcast(lb, 0)
+                db.copy_(depth.index_select(0, idx))
+                lb.copy_(label.index_select(0, idx))
+            dist.broadcast(rxp[bsel], 0)
             stream.wait_stream(cur)
         with torch.cuda.stream(stream):
             for j, (arr, n) in enumerate(prebuilt[step]):
@@ -455,6 +476,13 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = bytes_per_launch / (kern_us * 1e-6) / 1e9 if kern_us else None
+    traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_fuse_traffic.json")))
+        if B == tj["frames_per_launch"] and args.workload == "hall640" and not args.small:
+            traffic = tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"]
+    except Exception:
+        pass
 
     # ---- e2e: host (pinned) images through the same C ABI, H2D inside the timed region (rank-local)
     e2e = None
@@ -523,7 +551,7 @@ def main():
                           "blocks_visited": nblk_all / n_frames,
                           "block_frame_pairs_after_k0_culling_rank0": pairs / n_frames},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                          "kernel": "fuseKernel<16> (+ its tileMax/selectBlocks prologue; one launch triple per %d frames)" % B,
                          "launch_us": kern_us,
                          "algorithmic_bytes_per_launch": bytes_per_launch,
@@ -531,7 +559,7 @@ def main():
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 3 * n_launch, "clocks": clocks,
             "wall_s_timed": wall,
         }
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 

@@ -463,11 +463,13 @@ int kb_set_camera(kb_handle* h, const kb_camera* cam) {
   p.blocked_mask = h->blocked_mask;
   p.with_tracking = h->map.with_tracking;
   p.occ_thr = h->trk_cfg_thr;
-  p.tiles8_x = (c.width + 7) / 8;
-  p.tiles8_y = (c.height + 7) / 8;
-  p.tiles16_x = (p.tiles8_x + 1) / 2;
-  p.tiles16_y = (p.tiles8_y + 1) / 2;
-  h->tile_stride = static_cast<size_t>(p.tiles8_x) * p.tiles8_y + static_cast<size_t>(p.tiles16_x) * p.tiles16_y;
+  h->tile_stride = 0;
+  for (int l = 0; l < kTileLevels; ++l) {
+    p.lvl_tx[l] = l == 0 ? (c.width + 7) / 8 : (p.lvl_tx[l - 1] + 1) / 2;
+    p.lvl_ty[l] = l == 0 ? (c.height + 7) / 8 : (p.lvl_ty[l - 1] + 1) / 2;
+    p.lvl_off[l] = static_cast<int>(h->tile_stride);
+    h->tile_stride += static_cast<size_t>(p.lvl_tx[l]) * p.lvl_ty[l];
+  }
   p.work_slots = h->work_slots;
   p.work_masks = h->work_masks;
   p.work_upd = h->work_upd;
@@ -553,8 +555,7 @@ static int integrateBatch(kb_handle* h, const kb_frame* frames, int n, int alloc
     }
     if (f.mask == KB_MASK_LAST_DETECTION)  // dynamic image of the last kb_detect_motion, still on the device
       v.mask = h->motion_have_image ? h->d_dynamic : nullptr;
-    v.tile8 = h->tile_max + static_cast<size_t>(b) * h->tile_stride;
-    v.tile16 = v.tile8 + static_cast<size_t>(p.tiles8_x) * p.tiles8_y;
+    v.tiles = h->tile_max + static_cast<size_t>(b) * h->tile_stride;
     if (allocate_blocks) {
       const float reach = c.max_range + p.infl;
       const float inv = 1.f / h->block_size;

@@ -144,7 +144,8 @@ __device__ __forceinline__ int warpSum(int v) {
 }
 
 // ---- per-frame tile maxima of the depth image (input of the conservative culling) ---------------------
-// Two levels: 8x8-pixel tiles (box culling in K0b) and 16x16-pixel tiles (block culling in K0).
+// A max-pyramid with 8/16/32/64-pixel tiles: a culling query reads the level at which its footprint spans
+// only a handful of tiles. Levels 0 and 1 come from this kernel, the coarser ones from tilePyramidKernel.
 // One warp reduces a 16-row x 32-column strip: coalesced row reads, vertical max in registers,
 // horizontal max over 8-/16-lane groups by shuffles -> eight 8x8 and two 16x16 maxima per warp.
 __global__ void __launch_bounds__(256) tileMaxKernel(const __grid_constant__ BatchParams p) {
@@ -152,7 +153,7 @@ __global__ void __launch_bounds__(256) tileMaxKernel(const __grid_constant__ Bat
   const int warps_x = (p.W + 31) / 32;
   const int warp = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (warp >= warps_x * p.tiles16_y) return;
+  if (warp >= warps_x * p.lvl_ty[1]) return;
   const int ty16 = warp / warps_x, wx = warp % warps_x;
   const int u = wx * 32 + lane;
   const float* __restrict__ depth = p.f[b].depth;
@@ -168,12 +169,33 @@ __global__ void __launch_bounds__(256) tileMaxKernel(const __grid_constant__ Bat
     d[h] = fmaxf(d[h], __shfl_xor_sync(0xffffffffu, d[h], 2));
     d[h] = fmaxf(d[h], __shfl_xor_sync(0xffffffffu, d[h], 4));
     const int tx = wx * 4 + (lane >> 3), ty = ty16 * 2 + h;
-    if ((lane & 7) == 0 && tx < p.tiles8_x && ty < p.tiles8_y) p.f[b].tile8[ty * p.tiles8_x + tx] = d[h];
+    if ((lane & 7) == 0 && tx < p.lvl_tx[0] && ty < p.lvl_ty[0]) p.f[b].tiles[p.lvl_off[0] + ty * p.lvl_tx[0] + tx] = d[h];
   }
   float m16 = fmaxf(d[0], d[1]);
   m16 = fmaxf(m16, __shfl_xor_sync(0xffffffffu, m16, 8));
   const int tx16 = wx * 2 + (lane >> 4);
-  if ((lane & 15) == 0 && tx16 < p.tiles16_x) p.f[b].tile16[ty16 * p.tiles16_x + tx16] = m16;
+  if ((lane & 15) == 0 && tx16 < p.lvl_tx[1]) p.f[b].tiles[p.lvl_off[1] + ty16 * p.lvl_tx[1] + tx16] = m16;
+}
+
+// Coarser pyramid levels (32 and 64 pixel tiles) from the 16-pixel level: one CTA per frame.
+__global__ void __launch_bounds__(256) tilePyramidKernel(const __grid_constant__ BatchParams p) {
+  float* __restrict__ t = p.f[blockIdx.x].tiles;
+  for (int l = 2; l < kTileLevels; ++l) {
+    const int n = p.lvl_tx[l] * p.lvl_ty[l];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const int tx = i % p.lvl_tx[l], ty = i / p.lvl_tx[l];
+      float d = 0.f;
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const int x = tx * 2 + k, y = ty * 2 + j;
+          if (x < p.lvl_tx[l - 1] && y < p.lvl_ty[l - 1]) d = fmaxf(d, t[p.lvl_off[l - 1] + y * p.lvl_tx[l - 1] + x]);
+        }
+      t[p.lvl_off[l] + i] = d;
+    }
+    __syncthreads();
+  }
 }
 
 // Conservative culling rule for an axis-aligned box of voxel centres [lo, hi] (world frame) against frame
@@ -194,8 +216,7 @@ __device__ __forceinline__ void itemOrigin(int it, int& x0, int& y0, int& z0) {
 }
 
 // One lane tests one box: 8 corner projections, then the tile-maximum rectangle they span.
-__device__ __forceinline__ bool boxCulledLane(const BatchParams& p, const FrameView& f, const float* __restrict__ tiles,
-                                              int tiles_x, int tile_shift, float lox, float loy, float loz,
+__device__ __forceinline__ bool boxCulledLane(const BatchParams& p, const FrameView& f, float lox, float loy, float loz,
                                               float hix, float hiy, float hiz) {
   float zmin = 3.0e38f, umin = 3.0e38f, umax = -3.0e38f, vmin = 3.0e38f, vmax = -3.0e38f;
 #pragma unroll 1
@@ -212,8 +233,13 @@ __device__ __forceinline__ bool boxCulledLane(const BatchParams& p, const FrameV
     return true;
   const int u0 = max(static_cast<int>(floorf(umin)) - 2, 0), u1 = min(static_cast<int>(floorf(umax)) + 3, p.W - 1);
   const int v0 = max(static_cast<int>(floorf(vmin)) - 2, 0), v1 = min(static_cast<int>(floorf(vmax)) + 3, p.H - 1);
-  const int tx0 = u0 >> tile_shift, tx1 = u1 >> tile_shift, ty0 = v0 >> tile_shift, ty1 = v1 >> tile_shift;
-  if ((tx1 - tx0 + 1) * (ty1 - ty0 + 1) > 400) return false;  // huge footprint: keep
+  // pyramid level: the footprint spans at most ~5 x 5 tiles (coarser tiles only loosen the bound)
+  int l = 0;
+  while (l < kTileLevels - 1 && max(u1 - u0, v1 - v0) > (32 << l)) ++l;
+  const int sh = 3 + l;
+  const int tx0 = u0 >> sh, tx1 = u1 >> sh, ty0 = v0 >> sh, ty1 = v1 >> sh;
+  const float* __restrict__ tiles = f.tiles + p.lvl_off[l];
+  const int tiles_x = p.lvl_tx[l];
   float dmax = 0.f;
   for (int ty = ty0; ty <= ty1; ++ty) {
     const float* __restrict__ row = tiles + ty * tiles_x;
@@ -278,7 +304,7 @@ __global__ void __launch_bounds__(128) selectBlocksKernel(const DeviceMap m, con
     const float lo = 0.5f * p.voxel_size, hi = p.block_size - 0.5f * p.voxel_size;
     bool keep = false;
     if ((mask >> lane) & 1u)
-      keep = !boxCulledLane(p, p.f[lane], p.f[lane].tile16, p.tiles16_x, 4, ox + lo, oy + lo, oz + lo, ox + hi, oy + hi, oz + hi);
+      keep = !boxCulledLane(p, p.f[lane], ox + lo, oy + lo, oz + lo, ox + hi, oy + hi, oz + hi);
     mask = __ballot_sync(0xffffffffu, keep);
     if (!mask) return;
   }
@@ -332,7 +358,7 @@ __global__ void __launch_bounds__(128) itemCullKernel(const DeviceMap m, const _
     while (rem) {
       const int b = __ffs(rem) - 1;
       rem &= rem - 1;
-      if (!boxCulledLane(p, p.f[b], p.f[b].tile8, p.tiles8_x, 3, lx, ly, lz, hx, hy, hz)) keep |= 1u << b;
+      if (!boxCulledLane(p, p.f[b], lx, ly, lz, hx, hy, hz)) keep |= 1u << b;
     }
     if (keep) atomicOr(&p.item_fmask[static_cast<size_t>(wi) * ITEMS + lane], keep);
   }
@@ -816,8 +842,9 @@ __global__ void gatherSemanticKernel(const DeviceMap m, const int* slots, int L,
 }  // namespace
 
 void launchTileMax(const BatchParams& p, cudaStream_t s) {
-  const int warps = ((p.W + 31) / 32) * p.tiles16_y;
+  const int warps = ((p.W + 31) / 32) * p.lvl_ty[1];
   tileMaxKernel<<<dim3((warps + 7) / 8, p.n_frames), 256, 0, s>>>(p);
+  tilePyramidKernel<<<p.n_frames, 256, 0, s>>>(p);
 }
 void launchSelectBlocks(const DeviceMap& m, const BatchParams& p, int cull_grid, cudaStream_t s) {
   const int n = p.allocate ? p.dims[0] * p.dims[1] * p.dims[2] : p.n_slots;

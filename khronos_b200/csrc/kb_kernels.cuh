@@ -5,6 +5,7 @@
 
 namespace kb {
 
+constexpr int kTileLevels = 4;  // depth max-pyramid: 8, 16, 32, 64 pixel tiles
 constexpr int kMaxBatch = 32;  // frames fused per launch pair (bits of the per-block frame mask)
 
 // Per-frame part of a batch (pose, image pointers, frame index).
@@ -14,8 +15,7 @@ struct FrameView {
   const int* label;
   const int* mask;
   const int* object_image;
-  float* tile8;   // per-frame 8x8-pixel tile maxima of depth (K1 work-item culling)
-  float* tile16;  // per-frame 16x16-pixel tile maxima (K0 block culling)
+  float* tiles;   // per-frame depth max-pyramid (levels concatenated, see BatchParams::lvl_*)
   uint32_t frame_idx;
   int target_id;
 };
@@ -45,7 +45,7 @@ struct BatchParams {
   int n_frames;
   int parity;          // which of the two work-list counters this batch uses
   int cull;            // 1: conservative depth culling enabled
-  int tiles8_x, tiles8_y, tiles16_x, tiles16_y;
+  int lvl_tx[kTileLevels], lvl_ty[kTileLevels], lvl_off[kTileLevels];  // pyramid level dims / offsets
   int* work_slots;     // [max_work] selected block slots
   uint32_t* work_masks;  // [max_work] bit b set: block is processed for frame b of the batch
   uint32_t* work_upd;    // [max_work] bit b set: some voxel of the block was updated by frame b
