@@ -50,6 +50,9 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cull", action="store_true", help="disable the conservative depth culling (results identical)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--wire", default="f32", choices=["f32", "compact"],
+                    help="f32 = depth f32 + label i32 (hydra::InputData, 8 B/pixel; the headline); compact = u16 millimetre "
+                         "depth + u8 labels (3 B/pixel, expanded on the device): what crosses PCIe / NVLink")
     ap.add_argument("--small", action="store_true", help="tiny configuration for functional checks")
     ap.add_argument("--workload", default="hall640", choices=["hall640", "hall1280", "dynamic"],
                     help="hall640 = BASELINE config[1] (fusion only, the headline, used for every --gpus N); hall1280 = "
@@ -75,11 +78,11 @@ def workload(args):
     return cam, scene, poses, stamps
 
 
-def algorithmic_bytes(nv, nsem, nblk, pixels, lp=20):
+def algorithmic_bytes(nv, nsem, nblk, pixels, lp=20, bpp=BYTES_PER_PIXEL_IN):
     """Byte model: per integrated voxel 8 B read + 8 B write of {distance, weight} and a
     4 B last_observed write; per semantic update Lp*4 B read + write of the likelihood row and a 2 B
     label read + write; the frame's depth + label images once; 16 B of hash/index per visited block."""
-    return nv * (8 + 8 + 4) + nsem * (2 * 4 * lp + 4) + pixels * BYTES_PER_PIXEL_IN + nblk * 16
+    return nv * (8 + 8 + 4) + nsem * (2 * 4 * lp + 4) + pixels * bpp + nblk * 16
 
 
 class ClockSampler:
@@ -339,9 +342,19 @@ def main():
         depth, label = syn.render_stream(scene, cam, poses, stamps, device=dev, dtype=torch.float32)
     else:
         depth = label = None
+    compact = args.wire == "compact"
+    bpp = 3 if compact else BYTES_PER_PIXEL_IN
+    if compact and rank == 0:
+        # sensor-native formats: 16-bit millimetres (values < 32768, so int16 storage is bit-identical to u16), u8 ids
+        depth = (depth * 1000.0).round().to(torch.int16)
+        label = label.to(torch.uint8)
     torch.cuda.synchronize()
     t_render = time.perf_counter() - t_render
-    if world > 1:
+    if world > 1 and compact:
+        HW = cam.height * cam.width
+        rxp = [torch.empty((F, 3 * HW), dtype=torch.uint8, device=dev) for _ in range(2)]
+        rx = [(b[:, :2 * HW].view(torch.int16).view(F, cam.height, cam.width), b[:, 2 * HW:].view(F, cam.height, cam.width)) for b in rxp]
+    elif world > 1:
         # one packed receive buffer per step: [F, 2, H, W] int32 = (depth bits, label) -> a single broadcast
         rxp = [torch.empty((F, 2, cam.height, cam.width), dtype=torch.int32, device=dev) for _ in range(2)]
         rx = [(b[:, 0].view(torch.float32), b[:, 1]) for b in rxp]
@@ -376,8 +389,12 @@ def main():
             for j in range(j0, min(j0 + B, F)):
                 i = frame_index(step, j)
                 k = i if base is None else base + j
-                fr.append(h.make_frame(dbuf[k].data_ptr(), poses[i], stamp_of(step, j), label=lbuf[k].data_ptr(),
-                                       memory=capi.MEM_DEVICE))
+                if compact:
+                    fr.append(h.make_frame(None, poses[i], stamp_of(step, j), depth_u16=dbuf[k].data_ptr(),
+                                           label_u8=lbuf[k].data_ptr(), memory=capi.MEM_DEVICE))
+                else:
+                    fr.append(h.make_frame(dbuf[k].data_ptr(), poses[i], stamp_of(step, j), label=lbuf[k].data_ptr(),
+                                           memory=capi.MEM_DEVICE))
             arr = (capi.Frame * len(fr))(*fr)
             out.append((arr, len(fr)))
         return out
@@ -468,7 +485,7 @@ def main():
     full = [(a.elapsed_time(b), n) for a, b, n in samples if n == B]
     kern_us = float(np.mean([t for t, _ in full]) * 1e3) if full else None  # one K0+K1 launch pair (B frames)
     n_launch = sum(len(prebuilt[s]) for s in range(Wm, Wm + K))
-    bytes_per_launch = algorithmic_bytes(nv, nsem, nblk, n_frames * P) / n_frames * B  # this rank, per batch
+    bytes_per_launch = algorithmic_bytes(nv, nsem, nblk, n_frames * P, bpp=bpp) / n_frames * B  # this rank, per batch
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -493,13 +510,17 @@ def main():
             """Pinned host copies of the n_e frames that follow `step`, plus the kb_integrate_frames calls."""
             idx = [frame_index(step, j) for j in range(n_e)]
             it = torch.tensor(idx, device=dev)
-            hd = torch.empty((n_e, cam.height, cam.width), dtype=torch.float32, pin_memory=True)
-            hl = torch.empty((n_e, cam.height, cam.width), dtype=torch.int32, pin_memory=True)
+            hd = torch.empty((n_e, cam.height, cam.width), dtype=depth.dtype, pin_memory=True)
+            hl = torch.empty((n_e, cam.height, cam.width), dtype=label.dtype, pin_memory=True)
             hd.copy_(depth.index_select(0, it))
             hl.copy_(label.index_select(0, it))
             torch.cuda.synchronize()
-            fr = [h.make_frame(hd[j].data_ptr(), poses[idx[j]], stamp_of(step, j), label=hl[j].data_ptr(),
-                               memory=capi.MEM_HOST_ASYNC) for j in range(n_e)]
+            if compact:
+                fr = [h.make_frame(None, poses[idx[j]], stamp_of(step, j), depth_u16=hd[j].data_ptr(), label_u8=hl[j].data_ptr(),
+                                   memory=capi.MEM_HOST_ASYNC) for j in range(n_e)]
+            else:
+                fr = [h.make_frame(hd[j].data_ptr(), poses[idx[j]], stamp_of(step, j), label=hl[j].data_ptr(),
+                                   memory=capi.MEM_HOST_ASYNC) for j in range(n_e)]
             calls = [((capi.Frame * len(fr[j0:j0 + B]))(*fr[j0:j0 + B]), len(fr[j0:j0 + B])) for j0 in range(0, n_e, B)]
             return calls, (hd, hl)
 
@@ -519,7 +540,7 @@ def main():
         t0 = time.perf_counter()
         run_window(timed)
         dt = time.perf_counter() - t0
-        e2e = {"value": n_e / dt, "unit": "frames/s", "h2d_bytes_per_step": n_e * P * BYTES_PER_PIXEL_IN,
+        e2e = {"value": n_e / dt, "unit": "frames/s", "h2d_bytes_per_step": n_e * P * bpp,
                "d2h_bytes_per_step": ctypes.sizeof(capi.FrameStats) + 64, "frames_per_step": n_e,
                "note": "host pinned depth+label ring -> kb_integrate_frames(KB_MEM_HOST_ASYNC, %d frames/call); stats read back at step end" % B}
 
@@ -527,7 +548,10 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         n_c = min(args.cpu_sample_frames, lap)
-        fh = (depth[:n_c].cpu().numpy(), label[:n_c].cpu().numpy())
+        if compact:  # the CPU arm gets the same frames, expanded the same way (float(u16) * 0.001f, int32(u8))
+            fh = ((depth[:n_c].cpu().numpy().astype(np.float32) * np.float32(0.001)), label[:n_c].cpu().numpy().astype(np.int32))
+        else:
+            fh = (depth[:n_c].cpu().numpy(), label[:n_c].cpu().numpy())
         nt = best_cpu_threads(args, cam, fh, poses, list(range(n_c)))
         cfps, cores, secs = run_cpu(args, cam, fh, poses, stamps, n_c, threads=nt)
         cpu = {"value": cfps, "unit": "frames/s", "cores": cores, "kind": "port",
@@ -543,8 +567,9 @@ def main():
             "config": {"workload": args.workload if not args.small else "hall160-small",
                        "image": [cam.width, cam.height], "voxel_size": mc.voxel_size, "voxels_per_side": 16,
                        "truncation": mc.truncation_distance, "semantics": f"MLE L={L_LABELS}", "frames_per_step": F, "frames_per_call": B,
+                       "wire_format": "depth f32 + label i32 (8 B/px)" if not compact else "depth u16 mm + label u8 (3 B/px), expanded on device",
                        "lap_frames": lap, "live_blocks_rank0": total.total_blocks,
-                       "l2": "inputs larger than L2: each step streams %.1f GB of frames" % (F * P * 8 / 1e9),
+                       "l2": "inputs larger than L2: each step streams %.1f GB of frames" % (F * P * bpp / 1e9),
                        "parallelism": "block-hash shard x%d, NCCL frame broadcast" % world if world > 1 else "single GPU",
                        "render_s": round(t_render, 1)},
             "per_frame": {"voxels_updated": nv_all / n_frames, "voxels_semantic": nsem_all / n_frames,

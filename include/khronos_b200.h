@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define KB_ABI_VERSION 1
+#define KB_ABI_VERSION 2
 
 typedef enum kb_status {
   KB_OK = 0,
@@ -129,6 +129,14 @@ typedef struct kb_frame {
   uint64_t stamp_ns;           /* must be > 0 (0 is the reference's "never observed" sentinel) */
   int32_t object_target_id;    /* BINARY mode: ObjectIntegrator::setFrameData target id */
   int32_t memory;              /* KB_MEM_HOST | KB_MEM_DEVICE | KB_MEM_HOST_ASYNC for the image pointers */
+  /* Compact sensor formats (optional; `depth` / `label` must then be NULL). They are the raw inputs of hydra's
+   * input conversion (parseInputPacket, call site active_window.cpp:275: 16UC1 depth in millimetres -> 32FC1
+   * metres, 8-bit class ids -> 32SC1) and are expanded on the device: depth = float(depth_u16) * depth_u16_scale
+   * (0 stays invalid), label = int32(label_u8). 3 instead of 8 bytes per pixel cross PCIe / NVLink. */
+  const uint16_t* depth_u16;
+  const uint8_t* label_u8;
+  float depth_u16_scale;       /* metres per count, e.g. 0.001f */
+  int32_t reserved_;
 } kb_frame;
 
 typedef struct kb_frame_stats {

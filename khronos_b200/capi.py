@@ -64,7 +64,9 @@ class Frame(C.Structure):
     _fields_ = [("depth", C.c_void_p), ("label", C.c_void_p), ("mask", C.c_void_p),
                 ("object_image", C.c_void_p), ("color", C.c_void_p), ("vertex_world", C.c_void_p),
                 ("world_T_sensor", C.c_double * 16), ("stamp_ns", C.c_uint64),
-                ("object_target_id", C.c_int32), ("memory", C.c_int32)]
+                ("object_target_id", C.c_int32), ("memory", C.c_int32),
+                ("depth_u16", C.c_void_p), ("label_u8", C.c_void_p), ("depth_u16_scale", C.c_float),
+                ("reserved_", C.c_int32)]
 
 
 class FrameStats(C.Structure):
@@ -226,9 +228,11 @@ class MapHandle:
     # ---- hot path
     @staticmethod
     def make_frame(depth, pose, stamp_ns, label=None, mask=None, object_image=None, color=None,
-                   vertex_world=None, target_id=0, memory=MEM_HOST) -> Frame:
+                   vertex_world=None, target_id=0, memory=MEM_HOST, depth_u16=None, label_u8=None,
+                   depth_u16_scale=0.001) -> Frame:
         f = Frame()
         f.depth, f.label, f.mask = _ptr(depth), _ptr(label), _ptr(mask)
+        f.depth_u16, f.label_u8, f.depth_u16_scale = _ptr(depth_u16), _ptr(label_u8), depth_u16_scale
         f.object_image, f.color, f.vertex_world = _ptr(object_image), _ptr(color), _ptr(vertex_world)
         T = np.asarray(pose, dtype=np.float64).reshape(16)
         for i in range(16):
@@ -236,7 +240,7 @@ class MapHandle:
         f.stamp_ns = int(stamp_ns)
         f.object_target_id = int(target_id)
         f.memory = memory
-        f._keep = (depth, label, mask, object_image, color, vertex_world)  # keep buffers alive
+        f._keep = (depth, label, mask, object_image, color, vertex_world, depth_u16, label_u8)  # keep buffers alive
         return f
 
     def integrate_frame(self, frame: Frame, allocate_blocks=True, want_stats=True):

@@ -39,6 +39,9 @@ struct kb_handle {
   int* stg_label = nullptr;
   int* stg_mask = nullptr;
   int* stg_object = nullptr;
+  uint16_t* stg_depth16 = nullptr;  // compact inputs (2 sets x kMaxBatch frames)
+  uint8_t* stg_label8 = nullptr;
+  uint16_t* mot_depth16 = nullptr;
   float* stg_vertex = nullptr;
   float* mot_depth = nullptr;
   size_t stg_pixels = 0, mot_pixels = 0;
@@ -121,6 +124,9 @@ int ensureStaging(kb_handle* h, size_t pixels) {
   KB_CUDA(h, devAlloc(&h->stg_label, n, 0));
   KB_CUDA(h, devAlloc(&h->stg_mask, n, 0));
   KB_CUDA(h, devAlloc(&h->stg_object, n, 0));
+  cudaFree(h->stg_depth16); cudaFree(h->stg_label8);
+  KB_CUDA(h, devAlloc(&h->stg_depth16, n, 0));
+  KB_CUDA(h, devAlloc(&h->stg_label8, n, 0));
   h->stg_pixels = pixels;
   return KB_OK;
 }
@@ -132,6 +138,8 @@ int ensureMotionBuffers(kb_handle* h, size_t pixels) {
   cudaFree(h->d_dynamic);
   cudaFree(t.keys); cudaFree(t.count); cudaFree(t.flags); cudaFree(t.deg); cudaFree(t.parent); cudaFree(t.pix_total);
   cudaFree(t.min_seed); cudaFree(t.cluster_id); cudaFree(t.roots); cudaFree(t.scalars); cudaFree(t.pix_slot);
+  cudaFree(h->mot_depth16);
+  KB_CUDA(h, devAlloc(&h->mot_depth16, pixels, 0));
   KB_CUDA(h, devAlloc(&h->mot_depth, pixels, 0));
   KB_CUDA(h, devAlloc(&h->stg_vertex, pixels * 3, 0));
   KB_CUDA(h, devAlloc(&h->d_pixel_gidx, pixels, 0));
@@ -393,6 +401,7 @@ int kb_destroy(kb_handle* h) {
   { MotionTable& t = h->mt; cudaFree(t.keys); cudaFree(t.count); cudaFree(t.flags); cudaFree(t.deg); cudaFree(t.parent);
     cudaFree(t.pix_total); cudaFree(t.min_seed); cudaFree(t.cluster_id); cudaFree(t.roots); cudaFree(t.scalars); cudaFree(t.pix_slot); }
   if (h->h_mscal) cudaFreeHost(h->h_mscal);
+  cudaFree(h->stg_depth16); cudaFree(h->stg_label8); cudaFree(h->mot_depth16);
   cudaFree(h->mot_depth); cudaFree(h->tile_max); cudaFree(h->work_slots); cudaFree(h->work_masks); cudaFree(h->work_upd); cudaFree(h->item_fmask);
   for (int i = 0; i < 2; ++i) {
     if (h->stg_ready[i]) cudaEventDestroy(h->stg_ready[i]);
@@ -521,10 +530,14 @@ static int integrateBatch(kb_handle* h, const kb_frame* frames, int n, int alloc
   p.trk = h->pass;
 
   // ---- stage host images (double-buffered, on the copy stream so they overlap the previous batch)
-  bool any_host = false;
-  for (int b = 0; b < n; ++b) any_host |= frames[b].memory != KB_MEM_DEVICE;
+  bool any_host = false, any_compact = false;
+  for (int b = 0; b < n; ++b) {
+    any_host |= frames[b].memory != KB_MEM_DEVICE;
+    any_compact |= frames[b].depth_u16 != nullptr || frames[b].label_u8 != nullptr;
+  }
   const int set = h->stg_set;
-  if (any_host) {
+  const bool use_staging = any_host || any_compact;
+  if (use_staging) {
     int st = ensureStaging(h, px);
     if (st != KB_OK) return st;
     h->stg_set ^= 1;
@@ -544,15 +557,22 @@ static int integrateBatch(kb_handle* h, const kb_frame* frames, int n, int alloc
     if (st != KB_OK) return st;
     v.frame_idx = fidx;
     v.target_id = f.object_target_id;
+    const size_t off = (static_cast<size_t>(set) * kMaxBatch + b) * px;
     if (f.memory == KB_MEM_DEVICE) {
       v.depth = f.depth; v.label = f.label; v.mask = f.mask; v.object_image = f.object_image;
+      v.depth16 = f.depth_u16; v.label8 = f.label_u8;
     } else {
-      const size_t off = (static_cast<size_t>(set) * kMaxBatch + b) * px;
-      v.depth = h->stg_depth + off;
+      v.depth = f.depth ? h->stg_depth + off : nullptr;
       v.label = f.label ? h->stg_label + off : nullptr;
       v.mask = f.mask ? h->stg_mask + off : nullptr;
       v.object_image = f.object_image ? h->stg_object + off : nullptr;
+      v.depth16 = f.depth_u16 ? h->stg_depth16 + off : nullptr;
+      v.label8 = f.label_u8 ? h->stg_label8 + off : nullptr;
     }
+    v.depth_scale = f.depth_u16_scale;
+    if (v.depth16) v.depth = h->stg_depth + off;   // expandFramesKernel fills these staging slots
+    if (v.label8) v.label = h->stg_label + off;
+    if (!v.depth) return fail(h, KB_ERR_INVALID, "frame without depth image");
     if (f.mask == KB_MASK_LAST_DETECTION)  // dynamic image of the last kb_detect_motion, still on the device
       v.mask = h->motion_have_image ? h->d_dynamic : nullptr;
     v.tiles = h->tile_max + static_cast<size_t>(b) * h->tile_stride;
@@ -587,6 +607,8 @@ static int integrateBatch(kb_handle* h, const kb_frame* frames, int n, int alloc
     if ((cst = copyKind(&kb_frame::label, h->stg_label)) != KB_OK) return cst;
     if ((cst = copyKind(&kb_frame::mask, h->stg_mask)) != KB_OK) return cst;
     if ((cst = copyKind(&kb_frame::object_image, h->stg_object)) != KB_OK) return cst;
+    if ((cst = copyKind(&kb_frame::depth_u16, h->stg_depth16)) != KB_OK) return cst;
+    if ((cst = copyKind(&kb_frame::label_u8, h->stg_label8)) != KB_OK) return cst;
     KB_CUDA(h, cudaEventRecord(h->stg_ready[set], h->copy_stream));
     KB_CUDA(h, cudaStreamWaitEvent(h->stream, h->stg_ready[set], 0));
   }
@@ -602,12 +624,13 @@ static int integrateBatch(kb_handle* h, const kb_frame* frames, int n, int alloc
     }
     p.n_slots = h->hwm_cached;
   }
+  if (any_compact) launchExpandFrames(p, h->stream);
   if (p.cull) launchTileMax(p, h->stream);
   launchSelectBlocks(h->dm, p, h->cull_grid, h->stream);
   launchFuse(h->dm, p, h->fuse_grid, h->stream);
   KB_CUDA(h, cudaGetLastError());
+  if (use_staging) KB_CUDA(h, cudaEventRecord(h->stg_consumed[set], h->stream));
   if (any_host) {
-    KB_CUDA(h, cudaEventRecord(h->stg_consumed[set], h->stream));
     // KB_MEM_HOST buffers are borrowed only for the duration of the call: wait for the copies (the
     // kernels keep running asynchronously and overlap the next call's copies). KB_MEM_HOST_ASYNC
     // callers keep their (pinned) buffers valid until kb_synchronize, so the copy engine never idles.
@@ -624,7 +647,7 @@ int kb_integrate_frames(kb_handle* h, const kb_frame* frames, int32_t n_frames, 
   if (!h || !frames || n_frames < 0) return fail(h, KB_ERR_INVALID, "null frames");
   if (!h->has_cam) return fail(h, KB_ERR_STATE, "kb_set_camera must be called first");
   for (int i = 0; i < n_frames; ++i)
-    if (!frames[i].depth) return fail(h, KB_ERR_INVALID, "frame without depth image");
+    if (!frames[i].depth && !frames[i].depth_u16) return fail(h, KB_ERR_INVALID, "frame without depth image");
   KB_CUDA(h, cudaSetDevice(h->device));
   int st;
   if (stats && h->ctr_dirty) {
@@ -799,7 +822,7 @@ int kb_scan_object_confidence(kb_handle* h, float min_confidence, int32_t min_ob
 }
 
 int kb_detect_motion(kb_handle* h, const kb_frame* f, int32_t* dynamic_image_out, int32_t* n_seeds, int32_t* n_clusters) {
-  if (!h || !f || !f->depth || !dynamic_image_out) return fail(h, KB_ERR_INVALID, "null argument");
+  if (!h || !f || (!f->depth && !f->depth_u16) || !dynamic_image_out) return fail(h, KB_ERR_INVALID, "null argument");
   if (!h->has_mot || !h->map.with_tracking) return fail(h, KB_ERR_STATE, "motion detector not configured");
   if (!h->has_cam) return fail(h, KB_ERR_STATE, "kb_set_camera must be called first");
   KB_CUDA(h, cudaSetDevice(h->device));
@@ -815,7 +838,14 @@ int kb_detect_motion(kb_handle* h, const kb_frame* f, int32_t* dynamic_image_out
   p.block_size_inv = 1.f / h->block_size;
   p.voxel_size_inv = 1.f / h->map.voxel_size;
   int st;
-  if ((st = stage(h, f->depth, h->mot_depth, px, f->memory, &p.depth)) != KB_OK) return st;
+  if (f->depth_u16) {  // compact depth: expand on the device
+    const uint16_t* d16 = nullptr;
+    if ((st = stage(h, f->depth_u16, h->mot_depth16, px, f->memory, &d16)) != KB_OK) return st;
+    launchExpandDepth(d16, f->depth_u16_scale, h->mot_depth, static_cast<int>(px), h->stream);
+    p.depth = h->mot_depth;
+  } else if ((st = stage(h, f->depth, h->mot_depth, px, f->memory, &p.depth)) != KB_OK) {
+    return st;
+  }
   if ((st = stage(h, f->vertex_world, h->stg_vertex, px * 3, f->memory, &p.vertex)) != KB_OK) return st;
   p.pixel_gidx = h->d_pixel_gidx;
   p.pixel_seed = h->d_pixel_seed;

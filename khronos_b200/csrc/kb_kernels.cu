@@ -143,6 +143,24 @@ __device__ __forceinline__ int warpSum(int v) {
   return v;
 }
 
+// ---- input conversion: compact sensor formats -> the f32 / i32 images the fusion reads ------------------------
+// hydra's parseInputPacket (call site khronos/src/active_window/active_window.cpp:275) converts 16UC1 depth in
+// millimetres to 32FC1 metres and class ids to 32SC1 on the host; here the 3 B/pixel cross PCIe / NVLink and
+// are expanded on the device: depth = float(u16) * scale (one fp32 multiply), label = int32(u8).
+__global__ void __launch_bounds__(256) expandFramesKernel(const __grid_constant__ BatchParams p) {
+  const FrameView& f = p.f[blockIdx.y];
+  const int n = p.W * p.H;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (f.depth16) const_cast<float*>(f.depth)[i] = static_cast<float>(__ldg(&f.depth16[i])) * f.depth_scale;
+    if (f.label8) const_cast<int*>(f.label)[i] = static_cast<int>(__ldg(&f.label8[i]));
+  }
+}
+
+__global__ void expandDepthKernel(const uint16_t* __restrict__ src, float scale, float* __restrict__ dst, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = static_cast<float>(src[i]) * scale;
+}
+
 // ---- per-frame tile maxima of the depth image (input of the conservative culling) ---------------------
 // A max-pyramid with 8/16/32/64-pixel tiles: a culling query reads the level at which its footprint spans
 // only a handful of tiles. Levels 0 and 1 come from this kernel, the coarser ones from tilePyramidKernel.
@@ -233,9 +251,9 @@ __device__ __forceinline__ bool boxCulledLane(const BatchParams& p, const FrameV
     return true;
   const int u0 = max(static_cast<int>(floorf(umin)) - 2, 0), u1 = min(static_cast<int>(floorf(umax)) + 3, p.W - 1);
   const int v0 = max(static_cast<int>(floorf(vmin)) - 2, 0), v1 = min(static_cast<int>(floorf(vmax)) + 3, p.H - 1);
-  // pyramid level: the footprint spans at most ~5 x 5 tiles (coarser tiles only loosen the bound)
+  // pyramid level: the footprint spans at most ~9 x 9 tiles (coarser tiles only loosen the bound)
   int l = 0;
-  while (l < kTileLevels - 1 && max(u1 - u0, v1 - v0) > (32 << l)) ++l;
+  while (l < kTileLevels - 1 && max(u1 - u0, v1 - v0) > (64 << l)) ++l;
   const int sh = 3 + l;
   const int tx0 = u0 >> sh, tx1 = u1 >> sh, ty0 = v0 >> sh, ty1 = v1 >> sh;
   const float* __restrict__ tiles = f.tiles + p.lvl_off[l];
@@ -387,7 +405,7 @@ __device__ __noinline__ uint32_t trackingFold(const DeviceMap m, const TrackEval
 // ProjectiveIntegrator::updateBlock / getVoxelMeasurement / computeLabel / updateVoxel (UP App. A.6;
 // computeLabel structure pinned by khronos/src/active_window/integration/object_integrator.cpp:58-81);
 // SemanticIntegrator::updateLikelihoods (UP App. A.8).
-template <int VPS>
+template <int VPS, int LPI>
 __global__ void __launch_bounds__(kFuseThreads) fuseKernel(const DeviceMap m, const __grid_constant__ BatchParams p) {
   constexpr int V = VPS * VPS * VPS;
   constexpr int NK = 4;                                      // z-layers per culling box
@@ -396,7 +414,7 @@ __global__ void __launch_bounds__(kFuseThreads) fuseKernel(const DeviceMap m, co
   const int lane = threadIdx.x & 31;
   // Short batches have little work per voxel, so an item then covers all NK layers of its box (amortising the
   // fetch); long batches use one layer per item for balance.
-  const int lpi = p.layers_per_item, ipb = NK / lpi;  // layers per item, items per box
+  constexpr int lpi = LPI, ipb = NK / LPI;  // layers per item, items per box
   const int n_items = min(m.counters[kCtrWork0 + p.parity], p.max_work) * BOXES * ipb;
   const bool binary = p.sem_mode == KB_SEMANTICS_BINARY;
   const int L = p.L;
@@ -841,6 +859,12 @@ __global__ void gatherSemanticKernel(const DeviceMap m, const int* slots, int L,
 
 }  // namespace
 
+void launchExpandFrames(const BatchParams& p, cudaStream_t s) {
+  expandFramesKernel<<<dim3(148, p.n_frames), 256, 0, s>>>(p);
+}
+void launchExpandDepth(const uint16_t* src, float scale, float* dst, int n, cudaStream_t s) {
+  expandDepthKernel<<<(n + 255) / 256, 256, 0, s>>>(src, scale, dst, n);
+}
 void launchTileMax(const BatchParams& p, cudaStream_t s) {
   const int warps = ((p.W + 31) / 32) * p.lvl_ty[1];
   tileMaxKernel<<<dim3((warps + 7) / 8, p.n_frames), 256, 0, s>>>(p);
@@ -857,15 +881,21 @@ void launchSelectBlocks(const DeviceMap& m, const BatchParams& p, int cull_grid,
 static size_t fuseSmemBytes(int Lp) { return static_cast<size_t>(std::max(Lp, 2)) * kFuseThreads * sizeof(float); }
 int fuseBlocksPerSm(int vps, int Lp) {
   int n = 0;
-  if (vps == 16) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fuseKernel<16>, kFuseThreads, fuseSmemBytes(Lp));
-  else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fuseKernel<8>, kFuseThreads, fuseSmemBytes(Lp));
+  if (vps == 16) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fuseKernel<16, 1>, kFuseThreads, fuseSmemBytes(Lp));
+  else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fuseKernel<8, 1>, kFuseThreads, fuseSmemBytes(Lp));
   return n > 0 ? n : 4;
 }
 void launchFuse(const DeviceMap& m, const BatchParams& p, int grid, cudaStream_t s) {
   if (grid <= 0) return;
   const size_t smem = fuseSmemBytes(m.Lp);
-  if (m.vps == 16) fuseKernel<16><<<grid, kFuseThreads, smem, s>>>(m, p);
-  else fuseKernel<8><<<grid, kFuseThreads, smem, s>>>(m, p);
+  const bool one = p.layers_per_item == 1;
+  if (m.vps == 16) {
+    if (one) fuseKernel<16, 1><<<grid, kFuseThreads, smem, s>>>(m, p);
+    else fuseKernel<16, 4><<<grid, kFuseThreads, smem, s>>>(m, p);
+  } else {
+    if (one) fuseKernel<8, 1><<<grid, kFuseThreads, smem, s>>>(m, p);
+    else fuseKernel<8, 4><<<grid, kFuseThreads, smem, s>>>(m, p);
+  }
 }
 void launchTrackingPass(const DeviceMap& m, const TrackingParams& p, int everfree_grid, cudaStream_t s) {
   trackingPassKernel<<<(std::max(p.n_slots, 1) + 255) / 256, 256, 0, s>>>(m, p);

@@ -16,6 +16,9 @@ struct FrameView {
   const int* mask;
   const int* object_image;
   float* tiles;   // per-frame depth max-pyramid (levels concatenated, see BatchParams::lvl_*)
+  const uint16_t* depth16;  // compact inputs (device pointers) expanded into depth / label by expandFramesKernel
+  const uint8_t* label8;
+  float depth_scale;
   uint32_t frame_idx;
   int target_id;
 };
@@ -77,6 +80,8 @@ struct MotionParams {
 };
 
 void launchTileMax(const BatchParams& p, cudaStream_t s);
+void launchExpandFrames(const BatchParams& p, cudaStream_t s);  // compact u16 depth / u8 labels -> f32 / i32
+void launchExpandDepth(const uint16_t* src, float scale, float* dst, int n, cudaStream_t s);
 void launchSelectBlocks(const DeviceMap& m, const BatchParams& p, int cull_grid, cudaStream_t s);
 void launchFuse(const DeviceMap& m, const BatchParams& p, int grid, cudaStream_t s);
 int fuseBlocksPerSm(int vps, int Lp);  // resident 128-thread CTAs per SM (occupancy API)

@@ -2,6 +2,7 @@
 // one-to-one with a ko_ prefix so the same Python harness can drive either side.
 #include <algorithm>
 #include <cstring>
+#include <vector>
 
 #include "oracle.hpp"
 
@@ -11,6 +12,9 @@ struct ko_handle {
   Oracle* o;
   std::string last_error;
   kb_frame_stats totals{};
+  size_t pixels = 0;
+  std::vector<float> depth_f;
+  std::vector<int32_t> label_i;
 };
 
 static int fail(ko_handle* h, int code) {
@@ -24,7 +28,8 @@ int ko_create(const kb_map_config* map, const kb_integrator_config* integ,
               const kb_tracking_config* trk, const kb_motion_config* mot, int /*device*/,
               ko_handle** out) {
   if (!map || !integ || !out) return KB_ERR_INVALID;
-  auto* h = new ko_handle{new Oracle(*map, *integ, trk, mot), "", {}};
+  auto* h = new ko_handle();
+  h->o = new Oracle(*map, *integ, trk, mot);
   if (!h->o->ok()) {
     delete h->o;
     delete h;
@@ -49,11 +54,33 @@ int ko_synchronize(ko_handle*) { return KB_OK; }
 int ko_set_camera(ko_handle* h, const kb_camera* cam) {
   if (!h || !cam) return KB_ERR_INVALID;
   h->o->setCamera(*cam);
+  h->pixels = static_cast<size_t>(cam->width) * cam->height;
   return KB_OK;
 }
 
-int ko_integrate_frame(ko_handle* h, const kb_frame* f, int allocate_blocks, kb_frame_stats* stats) {
-  if (!h || !f || !f->depth) return KB_ERR_INVALID;
+// Compact sensor formats (kb_frame.depth_u16 / label_u8) are expanded exactly like the device does:
+// depth = float(u16) * scale, label = int32(u8).
+static const kb_frame* expandCompact(ko_handle* h, const kb_frame* f, kb_frame* tmp) {
+  if (!f->depth_u16 && !f->label_u8) return f;
+  const size_t px = h->pixels;
+  *tmp = *f;
+  if (f->depth_u16) {
+    h->depth_f.resize(px);
+    for (size_t i = 0; i < px; ++i) h->depth_f[i] = static_cast<float>(f->depth_u16[i]) * f->depth_u16_scale;
+    tmp->depth = h->depth_f.data();
+  }
+  if (f->label_u8) {
+    h->label_i.resize(px);
+    for (size_t i = 0; i < px; ++i) h->label_i[i] = static_cast<int32_t>(f->label_u8[i]);
+    tmp->label = h->label_i.data();
+  }
+  return tmp;
+}
+
+int ko_integrate_frame(ko_handle* h, const kb_frame* f_in, int allocate_blocks, kb_frame_stats* stats) {
+  if (!h || !f_in || (!f_in->depth && !f_in->depth_u16)) return KB_ERR_INVALID;
+  kb_frame tmp;
+  const kb_frame* f = expandCompact(h, f_in, &tmp);
   kb_frame_stats local{};
   h->o->integrateFrame(*f, allocate_blocks != 0, &local);
   h->totals.blocks_in_frustum += local.blocks_in_frustum;
@@ -116,9 +143,11 @@ int ko_reset_inactive(ko_handle* h, int32_t* removed_xyz, int32_t max_removed, i
 int ko_mark_all_inactive(ko_handle* h) { h->o->markAllInactive(); return KB_OK; }
 int ko_clear_updated(ko_handle* h) { h->o->clearUpdated(); return KB_OK; }
 
-int ko_detect_motion(ko_handle* h, const kb_frame* f, int32_t* dynamic_image_out, int32_t* n_seeds,
+int ko_detect_motion(ko_handle* h, const kb_frame* f_in, int32_t* dynamic_image_out, int32_t* n_seeds,
                      int32_t* n_clusters) {
-  if (!h || !f || !dynamic_image_out) return KB_ERR_INVALID;
+  if (!h || !f_in || !dynamic_image_out) return KB_ERR_INVALID;
+  kb_frame tmp;
+  const kb_frame* f = expandCompact(h, f_in, &tmp);
   h->o->detectMotion(*f, dynamic_image_out, n_seeds, n_clusters);
   return h->o->ok() ? KB_OK : fail(h, KB_ERR_INVALID);
 }

@@ -426,3 +426,35 @@ def test_config5_tesse_shapes_pipeline(oracle_lib, product_lib):
                         allocate_blocks=False, want_stats=False)
     assert eo.scan_object_confidence(0.5, 10) == eg.scan_object_confidence(0.5, 10) > 0
     hs.assert_blocks_equal(eo.export_blocks(), eg.export_blocks(), exact_float=True, what="config5 object")
+
+
+def test_compact_wire_format_u16_depth_u8_label(oracle_lib, product_lib):
+    """kb_frame.depth_u16 / label_u8: the device expands 16-bit millimetre depth and 8-bit labels exactly like the
+    host-side conversion (float(u16) * scale, int32(u8)); host, pinned-async and device-resident inputs agree with
+    the oracle fed the same compact frames and with the oracle fed the pre-expanded f32 / i32 images."""
+    import torch
+    cam = hs.small_camera(4)
+    frames, poses, stamps = room_frames(cam, 12, laps=0.2)
+    d16 = [np.round(d * 1000.0).astype(np.uint16) for d, _ in frames]
+    l8 = [l.astype(np.uint8) for _, l in frames]
+    scale = np.float32(0.001)
+    o, g = both(oracle_lib, product_lib, cam=cam)
+    o2 = hs.make_handle(oracle_lib, "ko_", cam=cam)
+    for i in range(len(frames)):
+        o.integrate_frame(o.make_frame(None, poses[i], stamps[i], depth_u16=d16[i], label_u8=l8[i]), want_stats=False)
+        o2.integrate_frame(o2.make_frame((d16[i].astype(np.float32) * scale), poses[i], stamps[i], label=l8[i].astype(np.int32)), want_stats=False)
+    hs.assert_blocks_equal(o2.export_blocks(), o.export_blocks(), exact_float=True, what="oracle compact vs expanded")
+    # product: 4 host frames, 4 device-resident frames, 4 pinned-async frames in one batch call
+    for i in range(4):
+        g.integrate_frame(g.make_frame(None, poses[i], stamps[i], depth_u16=d16[i], label_u8=l8[i]), want_stats=False)
+    dd = [torch.from_numpy(x).cuda() for x in d16[4:8]]
+    ll = [torch.from_numpy(x).cuda() for x in l8[4:8]]
+    torch.cuda.synchronize()
+    g.integrate_frames([g.make_frame(None, poses[4 + j], stamps[4 + j], depth_u16=dd[j], label_u8=ll[j], memory=capi.MEM_DEVICE)
+                        for j in range(4)], want_stats=False)
+    pd = torch.from_numpy(np.stack(d16[8:])).pin_memory()
+    pl = torch.from_numpy(np.stack(l8[8:])).pin_memory()
+    g.integrate_frames([g.make_frame(None, poses[8 + j], stamps[8 + j], depth_u16=pd[j].data_ptr(), label_u8=pl[j].data_ptr(),
+                                     memory=capi.MEM_HOST_ASYNC) for j in range(4)], want_stats=False)
+    g.synchronize()
+    hs.assert_blocks_equal(o.export_blocks(), g.export_blocks(), exact_float=True, what="compact wire format")
