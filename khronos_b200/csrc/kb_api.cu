@@ -624,7 +624,11 @@ static int integrateBatch(kb_handle* h, const kb_frame* frames, int n, int alloc
     }
     p.n_slots = h->hwm_cached;
   }
-  if (any_compact) launchExpandFrames(p, h->stream);
+  // All-compact batches are read in place (conversion per tap); mixed batches expand the compact frames first.
+  bool all_compact = any_compact;
+  for (int b = 0; b < n; ++b) all_compact = all_compact && frames[b].depth_u16 != nullptr && frames[b].label == nullptr;
+  p.compact_taps = all_compact ? 1 : 0;
+  if (any_compact && !all_compact) launchExpandFrames(p, h->stream);
   if (p.cull) launchTileMax(p, h->stream);
   launchSelectBlocks(h->dm, p, h->cull_grid, h->stream);
   launchFuse(h->dm, p, h->fuse_grid, h->stream);

@@ -46,30 +46,46 @@ __device__ __forceinline__ bool inFrustum(const BatchParams& p, float x, float y
   return true;
 }
 
+// Image reads. COMPACT: the frame's depth is 16-bit millimetres and its labels 8-bit ids; the conversion hydra's
+// parseInputPacket does on the host (float(u16) * scale, int32(u8)) happens per tap, so compact batches need no
+// expansion pass and their taps touch 2 B / 1 B instead of 4 B.
+template <bool COMPACT>
+__device__ __forceinline__ float depthAt(const FrameView& f, int i) {
+  if (COMPACT) return static_cast<float>(__ldg(&f.depth16[i])) * f.depth_scale;
+  return __ldg(&f.depth[i]);
+}
+template <bool COMPACT>
+__device__ __forceinline__ int labelAt(const FrameView& f, int i) {
+  if (COMPACT) return static_cast<int>(__ldg(&f.label8[i]));
+  return __ldg(&f.label[i]);
+}
+
 struct Taps {
   bool valid, bilinear;
   int u, v;
   float w0, w1, w2, w3;
 };
 
-__device__ __forceinline__ Taps nearestTaps(const BatchParams& p, const float* __restrict__ depth, float u, float v) {
+template <bool COMPACT>
+__device__ __forceinline__ Taps nearestTaps(const BatchParams& p, const FrameView& f, float u, float v) {
   Taps t;
   t.bilinear = false;
   t.u = static_cast<int>(roundf(u));
   t.v = static_cast<int>(roundf(v));
   t.w0 = t.w1 = t.w2 = t.w3 = 0.f;
-  t.valid = t.u >= 0 && t.u < p.W && t.v >= 0 && t.v < p.H && __ldg(&depth[t.v * p.W + t.u]) > 0.f;
+  t.valid = t.u >= 0 && t.u < p.W && t.v >= 0 && t.v < p.H && depthAt<COMPACT>(f, t.v * p.W + t.u) > 0.f;
   return t;
 }
 
 // ProjectionInterpolator{Nearest,Bilinear,Adaptive}::computeWeights (UP).
 // Returns the interpolated range through `range` when valid.
-__device__ __forceinline__ Taps computeTaps(const BatchParams& p, const float* __restrict__ depth, float u, float v, float& range) {
+template <bool COMPACT>
+__device__ __forceinline__ Taps computeTaps(const BatchParams& p, const FrameView& f, float u, float v, float& range) {
   Taps t;
   t.valid = false;
   if (p.interp == KB_INTERP_NEAREST) {
-    t = nearestTaps(p, depth, u, v);
-    if (t.valid) range = __ldg(&depth[t.v * p.W + t.u]);
+    t = nearestTaps<COMPACT>(p, f, u, v);
+    if (t.valid) range = depthAt<COMPACT>(f, t.v * p.W + t.u);
     return t;
   }
   const int u0 = static_cast<int>(floorf(u)), v0 = static_cast<int>(floorf(v));
@@ -77,11 +93,11 @@ __device__ __forceinline__ Taps computeTaps(const BatchParams& p, const float* _
   bool use_nearest = !inside;
   float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
   if (inside) {
-    const float* row0 = depth + v0 * p.W + u0;
-    r0 = __ldg(row0);
-    r2 = __ldg(row0 + 1);
-    r1 = __ldg(row0 + p.W);
-    r3 = __ldg(row0 + p.W + 1);
+    const int i0 = v0 * p.W + u0;
+    r0 = depthAt<COMPACT>(f, i0);
+    r2 = depthAt<COMPACT>(f, i0 + 1);
+    r1 = depthAt<COMPACT>(f, i0 + p.W);
+    r3 = depthAt<COMPACT>(f, i0 + p.W + 1);
     const bool all_valid = r0 > 0.f && r1 > 0.f && r2 > 0.f && r3 > 0.f;
     if (p.interp == KB_INTERP_ADAPTIVE) {
       const float mx = fmaxf(fmaxf(r0, r1), fmaxf(r2, r3));
@@ -94,8 +110,8 @@ __device__ __forceinline__ Taps computeTaps(const BatchParams& p, const float* _
     return t;
   }
   if (use_nearest) {
-    t = nearestTaps(p, depth, u, v);
-    if (t.valid) range = __ldg(&depth[t.v * p.W + t.u]);
+    t = nearestTaps<COMPACT>(p, f, u, v);
+    if (t.valid) range = depthAt<COMPACT>(f, t.v * p.W + t.u);
     return t;
   }
   const float du = u - static_cast<float>(u0), dv = v - static_cast<float>(v0);
@@ -113,7 +129,7 @@ __device__ __forceinline__ Taps computeTaps(const BatchParams& p, const float* _
 
 // interpolateID: value at the tap with the largest weight, ties -> lowest tap index
 // (taps ordered (u,v), (u,v+1), (u+1,v), (u+1,v+1)).
-__device__ __forceinline__ int tapID(const BatchParams& p, const int* __restrict__ img, const Taps& t) {
+__device__ __forceinline__ int tapIndex(const BatchParams& p, const Taps& t) {
   int du = 0, dv = 0;
   if (t.bilinear) {
     int best = 0;
@@ -124,7 +140,7 @@ __device__ __forceinline__ int tapID(const BatchParams& p, const int* __restrict
     du = best >> 1;
     dv = best & 1;
   }
-  return __ldg(&img[(t.v + dv) * p.W + t.u + du]);
+  return (t.v + dv) * p.W + t.u + du;
 }
 
 __device__ __forceinline__ float measurementWeight(const BatchParams& p, float depth, float sdf) {
@@ -174,12 +190,13 @@ __global__ void __launch_bounds__(256) tileMaxKernel(const __grid_constant__ Bat
   if (warp >= warps_x * p.lvl_ty[1]) return;
   const int ty16 = warp / warps_x, wx = warp % warps_x;
   const int u = wx * 32 + lane;
-  const float* __restrict__ depth = p.f[b].depth;
+  const FrameView& f = p.f[b];
   float d[2] = {0.f, 0.f};
 #pragma unroll
   for (int r = 0; r < 16; ++r) {
     const int v = ty16 * 16 + r;
-    if (u < p.W && v < p.H) d[r >> 3] = fmaxf(d[r >> 3], __ldg(&depth[v * p.W + u]));
+    if (u < p.W && v < p.H)
+      d[r >> 3] = fmaxf(d[r >> 3], p.compact_taps ? depthAt<true>(f, v * p.W + u) : depthAt<false>(f, v * p.W + u));
   }
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
@@ -292,6 +309,8 @@ __global__ void __launch_bounds__(128) selectBlocksKernel(const DeviceMap m, con
     const float cx = (static_cast<float>(bx) + 0.5f) * p.block_size;
     const float cy = (static_cast<float>(by) + 0.5f) * p.block_size;
     const float cz = (static_cast<float>(bz) + 0.5f) * p.block_size;
+    // shard filter first: at N ranks (N-1)/N of the candidate warps retire here
+    if (p.nranks > 1 && blockOwner(bx, by, bz, p.nranks) != p.rank) return;
     bool in = false;
     if (lane < p.n_frames) {
       float x, y, z;
@@ -300,7 +319,6 @@ __global__ void __launch_bounds__(128) selectBlocksKernel(const DeviceMap m, con
     }
     mask = __ballot_sync(0xffffffffu, in);
     if (!mask) return;
-    if (p.nranks > 1 && blockOwner(bx, by, bz, p.nranks) != p.rank) return;
     if (lane == 0) slot = hashFindOrInsert(m, bx, by, bz, p.f[__ffs(mask) - 1].frame_idx, &created);
     slot = __shfl_sync(0xffffffffu, slot, 0);
     if (slot < 0) return;
@@ -405,8 +423,8 @@ __device__ __noinline__ uint32_t trackingFold(const DeviceMap m, const TrackEval
 // ProjectiveIntegrator::updateBlock / getVoxelMeasurement / computeLabel / updateVoxel (UP App. A.6;
 // computeLabel structure pinned by khronos/src/active_window/integration/object_integrator.cpp:58-81);
 // SemanticIntegrator::updateLikelihoods (UP App. A.8).
-template <int VPS, int LPI>
-__global__ void __launch_bounds__(kFuseThreads) fuseKernel(const DeviceMap m, const __grid_constant__ BatchParams p) {
+template <int VPS, int LPI, bool COMPACT>
+__global__ void __launch_bounds__(kFuseThreads, 10) fuseKernel(const DeviceMap m, const __grid_constant__ BatchParams p) {
   constexpr int V = VPS * VPS * VPS;
   constexpr int NK = 4;                                      // z-layers per culling box
   constexpr int BOXES = (VPS / 4) * (VPS / 8) * (VPS / NK);  // 32 (16^3) or 4 (8^3) boxes of 128 voxels
@@ -457,7 +475,7 @@ __global__ void __launch_bounds__(kFuseThreads) fuseKernel(const DeviceMap m, co
       const int b = __ffs(rem) - 1;
       rem &= rem - 1;
       const FrameView& f = p.f[b];
-      const bool has_label_img = L > 0 && (binary ? f.object_image != nullptr : f.label != nullptr);
+      const bool has_label_img = L > 0 && (binary ? f.object_image != nullptr : (COMPACT ? f.label8 != nullptr : f.label != nullptr));
       float x, y, z;
       xform(f.R, f.t, wx, wy, wz, x, y, z);
       if (z <= 0.f) continue;
@@ -465,19 +483,20 @@ __global__ void __launch_bounds__(kFuseThreads) fuseKernel(const DeviceMap m, co
       const float v = p.fy * y / z + p.cy;
       if (u < 0.f || u > static_cast<float>(p.W - 1) || v < 0.f || v > static_cast<float>(p.H - 1)) continue;
       float range = 0.f;
-      const Taps taps = computeTaps(p, f.depth, u, v, range);
+      const Taps taps = computeTaps<COMPACT>(p, f, u, v, range);
       if (!taps.valid) continue;
       const float sdf = range - z;
       if (sdf < -p.trunc) continue;
       const bool in_band = fabsf(sdf) < p.trunc;
       uint32_t label = 0;
       if (in_band) {
-        if (f.mask != nullptr && tapID(p, f.mask, taps) != 0) continue;
+        const int ti = tapIndex(p, taps);  // interpolateID: the pixel of the dominant tap
+        if (f.mask != nullptr && __ldg(&f.mask[ti]) != 0) continue;
         if (has_label_img) {
           if (binary) {
-            label = tapID(p, f.object_image, taps) == f.target_id ? 1u : 0u;
+            label = __ldg(&f.object_image[ti]) == f.target_id ? 1u : 0u;
           } else {
-            label = static_cast<uint32_t>(tapID(p, f.label, taps));
+            label = static_cast<uint32_t>(labelAt<COMPACT>(f, ti));
             if (label < static_cast<uint32_t>(KB_MAX_LABELS) && ((p.blocked_mask >> label) & 1ull)) continue;
           }
         }
@@ -881,21 +900,23 @@ void launchSelectBlocks(const DeviceMap& m, const BatchParams& p, int cull_grid,
 static size_t fuseSmemBytes(int Lp) { return static_cast<size_t>(std::max(Lp, 2)) * kFuseThreads * sizeof(float); }
 int fuseBlocksPerSm(int vps, int Lp) {
   int n = 0;
-  if (vps == 16) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fuseKernel<16, 1>, kFuseThreads, fuseSmemBytes(Lp));
-  else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fuseKernel<8, 1>, kFuseThreads, fuseSmemBytes(Lp));
+  if (vps == 16) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fuseKernel<16, 1, false>, kFuseThreads, fuseSmemBytes(Lp));
+  else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fuseKernel<8, 1, false>, kFuseThreads, fuseSmemBytes(Lp));
   return n > 0 ? n : 4;
 }
 void launchFuse(const DeviceMap& m, const BatchParams& p, int grid, cudaStream_t s) {
   if (grid <= 0) return;
   const size_t smem = fuseSmemBytes(m.Lp);
-  const bool one = p.layers_per_item == 1;
+  const bool one = p.layers_per_item == 1, c = p.compact_taps != 0;
+#define KB_FUSE(V, LP, C) fuseKernel<V, LP, C><<<grid, kFuseThreads, smem, s>>>(m, p)
   if (m.vps == 16) {
-    if (one) fuseKernel<16, 1><<<grid, kFuseThreads, smem, s>>>(m, p);
-    else fuseKernel<16, 4><<<grid, kFuseThreads, smem, s>>>(m, p);
+    if (one) { if (c) KB_FUSE(16, 1, true); else KB_FUSE(16, 1, false); }
+    else { if (c) KB_FUSE(16, 4, true); else KB_FUSE(16, 4, false); }
   } else {
-    if (one) fuseKernel<8, 1><<<grid, kFuseThreads, smem, s>>>(m, p);
-    else fuseKernel<8, 4><<<grid, kFuseThreads, smem, s>>>(m, p);
+    if (one) { if (c) KB_FUSE(8, 1, true); else KB_FUSE(8, 1, false); }
+    else { if (c) KB_FUSE(8, 4, true); else KB_FUSE(8, 4, false); }
   }
+#undef KB_FUSE
 }
 void launchTrackingPass(const DeviceMap& m, const TrackingParams& p, int everfree_grid, cudaStream_t s) {
   trackingPassKernel<<<(std::max(p.n_slots, 1) + 255) / 256, 256, 0, s>>>(m, p);

@@ -47,6 +47,7 @@ struct BatchParams {
   float occ_thr;       // tsdf distance below which a voxel is occupied
   int n_frames;
   int parity;          // which of the two work-list counters this batch uses
+  int compact_taps;    // 1: every frame of the batch is compact (u16 depth, u8/no labels): kernels convert per tap
   int cull;            // 1: conservative depth culling enabled
   int lvl_tx[kTileLevels], lvl_ty[kTileLevels], lvl_off[kTileLevels];  // pyramid level dims / offsets
   int* work_slots;     // [max_work] selected block slots

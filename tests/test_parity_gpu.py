@@ -458,3 +458,13 @@ def test_compact_wire_format_u16_depth_u8_label(oracle_lib, product_lib):
                                      memory=capi.MEM_HOST_ASYNC) for j in range(4)], want_stats=False)
     g.synchronize()
     hs.assert_blocks_equal(o.export_blocks(), g.export_blocks(), exact_float=True, what="compact wire format")
+    # mixed batch: compact and pre-expanded frames interleaved in one call (compact ones are expanded on the device)
+    g2 = hs.make_handle(product_lib, "kb_", cam=cam)
+    mixed = []
+    for i in range(len(frames)):
+        if i % 2:
+            mixed.append(g2.make_frame(None, poses[i], stamps[i], depth_u16=d16[i], label_u8=l8[i]))
+        else:
+            mixed.append(g2.make_frame(d16[i].astype(np.float32) * scale, poses[i], stamps[i], label=l8[i].astype(np.int32)))
+    g2.integrate_frames(mixed, want_stats=False)
+    hs.assert_blocks_equal(o.export_blocks(), g2.export_blocks(), exact_float=True, what="mixed compact / f32 batch")
