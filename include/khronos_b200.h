@@ -228,6 +228,14 @@ int kb_detect_motion(kb_handle* h, const kb_frame* frame, int32_t* dynamic_image
 int kb_get_motion_clusters(kb_handle* h, int32_t* counts, int32_t* pixels_uv, int64_t* voxels_xyz,
                            float* bbox_min_max, int32_t* total_pixels, int32_t* total_voxels);
 
+/* Host-only entry point (needs no GPU, no handle): the M2-M4 host path on caller-supplied per-pixel voxel keys
+ * (3 ints per pixel, x == INT32_MIN for dropped pixels) and seed flags — what the M1 kernel produces. Used by the
+ * CPU test-suite to check the product's host clustering against the oracle; writes cluster ids into
+ * dynamic_image_out and returns the number of seed voxels / clusters. */
+int kb_host_cluster_motion(const kb_camera* camera, const kb_motion_config* motion, const double world_T_sensor[16],
+                           const int32_t* pixel_voxel_xyz, const uint8_t* pixel_seed, const float* depth,
+                           int32_t* dynamic_image_out, int32_t* n_seeds, int32_t* n_clusters);
+
 /* E0. Replaces the dense allocation loop of MeshObjectExtractor::extractStaticObject
  * (mesh_object_extractor.cpp:220-228): allocates all blocks in [min,max] (inclusive). */
 int kb_allocate_box(kb_handle* h, const int32_t min_block[3], const int32_t max_block[3]);

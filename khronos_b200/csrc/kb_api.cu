@@ -910,6 +910,26 @@ int kb_detect_motion(kb_handle* h, const kb_frame* f, int32_t* dynamic_image_out
   return KB_OK;
 }
 
+int kb_host_cluster_motion(const kb_camera* camera, const kb_motion_config* motion, const double world_T_sensor[16],
+                           const int32_t* pixel_voxel_xyz, const uint8_t* pixel_seed, const float* depth,
+                           int32_t* dynamic_image_out, int32_t* n_seeds, int32_t* n_clusters) {
+  if (!camera || !motion || !world_T_sensor || !pixel_voxel_xyz || !pixel_seed || !depth || !dynamic_image_out) return KB_ERR_INVALID;
+  MotionHostParams mp{};
+  float R[9], t[3];
+  poseToFloat(world_T_sensor, R, t, mp.Rw, mp.tw);
+  mp.W = camera->width; mp.H = camera->height; mp.fx = camera->fx; mp.fy = camera->fy; mp.cx = camera->cx; mp.cy = camera->cy;
+  mp.connectivity = motion->neighbor_connectivity;
+  mp.min_cluster_size = motion->min_cluster_size;
+  mp.max_cluster_size = motion->max_cluster_size;
+  mp.min_separation_distance = motion->min_separation_distance;
+  std::memset(dynamic_image_out, 0, sizeof(int32_t) * static_cast<size_t>(mp.W) * mp.H);
+  MotionResult res;
+  clusterMotion(mp, pixel_voxel_xyz, pixel_seed, depth, nullptr, dynamic_image_out, &res);
+  if (n_seeds) *n_seeds = res.n_seeds;
+  if (n_clusters) *n_clusters = static_cast<int32_t>(res.clusters.size());
+  return KB_OK;
+}
+
 int kb_get_motion_clusters(kb_handle* h, int32_t* counts, int32_t* pixels_uv, int64_t* voxels_xyz,
                            float* bbox_min_max, int32_t* total_pixels, int32_t* total_voxels) {
   if (!h) return KB_ERR_INVALID;
