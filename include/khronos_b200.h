@@ -220,6 +220,14 @@ int kb_clear_updated(kb_handle* h);
  * dynamic_image_out: H*W int32 (host), 0 = static, cluster ids 1..255. n_seeds/n_clusters optional. */
 int kb_detect_motion(kb_handle* h, const kb_frame* frame, int32_t* dynamic_image_out,
                      int32_t* n_seeds, int32_t* n_clusters);
+/* One frame of the active-window loop in a single call: motion detection (active_window.cpp:127), integration
+ * with the resulting dynamic image as mask (:209-210) and the tracking update (:214), enqueued back to back with
+ * ONE device->host round trip at the end (image + counters). Same results as kb_detect_motion +
+ * kb_integrate_frame(mask = dynamic image) + kb_update_tracking(frame->stamp_ns). dynamic_image_out (host; pinned
+ * memory avoids a staging copy) may be NULL when only the counts are needed. */
+int kb_spin_once(kb_handle* h, const kb_frame* frame, int32_t* dynamic_image_out, int32_t* n_seeds,
+                 int32_t* n_clusters);
+
 /* Clusters of the last kb_detect_motion call (MeasurementCluster, measurement_clusters.h:63-81):
  * counts[c*2+0]=#pixels, counts[c*2+1]=#voxels; then flat pixel (u,v) pairs (order within a cluster
  * unspecified, duplicates preserved as in the reference) and voxel (x,y,z) global indices (ascending

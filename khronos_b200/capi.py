@@ -296,6 +296,16 @@ class MapHandle:
         self._last_nc = nc.value
         return img, ns.value, nc.value
 
+    def spin_once(self, frame: Frame, want_image=True):
+        """kb_spin_once: detect -> integrate(mask) -> track with one host round trip."""
+        H, W = self._camera.height, self._camera.width
+        img = np.zeros((H, W), np.int32) if want_image else None
+        ns, nc = C.c_int32(0), C.c_int32(0)
+        self._check(self._fn("spin_once")(self._h, C.byref(frame), C.c_void_p(img.ctypes.data) if want_image else None,
+                                          C.byref(ns), C.byref(nc)))
+        self._last_nc = nc.value
+        return img, ns.value, nc.value
+
     def get_motion_clusters(self):
         tp, tv = C.c_int32(0), C.c_int32(0)
         f = self._fn("get_motion_clusters")

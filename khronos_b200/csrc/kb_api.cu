@@ -160,6 +160,7 @@ int ensureMotionBuffers(kb_handle* h, size_t pixels) {
   KB_CUDA(h, devAlloc(&t.roots, static_cast<size_t>(t.max_roots), 0));
   KB_CUDA(h, devAlloc(&t.scalars, static_cast<size_t>(kMsCount), 0));
   KB_CUDA(h, devAlloc(&t.pix_slot, pixels, 0xFF));
+  t.gate = h->dm.counters + kCtrSeeds;
   if (!h->h_mscal) KB_CUDA(h, cudaMallocHost(reinterpret_cast<void**>(&h->h_mscal), sizeof(int) * kMsCount));
   h->mot_pixels = pixels;
   return KB_OK;
@@ -703,10 +704,7 @@ int kb_get_totals(kb_handle* h, kb_frame_stats* t) {
   return KB_OK;
 }
 
-int kb_update_tracking(kb_handle* h, uint64_t stamp_ns) {
-  if (!h) return KB_ERR_INVALID;
-  if (!h->has_trk || !h->map.with_tracking) return fail(h, KB_ERR_STATE, "tracking not configured");
-  KB_CUDA(h, cudaSetDevice(h->device));
+static int updateTrackingImpl(kb_handle* h, uint64_t stamp_ns) {
   if (stamp_ns <= h->last_pass_stamp) return fail(h, KB_ERR_STATE, "tracking stamps must increase");
   uint32_t fidx = 0;
   int st = frameIndex(h, stamp_ns, &fidx);
@@ -743,6 +741,13 @@ int kb_update_tracking(kb_handle* h, uint64_t stamp_ns) {
   h->pass = p.ev;
   h->last_pass_stamp = stamp_ns;
   return KB_OK;
+}
+
+int kb_update_tracking(kb_handle* h, uint64_t stamp_ns) {
+  if (!h) return KB_ERR_INVALID;
+  if (!h->has_trk || !h->map.with_tracking) return fail(h, KB_ERR_STATE, "tracking not configured");
+  KB_CUDA(h, cudaSetDevice(h->device));
+  return updateTrackingImpl(h, stamp_ns);
 }
 
 int kb_reset_inactive(kb_handle* h, int32_t* removed_xyz, int32_t max_removed, int32_t* n_removed) {
@@ -825,11 +830,9 @@ int kb_scan_object_confidence(kb_handle* h, float min_confidence, int32_t min_ob
   return KB_OK;
 }
 
-int kb_detect_motion(kb_handle* h, const kb_frame* f, int32_t* dynamic_image_out, int32_t* n_seeds, int32_t* n_clusters) {
-  if (!h || !f || (!f->depth && !f->depth_u16) || !dynamic_image_out) return fail(h, KB_ERR_INVALID, "null argument");
-  if (!h->has_mot || !h->map.with_tracking) return fail(h, KB_ERR_STATE, "motion detector not configured");
-  if (!h->has_cam) return fail(h, KB_ERR_STATE, "kb_set_camera must be called first");
-  KB_CUDA(h, cudaSetDevice(h->device));
+// M1 launch shared by kb_detect_motion and kb_spin_once: stages depth / vertex map, resets the seed counter,
+// enqueues the per-pixel lookup and records the host parameters for lazily built cluster lists.
+static int enqueueMotionLookup(kb_handle* h, const kb_frame* f) {
   const kb_camera& c = h->cam;
   const size_t px = static_cast<size_t>(c.width) * c.height;
   MotionParams p{};
@@ -856,36 +859,53 @@ int kb_detect_motion(kb_handle* h, const kb_frame* f, int32_t* dynamic_image_out
   KB_CUDA(h, cudaMemsetAsync(h->dm.counters + kCtrSeeds, 0, sizeof(int), h->stream));
   launchMotionLookup(h->dm, p, h->stream);
   KB_CUDA(h, cudaGetLastError());
-  if ((st = readCounters(h)) != KB_OK) return st;  // one 4 B round trip: are there any seeds at all?
-  const int seed_pixels = h->h_ctr[kCtrSeeds];
-
+  // keep the depth image on the device for lazily built cluster lists (bounding boxes)
+  if (f->memory == KB_MEM_DEVICE && p.depth != h->mot_depth)
+    KB_CUDA(h, cudaMemcpyAsync(h->mot_depth, p.depth, sizeof(float) * px, cudaMemcpyDeviceToDevice, h->stream));
+  MotionHostParams& mp = h->motion_hp;
+  mp.W = c.width; mp.H = c.height; mp.fx = c.fx; mp.fy = c.fy; mp.cx = c.cx; mp.cy = c.cy;
+  std::memcpy(mp.Rw, p.Rw, sizeof(mp.Rw));
+  std::memcpy(mp.tw, p.tw, sizeof(mp.tw));
+  mp.connectivity = h->mot.neighbor_connectivity;
+  mp.min_cluster_size = h->mot.min_cluster_size;
+  mp.max_cluster_size = h->mot.max_cluster_size;
+  mp.min_separation_distance = h->mot.min_separation_distance;
   h->motion.clusters.clear();
   h->motion.n_seeds = 0;
   h->motion_stale = false;
   h->motion_have_image = false;
+  return KB_OK;
+}
+
+// M2-M4 on the device (connected components over the voxels that contain points); every stage is gated by the
+// device-side seed counter, so this can be enqueued without knowing whether M1 found seeds.
+static int enqueueDeviceClustering(kb_handle* h) {
+  const size_t px = static_cast<size_t>(h->cam.width) * h->cam.height;
+  const int D = static_cast<int>(std::ceil(h->mot.min_separation_distance));
+  launchMotionClustering(h->mt, h->d_pixel_gidx, h->d_pixel_seed, static_cast<int>(px), h->mot.neighbor_connectivity, D,
+                         h->mot.min_cluster_size, h->mot.max_cluster_size, h->d_dynamic, h->stream);
+  KB_CUDA(h, cudaGetLastError());
+  KB_CUDA(h, cudaMemcpyAsync(h->h_mscal, h->mt.scalars, sizeof(int) * kMsCount, cudaMemcpyDeviceToHost, h->stream));
+  return KB_OK;
+}
+
+int kb_detect_motion(kb_handle* h, const kb_frame* f, int32_t* dynamic_image_out, int32_t* n_seeds, int32_t* n_clusters) {
+  if (!h || !f || (!f->depth && !f->depth_u16) || !dynamic_image_out) return fail(h, KB_ERR_INVALID, "null argument");
+  if (!h->has_mot || !h->map.with_tracking) return fail(h, KB_ERR_STATE, "motion detector not configured");
+  if (!h->has_cam) return fail(h, KB_ERR_STATE, "kb_set_camera must be called first");
+  KB_CUDA(h, cudaSetDevice(h->device));
+  const size_t px = static_cast<size_t>(h->cam.width) * h->cam.height;
+  int st;
+  if ((st = enqueueMotionLookup(h, f)) != KB_OK) return st;
+  if ((st = readCounters(h)) != KB_OK) return st;  // one 4 B round trip: are there any seeds at all?
+  const int seed_pixels = h->h_ctr[kCtrSeeds];
   int n_clusters_out = 0;
   if (seed_pixels == 0) {
     std::memset(dynamic_image_out, 0, sizeof(int32_t) * px);
   } else {
-    MotionHostParams& mp = h->motion_hp;
-    mp.W = c.width; mp.H = c.height; mp.fx = c.fx; mp.fy = c.fy; mp.cx = c.cx; mp.cy = c.cy;
-    std::memcpy(mp.Rw, p.Rw, sizeof(mp.Rw));
-    std::memcpy(mp.tw, p.tw, sizeof(mp.tw));
-    mp.connectivity = h->mot.neighbor_connectivity;
-    mp.min_cluster_size = h->mot.min_cluster_size;
-    mp.max_cluster_size = h->mot.max_cluster_size;
-    mp.min_separation_distance = h->mot.min_separation_distance;
-    // keep the depth image on the device for lazily built cluster lists (bounding boxes)
-    if (f->memory == KB_MEM_DEVICE && p.depth != h->mot_depth)
-      KB_CUDA(h, cudaMemcpyAsync(h->mot_depth, p.depth, sizeof(float) * px, cudaMemcpyDeviceToDevice, h->stream));
     bool device_path = h->mot.min_separation_distance > 0.f && f->vertex_world == nullptr;
     if (device_path) {
-      // M2-M4 on the device: connected components over the voxels that contain points
-      const int D = static_cast<int>(std::ceil(h->mot.min_separation_distance));
-      launchMotionClustering(h->mt, h->d_pixel_gidx, h->d_pixel_seed, static_cast<int>(px), h->mot.neighbor_connectivity,
-                             D, h->mot.min_cluster_size, h->mot.max_cluster_size, h->d_dynamic, h->stream);
-      KB_CUDA(h, cudaGetLastError());
-      KB_CUDA(h, cudaMemcpyAsync(h->h_mscal, h->mt.scalars, sizeof(int) * kMsCount, cudaMemcpyDeviceToHost, h->stream));
+      if ((st = enqueueDeviceClustering(h)) != KB_OK) return st;
       KB_CUDA(h, cudaMemcpyAsync(dynamic_image_out, h->d_dynamic, sizeof(int32_t) * px, cudaMemcpyDeviceToHost, h->stream));
       KB_CUDA(h, cudaStreamSynchronize(h->stream));
       if (h->h_mscal[kMsRoots] > h->mt.max_roots) {
@@ -907,6 +927,44 @@ int kb_detect_motion(kb_handle* h, const kb_frame* f, int32_t* dynamic_image_out
   }
   if (n_seeds) *n_seeds = h->motion.n_seeds;
   if (n_clusters) *n_clusters = n_clusters_out;
+  return KB_OK;
+}
+
+int kb_spin_once(kb_handle* h, const kb_frame* f, int32_t* dynamic_image_out, int32_t* n_seeds, int32_t* n_clusters) {
+  if (!h || !f || (!f->depth && !f->depth_u16)) return fail(h, KB_ERR_INVALID, "null argument");
+  if (!h->has_mot || !h->has_trk || !h->map.with_tracking) return fail(h, KB_ERR_STATE, "motion detector / tracking not configured");
+  if (!h->has_cam) return fail(h, KB_ERR_STATE, "kb_set_camera must be called first");
+  KB_CUDA(h, cudaSetDevice(h->device));
+  const size_t px = static_cast<size_t>(h->cam.width) * h->cam.height;
+  int st;
+  if (!(h->mot.min_separation_distance > 0.f) || f->vertex_world != nullptr) {
+    // configurations the device clustering does not cover: run the three steps one after the other
+    std::vector<int32_t> tmp;
+    int32_t* img = dynamic_image_out;
+    if (!img) { tmp.assign(px, 0); img = tmp.data(); }
+    if ((st = kb_detect_motion(h, f, img, n_seeds, n_clusters)) != KB_OK) return st;
+    kb_frame g = *f;
+    g.mask = KB_MASK_LAST_DETECTION;
+    if ((st = kb_integrate_frames(h, &g, 1, 1, nullptr)) != KB_OK) return st;
+    return updateTrackingImpl(h, f->stamp_ns);
+  }
+  // Everything is enqueued back to back; the device decides (seed counter) whether the clustering stages do
+  // anything, and the host reads image + counters once at the end.
+  if ((st = enqueueMotionLookup(h, f)) != KB_OK) return st;
+  if ((st = enqueueDeviceClustering(h)) != KB_OK) return st;
+  if (dynamic_image_out)
+    KB_CUDA(h, cudaMemcpyAsync(dynamic_image_out, h->d_dynamic, sizeof(int32_t) * px, cudaMemcpyDeviceToHost, h->stream));
+  h->motion_have_image = true;
+  kb_frame g = *f;
+  g.mask = KB_MASK_LAST_DETECTION;
+  if ((st = kb_integrate_frames(h, &g, 1, 1, nullptr)) != KB_OK) return st;
+  if ((st = updateTrackingImpl(h, f->stamp_ns)) != KB_OK) return st;
+  KB_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (h->h_mscal[kMsRoots] > h->mt.max_roots) return fail(h, KB_ERR_CAPACITY, "too many motion clusters for the device path");
+  h->motion.n_seeds = h->h_mscal[kMsSeeds];
+  h->motion_stale = h->h_mscal[kMsClusters] > 0;
+  if (n_seeds) *n_seeds = h->h_mscal[kMsSeeds];
+  if (n_clusters) *n_clusters = h->h_mscal[kMsClusters];
   return KB_OK;
 }
 

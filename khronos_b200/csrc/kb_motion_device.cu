@@ -74,7 +74,7 @@ __device__ __forceinline__ void ufUnion(int* parent, int a, int b) {
 // C1: the reference's BlockToPointsMap: every valid pixel inserts its voxel; slots double as entry ids.
 __global__ void vtInsertKernel(MotionTable t, const int3* __restrict__ gidx, const uint8_t* __restrict__ seed, int P) {
   const int px = blockIdx.x * blockDim.x + threadIdx.x;
-  if (px >= P) return;
+  if (px >= P || *t.gate == 0) return;
   const int3 g = gidx[px];
   int slot = -1;
   if (g.x != INT_MIN) {
@@ -113,7 +113,7 @@ __device__ __forceinline__ void keyToVox(unsigned long long k, int& x, int& y, i
 // C2: seed-seed and seed-absorbed adjacency; counts an absorbed voxel's adjacent seeds (deg).
 __global__ void vtLinkKernel(MotionTable t, int conn) {
   const int slot = blockIdx.x * blockDim.x + threadIdx.x;
-  if (slot > static_cast<int>(t.mask)) return;
+  if (slot > static_cast<int>(t.mask) || *t.gate == 0) return;
   const unsigned long long key = t.keys[slot];
   if (key == kVtEmpty) return;
   int x, y, z;
@@ -140,7 +140,7 @@ __global__ void vtLinkKernel(MotionTable t, int conn) {
 // C3: merge clusters closer than min_separation_distance: |a-b|^2 < D^2 with D = ceil(d).
 __global__ void vtMergeNearKernel(MotionTable t, int D) {
   const int slot = blockIdx.x * blockDim.x + threadIdx.x;
-  if (slot > static_cast<int>(t.mask)) return;
+  if (slot > static_cast<int>(t.mask) || *t.gate == 0) return;
   const unsigned long long key = t.keys[slot];
   if (key == kVtEmpty || t.deg[slot] == 0) return;
   int x, y, z;
@@ -159,7 +159,7 @@ __global__ void vtMergeNearKernel(MotionTable t, int D) {
 // C4: per-component reductions: pixel multiset size, smallest seed, member list of roots.
 __global__ void vtReduceKernel(MotionTable t) {
   const int slot = blockIdx.x * blockDim.x + threadIdx.x;
-  if (slot > static_cast<int>(t.mask)) return;
+  if (slot > static_cast<int>(t.mask) || *t.gate == 0) return;
   const unsigned long long key = t.keys[slot];
   if (key == kVtEmpty || t.deg[slot] == 0) return;
   const int root = ufFind(t.parent, slot);
@@ -174,6 +174,7 @@ __global__ void vtReduceKernel(MotionTable t) {
 
 // C5: size filter + ranking by smallest seed -> cluster ids (single CTA; clusters are few).
 __global__ void vtRankKernel(MotionTable t, int min_size, int max_size) {
+  if (*t.gate == 0) return;
   const int n = min(t.scalars[kMsRoots], t.max_roots);
   __shared__ int s_kept;
   if (threadIdx.x == 0) s_kept = 0;
@@ -204,15 +205,18 @@ __global__ void vtRankKernel(MotionTable t, int min_size, int max_size) {
 __global__ void vtWriteImageKernel(MotionTable t, int32_t* __restrict__ image, int P) {
   const int px = blockIdx.x * blockDim.x + threadIdx.x;
   if (px >= P) return;
-  const int slot = t.pix_slot[px];
   int id = 0;
-  if (slot >= 0 && t.deg[slot] != 0) id = t.cluster_id[ufFind(t.parent, slot)];
-  image[px] = id;
+  if (*t.gate != 0) {
+    const int slot = t.pix_slot[px];
+    if (slot >= 0 && t.deg[slot] != 0) id = t.cluster_id[ufFind(t.parent, slot)];
+  }
+  image[px] = id;  // no seeds: an all-zero dynamic image
 }
 
 __global__ void vtInitKernel(MotionTable t) {
   const int slot = blockIdx.x * blockDim.x + threadIdx.x;
-  if (slot > static_cast<int>(t.mask)) return;
+  if (slot < kMsCount) t.scalars[slot] = 0;
+  if (slot > static_cast<int>(t.mask) || *t.gate == 0) return;
   t.keys[slot] = kVtEmpty;
   t.count[slot] = 0;
   t.flags[slot] = 0;
@@ -220,7 +224,6 @@ __global__ void vtInitKernel(MotionTable t) {
   t.pix_total[slot] = 0;
   t.min_seed[slot] = ~0ull;
   t.cluster_id[slot] = 0;
-  if (slot < kMsCount) t.scalars[slot] = 0;
 }
 
 }  // namespace

@@ -24,9 +24,11 @@ struct MotionTable {
   int max_roots;
   int* scalars;                   // MotionScalar
   int* pix_slot;                  // [pixels] slot of the pixel's voxel or -1
+  const int* gate;                // device counter of seed pixels of this frame: 0 => every stage is a no-op
 };
 
-// Runs C1-C6 on `s`; writes the dynamic image (device) and scalars (seeds, roots, clusters).
+// Runs C1-C6 on `s`; writes the dynamic image (device) and scalars (seeds, roots, clusters). All stages read the
+// device-side seed-pixel counter t.gate, so the sequence can be enqueued before the host knows whether M1 found seeds.
 void launchMotionClustering(const MotionTable& t, const int3* gidx, const uint8_t* seed, int P, int conn, int D,
                             int min_size, int max_size, int32_t* image, cudaStream_t s);
 

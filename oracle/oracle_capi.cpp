@@ -152,6 +152,19 @@ int ko_detect_motion(ko_handle* h, const kb_frame* f_in, int32_t* dynamic_image_
   return h->o->ok() ? KB_OK : fail(h, KB_ERR_INVALID);
 }
 
+int ko_spin_once(ko_handle* h, const kb_frame* f, int32_t* dynamic_image_out, int32_t* n_seeds, int32_t* n_clusters) {
+  if (!h || !f) return KB_ERR_INVALID;
+  std::vector<int32_t> tmp;
+  int32_t* img = dynamic_image_out;
+  if (!img) { tmp.assign(h->pixels, 0); img = tmp.data(); }
+  int st = ko_detect_motion(h, f, img, n_seeds, n_clusters);
+  if (st != KB_OK) return st;
+  kb_frame g = *f;
+  g.mask = img;
+  if ((st = ko_integrate_frame(h, &g, 1, nullptr)) != KB_OK) return st;
+  return ko_update_tracking(h, f->stamp_ns);
+}
+
 int ko_get_motion_clusters(ko_handle* h, int32_t* counts, int32_t* pixels_uv, int64_t* voxels_xyz,
                            float* bbox_min_max, int32_t* total_pixels, int32_t* total_voxels) {
   if (!h) return KB_ERR_INVALID;

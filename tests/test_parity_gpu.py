@@ -106,6 +106,7 @@ def test_tracking_everfree_motion(oracle_lib, product_lib, sep):
     scene, frames, poses, stamps = dynamic_scenario(cam)
     mot = capi.default_motion_config(min_cluster_size=5, min_separation_distance=sep)
     o, g = both(oracle_lib, product_lib, cam=cam, mot_cfg=mot)
+    g2 = hs.make_handle(product_lib, "kb_", cam=cam, mot_cfg=mot)  # driven through the fused kb_spin_once
     total_dyn = 0
     for i, ((d, l), T, st) in enumerate(zip(frames, poses, stamps)):
         fo, fg = o.make_frame(d, T, st, label=l), g.make_frame(d, T, st, label=l)
@@ -113,6 +114,9 @@ def test_tracking_everfree_motion(oracle_lib, product_lib, sep):
         ig, sg_, cg = g.detect_motion(fg)
         assert (so_, co) == (sg_, cg), f"frame {i}: seeds/clusters {so_, co} vs {sg_, cg}"
         np.testing.assert_array_equal(io, ig, err_msg=f"dynamic_image frame {i}")
+        i2, s2, c2 = g2.spin_once(g2.make_frame(d, T, st, label=l))
+        assert (s2, c2) == (so_, co), f"spin_once frame {i}"
+        np.testing.assert_array_equal(io, i2, err_msg=f"spin_once dynamic_image frame {i}")
         clo, clg = o.get_motion_clusters(), g.get_motion_clusters()
         assert len(clo) == len(clg)
         for a, b in zip(clo, clg):
@@ -129,6 +133,7 @@ def test_tracking_everfree_motion(oracle_lib, product_lib, sep):
         g.update_tracking(st)
     bo, bg = o.export_blocks(), g.export_blocks()
     hs.assert_blocks_equal(bo, bg, exact_float=True, what="dynamic")
+    hs.assert_blocks_equal(bo, g2.export_blocks(), exact_float=True, what="dynamic via kb_spin_once")
     assert bo.ever_free.sum() > 1000, "scenario must produce ever-free space"
     assert total_dyn > 100, "scenario must flag dynamic pixels"
 
