@@ -158,6 +158,8 @@ int ensureMotionBuffers(kb_handle* h, size_t pixels) {
   KB_CUDA(h, devAlloc(&t.min_seed, cap, 0xFF));
   KB_CUDA(h, devAlloc(&t.cluster_id, cap, 0));
   KB_CUDA(h, devAlloc(&t.roots, static_cast<size_t>(t.max_roots), 0));
+  cudaFree(t.occupied);
+  KB_CUDA(h, devAlloc(&t.occupied, pixels, 0));
   KB_CUDA(h, devAlloc(&t.scalars, static_cast<size_t>(kMsCount), 0));
   KB_CUDA(h, devAlloc(&t.pix_slot, pixels, 0xFF));
   t.gate = h->dm.counters + kCtrSeeds;
@@ -400,7 +402,7 @@ int kb_destroy(kb_handle* h) {
   cudaFree(h->stg_vertex); cudaFree(h->d_pixel_gidx); cudaFree(h->d_pixel_seed); cudaFree(h->d_removed);
   cudaFree(h->d_dynamic);
   { MotionTable& t = h->mt; cudaFree(t.keys); cudaFree(t.count); cudaFree(t.flags); cudaFree(t.deg); cudaFree(t.parent);
-    cudaFree(t.pix_total); cudaFree(t.min_seed); cudaFree(t.cluster_id); cudaFree(t.roots); cudaFree(t.scalars); cudaFree(t.pix_slot); }
+    cudaFree(t.pix_total); cudaFree(t.min_seed); cudaFree(t.cluster_id); cudaFree(t.roots); cudaFree(t.scalars); cudaFree(t.pix_slot); cudaFree(t.occupied); }
   if (h->h_mscal) cudaFreeHost(h->h_mscal);
   cudaFree(h->stg_depth16); cudaFree(h->stg_label8); cudaFree(h->mot_depth16);
   cudaFree(h->mot_depth); cudaFree(h->tile_max); cudaFree(h->work_slots); cudaFree(h->work_masks); cudaFree(h->work_upd); cudaFree(h->item_fmask);

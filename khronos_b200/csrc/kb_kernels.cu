@@ -638,10 +638,15 @@ __device__ __forceinline__ bool voxelFreeNow(const DeviceMap& m, const TrackEval
   return oc == 0 ? (t.zero_free != 0) : (oc < t.free_max);
 }
 
+// One CTA per pending block. The "free or ever-free" predicate of the block's voxels and of a one-voxel halo
+// (taken from the 26 neighbour blocks, resolved once into shared memory) is first materialised in shared
+// memory by all threads in parallel; the 6/18/26-neighbourhood test of every candidate voxel then only reads
+// shared memory, instead of chasing up to 18 dependent global loads per candidate.
 __global__ void __launch_bounds__(kThreads) everFreeKernel(const DeviceMap m, const TrackingParams p) {
   __shared__ int s_nbr[27];
+  __shared__ uint8_t s_free[18 * 18 * 18];  // bit0: free or ever-free, bit1: ever-free (halo of the largest block)
   const int n = m.counters[kCtrPending];
-  const int vps = m.vps, V = m.V;
+  const int vps = m.vps, V = m.V, hs = vps + 2;
   for (int w = blockIdx.x; w < n; w += gridDim.x) {
     const int slot = p.pending[w];
     __syncthreads();
@@ -651,28 +656,36 @@ __global__ void __launch_bounds__(kThreads) everFreeKernel(const DeviceMap m, co
       s_nbr[threadIdx.x] = (dx == 0 && dy == 0 && dz == 0) ? slot : hashLookup(m, bi.x + dx, bi.y + dy, bi.z + dz);
     }
     __syncthreads();
+    for (int i = threadIdx.x; i < hs * hs * hs; i += kThreads) {
+      int x = i % hs - 1, y = (i / hs) % hs - 1, z = i / (hs * hs) - 1;
+      int bx = 1, by = 1, bz = 1;
+      if (x < 0) { x += vps; bx = 0; } else if (x >= vps) { x -= vps; bx = 2; }
+      if (y < 0) { y += vps; by = 0; } else if (y >= vps) { y -= vps; by = 2; }
+      if (z < 0) { z += vps; bz = 0; } else if (z >= vps) { z -= vps; bz = 2; }
+      const int ns = s_nbr[bx + 3 * by + 9 * bz];
+      uint8_t v = 0;  // missing neighbour block: blocks its neighbours (:198-202)
+      if (ns >= 0) {
+        const size_t idx = static_cast<size_t>(ns) * V + (x + vps * (y + vps * z));
+        const uint8_t f = m.vflags[idx];
+        v = (voxelFreeNow(m, p.ev, idx, f) ? 1 : 0) | ((f & kVoxEverFree) ? 2 : 0);
+      }
+      s_free[i] = v;
+    }
+    __syncthreads();
     const size_t base = static_cast<size_t>(slot) * V;
     for (int lin = threadIdx.x; lin < V; lin += kThreads) {
-      const uint8_t f = m.vflags[base + lin];
-      if ((f & kVoxEverFree) || !voxelFreeNow(m, p.ev, base + lin, f)) continue;
       const int vx = lin % vps, vy = (lin / vps) % vps, vz = lin / (vps * vps);
+      const int c = (vx + 1) + hs * ((vy + 1) + hs * (vz + 1));
+      if (s_free[c] != 1) continue;  // needs: free now, not yet ever-free
       bool blocked = false;
       for (int dz = -1; dz <= 1 && !blocked; ++dz)
         for (int dy = -1; dy <= 1 && !blocked; ++dy)
           for (int dx = -1; dx <= 1; ++dx) {
             const int nnz = (dx != 0) + (dy != 0) + (dz != 0);
             if (nnz == 0 || (p.connectivity == 6 && nnz > 1) || (p.connectivity == 18 && nnz > 2)) continue;
-            int nx = vx + dx, ny = vy + dy, nz = vz + dz;
-            int bx = 1, by = 1, bz = 1;
-            if (nx < 0) { nx += vps; bx = 0; } else if (nx >= vps) { nx -= vps; bx = 2; }
-            if (ny < 0) { ny += vps; by = 0; } else if (ny >= vps) { ny -= vps; by = 2; }
-            if (nz < 0) { nz += vps; bz = 0; } else if (nz >= vps) { nz -= vps; bz = 2; }
-            const int ns = s_nbr[bx + 3 * by + 9 * bz];
-            if (ns < 0) { blocked = true; break; }  // missing neighbour block (:198-202)
-            const size_t nidx = static_cast<size_t>(ns) * V + (nx + vps * (ny + vps * nz));
-            if (!voxelFreeNow(m, p.ev, nidx, m.vflags[nidx])) { blocked = true; break; }
+            if (!(s_free[c + dx + hs * (dy + hs * dz)] & 1)) { blocked = true; break; }
           }
-      if (!blocked) m.vflags[base + lin] = f | kVoxEverFree;
+      if (!blocked) m.vflags[base + lin] |= kVoxEverFree;
     }
   }
 }

@@ -84,7 +84,11 @@ __global__ void vtInsertKernel(MotionTable t, const int3* __restrict__ gidx, con
       unsigned long long k = t.keys[h];
       if (k == kVtEmpty) {
         k = atomicCAS(&t.keys[h], kVtEmpty, key);
-        if (k == kVtEmpty) { t.parent[h] = static_cast<int>(h); k = key; }
+        if (k == kVtEmpty) {  // this thread created the entry
+          t.parent[h] = static_cast<int>(h);
+          t.occupied[atomicAdd(&t.scalars[kMsOccupied], 1)] = static_cast<int>(h);
+          k = key;
+        }
       }
       if (k == key) { slot = static_cast<int>(h); break; }
       h = (h + 1) & t.mask;
@@ -111,49 +115,59 @@ __device__ __forceinline__ void keyToVox(unsigned long long k, int& x, int& y, i
 }
 
 // C2: seed-seed and seed-absorbed adjacency; counts an absorbed voxel's adjacent seeds (deg).
-__global__ void vtLinkKernel(MotionTable t, int conn) {
-  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
-  if (slot > static_cast<int>(t.mask) || *t.gate == 0) return;
-  const unsigned long long key = t.keys[slot];
-  if (key == kVtEmpty) return;
-  int x, y, z;
-  keyToVox(key, x, y, z);
-  const bool is_seed = t.flags[slot] & kMvSeed;
-  int deg = 0;
-  for (int dz = -1; dz <= 1; ++dz)
-    for (int dy = -1; dy <= 1; ++dy)
-      for (int dx = -1; dx <= 1; ++dx) {
-        if (!inConn(dx, dy, dz, conn)) continue;
-        const int n = vtLookup(t, x + dx, y + dy, z + dz);
-        if (n < 0 || !(t.flags[n] & kMvSeed)) continue;
-        ++deg;
-        if (!is_seed || n < slot) ufUnion(t.parent, slot, n);  // each seed pair once; absorbed -> all its seeds
+// One warp per occupied voxel, lane = neighbour offset (27 cells of the 3x3x3 cube), so the hash probes of a
+// voxel's neighbourhood run in parallel instead of as 26 dependent chains.
+__global__ void __launch_bounds__(256) vtLinkKernel(MotionTable t, int conn) {
+  if (*t.gate == 0) return;
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+  const int n = t.scalars[kMsOccupied];
+  const int dx = lane % 3 - 1, dy = (lane / 3) % 3 - 1, dz = lane / 9 - 1;
+  const bool active = lane < 27 && inConn(dx, dy, dz, conn);
+  for (int w = warp; w < n; w += n_warps) {
+    const int slot = t.occupied[w];
+    int x, y, z;
+    keyToVox(t.keys[slot], x, y, z);
+    const bool is_seed = t.flags[slot] & kMvSeed;
+    bool nb_seed = false;
+    if (active) {
+      const int nb = vtLookup(t, x + dx, y + dy, z + dz);
+      nb_seed = nb >= 0 && (t.flags[nb] & kMvSeed);
+      if (nb_seed && (!is_seed || nb < slot)) ufUnion(t.parent, slot, nb);  // each seed pair once; absorbed -> all its seeds
+    }
+    const int deg = __popc(__ballot_sync(0xffffffffu, nb_seed));
+    if (lane == 0) {
+      if (is_seed) {
+        atomicAdd(&t.scalars[kMsSeeds], 1);
+        t.deg[slot] = 1;
+      } else {
+        t.deg[slot] = deg;  // 0: not part of any cluster
       }
-  if (is_seed) {
-    atomicAdd(&t.scalars[kMsSeeds], 1);
-    t.deg[slot] = 1;
-  } else {
-    t.deg[slot] = deg;  // 0: not part of any cluster
+    }
   }
 }
 
-// C3: merge clusters closer than min_separation_distance: |a-b|^2 < D^2 with D = ceil(d).
-__global__ void vtMergeNearKernel(MotionTable t, int D) {
-  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
-  if (slot > static_cast<int>(t.mask) || *t.gate == 0) return;
-  const unsigned long long key = t.keys[slot];
-  if (key == kVtEmpty || t.deg[slot] == 0) return;
-  int x, y, z;
-  keyToVox(key, x, y, z);
-  const int r = D - 1, D2 = D * D;
-  for (int dz = -r; dz <= r; ++dz)
-    for (int dy = -r; dy <= r; ++dy)
-      for (int dx = -r; dx <= r; ++dx) {
-        const int s = dx * dx + dy * dy + dz * dz;
-        if (s == 0 || s >= D2) continue;
-        const int n = vtLookup(t, x + dx, y + dy, z + dz);
-        if (n >= 0 && n < slot && t.deg[n] != 0) ufUnion(t.parent, slot, n);
-      }
+// C3: merge clusters closer than min_separation_distance: |a-b|^2 < D^2 with D = ceil(d). One warp per cluster
+// voxel; the lanes stride over the (2D-1)^3 offset cube.
+__global__ void __launch_bounds__(256) vtMergeNearKernel(MotionTable t, int D) {
+  if (*t.gate == 0) return;
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+  const int n = t.scalars[kMsOccupied];
+  const int side = 2 * D - 1, cells = side * side * side, D2 = D * D;
+  for (int w = warp; w < n; w += n_warps) {
+    const int slot = t.occupied[w];
+    if (t.deg[slot] == 0) continue;
+    int x, y, z;
+    keyToVox(t.keys[slot], x, y, z);
+    for (int c = lane; c < cells; c += 32) {
+      const int dx = c % side - (D - 1), dy = (c / side) % side - (D - 1), dz = c / (side * side) - (D - 1);
+      const int s = dx * dx + dy * dy + dz * dz;
+      if (s == 0 || s >= D2) continue;
+      const int nb = vtLookup(t, x + dx, y + dy, z + dz);
+      if (nb >= 0 && nb < slot && t.deg[nb] != 0) ufUnion(t.parent, slot, nb);
+    }
+  }
 }
 
 // C4: per-component reductions: pixel multiset size, smallest seed, member list of roots.
@@ -233,8 +247,8 @@ void launchMotionClustering(const MotionTable& t, const int3* gidx, const uint8_
   const int cap = static_cast<int>(t.mask) + 1;
   vtInitKernel<<<(cap + 255) / 256, 256, 0, s>>>(t);
   vtInsertKernel<<<(P + 255) / 256, 256, 0, s>>>(t, gidx, seed, P);
-  vtLinkKernel<<<(cap + 255) / 256, 256, 0, s>>>(t, conn);
-  if (D > 1) vtMergeNearKernel<<<(cap + 255) / 256, 256, 0, s>>>(t, D);
+  vtLinkKernel<<<148 * 4, 256, 0, s>>>(t, conn);     // persistent warps over the occupied-voxel list
+  if (D > 1) vtMergeNearKernel<<<148 * 4, 256, 0, s>>>(t, D);
   vtReduceKernel<<<(cap + 255) / 256, 256, 0, s>>>(t);
   vtRankKernel<<<1, 1024, 0, s>>>(t, min_size, max_size);
   vtWriteImageKernel<<<(P + 255) / 256, 256, 0, s>>>(t, image, P);

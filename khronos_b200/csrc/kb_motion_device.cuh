@@ -6,7 +6,7 @@
 namespace kb {
 
 constexpr uint8_t kMvSeed = 1;
-enum MotionScalar { kMsSeeds = 0, kMsRoots = 1, kMsClusters = 2, kMsCount = 4 };
+enum MotionScalar { kMsSeeds = 0, kMsRoots = 1, kMsClusters = 2, kMsOccupied = 3, kMsCount = 4 };
 
 // Open-addressed table of the voxels that contain points of the current frame; a slot index is the voxel's
 // id in all per-voxel arrays (capacity = mask + 1 >= 2 * pixels).
@@ -20,6 +20,7 @@ struct MotionTable {
   unsigned long long* pix_total;  // per root: pixel multiset size of the cluster
   unsigned long long* min_seed;   // per root: smallest seed key (z,y,x order)
   int* cluster_id;                // per root: 0 = filtered, else 1..255
+  int* occupied;                  // compact list of occupied slots (capacity = pixels)
   int* roots;                     // compact list of roots
   int max_roots;
   int* scalars;                   // MotionScalar
