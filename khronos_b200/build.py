@@ -31,7 +31,8 @@ def build_product(force=False, verbose=False):
     deps = srcs + [h if os.path.isabs(h) else os.path.join(CSRC, h) for h in HEADERS]
     if not force and not _stale(LIB, deps):
         return LIB
-    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + srcs
+    extra = [f"-DKB_FUSE_MIN_BLOCKS={os.environ['KB_FUSE_MIN_BLOCKS']}"] if os.environ.get("KB_FUSE_MIN_BLOCKS") else []
+    cmd = ["nvcc"] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + srcs
     print(" ".join(cmd), file=sys.stderr)
     subprocess.check_call(cmd, cwd=CSRC)
     return LIB

@@ -25,6 +25,9 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kFuseThreads = 128;  // 4 independent warps per CTA
+#ifndef KB_FUSE_MIN_BLOCKS
+#define KB_FUSE_MIN_BLOCKS 10      // resident CTAs per SM the fuse kernel is compiled for (register cap 65536/(128*N))
+#endif
 
 __device__ __forceinline__ void xform(const float* R, const float* t, float x, float y, float z,
                                       float& ox, float& oy, float& oz) {
@@ -424,7 +427,7 @@ __device__ __noinline__ uint32_t trackingFold(const DeviceMap m, const TrackEval
 // computeLabel structure pinned by khronos/src/active_window/integration/object_integrator.cpp:58-81);
 // SemanticIntegrator::updateLikelihoods (UP App. A.8).
 template <int VPS, int LPI, bool COMPACT>
-__global__ void __launch_bounds__(kFuseThreads, 10) fuseKernel(const DeviceMap m, const __grid_constant__ BatchParams p) {
+__global__ void __launch_bounds__(kFuseThreads, KB_FUSE_MIN_BLOCKS) fuseKernel(const DeviceMap m, const __grid_constant__ BatchParams p) {
   constexpr int V = VPS * VPS * VPS;
   constexpr int NK = 4;                                      // z-layers per culling box
   constexpr int BOXES = (VPS / 4) * (VPS / 8) * (VPS / NK);  // 32 (16^3) or 4 (8^3) boxes of 128 voxels
