@@ -161,6 +161,7 @@ class Blocks:
     semantic_label: np.ndarray
     semantic_empty: np.ndarray
     semantic_likelihoods: Optional[np.ndarray] = None
+    color: Optional[np.ndarray] = None  # (n, V, 3) u8 TsdfVoxel::color (rgb)
     extra: dict = field(default_factory=dict)
 
     @property
@@ -352,7 +353,8 @@ class MapHandle:
             ever_free=np.zeros((n, V), np.uint8), active=np.zeros((n, V), np.uint8),
             to_remove=np.zeros((n, V), np.uint8), semantic_label=np.zeros((n, V), np.uint32),
             semantic_empty=np.ones((n, V), np.uint8),
-            semantic_likelihoods=np.zeros((n, V, L), np.float32) if (likelihoods and L > 0) else None)
+            semantic_likelihoods=np.zeros((n, V, L), np.float32) if (likelihoods and L > 0) else None,
+            color=np.zeros((n, V, 3), np.uint8))
         ex = BlockExport()
         for name, _ in BlockExport._fields_:
             arr = getattr(b, name, None)

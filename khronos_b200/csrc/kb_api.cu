@@ -41,6 +41,8 @@ struct kb_handle {
   int* stg_object = nullptr;
   uint16_t* stg_depth16 = nullptr;  // compact inputs (2 sets x kMaxBatch frames)
   uint8_t* stg_label8 = nullptr;
+  uint8_t* stg_color = nullptr;     // RGB staging (3 B/pixel), allocated with the first host colour image
+  size_t stg_color_pixels = 0;
   uint16_t* mot_depth16 = nullptr;
   float* stg_vertex = nullptr;
   float* mot_depth = nullptr;
@@ -128,6 +130,28 @@ int ensureStaging(kb_handle* h, size_t pixels) {
   KB_CUDA(h, devAlloc(&h->stg_depth16, n, 0));
   KB_CUDA(h, devAlloc(&h->stg_label8, n, 0));
   h->stg_pixels = pixels;
+  return KB_OK;
+}
+
+// TsdfVoxel::color lives in its own array that is only allocated once a frame carries a colour image
+// (the BASELINE workloads are colour-less and pay nothing for it).
+int ensureColorLayer(kb_handle* h) {
+  DeviceMap& m = h->dm;
+  if (m.color) return KB_OK;
+  const size_t n = static_cast<size_t>(m.max_blocks) * m.V;
+  KB_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&m.color), n * sizeof(uchar4)));
+  KB_CUDA(h, cudaMemsetAsync(m.color, 0, n * sizeof(uchar4), h->stream));
+  return KB_OK;
+}
+
+int ensureColorStaging(kb_handle* h, size_t pixels) {
+  if (h->stg_color_pixels >= pixels) return KB_OK;
+  KB_CUDA(h, cudaStreamSynchronize(h->stream));
+  KB_CUDA(h, cudaStreamSynchronize(h->copy_stream));
+  cudaFree(h->stg_color);
+  h->stg_color = nullptr;
+  KB_CUDA(h, devAlloc(&h->stg_color, pixels * 3 * kMaxBatch * 2, 0));
+  h->stg_color_pixels = pixels;
   return KB_OK;
 }
 
@@ -397,7 +421,7 @@ int kb_destroy(kb_handle* h) {
   cudaFree(m.sem_free_list); cudaFree(m.block_index); cudaFree(m.block_flags); cudaFree(m.block_sem);
   cudaFree(m.tsdf); cudaFree(m.last_obs); cudaFree(m.last_occ); cudaFree(m.vflags);
   cudaFree(m.born_frame); cudaFree(m.next_pass); cudaFree(m.act_min); cudaFree(h->pending);
-  cudaFree(m.sem_label); cudaFree(m.sem_lik);
+  cudaFree(m.sem_label); cudaFree(m.sem_lik); cudaFree(m.color); cudaFree(h->stg_color);
   cudaFree(h->stg_depth); cudaFree(h->stg_label); cudaFree(h->stg_mask); cudaFree(h->stg_object);
   cudaFree(h->stg_vertex); cudaFree(h->d_pixel_gidx); cudaFree(h->d_pixel_seed); cudaFree(h->d_removed);
   cudaFree(h->d_dynamic);
@@ -533,10 +557,18 @@ static int integrateBatch(kb_handle* h, const kb_frame* frames, int n, int alloc
   p.trk = h->pass;
 
   // ---- stage host images (double-buffered, on the copy stream so they overlap the previous batch)
-  bool any_host = false, any_compact = false;
+  bool any_host = false, any_compact = false, any_color = false, any_host_color = false;
   for (int b = 0; b < n; ++b) {
     any_host |= frames[b].memory != KB_MEM_DEVICE;
     any_compact |= frames[b].depth_u16 != nullptr || frames[b].label_u8 != nullptr;
+    any_color |= frames[b].color != nullptr;
+    any_host_color |= frames[b].color != nullptr && frames[b].memory != KB_MEM_DEVICE;
+  }
+  p.has_color = any_color ? 1 : 0;
+  if (any_color) {
+    int st = ensureColorLayer(h);
+    if (st == KB_OK && any_host_color) st = ensureColorStaging(h, px);
+    if (st != KB_OK) return st;
   }
   const int set = h->stg_set;
   const bool use_staging = any_host || any_compact;
@@ -564,7 +596,9 @@ static int integrateBatch(kb_handle* h, const kb_frame* frames, int n, int alloc
     if (f.memory == KB_MEM_DEVICE) {
       v.depth = f.depth; v.label = f.label; v.mask = f.mask; v.object_image = f.object_image;
       v.depth16 = f.depth_u16; v.label8 = f.label_u8;
+      v.color = f.color;
     } else {
+      v.color = f.color ? h->stg_color + off * 3 : nullptr;
       v.depth = f.depth ? h->stg_depth + off : nullptr;
       v.label = f.label ? h->stg_label + off : nullptr;
       v.mask = f.mask ? h->stg_mask + off : nullptr;
@@ -591,16 +625,17 @@ static int integrateBatch(kb_handle* h, const kb_frame* frames, int n, int alloc
   if (any_host) {
     // H2D staging. Runs of frames whose host images are contiguous in memory (a ring buffer / video
     // tensor) are coalesced into one copy per image kind; separate cv::Mat buffers copy one by one.
-    auto copyKind = [&](auto member, auto* staging) -> int {
+    auto copyKind = [&](auto member, auto* staging, size_t per = 1) -> int {  // per: elements per pixel
       using T = std::remove_pointer_t<decltype(staging)>;
+      const size_t img = px * per;
       int b = 0;
       while (b < n) {
         const T* src = (frames[b].memory == KB_MEM_DEVICE) ? nullptr : static_cast<const T*>(frames[b].*member);
         if (!src || static_cast<const void*>(src) == static_cast<const void*>(KB_MASK_LAST_DETECTION)) { ++b; continue; }
         int e = b + 1;
-        while (e < n && frames[e].memory != KB_MEM_DEVICE && static_cast<const T*>(frames[e].*member) == src + static_cast<size_t>(e - b) * px) ++e;  // contiguous run
-        T* dst = staging + (static_cast<size_t>(set) * kMaxBatch + b) * px;
-        KB_CUDA(h, cudaMemcpyAsync(dst, src, static_cast<size_t>(e - b) * px * sizeof(T), cudaMemcpyHostToDevice, h->copy_stream));
+        while (e < n && frames[e].memory != KB_MEM_DEVICE && static_cast<const T*>(frames[e].*member) == src + static_cast<size_t>(e - b) * img) ++e;  // contiguous run
+        T* dst = staging + (static_cast<size_t>(set) * kMaxBatch + b) * img;
+        KB_CUDA(h, cudaMemcpyAsync(dst, src, static_cast<size_t>(e - b) * img * sizeof(T), cudaMemcpyHostToDevice, h->copy_stream));
         b = e;
       }
       return KB_OK;
@@ -612,6 +647,7 @@ static int integrateBatch(kb_handle* h, const kb_frame* frames, int n, int alloc
     if ((cst = copyKind(&kb_frame::object_image, h->stg_object)) != KB_OK) return cst;
     if ((cst = copyKind(&kb_frame::depth_u16, h->stg_depth16)) != KB_OK) return cst;
     if ((cst = copyKind(&kb_frame::label_u8, h->stg_label8)) != KB_OK) return cst;
+    if (any_host_color && (cst = copyKind(&kb_frame::color, h->stg_color, 3)) != KB_OK) return cst;
     KB_CUDA(h, cudaEventRecord(h->stg_ready[set], h->copy_stream));
     KB_CUDA(h, cudaStreamWaitEvent(h->stream, h->stg_ready[set], 0));
   }
@@ -1062,13 +1098,14 @@ int kb_export_blocks(kb_handle* h, int which, int32_t max_blocks, kb_block_expor
     if (out->block_index) { out->block_index[i * 3] = index[i].x; out->block_index[i * 3 + 1] = index[i].y; out->block_index[i * 3 + 2] = index[i].z; }
     if (out->block_flags) out->block_flags[i] = static_cast<uint8_t>(flags[i] & kPublicFlagMask);
   }
-  if (out->color && n) std::memset(out->color, 0, static_cast<size_t>(n) * V * 3);
+  if (out->color && n && !h->dm.color) std::memset(out->color, 0, static_cast<size_t>(n) * V * 3);  // no colour seen yet
   // Gather in chunks through dense device buffers, then copy out.
   const int chunk = 1024;
   int* d_slots = nullptr;
   unsigned long long* d_stamps = nullptr;
   char* d_buf = nullptr;
   const size_t per_block = V * (4 + 4) + V * (8 + 8 + 3) + V * (4 + 1) + V * L * 4 + 16;
+  const size_t rgb_off = per_block * std::min(chunk, std::max(n, 1));  // colour gather area behind the other fields
   auto cleanup = [&]() { cudaFree(d_slots); cudaFree(d_stamps); cudaFree(d_buf); };
   auto body = [&]() -> int {
     if (n == 0) return KB_OK;
@@ -1076,7 +1113,7 @@ int kb_export_blocks(kb_handle* h, int which, int32_t max_blocks, kb_block_expor
     KB_CUDA(h, cudaMemcpy(d_slots, slots.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
     KB_CUDA(h, cudaMalloc(&d_stamps, sizeof(uint64_t) * h->stamps.size()));
     KB_CUDA(h, cudaMemcpy(d_stamps, h->stamps.data(), sizeof(uint64_t) * h->stamps.size(), cudaMemcpyHostToDevice));
-    KB_CUDA(h, cudaMalloc(&d_buf, per_block * std::min(chunk, n)));
+    KB_CUDA(h, cudaMalloc(&d_buf, (per_block + V * 3) * std::min(chunk, n)));
     for (int b0 = 0; b0 < n; b0 += chunk) {
       const int nb = std::min(chunk, n - b0);
       char* q = d_buf;
@@ -1091,11 +1128,16 @@ int kb_export_blocks(kb_handle* h, int which, int32_t max_blocks, kb_block_expor
       uint8_t* d_tr = reinterpret_cast<uint8_t*>(q); q += nb * V;
       uint8_t* d_em = reinterpret_cast<uint8_t*>(q); q += nb * V;
       uint8_t* d_ba = reinterpret_cast<uint8_t*>(q); q += nb;
+      uint8_t* d_rgb = reinterpret_cast<uint8_t*>(d_buf) + rgb_off;
       const size_t off = static_cast<size_t>(b0) * V;
       if (out->distance || out->weight) {
         launchGatherTsdf(h->dm, d_slots + b0, nb, d_dist, d_w, h->stream);
         if (out->distance) KB_CUDA(h, cudaMemcpyAsync(out->distance + off, d_dist, nb * V * 4, cudaMemcpyDeviceToHost, h->stream));
         if (out->weight) KB_CUDA(h, cudaMemcpyAsync(out->weight + off, d_w, nb * V * 4, cudaMemcpyDeviceToHost, h->stream));
+      }
+      if (out->color && h->dm.color) {
+        launchGatherColor(h->dm, d_slots + b0, nb, d_rgb, h->stream);
+        KB_CUDA(h, cudaMemcpyAsync(out->color + off * 3, d_rgb, nb * V * 3, cudaMemcpyDeviceToHost, h->stream));
       }
       const bool want_trk = out->last_observed || out->last_occupied || out->ever_free || out->active ||
                             out->to_remove || out->block_flags;

@@ -8,6 +8,7 @@
 //                                            index -> u64 stamp table, halving tracking traffic
 //   vflags[S][V] u8                         bit0 ever_free, bit1 active, bit2 to_remove
 //   sem_label[Q][V] u16 (0xFFFF = empty), sem_lik[Q][V][Lp] f32   lazily assigned semantic slots
+//   color[S][V] uchar4                      TsdfVoxel::color, allocated on the first frame that carries colour
 #pragma once
 
 #include <cuda_runtime.h>
@@ -51,6 +52,7 @@ struct DeviceMap {
   int frame_capacity;
   uint16_t* sem_label;
   float* sem_lik;
+  uchar4* color;  // [S][V] TsdfVoxel::color (rgb, w unused); null until the first frame with a colour image
 };
 
 // Cumulative device counters (never reset on the hot path; the host reports differences).

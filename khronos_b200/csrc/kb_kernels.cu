@@ -28,6 +28,9 @@ constexpr int kFuseThreads = 128;  // 4 independent warps per CTA
 #ifndef KB_FUSE_MIN_BLOCKS
 #define KB_FUSE_MIN_BLOCKS 10      // resident CTAs per SM the fuse kernel is compiled for (register cap 65536/(128*N))
 #endif
+#ifndef KB_FUSE_COLOR_MIN_BLOCKS
+#define KB_FUSE_COLOR_MIN_BLOCKS 8  // the colour-blending variant carries a few more live registers
+#endif
 
 __device__ __forceinline__ void xform(const float* R, const float* t, float x, float y, float z,
                                       float& ox, float& oy, float& oz) {
@@ -154,6 +157,28 @@ __device__ __forceinline__ float measurementWeight(const BatchParams& p, float d
     w = fmaxf(w, 0.f);
   }
   return w;
+}
+
+// ProjectionInterpolator::interpolateColor (UP App. A.6 step 5; docs/ORACLE_SPEC.md §5.6): nearest -> the pixel's
+// colour; bilinear -> per channel ((w0 c0 + w1 c1) + w2 c2) + w3 c3 over the taps (u,v), (u,v+1), (u+1,v), (u+1,v+1),
+// truncated to u8.
+__device__ __forceinline__ uchar3 measuredColor(const BatchParams& p, const FrameView& f, const Taps& t) {
+  const uint8_t* __restrict__ p0 = f.color + (static_cast<size_t>(t.v) * p.W + t.u) * 3;
+  if (!t.bilinear) return make_uchar3(__ldg(p0), __ldg(p0 + 1), __ldg(p0 + 2));
+  const uint8_t* __restrict__ p1 = p0 + static_cast<size_t>(p.W) * 3;
+  uint8_t o[3];
+#pragma unroll
+  for (int ch = 0; ch < 3; ++ch) {
+    const float s = ((t.w0 * static_cast<float>(__ldg(p0 + ch)) + t.w1 * static_cast<float>(__ldg(p1 + ch))) +
+                     t.w2 * static_cast<float>(__ldg(p0 + 3 + ch))) + t.w3 * static_cast<float>(__ldg(p1 + 3 + ch));
+    o[ch] = static_cast<uint8_t>(static_cast<int>(s));
+  }
+  return make_uchar3(o[0], o[1], o[2]);
+}
+
+// spark_dsg Color::merge as called by updateVoxel: c = u8(c * (1 - ratio) + c_m * ratio).
+__device__ __forceinline__ uint8_t mergeChannel(uint8_t c, uint8_t cm, float ratio) {
+  return static_cast<uint8_t>(static_cast<int>(static_cast<float>(c) * (1.f - ratio) + static_cast<float>(cm) * ratio));
 }
 
 __device__ __forceinline__ int warpSum(int v) {
@@ -426,8 +451,11 @@ __device__ __noinline__ uint32_t trackingFold(const DeviceMap m, const TrackEval
 // ProjectiveIntegrator::updateBlock / getVoxelMeasurement / computeLabel / updateVoxel (UP App. A.6;
 // computeLabel structure pinned by khronos/src/active_window/integration/object_integrator.cpp:58-81);
 // SemanticIntegrator::updateLikelihoods (UP App. A.8).
-template <int VPS, int LPI, bool COMPACT>
-__global__ void __launch_bounds__(kFuseThreads, KB_FUSE_MIN_BLOCKS) fuseKernel(const DeviceMap m, const __grid_constant__ BatchParams p) {
+// COLOR: some frame of the batch carries a colour image; band voxels blend it into TsdfVoxel::color (kept in a
+// register like the rest of the voxel state: one 4 B read + write per batch). The colour-less instantiations
+// are the ones the BASELINE workloads run and are unchanged by this parameter.
+template <int VPS, int LPI, bool COMPACT, bool COLOR>
+__global__ void __launch_bounds__(kFuseThreads, COLOR ? KB_FUSE_COLOR_MIN_BLOCKS : KB_FUSE_MIN_BLOCKS) fuseKernel(const DeviceMap m, const __grid_constant__ BatchParams p) {
   constexpr int V = VPS * VPS * VPS;
   constexpr int NK = 4;                                      // z-layers per culling box
   constexpr int BOXES = (VPS / 4) * (VPS / 8) * (VPS / NK);  // 32 (16^3) or 4 (8^3) boxes of 128 voxels
@@ -472,6 +500,8 @@ __global__ void __launch_bounds__(kFuseThreads, KB_FUSE_MIN_BLOCKS) fuseKernel(c
     uint32_t lobs = 0, vfl = 0, upd_frames = 0;
     bool have = false, row_resident = false;
     int best_label = 0;
+    uchar4 col = make_uchar4(0, 0, 0, 0);
+    bool col_dirty = false;
 
     uint32_t rem = fmask;
     while (rem) {
@@ -509,6 +539,7 @@ __global__ void __launch_bounds__(kFuseThreads, KB_FUSE_MIN_BLOCKS) fuseKernel(c
         st = m.tsdf[gi];
         have = true;
         if (p.with_tracking) vfl = trackingFold(m, p.trk, m.born_frame[slot], gi);
+        if constexpr (COLOR) col = m.color[gi];
       }
       const float sdf_c = fminf(fmaxf(sdf, -p.trunc), p.trunc);
       const float2 old = st;
@@ -519,6 +550,17 @@ __global__ void __launch_bounds__(kFuseThreads, KB_FUSE_MIN_BLOCKS) fuseKernel(c
       ++n_valid;
       if (!in_band) continue;
       ++n_band;
+      if constexpr (COLOR) {
+        if (f.color != nullptr) {  // updateVoxel: colour is merged near the surface only
+          const uchar3 cm = measuredColor(p, f, taps);
+          const float tot = old.y + wm;
+          const float ratio = tot > 0.f ? wm / tot : 0.f;
+          col.x = mergeChannel(col.x, cm.x, ratio);
+          col.y = mergeChannel(col.y, cm.y, ratio);
+          col.z = mergeChannel(col.z, cm.z, ratio);
+          col_dirty = true;
+        }
+      }
       if (sem >= 0 && has_label_img && label < static_cast<uint32_t>(L)) {
         const size_t si = static_cast<size_t>(sem) * V + lin;
         if (!row_resident) {  // bring the voxel's likelihood row on chip (or start it)
@@ -558,6 +600,9 @@ __global__ void __launch_bounds__(kFuseThreads, KB_FUSE_MIN_BLOCKS) fuseKernel(c
     // ---- write the voxel back once; block flags + per-(block, frame) update bookkeeping ----
     if (have) {
       m.tsdf[gi] = st;
+      if constexpr (COLOR) {
+        if (col_dirty) m.color[gi] = col;
+      }
       if (p.with_tracking) {
         m.last_obs[gi] = lobs;
         m.vflags[gi] = static_cast<uint8_t>(vfl | (st.x < p.occ_thr ? 0 : kVoxNotOccupied));
@@ -725,6 +770,7 @@ __global__ void __launch_bounds__(kThreads) resetInactiveKernel(const DeviceMap 
     m.last_obs[base + lin] = 0;
     m.last_occ[base + lin] = 0;
     m.vflags[base + lin] = 0;
+    if (m.color) m.color[base + lin] = make_uchar4(0, 0, 0, 0);
     if (sem >= 0) m.sem_label[static_cast<size_t>(sem) * V + lin] = kSemEmpty;
   }
   if (threadIdx.x == 0) {
@@ -874,6 +920,15 @@ __global__ void gatherTrackingKernel(const DeviceMap m, const TrackEval ev, cons
   }
 }
 
+__global__ void gatherColorKernel(const DeviceMap m, const int* slots, uint8_t* rgb) {
+  const int V = m.V, slot = slots[blockIdx.x];
+  for (int lin = threadIdx.x; lin < V; lin += blockDim.x) {
+    const uchar4 c = m.color[static_cast<size_t>(slot) * V + lin];
+    uint8_t* o = rgb + (static_cast<size_t>(blockIdx.x) * V + lin) * 3;
+    o[0] = c.x; o[1] = c.y; o[2] = c.z;
+  }
+}
+
 __global__ void gatherSemanticKernel(const DeviceMap m, const int* slots, int L, uint32_t* label,
                                      uint8_t* empty, float* lik) {
   const int V = m.V, slot = slots[blockIdx.x];
@@ -916,15 +971,19 @@ void launchSelectBlocks(const DeviceMap& m, const BatchParams& p, int cull_grid,
 static size_t fuseSmemBytes(int Lp) { return static_cast<size_t>(std::max(Lp, 2)) * kFuseThreads * sizeof(float); }
 int fuseBlocksPerSm(int vps, int Lp) {
   int n = 0;
-  if (vps == 16) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fuseKernel<16, 1, false>, kFuseThreads, fuseSmemBytes(Lp));
-  else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fuseKernel<8, 1, false>, kFuseThreads, fuseSmemBytes(Lp));
+  if (vps == 16) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fuseKernel<16, 1, false, false>, kFuseThreads, fuseSmemBytes(Lp));
+  else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fuseKernel<8, 1, false, false>, kFuseThreads, fuseSmemBytes(Lp));
   return n > 0 ? n : 4;
 }
 void launchFuse(const DeviceMap& m, const BatchParams& p, int grid, cudaStream_t s) {
   if (grid <= 0) return;
   const size_t smem = fuseSmemBytes(m.Lp);
-  const bool one = p.layers_per_item == 1, c = p.compact_taps != 0;
-#define KB_FUSE(V, LP, C) fuseKernel<V, LP, C><<<grid, kFuseThreads, smem, s>>>(m, p)
+  const bool one = p.layers_per_item == 1, c = p.compact_taps != 0, col = p.has_color != 0 && m.color != nullptr;
+#define KB_FUSE(V, LP, C)                                                                        \
+  do {                                                                                           \
+    if (col) fuseKernel<V, LP, C, true><<<grid, kFuseThreads, smem, s>>>(m, p);                  \
+    else fuseKernel<V, LP, C, false><<<grid, kFuseThreads, smem, s>>>(m, p);                     \
+  } while (0)
   if (m.vps == 16) {
     if (one) { if (c) KB_FUSE(16, 1, true); else KB_FUSE(16, 1, false); }
     else { if (c) KB_FUSE(16, 4, true); else KB_FUSE(16, 4, false); }
@@ -967,6 +1026,9 @@ void launchGatherTracking(const DeviceMap& m, const TrackEval& ev, const int* sl
                           unsigned long long* last_occ, uint8_t* ever_free, uint8_t* active, uint8_t* to_remove,
                           uint8_t* block_active, cudaStream_t s) {
   if (n > 0) gatherTrackingKernel<<<n, 256, 0, s>>>(m, ev, slots, stamps, last_obs, last_occ, ever_free, active, to_remove, block_active);
+}
+void launchGatherColor(const DeviceMap& m, const int* slots, int n, uint8_t* rgb, cudaStream_t s) {
+  if (n > 0) gatherColorKernel<<<n, 256, 0, s>>>(m, slots, rgb);
 }
 void launchGatherSemantic(const DeviceMap& m, const int* slots, int n, int L, uint32_t* label, uint8_t* empty,
                           float* lik, cudaStream_t s) {

@@ -15,6 +15,7 @@ struct FrameView {
   const int* label;
   const int* mask;
   const int* object_image;
+  const uint8_t* color;  // H*W*3 RGB (InputData::color_image, CV_8UC3) or null
   float* tiles;   // per-frame depth max-pyramid (levels concatenated, see BatchParams::lvl_*)
   const uint16_t* depth16;  // compact inputs (device pointers) expanded into depth / label by expandFramesKernel
   const uint8_t* label8;
@@ -49,6 +50,7 @@ struct BatchParams {
   int parity;          // which of the two work-list counters this batch uses
   int compact_taps;    // 1: every frame of the batch is compact (u16 depth, u8/no labels): kernels convert per tap
   int cull;            // 1: conservative depth culling enabled
+  int has_color;       // 1: some frame of the batch carries a colour image (selects the colour-blending fuse kernel)
   int lvl_tx[kTileLevels], lvl_ty[kTileLevels], lvl_off[kTileLevels];  // pyramid level dims / offsets
   int* work_slots;     // [max_work] selected block slots
   uint32_t* work_masks;  // [max_work] bit b set: block is processed for frame b of the batch
@@ -101,6 +103,7 @@ void launchGatherTracking(const DeviceMap& m, const TrackEval& ev, const int* sl
                           const unsigned long long* stamps, unsigned long long* last_obs,
                           unsigned long long* last_occ, uint8_t* ever_free, uint8_t* active, uint8_t* to_remove,
                           uint8_t* block_active, cudaStream_t s);
+void launchGatherColor(const DeviceMap& m, const int* slots, int n, uint8_t* rgb, cudaStream_t s);
 void launchGatherSemantic(const DeviceMap& m, const int* slots, int n, int L, uint32_t* label,
                           uint8_t* empty, float* lik, cudaStream_t s);
 

@@ -98,7 +98,7 @@ inline kb_frame makeFrame(const hydra::InputData& data, const cv::Mat* mask, con
   f.label = data.label_image.empty() ? nullptr : data.label_image.ptr<int32_t>();
   f.mask = (mask && !mask->empty()) ? mask->ptr<int32_t>() : nullptr;
   f.object_image = (object_image && !object_image->empty()) ? object_image->ptr<int32_t>() : nullptr;
-  f.color = nullptr;
+  f.color = data.color_image.empty() ? nullptr : data.color_image.ptr<uint8_t>();  // CV_8UC3, RGB
   f.vertex_world = data.vertex_map.empty() ? nullptr : data.vertex_map.ptr<float>();
   const auto T = data.getSensorPose();
 #ifdef KB_HAVE_HYDRA
@@ -227,11 +227,13 @@ inline void mirrorBack(GpuVolumetricMap& gmap, hydra::VolumetricMap& host, bool 
   std::vector<float> dist(n * V), weight(n * V), lik(n * V * L);
   std::vector<uint64_t> lo(n * V), lc(n * V);
   std::vector<uint32_t> sl(n * V);
+  std::vector<uint8_t> rgb(n * V * 3);
   kb_block_export ex{};
   ex.block_index = index.data(); ex.block_flags = flags.data(); ex.distance = dist.data(); ex.weight = weight.data();
   ex.last_observed = lo.data(); ex.last_occupied = lc.data(); ex.ever_free = ef.data(); ex.active = ac.data();
   ex.to_remove = tr.data(); ex.semantic_label = sl.data(); ex.semantic_empty = se.data();
   ex.semantic_likelihoods = L ? lik.data() : nullptr;
+  ex.color = rgb.data();
   int32_t nw = 0;
   check(kb_export_blocks(h, which, n, &ex, &nw), h, "kb_export_blocks");
   for (int b = 0; b < nw; ++b) {
@@ -239,7 +241,11 @@ inline void mirrorBack(GpuVolumetricMap& gmap, hydra::VolumetricMap& host, bool 
     auto tb = host.getTsdfLayer().allocateBlock(bi, V);
     tb->updated = flags[b] & KB_FLAG_UPDATED; tb->mesh_updated = flags[b] & KB_FLAG_MESH_UPDATED;
     tb->esdf_updated = flags[b] & KB_FLAG_ESDF_UPDATED; tb->tracking_updated = flags[b] & KB_FLAG_TRACKING_UPDATED;
-    for (size_t i = 0; i < V; ++i) { tb->voxels[i].distance = dist[b * V + i]; tb->voxels[i].weight = weight[b * V + i]; }
+    for (size_t i = 0; i < V; ++i) {
+      auto& v = tb->voxels[i];
+      v.distance = dist[b * V + i]; v.weight = weight[b * V + i];
+      std::memcpy(v.color, &rgb[(b * V + i) * 3], 3);
+    }
     if (auto* tl = host.getTrackingLayer()) {
       auto kb_ = tl->allocateBlock(bi, V);
       kb_->has_active_data = flags[b] & KB_FLAG_HAS_ACTIVE_DATA;

@@ -181,6 +181,19 @@ def render(scene: Scene, cam: Camera, pose: np.ndarray, t_s: float = 0.0, device
             label.reshape(H, W).to(torch.int32).contiguous())
 
 
+def colorize(label, depth=None) -> np.ndarray:
+    """Deterministic textured RGB image (H, W, 3) u8 for a label image: a per-label base colour plus a
+    pixel-dependent pattern, so that bilinear colour interpolation and blending are exercised. Pixels with
+    invalid depth are black. Input generation only (InputData::color_image, CV_8UC3)."""
+    lab = np.asarray(label).astype(np.int64)
+    H, W = lab.shape
+    v, u = np.meshgrid(np.arange(H, dtype=np.int64), np.arange(W, dtype=np.int64), indexing="ij")
+    rgb = np.stack([(lab * 37 + 3 * u + 5 * v) % 256, (lab * 91 + 7 * u + v) % 256, (lab * 53 + u + 11 * v) % 256], axis=-1)
+    if depth is not None:
+        rgb = np.where((np.asarray(depth) > 0)[..., None], rgb, 0)
+    return np.ascontiguousarray(rgb.astype(np.uint8))
+
+
 def companion_cuboids(poses, start_frame=60, distance=2.2, size=(1.05, 1.05, 1.6), sway=0.8, period=120):
     """Config 3 dynamic object: an axis-aligned box that stays `distance` metres in front of the camera
     (swaying sideways), appearing after `start_frame` frames of burn-in. At 2.2 m a 1.05 x 1.6 m face covers

@@ -212,6 +212,23 @@ int32_t Oracle::interpolateID(const int32_t* img, const Weights& w) const {
   return img[(w.v + dv) * W + w.u + du];
 }
 
+void Oracle::interpolateColor(const uint8_t* rgb, const Weights& w, uint8_t out[3]) const {
+  const int W = cam_.width;
+  const uint8_t* p0 = rgb + (static_cast<size_t>(w.v) * W + w.u) * 3;
+  if (!w.bilinear) {
+    out[0] = p0[0]; out[1] = p0[1]; out[2] = p0[2];
+    return;
+  }
+  const uint8_t* p1 = p0 + static_cast<size_t>(W) * 3;  // (u, v+1)
+  const uint8_t* p2 = p0 + 3;                            // (u+1, v)
+  const uint8_t* p3 = p1 + 3;                            // (u+1, v+1)
+  for (int ch = 0; ch < 3; ++ch) {
+    const float s = ((w.w[0] * static_cast<float>(p0[ch]) + w.w[1] * static_cast<float>(p1[ch])) +
+                     w.w[2] * static_cast<float>(p2[ch])) + w.w[3] * static_cast<float>(p3[ch]);
+    out[ch] = static_cast<uint8_t>(static_cast<int>(s));
+  }
+}
+
 float Oracle::computeWeight(float depth, float sdf) const {
   // UP App. A.6 step 4: ray density fx*fy*vs^2/z^2, optional 1/z^2, linear drop-off behind surface.
   const float vs = map_.voxel_size;
@@ -358,6 +375,19 @@ void Oracle::updateBlock(Block& b, const kb_frame& f, const float R[9], const fl
     ++n_valid;
     if (!in_band) continue;
     ++n_band;
+    // colour (UP App. A.6 step 5 / updateVoxel): only near the surface, only with a colour image.
+    // interpolateColor: nearest -> that pixel; bilinear -> per channel ((w0 c0 + w1 c1) + w2 c2) + w3 c3,
+    // truncated to u8. Color::merge with ratio = w_m / (w_old + w_m): c = u8(c (1 - ratio) + c_m ratio).
+    if (f.color) {
+      uint8_t cm[3];
+      interpolateColor(f.color, w, cm);
+      const float tot = w_old + wm;
+      const float ratio = tot > 0.f ? wm / tot : 0.f;
+      for (int ch = 0; ch < 3; ++ch) {
+        uint8_t& c = b.color[static_cast<size_t>(lin) * 3 + ch];
+        c = static_cast<uint8_t>(static_cast<int>(static_cast<float>(c) * (1.f - ratio) + static_cast<float>(cm[ch]) * ratio));
+      }
+    }
     if (have_label && label < static_cast<uint32_t>(L_)) {  // isValidLabel
       if (b.likelihoods.empty()) b.likelihoods.assign(static_cast<size_t>(V_) * L_, 0.f);
       float* lik = &b.likelihoods[static_cast<size_t>(lin) * L_];

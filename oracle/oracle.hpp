@@ -120,6 +120,7 @@ class Oracle {
   Weights computeWeights(float u, float v, const float* range) const;
   float interpolateRange(const float* range, const Weights& w) const;
   int32_t interpolateID(const int32_t* img, const Weights& w) const;
+  void interpolateColor(const uint8_t* rgb, const Weights& w, uint8_t out[3]) const;
   bool project(const float p_C[3], float* u, float* v) const;
   float computeWeight(float depth, float sdf) const;
   bool pointInFrustum(const float p_C[3], float inflation) const;

@@ -72,9 +72,30 @@ def dynamic_case(lib):
     return out
 
 
+def colour_case(lib):
+    """K1 colour path: 6 orbit frames, the third one without a colour image."""
+    cam = golden_camera()
+    scene = syn.room_scene()
+    poses, stamps = syn.orbit_trajectory(6, laps=0.06)
+    frames = hs.render_frames(scene, cam, poses, stamps)
+    cols = [syn.colorize(l, d) for d, l in frames]
+    has = np.array([1, 1, 0, 1, 1, 1], np.uint8)
+    h = hs.make_handle(lib, "ko_", cam=cam)
+    hs.run_fusion(h, frames, poses, stamps, colors=[c if k else None for c, k in zip(cols, has)])
+    out = {"depth": np.stack([f[0] for f in frames]), "label": np.stack([f[1] for f in frames]),
+           "color": np.stack(cols), "has_color": has, "poses": np.stack(poses), "stamps": np.array(stamps, np.uint64)}
+    b = h.export_blocks()
+    out.update(pack_blocks(b, "b_"))
+    out["b_color"] = b.color
+    return out
+
+
 if __name__ == "__main__":
     lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "liboracle.so"))
-    for name, fn in (("fusion", fusion_case), ("dynamic", dynamic_case)):
+    cases = (("fusion", fusion_case), ("dynamic", dynamic_case), ("colour", colour_case))
+    for name, fn in cases:
+        if len(sys.argv) > 1 and name not in sys.argv[1:]:
+            continue
         data = fn(lib)
         path = os.path.join(HERE, f"{name}.npz")
         np.savez_compressed(path, **data)

@@ -36,11 +36,12 @@ def render_frames(scene, cam, poses, stamps):
     return out
 
 
-def run_fusion(h, frames, poses, stamps, tracking=False, masks=None):
+def run_fusion(h, frames, poses, stamps, tracking=False, masks=None, colors=None):
     stats = []
     for i, ((d, l), T, st) in enumerate(zip(frames, poses, stamps)):
         m = None if masks is None else masks[i]
-        f = h.make_frame(d, T, st, label=l, mask=m)
+        c = None if colors is None else colors[i]
+        f = h.make_frame(d, T, st, label=l, mask=m, color=c)
         stats.append(h.integrate_frame(f).as_dict())
         if tracking:
             h.update_tracking(st)
@@ -53,7 +54,7 @@ def assert_blocks_equal(a: capi.Blocks, b: capi.Blocks, rtol=1e-4, exact_float=F
     np.testing.assert_array_equal(a.block_index, b.block_index, err_msg=f"{what} block_index")
     np.testing.assert_array_equal(a.block_flags, b.block_flags, err_msg=f"{what} block_flags")
     for name in ("last_observed", "last_occupied", "ever_free", "active", "to_remove",
-                 "semantic_label", "semantic_empty"):
+                 "semantic_label", "semantic_empty", "color"):
         np.testing.assert_array_equal(getattr(a, name), getattr(b, name), err_msg=f"{what} {name}")
     if exact_float:
         np.testing.assert_array_equal(a.distance.view(np.uint32), b.distance.view(np.uint32), err_msg=f"{what} distance bits")

@@ -52,12 +52,27 @@ def run_dynamic_case(lib, prefix):
     check_blocks(g, h.export_blocks())
 
 
+def run_colour_case(lib, prefix):
+    g = np.load(os.path.join(GOLD, "colour.npz"))
+    h = hs.make_handle(lib, prefix, cam=golden_camera())
+    for i in range(len(g["stamps"])):
+        d, l, c = (np.ascontiguousarray(g[k][i]) for k in ("depth", "label", "color"))
+        h.integrate_frame(h.make_frame(d, g["poses"][i], int(g["stamps"][i]), label=l, color=c if g["has_color"][i] else None))
+    b = h.export_blocks()
+    check_blocks(g, b)
+    np.testing.assert_array_equal(g["b_color"], b.color)
+
+
 def test_oracle_matches_golden_fusion(oracle_lib):
     run_fusion_case(oracle_lib, "ko_")
 
 
 def test_oracle_matches_golden_dynamic(oracle_lib):
     run_dynamic_case(oracle_lib, "ko_")
+
+
+def test_oracle_matches_golden_colour(oracle_lib):
+    run_colour_case(oracle_lib, "ko_")
 
 
 def test_oracle_is_thread_count_invariant(oracle_lib):

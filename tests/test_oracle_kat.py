@@ -291,3 +291,91 @@ def test_motion_seed_and_cluster_known_answer(oracle_lib):
     assert len(cl) == 1 and len(cl[0]["pixels"]) >= 64
     assert (cl[0]["voxels"][:, 2] == 12).all()  # global z index of 1.25 m at 0.1 m voxels
     np.testing.assert_allclose(cl[0]["bbox"][[2, 5]], [1.25, 1.25])
+
+
+@pytest.mark.parametrize("interp", [capi.INTERP_NEAREST, capi.INTERP_ADAPTIVE])
+def test_colour_blend_known_answer(oracle_lib, interp):
+    """ORACLE_SPEC §5.6: interpolateColor + Color::merge, restated independently in numpy fp32 (identity pose,
+    flat wall, three frames with different textured colour images)."""
+    cam = syn.make_camera(64, 48, 32.0, 32.0, max_range=3.0)
+    mc = capi.default_map_config(voxel_size=0.1, vps=8, trunc=0.3)
+    ic = capi.default_integrator_config(interpolation=interp, num_threads=1)
+    h = hs.make_handle(oracle_lib, "ko_", map_cfg=mc, integ_cfg=ic, cam=cam)
+    D = 2.0
+    d, _ = flat_wall(cam, D)
+    labs = [np.full((cam.height, cam.width), k, np.int32) for k in (3, 9, 4)]
+    cols = [syn.colorize(l, d) for l in labs]
+    for k, (l, c) in enumerate(zip(labs, cols)):
+        h.integrate_frame(h.make_frame(d, np.eye(4), 1_000_000_000 + k, label=l, color=c))
+    b = h.export_blocks()
+    assert b.color.any()
+    W, H = cam.width, cam.height
+    vps, vs, trunc = 8, F32(0.1), F32(0.3)
+    bs = F32(vs * F32(vps))
+    checked = 0
+    eps = F32(0.1)
+    for i, bidx in enumerate(b.block_index):
+        expect = np.zeros((vps ** 3, 3), np.uint8)
+        for j in range(vps ** 3):
+            vx, vy, vz = j % vps, (j // vps) % vps, j // (vps * vps)
+            px = F32(F32(bidx[0]) * bs + F32(F32(F32(vx) + F32(0.5)) * vs))
+            py = F32(F32(bidx[1]) * bs + F32(F32(F32(vy) + F32(0.5)) * vs))
+            pz = F32(F32(bidx[2]) * bs + F32(F32(F32(vz) + F32(0.5)) * vs))
+            if pz <= 0:
+                continue
+            u = F32(F32(F32(cam.fx) * px) / pz + F32(cam.cx))
+            v = F32(F32(F32(cam.fy) * py) / pz + F32(cam.cy))
+            if u < 0 or u > W - 1 or v < 0 or v > H - 1:
+                continue
+            u0, v0 = int(np.floor(u)), int(np.floor(v))
+            bil = interp == capi.INTERP_ADAPTIVE and u0 + 1 < W and v0 + 1 < H  # flat wall: taps valid and equal
+            if bil:
+                du, dv = F32(u - F32(u0)), F32(v - F32(v0))
+                w4 = [F32(F32(F32(1) - du) * F32(F32(1) - dv)), F32(F32(F32(1) - du) * dv), F32(du * F32(F32(1) - dv)), F32(du * dv)]
+                rng = F32(F32(F32(w4[0] * F32(D)) + F32(w4[1] * F32(D))) + F32(w4[2] * F32(D)))
+                rng = F32(rng + F32(w4[3] * F32(D)))
+            else:
+                rng = F32(D)
+                # np.round is half-to-even, std::round half-away: the flat-wall coordinates avoid exact halves
+                un, vn = int(np.floor(u + F32(0.5))), int(np.floor(v + F32(0.5)))
+            sdf = F32(rng - pz)
+            if sdf < -trunc or not abs(sdf) < trunc:
+                continue
+            wm = F32(F32(F32(cam.fx) * F32(cam.fy)) * F32(vs * vs) / F32(pz * pz))
+            wm = F32(wm / F32(pz * pz))
+            if sdf < -eps:
+                wm = F32(max(F32(wm * F32(F32(trunc + sdf) / F32(trunc - eps))), F32(0)))
+            w_old = F32(0)
+            c = np.zeros(3, np.uint8)
+            for img in cols:
+                if bil:
+                    taps = [img[v0, u0], img[v0 + 1, u0], img[v0, u0 + 1], img[v0 + 1, u0 + 1]]
+                    cm = np.zeros(3, np.uint8)
+                    for ch in range(3):
+                        sc = F32(F32(F32(w4[0] * F32(taps[0][ch])) + F32(w4[1] * F32(taps[1][ch]))) + F32(w4[2] * F32(taps[2][ch])))
+                        sc = F32(sc + F32(w4[3] * F32(taps[3][ch])))
+                        cm[ch] = int(sc)
+                else:
+                    cm = img[vn, un]
+                ratio = F32(wm / F32(w_old + wm))
+                for ch in range(3):
+                    c[ch] = int(F32(F32(F32(c[ch]) * F32(F32(1) - ratio)) + F32(F32(cm[ch]) * ratio)))
+                w_old = F32(w_old + wm)
+            expect[j] = c
+            checked += 1
+        np.testing.assert_array_equal(b.color[i], expect, err_msg=f"block {bidx}")
+    assert checked > 300
+
+
+def test_colour_is_left_alone_without_colour_image(oracle_lib):
+    cam = syn.make_camera(64, 48, 32.0, 32.0, max_range=3.0)
+    mc = capi.default_map_config(voxel_size=0.1, vps=8, trunc=0.3)
+    h = hs.make_handle(oracle_lib, "ko_", map_cfg=mc, cam=cam)
+    d, l = flat_wall(cam, 2.0)
+    c = syn.colorize(l, d)
+    h.integrate_frame(h.make_frame(d, np.eye(4), 1_000_000_000, label=l, color=c))
+    before = h.export_blocks().color.copy()
+    h.integrate_frame(h.make_frame(d, np.eye(4), 1_000_000_001, label=l))  # no colour image: TSDF only
+    after = h.export_blocks()
+    np.testing.assert_array_equal(before, after.color)
+    assert before.any() and (after.weight > 0).any()
