@@ -45,7 +45,10 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=32, help="frames per kb_integrate_frames call (1 = per-frame calls)")
     ap.add_argument("--lap-frames", type=int, default=5000, help="frames in one lap of the trajectory (pool in HBM)")
     ap.add_argument("--max-blocks", type=int, default=90000)
-    ap.add_argument("--cpu-sample-frames", type=int, default=96)
+    ap.add_argument("--cpu-sample-frames", type=int, default=5000,
+                    help="upper bound on the frames of the cpu_baseline sample (it stops after --cpu-sample-seconds)")
+    ap.add_argument("--cpu-sample-seconds", type=float, default=12.0, help="CPU work of the cpu_baseline sample")
+    ap.add_argument("--ref-frames-per-step", type=int, default=256, help="--impl reference: frames per step")
     ap.add_argument("--e2e-frames", type=int, default=512)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cull", action="store_true", help="disable the conservative depth culling (results identical)")
@@ -138,20 +141,34 @@ def map_configs(args):
 
 def run_cpu(args, cam, frames_host, poses, stamps, n_frames, threads=-1):
     """Times the oracle port on host cores over frames [0, n_frames). Returns (fps, cores, seconds)."""
+    fps, cores, dt, _ = run_cpu_stream(args, cam, lambda i, k: (frames_host[0][i:i + k], frames_host[1][i:i + k]),
+                                       poses, stamps, n_frames, float("inf"), threads)
+    return fps, cores, dt
+
+
+def run_cpu_stream(args, cam, chunk_fn, poses, stamps, max_frames, budget_s, threads=-1, chunk=128):
+    """Oracle port over consecutive frames from the start of the stream into an empty map, fetched in chunks
+    (chunk_fn(i, k) -> host depth/label arrays of frames [i, i+k)) until `budget_s` seconds of integration time
+    or `max_frames` frames. Only the integrate calls are timed. Returns (fps, cores, seconds, frames)."""
     from khronos_b200 import capi
     lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "liboracle.so"))
     mc, ic = map_configs(args)
     ic.num_threads = threads
     h = capi.MapHandle(lib, "ko_", mc, ic, capi.default_tracking_config(), None)
     h.set_camera(cam)
-    fr = [h.make_frame(frames_host[0][i], poses[i], stamps[i], label=frames_host[1][i]) for i in range(n_frames)]
-    t0 = time.perf_counter()
-    for f in fr:
-        h.integrate_frame(f, want_stats=False)
-    dt = time.perf_counter() - t0
+    n, dt = 0, 0.0
+    while n < max_frames and dt < budget_s:
+        k = min(chunk, max_frames - n)
+        d, l = chunk_fn(n, k)
+        fr = [h.make_frame(d[j], poses[n + j], stamps[n + j], label=l[j]) for j in range(k)]
+        t0 = time.perf_counter()
+        for f in fr:
+            h.integrate_frame(f, want_stats=False)
+        dt += time.perf_counter() - t0
+        n += k
     cores = os.cpu_count() if threads <= 0 else threads
     h.close()
-    return n_frames / dt, cores, dt
+    return n / dt, cores, dt, n
 
 
 def best_cpu_threads(args, cam, frames_host, poses, sel, n_probe=12):
@@ -177,7 +194,7 @@ def main_reference(args):
     import torch
     from khronos_b200 import synthetic as syn
     cam, scene, poses, stamps = workload(args)
-    per_step = max(4, min(32, args.cpu_sample_frames // 3))
+    per_step = max(4, args.ref_frames_per_step if not args.small else 8)
     n = per_step * (args.steps + args.warmup)
     stride = 1  # a contiguous chunk of the same stream (same inter-frame overlap as the GPU arm sees)
     sel = [i % len(poses) for i in range(n)]
@@ -575,16 +592,20 @@ def main():
     # ---- CPU baseline on a bounded sample of the same stream (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        n_c = min(args.cpu_sample_frames, lap)
-        if compact:  # the CPU arm gets the same frames, expanded the same way (float(u16) * 0.001f, int32(u8))
-            fh = ((depth[:n_c].cpu().numpy().astype(np.float32) * np.float32(0.001)), label[:n_c].cpu().numpy().astype(np.int32))
-        else:
-            fh = (depth[:n_c].cpu().numpy(), label[:n_c].cpu().numpy())
-        nt = best_cpu_threads(args, cam, fh, poses, list(range(n_c)))
-        cfps, cores, secs = run_cpu(args, cam, fh, poses, stamps, n_c, threads=nt)
+        n_c = min(args.cpu_sample_frames, lap) if not args.small else min(96, lap)
+
+        def host_chunk(i, k):  # the CPU arm gets the same frames (compact: expanded the same way, float(u16) * 0.001f)
+            d, l = depth[i:i + k].cpu().numpy(), label[i:i + k].cpu().numpy()
+            if compact:
+                d, l = d.astype(np.float32) * np.float32(0.001), l.astype(np.int32)
+            return d, l
+
+        probe = host_chunk(0, 12)
+        nt = best_cpu_threads(args, cam, probe, poses, list(range(12)))
+        cfps, cores, secs, n_done = run_cpu_stream(args, cam, host_chunk, poses, stamps, n_c, args.cpu_sample_seconds, threads=nt)
         cpu = {"value": cfps, "unit": "frames/s", "cores": cores, "kind": "port",
-               "sample": f"first {n_c} frames of the lap into an empty map, oracle port, {secs:.1f}s, best of a "
-                         f"thread-count sweep up to {os.cpu_count()} host threads"}
+               "sample": f"first {n_done} frames of the lap into an empty map, oracle port, {secs:.1f} s of integration, "
+                         f"best of a thread-count sweep up to {os.cpu_count()} host threads"}
 
     if rank == 0:
         total = h.get_totals()
