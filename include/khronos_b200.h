@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define KB_ABI_VERSION 2
+#define KB_ABI_VERSION 3
 
 typedef enum kb_status {
   KB_OK = 0,
@@ -253,6 +253,40 @@ int kb_allocate_box(kb_handle* h, const int32_t min_block[3], const int32_t max_
  * distance = +truncation. */
 int kb_scan_object_confidence(kb_handle* h, float min_confidence, int32_t min_observations,
                               int32_t* n_erased);
+
+/* ---- sharded per-frame pipeline (new in this build; SURVEY.md §8e exchange steps 1 and 2) -----------------------
+ * With kb_set_shard(rank, nranks > 1) a handle holds only the blocks it owns. Fusion (K0/K1/K1b), K2, K2r and K4 are
+ * independent per block and need nothing else. Two steps of ActiveWindow::spinOnce look across blocks:
+ *   M1 (free_space_motion_detector.cpp:158-203) asks the block of every pixel's endpoint whether that voxel is
+ *      ever-free: only the owner knows  ->  per-pixel flag bytes, MAX-all-reduced over the ranks;
+ *   K3 (tracking_integrator.cpp:168-222) reads the 6/18/26 neighbours of every voxel of an updated block, across
+ *      block borders  ->  the owners publish 1 bit per voxel ("ever_free || voxelIsFree at this pass", exactly the
+ *      predicate K3 evaluates on neighbours) for the blocks that neighbour another rank's updated blocks.
+ * The collectives themselves (2 all-gathers, 1 all-reduce per frame) are issued by the host program between these
+ * calls (khronos_b200/distributed.py uses torch.distributed / NCCL) on buffers of the sizes kb_shard_buffer_sizes
+ * reports; all buffer arguments are DEVICE pointers on the handle's stream (make it the stream the collectives
+ * are ordered with via kb_set_stream). Buffer layouts: struct ShardExchange in csrc/kb_kernels.cuh. Lists that
+ * do not fit raise capacity_exceeded (reported by the next stats / totals read). */
+int kb_set_shard_capacity(kb_handle* h, int32_t pending_capacity, int32_t halo_capacity); /* blocks per rank and pass; default 1024 / 2048 */
+int kb_shard_buffer_sizes(kb_handle* h, int64_t* pending_bytes, int64_t* halo_bytes, int64_t* pixel_flag_bytes);
+/* K2 on the local shard (TrackingIntegrator::updateBlockTracking, tracking_integrator.cpp:133-166) + export of this
+ * rank's ever-free work list (the tracking_updated blocks, :75-77) into pending_out. */
+int kb_tracking_begin(kb_handle* h, uint64_t stamp_ns, void* pending_out);
+/* all_pending = the nranks pending buffers concatenated in rank order (all-gather). Writes the free masks of the
+ * locally owned blocks that neighbour another rank's pending block into halo_out. */
+int kb_tracking_pack_halo(kb_handle* h, const void* all_pending, void* halo_out);
+/* all_halo = the nranks halo buffers concatenated. K3 (updateBlockEverFree, :168-222) on the local pending blocks;
+ * must stay valid until the stream has run the pass. Completes the pass kb_tracking_begin opened. */
+int kb_tracking_finish(kb_handle* h, const void* all_pending, const void* all_halo);
+/* M1 on the local shard: pixel_flags[H*W] (device) gets bit0 = the pixel is in this rank's point map (its block
+ * exists here and the voxel index is valid), bit1 = that voxel is ever-free (a seed). */
+int kb_motion_lookup_local(kb_handle* h, const kb_frame* frame, uint8_t* pixel_flags);
+/* pixel_flags after the MAX all-reduce: M2-M4 run replicated (and deterministically) on every rank; the dynamic
+ * image stays on the device for KB_MASK_LAST_DETECTION. Enqueue only. */
+int kb_motion_cluster_global(kb_handle* h, const uint8_t* pixel_flags);
+/* Synchronises the handle's stream and returns the last detection's counts (+ the dynamic image to host memory if
+ * dynamic_image_out != NULL). */
+int kb_motion_result(kb_handle* h, int32_t* dynamic_image_out, int32_t* n_seeds, int32_t* n_clusters);
 
 /* ---- mirror-back / parity export ---------------------------------------------------------------- */
 

@@ -307,6 +307,40 @@ class MapHandle:
         self._last_nc = nc.value
         return img, ns.value, nc.value
 
+    # ---- sharded per-frame pipeline (include/khronos_b200.h "sharded per-frame pipeline"); buffers are torch
+    # tensors / raw pointers in the library's memory space (device for the product)
+    def set_shard_capacity(self, pending_capacity: int, halo_capacity: int):
+        self._check(self._fn("set_shard_capacity")(self._h, int(pending_capacity), int(halo_capacity)))
+
+    def shard_buffer_sizes(self):
+        a, b, c = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        self._check(self._fn("shard_buffer_sizes")(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def tracking_begin(self, stamp_ns: int, pending_out):
+        self._check(self._fn("tracking_begin")(self._h, C.c_uint64(int(stamp_ns)), C.c_void_p(_ptr(pending_out))))
+
+    def tracking_pack_halo(self, all_pending, halo_out):
+        self._check(self._fn("tracking_pack_halo")(self._h, C.c_void_p(_ptr(all_pending)), C.c_void_p(_ptr(halo_out))))
+
+    def tracking_finish(self, all_pending, all_halo):
+        self._check(self._fn("tracking_finish")(self._h, C.c_void_p(_ptr(all_pending)), C.c_void_p(_ptr(all_halo))))
+
+    def motion_lookup_local(self, frame: Frame, pixel_flags):
+        self._check(self._fn("motion_lookup_local")(self._h, C.byref(frame), C.c_void_p(_ptr(pixel_flags))))
+
+    def motion_cluster_global(self, pixel_flags):
+        self._check(self._fn("motion_cluster_global")(self._h, C.c_void_p(_ptr(pixel_flags))))
+
+    def motion_result(self, want_image=True):
+        H, W = self._camera.height, self._camera.width
+        img = np.zeros((H, W), np.int32) if want_image else None
+        ns, nc = C.c_int32(0), C.c_int32(0)
+        self._check(self._fn("motion_result")(self._h, C.c_void_p(img.ctypes.data) if want_image else None,
+                                              C.byref(ns), C.byref(nc)))
+        self._last_nc = nc.value
+        return img, ns.value, nc.value
+
     def get_motion_clusters(self):
         tp, tv = C.c_int32(0), C.c_int32(0)
         f = self._fn("get_motion_clusters")

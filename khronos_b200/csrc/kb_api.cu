@@ -90,6 +90,12 @@ struct kb_handle {
   bool motion_have_image = false;
   int3* d_removed = nullptr;
   int max_removed = 0;
+  // sharded per-frame pipeline (kb_tracking_begin / pack_halo / finish, kb_motion_lookup_local / cluster_global)
+  ShardExchange xch{};
+  int cap_pending = 1024, cap_halo = 2048;
+  TrackingParams open_pass{};   // parameters of the pass between kb_tracking_begin and kb_tracking_finish
+  uint64_t open_pass_stamp = 0;
+  int open_pass_state = 0;      // 0 none, 1 begun, 2 halo packed
   std::string err;
 };
 
@@ -152,6 +158,28 @@ int ensureColorStaging(kb_handle* h, size_t pixels) {
   h->stg_color = nullptr;
   KB_CUDA(h, devAlloc(&h->stg_color, pixels * 3 * kMaxBatch * 2, 0));
   h->stg_color_pixels = pixels;
+  return KB_OK;
+}
+
+int ensureShardBuffers(kb_handle* h) {
+  ShardExchange& x = h->xch;
+  if (x.halo_mark && x.nranks == h->nranks && x.cap_pending == h->cap_pending && x.cap_halo == h->cap_halo) {
+    x.rank = h->rank;
+    return KB_OK;
+  }
+  KB_CUDA(h, cudaStreamSynchronize(h->stream));
+  cudaFree(x.halo_mark); cudaFree(x.publish); cudaFree(x.ghost_keys); cudaFree(x.ghost_vals);
+  x = ShardExchange{};
+  x.rank = h->rank; x.nranks = h->nranks;
+  x.cap_pending = h->cap_pending; x.cap_halo = h->cap_halo;
+  x.mask_words = h->dm.V / 32;
+  uint32_t cap = 1024;
+  while (cap < 2u * static_cast<uint32_t>(x.nranks) * static_cast<uint32_t>(x.cap_halo)) cap <<= 1;
+  x.ghost_mask = cap - 1;
+  KB_CUDA(h, devAlloc(&x.halo_mark, static_cast<size_t>(h->dm.max_blocks), 0));
+  KB_CUDA(h, devAlloc(&x.publish, static_cast<size_t>(x.cap_halo), 0));
+  KB_CUDA(h, devAlloc(&x.ghost_keys, static_cast<size_t>(cap), 0xFF));
+  KB_CUDA(h, devAlloc(&x.ghost_vals, static_cast<size_t>(cap), 0));
   return KB_OK;
 }
 
@@ -422,6 +450,7 @@ int kb_destroy(kb_handle* h) {
   cudaFree(m.tsdf); cudaFree(m.last_obs); cudaFree(m.last_occ); cudaFree(m.vflags);
   cudaFree(m.born_frame); cudaFree(m.next_pass); cudaFree(m.act_min); cudaFree(h->pending);
   cudaFree(m.sem_label); cudaFree(m.sem_lik); cudaFree(m.color); cudaFree(h->stg_color);
+  cudaFree(h->xch.halo_mark); cudaFree(h->xch.publish); cudaFree(h->xch.ghost_keys); cudaFree(h->xch.ghost_vals);
   cudaFree(h->stg_depth); cudaFree(h->stg_label); cudaFree(h->stg_mask); cudaFree(h->stg_object);
   cudaFree(h->stg_vertex); cudaFree(h->d_pixel_gidx); cudaFree(h->d_pixel_seed); cudaFree(h->d_removed);
   cudaFree(h->d_dynamic);
@@ -742,7 +771,8 @@ int kb_get_totals(kb_handle* h, kb_frame_stats* t) {
   return KB_OK;
 }
 
-static int updateTrackingImpl(kb_handle* h, uint64_t stamp_ns) {
+// Parameters of the tracking pass at `stamp_ns` (no launch, no state change besides the stamp table).
+static int trackingParams(kb_handle* h, uint64_t stamp_ns, TrackingParams* out) {
   if (stamp_ns <= h->last_pass_stamp) return fail(h, KB_ERR_STATE, "tracking stamps must increase");
   uint32_t fidx = 0;
   int st = frameIndex(h, stamp_ns, &fidx);
@@ -774,6 +804,17 @@ static int updateTrackingImpl(kb_handle* h, uint64_t stamp_ns) {
   p.connectivity = h->trk.neighbor_connectivity;
   p.n_slots = h->dm.max_blocks;
   p.pending = h->pending;
+  p.rank = h->rank;
+  p.nranks = h->nranks;
+  *out = p;
+  return KB_OK;
+}
+
+static int updateTrackingImpl(kb_handle* h, uint64_t stamp_ns) {
+  if (h->open_pass_state != 0) return fail(h, KB_ERR_STATE, "a sharded tracking pass is open (kb_tracking_finish missing)");
+  TrackingParams p{};
+  int st = trackingParams(h, stamp_ns, &p);
+  if (st != KB_OK) return st;
   launchTrackingPass(h->dm, p, h->everfree_grid, h->stream);
   KB_CUDA(h, cudaGetLastError());
   h->pass = p.ev;
@@ -786,6 +827,70 @@ int kb_update_tracking(kb_handle* h, uint64_t stamp_ns) {
   if (!h->has_trk || !h->map.with_tracking) return fail(h, KB_ERR_STATE, "tracking not configured");
   KB_CUDA(h, cudaSetDevice(h->device));
   return updateTrackingImpl(h, stamp_ns);
+}
+
+int kb_set_shard_capacity(kb_handle* h, int32_t pending_capacity, int32_t halo_capacity) {
+  if (!h || pending_capacity <= 0 || halo_capacity <= 0) return fail(h, KB_ERR_INVALID, "invalid shard capacity");
+  if (h->open_pass_state != 0) return fail(h, KB_ERR_STATE, "a sharded tracking pass is open");
+  h->cap_pending = pending_capacity;
+  h->cap_halo = halo_capacity;
+  return KB_OK;
+}
+
+int kb_shard_buffer_sizes(kb_handle* h, int64_t* pending_bytes, int64_t* halo_bytes, int64_t* pixel_flag_bytes) {
+  if (!h) return KB_ERR_INVALID;
+  ShardExchange x{};
+  x.cap_pending = h->cap_pending; x.cap_halo = h->cap_halo; x.mask_words = h->dm.V / 32;
+  if (pending_bytes) *pending_bytes = static_cast<int64_t>(x.pending_stride()) * 4;
+  if (halo_bytes) *halo_bytes = static_cast<int64_t>(x.halo_stride()) * 4;
+  if (pixel_flag_bytes) *pixel_flag_bytes = h->has_cam ? static_cast<int64_t>(h->cam.width) * h->cam.height : 0;
+  return KB_OK;
+}
+
+int kb_tracking_begin(kb_handle* h, uint64_t stamp_ns, void* pending_out) {
+  if (!h || !pending_out) return fail(h, KB_ERR_INVALID, "null argument");
+  if (!h->has_trk || !h->map.with_tracking) return fail(h, KB_ERR_STATE, "tracking not configured");
+  if (h->open_pass_state != 0) return fail(h, KB_ERR_STATE, "kb_tracking_begin: the previous pass was not finished");
+  KB_CUDA(h, cudaSetDevice(h->device));
+  int st = ensureShardBuffers(h);
+  if (st != KB_OK) return st;
+  TrackingParams p{};
+  if ((st = trackingParams(h, stamp_ns, &p)) != KB_OK) return st;
+  launchTrackingBegin(h->dm, p, h->xch, static_cast<int32_t*>(pending_out), h->stream);
+  KB_CUDA(h, cudaGetLastError());
+  h->open_pass = p;
+  h->open_pass_stamp = stamp_ns;
+  h->open_pass_state = 1;
+  return KB_OK;
+}
+
+int kb_tracking_pack_halo(kb_handle* h, const void* all_pending, void* halo_out) {
+  if (!h || !all_pending || !halo_out) return fail(h, KB_ERR_INVALID, "null argument");
+  if (h->open_pass_state != 1) return fail(h, KB_ERR_STATE, "kb_tracking_pack_halo needs kb_tracking_begin first");
+  KB_CUDA(h, cudaSetDevice(h->device));
+  launchHaloPack(h->dm, h->open_pass, h->xch, static_cast<const int32_t*>(all_pending), static_cast<int32_t*>(halo_out), h->stream);
+  KB_CUDA(h, cudaGetLastError());
+  h->open_pass_state = 2;
+  return KB_OK;
+}
+
+int kb_tracking_finish(kb_handle* h, const void* all_pending, const void* all_halo) {
+  if (!h || !all_pending || !all_halo) return fail(h, KB_ERR_INVALID, "null argument");
+  if (h->open_pass_state != 2) return fail(h, KB_ERR_STATE, "kb_tracking_finish needs kb_tracking_pack_halo first");
+  KB_CUDA(h, cudaSetDevice(h->device));
+  TrackingParams p = h->open_pass;
+  p.ghost_bits = static_cast<const int32_t*>(all_halo);
+  p.ghost_keys = h->xch.ghost_keys;
+  p.ghost_vals = h->xch.ghost_vals;
+  p.ghost_mask = h->xch.ghost_mask;
+  launchTrackingFinish(h->dm, p, h->xch, static_cast<const int32_t*>(all_pending), static_cast<const int32_t*>(all_halo),
+                       h->everfree_grid, h->stream);
+  KB_CUDA(h, cudaGetLastError());
+  h->pass = p.ev;
+  h->last_pass_stamp = h->open_pass_stamp;
+  h->open_pass_state = 0;
+  h->ctr_dirty = true;
+  return KB_OK;
 }
 
 int kb_reset_inactive(kb_handle* h, int32_t* removed_xyz, int32_t max_removed, int32_t* n_removed) {
@@ -870,7 +975,7 @@ int kb_scan_object_confidence(kb_handle* h, float min_confidence, int32_t min_ob
 
 // M1 launch shared by kb_detect_motion and kb_spin_once: stages depth / vertex map, resets the seed counter,
 // enqueues the per-pixel lookup and records the host parameters for lazily built cluster lists.
-static int enqueueMotionLookup(kb_handle* h, const kb_frame* f) {
+static int enqueueMotionLookup(kb_handle* h, const kb_frame* f, uint8_t* shard_flags = nullptr) {
   const kb_camera& c = h->cam;
   const size_t px = static_cast<size_t>(c.width) * c.height;
   MotionParams p{};
@@ -894,8 +999,10 @@ static int enqueueMotionLookup(kb_handle* h, const kb_frame* f) {
   if ((st = stage(h, f->vertex_world, h->stg_vertex, px * 3, f->memory, &p.vertex)) != KB_OK) return st;
   p.pixel_gidx = h->d_pixel_gidx;
   p.pixel_seed = h->d_pixel_seed;
+  p.pixel_flags = shard_flags;
   KB_CUDA(h, cudaMemsetAsync(h->dm.counters + kCtrSeeds, 0, sizeof(int), h->stream));
-  launchMotionLookup(h->dm, p, h->stream);
+  if (shard_flags) launchMotionLookupLocal(h->dm, p, h->stream);  // seeds are counted after the cross-rank reduce
+  else launchMotionLookup(h->dm, p, h->stream);
   KB_CUDA(h, cudaGetLastError());
   // keep the depth image on the device for lazily built cluster lists (bounding boxes)
   if (f->memory == KB_MEM_DEVICE && p.depth != h->mot_depth)
@@ -997,6 +1104,45 @@ int kb_spin_once(kb_handle* h, const kb_frame* f, int32_t* dynamic_image_out, in
   g.mask = KB_MASK_LAST_DETECTION;
   if ((st = kb_integrate_frames(h, &g, 1, 1, nullptr)) != KB_OK) return st;
   if ((st = updateTrackingImpl(h, f->stamp_ns)) != KB_OK) return st;
+  KB_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (h->h_mscal[kMsRoots] > h->mt.max_roots) return fail(h, KB_ERR_CAPACITY, "too many motion clusters for the device path");
+  h->motion.n_seeds = h->h_mscal[kMsSeeds];
+  h->motion_stale = h->h_mscal[kMsClusters] > 0;
+  if (n_seeds) *n_seeds = h->h_mscal[kMsSeeds];
+  if (n_clusters) *n_clusters = h->h_mscal[kMsClusters];
+  return KB_OK;
+}
+
+int kb_motion_lookup_local(kb_handle* h, const kb_frame* f, uint8_t* pixel_flags) {
+  if (!h || !f || (!f->depth && !f->depth_u16) || !pixel_flags) return fail(h, KB_ERR_INVALID, "null argument");
+  if (!h->has_mot || !h->map.with_tracking) return fail(h, KB_ERR_STATE, "motion detector not configured");
+  if (!h->has_cam) return fail(h, KB_ERR_STATE, "kb_set_camera must be called first");
+  if (!(h->mot.min_separation_distance > 0.f) || f->vertex_world != nullptr)
+    return fail(h, KB_ERR_STATE, "the sharded motion path needs min_separation_distance > 0 and no caller-supplied vertex map");
+  KB_CUDA(h, cudaSetDevice(h->device));
+  return enqueueMotionLookup(h, f, pixel_flags);
+}
+
+int kb_motion_cluster_global(kb_handle* h, const uint8_t* pixel_flags) {
+  if (!h || !pixel_flags) return fail(h, KB_ERR_INVALID, "null argument");
+  if (!h->has_mot || !h->has_cam) return fail(h, KB_ERR_STATE, "motion detector not configured");
+  KB_CUDA(h, cudaSetDevice(h->device));
+  const size_t px = static_cast<size_t>(h->cam.width) * h->cam.height;
+  launchMotionFinalize(h->dm, pixel_flags, h->d_pixel_gidx, h->d_pixel_seed, static_cast<int>(px), h->stream);
+  KB_CUDA(h, cudaGetLastError());
+  int st = enqueueDeviceClustering(h);
+  if (st != KB_OK) return st;
+  h->motion_have_image = true;
+  return KB_OK;
+}
+
+int kb_motion_result(kb_handle* h, int32_t* dynamic_image_out, int32_t* n_seeds, int32_t* n_clusters) {
+  if (!h) return KB_ERR_INVALID;
+  if (!h->motion_have_image) return fail(h, KB_ERR_STATE, "no motion detection result");
+  KB_CUDA(h, cudaSetDevice(h->device));
+  const size_t px = static_cast<size_t>(h->cam.width) * h->cam.height;
+  if (dynamic_image_out)
+    KB_CUDA(h, cudaMemcpyAsync(dynamic_image_out, h->d_dynamic, sizeof(int32_t) * px, cudaMemcpyDeviceToHost, h->stream));
   KB_CUDA(h, cudaStreamSynchronize(h->stream));
   if (h->h_mscal[kMsRoots] > h->mt.max_roots) return fail(h, KB_ERR_CAPACITY, "too many motion clusters for the device path");
   h->motion.n_seeds = h->h_mscal[kMsSeeds];

@@ -77,6 +77,7 @@ enum Counter {
   kCtrPairs = 17,  // (block, frame) pairs that survived K0 culling
   kCtrPending = 18,  // ever-free work list length of the current tracking pass
   kCtrFetch = 19,    // dynamic work cursor of the fuse kernel
+  kCtrHalo = 20,     // sharded ever-free pass: locally owned blocks whose free masks are published this pass
   kNumCounters = 24
 };
 

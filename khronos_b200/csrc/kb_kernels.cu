@@ -690,6 +690,21 @@ __device__ __forceinline__ bool voxelFreeNow(const DeviceMap& m, const TrackEval
 // (taken from the 26 neighbour blocks, resolved once into shared memory) is first materialised in shared
 // memory by all threads in parallel; the 6/18/26-neighbourhood test of every candidate voxel then only reads
 // shared memory, instead of chasing up to 18 dependent global loads per candidate.
+// SHARD: neighbour blocks owned by another rank are not in the local hash; their predicate bits come from the
+// all-gathered halo masks (ShardExchange), found through the ghost table; s_nbr then holds -(2 + word offset).
+__device__ __forceinline__ int ghostLookup(const TrackingParams& p, int x, int y, int z) {
+  const unsigned long long key = packKey(x, y, z);
+  uint32_t h = static_cast<uint32_t>(mix64(key)) & p.ghost_mask;
+  for (uint32_t probe = 0; probe <= p.ghost_mask; ++probe) {
+    const unsigned long long k = p.ghost_keys[h];
+    if (k == key) return p.ghost_vals[h];
+    if (k == kEmptyKey) return -1;
+    h = (h + 1) & p.ghost_mask;
+  }
+  return -1;
+}
+
+template <bool SHARD>
 __global__ void __launch_bounds__(kThreads) everFreeKernel(const DeviceMap m, const TrackingParams p) {
   __shared__ int s_nbr[27];
   __shared__ uint8_t s_free[18 * 18 * 18];  // bit0: free or ever-free, bit1: ever-free (halo of the largest block)
@@ -701,7 +716,12 @@ __global__ void __launch_bounds__(kThreads) everFreeKernel(const DeviceMap m, co
     if (threadIdx.x < 27) {
       const int3 bi = m.block_index[slot];
       const int dx = threadIdx.x % 3 - 1, dy = (threadIdx.x / 3) % 3 - 1, dz = threadIdx.x / 9 - 1;
-      s_nbr[threadIdx.x] = (dx == 0 && dy == 0 && dz == 0) ? slot : hashLookup(m, bi.x + dx, bi.y + dy, bi.z + dz);
+      int ns = (dx == 0 && dy == 0 && dz == 0) ? slot : hashLookup(m, bi.x + dx, bi.y + dy, bi.z + dz);
+      if (SHARD && ns < 0 && blockOwner(bi.x + dx, bi.y + dy, bi.z + dz, p.nranks) != p.rank) {
+        const int off = ghostLookup(p, bi.x + dx, bi.y + dy, bi.z + dz);
+        if (off >= 0) ns = -(2 + off);
+      }
+      s_nbr[threadIdx.x] = ns;
     }
     __syncthreads();
     for (int i = threadIdx.x; i < hs * hs * hs; i += kThreads) {
@@ -716,6 +736,9 @@ __global__ void __launch_bounds__(kThreads) everFreeKernel(const DeviceMap m, co
         const size_t idx = static_cast<size_t>(ns) * V + (x + vps * (y + vps * z));
         const uint8_t f = m.vflags[idx];
         v = (voxelFreeNow(m, p.ev, idx, f) ? 1 : 0) | ((f & kVoxEverFree) ? 2 : 0);
+      } else if (SHARD && ns <= -2) {  // remote neighbour: bit of its published mask (halo voxels only need bit 0)
+        const int lin = x + vps * (y + vps * z);
+        v = (static_cast<uint32_t>(__ldg(&p.ghost_bits[(-ns - 2) + (lin >> 5)])) >> (lin & 31)) & 1u;
       }
       s_free[i] = v;
     }
@@ -740,6 +763,99 @@ __global__ void __launch_bounds__(kThreads) everFreeKernel(const DeviceMap m, co
 
 // Resets the ever-free work counter after K3 (separate tiny launch: K3's CTAs all read it).
 __global__ void resetPendingKernel(const DeviceMap m) { m.counters[kCtrPending] = 0; }
+
+// ---- sharded K2/K3 exchange (buffer layouts: ShardExchange in kb_kernels.cuh) ----------
+// Exports this rank's ever-free work list as block indices.
+__global__ void exportPendingKernel(const DeviceMap m, const int* __restrict__ pending, int32_t* __restrict__ out, int cap) {
+  const int n = m.counters[kCtrPending];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) {
+    out[0] = min(n, cap);
+    out[1] = n > cap ? 1 : 0;
+    out[2] = out[3] = 0;
+    m.counters[kCtrHalo] = 0;
+  }
+  if (i < min(n, cap)) {
+    const int3 bi = m.block_index[pending[i]];
+    out[4 + 3 * i] = bi.x; out[4 + 3 * i + 1] = bi.y; out[4 + 3 * i + 2] = bi.z;
+  }
+}
+
+// One thread per (rank r != me, pending block i of r, neighbour offset k): if the neighbour is owned by this rank
+// and exists, its slot joins the publish list (once).
+__global__ void haloMarkKernel(const DeviceMap m, const ShardExchange x, const int32_t* __restrict__ all_pending) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int per_rank = x.cap_pending * 27;
+  if (t >= x.nranks * per_rank) return;
+  const int r = t / per_rank, i = (t % per_rank) / 27, k = t % 27;
+  if (r == x.rank || k == 13) return;
+  const int32_t* __restrict__ buf = all_pending + static_cast<size_t>(r) * x.pending_stride();
+  if (i >= buf[0]) return;
+  const int bx = buf[4 + 3 * i] + (k % 3 - 1), by = buf[4 + 3 * i + 1] + ((k / 3) % 3 - 1), bz = buf[4 + 3 * i + 2] + (k / 9 - 1);
+  if (blockOwner(bx, by, bz, x.nranks) != x.rank) return;
+  const int slot = hashLookup(m, bx, by, bz);
+  if (slot < 0) return;
+  if (atomicExch(&x.halo_mark[slot], 1) != 0) return;
+  const int j = atomicAdd(&m.counters[kCtrHalo], 1);
+  if (j < x.cap_halo) x.publish[j] = slot;
+}
+
+// One CTA per published block: 1 bit per voxel = "ever_free || voxelIsFree at this pass" (the K3 neighbour predicate).
+__global__ void __launch_bounds__(kThreads) haloPackKernel(const DeviceMap m, const TrackingParams p, const ShardExchange x,
+                                                           int32_t* __restrict__ out) {
+  const int n_all = m.counters[kCtrHalo];
+  const int n = min(n_all, x.cap_halo);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    out[0] = n;
+    out[1] = n_all > x.cap_halo ? 1 : 0;
+    out[2] = out[3] = 0;
+  }
+  const int V = m.V;
+  for (int j = blockIdx.x; j < n_all; j += gridDim.x) {
+    const int slot = j < x.cap_halo ? x.publish[j] : -1;
+    if (slot < 0) continue;
+    if (threadIdx.x == 0) x.halo_mark[slot] = 0;
+    int32_t* __restrict__ e = out + 4 + static_cast<size_t>(j) * x.halo_entry();
+    if (threadIdx.x == 0) {
+      const int3 bi = m.block_index[slot];
+      e[0] = bi.x; e[1] = bi.y; e[2] = bi.z; e[3] = 0;
+    }
+    const size_t base = static_cast<size_t>(slot) * V;
+    for (int lin = threadIdx.x; lin < V; lin += kThreads) {  // V and kThreads are multiples of 32: full warps
+      const bool fr = voxelFreeNow(m, p.ev, base + lin, m.vflags[base + lin]);
+      const unsigned bits = __ballot_sync(0xffffffffu, fr);
+      if ((threadIdx.x & 31) == 0) e[4 + (lin >> 5)] = static_cast<int32_t>(bits);
+    }
+  }
+}
+
+// Overflowed publish lists leave marks behind: clear the marks of the slots that did not fit (rare; error path).
+__global__ void haloUnmarkKernel(const DeviceMap m, const ShardExchange x, int n_slots) {
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot < n_slots && m.counters[kCtrHalo] > x.cap_halo) x.halo_mark[slot] = 0;
+}
+
+// Builds the ghost table from the other ranks' halo buffers: block key -> word offset of its mask.
+__global__ void ghostBuildKernel(const DeviceMap m, const ShardExchange x, const int32_t* __restrict__ all_pending,
+                                 const int32_t* __restrict__ all_halo) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= x.nranks * x.cap_halo) return;
+  const int r = t / x.cap_halo, i = t % x.cap_halo;
+  const int32_t* __restrict__ buf = all_halo + static_cast<size_t>(r) * x.halo_stride();
+  if (i == 0 && (buf[1] != 0 || all_pending[static_cast<size_t>(r) * x.pending_stride() + 1] != 0))
+    atomicExch(&m.counters[kCtrCapacityExceeded], 1);  // a list did not fit its exchange buffer: results incomplete
+  if (r == x.rank || i >= buf[0]) return;
+  const int off = r * x.halo_stride() + 4 + i * x.halo_entry();
+  const unsigned long long key = packKey(all_halo[off], all_halo[off + 1], all_halo[off + 2]);
+  uint32_t h = static_cast<uint32_t>(mix64(key)) & x.ghost_mask;
+  for (uint32_t probe = 0; probe <= x.ghost_mask; ++probe) {
+    if (atomicCAS(&x.ghost_keys[h], kEmptyKey, key) == kEmptyKey) {  // keys are unique: each block has one owner
+      x.ghost_vals[h] = off + 4;
+      return;
+    }
+    h = (h + 1) & x.ghost_mask;
+  }
+}
 
 // ---- K2r: TrackingIntegrator::resetInactive (tracking_integrator.cpp:106-131) -----------------------
 __global__ void __launch_bounds__(kThreads) resetInactiveKernel(const DeviceMap m, const TrackEval ev, int3* removed, int max_removed) {
@@ -804,11 +920,16 @@ __global__ void clearUpdatedKernel(const DeviceMap m, int n) {
 }
 
 // ---- M1: FreeSpaceMotionDetector::setUpPointMapPart (free_space_motion_detector.cpp:158-203) --------
+// SHARD (block-hash sharded map): only the owner rank knows whether the pixel's block exists
+// and whether its voxel is ever-free, so the kernel writes the voxel index of every pixel with a valid index plus a
+// flag byte (bit0 block exists here, bit1 ever-free) that is MAX-reduced over the ranks; motionFinalizeKernel then
+// produces what the unsharded kernel writes directly.
+template <bool SHARD>
 __global__ void motionLookupKernel(const DeviceMap m, const __grid_constant__ MotionParams p) {
   const int px = blockIdx.x * blockDim.x + threadIdx.x;
   if (px >= p.W * p.H) return;
   int3 g = make_int3(INT_MIN, 0, 0);
-  uint8_t seed = 0;
+  uint8_t seed = 0, flags = 0;
   const float range = __ldg(&p.depth[px]);
   if (range > 0.f && range <= p.max_range) {
     float wx, wy, wz;
@@ -825,22 +946,44 @@ __global__ void motionLookupKernel(const DeviceMap m, const __grid_constant__ Mo
       const int by = static_cast<int>(floorf(wy * p.block_size_inv));
       const int bz = static_cast<int>(floorf(wz * p.block_size_inv));
       const int slot = hashLookup(m, bx, by, bz);
-      if (slot >= 0) {
+      if (SHARD || slot >= 0) {
         const int vps = m.vps;
         const int vx = static_cast<int>(floorf((wx - static_cast<float>(bx) * p.block_size) * p.voxel_size_inv));
         const int vy = static_cast<int>(floorf((wy - static_cast<float>(by) * p.block_size) * p.voxel_size_inv));
         const int vz = static_cast<int>(floorf((wz - static_cast<float>(bz) * p.block_size) * p.voxel_size_inv));
         if (vx >= 0 && vy >= 0 && vz >= 0 && vx < vps && vy < vps && vz < vps) {
           g = make_int3(bx * vps + vx, by * vps + vy, bz * vps + vz);
-          seed = (m.vflags[static_cast<size_t>(slot) * m.V + (vx + vps * (vy + vps * vz))] & kVoxEverFree) ? 1 : 0;
+          if (slot >= 0) {
+            seed = (m.vflags[static_cast<size_t>(slot) * m.V + (vx + vps * (vy + vps * vz))] & kVoxEverFree) ? 1 : 0;
+            flags = static_cast<uint8_t>(1 | (seed << 1));
+          }
         }
       }
     }
   }
   p.pixel_gidx[px] = g;
+  if (SHARD) {
+    p.pixel_flags[px] = flags;
+    return;
+  }
   p.pixel_seed[px] = seed;
   // one counter update per warp
   const unsigned ballot = __ballot_sync(__activemask(), seed != 0);
+  if (ballot && (threadIdx.x & 31) == (__ffs(ballot) - 1)) atomicAdd(&m.counters[kCtrSeeds], __popc(ballot));
+}
+
+// Sharded M1, second half: flags = MAX over the ranks of the per-rank flag bytes.
+__global__ void motionFinalizeKernel(const DeviceMap m, const uint8_t* __restrict__ flags, int3* __restrict__ gidx,
+                                     uint8_t* __restrict__ seed_out, int n) {
+  const int px = blockIdx.x * blockDim.x + threadIdx.x;
+  uint8_t seed = 0;
+  if (px < n) {
+    const uint8_t f = flags[px];
+    if (!(f & 1)) gidx[px] = make_int3(INT_MIN, 0, 0);  // no rank holds the pixel's block: not in the point map
+    seed = (f >> 1) & 1;
+    seed_out[px] = seed;
+  }
+  const unsigned ballot = __ballot_sync(0xffffffffu, seed != 0);  // n-tail threads stay in the warp (no early return)
   if (ballot && (threadIdx.x & 31) == (__ffs(ballot) - 1)) atomicAdd(&m.counters[kCtrSeeds], __popc(ballot));
 }
 
@@ -995,7 +1138,26 @@ void launchFuse(const DeviceMap& m, const BatchParams& p, int grid, cudaStream_t
 }
 void launchTrackingPass(const DeviceMap& m, const TrackingParams& p, int everfree_grid, cudaStream_t s) {
   trackingPassKernel<<<(std::max(p.n_slots, 1) + 255) / 256, 256, 0, s>>>(m, p);
-  everFreeKernel<<<everfree_grid, kThreads, 0, s>>>(m, p);
+  everFreeKernel<false><<<everfree_grid, kThreads, 0, s>>>(m, p);
+  resetPendingKernel<<<1, 1, 0, s>>>(m);
+}
+void launchTrackingBegin(const DeviceMap& m, const TrackingParams& p, const ShardExchange& x, int32_t* pending_out, cudaStream_t s) {
+  trackingPassKernel<<<(std::max(p.n_slots, 1) + 255) / 256, 256, 0, s>>>(m, p);
+  exportPendingKernel<<<(x.cap_pending + 255) / 256, 256, 0, s>>>(m, p.pending, pending_out, x.cap_pending);
+}
+void launchHaloPack(const DeviceMap& m, const TrackingParams& p, const ShardExchange& x, const int32_t* all_pending,
+                    int32_t* halo_out, cudaStream_t s) {
+  const int n = x.nranks * x.cap_pending * 27;
+  haloMarkKernel<<<(n + 255) / 256, 256, 0, s>>>(m, x, all_pending);
+  haloPackKernel<<<148 * 4, kThreads, 0, s>>>(m, p, x, halo_out);
+  haloUnmarkKernel<<<(m.max_blocks + 255) / 256, 256, 0, s>>>(m, x, m.max_blocks);
+}
+void launchTrackingFinish(const DeviceMap& m, const TrackingParams& p, const ShardExchange& x, const int32_t* all_pending,
+                          const int32_t* all_halo, int everfree_grid, cudaStream_t s) {
+  cudaMemsetAsync(x.ghost_keys, 0xFF, (static_cast<size_t>(x.ghost_mask) + 1) * sizeof(unsigned long long), s);
+  const int n = x.nranks * x.cap_halo;
+  ghostBuildKernel<<<(n + 255) / 256, 256, 0, s>>>(m, x, all_pending, all_halo);
+  everFreeKernel<true><<<everfree_grid, kThreads, 0, s>>>(m, p);
   resetPendingKernel<<<1, 1, 0, s>>>(m);
 }
 void launchResetInactive(const DeviceMap& m, const TrackEval& ev, int n, int3* removed, int max_removed, cudaStream_t s) {
@@ -1009,7 +1171,14 @@ void launchClearUpdated(const DeviceMap& m, int n, cudaStream_t s) {
 }
 void launchMotionLookup(const DeviceMap& m, const MotionParams& p, cudaStream_t s) {
   const int n = p.W * p.H;
-  motionLookupKernel<<<(n + 255) / 256, 256, 0, s>>>(m, p);
+  motionLookupKernel<false><<<(n + 255) / 256, 256, 0, s>>>(m, p);
+}
+void launchMotionLookupLocal(const DeviceMap& m, const MotionParams& p, cudaStream_t s) {
+  const int n = p.W * p.H;
+  motionLookupKernel<true><<<(n + 255) / 256, 256, 0, s>>>(m, p);
+}
+void launchMotionFinalize(const DeviceMap& m, const uint8_t* flags, int3* gidx, uint8_t* seed, int n, cudaStream_t s) {
+  motionFinalizeKernel<<<(n + 255) / 256, 256, 0, s>>>(m, flags, gidx, seed, n);
 }
 void launchAllocateBox(const DeviceMap& m, int3 lo, int3 dims, int rank, int nranks, uint32_t born, cudaStream_t s) {
   const int n = dims.x * dims.y * dims.z;

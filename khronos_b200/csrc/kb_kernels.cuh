@@ -68,6 +68,31 @@ struct TrackingParams {
   int connectivity;         // 6 | 18 | 26
   int n_slots;              // pool slots to scan
   int* pending;             // [max_blocks] ever-free work list (slots whose TSDF was updated since the last pass)
+  // sharded pass only (everFreeKernel<true>): free masks of neighbour blocks owned by other ranks
+  int rank, nranks;
+  const int32_t* ghost_bits;             // the all-gathered halo buffers (see ShardExchange)
+  const unsigned long long* ghost_keys;  // open-addressed block key -> int offset of the block's mask words
+  const int* ghost_vals;
+  uint32_t ghost_mask;
+};
+
+// Exchange buffers of the sharded tracking pass, all int32 words, one per rank, concatenated
+// by the all-gather:
+//   pending buffer  [0] count  [1] overflow  [2..3] 0   then count x (bx, by, bz)                  (4 + 3*cap_pending words)
+//   halo buffer     [0] count  [1] overflow  [2..3] 0   then count x (bx, by, bz, 0, V/32 mask words) (4 + cap_halo*(4 + V/32))
+// A mask bit is the K3 neighbour predicate "ever_free || voxelIsFree at this pass" of one voxel (linear index order).
+struct ShardExchange {
+  int rank, nranks;
+  int cap_pending, cap_halo;
+  int mask_words;            // V / 32
+  int* halo_mark;            // [max_blocks] 0/1: slot already in this pass's publish list
+  int* publish;              // [cap_halo] slots to publish
+  unsigned long long* ghost_keys;
+  int* ghost_vals;
+  uint32_t ghost_mask;
+  __host__ __device__ int pending_stride() const { return 4 + 3 * cap_pending; }
+  __host__ __device__ int halo_entry() const { return 4 + mask_words; }
+  __host__ __device__ int halo_stride() const { return 4 + cap_halo * halo_entry(); }
 };
 
 struct MotionParams {
@@ -80,6 +105,8 @@ struct MotionParams {
   const float* vertex;  // may be null -> computed from depth
   int3* pixel_gidx;     // out: global voxel index per pixel, x = INT_MIN if the pixel is dropped
   uint8_t* pixel_seed;  // out: 1 if the pixel's voxel is ever-free
+  uint8_t* pixel_flags; // sharded lookup only: bit0 = the pixel's block exists on this rank (pixel is in the point
+                        // map), bit1 = its voxel is ever-free; pixel_gidx is then written for every valid voxel index
 };
 
 void launchTileMax(const BatchParams& p, cudaStream_t s);
@@ -93,6 +120,17 @@ void launchResetInactive(const DeviceMap& m, const TrackEval& ev, int n_slots, i
 void launchMarkAllInactive(const DeviceMap& m, int n_slots, cudaStream_t s);
 void launchClearUpdated(const DeviceMap& m, int n_slots, cudaStream_t s);
 void launchMotionLookup(const DeviceMap& m, const MotionParams& p, cudaStream_t s);
+// Sharded M1: local lookup -> per-pixel flags; after the MAX all-reduce of the flags the
+// finalize kernel drops pixels no rank has a block for, writes the seed bytes and counts the seed pixels.
+void launchMotionLookupLocal(const DeviceMap& m, const MotionParams& p, cudaStream_t s);
+void launchMotionFinalize(const DeviceMap& m, const uint8_t* flags, int3* gidx, uint8_t* seed, int n, cudaStream_t s);
+// Sharded K2/K3: begin = K2 + export of the local ever-free work list; pack = free masks of local blocks that
+// neighbour other ranks' pending blocks; finish = ghost table + K3.
+void launchTrackingBegin(const DeviceMap& m, const TrackingParams& p, const ShardExchange& x, int32_t* pending_out, cudaStream_t s);
+void launchHaloPack(const DeviceMap& m, const TrackingParams& p, const ShardExchange& x, const int32_t* all_pending,
+                    int32_t* halo_out, cudaStream_t s);
+void launchTrackingFinish(const DeviceMap& m, const TrackingParams& p, const ShardExchange& x, const int32_t* all_pending,
+                          const int32_t* all_halo, int everfree_grid, cudaStream_t s);
 void launchAllocateBox(const DeviceMap& m, int3 lo, int3 dims, int rank, int nranks, uint32_t born, cudaStream_t s);
 void launchScanConfidence(const DeviceMap& m, float min_conf, float min_obs, float trunc, int n_slots,
                           cudaStream_t s);

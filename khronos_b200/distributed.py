@@ -35,3 +35,104 @@ def gather_block_indices(local_index: np.ndarray, world: int):
     out = [torch.zeros_like(buf) for _ in range(world)]
     dist.all_gather(out, buf)
     return [o[: int(s.item())].numpy() for o, s in zip(out, sizes)]
+
+
+# ---- sharded per-frame pipeline (SURVEY.md §8e exchange steps 1 and 2) ------------------------------------------
+
+class DistComm:
+    """Collectives of one rank of a torch.distributed job (NCCL on the GPU box, gloo in the CPU tests). Every method
+    takes / returns a list with this rank's single tensor so that LocalComm can stand in for it."""
+
+    def __init__(self, world: int, group=None):
+        self.world, self.group = world, group
+
+    def all_gather(self, bufs):
+        import torch
+        import torch.distributed as dist
+        (buf,) = bufs
+        out = torch.empty((self.world * buf.numel(),), dtype=buf.dtype, device=buf.device)
+        try:
+            dist.all_gather_into_tensor(out, buf, group=self.group)
+        except (RuntimeError, NotImplementedError):  # backends without the flat variant
+            parts = [torch.empty_like(buf) for _ in range(self.world)]
+            dist.all_gather(parts, buf, group=self.group)
+            out = torch.cat(parts)
+        return [out]
+
+    def all_reduce_max(self, bufs):
+        import torch.distributed as dist
+        dist.all_reduce(bufs[0], op=dist.ReduceOp.MAX, group=self.group)
+        return bufs
+
+
+class LocalComm:
+    """All shards live in this process (tests: S handles on one device): collectives become tensor ops."""
+
+    def all_gather(self, bufs):
+        import torch
+        cat = torch.cat([b.reshape(-1) for b in bufs]).contiguous()
+        return [cat] * len(bufs)
+
+    def all_reduce_max(self, bufs):
+        import torch
+        m = torch.stack(bufs).max(dim=0).values
+        for b in bufs:
+            b.copy_(m)
+        return bufs
+
+
+class ShardedActiveWindow:
+    """The per-frame active-window loop (ActiveWindow::spinOnce, khronos/src/active_window/active_window.cpp:127,
+    209-214: motion detection -> integration with the dynamic image as mask -> tracking update) over a block-hash
+    sharded map. `handles` are this process' shard handles — one per rank in a torch.distributed job (comm =
+    DistComm), or all of them for an in-process emulation (comm = LocalComm). Every handle must already be
+    configured (camera, kb_set_shard). Results: the union of the shards equals the unsharded map, and every rank
+    gets the same dynamic image (tests/test_sharded_pipeline.py, tests/test_multiproc_gloo.py).
+
+    Per frame: 1 all-reduce (H*W flag bytes) + 2 all-gathers (pending block list, free masks); no host round trip
+    before the final kb_motion_result."""
+
+    def __init__(self, handles, comm, device="cpu"):
+        import torch
+        self.handles, self.comm = list(handles), comm
+        self.device = torch.device(device)
+        pb, hb, fb = self.handles[0].shard_buffer_sizes()
+        mk = lambda nbytes, dt: [torch.zeros(nbytes // torch.empty((), dtype=dt).element_size(), dtype=dt, device=self.device)
+                                 for _ in self.handles]
+        self.pending, self.halo = mk(pb, torch.int32), mk(hb, torch.int32)
+        self.flags = mk(fb, torch.uint8)
+        self._keep = None
+        if self.device.type == "cuda":  # order the library's kernels with the collectives on torch's current stream
+            for h in self.handles:
+                h.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def spin_once(self, frames, want_image=True):
+        """frames: one kb_frame per local handle (the same images on every rank). Returns per handle
+        (dynamic image or None, n_seeds, n_clusters)."""
+        from . import capi
+        hs = self.handles
+        for h, f, fl in zip(hs, frames, self.flags):
+            h.motion_lookup_local(f, fl)
+        self.comm.all_reduce_max(self.flags)
+        for h, f, fl in zip(hs, frames, self.flags):
+            h.motion_cluster_global(fl)
+            g = capi.Frame.from_buffer_copy(f)
+            g.mask = capi.MASK_LAST_DETECTION
+            h.integrate_frame(g, want_stats=False)
+        return self.update_tracking([int(f.stamp_ns) for f in frames], want_image=want_image)
+
+    def update_tracking(self, stamps, want_image=False, with_motion_result=True):
+        """Sharded TrackingIntegrator::updateBlocks (tracking_integrator.cpp:71-104)."""
+        hs = self.handles
+        for h, st, pb in zip(hs, stamps, self.pending):
+            h.tracking_begin(st, pb)
+        all_pending = self.comm.all_gather(self.pending)
+        for h, ap, hb in zip(hs, all_pending, self.halo):
+            h.tracking_pack_halo(ap, hb)
+        all_halo = self.comm.all_gather(self.halo)
+        for h, ap, ah in zip(hs, all_pending, all_halo):
+            h.tracking_finish(ap, ah)
+        self._keep = (all_pending, all_halo)  # the ever-free kernel reads them asynchronously
+        if not with_motion_result:
+            return None
+        return [h.motion_result(want_image) for h in hs]

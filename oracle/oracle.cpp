@@ -296,6 +296,7 @@ void Oracle::integrateFrame(const kb_frame& f, bool allocate_blocks, kb_frame_st
           transform(R, t, c, cC);
           if (!pointInFrustum(cC, infl)) continue;
           const Idx3 idx{bx, by, bz};
+          if (nranks_ > 1 && blockOwner(idx, nranks_) != rank_) continue;  // block-hash shard (§8e)
           if (!getBlock(idx)) ++n_new;
           todo.push_back(allocateBlock(idx));
         }
@@ -441,7 +442,7 @@ void Oracle::updateBlockTracking(Block& b, uint64_t stamp, float thr) {
   b.has_active_data = any_active;
 }
 
-void Oracle::updateBlockEverFree(const Block& b, uint64_t stamp, std::vector<int>* to_set) const {
+void Oracle::updateBlockEverFree(const Block& b, uint64_t stamp, std::vector<int>* to_set, const GhostMap* ghosts) const {
   // tracking_integrator.cpp:168-222. The reference writes ever_free while other threads read it; the
   // outcome is order independent because a neighbour that became ever-free during this pass
   // necessarily satisfies voxelIsFree at this stamp. We therefore evaluate every voxel against the
@@ -459,8 +460,16 @@ void Oracle::updateBlockEverFree(const Block& b, uint64_t stamp, std::vector<int
       if (ny < 0) { ny += vps_; --nb.y; } else if (ny >= vps_) { ny -= vps_; ++nb.y; }
       if (nz < 0) { nz += vps_; --nb.z; } else if (nz >= vps_) { nz -= vps_; ++nb.z; }
       const Block* nblk = (nb == b.index) ? &b : getBlock(nb);
-      if (!nblk) { blocked = true; break; }  // :198-202 missing neighbour block
       const int nlin = nx + vps_ * (ny + vps_ * nz);
+      if (!nblk && ghosts) {  // sharded: the neighbour block lives on another rank, which published this predicate
+        auto git = ghosts->find(nb);
+        if (git != ghosts->end()) {
+          if ((git->second[nlin >> 5] >> (nlin & 31)) & 1u) continue;
+          blocked = true;
+          break;
+        }
+      }
+      if (!nblk) { blocked = true; break; }  // :198-202 missing neighbour block
       if (nblk->ever_free[nlin]) continue;
       if (!voxelIsFree(*nblk, nlin, stamp)) { blocked = true; break; }
     }
@@ -468,8 +477,7 @@ void Oracle::updateBlockEverFree(const Block& b, uint64_t stamp, std::vector<int
   }
 }
 
-void Oracle::updateTracking(uint64_t stamp) {
-  if (!has_trk_ || !map_.with_tracking) { error_ = "tracking not configured"; return; }
+std::vector<Block*> Oracle::trackingPassLocal(uint64_t stamp) {
   // tracking_integrator.cpp:71-104: all blocks get the tracking pass, then blocks whose TSDF was
   // updated this frame get the ever-free pass.
   std::vector<Block*> all, updated;
@@ -482,11 +490,100 @@ void Oracle::updateTracking(uint64_t stamp) {
                         : trk_.tsdf_occupancy_threshold;
   const int nt = resolveThreads(trk_.num_threads);
   parallelFor(static_cast<int>(all.size()), nt, [&](int i) { updateBlockTracking(*all[i], stamp, thr); });
+  return updated;
+}
+
+void Oracle::applyEverFree(const std::vector<Block*>& updated, uint64_t stamp, const GhostMap* ghosts) {
+  const int nt = resolveThreads(trk_.num_threads);
   std::vector<std::vector<int>> to_set(updated.size());
   parallelFor(static_cast<int>(updated.size()), nt,
-              [&](int i) { updateBlockEverFree(*updated[i], stamp, &to_set[i]); });
+              [&](int i) { updateBlockEverFree(*updated[i], stamp, &to_set[i], ghosts); });
   for (size_t i = 0; i < updated.size(); ++i)
     for (int lin : to_set[i]) updated[i]->ever_free[lin] = 1;
+}
+
+void Oracle::updateTracking(uint64_t stamp) {
+  if (!has_trk_ || !map_.with_tracking) { error_ = "tracking not configured"; return; }
+  const std::vector<Block*> updated = trackingPassLocal(stamp);
+  applyEverFree(updated, stamp, nullptr);
+}
+
+// ---- sharded K2/K3 (buffer layouts: csrc/kb_kernels.cuh ShardExchange) ---------------------------------
+
+static inline uint64_t shardMix64(uint64_t k) {
+  k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
+  return k;
+}
+
+int Oracle::blockOwner(const Idx3& b, int nranks) {
+  // restates csrc/kb_device.cuh packKey/blockOwner: 21-bit biased coordinates, upper hash bits modulo nranks
+  if (nranks <= 1) return 0;
+  const uint64_t o = 1ull << 20, m = (1ull << 21) - 1ull;
+  const uint64_t key = ((static_cast<uint64_t>(static_cast<int64_t>(b.x) + static_cast<int64_t>(o)) & m)) |
+                       ((static_cast<uint64_t>(static_cast<int64_t>(b.y) + static_cast<int64_t>(o)) & m) << 21) |
+                       ((static_cast<uint64_t>(static_cast<int64_t>(b.z) + static_cast<int64_t>(o)) & m) << 42);
+  return static_cast<int>((shardMix64(key) >> 40) % static_cast<uint64_t>(nranks));
+}
+
+void Oracle::trackingBegin(uint64_t stamp, int32_t* out, int cap) {
+  if (!has_trk_ || !map_.with_tracking) { error_ = "tracking not configured"; return; }
+  open_pending_ = trackingPassLocal(stamp);
+  std::sort(open_pending_.begin(), open_pending_.end(), [](const Block* a, const Block* b) { return a->index < b->index; });
+  open_stamp_ = stamp;
+  const int n = static_cast<int>(open_pending_.size());
+  out[0] = std::min(n, cap); out[1] = n > cap ? 1 : 0; out[2] = out[3] = 0;
+  for (int i = 0; i < std::min(n, cap); ++i) {
+    out[4 + 3 * i] = open_pending_[i]->index.x; out[4 + 3 * i + 1] = open_pending_[i]->index.y; out[4 + 3 * i + 2] = open_pending_[i]->index.z;
+  }
+}
+
+void Oracle::packHalo(const int32_t* all_pending, int cap_pending, int32_t* out, int cap_halo) {
+  const int stride = 4 + 3 * cap_pending, W = V_ / 32, entry = 4 + W;
+  std::map<Idx3, const Block*> publish;  // ordered: deterministic buffer contents
+  for (int r = 0; r < nranks_; ++r) {
+    if (r == rank_) continue;
+    const int32_t* buf = all_pending + static_cast<size_t>(r) * stride;
+    for (int i = 0; i < buf[0]; ++i)
+      for (int k = 0; k < 27; ++k) {
+        if (k == 13) continue;
+        const Idx3 nb{buf[4 + 3 * i] + (k % 3 - 1), buf[4 + 3 * i + 1] + ((k / 3) % 3 - 1), buf[4 + 3 * i + 2] + (k / 9 - 1)};
+        if (blockOwner(nb, nranks_) != rank_) continue;
+        if (const Block* b = getBlock(nb)) publish.emplace(nb, b);
+      }
+  }
+  const int n = static_cast<int>(publish.size());
+  out[0] = std::min(n, cap_halo); out[1] = n > cap_halo ? 1 : 0; out[2] = out[3] = 0;
+  int j = 0;
+  for (const auto& kv : publish) {
+    if (j >= cap_halo) break;
+    int32_t* e = out + 4 + static_cast<size_t>(j) * entry;
+    e[0] = kv.first.x; e[1] = kv.first.y; e[2] = kv.first.z; e[3] = 0;
+    for (int w = 0; w < W; ++w) {
+      uint32_t bits = 0;
+      for (int b = 0; b < 32; ++b) {
+        const int lin = w * 32 + b;
+        if (kv.second->ever_free[lin] || voxelIsFree(*kv.second, lin, open_stamp_)) bits |= 1u << b;
+      }
+      e[4 + w] = static_cast<int32_t>(bits);
+    }
+    ++j;
+  }
+}
+
+void Oracle::trackingFinish(const int32_t* all_pending, int cap_pending, const int32_t* all_halo, int cap_halo) {
+  const int W = V_ / 32, entry = 4 + W, stride = 4 + cap_halo * entry;
+  GhostMap ghosts;
+  for (int r = 0; r < nranks_; ++r) {
+    const int32_t* buf = all_halo + static_cast<size_t>(r) * stride;
+    if (buf[1] != 0 || all_pending[static_cast<size_t>(r) * (4 + 3 * cap_pending) + 1] != 0) error_ = "shard exchange buffer overflow";
+    if (r == rank_) continue;
+    for (int i = 0; i < buf[0]; ++i) {
+      const int32_t* e = buf + 4 + static_cast<size_t>(i) * entry;
+      ghosts.emplace(Idx3{e[0], e[1], e[2]}, reinterpret_cast<const uint32_t*>(e + 4));
+    }
+  }
+  applyEverFree(open_pending_, open_stamp_, &ghosts);
+  open_pending_.clear();
 }
 
 void Oracle::resetInactive(std::vector<Idx3>* removed) {
@@ -515,15 +612,14 @@ void Oracle::clearUpdated() {
 
 // ---- M1 - M4 --------------------------------------------------------------------------------------------
 
-void Oracle::detectMotion(const kb_frame& f, int32_t* dynamic_image, int32_t* n_seeds_out,
-                          int32_t* n_clusters_out) {
-  if (!has_mot_ || !map_.with_tracking) { error_ = "motion detector not configured"; return; }
+// M1 is split into three steps so that the block-hash sharded protocol can exchange the
+// per-pixel "block exists / voxel ever-free" answers between ranks; unsharded, the three run back to back and
+// give exactly FreeSpaceMotionDetector::setUpPointMap (free_space_motion_detector.cpp:105-203).
+
+void Oracle::computePixelKeys(const kb_frame& f) {
   const int W = cam_.width, H = cam_.height;
   float R[9], t[3], Rw[9], tw[3];
   invertPose(f.world_T_sensor, R, t, Rw, tw);
-  std::memset(dynamic_image, 0, sizeof(int32_t) * W * H);
-  clusters_.clear();
-
   // vertex map in the world frame (hydra parseInputPacket, UP): back-project depth, then transform.
   const float* vertex = f.vertex_world;
   if (!vertex) {
@@ -537,9 +633,81 @@ void Oracle::detectMotion(const kb_frame& f, int32_t* dynamic_image, int32_t* n_
       }
     vertex = vertex_scratch_.data();
   }
-
-  // M1: setUpPointMap / setUpPointMapPart (free_space_motion_detector.cpp:105-203).
+  vertex_ = vertex;
   const float min_z_world = tw[2] + mot_.min_z_coordinate;  // :80
+  pix_keys_.assign(static_cast<size_t>(W) * H, PixKey{});
+  const int nt = std::max(1, std::min(resolveThreads(mot_.num_threads), W));
+  int u_step = W / nt;
+  if (u_step * nt < W) ++u_step;  // :112-115
+  std::vector<std::thread> threads;
+  for (int i = 0; i < nt; ++i) {
+    threads.emplace_back([&, i]() {
+      const int u_start = u_step * i, u_stop = std::min(u_step * (i + 1), W);
+      for (int v = 0; v < H; ++v)
+        for (int u = u_start; u < u_stop; ++u) {
+          const float range = f.depth[v * W + u];
+          if (range <= 0.f || range > mot_.max_range) continue;  // :169-172
+          const float* p = &vertex[(static_cast<size_t>(v) * W + u) * 3];
+          if (p[2] < min_z_world) continue;  // :176-178
+          const Idx3 bi{static_cast<int>(std::floor(p[0] * block_size_inv_)),
+                        static_cast<int>(std::floor(p[1] * block_size_inv_)),
+                        static_cast<int>(std::floor(p[2] * block_size_inv_))};
+          // block->getVoxelIndex(p): floor((p - origin) * voxel_size_inv), may be out of range.
+          const int vx = static_cast<int>(std::floor((p[0] - static_cast<float>(bi.x) * block_size_) * voxel_size_inv_));
+          const int vy = static_cast<int>(std::floor((p[1] - static_cast<float>(bi.y) * block_size_) * voxel_size_inv_));
+          const int vz = static_cast<int>(std::floor((p[2] - static_cast<float>(bi.z) * block_size_) * voxel_size_inv_));
+          // The reference appends the pixel under (block, voxel_index) before the validity check
+          // (:187-196); invalid indices can never be looked up again (keyFromGlobalIndex always
+          // yields valid voxel indices, :234), so such pixels never reach a cluster. We drop them.
+          if (vx < 0 || vy < 0 || vz < 0 || vx >= vps_ || vy >= vps_ || vz >= vps_) continue;
+          PixKey& k = pix_keys_[static_cast<size_t>(v) * W + u];
+          k.valid = true;
+          k.block = bi;
+          k.lin = vx + vps_ * (vy + vps_ * vz);
+          k.g = GIdx{static_cast<int64_t>(bi.x) * vps_ + vx, static_cast<int64_t>(bi.y) * vps_ + vy,
+                     static_cast<int64_t>(bi.z) * vps_ + vz};
+        }
+    });
+  }
+  for (auto& th : threads) th.join();
+}
+
+void Oracle::motionLookupLocal(const kb_frame& f, uint8_t* flags) {
+  if (!has_mot_ || !map_.with_tracking) { error_ = "motion detector not configured"; return; }
+  computePixelKeys(f);
+  // bit0: tracking_layer.getBlockPtr(p_W) exists (:180-183) -> the pixel is in the point map;
+  // bit1: that voxel is ever-free (:197-200) -> seed.
+  for (size_t px = 0; px < pix_keys_.size(); ++px) {
+    uint8_t fl = 0;
+    const PixKey& k = pix_keys_[px];
+    if (k.valid) {
+      if (const Block* blk = getBlock(k.block)) fl = static_cast<uint8_t>(1 | (blk->ever_free[k.lin] ? 2 : 0));
+    }
+    flags[px] = fl;
+  }
+}
+
+void Oracle::motionClusterGlobal(const uint8_t* flags, int32_t* dynamic_image, int32_t* n_seeds, int32_t* n_clusters) {
+  if (pix_keys_.size() != static_cast<size_t>(cam_.width) * cam_.height) { error_ = "motionLookupLocal must run first"; return; }
+  clusterFromFlags(flags, dynamic_image, n_seeds, n_clusters);
+}
+
+void Oracle::detectMotion(const kb_frame& f, int32_t* dynamic_image, int32_t* n_seeds_out,
+                          int32_t* n_clusters_out) {
+  if (!has_mot_ || !map_.with_tracking) { error_ = "motion detector not configured"; return; }
+  flags_scratch_.resize(static_cast<size_t>(cam_.width) * cam_.height);
+  motionLookupLocal(f, flags_scratch_.data());
+  clusterFromFlags(flags_scratch_.data(), dynamic_image, n_seeds_out, n_clusters_out);
+}
+
+void Oracle::clusterFromFlags(const uint8_t* flags, int32_t* dynamic_image, int32_t* n_seeds_out,
+                              int32_t* n_clusters_out) {
+  const int W = cam_.width, H = cam_.height;
+  const float* vertex = vertex_;
+  std::memset(dynamic_image, 0, sizeof(int32_t) * W * H);
+  clusters_.clear();
+
+  // setUpPointMap (:105-156): per-thread strip maps merged under a mutex.
   using VoxelPoints = std::unordered_map<GIdx, std::vector<Pixel>, GIdxHash>;
   VoxelPoints point_map;  // keyed by global voxel index of *valid* voxel indices
   std::unordered_set<GIdx, GIdxHash> seeds;
@@ -555,27 +723,10 @@ void Oracle::detectMotion(const kb_frame& f, int32_t* dynamic_image, int32_t* n_
       const int u_start = u_step * i, u_stop = std::min(u_step * (i + 1), W);
       for (int v = 0; v < H; ++v)
         for (int u = u_start; u < u_stop; ++u) {
-          const float range = f.depth[v * W + u];
-          if (range <= 0.f || range > mot_.max_range) continue;  // :169-172
-          const float* p = &vertex[(static_cast<size_t>(v) * W + u) * 3];
-          if (p[2] < min_z_world) continue;  // :176-178
-          const Idx3 bi{static_cast<int>(std::floor(p[0] * block_size_inv_)),
-                        static_cast<int>(std::floor(p[1] * block_size_inv_)),
-                        static_cast<int>(std::floor(p[2] * block_size_inv_))};
-          const Block* blk = getBlock(bi);
-          if (!blk) continue;  // :180-183
-          // block->getVoxelIndex(p): floor((p - origin) * voxel_size_inv), may be out of range.
-          const int vx = static_cast<int>(std::floor((p[0] - static_cast<float>(bi.x) * block_size_) * voxel_size_inv_));
-          const int vy = static_cast<int>(std::floor((p[1] - static_cast<float>(bi.y) * block_size_) * voxel_size_inv_));
-          const int vz = static_cast<int>(std::floor((p[2] - static_cast<float>(bi.z) * block_size_) * voxel_size_inv_));
-          // The reference appends the pixel under (block, voxel_index) before the validity check
-          // (:187-196); invalid indices can never be looked up again (keyFromGlobalIndex always
-          // yields valid voxel indices, :234), so such pixels never reach a cluster. We drop them.
-          if (vx < 0 || vy < 0 || vz < 0 || vx >= vps_ || vy >= vps_ || vz >= vps_) continue;
-          const GIdx g{static_cast<int64_t>(bi.x) * vps_ + vx, static_cast<int64_t>(bi.y) * vps_ + vy,
-                       static_cast<int64_t>(bi.z) * vps_ + vz};
-          local_map[g].push_back({u, v});
-          if (blk->ever_free[vx + vps_ * (vy + vps_ * vz)]) local_seeds.insert(g);  // :197-200
+          const size_t px = static_cast<size_t>(v) * W + u;
+          if (!pix_keys_[px].valid || !(flags[px] & 1)) continue;
+          local_map[pix_keys_[px].g].push_back({u, v});
+          if (flags[px] & 2) local_seeds.insert(pix_keys_[px].g);
         }
       std::lock_guard<std::mutex> lock(mtx);
       seeds.insert(local_seeds.begin(), local_seeds.end());
@@ -700,7 +851,10 @@ void Oracle::detectMotion(const kb_frame& f, int32_t* dynamic_image, int32_t* n_
 void Oracle::allocateBox(const int32_t mn[3], const int32_t mx[3]) {
   for (int x = mn[0]; x <= mx[0]; ++x)
     for (int y = mn[1]; y <= mx[1]; ++y)
-      for (int z = mn[2]; z <= mx[2]; ++z) allocateBlock(Idx3{x, y, z});
+      for (int z = mn[2]; z <= mx[2]; ++z) {
+        if (nranks_ > 1 && blockOwner(Idx3{x, y, z}, nranks_) != rank_) continue;
+        allocateBlock(Idx3{x, y, z});
+      }
 }
 
 int Oracle::scanObjectConfidence(float min_confidence, int min_observations) {

@@ -105,6 +105,17 @@ class Oracle {
   void allocateBox(const int32_t mn[3], const int32_t mx[3]);
   int scanObjectConfidence(float min_confidence, int min_observations);
 
+  // ---- block-hash sharded protocol (our multi-GPU design, not in the reference). The oracle
+  // implements it on host buffers with the layouts of csrc/kb_kernels.cuh::ShardExchange so that world-size-2
+  // gloo tests can prove "union of the shards == the unsharded map" on CPU.
+  void setShard(int rank, int nranks) { rank_ = rank; nranks_ = nranks; }
+  static int blockOwner(const Idx3& b, int nranks);
+  void motionLookupLocal(const kb_frame& f, uint8_t* flags);
+  void motionClusterGlobal(const uint8_t* flags, int32_t* dynamic_image, int32_t* n_seeds, int32_t* n_clusters);
+  void trackingBegin(uint64_t stamp_ns, int32_t* pending_out, int cap_pending);
+  void packHalo(const int32_t* all_pending, int cap_pending, int32_t* halo_out, int cap_halo);
+  void trackingFinish(const int32_t* all_pending, int cap_pending, const int32_t* all_halo, int cap_halo);
+
   std::vector<const Block*> sortedBlocks(int which) const;
   int V() const { return V_; }
   int L() const { return L_; }
@@ -131,7 +142,14 @@ class Oracle {
   void updateBlock(Block& b, const kb_frame& f, const float R[9], const float t[3],
                    std::atomic<int>* counters);
   void updateBlockTracking(Block& b, uint64_t stamp, float thr);
-  void updateBlockEverFree(const Block& b, uint64_t stamp, std::vector<int>* to_set) const;
+  using GhostMap = std::unordered_map<Idx3, const uint32_t*, Idx3Hash>;  // remote block -> its published free mask
+  void updateBlockEverFree(const Block& b, uint64_t stamp, std::vector<int>* to_set, const GhostMap* ghosts = nullptr) const;
+  std::vector<Block*> trackingPassLocal(uint64_t stamp);  // K2 on all blocks; returns the tracking_updated ones
+  void applyEverFree(const std::vector<Block*>& updated, uint64_t stamp, const GhostMap* ghosts);
+  // M1 split: per-pixel voxel keys (range / z / index validity, no block lookup), then flags, then clustering.
+  struct PixKey { bool valid = false; Idx3 block; int lin = 0; GIdx g; };
+  void computePixelKeys(const kb_frame& f);
+  void clusterFromFlags(const uint8_t* flags, int32_t* dynamic_image, int32_t* n_seeds, int32_t* n_clusters);
   bool voxelIsFree(const Block& b, int lin, uint64_t stamp) const;
 
   kb_map_config map_;
@@ -146,6 +164,12 @@ class Oracle {
   std::unordered_map<Idx3, std::unique_ptr<Block>, Idx3Hash> blocks_;
   std::vector<Cluster> clusters_;
   std::vector<float> vertex_scratch_;
+  const float* vertex_ = nullptr;          // world-frame vertex map of the frame whose keys are in pix_keys_
+  std::vector<PixKey> pix_keys_;
+  std::vector<uint8_t> flags_scratch_;
+  int rank_ = 0, nranks_ = 1;
+  std::vector<Block*> open_pending_;       // ever-free work list between trackingBegin and trackingFinish
+  uint64_t open_stamp_ = 0;
   std::string error_;
 };
 

@@ -15,6 +15,11 @@ struct ko_handle {
   size_t pixels = 0;
   std::vector<float> depth_f;
   std::vector<int32_t> label_i;
+  // sharded protocol state
+  int cap_pending = 1024, cap_halo = 2048;
+  std::vector<int32_t> last_dynamic;  // dynamic image of the last detection (KB_MASK_LAST_DETECTION)
+  int32_t last_seeds = 0, last_clusters = 0;
+  bool have_dynamic = false;
 };
 
 static int fail(ko_handle* h, int code) {
@@ -79,8 +84,13 @@ static const kb_frame* expandCompact(ko_handle* h, const kb_frame* f, kb_frame* 
 
 int ko_integrate_frame(ko_handle* h, const kb_frame* f_in, int allocate_blocks, kb_frame_stats* stats) {
   if (!h || !f_in || (!f_in->depth && !f_in->depth_u16)) return KB_ERR_INVALID;
-  kb_frame tmp;
+  kb_frame tmp, tmp2;
   const kb_frame* f = expandCompact(h, f_in, &tmp);
+  if (f->mask == KB_MASK_LAST_DETECTION) {  // dynamic image of the last detection kept by the handle
+    tmp2 = *f;
+    tmp2.mask = h->have_dynamic ? h->last_dynamic.data() : nullptr;
+    f = &tmp2;
+  }
   kb_frame_stats local{};
   h->o->integrateFrame(*f, allocate_blocks != 0, &local);
   h->totals.blocks_in_frustum += local.blocks_in_frustum;
@@ -125,6 +135,73 @@ int ko_update_tracking(ko_handle* h, uint64_t stamp_ns) {
   return h->o->ok() ? KB_OK : fail(h, KB_ERR_INVALID);
 }
 
+// ---- block-hash sharded protocol on host buffers (same layouts as the product's device buffers) ----------
+
+int ko_set_shard(ko_handle* h, int rank, int nranks) {
+  if (!h || nranks < 1 || rank < 0 || rank >= nranks) return KB_ERR_INVALID;
+  h->o->setShard(rank, nranks);
+  return KB_OK;
+}
+
+int ko_block_owner(int32_t bx, int32_t by, int32_t bz, int nranks) { return Oracle::blockOwner(ko::Idx3{bx, by, bz}, nranks); }
+
+int ko_set_shard_capacity(ko_handle* h, int32_t pending_capacity, int32_t halo_capacity) {
+  if (!h || pending_capacity <= 0 || halo_capacity <= 0) return KB_ERR_INVALID;
+  h->cap_pending = pending_capacity;
+  h->cap_halo = halo_capacity;
+  return KB_OK;
+}
+
+int ko_shard_buffer_sizes(ko_handle* h, int64_t* pending_bytes, int64_t* halo_bytes, int64_t* pixel_flag_bytes) {
+  if (!h) return KB_ERR_INVALID;
+  if (pending_bytes) *pending_bytes = static_cast<int64_t>(4 + 3 * h->cap_pending) * 4;
+  if (halo_bytes) *halo_bytes = static_cast<int64_t>(4 + static_cast<int64_t>(h->cap_halo) * (4 + h->o->V() / 32)) * 4;
+  if (pixel_flag_bytes) *pixel_flag_bytes = static_cast<int64_t>(h->pixels);
+  return KB_OK;
+}
+
+int ko_tracking_begin(ko_handle* h, uint64_t stamp_ns, void* pending_out) {
+  if (!h || !pending_out) return KB_ERR_INVALID;
+  h->o->trackingBegin(stamp_ns, static_cast<int32_t*>(pending_out), h->cap_pending);
+  return h->o->ok() ? KB_OK : fail(h, KB_ERR_INVALID);
+}
+
+int ko_tracking_pack_halo(ko_handle* h, const void* all_pending, void* halo_out) {
+  if (!h || !all_pending || !halo_out) return KB_ERR_INVALID;
+  h->o->packHalo(static_cast<const int32_t*>(all_pending), h->cap_pending, static_cast<int32_t*>(halo_out), h->cap_halo);
+  return h->o->ok() ? KB_OK : fail(h, KB_ERR_INVALID);
+}
+
+int ko_tracking_finish(ko_handle* h, const void* all_pending, const void* all_halo) {
+  if (!h || !all_pending || !all_halo) return KB_ERR_INVALID;
+  h->o->trackingFinish(static_cast<const int32_t*>(all_pending), h->cap_pending, static_cast<const int32_t*>(all_halo), h->cap_halo);
+  return h->o->ok() ? KB_OK : fail(h, KB_ERR_CAPACITY);
+}
+
+int ko_motion_lookup_local(ko_handle* h, const kb_frame* f_in, uint8_t* pixel_flags) {
+  if (!h || !f_in || !pixel_flags) return KB_ERR_INVALID;
+  kb_frame tmp;
+  const kb_frame* f = expandCompact(h, f_in, &tmp);
+  h->o->motionLookupLocal(*f, pixel_flags);
+  return h->o->ok() ? KB_OK : fail(h, KB_ERR_INVALID);
+}
+
+int ko_motion_cluster_global(ko_handle* h, const uint8_t* pixel_flags) {
+  if (!h || !pixel_flags) return KB_ERR_INVALID;
+  h->last_dynamic.assign(h->pixels, 0);
+  h->o->motionClusterGlobal(pixel_flags, h->last_dynamic.data(), &h->last_seeds, &h->last_clusters);
+  h->have_dynamic = true;
+  return h->o->ok() ? KB_OK : fail(h, KB_ERR_INVALID);
+}
+
+int ko_motion_result(ko_handle* h, int32_t* dynamic_image_out, int32_t* n_seeds, int32_t* n_clusters) {
+  if (!h || !h->have_dynamic) return KB_ERR_STATE;
+  if (dynamic_image_out) std::memcpy(dynamic_image_out, h->last_dynamic.data(), sizeof(int32_t) * h->pixels);
+  if (n_seeds) *n_seeds = h->last_seeds;
+  if (n_clusters) *n_clusters = h->last_clusters;
+  return KB_OK;
+}
+
 int ko_reset_inactive(ko_handle* h, int32_t* removed_xyz, int32_t max_removed, int32_t* n_removed) {
   if (!h) return KB_ERR_INVALID;
   std::vector<ko::Idx3> removed;
@@ -148,7 +225,11 @@ int ko_detect_motion(ko_handle* h, const kb_frame* f_in, int32_t* dynamic_image_
   if (!h || !f_in || !dynamic_image_out) return KB_ERR_INVALID;
   kb_frame tmp;
   const kb_frame* f = expandCompact(h, f_in, &tmp);
-  h->o->detectMotion(*f, dynamic_image_out, n_seeds, n_clusters);
+  h->o->detectMotion(*f, dynamic_image_out, &h->last_seeds, &h->last_clusters);
+  h->last_dynamic.assign(dynamic_image_out, dynamic_image_out + h->pixels);
+  h->have_dynamic = true;
+  if (n_seeds) *n_seeds = h->last_seeds;
+  if (n_clusters) *n_clusters = h->last_clusters;
   return h->o->ok() ? KB_OK : fail(h, KB_ERR_INVALID);
 }
 

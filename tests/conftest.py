@@ -11,6 +11,9 @@ sys.path.insert(0, ROOT)
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # the synthetic renderer works on tiny tensors: intra-op threading only adds (large) overhead
+    import torch
+    torch.set_num_threads(1)
 
 
 @pytest.fixture(scope="session")

@@ -8,13 +8,16 @@ import numpy as np
 from khronos_b200 import capi, synthetic as syn
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# Oracle worker threads for handles built with default configs: small test inputs gain nothing from one thread per
+# core (the oracle spawns its workers per call like the reference), and CI containers oversubscribe badly.
+TEST_THREADS = int(os.environ.get("KB_TEST_THREADS", "4"))
 
 
 def make_handle(lib, prefix, map_cfg=None, integ_cfg=None, trk_cfg="default", mot_cfg="default", cam=None, device=0):
     map_cfg = map_cfg or capi.default_map_config()
-    integ_cfg = integ_cfg or capi.default_integrator_config()
-    trk = capi.default_tracking_config() if trk_cfg == "default" else trk_cfg
-    mot = capi.default_motion_config() if mot_cfg == "default" else mot_cfg
+    integ_cfg = integ_cfg or capi.default_integrator_config(num_threads=TEST_THREADS)
+    trk = capi.default_tracking_config(num_threads=TEST_THREADS) if trk_cfg == "default" else trk_cfg
+    mot = capi.default_motion_config(num_threads=TEST_THREADS) if mot_cfg == "default" else mot_cfg
     if not map_cfg.with_tracking:
         trk, mot = None, None
     h = capi.MapHandle(lib, prefix, map_cfg, integ_cfg, trk, mot, device)
