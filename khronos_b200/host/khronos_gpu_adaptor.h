@@ -11,14 +11,19 @@
 //                             (integration/tracking_integrator.h:96,102)
 //   GpuFreeSpaceMotionDetector khronos::FreeSpaceMotionDetector::processInput
 //                             (motion_detection/free_space_motion_detector.h:121; base motion_detector.h:62)
+//   reconstructStaticObject   the map set-up / integrate / erase steps of MeshObjectExtractor::extractStaticObject
+//                             (object_extraction/mesh_object_extractor.cpp:201-264)
 //   mirrorBack                repopulates a host hydra::VolumetricMap for MeshIntegrator::generateMesh /
 //                             cloneUpdated (active_window.cpp:223,229)
 // Error behaviour follows the reference: configuration errors throw at construction
 // (config::checkValid), the per-frame path never throws — failures are logged and the frame skipped.
 #pragma once
 
+#include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -210,6 +215,64 @@ inline int eraseLowConfidence(GpuVolumetricMap& map, float min_confidence, int m
   int32_t n = 0;
   check(kb_scan_object_confidence(map.handle(), min_confidence, min_observations, &n), map.handle(), "kb_scan_object_confidence");
   return n;
+}
+
+// The GPU part of MeshObjectExtractor::extractStaticObject (mesh_object_extractor.cpp:201-264): private map sized from
+// the track's extent (vps 8, truncation 2 voxels, semantics on, tracking off, :201-211), dense allocation of the
+// blocks in [centre - dims, centre + dims] (:218-228), projective updates of every semantic frame with the
+// ObjectIntegrator's binary labels (:237-243; one kb_integrate_frames call, the frames are fused in batches of 32 on
+// the device) and the low-confidence erase (:246-264). The caller mirrors the result back and runs the unchanged
+// MeshIntegrator::generateMesh (:267). Returns nullptr where the reference returns "no object" (:177-179, :211-213).
+struct ObjectReconstructionConfig {  // the fields of MeshObjectExtractor::Config this step reads (mesh_object_extractor.h:80-100)
+  float min_object_reconstruction_confidence = 0.5f;
+  int min_object_reconstruction_observations = 10;
+  float object_reconstruction_resolution = -0.02f;
+  float min_reconstruction_resolution = 0.0f;
+  kb_integrator_config projective_integrator{};  // semantic_mode is forced to BINARY (object_integrator.cpp:44-48)
+  int max_blocks = 1 << 16;
+};
+
+inline std::unique_ptr<GpuVolumetricMap> reconstructStaticObject(
+    const float extent_center[3], const float extent_dimensions[3],
+    const std::vector<std::pair<const khronos::FrameData*, int>>& frames, const ObjectReconstructionConfig& config,
+    int* n_erased = nullptr, int device = 0) {
+  if (config.object_reconstruction_resolution == 0.f || frames.empty()) return nullptr;
+  hydra::VolumetricMap::Config mc;
+  if (config.object_reconstruction_resolution < 0.f) {
+    const float max_dim = std::max(extent_dimensions[0], std::max(extent_dimensions[1], extent_dimensions[2]));
+    mc.voxel_size = std::max(max_dim * -config.object_reconstruction_resolution, config.min_reconstruction_resolution);
+  } else {
+    mc.voxel_size = config.object_reconstruction_resolution;
+  }
+  mc.voxels_per_side = 8;
+  mc.truncation_distance = mc.voxel_size * 2;
+  mc.with_semantics = true;
+  mc.with_tracking = false;
+  if (!(mc.voxel_size > 0.f)) return nullptr;  // config::isValid(map_config)
+  kb_integrator_config ic = config.projective_integrator;
+  ic.semantic_mode = KB_SEMANTICS_BINARY;
+  ic.num_labels = 2;
+  auto map = std::make_unique<GpuVolumetricMap>(mc, ic, nullptr, nullptr, config.max_blocks, device);
+  // tsdf_layer.getBlockIndex(p) = floor(p / block_size) per axis
+  const float inv = 1.f / (mc.voxel_size * static_cast<float>(mc.voxels_per_side));
+  int32_t lo[3], hi[3];
+  for (int a = 0; a < 3; ++a) {
+    lo[a] = static_cast<int32_t>(std::floor((extent_center[a] - extent_dimensions[a]) * inv));
+    hi[a] = static_cast<int32_t>(std::floor((extent_center[a] + extent_dimensions[a]) * inv));
+  }
+  check(kb_allocate_box(map->handle(), lo, hi), map->handle(), "kb_allocate_box");
+  std::vector<kb_frame> kf;
+  kf.reserve(frames.size());
+  for (const auto& fr : frames) kf.push_back(makeFrame(fr.first->input, nullptr, &fr.first->object_image, fr.second));
+  map->setSensor(frames.front().first->input.getSensor());
+  check(kb_integrate_frames(map->handle(), kf.data(), static_cast<int32_t>(kf.size()), /*allocate_blocks=*/0, nullptr),
+        map->handle(), "kb_integrate_frames");
+  int32_t erased = 0;
+  check(kb_scan_object_confidence(map->handle(), config.min_object_reconstruction_confidence,
+                                  config.min_object_reconstruction_observations, &erased),
+        map->handle(), "kb_scan_object_confidence");
+  if (n_erased) *n_erased = erased;
+  return map;
 }
 
 #ifndef KB_HAVE_HYDRA

@@ -38,6 +38,21 @@ int main(int argc, char** argv) {
     auto blk = host.getTsdfLayer().getBlockPtr({0, 0, 2});
     if (!blk) { std::printf("missing block\n"); return 2; }
     const auto& v = blk->getVoxel(0 + 8 * (0 + 8 * 3));
+    // extractor path: private vps-8 binary map around the wall patch in front of the camera, same frame 12 times
+    frame.object_image = cv::Mat(48, 64, 4);
+    for (int i = 0; i < 48 * 64; ++i) frame.object_image.ptr<int32_t>()[i] = (i % 64) < 32 ? 7 : 0;
+    ObjectReconstructionConfig oc;
+    oc.projective_integrator = ic;
+    oc.min_object_reconstruction_observations = 3;
+    const float centre[3] = {0.f, 0.f, 2.f}, dims[3] = {0.5f, 0.5f, 0.25f};
+    std::vector<khronos::FrameData> copies(12, frame);
+    std::vector<std::pair<const khronos::FrameData*, int>> obs;
+    for (size_t k = 0; k < copies.size(); ++k) { copies[k].input.timestamp_ns += k + 1; obs.emplace_back(&copies[k], 7); }
+    int erased = -1;
+    auto omap = reconstructStaticObject(centre, dims, obs, oc, &erased);
+    int32_t oblocks = 0;
+    if (omap) kb_num_blocks(omap->handle(), KB_EXPORT_ALL, &oblocks);
+    std::printf("object_blocks=%d erased=%d ", oblocks, erased);
     std::printf("blocks=%zu distance=%.9g weight=%.9g label=%u\n", host.getTsdfLayer().numBlocks(), v.distance, v.weight,
                 host.getSemanticLayer()->getBlockPtr({0, 0, 2})->getVoxel(0 + 8 * (0 + 8 * 3)).semantic_label);
   } catch (const std::exception& e) {
