@@ -89,39 +89,52 @@ def algorithmic_bytes(nv, nsem, nblk, pixels, lp=20, bpp=BYTES_PER_PIXEL_IN):
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md)."""
+    """Samples nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md). The timed region of the
+    default run is ~0.1 s, so nvidia-smi is started early (before the last warm-up step: its start-up latency is of
+    that order) with a 20 ms period, every sample is stamped on arrival, and stop(t0, t1) keeps the samples that fell
+    inside the timed window [t0, t1] (perf_counter seconds)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index=0):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index=0, period_ms=20):
+        self.index, self.rows, self.proc, self.period_ms = index, [], None, period_ms
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.index), "-lms", str(self.period_ms)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        rows = [(t, r) for t, r in list(self.rows) if len(r) >= 6]
+        inside = [r for t, r in rows if (t0 is None or t >= t0) and (t1 is None or t <= t1 + 0.5 * self.period_ms * 1e-3)]
+        note = None
+        if not inside and rows and t0 is not None:  # region shorter than the sampling period: nearest samples around it
+            mid = 0.5 * (t0 + t1)
+            inside = [r for _, r in sorted(rows, key=lambda tr: abs(tr[0] - mid))[:2]]
+            note = "no sample landed inside the timed window; the 2 nearest samples are reported"
+        num = lambda x: x.replace(".", "").isdigit()
+        sm = [float(r[0]) for r in inside if num(r[0])]
+        mx = [float(r[1]) for r in inside if num(r[1])]
         reasons = set()
-        for r in self.rows:
-            if len(r) >= 6:
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        for r in inside:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        out = {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+               "reasons": sorted(reasons), "samples": len(sm), "samples_total": len(rows)}
+        if note:
+            out["note"] = note
+        return out
 
 
 def map_configs(args):
@@ -284,7 +297,7 @@ def main_dynamic(args):
     h.synchronize()
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    clocks = sampler.stop()
+    clocks = sampler.stop(t0, t0 + dt)
     tot = h.get_totals()
     # CPU arm of the same pipeline on a bounded sample: the oracle port replays the first frames (burn-in + the first
     # dynamic frames) and is timed on the frames in which it finds clusters
@@ -376,7 +389,7 @@ def main_dynamic_sharded(args):
     torch.cuda.synchronize()
     dist.barrier()
     dt = time.perf_counter() - t0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t0, t0 + dt) if rank == 0 else None
     t = torch.tensor([dt], device=dev, dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dt = float(t.item())
@@ -559,14 +572,16 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    if Wm == 0 and rank == 0:
+        sampler.start()
     for s in range(Wm):
+        if s == Wm - 1 and rank == 0:
+            sampler.start()  # running (and past nvidia-smi's start-up) when the timed region begins
         run_step(s)
     barrier()
     tot0 = h.get_totals()
     dbg0 = h.get_debug_counters()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     samples = []
     wall0 = time.perf_counter()
@@ -576,7 +591,7 @@ def main():
     ev1.record(stream)
     barrier()
     wall = time.perf_counter() - wall0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(wall0, wall0 + wall) if rank == 0 else None
     gpu_ms = ev0.elapsed_time(ev1)
     if world > 1:
         # the device-timed region excludes nothing: broadcasts run on torch's stream between the
