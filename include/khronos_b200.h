@@ -254,6 +254,36 @@ int kb_allocate_box(kb_handle* h, const int32_t min_block[3], const int32_t max_
 int kb_scan_object_confidence(kb_handle* h, float min_confidence, int32_t min_observations,
                               int32_t* n_erased);
 
+/* ---- semantic object detection (the step before the path) ----------------------------------
+ * khronos::ConnectedSemantics::Config (khronos/include/khronos/active_window/object_detection/connected_semantics.h
+ * :64-84) + the object classes of hydra's label space (GlobalInfo::getLabelSpaceConfig().isObject, call sites
+ * connected_semantics.cpp:134,164). */
+typedef struct kb_object_detector_config {
+  int32_t use_full_connectivity;  /* 26 / 8 neighbours if non-zero, else 6 / 4; default 1 */
+  int32_t min_cluster_size;       /* pixels; default 0 */
+  int32_t max_cluster_size;       /* pixels; <= 0 disables (3D mode only, as in the reference); default -1 */
+  int32_t use_3d;                 /* 1: cluster in a voxel grid (semanticClustering3D), 0: in image space; default 1 */
+  float grid_size;                /* m, 3D mode; default 0.1 */
+  float max_range;                /* m, 3D mode; 0 = infinite; default 0 */
+  uint8_t is_object[KB_MAX_LABELS]; /* 1 => the label is an object class */
+} kb_object_detector_config;
+
+/* Replaces ConnectedSemantics::processInput (connected_semantics.cpp:60-69 -> semanticClustering3D :71-122 with
+ * computeCandidateVoxels :124-146, or semanticClustering2D :148-198 + filterClusters :200-217): connected components
+ * of the object-class pixels (per semantic id) in a voxel grid of the world-frame vertex map or in image space.
+ * object_image_out: H*W int32 (host), 0 = no object, else the cluster id (FrameData::object_image, the label source
+ * of the ObjectIntegrator, object_integrator.cpp:76-79). The frame needs depth (+ pose, or vertex_world) and label.
+ * Cluster ids: 2D mode exactly as the reference (creation order of the column-major scan, ids of filtered clusters
+ * are not reused); 3D mode: semantic ids ascending (std::map, connected_semantics.h:88), clusters of one id ordered
+ * by their smallest voxel in (z, y, x) order — a determinisation of the reference's unordered_map iteration. */
+int kb_detect_objects(kb_handle* h, const kb_object_detector_config* config, const kb_frame* frame,
+                      int32_t* object_image_out, int32_t* n_clusters);
+/* Clusters of the last kb_detect_objects call (MeasurementCluster id / semantics.category_id / pixels,
+ * measurement_clusters.h:63-81), ascending id: id_semantic_count[c*3+0..2] = id, semantic id, #pixels; then the
+ * flat (u, v) pixel list in cluster order (order within a cluster unspecified). NULL pointers are skipped. */
+int kb_get_object_clusters(kb_handle* h, int32_t* id_semantic_count, int32_t* pixels_uv, int32_t* n_clusters,
+                           int32_t* total_pixels);
+
 /* ---- sharded per-frame pipeline (new in this build; SURVEY.md §8e exchange steps 1 and 2) -----------------------
  * With kb_set_shard(rank, nranks > 1) a handle holds only the blocks it owns. Fusion (K0/K1/K1b), K2, K2r and K4 are
  * independent per block and need nothing else. Two steps of ActiveWindow::spinOnce look across blocks:

@@ -54,6 +54,12 @@ class MotionConfig(C.Structure):
                 ("num_threads", C.c_int32)]
 
 
+class ObjectDetectorConfig(C.Structure):
+    _fields_ = [("use_full_connectivity", C.c_int32), ("min_cluster_size", C.c_int32),
+                ("max_cluster_size", C.c_int32), ("use_3d", C.c_int32), ("grid_size", C.c_float),
+                ("max_range", C.c_float), ("is_object", C.c_uint8 * KB_MAX_LABELS)]
+
+
 class Camera(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("fx", C.c_float), ("fy", C.c_float),
                 ("cx", C.c_float), ("cy", C.c_float), ("min_range", C.c_float),
@@ -123,6 +129,15 @@ def default_motion_config(num_threads=-1, min_cluster_size=0, max_cluster_size=1
     """khronos::FreeSpaceMotionDetector::Config defaults (free_space_motion_detector.h:70-95)."""
     return MotionConfig(connectivity, min_cluster_size, max_cluster_size, min_separation_distance,
                         10000.0, -10000.0, num_threads)
+
+
+def default_object_detector_config(object_labels=(), use_3d=True, min_cluster_size=0, max_cluster_size=-1,
+                                   use_full_connectivity=True, grid_size=0.1, max_range=0.0) -> ObjectDetectorConfig:
+    """khronos::ConnectedSemantics::Config defaults (object_detection/connected_semantics.h:64-84)."""
+    c = ObjectDetectorConfig(int(use_full_connectivity), min_cluster_size, max_cluster_size, int(use_3d), grid_size, max_range)
+    for l in object_labels:
+        c.is_object[l] = 1
+    return c
 
 
 class KbError(RuntimeError):
@@ -359,6 +374,28 @@ class MapHandle:
                         "bbox": bb[c].copy()})
             po += npx
             vo += nvx
+        return out
+
+    def detect_objects(self, cfg: ObjectDetectorConfig, frame: Frame):
+        """kb_detect_objects: returns (object image H x W int32, number of clusters)."""
+        H, W = self._camera.height, self._camera.width
+        img = np.zeros((H, W), np.int32)
+        nc = C.c_int32(0)
+        self._check(self._fn("detect_objects")(self._h, C.byref(cfg), C.byref(frame), C.c_void_p(img.ctypes.data), C.byref(nc)))
+        return img, nc.value
+
+    def get_object_clusters(self):
+        f = self._fn("get_object_clusters")
+        nc, tp = C.c_int32(0), C.c_int32(0)
+        self._check(f(self._h, None, None, C.byref(nc), C.byref(tp)))
+        info = np.zeros((max(nc.value, 1), 3), np.int32)
+        px = np.zeros((max(tp.value, 1), 2), np.int32)
+        self._check(f(self._h, C.c_void_p(info.ctypes.data), C.c_void_p(px.ctypes.data), C.byref(nc), C.byref(tp)))
+        out, po = [], 0
+        for c in range(nc.value):
+            n = int(info[c, 2])
+            out.append({"id": int(info[c, 0]), "semantic_id": int(info[c, 1]), "pixels": px[po:po + n].copy()})
+            po += n
         return out
 
     def allocate_box(self, mn, mx):

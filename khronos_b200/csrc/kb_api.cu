@@ -13,6 +13,7 @@
 #include "../../include/khronos_b200.h"
 #include "kb_kernels.cuh"
 #include "kb_motion_device.cuh"
+#include "kb_objects_device.cuh"
 #include "kb_motion_host.h"
 
 using namespace kb;
@@ -90,6 +91,14 @@ struct kb_handle {
   bool motion_have_image = false;
   int3* d_removed = nullptr;
   int max_removed = 0;
+  // semantic object detection (kb_detect_objects): inputs staged here, result image on the device + host copies
+  float* obj_depth = nullptr;
+  int* obj_label = nullptr;
+  int32_t* d_object = nullptr;
+  int* h_oscal = nullptr;       // pinned mirror of the clustering scalars
+  size_t obj_pixels = 0;
+  std::vector<int32_t> obj_image_host, obj_label_host;
+  bool obj_have = false;
   // sharded per-frame pipeline (kb_tracking_begin / pack_halo / finish, kb_motion_lookup_local / cluster_global)
   ShardExchange xch{};
   int cap_pending = 1024, cap_halo = 2048;
@@ -158,6 +167,17 @@ int ensureColorStaging(kb_handle* h, size_t pixels) {
   h->stg_color = nullptr;
   KB_CUDA(h, devAlloc(&h->stg_color, pixels * 3 * kMaxBatch * 2, 0));
   h->stg_color_pixels = pixels;
+  return KB_OK;
+}
+
+int ensureObjectBuffers(kb_handle* h, size_t pixels) {
+  if (h->obj_pixels >= pixels) return KB_OK;
+  cudaFree(h->obj_depth); cudaFree(h->obj_label); cudaFree(h->d_object);
+  KB_CUDA(h, devAlloc(&h->obj_depth, pixels, 0));
+  KB_CUDA(h, devAlloc(&h->obj_label, pixels, 0));
+  KB_CUDA(h, devAlloc(&h->d_object, pixels, 0));
+  if (!h->h_oscal) KB_CUDA(h, cudaMallocHost(reinterpret_cast<void**>(&h->h_oscal), sizeof(int) * kMsCount));
+  h->obj_pixels = pixels;
   return KB_OK;
 }
 
@@ -451,6 +471,8 @@ int kb_destroy(kb_handle* h) {
   cudaFree(m.born_frame); cudaFree(m.next_pass); cudaFree(m.act_min); cudaFree(h->pending);
   cudaFree(m.sem_label); cudaFree(m.sem_lik); cudaFree(m.color); cudaFree(h->stg_color);
   cudaFree(h->xch.halo_mark); cudaFree(h->xch.publish); cudaFree(h->xch.ghost_keys); cudaFree(h->xch.ghost_vals);
+  cudaFree(h->obj_depth); cudaFree(h->obj_label); cudaFree(h->d_object);
+  if (h->h_oscal) cudaFreeHost(h->h_oscal);
   cudaFree(h->stg_depth); cudaFree(h->stg_label); cudaFree(h->stg_mask); cudaFree(h->stg_object);
   cudaFree(h->stg_vertex); cudaFree(h->d_pixel_gidx); cudaFree(h->d_pixel_seed); cudaFree(h->d_removed);
   cudaFree(h->d_dynamic);
@@ -1110,6 +1132,109 @@ int kb_spin_once(kb_handle* h, const kb_frame* f, int32_t* dynamic_image_out, in
   h->motion_stale = h->h_mscal[kMsClusters] > 0;
   if (n_seeds) *n_seeds = h->h_mscal[kMsSeeds];
   if (n_clusters) *n_clusters = h->h_mscal[kMsClusters];
+  return KB_OK;
+}
+
+int kb_detect_objects(kb_handle* h, const kb_object_detector_config* cfg, const kb_frame* f, int32_t* object_image_out,
+                      int32_t* n_clusters) {
+  if (!h || !cfg || !f || !object_image_out || (!f->depth && !f->depth_u16)) return fail(h, KB_ERR_INVALID, "null argument");
+  if (!h->has_cam) return fail(h, KB_ERR_STATE, "kb_set_camera must be called first");
+  if (cfg->use_3d && !(cfg->grid_size > 0.f)) return fail(h, KB_ERR_INVALID, "grid_size must be positive");
+  KB_CUDA(h, cudaSetDevice(h->device));
+  const kb_camera& c = h->cam;
+  const size_t px = static_cast<size_t>(c.width) * c.height;
+  int st;
+  if ((st = ensureObjectBuffers(h, px)) != KB_OK) return st;
+  if (h->mt.max_roots * 1024 < static_cast<int>(px)) return fail(h, KB_ERR_CAPACITY, "image too large for the 2D scan");
+  h->obj_have = false;
+  if (!f->label && !f->label_u8) {  // no semantic image: no objects (connected_semantics.cpp reads label_image only)
+    std::memset(object_image_out, 0, sizeof(int32_t) * px);
+    KB_CUDA(h, cudaMemsetAsync(h->d_object, 0, sizeof(int32_t) * px, h->stream));
+    h->obj_image_host.assign(px, 0);
+    h->obj_label_host.assign(px, 0);
+    h->obj_have = true;
+    if (n_clusters) *n_clusters = 0;
+    return KB_OK;
+  }
+  ObjectParams p{};
+  float R[9], t[3];
+  poseToFloat(f->world_T_sensor, R, t, p.Rw, p.tw);
+  p.W = c.width; p.H = c.height; p.fx = c.fx; p.fy = c.fy; p.cx = c.cx; p.cy = c.cy;
+  p.inv_grid = cfg->use_3d ? 1.f / cfg->grid_size : 0.f;
+  p.max_range = cfg->max_range;
+  for (int i = 0; i < KB_MAX_LABELS; ++i)
+    if (cfg->is_object[i]) p.object_mask |= 1ull << i;
+  p.full = cfg->use_full_connectivity;
+  p.min_size = cfg->min_cluster_size;
+  p.max_size = cfg->max_cluster_size;
+  p.image = h->d_object;
+  // inputs: compact formats are expanded like everywhere else (float(u16) * scale, int32(u8))
+  if (f->depth_u16) {
+    const uint16_t* d16 = nullptr;
+    if ((st = stage(h, f->depth_u16, h->mot_depth16, px, f->memory, &d16)) != KB_OK) return st;
+    launchExpandDepth(d16, f->depth_u16_scale, h->obj_depth, static_cast<int>(px), h->stream);
+    p.depth = h->obj_depth;
+  } else if ((st = stage(h, f->depth, h->obj_depth, px, f->memory, &p.depth)) != KB_OK) {
+    return st;
+  }
+  h->obj_label_host.resize(px);
+  if (f->label_u8) {
+    std::vector<uint8_t> tmp(px);  // rare path: expand the 8-bit ids on the host side of the staging copy
+    if (f->memory == KB_MEM_DEVICE) KB_CUDA(h, cudaMemcpy(tmp.data(), f->label_u8, px, cudaMemcpyDeviceToHost));
+    else std::memcpy(tmp.data(), f->label_u8, px);
+    for (size_t i = 0; i < px; ++i) h->obj_label_host[i] = tmp[i];
+    KB_CUDA(h, cudaMemcpyAsync(h->obj_label, h->obj_label_host.data(), sizeof(int) * px, cudaMemcpyHostToDevice, h->stream));
+    p.label = h->obj_label;
+  } else {
+    if ((st = stage(h, f->label, h->obj_label, px, f->memory, &p.label)) != KB_OK) return st;
+    if (f->memory == KB_MEM_DEVICE) KB_CUDA(h, cudaMemcpyAsync(h->obj_label_host.data(), f->label, sizeof(int) * px, cudaMemcpyDeviceToHost, h->stream));
+    else std::memcpy(h->obj_label_host.data(), f->label, sizeof(int) * px);
+  }
+  if (cfg->use_3d && (st = stage(h, f->vertex_world, h->stg_vertex, px * 3, f->memory, &p.vertex)) != KB_OK) return st;
+  if (cfg->use_3d) launchObjectClustering3D(h->mt, p, h->stream);
+  else launchObjectClustering2D(h->mt, p, h->stream);
+  KB_CUDA(h, cudaGetLastError());
+  KB_CUDA(h, cudaMemcpyAsync(h->h_oscal, h->mt.scalars, sizeof(int) * kMsCount, cudaMemcpyDeviceToHost, h->stream));
+  KB_CUDA(h, cudaMemcpyAsync(object_image_out, h->d_object, sizeof(int32_t) * px, cudaMemcpyDeviceToHost, h->stream));
+  KB_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (cfg->use_3d && h->h_oscal[kMsRoots] > h->mt.max_roots)
+    return fail(h, KB_ERR_CAPACITY, "too many semantic clusters for the device ranking");
+  h->obj_image_host.assign(object_image_out, object_image_out + px);
+  h->obj_have = true;
+  if (n_clusters) *n_clusters = h->h_oscal[kMsClusters];
+  return KB_OK;
+}
+
+int kb_get_object_clusters(kb_handle* h, int32_t* id_semantic_count, int32_t* pixels_uv, int32_t* n_clusters,
+                           int32_t* total_pixels) {
+  if (!h) return KB_ERR_INVALID;
+  if (!h->obj_have) return fail(h, KB_ERR_STATE, "no object detection result");
+  // Cluster lists are derived on demand from the object image: ascending id, semantic id = the label under any of
+  // the cluster's pixels (all agree), pixels in row-major order.
+  const int W = h->cam.width;
+  const size_t px = h->obj_image_host.size();
+  std::vector<std::pair<int32_t, int32_t>> by_id;  // (id, pixel)
+  by_id.reserve(px / 8);
+  for (size_t i = 0; i < px; ++i)
+    if (h->obj_image_host[i] != 0) by_id.emplace_back(h->obj_image_host[i], static_cast<int32_t>(i));
+  std::stable_sort(by_id.begin(), by_id.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+  int32_t nc = 0;
+  size_t i = 0;
+  while (i < by_id.size()) {
+    size_t e = i;
+    while (e < by_id.size() && by_id[e].first == by_id[i].first) ++e;
+    if (id_semantic_count) {
+      id_semantic_count[nc * 3] = by_id[i].first;
+      id_semantic_count[nc * 3 + 1] = h->obj_label_host[by_id[i].second];
+      id_semantic_count[nc * 3 + 2] = static_cast<int32_t>(e - i);
+    }
+    if (pixels_uv)
+      for (size_t k = i; k < e; ++k) { pixels_uv[k * 2] = by_id[k].second % W; pixels_uv[k * 2 + 1] = by_id[k].second / W; }
+    ++nc;
+    i = e;
+  }
+  if (n_clusters) *n_clusters = nc;
+  if (total_pixels) *total_pixels = static_cast<int32_t>(by_id.size());
   return KB_OK;
 }
 

@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <thread>
 
@@ -844,6 +845,116 @@ void Oracle::clusterFromFlags(const uint8_t* flags, int32_t* dynamic_image, int3
     if (id < 255) ++id;  // ids saturate at 255 (:390-395)
   }
   if (n_clusters_out) *n_clusters_out = static_cast<int32_t>(clusters_.size());
+}
+
+// ---- object detection: ConnectedSemantics (object_detection/connected_semantics.cpp, fully in-tree) -----------
+
+void Oracle::detectObjects(const kb_object_detector_config& cfg, const kb_frame& f, int32_t* object_image,
+                           std::vector<ObjectCluster>* clusters_out) {
+  if (!has_cam_) { error_ = "camera not set"; return; }
+  const int W = cam_.width, H = cam_.height;
+  std::memset(object_image, 0, sizeof(int32_t) * W * H);  // createData: cv::Mat::zeros (active_window.cpp:284)
+  object_clusters_.clear();
+  if (!f.label) { if (clusters_out) clusters_out->clear(); return; }
+  auto isObject = [&](int id) { return id >= 0 && id < KB_MAX_LABELS && cfg.is_object[id] != 0; };
+  if (cfg.use_3d) {
+    // computeCandidateVoxels (:124-146): pixels of object classes within max_range, grouped by semantic id and by
+    // the voxel (grid_size) of their world-frame vertex. NOTE: like the reference, no depth-validity test here.
+    float R[9], t[3], Rw[9], tw[3];
+    invertPose(f.world_T_sensor, R, t, Rw, tw);
+    const float inv = 1.f / cfg.grid_size;  // semanticClustering3D(data, config.grid_size) -> 1.f / grid_size (:76)
+    // std::map<int, VoxelPixelMap> (connected_semantics.h:88): semantic ids ascending. The inner map is an
+    // unordered_map in the reference; ordering its voxels by (z, y, x) makes `begin()` (:87) deterministic.
+    std::map<int, std::map<GIdx, std::vector<Pixel>, GIdxZyxLess>> maps;
+    for (int u = 0; u < W; ++u)
+      for (int v = 0; v < H; ++v) {
+        const size_t px = static_cast<size_t>(v) * W + u;
+        const float range = f.depth[px];
+        if (cfg.max_range > 0.f && range > cfg.max_range) continue;
+        const int semantic_id = f.label[px];
+        if (!isObject(semantic_id)) continue;
+        float p[3];
+        if (f.vertex_world) {
+          p[0] = f.vertex_world[px * 3]; p[1] = f.vertex_world[px * 3 + 1]; p[2] = f.vertex_world[px * 3 + 2];
+        } else {
+          const float pC[3] = {(static_cast<float>(u) - cam_.cx) / cam_.fx * range,
+                               (static_cast<float>(v) - cam_.cy) / cam_.fy * range, range};
+          transform(Rw, tw, pC, p);
+        }
+        const GIdx g{static_cast<int64_t>(std::floor(p[0] * inv)), static_cast<int64_t>(std::floor(p[1] * inv)),
+                     static_cast<int64_t>(std::floor(p[2] * inv))};  // spatial_hash::indexFromPoint (:142-143)
+        maps[semantic_id][g].push_back({u, v});
+      }
+    const auto offs = neighborOffsets(cfg.use_full_connectivity ? 26 : 6);  // :58
+    for (auto& sm : maps) {
+      auto& voxel_to_pixels = sm.second;
+      while (!voxel_to_pixels.empty()) {  // :84-121
+        ObjectCluster cluster;
+        std::vector<GIdx> stack;
+        auto item = voxel_to_pixels.begin();
+        stack.push_back(item->first);
+        cluster.pixels.insert(cluster.pixels.end(), item->second.begin(), item->second.end());
+        voxel_to_pixels.erase(item);
+        while (!stack.empty()) {
+          const GIdx g = stack.back();
+          stack.pop_back();
+          for (const auto& o : offs) {
+            auto it = voxel_to_pixels.find(GIdx{g.x + o[0], g.y + o[1], g.z + o[2]});
+            if (it == voxel_to_pixels.end()) continue;
+            stack.push_back(it->first);
+            cluster.pixels.insert(cluster.pixels.end(), it->second.begin(), it->second.end());
+            voxel_to_pixels.erase(it);
+          }
+        }
+        const int size = static_cast<int>(cluster.pixels.size());
+        if (size < cfg.min_cluster_size || (cfg.max_cluster_size > 0 && size > cfg.max_cluster_size)) continue;  // :107-111
+        cluster.id = static_cast<int>(object_clusters_.size()) + 1;
+        cluster.semantic_id = sm.first;
+        for (const Pixel& px : cluster.pixels) object_image[px.v * W + px.u] = cluster.id;
+        object_clusters_.emplace_back(std::move(cluster));
+      }
+    }
+  } else {
+    // semanticClustering2D (:148-163) + growCluster2D (:165-198): column-major scan, region growing over pixels
+    // with the same semantic id; then filterClusters (:200-217) zeroes small clusters without renumbering.
+    std::vector<ObjectCluster> all;
+    for (int u = 0; u < W; ++u)
+      for (int v = 0; v < H; ++v) {
+        if (object_image[v * W + u] != 0) continue;
+        const int semantic_id = f.label[v * W + u];
+        if (!isObject(semantic_id)) continue;
+        ObjectCluster cluster;
+        cluster.id = static_cast<int>(all.size()) + 1;
+        cluster.semantic_id = semantic_id;
+        std::vector<Pixel> stack{{u, v}};
+        cluster.pixels.push_back({u, v});
+        object_image[v * W + u] = cluster.id;
+        while (!stack.empty()) {
+          const Pixel p = stack.back();
+          stack.pop_back();
+          for (int dv = -1; dv <= 1; ++dv)
+            for (int du = -1; du <= 1; ++du) {
+              if ((du == 0 && dv == 0) || (!cfg.use_full_connectivity && du != 0 && dv != 0)) continue;
+              const int nu = p.u + du, nv = p.v + dv;
+              if (nu < 0 || nv < 0 || nu >= W || nv >= H) continue;
+              if (object_image[nv * W + nu] != 0) continue;
+              if (f.label[nv * W + nu] != semantic_id) continue;
+              cluster.pixels.push_back({nu, nv});
+              object_image[nv * W + nu] = cluster.id;
+              stack.push_back({nu, nv});
+            }
+        }
+        all.emplace_back(std::move(cluster));
+      }
+    for (auto& c : all) {
+      if (static_cast<int>(c.pixels.size()) < cfg.min_cluster_size) {
+        for (const Pixel& px : c.pixels) object_image[px.v * W + px.u] = 0;
+      } else {
+        object_clusters_.emplace_back(std::move(c));
+      }
+    }
+  }
+  if (clusters_out) *clusters_out = object_clusters_;
 }
 
 // ---- E0 / K4 ----------------------------------------------------------------------------------------------

@@ -105,6 +105,12 @@ class Oracle {
   void allocateBox(const int32_t mn[3], const int32_t mx[3]);
   int scanObjectConfidence(float min_confidence, int min_observations);
 
+  // Object detection: khronos::ConnectedSemantics::processInput (object_detection/connected_semantics.cpp:60-217).
+  struct ObjectCluster { int id = 0, semantic_id = 0; std::vector<Pixel> pixels; };
+  void detectObjects(const kb_object_detector_config& cfg, const kb_frame& f, int32_t* object_image,
+                     std::vector<ObjectCluster>* clusters);
+  const std::vector<ObjectCluster>& objectClusters() const { return object_clusters_; }
+
   // ---- block-hash sharded protocol (our multi-GPU design, not in the reference). The oracle
   // implements it on host buffers with the layouts of csrc/kb_kernels.cuh::ShardExchange so that world-size-2
   // gloo tests can prove "union of the shards == the unsharded map" on CPU.
@@ -168,6 +174,7 @@ class Oracle {
   std::vector<PixKey> pix_keys_;
   std::vector<uint8_t> flags_scratch_;
   int rank_ = 0, nranks_ = 1;
+  std::vector<ObjectCluster> object_clusters_;
   std::vector<Block*> open_pending_;       // ever-free work list between trackingBegin and trackingFinish
   uint64_t open_stamp_ = 0;
   std::string error_;

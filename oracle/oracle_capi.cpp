@@ -135,6 +135,35 @@ int ko_update_tracking(ko_handle* h, uint64_t stamp_ns) {
   return h->o->ok() ? KB_OK : fail(h, KB_ERR_INVALID);
 }
 
+int ko_detect_objects(ko_handle* h, const kb_object_detector_config* config, const kb_frame* f_in,
+                      int32_t* object_image_out, int32_t* n_clusters) {
+  if (!h || !config || !f_in || !object_image_out || (!f_in->depth && !f_in->depth_u16)) return KB_ERR_INVALID;
+  kb_frame tmp;
+  const kb_frame* f = expandCompact(h, f_in, &tmp);
+  h->o->detectObjects(*config, *f, object_image_out, nullptr);
+  if (n_clusters) *n_clusters = static_cast<int32_t>(h->o->objectClusters().size());
+  return h->o->ok() ? KB_OK : fail(h, KB_ERR_INVALID);
+}
+
+int ko_get_object_clusters(ko_handle* h, int32_t* id_semantic_count, int32_t* pixels_uv, int32_t* n_clusters,
+                           int32_t* total_pixels) {
+  if (!h) return KB_ERR_INVALID;
+  const auto& cl = h->o->objectClusters();
+  size_t tp = 0;
+  for (size_t c = 0; c < cl.size(); ++c) {
+    if (id_semantic_count) {
+      id_semantic_count[c * 3] = cl[c].id; id_semantic_count[c * 3 + 1] = cl[c].semantic_id;
+      id_semantic_count[c * 3 + 2] = static_cast<int32_t>(cl[c].pixels.size());
+    }
+    if (pixels_uv)
+      for (size_t i = 0; i < cl[c].pixels.size(); ++i) { pixels_uv[(tp + i) * 2] = cl[c].pixels[i].u; pixels_uv[(tp + i) * 2 + 1] = cl[c].pixels[i].v; }
+    tp += cl[c].pixels.size();
+  }
+  if (n_clusters) *n_clusters = static_cast<int32_t>(cl.size());
+  if (total_pixels) *total_pixels = static_cast<int32_t>(tp);
+  return KB_OK;
+}
+
 // ---- block-hash sharded protocol on host buffers (same layouts as the product's device buffers) ----------
 
 int ko_set_shard(ko_handle* h, int rank, int nranks) {
