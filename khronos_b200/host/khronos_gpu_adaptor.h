@@ -11,6 +11,7 @@
 //                             (integration/tracking_integrator.h:96,102)
 //   GpuFreeSpaceMotionDetector khronos::FreeSpaceMotionDetector::processInput
 //                             (motion_detection/free_space_motion_detector.h:121; base motion_detector.h:62)
+//   GpuConnectedSemantics     khronos::ConnectedSemantics::processInput (object_detection/connected_semantics.h:100)
 //   reconstructStaticObject   the map set-up / integrate / erase steps of MeshObjectExtractor::extractStaticObject
 //                             (object_extraction/mesh_object_extractor.cpp:201-264)
 //   mirrorBack                repopulates a host hydra::VolumetricMap for MeshIntegrator::generateMesh /
@@ -43,6 +44,7 @@ struct MeasurementCluster {  // khronos/include/khronos/active_window/data/measu
   float bbox_min[3], bbox_max[3];
   std::vector<std::array<int64_t, 3>> voxels;
   int id = 0;
+  int semantic_id = -1;  // stands in for std::optional<SemanticClusterInfo>::category_id (measurement_clusters.h:46-58)
 };
 struct FrameData {  // khronos/include/khronos/active_window/data/frame_data.h:59-83
   hydra::InputData input;
@@ -208,6 +210,44 @@ class GpuFreeSpaceMotionDetector {
       data.dynamic_clusters.push_back(std::move(cl));
     }
   }
+};
+
+// khronos::ObjectDetector plugin "ConnectedSemantics" (object_detection/connected_semantics.h:60-160; registered as
+// "GpuConnectedSemantics"): fills object_image (CV_32SC1) and semantic_clusters.
+class GpuConnectedSemantics {
+ public:
+  explicit GpuConnectedSemantics(const kb_object_detector_config& config) : config_(config) {}
+  void processInput(GpuVolumetricMap& map, khronos::FrameData& data) const {
+    kb_frame f = makeFrame(data.input, nullptr, nullptr, 0);
+    map.setSensor(data.input.getSensor());
+    if (data.object_image.empty()) data.object_image = cv::Mat(data.input.depth_image.rows, data.input.depth_image.cols, 4);
+    int32_t n = 0;
+    if (kb_detect_objects(map.handle(), &config_, &f, data.object_image.ptr<int32_t>(), &n) != KB_OK) {
+      std::fprintf(stderr, "[GpuConnectedSemantics] %s\n", kb_last_error(map.handle()));
+      return;
+    }
+    data.semantic_clusters.clear();
+    if (n == 0) return;
+    int32_t nc = 0, tp = 0;
+    kb_get_object_clusters(map.handle(), nullptr, nullptr, &nc, &tp);
+    std::vector<int32_t> info(3 * static_cast<size_t>(nc)), px(2 * static_cast<size_t>(tp));
+    kb_get_object_clusters(map.handle(), info.data(), px.data(), &nc, &tp);
+    size_t po = 0;
+    for (int c = 0; c < nc; ++c) {
+      khronos::MeasurementCluster cl;
+      cl.id = info[3 * c];
+#ifndef KB_HAVE_HYDRA
+      cl.semantic_id = info[3 * c + 1];
+#else
+      cl.semantics = khronos::SemanticClusterInfo(info[3 * c + 1]);
+#endif
+      for (int i = 0; i < info[3 * c + 2]; ++i, ++po) cl.pixels.push_back({px[2 * po], px[2 * po + 1]});
+      data.semantic_clusters.push_back(std::move(cl));
+    }
+  }
+
+ private:
+  kb_object_detector_config config_;
 };
 
 // K4 wrapper for MeshObjectExtractor::extractStaticObject (mesh_object_extractor.cpp:246-264).

@@ -38,6 +38,15 @@ int main(int argc, char** argv) {
     auto blk = host.getTsdfLayer().getBlockPtr({0, 0, 2});
     if (!blk) { std::printf("missing block\n"); return 2; }
     const auto& v = blk->getVoxel(0 + 8 * (0 + 8 * 3));
+    // object detector: the whole wall has label 3 -> one cluster when 3 is an object class
+    kb_object_detector_config dc{};
+    dc.use_full_connectivity = 1; dc.max_cluster_size = -1; dc.use_3d = 1; dc.grid_size = 0.1f; dc.is_object[3] = 1;
+    GpuConnectedSemantics object_detector(dc);
+    if (argc > 2) {  // second argument: also run the object detector (tests/test_zz_object_detection.py)
+      object_detector.processInput(gmap, frame);
+      std::printf("semantic_clusters=%zu cluster_pixels=%zu ", frame.semantic_clusters.size(),
+                  frame.semantic_clusters.empty() ? size_t(0) : frame.semantic_clusters[0].pixels.size());
+    }
     // extractor path: private vps-8 binary map around the wall patch in front of the camera, same frame 12 times
     frame.object_image = cv::Mat(48, 64, 4);
     for (int i = 0; i < 48 * 64; ++i) frame.object_image.ptr<int32_t>()[i] = (i % 64) < 32 ? 7 : 0;

@@ -85,3 +85,18 @@ def test_object_detection_does_not_disturb_motion_detection(oracle_lib, product_
             h.update_tracking(st)
     assert dyn > 100
     hs.assert_blocks_equal(o.export_blocks(), g.export_blocks(), exact_float=True, what="interleaved")
+
+
+def test_adaptor_object_detector(tmp_path):
+    """GpuConnectedSemantics through the C++ host adaptor: a wall of one object class is one cluster of all pixels."""
+    import os
+    import subprocess
+    from harness import ROOT
+    csrc = os.path.join(ROOT, "khronos_b200", "csrc")
+    exe = str(tmp_path / "adaptor_check")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", os.path.join(ROOT, "tests", "cpp", "adaptor_compile_check.cpp"),
+                           "-o", exe, "-L", csrc, "-lkhronos_b200", f"-Wl,-rpath,{csrc}"])
+    out = subprocess.run([exe, "require-gpu", "objects"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    fields = dict(kv.split("=") for kv in out.stdout.split())
+    assert int(fields["semantic_clusters"]) == 1 and int(fields["cluster_pixels"]) == 64 * 48
