@@ -5,6 +5,7 @@
 #include <climits>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <type_traits>
@@ -59,6 +60,9 @@ struct kb_handle {
   uint32_t* work_masks = nullptr;
   uint32_t* work_upd = nullptr;
   uint32_t* item_fmask = nullptr;
+  int* item_list = nullptr;    // KB_FUSE_ITEM_LIST experiment: compacted heaviest-first item lists (3 x item_list_cap)
+  int item_list_cap = 0;
+  bool use_item_list = false;
   int cull_grid = 0;
   int parity = 0;
   // lazy tracking
@@ -438,6 +442,11 @@ int kb_create(const kb_map_config* map, const kb_integrator_config* integ, const
     KB_CUDA(h, devAlloc(&h->work_upd, S, 0));
     h->batch.items_per_block = m.V / 128;
     KB_CUDA(h, devAlloc(&h->item_fmask, S * h->batch.items_per_block, 0));
+    if (const char* e = std::getenv("KB_FUSE_ITEM_LIST")) h->use_item_list = e[0] == '1';
+    if (h->use_item_list) {  // experiment, off by default (results are identical either way: only the item order changes)
+      h->item_list_cap = static_cast<int>(std::min<size_t>(S * h->batch.items_per_block, size_t(1) << 28));
+      KB_CUDA(h, devAlloc(&h->item_list, static_cast<size_t>(3) * h->item_list_cap, 0));
+    }
     {
       cudaDeviceProp prop{};
       KB_CUDA(h, cudaGetDeviceProperties(&prop, device));
@@ -480,7 +489,7 @@ int kb_destroy(kb_handle* h) {
     cudaFree(t.pix_total); cudaFree(t.min_seed); cudaFree(t.cluster_id); cudaFree(t.roots); cudaFree(t.scalars); cudaFree(t.pix_slot); cudaFree(t.occupied); }
   if (h->h_mscal) cudaFreeHost(h->h_mscal);
   cudaFree(h->stg_depth16); cudaFree(h->stg_label8); cudaFree(h->mot_depth16);
-  cudaFree(h->mot_depth); cudaFree(h->tile_max); cudaFree(h->work_slots); cudaFree(h->work_masks); cudaFree(h->work_upd); cudaFree(h->item_fmask);
+  cudaFree(h->mot_depth); cudaFree(h->tile_max); cudaFree(h->work_slots); cudaFree(h->work_masks); cudaFree(h->work_upd); cudaFree(h->item_fmask); cudaFree(h->item_list);
   for (int i = 0; i < 2; ++i) {
     if (h->stg_ready[i]) cudaEventDestroy(h->stg_ready[i]);
     if (h->stg_consumed[i]) cudaEventDestroy(h->stg_consumed[i]);
@@ -616,6 +625,9 @@ static int integrateBatch(kb_handle* h, const kb_frame* frames, int n, int alloc
     any_host_color |= frames[b].color != nullptr && frames[b].memory != KB_MEM_DEVICE;
   }
   p.has_color = any_color ? 1 : 0;
+  // the compacted item lists pay for their extra launch only where items are many and uneven: long culled batches
+  p.item_list = (h->use_item_list && p.cull && n >= 8 && !any_color) ? h->item_list : nullptr;
+  p.item_list_cap = h->item_list_cap;
   if (any_color) {
     int st = ensureColorLayer(h);
     if (st == KB_OK && any_host_color) st = ensureColorStaging(h, px);

@@ -78,6 +78,9 @@ enum Counter {
   kCtrPending = 18,  // ever-free work list length of the current tracking pass
   kCtrFetch = 19,    // dynamic work cursor of the fuse kernel
   kCtrHalo = 20,     // sharded ever-free pass: locally owned blocks whose free masks are published this pass
+  kCtrItems0 = 21,   // KB_FUSE_ITEM_LIST: non-empty culling boxes of the batch in 3 weight classes (heavy first)
+  kCtrItems1 = 22,
+  kCtrItems2 = 23,
   kNumCounters = 24
 };
 

@@ -428,6 +428,35 @@ __global__ void __launch_bounds__(128) itemCullKernel(const DeviceMap m, const _
   }
 }
 
+// ---- K0c (optional, KB_FUSE_ITEM_LIST): compaction of the non-empty culling boxes, heaviest first ----------------
+// The fuse kernel's warps fetch items from a shared cursor; with ~4 items per warp and item costs between 1 and 32
+// frame iterations, the order matters (longest-processing-time first shortens the tail) and every empty box costs a
+// cursor round trip. This pass lists the boxes whose frame mask is non-zero in three weight classes.
+template <int VPS>
+__global__ void __launch_bounds__(256) itemCompactKernel(const DeviceMap m, const __grid_constant__ BatchParams p) {
+  constexpr int BOXES = (VPS / 4) * (VPS / 8) * (VPS / 4);
+  const int n = min(m.counters[kCtrWork0 + p.parity], p.max_work) * BOXES;
+  const int lane = threadIdx.x & 31;
+  for (int base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < n; base += gridDim.x * blockDim.x) {
+    const int i = base + lane;
+    const uint32_t fm = i < n ? p.item_fmask[i] : 0u;
+    const int c = __popc(fm);
+    const int cls = c >= 20 ? 0 : (c >= 8 ? 1 : 2);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const unsigned vote = __ballot_sync(0xffffffffu, fm != 0u && cls == k);
+      if (!vote) continue;
+      int start = 0;
+      if (lane == __ffs(vote) - 1) start = atomicAdd(&m.counters[kCtrItems0 + k], __popc(vote));
+      start = __shfl_sync(0xffffffffu, start, __ffs(vote) - 1);
+      if (fm != 0u && cls == k) {
+        const int idx = start + __popc(vote & ((1u << lane) - 1u));
+        if (idx < p.item_list_cap) p.item_list[static_cast<size_t>(k) * p.item_list_cap + idx] = i;
+      }
+    }
+  }
+}
+
 // ---- K1: projective TSDF + semantic fusion ----------------------------------------------------------------
 // Lazy tracking fold (see evalTracking): what the tracking passes since the voxel's last write would have
 // done to it. Returns the flag byte to carry (ever_free, active, to_remove); refreshes last_occupied.
@@ -454,7 +483,8 @@ __device__ __noinline__ uint32_t trackingFold(const DeviceMap m, const TrackEval
 // COLOR: some frame of the batch carries a colour image; band voxels blend it into TsdfVoxel::color (kept in a
 // register like the rest of the voxel state: one 4 B read + write per batch). The colour-less instantiations
 // are the ones the BASELINE workloads run and are unchanged by this parameter.
-template <int VPS, int LPI, bool COMPACT, bool COLOR>
+// LIST: items come from the compacted, heaviest-first box lists of itemCompactKernel instead of the dense box range.
+template <int VPS, int LPI, bool COMPACT, bool COLOR, bool LIST = false>
 __global__ void __launch_bounds__(kFuseThreads, COLOR ? KB_FUSE_COLOR_MIN_BLOCKS : KB_FUSE_MIN_BLOCKS) fuseKernel(const DeviceMap m, const __grid_constant__ BatchParams p) {
   constexpr int V = VPS * VPS * VPS;
   constexpr int NK = 4;                                      // z-layers per culling box
@@ -464,7 +494,15 @@ __global__ void __launch_bounds__(kFuseThreads, COLOR ? KB_FUSE_COLOR_MIN_BLOCKS
   // Short batches have little work per voxel, so an item then covers all NK layers of its box (amortising the
   // fetch); long batches use one layer per item for balance.
   constexpr int lpi = LPI, ipb = NK / LPI;  // layers per item, items per box
-  const int n_items = min(m.counters[kCtrWork0 + p.parity], p.max_work) * BOXES * ipb;
+  int n0 = 0, n1 = 0;  // LIST: sizes of the first two weight classes
+  int n_items;
+  if constexpr (LIST) {
+    n0 = min(m.counters[kCtrItems0], p.item_list_cap);
+    n1 = min(m.counters[kCtrItems1], p.item_list_cap);
+    n_items = (n0 + n1 + min(m.counters[kCtrItems2], p.item_list_cap)) * ipb;
+  } else {
+    n_items = min(m.counters[kCtrWork0 + p.parity], p.max_work) * BOXES * ipb;
+  }
   const bool binary = p.sem_mode == KB_SEMANTICS_BINARY;
   const int L = p.L;
   int n_valid = 0, n_band = 0, n_sem = 0;
@@ -477,7 +515,13 @@ __global__ void __launch_bounds__(kFuseThreads, COLOR ? KB_FUSE_COLOR_MIN_BLOCKS
     const int w = __shfl_sync(0xffffffffu, pending, 0);
     if (w >= n_items) break;
     if (lane == 0) pending = atomicAdd(&m.counters[kCtrFetch], 1);
-    const int box = w / ipb;
+    int box = w / ipb;
+    if constexpr (LIST) {
+      const int j = box;
+      box = j < n0 ? p.item_list[j]
+                   : (j < n0 + n1 ? p.item_list[static_cast<size_t>(p.item_list_cap) + (j - n0)]
+                                  : p.item_list[2 * static_cast<size_t>(p.item_list_cap) + (j - n0 - n1)]);
+    }
     const uint32_t fmask = p.item_fmask[box];
     if (!fmask) continue;
     const int wi = box / BOXES, it = box % BOXES;
@@ -1110,6 +1154,11 @@ void launchSelectBlocks(const DeviceMap& m, const BatchParams& p, int cull_grid,
     if (m.vps == 16) itemCullKernel<16><<<cull_grid, 128, 0, s>>>(m, p);
     else itemCullKernel<8><<<cull_grid, 128, 0, s>>>(m, p);
   }
+  if (p.item_list) {
+    cudaMemsetAsync(m.counters + kCtrItems0, 0, 3 * sizeof(int), s);
+    if (m.vps == 16) itemCompactKernel<16><<<cull_grid, 256, 0, s>>>(m, p);
+    else itemCompactKernel<8><<<cull_grid, 256, 0, s>>>(m, p);
+  }
 }
 static size_t fuseSmemBytes(int Lp) { return static_cast<size_t>(std::max(Lp, 2)) * kFuseThreads * sizeof(float); }
 int fuseBlocksPerSm(int vps, int Lp) {
@@ -1125,6 +1174,7 @@ void launchFuse(const DeviceMap& m, const BatchParams& p, int grid, cudaStream_t
 #define KB_FUSE(V, LP, C)                                                                        \
   do {                                                                                           \
     if (col) fuseKernel<V, LP, C, true><<<grid, kFuseThreads, smem, s>>>(m, p);                  \
+    else if (p.item_list) fuseKernel<V, LP, C, false, true><<<grid, kFuseThreads, smem, s>>>(m, p); \
     else fuseKernel<V, LP, C, false><<<grid, kFuseThreads, smem, s>>>(m, p);                     \
   } while (0)
   if (m.vps == 16) {
