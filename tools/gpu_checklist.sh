@@ -1,0 +1,29 @@
+#!/bin/bash
+# One gpurun call that covers everything round 1 left unmeasured (run from the repo root on a B200 box):
+#   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash tools/gpu_checklist.sh'
+# Outputs land in gpurun_out/ (copy the summaries worth keeping to profiles/).
+set -u
+mkdir -p gpurun_out
+echo "== 1. GPU tests not yet run on hardware (object detection, item-list variant)"
+timeout 300 python -m pytest tests/test_zz_object_detection.py tests/test_zz_item_list.py -m gpu -q --tb=short -p no:cacheprovider \
+  > gpurun_out/zz_tests.log 2>&1; tail -5 gpurun_out/zz_tests.log
+echo "== 2. headline bench, default vs compacted heaviest-first item lists"
+timeout 200 python bench.py --no-e2e --no-cpu-baseline > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err
+KB_FUSE_ITEM_LIST=1 timeout 200 python bench.py --no-e2e --no-cpu-baseline > gpurun_out/bench_item_list.json 2> gpurun_out/bench_item_list.err
+python - <<'PY'
+import json
+for n in ("default", "item_list"):
+    try:
+        d = json.load(open(f"gpurun_out/bench_{n}.json"))
+        print(n, round(d["value"]), "fps", d["roofline"]["launch_us"], "us/launch", d["clocks"])
+    except Exception as e:
+        print(n, "failed:", e)
+PY
+echo "== 3. per-frame pipeline (config[2]) on one GPU"
+timeout 200 python bench.py --workload dynamic --steps 4 --warmup 2 --no-cpu-baseline > gpurun_out/bench_dynamic.json 2> gpurun_out/bench_dynamic.err
+tail -c 600 gpurun_out/bench_dynamic.json
+echo "== 4. launch list of the sharded / object kernels (2 shards on one device)"
+timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_sharded.csv \
+  -k regex:everFree\|halo\|ghost\|exportPending\|motionFinalize\|motionLookup\|os.*Kernel\|o2.*Kernel \
+  python -m pytest "tests/test_sharded_pipeline.py::test_product_shards_equal_unsharded_oracle[2-2.0]" tests/test_zz_object_detection.py -m gpu -q -x -p no:cacheprovider \
+  > gpurun_out/ncu_sharded.log 2>&1; tail -3 gpurun_out/ncu_sharded.log
