@@ -54,9 +54,10 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cull", action="store_true", help="disable the conservative depth culling (results identical)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--wire", default="f32", choices=["f32", "compact"],
+    ap.add_argument("--wire", default="f32", choices=["f32", "compact", "f32u8"],
                     help="f32 = depth f32 + label i32 (hydra::InputData, 8 B/pixel; the headline); compact = u16 millimetre "
-                         "depth + u8 labels (3 B/pixel, expanded on the device): what crosses PCIe / NVLink")
+                         "depth + u8 labels (3 B/pixel, expanded on the device): what crosses PCIe / NVLink; f32u8 (N > 1 only, "
+                         "experiment): lossless 5 B/pixel broadcast, depth f32 + labels narrowed to u8 on the ingest rank")
     ap.add_argument("--small", action="store_true", help="tiny configuration for functional checks")
     ap.add_argument("--workload", default="hall640", choices=["hall640", "hall1280", "dynamic"],
                     help="hall640 = BASELINE config[1] (fusion only, the headline, used for every --gpus N); hall1280 = "
@@ -480,7 +481,10 @@ def main():
     else:
         depth = label = None
     compact = args.wire == "compact"
-    bpp = 3 if compact else BYTES_PER_PIXEL_IN
+    f32u8 = args.wire == "f32u8"
+    if f32u8 and world == 1:
+        raise SystemExit("--wire f32u8 only changes what is broadcast: use it with --gpus N > 1 (torchrun)")
+    bpp = 3 if compact else (5 if f32u8 else BYTES_PER_PIXEL_IN)
     if compact and rank == 0:
         # sensor-native formats: 16-bit millimetres (values < 32768, so int16 storage is bit-identical to u16), u8 ids
         depth = (depth * 1000.0).round().to(torch.int16)
@@ -491,6 +495,12 @@ def main():
         HW = cam.height * cam.width
         rxp = [torch.empty((F, 3 * HW), dtype=torch.uint8, device=dev) for _ in range(2)]
         rx = [(b[:, :2 * HW].view(torch.int16).view(F, cam.height, cam.width), b[:, 2 * HW:].view(F, cam.height, cam.width)) for b in rxp]
+    elif world > 1 and f32u8:
+        # lossless narrow wire: depth stays f32, the (< 256) label ids travel as u8; the receiving ranks' frames carry
+        # kb_frame.depth + kb_frame.label_u8 and the library widens the labels on the device
+        HW = cam.height * cam.width
+        rxp = [torch.empty((F, 5 * HW), dtype=torch.uint8, device=dev) for _ in range(2)]
+        rx = [(b[:, :4 * HW].view(torch.float32).view(F, cam.height, cam.width), b[:, 4 * HW:].view(F, cam.height, cam.width)) for b in rxp]
     elif world > 1:
         # one packed receive buffer per step: [F, 2, H, W] int32 = (depth bits, label) -> a single broadcast
         rxp = [torch.empty((F, 2, cam.height, cam.width), dtype=torch.int32, device=dev) for _ in range(2)]
@@ -529,6 +539,9 @@ def main():
                 if compact:
                     fr.append(h.make_frame(None, poses[i], stamp_of(step, j), depth_u16=dbuf[k].data_ptr(),
                                            label_u8=lbuf[k].data_ptr(), memory=capi.MEM_DEVICE))
+                elif f32u8:
+                    fr.append(h.make_frame(dbuf[k].data_ptr(), poses[i], stamp_of(step, j), label_u8=lbuf[k].data_ptr(),
+                                           memory=capi.MEM_DEVICE))
                 else:
                     fr.append(h.make_frame(dbuf[k].data_ptr(), poses[i], stamp_of(step, j), label=lbuf[k].data_ptr(),
                                            memory=capi.MEM_DEVICE))
@@ -716,7 +729,9 @@ def main():
             "config": {"workload": args.workload if not args.small else "hall160-small",
                        "image": [cam.width, cam.height], "voxel_size": mc.voxel_size, "voxels_per_side": 16,
                        "truncation": mc.truncation_distance, "semantics": f"MLE L={L_LABELS}", "frames_per_step": F, "frames_per_call": B,
-                       "wire_format": "depth f32 + label i32 (8 B/px)" if not compact else "depth u16 mm + label u8 (3 B/px), expanded on device",
+                       "wire_format": ("depth u16 mm + label u8 (3 B/px), expanded on device" if compact else
+                                       "depth f32 + label u8 (5 B/px, lossless; labels widened on device)" if f32u8 else
+                                       "depth f32 + label i32 (8 B/px)"),
                        "lap_frames": lap, "live_blocks_rank0": total.total_blocks,
                        "l2": "inputs larger than L2: each step streams %.1f GB of frames" % (F * P * bpp / 1e9),
                        "parallelism": "block-hash shard x%d, NCCL frame broadcast" % world if world > 1 else "single GPU",

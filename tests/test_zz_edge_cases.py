@@ -129,3 +129,23 @@ def test_repeated_stamps_and_identical_frames(oracle_lib, product_lib):
     bo = o.export_blocks()
     assert (bo.weight == 50.0).any()
     hs.assert_blocks_equal(bo, g.export_blocks(), exact_float=True, what="saturation")
+
+
+def test_f32_depth_with_u8_labels_in_one_frame(oracle_lib, product_lib):
+    """kb_frame.depth (f32) together with kb_frame.label_u8: the lossless 5 B/pixel wire of bench.py --wire f32u8.
+    Host frames one by one and device-resident frames in a batch."""
+    import torch
+    cam = hs.small_camera(4)
+    frames, poses, stamps = room_frames(cam, 12, laps=0.2)
+    l8 = [l.astype(np.uint8) for _, l in frames]
+    o, g = both(oracle_lib, product_lib, cam=cam)
+    hs.run_fusion(o, frames, poses, stamps)
+    for i in range(4):
+        g.integrate_frame(g.make_frame(frames[i][0], poses[i], stamps[i], label_u8=l8[i]), want_stats=False)
+    dd = [torch.from_numpy(frames[i][0]).cuda() for i in range(4, 12)]
+    ll = [torch.from_numpy(l8[i]).cuda() for i in range(4, 12)]
+    torch.cuda.synchronize()
+    g.integrate_frames([g.make_frame(dd[j], poses[4 + j], stamps[4 + j], label_u8=ll[j], memory=capi.MEM_DEVICE) for j in range(8)],
+                       want_stats=False)
+    g.synchronize()
+    hs.assert_blocks_equal(o.export_blocks(), g.export_blocks(), exact_float=True, what="f32 depth + u8 labels")
