@@ -1,0 +1,17 @@
+#!/bin/bash
+# Multi-GPU measurements round 1 left open. Run with N GPUs of one box:
+#   /usr/local/graft/bin/gpurun --gpus 2 --timeout 900 -- 'bash tools/gpu_checklist_multi.sh 2'
+set -u
+N=${1:-2}
+mkdir -p gpurun_out
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29611"
+echo "== 1. NCCL tests (sharded fusion + sharded per-frame pipeline)"
+timeout 400 python -m pytest tests/test_multigpu_nccl.py -m gpu -q --tb=short -p no:cacheprovider > gpurun_out/nccl_tests.log 2>&1; tail -4 gpurun_out/nccl_tests.log
+echo "== 2. fusion-only bench, f32 wire vs lossless 5 B/px wire"
+for w in f32 f32u8; do
+  timeout 300 $TR bench.py --gpus $N --wire $w > gpurun_out/bench_n${N}_$w.json 2> gpurun_out/bench_n${N}_$w.err
+  python -c "import json;d=json.load(open('gpurun_out/bench_n${N}_$w.json'));print('$w', round(d['value']), 'fps', d['ms_per_step'], 'ms/step')" || tail -3 gpurun_out/bench_n${N}_$w.err
+done
+echo "== 3. per-frame pipeline (config[2]) sharded over $N GPUs"
+timeout 300 $TR bench.py --gpus $N --workload dynamic --steps 4 --warmup 2 > gpurun_out/bench_n${N}_dynamic.json 2> gpurun_out/bench_n${N}_dynamic.err
+tail -c 700 gpurun_out/bench_n${N}_dynamic.json || tail -3 gpurun_out/bench_n${N}_dynamic.err
