@@ -50,7 +50,7 @@ def parse_args():
                     help="upper bound on the frames of the cpu_baseline sample (it stops after --cpu-sample-seconds)")
     ap.add_argument("--cpu-sample-seconds", type=float, default=12.0, help="CPU work of the cpu_baseline sample")
     ap.add_argument("--ref-frames-per-step", type=int, default=256, help="--impl reference: frames per step")
-    ap.add_argument("--e2e-frames", type=int, default=512)
+    ap.add_argument("--e2e-frames", type=int, default=2048, help="frames of the e2e window (pinned host ring, ~0.1 s of PCIe traffic)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cull", action="store_true", help="disable the conservative depth culling (results identical)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
