@@ -63,6 +63,7 @@ struct kb_handle {
   int* item_list = nullptr;    // KB_FUSE_ITEM_LIST experiment: compacted heaviest-first item lists (3 x item_list_cap)
   int item_list_cap = 0;
   bool use_item_list = false;
+  int mlp_group = 0;           // KB_FUSE_MLP experiment: 0 (off), 2 or 4 frames per memory-level-parallel group
   int cull_grid = 0;
   int parity = 0;
   // lazy tracking
@@ -443,6 +444,7 @@ int kb_create(const kb_map_config* map, const kb_integrator_config* integ, const
     h->batch.items_per_block = m.V / 128;
     KB_CUDA(h, devAlloc(&h->item_fmask, S * h->batch.items_per_block, 0));
     if (const char* e = std::getenv("KB_FUSE_ITEM_LIST")) h->use_item_list = e[0] == '1';
+    if (const char* e = std::getenv("KB_FUSE_MLP")) h->mlp_group = e[0] == '2' ? 2 : (e[0] == '4' ? 4 : 0);
     if (h->use_item_list) {  // experiment, off by default (results are identical either way: only the item order changes)
       h->item_list_cap = static_cast<int>(std::min<size_t>(S * h->batch.items_per_block, size_t(1) << 28));
       KB_CUDA(h, devAlloc(&h->item_list, static_cast<size_t>(3) * h->item_list_cap, 0));
@@ -628,6 +630,7 @@ static int integrateBatch(kb_handle* h, const kb_frame* frames, int n, int alloc
   // the compacted item lists pay for their extra launch only where items are many and uneven: long culled batches
   p.item_list = (h->use_item_list && p.cull && n >= 8 && !any_color) ? h->item_list : nullptr;
   p.item_list_cap = h->item_list_cap;
+  p.mlp_group = h->mlp_group;
   if (any_color) {
     int st = ensureColorLayer(h);
     if (st == KB_OK && any_host_color) st = ensureColorStaging(h, px);

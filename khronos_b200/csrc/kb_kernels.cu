@@ -696,6 +696,305 @@ __global__ void __launch_bounds__(kFuseThreads, COLOR ? KB_FUSE_COLOR_MIN_BLOCKS
   }
 }
 
+// ---- K1, memory-level-parallel variant (experiment, KB_FUSE_MLP=G; off by default) -------------------------------
+// fuseKernel walks an item's frames one at a time: projection -> 4 depth taps -> label/mask tap -> update, i.e. two
+// to three dependent memory round trips per frame and voxel, with ~26 resident warps per SM to hide them (ncu: issue
+// slots 54 % busy, the rest is latency). Only the last step depends on the voxel state. This variant processes the
+// frames of an item in groups of G: phase A projects the voxel into all G frames and issues their 4 x G depth taps
+// together (clamped addresses, so the loads are unconditional and the nearest-pixel fallback is a select among the
+// four taps instead of another dependent load: round(u) is floor(u) or floor(u)+1); phase B1 derives taps / sdf /
+// weight per frame and issues the G label + mask taps together; phase B2 applies the G updates in frame order.
+// Arithmetic, order and results are those of fuseKernel; registers go up (G x ~9 live values), occupancy down.
+#ifndef KB_FUSE_MLP_MIN_BLOCKS
+#define KB_FUSE_MLP_MIN_BLOCKS 5
+#endif
+template <int VPS, int LPI, bool COMPACT, int G, bool LIST>
+__global__ void __launch_bounds__(kFuseThreads, KB_FUSE_MLP_MIN_BLOCKS) fuseKernelMlp(const DeviceMap m, const __grid_constant__ BatchParams p) {
+  constexpr int V = VPS * VPS * VPS;
+  constexpr int NK = 4;
+  constexpr int BOXES = (VPS / 4) * (VPS / 8) * (VPS / NK);
+  extern __shared__ float s_rows[];
+  const int lane = threadIdx.x & 31;
+  constexpr int lpi = LPI, ipb = NK / LPI;
+  int n0 = 0, n1 = 0;
+  int n_items;
+  if constexpr (LIST) {
+    n0 = min(m.counters[kCtrItems0], p.item_list_cap);
+    n1 = min(m.counters[kCtrItems1], p.item_list_cap);
+    n_items = (n0 + n1 + min(m.counters[kCtrItems2], p.item_list_cap)) * ipb;
+  } else {
+    n_items = min(m.counters[kCtrWork0 + p.parity], p.max_work) * BOXES * ipb;
+  }
+  const bool binary = p.sem_mode == KB_SEMANTICS_BINARY;
+  const int L = p.L;
+  const int W = p.W, H = p.H;
+  int n_valid = 0, n_band = 0, n_sem = 0;
+
+  int pending = 0;
+  if (lane == 0) pending = atomicAdd(&m.counters[kCtrFetch], 1);
+  for (;;) {
+    const int w = __shfl_sync(0xffffffffu, pending, 0);
+    if (w >= n_items) break;
+    if (lane == 0) pending = atomicAdd(&m.counters[kCtrFetch], 1);
+    int box = w / ipb;
+    if constexpr (LIST) {
+      const int j = box;
+      box = j < n0 ? p.item_list[j]
+                   : (j < n0 + n1 ? p.item_list[static_cast<size_t>(p.item_list_cap) + (j - n0)]
+                                  : p.item_list[2 * static_cast<size_t>(p.item_list_cap) + (j - n0 - n1)]);
+    }
+    const uint32_t fmask = p.item_fmask[box];
+    if (!fmask) continue;
+    const int wi = box / BOXES, it = box % BOXES;
+    const int slot = p.work_slots[wi];
+    const int3 bi = m.block_index[slot];
+    const int sem = L > 0 ? m.block_sem[slot] : -1;
+    int x0, y0, z0;
+    itemOrigin<VPS>(it, x0, y0, z0);
+    uint32_t upd_all = 0;
+    bool any_have = false;
+#pragma unroll 1
+    for (int k = (w % ipb) * lpi; k < (w % ipb) * lpi + lpi; ++k) {
+      const int vx = x0 + (lane & 3), vy = y0 + (lane >> 2), vz = z0 + k;
+      const int lin = vx + VPS * (vy + VPS * vz);
+      const size_t gi = static_cast<size_t>(slot) * V + lin;
+      const float wx = static_cast<float>(bi.x) * p.block_size + (static_cast<float>(vx) + 0.5f) * p.voxel_size;
+      const float wy = static_cast<float>(bi.y) * p.block_size + (static_cast<float>(vy) + 0.5f) * p.voxel_size;
+      const float wz = static_cast<float>(bi.z) * p.block_size + (static_cast<float>(vz) + 0.5f) * p.voxel_size;
+      float2 st = make_float2(0.f, 0.f);
+      uint32_t lobs = 0, vfl = 0, upd_frames = 0;
+      bool have = false, row_resident = false;
+      int best_label = 0;
+
+      uint32_t rem = fmask;  // warp-uniform
+#pragma unroll 1
+      while (rem) {
+        int fb[G];
+        bool ok[G], inside[G];
+        int u0[G], v0[G];
+        float fz[G], du[G], dv[G], r0[G], r1[G], r2[G], r3[G];
+        // ---- phase A: projections and depth taps of up to G frames (no dependence on the voxel state)
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          ok[g] = false;
+          fb[g] = 0;
+          if (rem) {
+            const int b = __ffs(rem) - 1;
+            rem &= rem - 1;
+            fb[g] = b;
+            const FrameView& f = p.f[b];
+            float x, y, z;
+            xform(f.R, f.t, wx, wy, wz, x, y, z);
+            const float zs = z > 0.f ? z : 1.f;  // z <= 0: the voxel is skipped, the quotients are not used
+            const float u = p.fx * x / zs + p.cx;
+            const float v = p.fy * y / zs + p.cy;
+            const bool o = z > 0.f && !(u < 0.f || u > static_cast<float>(W - 1) || v < 0.f || v > static_cast<float>(H - 1));
+            const int iu = o ? static_cast<int>(floorf(u)) : 0, iv = o ? static_cast<int>(floorf(v)) : 0;
+            ok[g] = o;
+            fz[g] = z;
+            u0[g] = iu;
+            v0[g] = iv;
+            du[g] = u - static_cast<float>(iu);
+            dv[g] = v - static_cast<float>(iv);
+            inside[g] = iu + 1 < W && iv + 1 < H;
+            const int iu1 = min(iu + 1, W - 1), iv1 = min(iv + 1, H - 1);  // clamped: always a valid address
+            r0[g] = depthAt<COMPACT>(f, iv * W + iu);
+            r2[g] = depthAt<COMPACT>(f, iv * W + iu1);
+            r1[g] = depthAt<COMPACT>(f, iv1 * W + iu);
+            r3[g] = depthAt<COMPACT>(f, iv1 * W + iu1);
+          }
+        }
+        // ---- phase B1: taps, sdf, weight; label / mask taps of the G frames issued together
+        bool valid[G], band[G];
+        float sdfc[G], wm[G];
+        uint32_t lab[G];
+        int maskv[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          valid[g] = false;
+          band[g] = false;
+          sdfc[g] = 0.f;
+          wm[g] = 0.f;
+          lab[g] = 0;
+          maskv[g] = 0;
+          if (!ok[g]) continue;
+          const FrameView& f = p.f[fb[g]];
+          // computeTaps restated on the four loaded taps. Nearest pixel: round(u) = floor(u) + (du >= 0.5) for u >= 0.
+          const bool ru = du[g] >= 0.5f, rv = dv[g] >= 0.5f;
+          const float rn = ru ? (rv ? r3[g] : r2[g]) : (rv ? r1[g] : r0[g]);
+          bool tv = false, bil = false;
+          float range = 0.f, w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
+          if (p.interp == KB_INTERP_NEAREST) {
+            tv = rn > 0.f;
+            range = rn;
+          } else {
+            bool use_nearest = !inside[g], reject = false;
+            if (inside[g]) {
+              const bool all_valid = r0[g] > 0.f && r1[g] > 0.f && r2[g] > 0.f && r3[g] > 0.f;
+              if (p.interp == KB_INTERP_ADAPTIVE) {
+                const float mx = fmaxf(fmaxf(r0[g], r1[g]), fmaxf(r2[g], r3[g]));
+                const float mn = fminf(fminf(r0[g], r1[g]), fminf(r2[g], r3[g]));
+                use_nearest = !all_valid || !(mx - mn < p.adaptive_thr);
+              } else if (!all_valid) {
+                reject = true;  // bilinear: invalid
+              }
+            } else if (p.interp != KB_INTERP_ADAPTIVE) {
+              reject = true;
+            }
+            if (!reject) {
+              if (use_nearest) {
+                tv = rn > 0.f;
+                range = rn;
+              } else {
+                tv = true;
+                bil = true;
+                w0 = (1.f - du[g]) * (1.f - dv[g]);
+                w1 = (1.f - du[g]) * dv[g];
+                w2 = du[g] * (1.f - dv[g]);
+                w3 = du[g] * dv[g];
+                range = ((w0 * r0[g] + w1 * r1[g]) + w2 * r2[g]) + w3 * r3[g];
+              }
+            }
+          }
+          if (!tv) continue;
+          const float sdf = range - fz[g];
+          if (sdf < -p.trunc) continue;
+          valid[g] = true;
+          band[g] = fabsf(sdf) < p.trunc;
+          sdfc[g] = fminf(fmaxf(sdf, -p.trunc), p.trunc);
+          wm[g] = measurementWeight(p, fz[g], sdf);
+          if (band[g]) {
+            // interpolateID pixel: dominant bilinear tap (ties -> lowest tap index) or the nearest pixel
+            int tu = u0[g] + (ru ? 1 : 0), tvv = v0[g] + (rv ? 1 : 0);
+            if (bil) {
+              int best = 0;
+              float bw = w0;
+              if (w1 > bw) { best = 1; bw = w1; }
+              if (w2 > bw) { best = 2; bw = w2; }
+              if (w3 > bw) { best = 3; }
+              tu = u0[g] + (best >> 1);
+              tvv = v0[g] + (best & 1);
+            }
+            const int ti = tvv * W + tu;
+            if (f.mask != nullptr) maskv[g] = __ldg(&f.mask[ti]);
+            const bool has_label_img = L > 0 && (binary ? f.object_image != nullptr : (COMPACT ? f.label8 != nullptr : f.label != nullptr));
+            if (has_label_img) {
+              if (binary) lab[g] = __ldg(&f.object_image[ti]) == f.target_id ? 1u : 0u;
+              else lab[g] = static_cast<uint32_t>(labelAt<COMPACT>(f, ti));
+            }
+          }
+        }
+        // ---- phase B2: the G updates in frame order (the only part that depends on the voxel state)
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          if (!valid[g]) continue;
+          const int b = fb[g];
+          const FrameView& f = p.f[b];
+          const bool has_label_img = L > 0 && (binary ? f.object_image != nullptr : (COMPACT ? f.label8 != nullptr : f.label != nullptr));
+          const uint32_t label = lab[g];
+          if (band[g]) {
+            if (maskv[g] != 0) continue;
+            if (has_label_img && !binary && label < static_cast<uint32_t>(KB_MAX_LABELS) && ((p.blocked_mask >> label) & 1ull)) continue;
+          }
+          if (!have) {
+            st = m.tsdf[gi];
+            have = true;
+            if (p.with_tracking) vfl = trackingFold(m, p.trk, m.born_frame[slot], gi);
+          }
+          const float2 old = st;
+          st.x = (old.x * old.y + sdfc[g] * wm[g]) / (old.y + wm[g]);
+          st.y = fminf(old.y + wm[g], p.max_weight);
+          lobs = f.frame_idx;
+          upd_frames |= 1u << b;
+          ++n_valid;
+          if (!band[g]) continue;
+          ++n_band;
+          if (sem >= 0 && has_label_img && label < static_cast<uint32_t>(L)) {
+            const size_t si = static_cast<size_t>(sem) * V + lin;
+            if (!row_resident) {
+              row_resident = true;
+              const bool empty = m.sem_label[si] == kSemEmpty;
+              if (binary) {
+                const float2 c = empty ? make_float2(0.f, 0.f) : *reinterpret_cast<const float2*>(m.sem_lik + si * 2);
+                s_rows[threadIdx.x] = c.x;
+                s_rows[kFuseThreads + threadIdx.x] = c.y;
+              } else {
+                const float4* __restrict__ lk = reinterpret_cast<const float4*>(m.sem_lik + si * m.Lp);
+                for (int k4 = 0; k4 < m.Lp; k4 += 4) {
+                  const float4 c = empty ? make_float4(p.mle_init, p.mle_init, p.mle_init, p.mle_init) : lk[k4 >> 2];
+                  s_rows[(k4 + 0) * kFuseThreads + threadIdx.x] = c.x;
+                  s_rows[(k4 + 1) * kFuseThreads + threadIdx.x] = c.y;
+                  s_rows[(k4 + 2) * kFuseThreads + threadIdx.x] = c.z;
+                  s_rows[(k4 + 3) * kFuseThreads + threadIdx.x] = c.w;
+                }
+              }
+            }
+            if (binary) {
+              const float c = s_rows[label * kFuseThreads + threadIdx.x] + 1.f;
+              s_rows[label * kFuseThreads + threadIdx.x] = c;
+              best_label = s_rows[kFuseThreads + threadIdx.x] > s_rows[threadIdx.x] ? 1 : 0;
+            } else {
+              float bestv = 0.f;
+              for (int kk = 0; kk < L; ++kk) {
+                const float c = s_rows[kk * kFuseThreads + threadIdx.x] + (static_cast<uint32_t>(kk) == label ? p.mle_diag : p.mle_off);
+                s_rows[kk * kFuseThreads + threadIdx.x] = c;
+                if (kk == 0 || c > bestv) { bestv = c; best_label = kk; }
+              }
+            }
+            ++n_sem;
+          }
+        }
+      }
+
+      if (have) {
+        m.tsdf[gi] = st;
+        if (p.with_tracking) {
+          m.last_obs[gi] = lobs;
+          m.vflags[gi] = static_cast<uint8_t>(vfl | (st.x < p.occ_thr ? 0 : kVoxNotOccupied));
+        }
+        if (row_resident) {
+          const size_t si = static_cast<size_t>(sem) * V + lin;
+          if (binary) {
+            *reinterpret_cast<float2*>(m.sem_lik + si * 2) = make_float2(s_rows[threadIdx.x], s_rows[kFuseThreads + threadIdx.x]);
+          } else {
+            float4* __restrict__ lk = reinterpret_cast<float4*>(m.sem_lik + si * m.Lp);
+            for (int k4 = 0; k4 < m.Lp; k4 += 4)
+              lk[k4 >> 2] = make_float4(s_rows[(k4 + 0) * kFuseThreads + threadIdx.x], s_rows[(k4 + 1) * kFuseThreads + threadIdx.x],
+                                        s_rows[(k4 + 2) * kFuseThreads + threadIdx.x], s_rows[(k4 + 3) * kFuseThreads + threadIdx.x]);
+          }
+          m.sem_label[si] = static_cast<uint16_t>(best_label);
+        }
+      }
+      upd_all |= upd_frames;
+      any_have |= have;
+    }  // layers of the item
+    if (__any_sync(0xffffffffu, any_have)) {
+      uint32_t upd_frames = upd_all;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) upd_frames |= __shfl_xor_sync(0xffffffffu, upd_frames, o);
+      if (lane == 0) {
+        const uint32_t all = KB_FLAG_UPDATED | KB_FLAG_MESH_UPDATED | KB_FLAG_ESDF_UPDATED | KB_FLAG_TRACKING_UPDATED;
+        if ((m.block_flags[slot] & all) != all) atomicOr(&m.block_flags[slot], all);
+        if ((p.work_upd[wi] & upd_frames) != upd_frames) {
+          const uint32_t prev = atomicOr(&p.work_upd[wi], upd_frames);
+          const int fresh = __popc(upd_frames & ~prev);
+          if (fresh) atomicAdd(&m.counters[kCtrBlocksUpdated], fresh);
+        }
+      }
+    }
+  }
+  n_valid = warpSum(n_valid);
+  if (n_valid) {
+    n_band = warpSum(n_band);
+    n_sem = warpSum(n_sem);
+    if (lane == 0) {
+      atomicAdd(&m.counters[kCtrVoxelsUpdated], n_valid);
+      if (n_band) atomicAdd(&m.counters[kCtrVoxelsBand], n_band);
+      if (n_sem) atomicAdd(&m.counters[kCtrVoxelsSemantic], n_sem);
+    }
+  }
+}
+
 // ---- K2 (lazy): TrackingIntegrator::updateBlockTracking (tracking_integrator.cpp:133-166,224-246) ------
 // The reference rewrites last_occupied / active / to_remove of EVERY voxel of EVERY allocated block each
 // frame (~10 GB/frame at 50 k blocks). All three are pure functions of (distance, last_observed, the
@@ -1177,6 +1476,26 @@ void launchFuse(const DeviceMap& m, const BatchParams& p, int grid, cudaStream_t
     else if (p.item_list) fuseKernel<V, LP, C, false, true><<<grid, kFuseThreads, smem, s>>>(m, p); \
     else fuseKernel<V, LP, C, false><<<grid, kFuseThreads, smem, s>>>(m, p);                     \
   } while (0)
+#define KB_FUSE_MLP(V, LP, C)                                                                                        \
+  do {                                                                                                               \
+    if (p.mlp_group == 2) {                                                                                          \
+      if (p.item_list) fuseKernelMlp<V, LP, C, 2, true><<<grid, kFuseThreads, smem, s>>>(m, p);                      \
+      else fuseKernelMlp<V, LP, C, 2, false><<<grid, kFuseThreads, smem, s>>>(m, p);                                 \
+    } else {                                                                                                         \
+      if (p.item_list) fuseKernelMlp<V, LP, C, 4, true><<<grid, kFuseThreads, smem, s>>>(m, p);                      \
+      else fuseKernelMlp<V, LP, C, 4, false><<<grid, kFuseThreads, smem, s>>>(m, p);                                 \
+    }                                                                                                                \
+  } while (0)
+  if (p.mlp_group != 0 && !col) {  // experiment: memory-level-parallel variant (same results)
+    if (m.vps == 16) {
+      if (one) { if (c) KB_FUSE_MLP(16, 1, true); else KB_FUSE_MLP(16, 1, false); }
+      else { if (c) KB_FUSE_MLP(16, 4, true); else KB_FUSE_MLP(16, 4, false); }
+    } else {
+      if (one) { if (c) KB_FUSE_MLP(8, 1, true); else KB_FUSE_MLP(8, 1, false); }
+      else { if (c) KB_FUSE_MLP(8, 4, true); else KB_FUSE_MLP(8, 4, false); }
+    }
+    return;
+  }
   if (m.vps == 16) {
     if (one) { if (c) KB_FUSE(16, 1, true); else KB_FUSE(16, 1, false); }
     else { if (c) KB_FUSE(16, 4, true); else KB_FUSE(16, 4, false); }
@@ -1185,6 +1504,7 @@ void launchFuse(const DeviceMap& m, const BatchParams& p, int grid, cudaStream_t
     else { if (c) KB_FUSE(8, 4, true); else KB_FUSE(8, 4, false); }
   }
 #undef KB_FUSE
+#undef KB_FUSE_MLP
 }
 void launchTrackingPass(const DeviceMap& m, const TrackingParams& p, int everfree_grid, cudaStream_t s) {
   trackingPassKernel<<<(std::max(p.n_slots, 1) + 255) / 256, 256, 0, s>>>(m, p);

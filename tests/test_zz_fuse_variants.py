@@ -1,0 +1,105 @@
+"""Experimental fuse-kernel variants (all off by default, selected by environment variables read in kb_create):
+  KB_FUSE_ITEM_LIST=1  items come from compacted heaviest-first lists instead of the dense box range
+  KB_FUSE_MLP=2|4      fuseKernelMlp: the frames of an item are processed in groups whose depth / label taps are issued
+                       together (memory-level parallelism); nearest-pixel fallback selected from the four loaded taps
+Only the processing order / instruction schedule changes: every result must stay bit-identical to the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+from khronos_b200 import capi, synthetic as syn
+import harness as hs
+from test_parity_gpu import room_frames
+
+pytestmark = pytest.mark.gpu
+
+VARIANTS = [{"KB_FUSE_ITEM_LIST": "1"}, {"KB_FUSE_MLP": "2"}, {"KB_FUSE_MLP": "4"}, {"KB_FUSE_MLP": "4", "KB_FUSE_ITEM_LIST": "1"}]
+
+
+@pytest.fixture(params=VARIANTS, ids=lambda v: "+".join(f"{k[8:]}={x}" for k, x in v.items()))
+def variant_env(request):
+    os.environ.update(request.param)   # read by kb_create
+    yield request.param
+    for k in request.param:
+        os.environ.pop(k, None)
+
+
+def batched(g, frames, poses, stamps, batch, masks=None, **kw):
+    for i in range(0, len(frames), batch):
+        fr = [g.make_frame(d, T, st, label=l, mask=None if masks is None else masks[i + j], **kw)
+              for j, ((d, l), T, st) in enumerate(zip(frames[i:i + batch], poses[i:i + batch], stamps[i:i + batch]))]
+        g.integrate_frames(fr)
+
+
+@pytest.mark.parametrize("vps,batch", [(16, 32), (16, 11), (8, 32)])
+def test_variant_hall_sweep_is_bit_identical(oracle_lib, product_lib, variant_env, vps, batch):
+    cam = hs.small_camera(4)
+    scene = syn.hall_scene(size=(20.0, 16.0, 6.0))
+    poses, stamps = syn.sweep_trajectory(40, size=(20.0, 16.0), margin=4.0, lanes=2, yaw_turns=1.5)
+    frames = hs.render_frames(scene, cam, poses, stamps)
+    mc = capi.default_map_config(voxel_size=0.05 if vps == 16 else 0.1, vps=vps, trunc=0.15 if vps == 16 else 0.3, max_blocks=16384)
+    o = hs.make_handle(oracle_lib, "ko_", cam=cam, map_cfg=mc)
+    g = hs.make_handle(product_lib, "kb_", cam=cam, map_cfg=mc)
+    so = hs.run_fusion(o, frames, poses, stamps)
+    for i in range(0, len(frames), batch):
+        fr = [g.make_frame(d, T, st, label=l) for (d, l), T, st in zip(frames[i:i + batch], poses[i:i + batch], stamps[i:i + batch])]
+        s = g.integrate_frames(fr).as_dict()
+        want = {k: sum(x[k] for x in so[i:i + batch]) for k in s}
+        want["total_blocks"] = so[min(i + batch, len(so)) - 1]["total_blocks"]
+        assert s == want, (i, s, want)
+    hs.assert_blocks_equal(o.export_blocks(), g.export_blocks(), exact_float=True, what=f"{variant_env} vps{vps} batch{batch}")
+
+
+@pytest.mark.parametrize("interp", [capi.INTERP_ADAPTIVE, capi.INTERP_NEAREST, capi.INTERP_BILINEAR])
+def test_variant_masks_blocked_labels_interpolators_tracking(oracle_lib, product_lib, variant_env, interp):
+    cam = hs.small_camera(4)
+    frames, poses, stamps = room_frames(cam, 24, laps=0.3)
+    rng = np.random.default_rng(4)
+    masks = []
+    for _ in frames:
+        mk = np.zeros((cam.height, cam.width), np.int32)
+        mk[20:70, 30:90] = rng.integers(0, 3, size=(50, 60))
+        masks.append(mk)
+    ic = capi.default_integrator_config(interpolation=interp, blocked=(4, 9), num_threads=4)
+    o = hs.make_handle(oracle_lib, "ko_", cam=cam, integ_cfg=ic)
+    g = hs.make_handle(product_lib, "kb_", cam=cam, integ_cfg=ic)
+    g.set_culling(2)
+    hs.run_fusion(o, frames[:12], poses[:12], stamps[:12], masks=masks[:12])
+    o.update_tracking(stamps[11])
+    hs.run_fusion(o, frames[12:], poses[12:], stamps[12:], masks=masks[12:])
+    o.update_tracking(stamps[-1])
+    batched(g, frames[:12], poses[:12], stamps[:12], 12, masks=masks[:12])
+    g.update_tracking(stamps[11])
+    batched(g, frames[12:], poses[12:], stamps[12:], 12, masks=masks[12:])
+    g.update_tracking(stamps[-1])
+    hs.assert_blocks_equal(o.export_blocks(), g.export_blocks(), exact_float=True, what=f"{variant_env} interp{interp}")
+
+
+def test_variant_compact_frames_and_binary_extraction_map(oracle_lib, product_lib, variant_env):
+    cam = hs.small_camera(4)
+    frames, poses, stamps = room_frames(cam, 16, laps=0.2)
+    d16 = [np.round(d * 1000.0).astype(np.uint16) for d, _ in frames]
+    l8 = [l.astype(np.uint8) for _, l in frames]
+    o = hs.make_handle(oracle_lib, "ko_", cam=cam)
+    g = hs.make_handle(product_lib, "kb_", cam=cam)
+    g.set_culling(2)
+    for i in range(16):
+        o.integrate_frame(o.make_frame(None, poses[i], stamps[i], depth_u16=d16[i], label_u8=l8[i]), want_stats=False)
+    g.integrate_frames([g.make_frame(None, poses[i], stamps[i], depth_u16=d16[i], label_u8=l8[i]) for i in range(16)], want_stats=False)
+    hs.assert_blocks_equal(o.export_blocks(), g.export_blocks(), exact_float=True, what=f"{variant_env} compact taps")
+    # the extractor's private map: vps 8, binary semantics, no tracking, pre-allocated, 16 frames in one call
+    mc = capi.default_map_config(voxel_size=0.04, vps=8, trunc=0.08, with_tracking=False, max_blocks=32768)
+    ic = capi.default_integrator_config(semantic_mode=capi.SEM_BINARY)
+    o2 = hs.make_handle(oracle_lib, "ko_", cam=cam, map_cfg=mc, integ_cfg=ic)
+    g2 = hs.make_handle(product_lib, "kb_", cam=cam, map_cfg=mc, integ_cfg=ic)
+    g2.set_culling(2)
+    bs = 0.04 * 8
+    lo, hi = np.floor(np.array([1.5, 1.5, -0.3]) / bs).astype(int), np.floor(np.array([3.5, 4.0, 1.7]) / bs).astype(int)
+    for h in (o2, g2):
+        h.allocate_box(lo, hi)
+    for (d, l), T, st in zip(frames, poses, stamps):
+        o2.integrate_frame(o2.make_frame(d, T, st, object_image=l, target_id=7), allocate_blocks=False, want_stats=False)
+    g2.integrate_frames([g2.make_frame(d, T, st, object_image=l, target_id=7) for (d, l), T, st in zip(frames, poses, stamps)],
+                        allocate_blocks=False, want_stats=False)
+    hs.assert_blocks_equal(o2.export_blocks(), g2.export_blocks(), exact_float=True, what=f"{variant_env} binary vps8")

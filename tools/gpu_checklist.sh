@@ -4,15 +4,18 @@
 # Outputs land in gpurun_out/ (copy the summaries worth keeping to profiles/).
 set -u
 mkdir -p gpurun_out
-echo "== 1. GPU tests not yet run on hardware (object detection, item-list variant)"
-timeout 300 python -m pytest tests/test_zz_object_detection.py tests/test_zz_item_list.py -m gpu -q --tb=short -p no:cacheprovider \
+echo "== 1. GPU tests not yet run on hardware (object detection, experimental fuse variants)"
+timeout 300 python -m pytest tests/test_zz_object_detection.py tests/test_zz_fuse_variants.py -m gpu -q --tb=short -p no:cacheprovider \
   > gpurun_out/zz_tests.log 2>&1; tail -5 gpurun_out/zz_tests.log
 echo "== 2. headline bench, default vs compacted heaviest-first item lists"
 timeout 200 python bench.py --no-e2e --no-cpu-baseline > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err
 KB_FUSE_ITEM_LIST=1 timeout 200 python bench.py --no-e2e --no-cpu-baseline > gpurun_out/bench_item_list.json 2> gpurun_out/bench_item_list.err
+KB_FUSE_MLP=2 timeout 200 python bench.py --no-e2e --no-cpu-baseline > gpurun_out/bench_mlp2.json 2> gpurun_out/bench_mlp2.err
+KB_FUSE_MLP=4 timeout 200 python bench.py --no-e2e --no-cpu-baseline > gpurun_out/bench_mlp4.json 2> gpurun_out/bench_mlp4.err
+KB_FUSE_MLP=4 KB_FUSE_ITEM_LIST=1 timeout 200 python bench.py --no-e2e --no-cpu-baseline > gpurun_out/bench_mlp4_list.json 2> gpurun_out/bench_mlp4_list.err
 python - <<'PY'
 import json
-for n in ("default", "item_list"):
+for n in ("default", "item_list", "mlp2", "mlp4", "mlp4_list"):
     try:
         d = json.load(open(f"gpurun_out/bench_{n}.json"))
         print(n, round(d["value"]), "fps", d["roofline"]["launch_us"], "us/launch", d["clocks"])
