@@ -158,3 +158,38 @@ def test_product_shards_tracking_only_with_removal(oracle_lib, product_lib):
             removed += len(ro)
     assert removed > 0
     assert_union_equals([g.export_blocks() for g in shards], o.export_blocks(), "tracking-only shards")
+
+
+@pytest.mark.parametrize("nshards,conn,seed", [(4, 6, 0), (8, 26, 1), (5, 18, 2)])
+def test_oracle_shards_random_walk(oracle_lib, nshards, conn, seed):
+    """Random camera walk through the room (irregular frame periods, so blocks enter and leave the ever-free work list
+    at different passes on different shards), all three ever-free connectivities, up to 8 shards."""
+    rng = np.random.default_rng(seed)
+    cam = hs.small_camera(8)
+    scene = syn.room_scene()
+    n = 16
+    poses, stamps, t = [], [], 1_000_000_000
+    pos, yaw = np.array([6.0, 5.0, 1.5]), 0.0
+    for _ in range(n):
+        pos = np.clip(pos + rng.normal(0, 0.15, 3) * np.array([1, 1, 0.2]), [3, 3, 1.0], [9, 7, 2.0])
+        yaw += rng.normal(0, 0.15)
+        poses.append(syn.look_pose(tuple(pos), yaw, np.radians(10.0)))
+        t += int(rng.integers(100_000_000, 400_000_000))
+        stamps.append(t)
+    frames = hs.render_frames(scene, cam, poses, stamps)
+    trk = capi.default_tracking_config(num_threads=2)
+    trk.neighbor_connectivity = conn
+    mot = capi.default_motion_config(min_cluster_size=3, min_separation_distance=1.0, num_threads=2)
+    o = hs.make_handle(oracle_lib, "ko_", cam=cam, trk_cfg=trk, mot_cfg=mot)
+    shards = [hs.make_handle(oracle_lib, "ko_", cam=cam, trk_cfg=trk, mot_cfg=mot) for _ in range(nshards)]
+    for r, g in enumerate(shards):
+        g.set_shard(r, nshards)
+    win = kd.ShardedActiveWindow(shards, kd.LocalComm(), device="cpu")
+    for (d, l), T, st in zip(frames, poses, stamps):
+        img_o, ns_o, nc_o = o.spin_once(o.make_frame(d, T, st, label=l))
+        for img, ns, nc in win.spin_once([g.make_frame(d, T, st, label=l) for g in shards]):
+            assert (ns, nc) == (ns_o, nc_o)
+            np.testing.assert_array_equal(img, img_o)
+    bo = o.export_blocks()
+    assert_union_equals([g.export_blocks() for g in shards], bo, f"random walk {nshards} shards conn {conn}")
+    assert bo.ever_free.sum() > 100
