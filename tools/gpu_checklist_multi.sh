@@ -12,6 +12,11 @@ for w in f32 f32u8; do
   timeout 300 $TR bench.py --gpus $N --wire $w > gpurun_out/bench_n${N}_$w.json 2> gpurun_out/bench_n${N}_$w.err
   python -c "import json;d=json.load(open('gpurun_out/bench_n${N}_$w.json'));print('$w', round(d['value']), 'fps', d['ms_per_step'], 'ms/step')" || tail -3 gpurun_out/bench_n${N}_$w.err
 done
+echo "== 2b. is the frame broadcast channel-limited? (the f32 wire is broadcast bound at ~280 GB/s)"
+for ch in 16 32; do
+  NCCL_MIN_NCHANNELS=$ch timeout 300 $TR bench.py --gpus $N --wire f32 > gpurun_out/bench_n${N}_f32_ch$ch.json 2> gpurun_out/bench_n${N}_f32_ch$ch.err
+  python -c "import json;d=json.load(open('gpurun_out/bench_n${N}_f32_ch$ch.json'));print('NCCL_MIN_NCHANNELS=$ch', round(d['value']), 'fps')" || true
+done
 echo "== 3. per-frame pipeline (config[2]) sharded over $N GPUs"
 timeout 300 $TR bench.py --gpus $N --workload dynamic --steps 4 --warmup 2 > gpurun_out/bench_n${N}_dynamic.json 2> gpurun_out/bench_n${N}_dynamic.err
 tail -c 700 gpurun_out/bench_n${N}_dynamic.json || tail -3 gpurun_out/bench_n${N}_dynamic.err
