@@ -1208,6 +1208,10 @@ __global__ void __launch_bounds__(kThreads) resetInactiveKernel(const DeviceMap 
   const int V = m.V;
   const size_t base = static_cast<size_t>(slot) * V;
   const uint32_t born = m.born_frame[slot];
+  // read before the block-wide reductions below: thread 0 resets block_sem at the end, and without a barrier in
+  // between a slow warp could otherwise see -1 and skip scrubbing its part of the semantic slot (found by running
+  // the kernels under tools/cuda_emu, whose sequential fiber schedule makes thread 0 finish first)
+  const int sem = m.block_sem[slot];
   int all_remove = 1, any_active = 0;
   for (int lin = threadIdx.x; lin < V; lin += kThreads) {
     uint32_t c;
@@ -1223,7 +1227,6 @@ __global__ void __launch_bounds__(kThreads) resetInactiveKernel(const DeviceMap 
   const bool has_active = seen && any_active && !(flags & kFlagInactiveOverride);
   if (has_active && !all_remove) return;
   // Remove: scrub the slot so that a later allocation starts from the default voxel state.
-  const int sem = m.block_sem[slot];
   for (int lin = threadIdx.x; lin < V; lin += kThreads) {
     m.tsdf[base + lin] = make_float2(0.f, 0.f);
     m.last_obs[base + lin] = 0;
