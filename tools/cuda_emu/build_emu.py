@@ -25,6 +25,11 @@ def rewrite(src: str) -> str:
 
 
 def build(verbose=False):
+    deps = [os.path.join(CSRC, n) for n in os.listdir(CSRC) if n.endswith((".cu", ".cuh", ".h", ".cpp"))]
+    deps += [os.path.join(HERE, "emu_runtime.cpp"), os.path.join(HERE, "include", "cuda_runtime.h"), os.path.abspath(__file__),
+             os.path.join(ROOT, "include", "khronos_b200.h")]
+    if os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps):
+        return LIB
     os.makedirs(OUT, exist_ok=True)
     os.makedirs(os.path.join(OUT, "include"), exist_ok=True)
     srcs = []
