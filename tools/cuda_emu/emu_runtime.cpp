@@ -1,6 +1,4 @@
 // TEST TOOLING — NOT PRODUCT CODE. Fiber scheduler of the CUDA-on-CPU shim (see include/cuda_runtime.h).
-#include <ucontext.h>
-
 #include <cstdio>
 #include <vector>
 
@@ -15,8 +13,34 @@ namespace {
 enum State { kRunnable, kWaitWarp, kWaitBlock, kDone };
 constexpr size_t kStack = 256 * 1024;
 
+// Minimal x86-64 System V context switch (callee-saved registers + stack pointer): ucontext's swapcontext makes two
+// signal-mask system calls per switch, which dominated the run time.
+extern "C" void emu_switch(void** save_sp, void* load_sp);
+asm(R"(
+.text
+.globl emu_switch
+.type emu_switch,@function
+emu_switch:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    movq %rsp, (%rdi)
+    movq %rsi, %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+.size emu_switch,.-emu_switch
+)");
+
 struct Fiber {
-  ucontext_t ctx;
+  void* sp = nullptr;
   char* stack = nullptr;
   State state = kDone;
   uint3 tid{0, 0, 0};
@@ -29,22 +53,34 @@ struct Fiber {
 };
 
 std::vector<Fiber> g_fibers;
-ucontext_t g_sched;
+void* g_sched_sp = nullptr;
 int g_current = -1, g_nthreads = 0;
 std::function<void()>* g_body = nullptr;
 std::vector<char> g_smem;
 std::vector<unsigned> g_warp_mask;  // participants of the exchange a warp was last released from
+const bool g_reverse = [] { const char* e = std::getenv("KB_EMU_ORDER"); return e && e[0] == 'r'; }();
 
 void trampoline() {
   (*g_body)();
   g_fibers[g_current].state = kDone;
-  swapcontext(&g_fibers[g_current].ctx, &g_sched);
+  emu_switch(&g_fibers[g_current].sp, g_sched_sp);
+  std::abort();  // a finished fiber is never resumed
 }
 
 void yield(State st) {
   Fiber& f = g_fibers[g_current];
   f.state = st;
-  swapcontext(&f.ctx, &g_sched);
+  emu_switch(&f.sp, g_sched_sp);
+}
+
+// Prepares a fresh stack so that the first switch into the fiber "returns" into trampoline().
+void prepare(Fiber& f) {
+  uintptr_t top = (reinterpret_cast<uintptr_t>(f.stack) + kStack) & ~uintptr_t(15);
+  void** sp = reinterpret_cast<void**>(top);
+  *--sp = nullptr;                                   // fake return address of trampoline (keeps rsp % 16 == 8 at entry)
+  *--sp = reinterpret_cast<void*>(&trampoline);      // popped by `ret` in emu_switch
+  for (int i = 0; i < 6; ++i) *--sp = nullptr;       // rbp, rbx, r12-r15
+  f.sp = sp;
 }
 
 void run_block() {
@@ -53,11 +89,7 @@ void run_block() {
   for (int i = 0; i < n; ++i) {
     Fiber& f = g_fibers[i];
     if (!f.stack) f.stack = static_cast<char*>(std::malloc(kStack));
-    getcontext(&f.ctx);
-    f.ctx.uc_stack.ss_sp = f.stack;
-    f.ctx.uc_stack.ss_size = kStack;
-    f.ctx.uc_link = &g_sched;
-    makecontext(&f.ctx, trampoline, 0);
+    prepare(f);
     f.state = kRunnable;
     f.wgen = f.bgen = 0;
     f.tid = {static_cast<unsigned>(i % blockDim.x), static_cast<unsigned>((i / blockDim.x) % blockDim.y),
@@ -66,11 +98,12 @@ void run_block() {
   int remaining = n;
   while (remaining > 0) {
     bool progress = false;
-    for (int i = 0; i < n; ++i) {
+    for (int k = 0; k < n; ++k) {
+      const int i = g_reverse ? n - 1 - k : k;  // KB_EMU_ORDER=reverse: last thread first (another extreme schedule)
       if (g_fibers[i].state != kRunnable) continue;
       g_current = i;
       threadIdx = g_fibers[i].tid;
-      swapcontext(&g_sched, &g_fibers[i].ctx);
+      emu_switch(&g_sched_sp, g_fibers[i].sp);
       progress = true;
       if (g_fibers[i].state == kDone) --remaining;
     }
@@ -116,12 +149,13 @@ void launch_(std::function<void()> body, dim3 grid, dim3 block, size_t smem, cud
   g_nthreads = static_cast<int>(block.x * block.y * block.z);
   if (static_cast<int>(g_fibers.size()) < g_nthreads) g_fibers.resize(g_nthreads);
   g_smem.assign(smem + 16, 0);
-  for (unsigned bz = 0; bz < grid.z; ++bz)
-    for (unsigned by = 0; by < grid.y; ++by)
-      for (unsigned bx = 0; bx < grid.x; ++bx) {
-        blockIdx = {bx, by, bz};
-        run_block();
-      }
+  const unsigned long long n_blocks = static_cast<unsigned long long>(grid.x) * grid.y * grid.z;
+  for (unsigned long long k = 0; k < n_blocks; ++k) {
+    const unsigned long long b = g_reverse ? n_blocks - 1 - k : k;
+    blockIdx = {static_cast<unsigned>(b % grid.x), static_cast<unsigned>((b / grid.x) % grid.y),
+                static_cast<unsigned>(b / (static_cast<unsigned long long>(grid.x) * grid.y))};
+    run_block();
+  }
   g_body = nullptr;
 }
 
