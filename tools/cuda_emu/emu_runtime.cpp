@@ -58,7 +58,16 @@ int g_current = -1, g_nthreads = 0;
 std::function<void()>* g_body = nullptr;
 std::vector<char> g_smem;
 std::vector<unsigned> g_warp_mask;  // participants of the exchange a warp was last released from
+// Scheduling order of the fibers within a pass (and of the blocks): KB_EMU_ORDER = forward (default) | reverse |
+// shuffle (a fresh pseudo-random permutation per pass, seeded by KB_EMU_SEED): different extremes of what a GPU may do.
 const bool g_reverse = [] { const char* e = std::getenv("KB_EMU_ORDER"); return e && e[0] == 'r'; }();
+const bool g_shuffle = [] { const char* e = std::getenv("KB_EMU_ORDER"); return e && e[0] == 's'; }();
+unsigned long long g_rng = [] { const char* e = std::getenv("KB_EMU_SEED"); return 0x9E3779B97F4A7C15ull ^ (e ? std::strtoull(e, nullptr, 10) : 1ull); }();
+inline unsigned rnd(unsigned n) {  // xorshift64*
+  g_rng ^= g_rng >> 12; g_rng ^= g_rng << 25; g_rng ^= g_rng >> 27;
+  return static_cast<unsigned>(((g_rng * 0x2545F4914F6CDD1Dull) >> 33) % n);
+}
+std::vector<int> g_order;
 
 void trampoline() {
   (*g_body)();
@@ -98,8 +107,13 @@ void run_block() {
   int remaining = n;
   while (remaining > 0) {
     bool progress = false;
+    if (g_shuffle) {
+      g_order.resize(n);
+      for (int k = 0; k < n; ++k) g_order[k] = k;
+      for (int k = n - 1; k > 0; --k) std::swap(g_order[k], g_order[rnd(k + 1)]);
+    }
     for (int k = 0; k < n; ++k) {
-      const int i = g_reverse ? n - 1 - k : k;  // KB_EMU_ORDER=reverse: last thread first (another extreme schedule)
+      const int i = g_shuffle ? g_order[k] : (g_reverse ? n - 1 - k : k);
       if (g_fibers[i].state != kRunnable) continue;
       g_current = i;
       threadIdx = g_fibers[i].tid;
