@@ -63,6 +63,16 @@ struct kb_handle {
   int* item_list = nullptr;    // KB_FUSE_ITEM_LIST experiment: compacted heaviest-first item lists (3 x item_list_cap)
   int item_list_cap = 0;
   bool use_item_list = false;
+  // KB_PIPELINE experiment: the prologue (tile pyramid, K0, K0b[, compaction]) of batch i+1 runs on its own stream while
+  // the fuse kernel of batch i is still busy; work lists, tile pyramids and cursors exist twice (index = batch parity)
+  bool pipelined = false;
+  cudaStream_t pre_stream = nullptr;
+  cudaEvent_t pre_done[2] = {nullptr, nullptr}, fuse_done[2] = {nullptr, nullptr}, main_front = nullptr;
+  bool main_dirty = true;      // main-stream work other than fuse kernels was enqueued since the last prologue
+  int* work_slots2 = nullptr;
+  uint32_t* work_masks2 = nullptr;
+  uint32_t* work_upd2 = nullptr;
+  uint32_t* item_fmask2 = nullptr;
   int mlp_group = 0;           // KB_FUSE_MLP experiment: 0 (off), 2 or 4 frames per memory-level-parallel group
   int cull_grid = 0;
   int parity = 0;
@@ -444,10 +454,23 @@ int kb_create(const kb_map_config* map, const kb_integrator_config* integ, const
     h->batch.items_per_block = m.V / 128;
     KB_CUDA(h, devAlloc(&h->item_fmask, S * h->batch.items_per_block, 0));
     if (const char* e = std::getenv("KB_FUSE_ITEM_LIST")) h->use_item_list = e[0] == '1';
+    if (const char* e = std::getenv("KB_PIPELINE")) h->pipelined = e[0] == '1';
+    if (h->pipelined) {
+      KB_CUDA(h, cudaStreamCreateWithFlags(&h->pre_stream, cudaStreamNonBlocking));
+      for (int i = 0; i < 2; ++i) {
+        KB_CUDA(h, cudaEventCreateWithFlags(&h->pre_done[i], cudaEventDisableTiming));
+        KB_CUDA(h, cudaEventCreateWithFlags(&h->fuse_done[i], cudaEventDisableTiming));
+      }
+      KB_CUDA(h, cudaEventCreateWithFlags(&h->main_front, cudaEventDisableTiming));
+      KB_CUDA(h, devAlloc(&h->work_slots2, S, 0));
+      KB_CUDA(h, devAlloc(&h->work_masks2, S, 0));
+      KB_CUDA(h, devAlloc(&h->work_upd2, S, 0));
+      KB_CUDA(h, devAlloc(&h->item_fmask2, S * h->batch.items_per_block, 0));
+    }
     if (const char* e = std::getenv("KB_FUSE_MLP")) h->mlp_group = e[0] == '2' ? 2 : (e[0] == '4' ? 4 : 0);
     if (h->use_item_list) {  // experiment, off by default (results are identical either way: only the item order changes)
       h->item_list_cap = static_cast<int>(std::min<size_t>(S * h->batch.items_per_block, size_t(1) << 28));
-      KB_CUDA(h, devAlloc(&h->item_list, static_cast<size_t>(3) * h->item_list_cap, 0));
+      KB_CUDA(h, devAlloc(&h->item_list, static_cast<size_t>(6) * h->item_list_cap, 0));  // 2 parities x 3 classes
     }
     {
       cudaDeviceProp prop{};
@@ -455,6 +478,10 @@ int kb_create(const kb_map_config* map, const kb_integrator_config* integ, const
       h->everfree_grid = prop.multiProcessorCount * 4;
       h->cull_grid = prop.multiProcessorCount * 8;
       h->fuse_grid = prop.multiProcessorCount * fuseBlocksPerSm(m.vps, m.Lp);  // persistent CTAs of independent warps
+      if (const char* e = std::getenv("KB_FUSE_CTAS_PER_SM")) {  // tuning knob (e.g. leave SM room for KB_PIPELINE's prologue)
+        const int n = std::atoi(e);
+        if (n > 0) h->fuse_grid = prop.multiProcessorCount * n;
+      }
     }
     h->max_removed = m.max_blocks;
     KB_CUDA(h, devAlloc(&h->d_removed, static_cast<size_t>(h->max_removed), 0));
@@ -497,6 +524,13 @@ int kb_destroy(kb_handle* h) {
     if (h->stg_consumed[i]) cudaEventDestroy(h->stg_consumed[i]);
   }
   if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+  if (h->pre_stream) { cudaStreamSynchronize(h->pre_stream); cudaStreamDestroy(h->pre_stream); }
+  for (int i = 0; i < 2; ++i) {
+    if (h->pre_done[i]) cudaEventDestroy(h->pre_done[i]);
+    if (h->fuse_done[i]) cudaEventDestroy(h->fuse_done[i]);
+  }
+  if (h->main_front) cudaEventDestroy(h->main_front);
+  cudaFree(h->work_slots2); cudaFree(h->work_masks2); cudaFree(h->work_upd2); cudaFree(h->item_fmask2);
   if (h->h_ctr) cudaFreeHost(h->h_ctr);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -504,6 +538,7 @@ int kb_destroy(kb_handle* h) {
 }
 
 int kb_set_stream(kb_handle* h, void* cuda_stream) {
+  if (h) h->main_dirty = true;  // KB_PIPELINE: the next prologue must wait for this main-stream work
   if (!h) return KB_ERR_INVALID;
   KB_CUDA(h, cudaSetDevice(h->device));
   KB_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -575,7 +610,7 @@ int kb_set_camera(kb_handle* h, const kb_camera* cam) {
   p.max_work = h->dm.max_blocks;
   cudaFree(h->tile_max);
   h->tile_max = nullptr;
-  KB_CUDA(h, devAlloc(&h->tile_max, h->tile_stride * kMaxBatch, 0));
+  KB_CUDA(h, devAlloc(&h->tile_max, h->tile_stride * kMaxBatch * 2, 0));  // two sets (KB_PIPELINE uses one per batch parity)
   return ensureMotionBuffers(h, static_cast<size_t>(c.width) * c.height);
 }
 
@@ -596,6 +631,7 @@ int kb_set_culling(kb_handle* h, int enabled) {
 }
 
 int kb_set_shard(kb_handle* h, int rank, int nranks) {
+  if (h) h->main_dirty = true;  // KB_PIPELINE: the next prologue must wait for this main-stream work
   if (!h || nranks < 1 || rank < 0 || rank >= nranks) return fail(h, KB_ERR_INVALID, "invalid shard");
   h->rank = rank;
   h->nranks = nranks;
@@ -613,6 +649,16 @@ static int integrateBatch(kb_handle* h, const kb_frame* frames, int n, int alloc
   p.nranks = h->nranks;
   p.parity = h->parity;
   h->parity ^= 1;
+  const int par = p.parity;
+  const bool pipe = h->pipelined;
+  p.pipelined = pipe ? 1 : 0;
+  p.fetch_ctr = (pipe && par) ? kCtrFetchB : kCtrFetch;
+  p.items_ctr = (pipe && par) ? kCtrItemsB0 : kCtrItems0;
+  p.work_slots = (pipe && par) ? h->work_slots2 : h->work_slots;
+  p.work_masks = (pipe && par) ? h->work_masks2 : h->work_masks;
+  p.work_upd = (pipe && par) ? h->work_upd2 : h->work_upd;
+  p.item_fmask = (pipe && par) ? h->item_fmask2 : h->item_fmask;
+  const size_t tile_set = (pipe && par) ? h->tile_stride * kMaxBatch : 0;
   // the culling stages cost ~3 extra launches: they pay off once a few frames share them
   p.cull = (h->cull && (n >= 4 || h->cull_forced)) ? 1 : 0;
   p.layers_per_item = n >= 8 ? 1 : 4;
@@ -628,7 +674,8 @@ static int integrateBatch(kb_handle* h, const kb_frame* frames, int n, int alloc
   }
   p.has_color = any_color ? 1 : 0;
   // the compacted item lists pay for their extra launch only where items are many and uneven: long culled batches
-  p.item_list = (h->use_item_list && p.cull && n >= 8 && !any_color) ? h->item_list : nullptr;
+  p.item_list = (h->use_item_list && p.cull && n >= 8 && !any_color)
+                    ? h->item_list + ((pipe && par) ? static_cast<size_t>(3) * h->item_list_cap : 0) : nullptr;
   p.item_list_cap = h->item_list_cap;
   p.mlp_group = h->mlp_group;
   if (any_color) {
@@ -678,7 +725,7 @@ static int integrateBatch(kb_handle* h, const kb_frame* frames, int n, int alloc
     if (!v.depth) return fail(h, KB_ERR_INVALID, "frame without depth image");
     if (f.mask == KB_MASK_LAST_DETECTION)  // dynamic image of the last kb_detect_motion, still on the device
       v.mask = h->motion_have_image ? h->d_dynamic : nullptr;
-    v.tiles = h->tile_max + static_cast<size_t>(b) * h->tile_stride;
+    v.tiles = h->tile_max + tile_set + static_cast<size_t>(b) * h->tile_stride;
     if (allocate_blocks) {
       const float reach = c.max_range + p.infl;
       const float inv = 1.f / h->block_size;
@@ -733,10 +780,32 @@ static int integrateBatch(kb_handle* h, const kb_frame* frames, int n, int alloc
   bool all_compact = any_compact;
   for (int b = 0; b < n; ++b) all_compact = all_compact && frames[b].depth_u16 != nullptr && frames[b].label == nullptr;
   p.compact_taps = all_compact ? 1 : 0;
-  if (any_compact && !all_compact) launchExpandFrames(p, h->stream);
-  if (p.cull) launchTileMax(p, h->stream);
-  launchSelectBlocks(h->dm, p, h->cull_grid, h->stream);
+  cudaStream_t ps = h->stream;
+  if (pipe) {
+    // The prologue of this batch goes to its own stream: it may run while the previous batch's fuse kernel is still
+    // busy (that kernel only reads the other parity's lists). It has to wait for (a) the staged frames, (b) the fuse
+    // kernel that last used this parity's buffers, (c) any other main-stream work enqueued since the last prologue
+    // (tracking pass, block removal, box allocation ...: K0 reads what they write).
+    ps = h->pre_stream;
+    if (any_host) KB_CUDA(h, cudaStreamWaitEvent(ps, h->stg_ready[set], 0));
+    KB_CUDA(h, cudaStreamWaitEvent(ps, h->fuse_done[par], 0));
+    if (h->main_dirty) {
+      KB_CUDA(h, cudaEventRecord(h->main_front, h->stream));
+      KB_CUDA(h, cudaStreamWaitEvent(ps, h->main_front, 0));
+      h->main_dirty = false;
+    }
+    KB_CUDA(h, cudaMemsetAsync(h->dm.counters + kCtrWork0 + par, 0, sizeof(int), ps));
+    KB_CUDA(h, cudaMemsetAsync(h->dm.counters + p.fetch_ctr, 0, sizeof(int), ps));
+  }
+  if (any_compact && !all_compact) launchExpandFrames(p, ps);
+  if (p.cull) launchTileMax(p, ps);
+  launchSelectBlocks(h->dm, p, h->cull_grid, ps);
+  if (pipe) {
+    KB_CUDA(h, cudaEventRecord(h->pre_done[par], ps));
+    KB_CUDA(h, cudaStreamWaitEvent(h->stream, h->pre_done[par], 0));
+  }
   launchFuse(h->dm, p, h->fuse_grid, h->stream);
+  if (pipe) KB_CUDA(h, cudaEventRecord(h->fuse_done[par], h->stream));
   KB_CUDA(h, cudaGetLastError());
   if (use_staging) KB_CUDA(h, cudaEventRecord(h->stg_consumed[set], h->stream));
   if (any_host) {
@@ -848,6 +917,7 @@ static int trackingParams(kb_handle* h, uint64_t stamp_ns, TrackingParams* out) 
 }
 
 static int updateTrackingImpl(kb_handle* h, uint64_t stamp_ns) {
+  if (h) h->main_dirty = true;  // KB_PIPELINE: the next prologue must wait for this main-stream work
   if (h->open_pass_state != 0) return fail(h, KB_ERR_STATE, "a sharded tracking pass is open (kb_tracking_finish missing)");
   TrackingParams p{};
   int st = trackingParams(h, stamp_ns, &p);
@@ -885,6 +955,7 @@ int kb_shard_buffer_sizes(kb_handle* h, int64_t* pending_bytes, int64_t* halo_by
 }
 
 int kb_tracking_begin(kb_handle* h, uint64_t stamp_ns, void* pending_out) {
+  if (h) h->main_dirty = true;  // KB_PIPELINE: the next prologue must wait for this main-stream work
   if (!h || !pending_out) return fail(h, KB_ERR_INVALID, "null argument");
   if (!h->has_trk || !h->map.with_tracking) return fail(h, KB_ERR_STATE, "tracking not configured");
   if (h->open_pass_state != 0) return fail(h, KB_ERR_STATE, "kb_tracking_begin: the previous pass was not finished");
@@ -902,6 +973,7 @@ int kb_tracking_begin(kb_handle* h, uint64_t stamp_ns, void* pending_out) {
 }
 
 int kb_tracking_pack_halo(kb_handle* h, const void* all_pending, void* halo_out) {
+  if (h) h->main_dirty = true;  // KB_PIPELINE: the next prologue must wait for this main-stream work
   if (!h || !all_pending || !halo_out) return fail(h, KB_ERR_INVALID, "null argument");
   if (h->open_pass_state != 1) return fail(h, KB_ERR_STATE, "kb_tracking_pack_halo needs kb_tracking_begin first");
   KB_CUDA(h, cudaSetDevice(h->device));
@@ -912,6 +984,7 @@ int kb_tracking_pack_halo(kb_handle* h, const void* all_pending, void* halo_out)
 }
 
 int kb_tracking_finish(kb_handle* h, const void* all_pending, const void* all_halo) {
+  if (h) h->main_dirty = true;  // KB_PIPELINE: the next prologue must wait for this main-stream work
   if (!h || !all_pending || !all_halo) return fail(h, KB_ERR_INVALID, "null argument");
   if (h->open_pass_state != 2) return fail(h, KB_ERR_STATE, "kb_tracking_finish needs kb_tracking_pack_halo first");
   KB_CUDA(h, cudaSetDevice(h->device));
@@ -931,6 +1004,7 @@ int kb_tracking_finish(kb_handle* h, const void* all_pending, const void* all_ha
 }
 
 int kb_reset_inactive(kb_handle* h, int32_t* removed_xyz, int32_t max_removed, int32_t* n_removed) {
+  if (h) h->main_dirty = true;  // KB_PIPELINE: the next prologue must wait for this main-stream work
   if (!h) return KB_ERR_INVALID;
   if (!h->map.with_tracking) { if (n_removed) *n_removed = 0; return KB_OK; }  // no tracking blocks
   KB_CUDA(h, cudaSetDevice(h->device));
@@ -956,6 +1030,7 @@ int kb_reset_inactive(kb_handle* h, int32_t* removed_xyz, int32_t max_removed, i
 }
 
 int kb_mark_all_inactive(kb_handle* h) {
+  if (h) h->main_dirty = true;  // KB_PIPELINE: the next prologue must wait for this main-stream work
   if (!h) return KB_ERR_INVALID;
   KB_CUDA(h, cudaSetDevice(h->device));
   int st, n = 0;
@@ -966,6 +1041,7 @@ int kb_mark_all_inactive(kb_handle* h) {
 }
 
 int kb_clear_updated(kb_handle* h) {
+  if (h) h->main_dirty = true;  // KB_PIPELINE: the next prologue must wait for this main-stream work
   if (!h) return KB_ERR_INVALID;
   KB_CUDA(h, cudaSetDevice(h->device));
   int st, n = 0;
@@ -976,6 +1052,7 @@ int kb_clear_updated(kb_handle* h) {
 }
 
 int kb_allocate_box(kb_handle* h, const int32_t mn[3], const int32_t mx[3]) {
+  if (h) h->main_dirty = true;  // KB_PIPELINE: the next prologue must wait for this main-stream work
   if (!h || !mn || !mx) return KB_ERR_INVALID;
   KB_CUDA(h, cudaSetDevice(h->device));
   const int3 lo = make_int3(mn[0], mn[1], mn[2]);
@@ -994,6 +1071,7 @@ int kb_allocate_box(kb_handle* h, const int32_t mn[3], const int32_t mx[3]) {
 }
 
 int kb_scan_object_confidence(kb_handle* h, float min_confidence, int32_t min_observations, int32_t* n_erased) {
+  if (h) h->main_dirty = true;  // KB_PIPELINE: the next prologue must wait for this main-stream work
   if (!h) return KB_ERR_INVALID;
   if (h->L != 2 || h->integ.semantic_mode != KB_SEMANTICS_BINARY)
     return fail(h, KB_ERR_STATE, "kb_scan_object_confidence needs binary semantics");
@@ -1013,6 +1091,7 @@ int kb_scan_object_confidence(kb_handle* h, float min_confidence, int32_t min_ob
 // M1 launch shared by kb_detect_motion and kb_spin_once: stages depth / vertex map, resets the seed counter,
 // enqueues the per-pixel lookup and records the host parameters for lazily built cluster lists.
 static int enqueueMotionLookup(kb_handle* h, const kb_frame* f, uint8_t* shard_flags = nullptr) {
+  if (h) h->main_dirty = true;  // KB_PIPELINE: the next prologue must wait for this main-stream work
   const kb_camera& c = h->cam;
   const size_t px = static_cast<size_t>(c.width) * c.height;
   MotionParams p{};
@@ -1264,6 +1343,7 @@ int kb_motion_lookup_local(kb_handle* h, const kb_frame* f, uint8_t* pixel_flags
 }
 
 int kb_motion_cluster_global(kb_handle* h, const uint8_t* pixel_flags) {
+  if (h) h->main_dirty = true;  // KB_PIPELINE: the next prologue must wait for this main-stream work
   if (!h || !pixel_flags) return fail(h, KB_ERR_INVALID, "null argument");
   if (!h->has_mot || !h->has_cam) return fail(h, KB_ERR_STATE, "motion detector not configured");
   KB_CUDA(h, cudaSetDevice(h->device));

@@ -81,7 +81,11 @@ enum Counter {
   kCtrItems0 = 21,   // KB_FUSE_ITEM_LIST: non-empty culling boxes of the batch in 3 weight classes (heavy first)
   kCtrItems1 = 22,
   kCtrItems2 = 23,
-  kNumCounters = 24
+  kCtrFetchB = 24,   // KB_PIPELINE: second work cursor / item-list counters, so that the prologue of batch i+1 can
+  kCtrItemsB0 = 25,  //   run while the fuse kernel of batch i is still fetching
+  kCtrItemsB1 = 26,
+  kCtrItemsB2 = 27,
+  kNumCounters = 32
 };
 
 __host__ __device__ inline unsigned long long packKey(int x, int y, int z) {

@@ -317,10 +317,13 @@ __device__ __forceinline__ bool boxCulledLane(const BatchParams& p, const FrameV
 // One WARP per candidate block of the batch's AABB (allocate mode; hydra findBlocksInViewFrustum,
 // SURVEY App. A.5) or per pool slot (allocate == 0: all allocated blocks, mesh_object_extractor.cpp:242).
 // Lane b evaluates frame b of the batch: frustum test -> ballot -> 32-bit frame mask.
+// PIPE (KB_PIPELINE): the host zeroes this batch's own counters on the prologue stream; the other batch's counters may
+// be in use by its fuse kernel, so K0 must not touch them.
+template <bool PIPE>
 __global__ void __launch_bounds__(128) selectBlocksKernel(const DeviceMap m, const __grid_constant__ BatchParams p) {
   const int c0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (c0 == 0 && lane == 0) {  // reset the next batch's work counter and this batch's fetch cursor
+  if (!PIPE && c0 == 0 && lane == 0) {  // reset the next batch's work counter and this batch's fetch cursor
     m.counters[kCtrWork0 + (p.parity ^ 1)] = 0;
     m.counters[kCtrFetch] = 0;
   }
@@ -432,8 +435,9 @@ __global__ void __launch_bounds__(128) itemCullKernel(const DeviceMap m, const _
 // The fuse kernel's warps fetch items from a shared cursor; with ~4 items per warp and item costs between 1 and 32
 // frame iterations, the order matters (longest-processing-time first shortens the tail) and every empty box costs a
 // cursor round trip. This pass lists the boxes whose frame mask is non-zero in three weight classes.
-template <int VPS>
+template <int VPS, bool PB>
 __global__ void __launch_bounds__(256) itemCompactKernel(const DeviceMap m, const __grid_constant__ BatchParams p) {
+  constexpr int kItems = PB ? kCtrItemsB0 : kCtrItems0;  // PB: second counter set (odd batches of KB_PIPELINE)
   constexpr int BOXES = (VPS / 4) * (VPS / 8) * (VPS / 4);
   const int n = min(m.counters[kCtrWork0 + p.parity], p.max_work) * BOXES;
   const int lane = threadIdx.x & 31;
@@ -447,7 +451,7 @@ __global__ void __launch_bounds__(256) itemCompactKernel(const DeviceMap m, cons
       const unsigned vote = __ballot_sync(0xffffffffu, fm != 0u && cls == k);
       if (!vote) continue;
       int start = 0;
-      if (lane == __ffs(vote) - 1) start = atomicAdd(&m.counters[kCtrItems0 + k], __popc(vote));
+      if (lane == __ffs(vote) - 1) start = atomicAdd(&m.counters[kItems + k], __popc(vote));
       start = __shfl_sync(0xffffffffu, start, __ffs(vote) - 1);
       if (fm != 0u && cls == k) {
         const int idx = start + __popc(vote & ((1u << lane) - 1u));
@@ -484,8 +488,11 @@ __device__ __noinline__ uint32_t trackingFold(const DeviceMap m, const TrackEval
 // register like the rest of the voxel state: one 4 B read + write per batch). The colour-less instantiations
 // are the ones the BASELINE workloads run and are unchanged by this parameter.
 // LIST: items come from the compacted, heaviest-first box lists of itemCompactKernel instead of the dense box range.
-template <int VPS, int LPI, bool COMPACT, bool COLOR, bool LIST = false>
+// PB: the batch uses the second cursor / item-list counter set (odd batches of KB_PIPELINE).
+template <int VPS, int LPI, bool COMPACT, bool COLOR, bool LIST = false, bool PB = false>
 __global__ void __launch_bounds__(kFuseThreads, COLOR ? KB_FUSE_COLOR_MIN_BLOCKS : KB_FUSE_MIN_BLOCKS) fuseKernel(const DeviceMap m, const __grid_constant__ BatchParams p) {
+  constexpr int kFetch = PB ? kCtrFetchB : kCtrFetch;
+  [[maybe_unused]] constexpr int kItems = PB ? kCtrItemsB0 : kCtrItems0;
   constexpr int V = VPS * VPS * VPS;
   constexpr int NK = 4;                                      // z-layers per culling box
   constexpr int BOXES = (VPS / 4) * (VPS / 8) * (VPS / NK);  // 32 (16^3) or 4 (8^3) boxes of 128 voxels
@@ -497,9 +504,9 @@ __global__ void __launch_bounds__(kFuseThreads, COLOR ? KB_FUSE_COLOR_MIN_BLOCKS
   int n0 = 0, n1 = 0;  // LIST: sizes of the first two weight classes
   int n_items;
   if constexpr (LIST) {
-    n0 = min(m.counters[kCtrItems0], p.item_list_cap);
-    n1 = min(m.counters[kCtrItems1], p.item_list_cap);
-    n_items = (n0 + n1 + min(m.counters[kCtrItems2], p.item_list_cap)) * ipb;
+    n0 = min(m.counters[kItems], p.item_list_cap);
+    n1 = min(m.counters[kItems + 1], p.item_list_cap);
+    n_items = (n0 + n1 + min(m.counters[kItems + 2], p.item_list_cap)) * ipb;
   } else {
     n_items = min(m.counters[kCtrWork0 + p.parity], p.max_work) * BOXES * ipb;
   }
@@ -510,11 +517,11 @@ __global__ void __launch_bounds__(kFuseThreads, COLOR ? KB_FUSE_COLOR_MIN_BLOCKS
   // The cursor fetch for the NEXT item is issued before the current item is processed, so the atomic's
   // L2 round trip (a quarter of all stall samples in profiles/r1_v5_*) overlaps useful work.
   int pending = 0;
-  if (lane == 0) pending = atomicAdd(&m.counters[kCtrFetch], 1);
+  if (lane == 0) pending = atomicAdd(&m.counters[kFetch], 1);
   for (;;) {
     const int w = __shfl_sync(0xffffffffu, pending, 0);
     if (w >= n_items) break;
-    if (lane == 0) pending = atomicAdd(&m.counters[kCtrFetch], 1);
+    if (lane == 0) pending = atomicAdd(&m.counters[kFetch], 1);
     int box = w / ipb;
     if constexpr (LIST) {
       const int j = box;
@@ -708,8 +715,10 @@ __global__ void __launch_bounds__(kFuseThreads, COLOR ? KB_FUSE_COLOR_MIN_BLOCKS
 #ifndef KB_FUSE_MLP_MIN_BLOCKS
 #define KB_FUSE_MLP_MIN_BLOCKS 5
 #endif
-template <int VPS, int LPI, bool COMPACT, int G, bool LIST>
+template <int VPS, int LPI, bool COMPACT, int G, bool LIST, bool PB = false>
 __global__ void __launch_bounds__(kFuseThreads, KB_FUSE_MLP_MIN_BLOCKS) fuseKernelMlp(const DeviceMap m, const __grid_constant__ BatchParams p) {
+  constexpr int kFetch = PB ? kCtrFetchB : kCtrFetch;
+  [[maybe_unused]] constexpr int kItems = PB ? kCtrItemsB0 : kCtrItems0;
   constexpr int V = VPS * VPS * VPS;
   constexpr int NK = 4;
   constexpr int BOXES = (VPS / 4) * (VPS / 8) * (VPS / NK);
@@ -719,9 +728,9 @@ __global__ void __launch_bounds__(kFuseThreads, KB_FUSE_MLP_MIN_BLOCKS) fuseKern
   int n0 = 0, n1 = 0;
   int n_items;
   if constexpr (LIST) {
-    n0 = min(m.counters[kCtrItems0], p.item_list_cap);
-    n1 = min(m.counters[kCtrItems1], p.item_list_cap);
-    n_items = (n0 + n1 + min(m.counters[kCtrItems2], p.item_list_cap)) * ipb;
+    n0 = min(m.counters[kItems], p.item_list_cap);
+    n1 = min(m.counters[kItems + 1], p.item_list_cap);
+    n_items = (n0 + n1 + min(m.counters[kItems + 2], p.item_list_cap)) * ipb;
   } else {
     n_items = min(m.counters[kCtrWork0 + p.parity], p.max_work) * BOXES * ipb;
   }
@@ -731,11 +740,11 @@ __global__ void __launch_bounds__(kFuseThreads, KB_FUSE_MLP_MIN_BLOCKS) fuseKern
   int n_valid = 0, n_band = 0, n_sem = 0;
 
   int pending = 0;
-  if (lane == 0) pending = atomicAdd(&m.counters[kCtrFetch], 1);
+  if (lane == 0) pending = atomicAdd(&m.counters[kFetch], 1);
   for (;;) {
     const int w = __shfl_sync(0xffffffffu, pending, 0);
     if (w >= n_items) break;
-    if (lane == 0) pending = atomicAdd(&m.counters[kCtrFetch], 1);
+    if (lane == 0) pending = atomicAdd(&m.counters[kFetch], 1);
     int box = w / ipb;
     if constexpr (LIST) {
       const int j = box;
@@ -1451,15 +1460,17 @@ void launchTileMax(const BatchParams& p, cudaStream_t s) {
 }
 void launchSelectBlocks(const DeviceMap& m, const BatchParams& p, int cull_grid, cudaStream_t s) {
   const int n = p.allocate ? p.dims[0] * p.dims[1] * p.dims[2] : p.n_slots;
-  selectBlocksKernel<<<(std::max(n, 1) + 3) / 4, 128, 0, s>>>(m, p);  // one warp per candidate
+  if (p.pipelined) selectBlocksKernel<true><<<(std::max(n, 1) + 3) / 4, 128, 0, s>>>(m, p);  // one warp per candidate
+  else selectBlocksKernel<false><<<(std::max(n, 1) + 3) / 4, 128, 0, s>>>(m, p);
   if (p.cull) {
     if (m.vps == 16) itemCullKernel<16><<<cull_grid, 128, 0, s>>>(m, p);
     else itemCullKernel<8><<<cull_grid, 128, 0, s>>>(m, p);
   }
   if (p.item_list) {
-    cudaMemsetAsync(m.counters + kCtrItems0, 0, 3 * sizeof(int), s);
-    if (m.vps == 16) itemCompactKernel<16><<<cull_grid, 256, 0, s>>>(m, p);
-    else itemCompactKernel<8><<<cull_grid, 256, 0, s>>>(m, p);
+    const bool pb = p.fetch_ctr == kCtrFetchB;
+    cudaMemsetAsync(m.counters + (pb ? kCtrItemsB0 : kCtrItems0), 0, 3 * sizeof(int), s);
+    if (m.vps == 16) { if (pb) itemCompactKernel<16, true><<<cull_grid, 256, 0, s>>>(m, p); else itemCompactKernel<16, false><<<cull_grid, 256, 0, s>>>(m, p); }
+    else { if (pb) itemCompactKernel<8, true><<<cull_grid, 256, 0, s>>>(m, p); else itemCompactKernel<8, false><<<cull_grid, 256, 0, s>>>(m, p); }
   }
 }
 static size_t fuseSmemBytes(int Lp) { return static_cast<size_t>(std::max(Lp, 2)) * kFuseThreads * sizeof(float); }
@@ -1473,21 +1484,33 @@ void launchFuse(const DeviceMap& m, const BatchParams& p, int grid, cudaStream_t
   if (grid <= 0) return;
   const size_t smem = fuseSmemBytes(m.Lp);
   const bool one = p.layers_per_item == 1, c = p.compact_taps != 0, col = p.has_color != 0 && m.color != nullptr;
+  const bool pb = p.fetch_ctr == kCtrFetchB;  // odd batch of KB_PIPELINE: second counter set
 #define KB_FUSE(V, LP, C)                                                                        \
   do {                                                                                           \
-    if (col) fuseKernel<V, LP, C, true><<<grid, kFuseThreads, smem, s>>>(m, p);                  \
-    else if (p.item_list) fuseKernel<V, LP, C, false, true><<<grid, kFuseThreads, smem, s>>>(m, p); \
-    else fuseKernel<V, LP, C, false><<<grid, kFuseThreads, smem, s>>>(m, p);                     \
+    if (pb) {                                                                                    \
+      if (col) fuseKernel<V, LP, C, true, false, true><<<grid, kFuseThreads, smem, s>>>(m, p);   \
+      else if (p.item_list) fuseKernel<V, LP, C, false, true, true><<<grid, kFuseThreads, smem, s>>>(m, p); \
+      else fuseKernel<V, LP, C, false, false, true><<<grid, kFuseThreads, smem, s>>>(m, p);      \
+    } else {                                                                                     \
+      if (col) fuseKernel<V, LP, C, true><<<grid, kFuseThreads, smem, s>>>(m, p);                \
+      else if (p.item_list) fuseKernel<V, LP, C, false, true><<<grid, kFuseThreads, smem, s>>>(m, p); \
+      else fuseKernel<V, LP, C, false><<<grid, kFuseThreads, smem, s>>>(m, p);                   \
+    }                                                                                            \
+  } while (0)
+#define KB_FUSE_MLP_G(V, LP, C, GG)                                                                                  \
+  do {                                                                                                               \
+    if (pb) {                                                                                                        \
+      if (p.item_list) fuseKernelMlp<V, LP, C, GG, true, true><<<grid, kFuseThreads, smem, s>>>(m, p);               \
+      else fuseKernelMlp<V, LP, C, GG, false, true><<<grid, kFuseThreads, smem, s>>>(m, p);                          \
+    } else {                                                                                                         \
+      if (p.item_list) fuseKernelMlp<V, LP, C, GG, true><<<grid, kFuseThreads, smem, s>>>(m, p);                     \
+      else fuseKernelMlp<V, LP, C, GG, false><<<grid, kFuseThreads, smem, s>>>(m, p);                                \
+    }                                                                                                                \
   } while (0)
 #define KB_FUSE_MLP(V, LP, C)                                                                                        \
   do {                                                                                                               \
-    if (p.mlp_group == 2) {                                                                                          \
-      if (p.item_list) fuseKernelMlp<V, LP, C, 2, true><<<grid, kFuseThreads, smem, s>>>(m, p);                      \
-      else fuseKernelMlp<V, LP, C, 2, false><<<grid, kFuseThreads, smem, s>>>(m, p);                                 \
-    } else {                                                                                                         \
-      if (p.item_list) fuseKernelMlp<V, LP, C, 4, true><<<grid, kFuseThreads, smem, s>>>(m, p);                      \
-      else fuseKernelMlp<V, LP, C, 4, false><<<grid, kFuseThreads, smem, s>>>(m, p);                                 \
-    }                                                                                                                \
+    if (p.mlp_group == 2) KB_FUSE_MLP_G(V, LP, C, 2);                                                                \
+    else KB_FUSE_MLP_G(V, LP, C, 4);                                                                                 \
   } while (0)
   if (p.mlp_group != 0 && !col) {  // experiment: memory-level-parallel variant (same results)
     if (m.vps == 16) {
@@ -1508,6 +1531,7 @@ void launchFuse(const DeviceMap& m, const BatchParams& p, int grid, cudaStream_t
   }
 #undef KB_FUSE
 #undef KB_FUSE_MLP
+#undef KB_FUSE_MLP_G
 }
 void launchTrackingPass(const DeviceMap& m, const TrackingParams& p, int everfree_grid, cudaStream_t s) {
   trackingPassKernel<<<(std::max(p.n_slots, 1) + 255) / 256, 256, 0, s>>>(m, p);

@@ -1,5 +1,7 @@
 """Experimental fuse-kernel variants (all off by default, selected by environment variables read in kb_create):
   KB_FUSE_ITEM_LIST=1  items come from compacted heaviest-first lists instead of the dense box range
+  KB_PIPELINE=1        the prologue (tile pyramid, K0, K0b) of batch i+1 runs on its own stream while the fuse kernel of
+                       batch i is busy; work lists, pyramids and cursors are double-buffered by batch parity
   KB_FUSE_MLP=2|4      fuseKernelMlp: the frames of an item are processed in groups whose depth / label taps are issued
                        together (memory-level parallelism); nearest-pixel fallback selected from the four loaded taps
 Only the processing order / instruction schedule changes: every result must stay bit-identical to the oracle."""
@@ -14,10 +16,11 @@ from test_parity_gpu import room_frames
 
 pytestmark = pytest.mark.gpu
 
-VARIANTS = [{"KB_FUSE_ITEM_LIST": "1"}, {"KB_FUSE_MLP": "2"}, {"KB_FUSE_MLP": "4"}, {"KB_FUSE_MLP": "4", "KB_FUSE_ITEM_LIST": "1"}]
+VARIANTS = [{"KB_FUSE_ITEM_LIST": "1"}, {"KB_FUSE_MLP": "2"}, {"KB_FUSE_MLP": "4"}, {"KB_FUSE_MLP": "4", "KB_FUSE_ITEM_LIST": "1"},
+            {"KB_PIPELINE": "1"}, {"KB_PIPELINE": "1", "KB_FUSE_MLP": "4", "KB_FUSE_ITEM_LIST": "1", "KB_FUSE_CTAS_PER_SM": "3"}]
 
 
-@pytest.fixture(params=VARIANTS, ids=lambda v: "+".join(f"{k[8:]}={x}" for k, x in v.items()))
+@pytest.fixture(params=VARIANTS, ids=lambda v: "+".join(f"{k.replace('KB_', '').replace('FUSE_', '')}={x}" for k, x in v.items()))
 def variant_env(request):
     os.environ.update(request.param)   # read by kb_create
     yield request.param

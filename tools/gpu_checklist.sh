@@ -13,9 +13,13 @@ KB_FUSE_ITEM_LIST=1 timeout 200 python bench.py --no-e2e --no-cpu-baseline > gpu
 KB_FUSE_MLP=2 timeout 200 python bench.py --no-e2e --no-cpu-baseline > gpurun_out/bench_mlp2.json 2> gpurun_out/bench_mlp2.err
 KB_FUSE_MLP=4 timeout 200 python bench.py --no-e2e --no-cpu-baseline > gpurun_out/bench_mlp4.json 2> gpurun_out/bench_mlp4.err
 KB_FUSE_MLP=4 KB_FUSE_ITEM_LIST=1 timeout 200 python bench.py --no-e2e --no-cpu-baseline > gpurun_out/bench_mlp4_list.json 2> gpurun_out/bench_mlp4_list.err
+for c in 10 8 6; do
+  KB_PIPELINE=1 KB_FUSE_CTAS_PER_SM=$c timeout 200 python bench.py --no-e2e --no-cpu-baseline > gpurun_out/bench_pipe$c.json 2> gpurun_out/bench_pipe$c.err
+done
+KB_PIPELINE=1 KB_FUSE_CTAS_PER_SM=4 KB_FUSE_MLP=4 timeout 200 python bench.py --no-e2e --no-cpu-baseline > gpurun_out/bench_pipe_mlp4.json 2> gpurun_out/bench_pipe_mlp4.err
 python - <<'PY'
 import json
-for n in ("default", "item_list", "mlp2", "mlp4", "mlp4_list"):
+for n in ("default", "item_list", "mlp2", "mlp4", "mlp4_list", "pipe10", "pipe8", "pipe6", "pipe_mlp4"):
     try:
         d = json.load(open(f"gpurun_out/bench_{n}.json"))
         print(n, round(d["value"]), "fps", d["roofline"]["launch_us"], "us/launch", d["clocks"])
