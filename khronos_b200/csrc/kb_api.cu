@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <type_traits>
 #include <vector>
 
@@ -73,6 +74,13 @@ struct kb_handle {
   uint32_t* work_masks2 = nullptr;
   uint32_t* work_upd2 = nullptr;
   uint32_t* item_fmask2 = nullptr;
+  // KB_H2D_NARROW_LABELS experiment: host i32 label images whose ids fit 8 bits are narrowed on the host (worker threads)
+  // into a pinned buffer, cross PCIe as 1 B/pixel and are widened again by expandFramesKernel: 5 instead of 8 B/pixel of
+  // H2D traffic for hydra::InputData frames, bit-identical results (frames with ids outside 0..255 take the i32 path)
+  bool narrow_labels = false;
+  int narrow_threads = 8;
+  uint8_t* pin_label8 = nullptr;
+  size_t pin_label8_pixels = 0;
   int mlp_group = 0;           // KB_FUSE_MLP experiment: 0 (off), 2 or 4 frames per memory-level-parallel group
   int cull_grid = 0;
   int parity = 0;
@@ -454,6 +462,8 @@ int kb_create(const kb_map_config* map, const kb_integrator_config* integ, const
     h->batch.items_per_block = m.V / 128;
     KB_CUDA(h, devAlloc(&h->item_fmask, S * h->batch.items_per_block, 0));
     if (const char* e = std::getenv("KB_FUSE_ITEM_LIST")) h->use_item_list = e[0] == '1';
+    if (const char* e = std::getenv("KB_H2D_NARROW_LABELS")) h->narrow_labels = e[0] == '1';
+    if (const char* e = std::getenv("KB_H2D_THREADS")) h->narrow_threads = std::max(1, std::atoi(e));
     if (const char* e = std::getenv("KB_PIPELINE")) h->pipelined = e[0] == '1';
     if (h->pipelined) {
       KB_CUDA(h, cudaStreamCreateWithFlags(&h->pre_stream, cudaStreamNonBlocking));
@@ -524,6 +534,7 @@ int kb_destroy(kb_handle* h) {
     if (h->stg_consumed[i]) cudaEventDestroy(h->stg_consumed[i]);
   }
   if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+  if (h->pin_label8) cudaFreeHost(h->pin_label8);
   if (h->pre_stream) { cudaStreamSynchronize(h->pre_stream); cudaStreamDestroy(h->pre_stream); }
   for (int i = 0; i < 2; ++i) {
     if (h->pre_done[i]) cudaEventDestroy(h->pre_done[i]);
@@ -692,6 +703,46 @@ static int integrateBatch(kb_handle* h, const kb_frame* frames, int n, int alloc
     // wait until the kernels that last read this staging set are done
     KB_CUDA(h, cudaStreamWaitEvent(h->copy_stream, h->stg_consumed[set], 0));
   }
+  // ---- optional host-side narrowing of i32 label images (KB_H2D_NARROW_LABELS)
+  bool narrowed[kMaxBatch] = {false};
+  bool any_narrowed = false;
+  if (h->narrow_labels && any_host) {
+    int cand[kMaxBatch], nc = 0;
+    for (int b = 0; b < n; ++b)
+      if (frames[b].memory != KB_MEM_DEVICE && frames[b].label && !frames[b].label_u8) cand[nc++] = b;
+    if (nc > 0) {
+      if (h->pin_label8_pixels < px) {
+        KB_CUDA(h, cudaStreamSynchronize(h->copy_stream));
+        if (h->pin_label8) cudaFreeHost(h->pin_label8);
+        h->pin_label8 = nullptr;
+        KB_CUDA(h, cudaMallocHost(reinterpret_cast<void**>(&h->pin_label8), px * kMaxBatch * 2));
+        h->pin_label8_pixels = px;
+      }
+      // the H2D copies that last read this half of the pinned buffer (two batches ago) must be done; the copies of the
+      // previous batch (other half) keep running while this batch is narrowed
+      KB_CUDA(h, cudaEventSynchronize(h->stg_ready[set]));
+      uint8_t* base8 = h->pin_label8 + static_cast<size_t>(set) * kMaxBatch * px;
+      auto work = [&](int t, int T) {
+        for (int k = t; k < nc; k += T) {
+          const int b = cand[k];
+          const int32_t* __restrict__ src = frames[b].label;
+          uint8_t* __restrict__ dst = base8 + static_cast<size_t>(b) * px;
+          int32_t acc = 0;
+          for (size_t i = 0; i < px; ++i) { acc |= src[i]; dst[i] = static_cast<uint8_t>(src[i]); }
+          narrowed[b] = (acc & ~0xFF) == 0;  // every id in 0..255 (negative ids set the high bits)
+        }
+      };
+      const int T = std::max(1, std::min(h->narrow_threads, nc));
+      if (T == 1) {
+        work(0, 1);
+      } else {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < T; ++t) pool.emplace_back(work, t, T);
+        for (auto& th : pool) th.join();
+      }
+      for (int b = 0; b < n; ++b) any_narrowed |= narrowed[b];
+    }
+  }
   int lo[3] = {INT32_MAX, INT32_MAX, INT32_MAX}, hi[3] = {INT32_MIN, INT32_MIN, INT32_MIN};
   for (int b = 0; b < n; ++b) {
     const kb_frame& f = frames[b];
@@ -717,7 +768,7 @@ static int integrateBatch(kb_handle* h, const kb_frame* frames, int n, int alloc
       v.mask = f.mask ? h->stg_mask + off : nullptr;
       v.object_image = f.object_image ? h->stg_object + off : nullptr;
       v.depth16 = f.depth_u16 ? h->stg_depth16 + off : nullptr;
-      v.label8 = f.label_u8 ? h->stg_label8 + off : nullptr;
+      v.label8 = (f.label_u8 || narrowed[b]) ? h->stg_label8 + off : nullptr;
     }
     v.depth_scale = f.depth_u16_scale;
     if (v.depth16) v.depth = h->stg_depth + off;   // expandFramesKernel fills these staging slots
@@ -755,7 +806,26 @@ static int integrateBatch(kb_handle* h, const kb_frame* frames, int n, int alloc
     };
     int cst;
     if ((cst = copyKind(&kb_frame::depth, h->stg_depth)) != KB_OK) return cst;
-    if ((cst = copyKind(&kb_frame::label, h->stg_label)) != KB_OK) return cst;
+    if (!any_narrowed) {
+      if ((cst = copyKind(&kb_frame::label, h->stg_label)) != KB_OK) return cst;
+    } else {
+      // narrowed frames ship their pinned 8-bit copy (runs of consecutive frames in one transfer), the others their i32 image
+      for (int b = 0; b < n;) {
+        if (narrowed[b]) {
+          int e = b + 1;
+          while (e < n && narrowed[e]) ++e;
+          const size_t o = (static_cast<size_t>(set) * kMaxBatch + b) * px;
+          KB_CUDA(h, cudaMemcpyAsync(h->stg_label8 + o, h->pin_label8 + o, static_cast<size_t>(e - b) * px, cudaMemcpyHostToDevice, h->copy_stream));
+          b = e;
+        } else {
+          if (frames[b].memory != KB_MEM_DEVICE && frames[b].label) {
+            const size_t o = (static_cast<size_t>(set) * kMaxBatch + b) * px;
+            KB_CUDA(h, cudaMemcpyAsync(h->stg_label + o, frames[b].label, px * sizeof(int32_t), cudaMemcpyHostToDevice, h->copy_stream));
+          }
+          ++b;
+        }
+      }
+    }
     if ((cst = copyKind(&kb_frame::mask, h->stg_mask)) != KB_OK) return cst;
     if ((cst = copyKind(&kb_frame::object_image, h->stg_object)) != KB_OK) return cst;
     if ((cst = copyKind(&kb_frame::depth_u16, h->stg_depth16)) != KB_OK) return cst;
@@ -777,6 +847,7 @@ static int integrateBatch(kb_handle* h, const kb_frame* frames, int n, int alloc
     p.n_slots = h->hwm_cached;
   }
   // All-compact batches are read in place (conversion per tap); mixed batches expand the compact frames first.
+  any_compact = any_compact || any_narrowed;  // narrowed labels are widened by expandFramesKernel like label_u8 inputs
   bool all_compact = any_compact;
   for (int b = 0; b < n; ++b) all_compact = all_compact && frames[b].depth_u16 != nullptr && frames[b].label == nullptr;
   p.compact_taps = all_compact ? 1 : 0;

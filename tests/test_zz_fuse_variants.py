@@ -2,6 +2,7 @@
   KB_FUSE_ITEM_LIST=1  items come from compacted heaviest-first lists instead of the dense box range
   KB_PIPELINE=1        the prologue (tile pyramid, K0, K0b) of batch i+1 runs on its own stream while the fuse kernel of
                        batch i is busy; work lists, pyramids and cursors are double-buffered by batch parity
+  KB_H2D_NARROW_LABELS=1  host i32 label images with ids in 0..255 cross PCIe as u8 (narrowed by host threads, widened on the device)
   KB_FUSE_MLP=2|4      fuseKernelMlp: the frames of an item are processed in groups whose depth / label taps are issued
                        together (memory-level parallelism); nearest-pixel fallback selected from the four loaded taps
 Only the processing order / instruction schedule changes: every result must stay bit-identical to the oracle."""
@@ -17,7 +18,8 @@ from test_parity_gpu import room_frames
 pytestmark = pytest.mark.gpu
 
 VARIANTS = [{"KB_FUSE_ITEM_LIST": "1"}, {"KB_FUSE_MLP": "2"}, {"KB_FUSE_MLP": "4"}, {"KB_FUSE_MLP": "4", "KB_FUSE_ITEM_LIST": "1"},
-            {"KB_PIPELINE": "1"}, {"KB_PIPELINE": "1", "KB_FUSE_MLP": "4", "KB_FUSE_ITEM_LIST": "1", "KB_FUSE_CTAS_PER_SM": "3"}]
+            {"KB_PIPELINE": "1"}, {"KB_PIPELINE": "1", "KB_FUSE_MLP": "4", "KB_FUSE_ITEM_LIST": "1", "KB_FUSE_CTAS_PER_SM": "3"},
+            {"KB_H2D_NARROW_LABELS": "1", "KB_H2D_THREADS": "3"}]
 
 
 @pytest.fixture(params=VARIANTS, ids=lambda v: "+".join(f"{k.replace('KB_', '').replace('FUSE_', '')}={x}" for k, x in v.items()))
@@ -106,3 +108,32 @@ def test_variant_compact_frames_and_binary_extraction_map(oracle_lib, product_li
     g2.integrate_frames([g2.make_frame(d, T, st, object_image=l, target_id=7) for (d, l), T, st in zip(frames, poses, stamps)],
                         allocate_blocks=False, want_stats=False)
     hs.assert_blocks_equal(o2.export_blocks(), g2.export_blocks(), exact_float=True, what=f"{variant_env} binary vps8")
+
+
+def test_narrowed_labels_fall_back_for_out_of_range_ids(oracle_lib, product_lib):
+    """KB_H2D_NARROW_LABELS: frames whose label ids do not fit 8 bits (negative, >= 256) keep the i32 path, the others are
+    narrowed; both kinds in one batch call, host and caller-kept (HOST_ASYNC) buffers."""
+    os.environ["KB_H2D_NARROW_LABELS"] = "1"
+    try:
+        cam = hs.small_camera(4)
+        frames, poses, stamps = room_frames(cam, 20, laps=0.3)
+        rng = np.random.default_rng(9)
+        out = []
+        for i, (d, l) in enumerate(frames):
+            l = l.copy()
+            if i % 3 == 1:
+                l[rng.random(l.shape) < 0.01] = rng.choice(np.array([-1, 256, 1000, 70000, -2 ** 31], np.int32))
+            out.append((d, l))
+        o = hs.make_handle(oracle_lib, "ko_", cam=cam)
+        g = hs.make_handle(product_lib, "kb_", cam=cam)
+        hs.run_fusion(o, out, poses, stamps)
+        for i in range(4):
+            g.integrate_frame(g.make_frame(out[i][0], poses[i], stamps[i], label=out[i][1]), want_stats=False)
+        g.integrate_frames([g.make_frame(d, T, st, label=l) for (d, l), T, st in zip(out[4:12], poses[4:12], stamps[4:12])], want_stats=False)
+        keep = [(np.ascontiguousarray(d), np.ascontiguousarray(l)) for d, l in out[12:]]
+        g.integrate_frames([g.make_frame(d, T, st, label=l, memory=capi.MEM_HOST_ASYNC) for (d, l), T, st in zip(keep, poses[12:], stamps[12:])],
+                           want_stats=False)
+        g.synchronize()
+        hs.assert_blocks_equal(o.export_blocks(), g.export_blocks(), exact_float=True, what="narrowed labels")
+    finally:
+        os.environ.pop("KB_H2D_NARROW_LABELS", None)

@@ -26,6 +26,20 @@ for n in ("default", "item_list", "mlp2", "mlp4", "mlp4_list", "pipe10", "pipe8"
     except Exception as e:
         print(n, "failed:", e)
 PY
+echo "== 2b. e2e (host f32 + i32 frames through the C ABI): default vs labels narrowed to u8 on the host (5 instead of 8 B/px over PCIe)"
+timeout 300 python bench.py --no-cpu-baseline > gpurun_out/bench_e2e_default.json 2> gpurun_out/bench_e2e_default.err
+for t in 8 16 32; do
+  KB_H2D_NARROW_LABELS=1 KB_H2D_THREADS=$t timeout 300 python bench.py --no-cpu-baseline > gpurun_out/bench_e2e_narrow$t.json 2> gpurun_out/bench_e2e_narrow$t.err
+done
+python - <<'PY'
+import json
+for n in ("default", "narrow8", "narrow16", "narrow32"):
+    try:
+        d = json.load(open(f"gpurun_out/bench_e2e_{n}.json"))
+        print("e2e", n, round(d["e2e"]["value"]), "fps")
+    except Exception as e:
+        print("e2e", n, "failed:", e)
+PY
 echo "== 3. per-frame pipeline (config[2]) on one GPU"
 timeout 200 python bench.py --workload dynamic --steps 4 --warmup 2 --no-cpu-baseline > gpurun_out/bench_dynamic.json 2> gpurun_out/bench_dynamic.err
 tail -c 600 gpurun_out/bench_dynamic.json
