@@ -56,7 +56,7 @@ enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDe
 enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2 };
 struct cudaDeviceProp { int multiProcessorCount; char name[64]; };
 
-inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
+inline cudaError_t cudaGetDeviceCount(int* n) { *n = 8; return cudaSuccess; }  // any rank of a multi-process dry run
 inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
