@@ -19,6 +19,7 @@
 #include <algorithm>
 
 #include "kb_motion_device.cuh"
+#include "kb_unionfind.cuh"
 
 namespace kb {
 
@@ -48,27 +49,6 @@ __device__ __forceinline__ int vtLookup(const MotionTable& t, int x, int y, int 
     h = (h + 1) & t.mask;
   }
   return -1;
-}
-
-__device__ __forceinline__ int ufFind(int* parent, int i) {
-  int p = parent[i];
-  while (p != i) {
-    const int g = parent[p];
-    parent[i] = g;  // path halving (benign race: always points to an ancestor)
-    i = p;
-    p = g;
-  }
-  return i;
-}
-
-__device__ __forceinline__ void ufUnion(int* parent, int a, int b) {
-  for (;;) {
-    a = ufFind(parent, a);
-    b = ufFind(parent, b);
-    if (a == b) return;
-    if (a < b) { const int t = a; a = b; b = t; }  // hook the larger root under the smaller
-    if (atomicCAS(&parent[a], a, b) == a) return;
-  }
 }
 
 // C1: the reference's BlockToPointsMap: every valid pixel inserts its voxel; slots double as entry ids.

@@ -20,6 +20,7 @@
 #include <algorithm>
 
 #include "kb_objects_device.cuh"
+#include "kb_unionfind.cuh"
 
 namespace kb {
 
@@ -56,27 +57,6 @@ __device__ __forceinline__ int osLookup(const MotionTable& t, unsigned long long
     h = (h + 1) & t.mask;
   }
   return -1;
-}
-
-__device__ __forceinline__ int ufFind(int* parent, int i) {
-  int p = parent[i];
-  while (p != i) {
-    const int g = parent[p];
-    parent[i] = g;  // path halving (benign race: always points to an ancestor)
-    i = p;
-    p = g;
-  }
-  return i;
-}
-
-__device__ __forceinline__ void ufUnion(int* parent, int a, int b) {
-  for (;;) {
-    a = ufFind(parent, a);
-    b = ufFind(parent, b);
-    if (a == b) return;
-    if (a < b) { const int t = a; a = b; b = t; }  // hook the larger root under the smaller
-    if (atomicCAS(&parent[a], a, b) == a) return;
-  }
 }
 
 __device__ __forceinline__ bool isObject(const ObjectParams& p, int label) {
