@@ -53,6 +53,8 @@ def parse_args():
     ap.add_argument("--e2e-frames", type=int, default=2048, help="frames of the e2e window (pinned host ring, ~0.1 s of PCIe traffic)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cull", action="store_true", help="disable the conservative depth culling (results identical)")
+    ap.add_argument("--force-cull", action="store_true",
+                    help="--workload dynamic: cull even single-frame calls (kb_set_culling(2)); results identical, 3 more launches per frame")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--wire", default="f32", choices=["f32", "compact", "f32u8"],
                     help="f32 = depth f32 + label i32 (hydra::InputData, 8 B/pixel; the headline); compact = u16 millimetre "
@@ -269,6 +271,8 @@ def main_dynamic(args):
     mot = capi.default_motion_config(min_cluster_size=500 if not args.small else 30, min_separation_distance=2.0)
     h = kb.create_map(mc, ic, capi.default_tracking_config(), mot, device=0)
     h.set_camera(cam)
+    if args.force_cull:
+        h.set_culling(2)
     flagged = []
     img_host = torch.zeros((cam.height, cam.width), dtype=torch.int32, pin_memory=True)  # FrameData::dynamic_image
     img_ptr = ctypes.c_void_p(img_host.data_ptr())
