@@ -53,6 +53,9 @@ def parse_args():
     ap.add_argument("--e2e-frames", type=int, default=2048, help="frames of the e2e window (pinned host ring, ~0.1 s of PCIe traffic)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cull", action="store_true", help="disable the conservative depth culling (results identical)")
+    ap.add_argument("--exchange", default="nccl", choices=["nccl", "peers"],
+                    help="--workload dynamic, N > 1: 'nccl' = all-reduce / all-gathers; 'peers' (experiment, unverified on hardware) = "
+                         "the producing kernels store into every rank's symmetric-memory buffers over NVLink, barriers only")
     ap.add_argument("--force-cull", action="store_true",
                     help="--workload dynamic: cull even single-frame calls (kb_set_culling(2)); results identical, 3 more launches per frame")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -369,7 +372,10 @@ def main_dynamic_sharded(args):
     h = kb.create_map(mc, ic, capi.default_tracking_config(), mot, device=local_rank)
     h.set_camera(cam)
     h.set_shard(rank, world)
-    win = kd.ShardedActiveWindow([h], kd.DistComm(world), device=dev)
+    if args.exchange == "peers":
+        win = kd.PeerShardedActiveWindow([h], kd.SymmMemPeers(device=dev), device=dev)
+    else:
+        win = kd.ShardedActiveWindow([h], kd.DistComm(world), device=dev)
     frames = [h.make_frame(rx_depth.data_ptr(), poses[i], stamps[i], label=rx_label.data_ptr(), memory=capi.MEM_DEVICE)
               for i in range(n)]
     clusters = []
@@ -410,8 +416,10 @@ def main_dynamic_sharded(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": "room640-dynamic (BASELINE config[2])", "image": [W, H], "voxel_size": 0.05,
                        "voxels_per_side": 16, "semantics": f"MLE L={L_LABELS}", "frames_per_step": F,
-                       "pipeline": "per frame: NCCL frame broadcast + ShardedActiveWindow.spin_once (pixel-flag all-reduce, "
-                                   "2 halo all-gathers, one host round trip)",
+                       "pipeline": ("per frame: NCCL frame broadcast + ShardedActiveWindow.spin_once (pixel-flag all-reduce, 2 halo "
+                                    "all-gathers, one host round trip)" if args.exchange == "nccl" else
+                                    "per frame: NCCL frame broadcast + PeerShardedActiveWindow.spin_once (producers store into "
+                                    "every rank's symmetric-memory buffers, 3 barriers, one host round trip)"),
                        "parallelism": "block-hash shard x%d" % world, "live_blocks_all_ranks": int(blocks.item()),
                        "exchange_bytes_per_frame_per_rank": {"pixel_flags": fb, "pending": pb, "halo": hb}},
             "per_frame": {"frames_with_clusters": int(sum(1 for x in clusters if x > 0))},

@@ -318,6 +318,17 @@ int kb_motion_cluster_global(kb_handle* h, const uint8_t* pixel_flags);
  * dynamic_image_out != NULL). */
 int kb_motion_result(kb_handle* h, int32_t* dynamic_image_out, int32_t* n_seeds, int32_t* n_clusters);
 
+/* Peer-memory variants of the three exchanges: instead of filling a local buffer for a collective, the producing kernels
+ * store this rank's part directly into every rank's buffer (peer_*[q] = base address of rank q's buffer as mapped on
+ * this device, e.g. torch.distributed._symmetric_memory buffer_ptrs; peer_*[rank] is the local one; n_peers = nranks
+ * <= 16). all_pending / all_halo buffers have the all-gather layout (nranks slots); the flag images are H*W bytes
+ * and must be zero before the peers write (the consumer zeroes its own image after kb_motion_cluster_global). The
+ * host places one barrier between each producer call and the matching consumer call (kb_tracking_pack_halo[_peers]
+ * reads all_pending, kb_tracking_finish reads all_halo, kb_motion_cluster_global reads the flag image). */
+int kb_tracking_begin_peers(kb_handle* h, uint64_t stamp_ns, void* const* peer_all_pending, int32_t n_peers);
+int kb_tracking_pack_halo_peers(kb_handle* h, const void* all_pending, void* const* peer_all_halo, int32_t n_peers);
+int kb_motion_lookup_peers(kb_handle* h, const kb_frame* frame, uint8_t* const* peer_flags, int32_t n_peers);
+
 /* ---- mirror-back / parity export ---------------------------------------------------------------- */
 
 enum { KB_EXPORT_ALL = 0, KB_EXPORT_UPDATED = 1 };

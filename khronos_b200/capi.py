@@ -341,6 +341,23 @@ class MapHandle:
     def tracking_finish(self, all_pending, all_halo):
         self._check(self._fn("tracking_finish")(self._h, C.c_void_p(_ptr(all_pending)), C.c_void_p(_ptr(all_halo))))
 
+    @staticmethod
+    def _ptr_array(bufs):
+        arr = (C.c_void_p * len(bufs))(*[_ptr(b) for b in bufs])
+        return arr
+
+    def tracking_begin_peers(self, stamp_ns: int, peer_all_pending):
+        arr = self._ptr_array(peer_all_pending)
+        self._check(self._fn("tracking_begin_peers")(self._h, C.c_uint64(int(stamp_ns)), arr, len(peer_all_pending)))
+
+    def tracking_pack_halo_peers(self, all_pending, peer_all_halo):
+        arr = self._ptr_array(peer_all_halo)
+        self._check(self._fn("tracking_pack_halo_peers")(self._h, C.c_void_p(_ptr(all_pending)), arr, len(peer_all_halo)))
+
+    def motion_lookup_peers(self, frame: Frame, peer_flags):
+        arr = self._ptr_array(peer_flags)
+        self._check(self._fn("motion_lookup_peers")(self._h, C.byref(frame), arr, len(peer_flags)))
+
     def motion_lookup_local(self, frame: Frame, pixel_flags):
         self._check(self._fn("motion_lookup_local")(self._h, C.byref(frame), C.c_void_p(_ptr(pixel_flags))))
 

@@ -125,6 +125,8 @@ struct kb_handle {
   // sharded per-frame pipeline (kb_tracking_begin / pack_halo / finish, kb_motion_lookup_local / cluster_global)
   ShardExchange xch{};
   int cap_pending = 1024, cap_halo = 2048;
+  uint8_t* d_flags_local = nullptr;  // peer-memory M1 exchange: this rank's flag bytes before they are scattered
+  size_t flags_local_pixels = 0;
   TrackingParams open_pass{};   // parameters of the pass between kb_tracking_begin and kb_tracking_finish
   uint64_t open_pass_stamp = 0;
   int open_pass_state = 0;      // 0 none, 1 begun, 2 halo packed
@@ -519,7 +521,7 @@ int kb_destroy(kb_handle* h) {
   cudaFree(m.born_frame); cudaFree(m.next_pass); cudaFree(m.act_min); cudaFree(h->pending);
   cudaFree(m.sem_label); cudaFree(m.sem_lik); cudaFree(m.color); cudaFree(h->stg_color);
   cudaFree(h->xch.halo_mark); cudaFree(h->xch.publish); cudaFree(h->xch.ghost_keys); cudaFree(h->xch.ghost_vals);
-  cudaFree(h->obj_depth); cudaFree(h->obj_label); cudaFree(h->d_object);
+  cudaFree(h->obj_depth); cudaFree(h->obj_label); cudaFree(h->d_object); cudaFree(h->d_flags_local);
   if (h->h_oscal) cudaFreeHost(h->h_oscal);
   cudaFree(h->stg_depth); cudaFree(h->stg_label); cudaFree(h->stg_mask); cudaFree(h->stg_object);
   cudaFree(h->stg_vertex); cudaFree(h->d_pixel_gidx); cudaFree(h->d_pixel_seed); cudaFree(h->d_removed);
@@ -1043,6 +1045,49 @@ int kb_tracking_begin(kb_handle* h, uint64_t stamp_ns, void* pending_out) {
   return KB_OK;
 }
 
+static int makePeers(kb_handle* h, void* const* ptrs, int32_t n, PeerBuffers* out) {
+  if (!ptrs || n != h->nranks || n > kMaxPeers) return fail(h, KB_ERR_INVALID, "peer buffer list must have one entry per rank (<= 16)");
+  out->n = n;
+  for (int i = 0; i < kMaxPeers; ++i) out->p[i] = i < n ? ptrs[i] : nullptr;
+  for (int i = 0; i < n; ++i)
+    if (!ptrs[i]) return fail(h, KB_ERR_INVALID, "null peer buffer");
+  return KB_OK;
+}
+
+int kb_tracking_begin_peers(kb_handle* h, uint64_t stamp_ns, void* const* peer_all_pending, int32_t n_peers) {
+  if (!h) return KB_ERR_INVALID;
+  if (!h->has_trk || !h->map.with_tracking) return fail(h, KB_ERR_STATE, "tracking not configured");
+  if (h->open_pass_state != 0) return fail(h, KB_ERR_STATE, "kb_tracking_begin: the previous pass was not finished");
+  h->main_dirty = true;
+  KB_CUDA(h, cudaSetDevice(h->device));
+  int st = ensureShardBuffers(h);
+  if (st != KB_OK) return st;
+  PeerBuffers peers{};
+  if ((st = makePeers(h, peer_all_pending, n_peers, &peers)) != KB_OK) return st;
+  TrackingParams p{};
+  if ((st = trackingParams(h, stamp_ns, &p)) != KB_OK) return st;
+  launchTrackingBeginPeers(h->dm, p, h->xch, peers, h->stream);
+  KB_CUDA(h, cudaGetLastError());
+  h->open_pass = p;
+  h->open_pass_stamp = stamp_ns;
+  h->open_pass_state = 1;
+  return KB_OK;
+}
+
+int kb_tracking_pack_halo_peers(kb_handle* h, const void* all_pending, void* const* peer_all_halo, int32_t n_peers) {
+  if (!h || !all_pending) return fail(h, KB_ERR_INVALID, "null argument");
+  if (h->open_pass_state != 1) return fail(h, KB_ERR_STATE, "kb_tracking_pack_halo needs kb_tracking_begin first");
+  h->main_dirty = true;
+  KB_CUDA(h, cudaSetDevice(h->device));
+  PeerBuffers peers{};
+  int st = makePeers(h, peer_all_halo, n_peers, &peers);
+  if (st != KB_OK) return st;
+  launchHaloPackPeers(h->dm, h->open_pass, h->xch, static_cast<const int32_t*>(all_pending), peers, h->stream);
+  KB_CUDA(h, cudaGetLastError());
+  h->open_pass_state = 2;
+  return KB_OK;
+}
+
 int kb_tracking_pack_halo(kb_handle* h, const void* all_pending, void* halo_out) {
   if (h) h->main_dirty = true;  // KB_PIPELINE: the next prologue must wait for this main-stream work
   if (!h || !all_pending || !halo_out) return fail(h, KB_ERR_INVALID, "null argument");
@@ -1411,6 +1456,29 @@ int kb_motion_lookup_local(kb_handle* h, const kb_frame* f, uint8_t* pixel_flags
     return fail(h, KB_ERR_STATE, "the sharded motion path needs min_separation_distance > 0 and no caller-supplied vertex map");
   KB_CUDA(h, cudaSetDevice(h->device));
   return enqueueMotionLookup(h, f, pixel_flags);
+}
+
+int kb_motion_lookup_peers(kb_handle* h, const kb_frame* f, uint8_t* const* peer_flags, int32_t n_peers) {
+  if (!h || !f || (!f->depth && !f->depth_u16)) return fail(h, KB_ERR_INVALID, "null argument");
+  if (!h->has_mot || !h->map.with_tracking) return fail(h, KB_ERR_STATE, "motion detector not configured");
+  if (!h->has_cam) return fail(h, KB_ERR_STATE, "kb_set_camera must be called first");
+  if (!(h->mot.min_separation_distance > 0.f) || f->vertex_world != nullptr)
+    return fail(h, KB_ERR_STATE, "the sharded motion path needs min_separation_distance > 0 and no caller-supplied vertex map");
+  KB_CUDA(h, cudaSetDevice(h->device));
+  PeerBuffers peers{};
+  int st = makePeers(h, reinterpret_cast<void* const*>(peer_flags), n_peers, &peers);
+  if (st != KB_OK) return st;
+  const size_t px = static_cast<size_t>(h->cam.width) * h->cam.height;
+  if (h->flags_local_pixels < px) {
+    cudaFree(h->d_flags_local);
+    h->d_flags_local = nullptr;
+    KB_CUDA(h, devAlloc(&h->d_flags_local, px, 0));
+    h->flags_local_pixels = px;
+  }
+  if ((st = enqueueMotionLookup(h, f, h->d_flags_local)) != KB_OK) return st;
+  launchFlagScatter(h->d_flags_local, peers, static_cast<int>(px), h->stream);
+  KB_CUDA(h, cudaGetLastError());
+  return KB_OK;
 }
 
 int kb_motion_cluster_global(kb_handle* h, const uint8_t* pixel_flags) {

@@ -1181,6 +1181,71 @@ __global__ void __launch_bounds__(kThreads) haloPackKernel(const DeviceMap m, co
   }
 }
 
+// ---- peer-memory producers: the same lists / masks, stored into slot `rank` of EVERY rank's buffer --------------------
+__global__ void exportPendingPeersKernel(const DeviceMap m, const int* __restrict__ pending, const PeerBuffers peers, int rank,
+                                         int stride, int cap) {
+  const int n = m.counters[kCtrPending];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) m.counters[kCtrHalo] = 0;
+  const bool entry = i < min(n, cap);
+  int3 bi = make_int3(0, 0, 0);
+  if (entry) bi = m.block_index[pending[i]];
+  for (int q = 0; q < peers.n; ++q) {
+    int32_t* __restrict__ out = static_cast<int32_t*>(peers.p[q]) + static_cast<size_t>(rank) * stride;
+    if (i == 0) {
+      out[0] = min(n, cap);
+      out[1] = n > cap ? 1 : 0;
+      out[2] = out[3] = 0;
+    }
+    if (entry) { out[4 + 3 * i] = bi.x; out[4 + 3 * i + 1] = bi.y; out[4 + 3 * i + 2] = bi.z; }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) haloPackPeersKernel(const DeviceMap m, const TrackingParams p, const ShardExchange x,
+                                                                const PeerBuffers peers) {
+  const int n_all = m.counters[kCtrHalo];
+  const int n = min(n_all, x.cap_halo);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    for (int q = 0; q < peers.n; ++q) {
+      int32_t* out = static_cast<int32_t*>(peers.p[q]) + static_cast<size_t>(x.rank) * x.halo_stride();
+      out[0] = n;
+      out[1] = n_all > x.cap_halo ? 1 : 0;
+      out[2] = out[3] = 0;
+    }
+  }
+  const int V = m.V;
+  for (int j = blockIdx.x; j < n_all; j += gridDim.x) {
+    const int slot = j < x.cap_halo ? x.publish[j] : -1;
+    if (slot < 0) continue;
+    if (threadIdx.x == 0) x.halo_mark[slot] = 0;
+    const size_t eoff = static_cast<size_t>(x.rank) * x.halo_stride() + 4 + static_cast<size_t>(j) * x.halo_entry();
+    if (threadIdx.x == 0) {
+      const int3 bi = m.block_index[slot];
+      for (int q = 0; q < peers.n; ++q) {
+        int32_t* e = static_cast<int32_t*>(peers.p[q]) + eoff;
+        e[0] = bi.x; e[1] = bi.y; e[2] = bi.z; e[3] = 0;
+      }
+    }
+    const size_t base = static_cast<size_t>(slot) * V;
+    for (int lin = threadIdx.x; lin < V; lin += kThreads) {
+      const bool fr = voxelFreeNow(m, p.ev, base + lin, m.vflags[base + lin]);
+      const unsigned bits = __ballot_sync(0xffffffffu, fr);
+      if ((threadIdx.x & 31) == 0)
+        for (int q = 0; q < peers.n; ++q) static_cast<int32_t*>(peers.p[q])[eoff + 4 + (lin >> 5)] = static_cast<int32_t>(bits);
+    }
+  }
+}
+
+// M1 exchange without a reduction: a pixel's flag byte is non-zero on at most one rank (the owner of its block), so every
+// rank simply stores its non-zero bytes into all reduced flag images (zeroed by their owners after the previous use).
+__global__ void flagScatterKernel(const uint8_t* __restrict__ local_flags, const PeerBuffers peers, int n) {
+  const int px = blockIdx.x * blockDim.x + threadIdx.x;
+  if (px >= n) return;
+  const uint8_t f = local_flags[px];
+  if (f == 0) return;
+  for (int q = 0; q < peers.n; ++q) static_cast<uint8_t*>(peers.p[q])[px] = f;
+}
+
 // Overflowed publish lists leave marks behind: clear the marks of the slots that did not fit (rare; error path).
 __global__ void haloUnmarkKernel(const DeviceMap m, const ShardExchange x, int n_slots) {
   const int slot = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1548,6 +1613,20 @@ void launchHaloPack(const DeviceMap& m, const TrackingParams& p, const ShardExch
   haloMarkKernel<<<(n + 255) / 256, 256, 0, s>>>(m, x, all_pending);
   haloPackKernel<<<148 * 4, kThreads, 0, s>>>(m, p, x, halo_out);
   haloUnmarkKernel<<<(m.max_blocks + 255) / 256, 256, 0, s>>>(m, x, m.max_blocks);
+}
+void launchTrackingBeginPeers(const DeviceMap& m, const TrackingParams& p, const ShardExchange& x, const PeerBuffers& peers, cudaStream_t s) {
+  trackingPassKernel<<<(std::max(p.n_slots, 1) + 255) / 256, 256, 0, s>>>(m, p);
+  exportPendingPeersKernel<<<(x.cap_pending + 255) / 256, 256, 0, s>>>(m, p.pending, peers, x.rank, x.pending_stride(), x.cap_pending);
+}
+void launchHaloPackPeers(const DeviceMap& m, const TrackingParams& p, const ShardExchange& x, const int32_t* all_pending,
+                         const PeerBuffers& peers, cudaStream_t s) {
+  const int n = x.nranks * x.cap_pending * 27;
+  haloMarkKernel<<<(n + 255) / 256, 256, 0, s>>>(m, x, all_pending);
+  haloPackPeersKernel<<<148 * 4, kThreads, 0, s>>>(m, p, x, peers);
+  haloUnmarkKernel<<<(m.max_blocks + 255) / 256, 256, 0, s>>>(m, x, m.max_blocks);
+}
+void launchFlagScatter(const uint8_t* local_flags, const PeerBuffers& peers, int n, cudaStream_t s) {
+  flagScatterKernel<<<(n + 255) / 256, 256, 0, s>>>(local_flags, peers, n);
 }
 void launchTrackingFinish(const DeviceMap& m, const TrackingParams& p, const ShardExchange& x, const int32_t* all_pending,
                           const int32_t* all_halo, int everfree_grid, cudaStream_t s) {

@@ -82,6 +82,15 @@ struct TrackingParams {
   uint32_t ghost_mask;
 };
 
+// Peer-memory variant of the exchanges: instead of writing a local buffer that an all-gather distributes, the producing
+// kernel stores this rank's part straight into every rank's buffer (slot `rank` of the all_* layout) over NVLink peer
+// mappings; the host only places a barrier between producer and consumer.
+constexpr int kMaxPeers = 16;
+struct PeerBuffers {
+  void* p[kMaxPeers];  // base address of each rank's buffer as mapped on this device (p[rank] = the local one)
+  int n;
+};
+
 // Exchange buffers of the sharded tracking pass, all int32 words, one per rank, concatenated
 // by the all-gather:
 //   pending buffer  [0] count  [1] overflow  [2..3] 0   then count x (bx, by, bz)                  (4 + 3*cap_pending words)
@@ -135,6 +144,12 @@ void launchMotionFinalize(const DeviceMap& m, const uint8_t* flags, int3* gidx, 
 void launchTrackingBegin(const DeviceMap& m, const TrackingParams& p, const ShardExchange& x, int32_t* pending_out, cudaStream_t s);
 void launchHaloPack(const DeviceMap& m, const TrackingParams& p, const ShardExchange& x, const int32_t* all_pending,
                     int32_t* halo_out, cudaStream_t s);
+// Peer-memory producers (see PeerBuffers): K2 + pending list into slot `rank` of every rank's all_pending buffer; free
+// masks into slot `rank` of every rank's all_halo buffer; non-zero pixel flags into every rank's reduced flag image.
+void launchTrackingBeginPeers(const DeviceMap& m, const TrackingParams& p, const ShardExchange& x, const PeerBuffers& peers, cudaStream_t s);
+void launchHaloPackPeers(const DeviceMap& m, const TrackingParams& p, const ShardExchange& x, const int32_t* all_pending,
+                         const PeerBuffers& peers, cudaStream_t s);
+void launchFlagScatter(const uint8_t* local_flags, const PeerBuffers& peers, int n, cudaStream_t s);
 void launchTrackingFinish(const DeviceMap& m, const TrackingParams& p, const ShardExchange& x, const int32_t* all_pending,
                           const int32_t* all_halo, int everfree_grid, cudaStream_t s);
 void launchAllocateBox(const DeviceMap& m, int3 lo, int3 dims, int rank, int nranks, uint32_t born, cudaStream_t s);

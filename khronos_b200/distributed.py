@@ -136,3 +136,92 @@ class ShardedActiveWindow:
         if not with_motion_result:
             return None
         return [h.motion_result(want_image) for h in hs]
+
+
+# ---- peer-memory exchange (no collectives: producers store straight into every rank's buffers) -----------------------
+
+class LocalPeers:
+    """All shards live in this process: every shard's buffers are directly addressable, the barrier is the program order."""
+
+    def __init__(self, n_shards: int, device="cpu"):
+        import torch
+        self.n, self.device = n_shards, torch.device(device)
+
+    def alloc(self, numel: int, dtype):
+        """One buffer per local shard + for each local shard the list of all ranks' buffers (as seen from that shard)."""
+        import torch
+        bufs = [torch.zeros(numel, dtype=dtype, device=self.device) for _ in range(self.n)]
+        return bufs, [bufs for _ in range(self.n)]
+
+    def barrier(self):
+        pass
+
+
+class SymmMemPeers:
+    """One rank of a torch.distributed job: buffers come from torch.distributed._symmetric_memory (peer-mapped over
+    NVLink), the barrier is the symmetric-memory barrier on the current stream. UNVERIFIED: written against the PyTorch
+    2.11 API without a multi-GPU box at hand; tests cover the kernels through LocalPeers only."""
+
+    def __init__(self, group=None, device=None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        self.symm_mem, self.group = symm_mem, group if group is not None else dist.group.WORLD
+        self.device, self.handles = device, []
+
+    def alloc(self, numel: int, dtype):
+        t = self.symm_mem.empty(numel, dtype=dtype, device=self.device)
+        t.zero_()
+        hdl = self.symm_mem.rendezvous(t, self.group)
+        self.handles.append(hdl)
+        return [t], [[int(p) for p in hdl.buffer_ptrs]]
+
+    def barrier(self):
+        self.handles[0].barrier()
+
+
+class PeerShardedActiveWindow:
+    """ShardedActiveWindow with the peer-memory variants of the three exchanges: kb_motion_lookup_peers,
+    kb_tracking_begin_peers and kb_tracking_pack_halo_peers store this rank's flag bytes / pending list / free masks
+    straight into every rank's buffers; the host only places a barrier between producer and consumer."""
+
+    def __init__(self, handles, peers, device="cpu"):
+        import torch
+        self.handles, self.peers = list(handles), peers
+        self.device = torch.device(device)
+        pb, hb, fb = self.handles[0].shard_buffer_sizes()
+        world = None
+        self.flags, self.flags_peers = peers.alloc(fb, torch.uint8)
+        world = len(self.flags_peers[0])
+        self.all_pending, self.pending_peers = peers.alloc(world * (pb // 4), torch.int32)
+        self.all_halo, self.halo_peers = peers.alloc(world * (hb // 4), torch.int32)
+        if self.device.type == "cuda":
+            for h in self.handles:
+                h.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def spin_once(self, frames, want_image=True):
+        from . import capi
+        hs = self.handles
+        for h, f, fp in zip(hs, frames, self.flags_peers):
+            h.motion_lookup_peers(f, fp)
+        self.peers.barrier()
+        for h, f, fl in zip(hs, frames, self.flags):
+            h.motion_cluster_global(fl)
+            fl.zero_()  # ready for the peers' stores of the next frame (ordered by the barriers of the tracking exchange)
+            g = capi.Frame.from_buffer_copy(f)
+            g.mask = capi.MASK_LAST_DETECTION
+            h.integrate_frame(g, want_stats=False)
+        return self.update_tracking([int(f.stamp_ns) for f in frames], want_image=want_image)
+
+    def update_tracking(self, stamps, want_image=False, with_motion_result=True):
+        hs = self.handles
+        for h, st, pp in zip(hs, stamps, self.pending_peers):
+            h.tracking_begin_peers(st, pp)
+        self.peers.barrier()
+        for h, ap, hp in zip(hs, self.all_pending, self.halo_peers):
+            h.tracking_pack_halo_peers(ap, hp)
+        self.peers.barrier()
+        for h, ap, ah in zip(hs, self.all_pending, self.all_halo):
+            h.tracking_finish(ap, ah)
+        if not with_motion_result:
+            return None
+        return [h.motion_result(want_image) for h in hs]

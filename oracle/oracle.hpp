@@ -115,6 +115,8 @@ class Oracle {
   // implements it on host buffers with the layouts of csrc/kb_kernels.cuh::ShardExchange so that world-size-2
   // gloo tests can prove "union of the shards == the unsharded map" on CPU.
   void setShard(int rank, int nranks) { rank_ = rank; nranks_ = nranks; }
+  int rank() const { return rank_; }
+  int nranks() const { return nranks_; }
   static int blockOwner(const Idx3& b, int nranks);
   void motionLookupLocal(const kb_frame& f, uint8_t* flags);
   void motionClusterGlobal(const uint8_t* flags, int32_t* dynamic_image, int32_t* n_seeds, int32_t* n_clusters);

@@ -207,6 +207,37 @@ int ko_tracking_finish(ko_handle* h, const void* all_pending, const void* all_ha
   return h->o->ok() ? KB_OK : fail(h, KB_ERR_CAPACITY);
 }
 
+// Peer-memory variants on host buffers: compute this shard's part, then store it into slot `rank` of every rank's buffer.
+int ko_tracking_begin_peers(ko_handle* h, uint64_t stamp_ns, void* const* peers, int32_t n) {
+  if (!h || !peers || n != h->o->nranks()) return KB_ERR_INVALID;
+  const size_t stride = 4 + 3 * static_cast<size_t>(h->cap_pending);
+  std::vector<int32_t> mine(stride, 0);
+  h->o->trackingBegin(stamp_ns, mine.data(), h->cap_pending);
+  for (int q = 0; q < n; ++q) std::memcpy(static_cast<int32_t*>(peers[q]) + h->o->rank() * stride, mine.data(), stride * 4);
+  return h->o->ok() ? KB_OK : fail(h, KB_ERR_INVALID);
+}
+
+int ko_tracking_pack_halo_peers(ko_handle* h, const void* all_pending, void* const* peers, int32_t n) {
+  if (!h || !all_pending || !peers || n != h->o->nranks()) return KB_ERR_INVALID;
+  const size_t stride = 4 + static_cast<size_t>(h->cap_halo) * (4 + h->o->V() / 32);
+  std::vector<int32_t> mine(stride, 0);
+  h->o->packHalo(static_cast<const int32_t*>(all_pending), h->cap_pending, mine.data(), h->cap_halo);
+  for (int q = 0; q < n; ++q) std::memcpy(static_cast<int32_t*>(peers[q]) + h->o->rank() * stride, mine.data(), stride * 4);
+  return h->o->ok() ? KB_OK : fail(h, KB_ERR_INVALID);
+}
+
+int ko_motion_lookup_peers(ko_handle* h, const kb_frame* f_in, uint8_t* const* peers, int32_t n) {
+  if (!h || !f_in || !peers || n != h->o->nranks()) return KB_ERR_INVALID;
+  kb_frame tmp;
+  const kb_frame* f = expandCompact(h, f_in, &tmp);
+  std::vector<uint8_t> mine(h->pixels, 0);
+  h->o->motionLookupLocal(*f, mine.data());
+  for (int q = 0; q < n; ++q)
+    for (size_t px = 0; px < h->pixels; ++px)
+      if (mine[px]) peers[q][px] = mine[px];
+  return h->o->ok() ? KB_OK : fail(h, KB_ERR_INVALID);
+}
+
 int ko_motion_lookup_local(ko_handle* h, const kb_frame* f_in, uint8_t* pixel_flags) {
   if (!h || !f_in || !pixel_flags) return KB_ERR_INVALID;
   kb_frame tmp;

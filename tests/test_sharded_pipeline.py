@@ -59,7 +59,7 @@ def assert_union_equals(parts, bo, what):
         np.testing.assert_array_equal(cat(name), getattr(bo, name), err_msg=f"{what} {name}")
 
 
-def run_sharded_vs_unsharded(ref_lib, lib, prefix, nshards, device, sep=2.0, caps=None, reset_every=0, scale=4, n=30):
+def run_sharded_vs_unsharded(ref_lib, lib, prefix, nshards, device, sep=2.0, caps=None, reset_every=0, scale=4, n=30, peers=False):
     cam = hs.small_camera(scale)
     frames, poses, stamps = dynamic_scenario(cam, n)
     mot = capi.default_motion_config(min_cluster_size=5, min_separation_distance=sep)
@@ -71,7 +71,8 @@ def run_sharded_vs_unsharded(ref_lib, lib, prefix, nshards, device, sep=2.0, cap
         if caps:
             g.set_shard_capacity(*caps)
         shards.append(g)
-    win = kd.ShardedActiveWindow(shards, kd.LocalComm(), device=device)
+    win = (kd.PeerShardedActiveWindow(shards, kd.LocalPeers(nshards, device), device=device) if peers
+           else kd.ShardedActiveWindow(shards, kd.LocalComm(), device=device))
     total_dyn, removed = 0, 0
     for i, ((d, l), T, st) in enumerate(zip(frames, poses, stamps)):
         img_o, ns_o, nc_o = o.spin_once(o.make_frame(d, T, st, label=l))
@@ -193,3 +194,14 @@ def test_oracle_shards_random_walk(oracle_lib, nshards, conn, seed):
     bo = o.export_blocks()
     assert_union_equals([g.export_blocks() for g in shards], bo, f"random walk {nshards} shards conn {conn}")
     assert bo.ever_free.sum() > 100
+
+
+def test_oracle_shards_peer_memory_exchange(oracle_lib):
+    """The peer-memory variants of the exchanges (producers store into every shard's buffers) give the same maps."""
+    run_sharded_vs_unsharded(oracle_lib, oracle_lib, "ko_", 3, "cpu", scale=8, n=22, peers=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nshards", [2, 4])
+def test_product_shards_peer_memory_exchange(oracle_lib, product_lib, nshards):
+    run_sharded_vs_unsharded(oracle_lib, product_lib, "kb_", nshards, "cuda", sep=2.0, peers=True)

@@ -36,6 +36,9 @@ def main(argv):
     torch.cuda.synchronize = lambda *a, **k: None
     orig = kd.ShardedActiveWindow.__init__
     kd.ShardedActiveWindow.__init__ = lambda self, handles, comm, device="cpu": orig(self, handles, comm, device="cpu")
+    orig_p, orig_l = kd.PeerShardedActiveWindow.__init__, kd.LocalPeers.__init__
+    kd.PeerShardedActiveWindow.__init__ = lambda self, handles, peers, device="cpu": orig_p(self, handles, peers, device="cpu")
+    kd.LocalPeers.__init__ = lambda self, n_shards, device="cpu": orig_l(self, n_shards, "cpu")
     args = list(argv) or [os.path.join(ROOT, "tests")]
     # tests that need a real device or a second process group are out of reach of the emulation
     deselect = ["-k", "not adaptor and not two_gpu"]

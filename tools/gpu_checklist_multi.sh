@@ -20,3 +20,6 @@ done
 echo "== 3. per-frame pipeline (config[2]) sharded over $N GPUs"
 timeout 300 $TR bench.py --gpus $N --workload dynamic --steps 4 --warmup 2 > gpurun_out/bench_n${N}_dynamic.json 2> gpurun_out/bench_n${N}_dynamic.err
 tail -c 700 gpurun_out/bench_n${N}_dynamic.json || tail -3 gpurun_out/bench_n${N}_dynamic.err
+echo "== 3b. the same with the peer-memory exchange (symmetric memory; first time on hardware)"
+timeout 300 $TR bench.py --gpus $N --workload dynamic --steps 4 --warmup 2 --exchange peers > gpurun_out/bench_n${N}_dynamic_peers.json 2> gpurun_out/bench_n${N}_dynamic_peers.err
+tail -c 400 gpurun_out/bench_n${N}_dynamic_peers.json || tail -5 gpurun_out/bench_n${N}_dynamic_peers.err
