@@ -53,6 +53,9 @@ def parse_args():
     ap.add_argument("--e2e-frames", type=int, default=2048, help="frames of the e2e window (pinned host ring, ~0.1 s of PCIe traffic)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cull", action="store_true", help="disable the conservative depth culling (results identical)")
+    ap.add_argument("--bcast", default="nccl", choices=["nccl", "multimem"],
+                    help="N > 1 frame broadcast: 'nccl' = dist.broadcast; 'multimem' (experiment, unverified on hardware) = rank 0 stores "
+                         "the step's frames once to the NVLS multicast mapping of a symmetric receive buffer (kb_multicast_copy)")
     ap.add_argument("--exchange", default="nccl", choices=["nccl", "peers"],
                     help="--workload dynamic, N > 1: 'nccl' = all-reduce / all-gathers; 'peers' (experiment, unverified on hardware) = "
                          "the producing kernels store into every rank's symmetric-memory buffers over NVLink, barriers only")
@@ -518,6 +521,36 @@ def main():
         rxp = [torch.empty((F, 2, cam.height, cam.width), dtype=torch.int32, device=dev) for _ in range(2)]
         rx = [(b[:, 0].view(torch.float32), b[:, 1]) for b in rxp]
 
+    mm_hdl, tx = None, None
+    if world > 1 and args.bcast == "multimem":
+        # receive buffers from symmetric memory (same layout as above) + a local transmit buffer on the ingest rank
+        import torch.distributed._symmetric_memory as symm_mem
+        shape, dt = rxp[0].shape, rxp[0].dtype
+        rxp, mm_hdl = [], []
+        for _ in range(2):
+            t = symm_mem.empty(int(np.prod(shape)), dtype=dt, device=dev)
+            mm_hdl.append(symm_mem.rendezvous(t, dist.group.WORLD))
+            rxp.append(t.view(shape))
+        if not mm_hdl[0].multicast_ptr:  # 0 when the system has no NVLS multicast support
+            raise SystemExit("--bcast multimem: no NVLS multicast mapping for the symmetric buffer on this system")
+        HW = cam.height * cam.width
+        if compact:
+            rx = [(b[:, :2 * HW].view(torch.int16).view(F, cam.height, cam.width), b[:, 2 * HW:].view(F, cam.height, cam.width)) for b in rxp]
+        elif f32u8:
+            rx = [(b[:, :4 * HW].view(torch.float32).view(F, cam.height, cam.width), b[:, 4 * HW:].view(F, cam.height, cam.width)) for b in rxp]
+        else:
+            rx = [(b[:, 0].view(torch.float32), b[:, 1]) for b in rxp]
+        if rank == 0:
+            tx = torch.empty(shape, dtype=dt, device=dev)
+            if compact:
+                txv = (tx[:, :2 * HW].view(torch.int16).view(F, cam.height, cam.width), tx[:, 2 * HW:].view(F, cam.height, cam.width))
+            elif f32u8:
+                txv = (tx[:, :4 * HW].view(torch.float32).view(F, cam.height, cam.width), tx[:, 4 * HW:].view(F, cam.height, cam.width))
+            else:
+                txv = (tx[:, 0].view(torch.float32), tx[:, 1])
+        mcopy = kb.lib().kb_multicast_copy
+        mcopy.restype = ctypes.c_int
+
     mc, ic = map_configs(args)
     h = kb.create_map(mc, ic, capi.default_tracking_config(), None, device=local_rank)
     h.set_camera(cam)
@@ -577,11 +610,28 @@ def main():
             db, lb = rx[bsel]
             cur = torch.cuda.current_stream()
             cur.wait_event(buf_free[bsel])
-            if rank == 0:
-                idx = torch.tensor([frame_index(step, j) for j in range(F)], device=dev)
-                db.copy_(depth.index_select(0, idx))
-                lb.copy_(label.index_select(0, idx))
-            dist.broadcast(rxp[bsel], 0)
+            if mm_hdl is not None:
+                # NVLS: every rank has released rx[bsel] (barrier), rank 0 stores the step's frames once to the multicast
+                # address, a second barrier publishes them
+                mm_hdl[bsel].barrier()
+                if rank == 0:
+                    idx = torch.tensor([frame_index(step, j) for j in range(F)], device=dev)
+                    txv[0].copy_(depth.index_select(0, idx))
+                    txv[1].copy_(label.index_select(0, idx))
+                    nbytes = tx.numel() * tx.element_size()
+                    st = mcopy(ctypes.c_void_p(int(mm_hdl[bsel].multicast_ptr)), ctypes.c_void_p(tx.data_ptr()),
+                               ctypes.c_size_t(nbytes - nbytes % 16), ctypes.c_void_p(cur.cuda_stream))
+                    if st != 0:
+                        raise RuntimeError(f"kb_multicast_copy failed: {st}")
+                    if nbytes % 16:  # tail (never for the shapes used here)
+                        rxp[bsel].view(-1).view(torch.uint8)[nbytes - nbytes % 16:].copy_(tx.view(-1).view(torch.uint8)[nbytes - nbytes % 16:])
+                mm_hdl[bsel].barrier()
+            else:
+                if rank == 0:
+                    idx = torch.tensor([frame_index(step, j) for j in range(F)], device=dev)
+                    db.copy_(depth.index_select(0, idx))
+                    lb.copy_(label.index_select(0, idx))
+                dist.broadcast(rxp[bsel], 0)
             stream.wait_stream(cur)
         with torch.cuda.stream(stream):
             for j, (arr, n) in enumerate(prebuilt[step]):
@@ -746,7 +796,7 @@ def main():
                                        "depth f32 + label i32 (8 B/px)"),
                        "lap_frames": lap, "live_blocks_rank0": total.total_blocks,
                        "l2": "inputs larger than L2: each step streams %.1f GB of frames" % (F * P * bpp / 1e9),
-                       "parallelism": "block-hash shard x%d, NCCL frame broadcast" % world if world > 1 else "single GPU",
+                       "parallelism": ("block-hash shard x%d, %s frame broadcast" % (world, "NVLS multimem" if args.bcast == "multimem" else "NCCL")) if world > 1 else "single GPU",
                        "render_s": round(t_render, 1)},
             "per_frame": {"voxels_updated": nv_all / n_frames, "voxels_semantic": nsem_all / n_frames,
                           "blocks_visited": nblk_all / n_frames,

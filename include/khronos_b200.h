@@ -329,6 +329,12 @@ int kb_tracking_begin_peers(kb_handle* h, uint64_t stamp_ns, void* const* peer_a
 int kb_tracking_pack_halo_peers(kb_handle* h, const void* all_pending, void* const* peer_all_halo, int32_t n_peers);
 int kb_motion_lookup_peers(kb_handle* h, const kb_frame* frame, uint8_t* const* peer_flags, int32_t n_peers);
 
+/* NVLS frame broadcast for the sharded map (no handle needed): copies `bytes` (multiple of 16, both pointers 16 B
+ * aligned) from local device memory to the MULTICAST address of a symmetric buffer (e.g. _SymmetricMemory.multicast_ptr
+ * + offset), on the given stream: NVSwitch delivers every store to all ranks of the multicast group. The caller orders
+ * it against the consumers with a barrier (e.g. _SymmetricMemory.barrier()). Untested on hardware in round 1. */
+int kb_multicast_copy(void* multicast_dst, const void* src, size_t bytes, void* cuda_stream);
+
 /* ---- mirror-back / parity export ---------------------------------------------------------------- */
 
 enum { KB_EXPORT_ALL = 0, KB_EXPORT_UPDATED = 1 };

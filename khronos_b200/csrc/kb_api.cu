@@ -1511,6 +1511,14 @@ int kb_motion_result(kb_handle* h, int32_t* dynamic_image_out, int32_t* n_seeds,
   return KB_OK;
 }
 
+int kb_multicast_copy(void* multicast_dst, const void* src, size_t bytes, void* cuda_stream) {
+  if (!multicast_dst || !src || (bytes % 16) != 0 || (reinterpret_cast<uintptr_t>(multicast_dst) % 16) != 0 ||
+      (reinterpret_cast<uintptr_t>(src) % 16) != 0)
+    return KB_ERR_INVALID;
+  launchMulticastCopy(multicast_dst, src, bytes, static_cast<cudaStream_t>(cuda_stream));
+  return cudaGetLastError() == cudaSuccess ? KB_OK : KB_ERR_CUDA;
+}
+
 int kb_host_cluster_motion(const kb_camera* camera, const kb_motion_config* motion, const double world_T_sensor[16],
                            const int32_t* pixel_voxel_xyz, const uint8_t* pixel_seed, const float* depth,
                            int32_t* dynamic_image_out, int32_t* n_seeds, int32_t* n_clusters) {

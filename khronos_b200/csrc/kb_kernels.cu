@@ -1246,6 +1246,22 @@ __global__ void flagScatterKernel(const uint8_t* __restrict__ local_flags, const
   for (int q = 0; q < peers.n; ++q) static_cast<uint8_t*>(peers.p[q])[px] = f;
 }
 
+// ---- NVLS frame broadcast: rank 0 stores the step's frames ONCE to the multicast mapping of the symmetric receive buffer;
+// NVSwitch replicates every store to all ranks (multimem.st; SASS: STG.E.128.STRONG.SYS on a multicast address), so the
+// ingest rank's egress is 1x the frame bytes instead of a ring / tree of point-to-point copies.
+__global__ void __launch_bounds__(256) multicastCopyKernel(float4* __restrict__ mc_dst, const float4* __restrict__ src, size_t n16) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n16; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float4 v = __ldg(&src[i]);
+#ifdef KB_CUDA_EMU
+    mc_dst[i] = v;
+#else
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_dst + i), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w)
+                 : "memory");
+#endif
+  }
+}
+
 // Overflowed publish lists leave marks behind: clear the marks of the slots that did not fit (rare; error path).
 __global__ void haloUnmarkKernel(const DeviceMap m, const ShardExchange x, int n_slots) {
   const int slot = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1624,6 +1640,12 @@ void launchHaloPackPeers(const DeviceMap& m, const TrackingParams& p, const Shar
   haloMarkKernel<<<(n + 255) / 256, 256, 0, s>>>(m, x, all_pending);
   haloPackPeersKernel<<<148 * 4, kThreads, 0, s>>>(m, p, x, peers);
   haloUnmarkKernel<<<(m.max_blocks + 255) / 256, 256, 0, s>>>(m, x, m.max_blocks);
+}
+void launchMulticastCopy(void* mc_dst, const void* src, size_t bytes, cudaStream_t s) {
+  const size_t n16 = bytes / 16;
+  if (n16 == 0) return;
+  const int grid = static_cast<int>(std::min<size_t>((n16 + 255) / 256, 148 * 8));
+  multicastCopyKernel<<<grid, 256, 0, s>>>(static_cast<float4*>(mc_dst), static_cast<const float4*>(src), n16);
 }
 void launchFlagScatter(const uint8_t* local_flags, const PeerBuffers& peers, int n, cudaStream_t s) {
   flagScatterKernel<<<(n + 255) / 256, 256, 0, s>>>(local_flags, peers, n);

@@ -150,6 +150,7 @@ void launchTrackingBeginPeers(const DeviceMap& m, const TrackingParams& p, const
 void launchHaloPackPeers(const DeviceMap& m, const TrackingParams& p, const ShardExchange& x, const int32_t* all_pending,
                          const PeerBuffers& peers, cudaStream_t s);
 void launchFlagScatter(const uint8_t* local_flags, const PeerBuffers& peers, int n, cudaStream_t s);
+void launchMulticastCopy(void* mc_dst, const void* src, size_t bytes, cudaStream_t s);  // bytes, both 16 B aligned
 void launchTrackingFinish(const DeviceMap& m, const TrackingParams& p, const ShardExchange& x, const int32_t* all_pending,
                           const int32_t* all_halo, int everfree_grid, cudaStream_t s);
 void launchAllocateBox(const DeviceMap& m, int3 lo, int3 dims, int rank, int nranks, uint32_t born, cudaStream_t s);

@@ -207,6 +207,8 @@ int ko_tracking_finish(ko_handle* h, const void* all_pending, const void* all_ha
   return h->o->ok() ? KB_OK : fail(h, KB_ERR_CAPACITY);
 }
 
+int ko_multicast_copy(void* dst, const void* src, size_t bytes, void*) { std::memcpy(dst, src, bytes); return KB_OK; }
+
 // Peer-memory variants on host buffers: compute this shard's part, then store it into slot `rank` of every rank's buffer.
 int ko_tracking_begin_peers(ko_handle* h, uint64_t stamp_ns, void* const* peers, int32_t n) {
   if (!h || !peers || n != h->o->nranks()) return KB_ERR_INVALID;

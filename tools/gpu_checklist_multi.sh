@@ -17,6 +17,13 @@ for ch in 16 32; do
   NCCL_MIN_NCHANNELS=$ch timeout 300 $TR bench.py --gpus $N --wire f32 > gpurun_out/bench_n${N}_f32_ch$ch.json 2> gpurun_out/bench_n${N}_f32_ch$ch.err
   python -c "import json;d=json.load(open('gpurun_out/bench_n${N}_f32_ch$ch.json'));print('NCCL_MIN_NCHANNELS=$ch', round(d['value']), 'fps')" || true
 done
+echo "== 2c. NVLS multicast frame broadcast (kb_multicast_copy into a symmetric buffer; first time on hardware; smaller steps)"
+for w in f32 f32u8; do
+  timeout 300 $TR bench.py --gpus $N --wire $w --bcast multimem --frames-per-step 1000 > gpurun_out/bench_n${N}_${w}_mm.json 2> gpurun_out/bench_n${N}_${w}_mm.err
+  python -c "import json;d=json.load(open('gpurun_out/bench_n${N}_${w}_mm.json'));print('multimem $w', round(d['value']), 'fps')" || tail -4 gpurun_out/bench_n${N}_${w}_mm.err
+  timeout 300 $TR bench.py --gpus $N --wire $w --frames-per-step 1000 > gpurun_out/bench_n${N}_${w}_f1000.json 2> gpurun_out/bench_n${N}_${w}_f1000.err
+  python -c "import json;d=json.load(open('gpurun_out/bench_n${N}_${w}_f1000.json'));print('nccl     $w', round(d['value']), 'fps (same step size)')" || true
+done
 echo "== 3. per-frame pipeline (config[2]) sharded over $N GPUs"
 timeout 300 $TR bench.py --gpus $N --workload dynamic --steps 4 --warmup 2 > gpurun_out/bench_n${N}_dynamic.json 2> gpurun_out/bench_n${N}_dynamic.err
 tail -c 700 gpurun_out/bench_n${N}_dynamic.json || tail -3 gpurun_out/bench_n${N}_dynamic.err
