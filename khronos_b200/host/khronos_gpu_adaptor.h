@@ -12,6 +12,8 @@
 //   GpuFreeSpaceMotionDetector khronos::FreeSpaceMotionDetector::processInput
 //                             (motion_detection/free_space_motion_detector.h:121; base motion_detector.h:62)
 //   GpuConnectedSemantics     khronos::ConnectedSemantics::processInput (object_detection/connected_semantics.h:100)
+//   GpuActiveWindowCore       the replaced steps of khronos::ActiveWindow::spinOnce / extractOutputData / finishMapping
+//                             (active_window.cpp:118-174, 176-189, 217-240) in one object
 //   reconstructStaticObject   the map set-up / integrate / erase steps of MeshObjectExtractor::extractStaticObject
 //                             (object_extraction/mesh_object_extractor.cpp:201-264)
 //   mirrorBack                repopulates a host hydra::VolumetricMap for MeshIntegrator::generateMesh /
@@ -315,6 +317,79 @@ inline std::unique_ptr<GpuVolumetricMap> reconstructStaticObject(
   return map;
 }
 
+// The steps of khronos::ActiveWindow::spinOnce / extractOutputData / finishMapping this build replaces, in one object a
+// GpuActiveWindow subclass delegates to. Reference order (active_window.cpp:118-174): motion
+// detection :127 -> object detection :130 -> tracker :134 (host, unchanged) -> updateMap :137 (= integrate with the
+// dynamic mask :209-210 + tracking update :214) -> ... -> every min_output_separation seconds extractOutputData :164
+// (generateMesh :223, cloneUpdated :229, resetInactive :235) and clearUpdated :169-171. Here motion detection,
+// integration and tracking are one kb_spin_once call (one device round trip); object detection neither reads nor writes
+// the map (connected_semantics.cpp:60 ignores it), so running it after that call changes nothing.
+class GpuActiveWindowCore {
+ public:
+  struct Config {
+    float min_output_separation = 0.f;            // s (ActiveWindow::Config, active_window.h:78-80)
+    bool detect_objects = false;
+    kb_object_detector_config object_detector{};
+  };
+
+  GpuActiveWindowCore(const Config& config, const hydra::VolumetricMap::Config& map, const kb_integrator_config& integ,
+                      const kb_tracking_config& tracking, const kb_motion_config& motion, int max_blocks, int device = 0)
+      : config_(config), map_(map, integ, &tracking, &motion, max_blocks, device), object_detector_(config.object_detector) {}
+
+  GpuVolumetricMap& map() { return map_; }
+
+  // Per-frame part of spinOnce. Fills data.dynamic_image (+ object_image / semantic_clusters when enabled; the dynamic
+  // cluster lists are fetched lazily by GpuFreeSpaceMotionDetector-style callers via kb_get_motion_clusters).
+  // Returns true when an output is due (:158-160), i.e. the caller should now call extractOutputData().
+  bool spinOnce(khronos::FrameData& data) {
+    latest_stamp_ = data.input.timestamp_ns;
+    kb_frame f = makeFrame(data.input, nullptr, nullptr, 0);
+    map_.setSensor(data.input.getSensor());
+    if (data.dynamic_image.empty()) data.dynamic_image = cv::Mat(data.input.depth_image.rows, data.input.depth_image.cols, 4);
+    int32_t n_seeds = 0, n_clusters = 0;
+    if (kb_spin_once(map_.handle(), &f, data.dynamic_image.ptr<int32_t>(), &n_seeds, &n_clusters) != KB_OK) {
+      std::fprintf(stderr, "[GpuActiveWindowCore] frame skipped: %s\n", kb_last_error(map_.handle()));
+      return false;
+    }
+    if (config_.detect_objects) object_detector_.processInput(map_, data);
+    ++num_frames_processed_;
+    const uint64_t sep = static_cast<uint64_t>(static_cast<double>(config_.min_output_separation) * 1e9);  // fromSeconds
+    return !(has_output_ && last_full_update_ + sep > latest_stamp_);
+  }
+
+  // extractOutputData (:217-240) + the clearUpdated loop of spinOnce (:169-171): the updated blocks are mirrored into
+  // the host map for MeshIntegrator::generateMesh / cloneUpdated, inactive blocks are removed and reported.
+  void extractOutputData(hydra::VolumetricMap& host_map, hydra::BlockIndices* archived) {
+#ifndef KB_HAVE_HYDRA
+    mirrorBackImpl(host_map);
+#else
+    (void)host_map;  // with real Hydra: khronos_b200::mirrorBack(map_, host_map, true) from the including translation unit
+#endif
+    GpuTrackingIntegrator().resetInactive(map_, archived);
+    if (archived)
+      for (const auto& b : *archived) host_map.removeBlock(b);
+    check(kb_clear_updated(map_.handle()), map_.handle(), "kb_clear_updated");
+    last_full_update_ = latest_stamp_;
+    has_output_ = true;
+  }
+
+  // finishMapping (:176-189): all blocks lose has_active_data, the next resetInactive archives everything.
+  void finishMapping() { check(kb_mark_all_inactive(map_.handle()), map_.handle(), "kb_mark_all_inactive"); }
+
+  size_t numFramesProcessed() const { return num_frames_processed_; }
+
+ private:
+#ifndef KB_HAVE_HYDRA
+  void mirrorBackImpl(hydra::VolumetricMap& host_map);
+#endif
+  Config config_;
+  GpuVolumetricMap map_;
+  GpuConnectedSemantics object_detector_;
+  uint64_t latest_stamp_ = 0, last_full_update_ = 0;
+  bool has_output_ = false;
+  size_t num_frames_processed_ = 0;
+};
+
 #ifndef KB_HAVE_HYDRA
 // Repopulates the host map from the device (updated blocks only at output ticks, everything for
 // parity dumps). With real Hydra the same loop writes through TsdfLayer::allocateBlock / getVoxel.
@@ -368,6 +443,7 @@ inline void mirrorBack(GpuVolumetricMap& gmap, hydra::VolumetricMap& host, bool 
     }
   }
 }
+inline void GpuActiveWindowCore::mirrorBackImpl(hydra::VolumetricMap& host_map) { mirrorBack(map_, host_map, /*updated_only=*/true); }
 #endif
 
 }  // namespace khronos_b200

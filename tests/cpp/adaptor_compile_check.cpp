@@ -41,6 +41,33 @@ int main(int argc, char** argv) {
     // object detector: the whole wall has label 3 -> one cluster when 3 is an object class
     kb_object_detector_config dc{};
     dc.use_full_connectivity = 1; dc.max_cluster_size = -1; dc.use_3d = 1; dc.grid_size = 0.1f; dc.is_object[3] = 1;
+    if (argc > 3) {  // third argument: drive GpuActiveWindowCore for a few frames (tests/test_zz_object_detection.py)
+      GpuActiveWindowCore::Config cc;
+      cc.min_output_separation = 0.25f;
+      cc.detect_objects = true;
+      cc.object_detector = dc;
+      GpuActiveWindowCore core(cc, mc, ic, tc, mo, 4096);
+      hydra::VolumetricMap out_map(mc);
+      int outputs = 0;
+      size_t archived_total = 0;
+      for (int k = 0; k < 8; ++k) {
+        khronos::FrameData fr = frame;
+        fr.dynamic_image = cv::Mat();
+        fr.object_image = cv::Mat();
+        fr.input.timestamp_ns = 1000000000ull + static_cast<uint64_t>(k) * 100000000ull;  // 10 Hz
+        if (core.spinOnce(fr)) {
+          hydra::BlockIndices archived;
+          core.extractOutputData(out_map, &archived);
+          archived_total += archived.size();
+          ++outputs;
+        }
+      }
+      core.finishMapping();
+      hydra::BlockIndices archived;
+      core.extractOutputData(out_map, &archived);
+      std::printf("core_frames=%zu core_outputs=%d core_blocks_after_finish=%zu core_archived=%zu ", core.numFramesProcessed(), outputs,
+                  out_map.getTsdfLayer().numBlocks(), archived_total + archived.size());
+    }
     GpuConnectedSemantics object_detector(dc);
     if (argc > 2) {  // second argument: also run the object detector (tests/test_zz_object_detection.py)
       object_detector.processInput(gmap, frame);

@@ -96,7 +96,11 @@ def test_adaptor_object_detector(tmp_path):
     exe = str(tmp_path / "adaptor_check")
     subprocess.check_call(["g++", "-std=c++17", "-O1", os.path.join(ROOT, "tests", "cpp", "adaptor_compile_check.cpp"),
                            "-o", exe, "-L", csrc, "-lkhronos_b200", f"-Wl,-rpath,{csrc}"])
-    out = subprocess.run([exe, "require-gpu", "objects"], capture_output=True, text=True)
+    out = subprocess.run([exe, "require-gpu", "objects", "core"], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     fields = dict(kv.split("=") for kv in out.stdout.split())
     assert int(fields["semantic_clusters"]) == 1 and int(fields["cluster_pixels"]) == 64 * 48
+    # GpuActiveWindowCore: 8 frames at 10 Hz with 0.25 s output separation -> outputs at frames 0, 3, 6; finishMapping archives
+    # every block (116 = the blocks of the known-answer frame) and empties the mirrored host map
+    assert (int(fields["core_frames"]), int(fields["core_outputs"])) == (8, 3)
+    assert int(fields["core_blocks_after_finish"]) == 0 and int(fields["core_archived"]) == int(fields["blocks"]) > 20
