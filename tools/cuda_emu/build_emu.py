@@ -24,7 +24,16 @@ def rewrite(src: str) -> str:
     return src
 
 
-def build(verbose=False):
+def build(verbose=False, asan=None):
+    """asan (default: environment KB_EMU_ASAN=1): AddressSanitizer build in _build_asan/ — every "device" allocation is a malloc,
+    so out-of-bounds kernel accesses are caught like compute-sanitizer memcheck would catch them. Run with
+    LD_PRELOAD=$(g++ -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0:detect_stack_use_after_return=0."""
+    global OUT, LIB
+    if asan is None:
+        asan = os.environ.get("KB_EMU_ASAN") == "1"
+    if asan:
+        OUT = os.path.join(HERE, "_build_asan")
+        LIB = os.path.join(OUT, "libkhronos_b200_emu.so")
     deps = [os.path.join(CSRC, n) for n in os.listdir(CSRC) if n.endswith((".cu", ".cuh", ".h", ".cpp"))]
     deps += [os.path.join(HERE, "emu_runtime.cpp"), os.path.join(HERE, "include", "cuda_runtime.h"), os.path.abspath(__file__),
              os.path.join(ROOT, "include", "khronos_b200.h")]
@@ -44,7 +53,10 @@ def build(verbose=False):
         open(out, "w").write(text)
         if out.endswith(".cpp"):
             srcs.append(out)
-    cmd = ["g++", "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-Wno-unknown-pragmas",
+    cmd = ["g++", "-O1" if asan else "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-Wno-unknown-pragmas"]
+    if asan:
+        cmd += ["-fsanitize=address", "-fno-omit-frame-pointer"]
+    cmd += [
            "-I", os.path.join(HERE, "include"), "-I", OUT, "-o", LIB, os.path.join(HERE, "emu_runtime.cpp")] + srcs
     if verbose:
         print(" ".join(cmd), file=sys.stderr)

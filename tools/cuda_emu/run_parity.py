@@ -4,6 +4,9 @@ product's own kernel sources (tools/cuda_emu/build_emu.py) instead of the real l
 checked against the oracle in a container without a GPU:
 
     python tools/cuda_emu/run_parity.py [pytest args / test files ...]
+    KB_EMU_ORDER=reverse|shuffle [KB_EMU_SEED=n] ...            other thread schedules (see emu_runtime.cpp)
+    KB_EMU_ASAN=1 LD_PRELOAD=$(g++ -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0:detect_stack_use_after_return=0 ...
+                                                                 AddressSanitizer build: a memcheck of every kernel access
 
 What this proves: the arithmetic, indexing, hashing, work distribution and synchronisation structure of the kernels
 give the oracle's results when executed with CUDA's thread / warp / block semantics (one fiber per CUDA thread).
