@@ -112,6 +112,8 @@ struct kb_handle {
   bool motion_stale = false;   // cluster lists of the last detection not yet built on the host
   MotionHostParams motion_hp{};
   bool motion_have_image = false;
+  bool motion_sparse = false;  // KB_MOTION_SPARSE experiment (kb_motion_device.cu)
+  bool mt_dirty = false;       // the shared table holds entries of another user (object detection / dense clustering)
   int3* d_removed = nullptr;
   int max_removed = 0;
   // semantic object detection (kb_detect_objects): inputs staged here, result image on the device + host copies
@@ -464,6 +466,7 @@ int kb_create(const kb_map_config* map, const kb_integrator_config* integ, const
     h->batch.items_per_block = m.V / 128;
     KB_CUDA(h, devAlloc(&h->item_fmask, S * h->batch.items_per_block, 0));
     if (const char* e = std::getenv("KB_FUSE_ITEM_LIST")) h->use_item_list = e[0] == '1';
+    if (const char* e = std::getenv("KB_MOTION_SPARSE")) h->motion_sparse = e[0] == '1';
     if (const char* e = std::getenv("KB_H2D_NARROW_LABELS")) h->narrow_labels = e[0] == '1';
     if (const char* e = std::getenv("KB_H2D_THREADS")) h->narrow_threads = std::max(1, std::atoi(e));
     if (const char* e = std::getenv("KB_PIPELINE")) h->pipelined = e[0] == '1';
@@ -1259,8 +1262,15 @@ static int enqueueMotionLookup(kb_handle* h, const kb_frame* f, uint8_t* shard_f
 static int enqueueDeviceClustering(kb_handle* h) {
   const size_t px = static_cast<size_t>(h->cam.width) * h->cam.height;
   const int D = static_cast<int>(std::ceil(h->mot.min_separation_distance));
-  launchMotionClustering(h->mt, h->d_pixel_gidx, h->d_pixel_seed, static_cast<int>(px), h->mot.neighbor_connectivity, D,
-                         h->mot.min_cluster_size, h->mot.max_cluster_size, h->d_dynamic, h->stream);
+  if (h->motion_sparse) {
+    launchMotionClusteringSparse(h->mt, h->d_pixel_gidx, h->d_pixel_seed, static_cast<int>(px), h->mot.neighbor_connectivity, D,
+                                 h->mot.min_cluster_size, h->mot.max_cluster_size, h->d_dynamic, h->mt_dirty, h->stream);
+    h->mt_dirty = false;
+  } else {
+    launchMotionClustering(h->mt, h->d_pixel_gidx, h->d_pixel_seed, static_cast<int>(px), h->mot.neighbor_connectivity, D,
+                           h->mot.min_cluster_size, h->mot.max_cluster_size, h->d_dynamic, h->stream);
+    h->mt_dirty = true;  // the dense path leaves its entries in the table
+  }
   KB_CUDA(h, cudaGetLastError());
   KB_CUDA(h, cudaMemcpyAsync(h->h_mscal, h->mt.scalars, sizeof(int) * kMsCount, cudaMemcpyDeviceToHost, h->stream));
   return KB_OK;
@@ -1403,6 +1413,7 @@ int kb_detect_objects(kb_handle* h, const kb_object_detector_config* cfg, const 
   if (cfg->use_3d && (st = stage(h, f->vertex_world, h->stg_vertex, px * 3, f->memory, &p.vertex)) != KB_OK) return st;
   if (cfg->use_3d) launchObjectClustering3D(h->mt, p, h->stream);
   else launchObjectClustering2D(h->mt, p, h->stream);
+  h->mt_dirty = true;  // shared table memory
   KB_CUDA(h, cudaGetLastError());
   KB_CUDA(h, cudaMemcpyAsync(h->h_oscal, h->mt.scalars, sizeof(int) * kMsCount, cudaMemcpyDeviceToHost, h->stream));
   KB_CUDA(h, cudaMemcpyAsync(object_image_out, h->d_object, sizeof(int32_t) * px, cudaMemcpyDeviceToHost, h->stream));

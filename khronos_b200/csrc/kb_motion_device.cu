@@ -220,7 +220,75 @@ __global__ void vtInitKernel(MotionTable t) {
   t.cluster_id[slot] = 0;
 }
 
+// ---- sparse variants (KB_MOTION_SPARSE=1): the table is kept clean between frames by resetting only the slots the frame
+// occupied (vtCleanupKernel), so neither the init nor the reduction has to walk all 2^20 slots (~8 us each at 640x480).
+// Unconditional full reset (vtInitKernel skips the table when the frame has no seeds, which would leave another user's
+// entries behind for the first frame that has some).
+__global__ void vtInitFullKernel(MotionTable t) {
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot < kMsCount) t.scalars[slot] = 0;
+  if (slot > static_cast<int>(t.mask)) return;
+  t.keys[slot] = kVtEmpty;
+  t.count[slot] = 0;
+  t.flags[slot] = 0;
+  t.deg[slot] = 0;
+  t.pix_total[slot] = 0;
+  t.min_seed[slot] = ~0ull;
+  t.cluster_id[slot] = 0;
+}
+
+__global__ void vtInitSparseKernel(MotionTable t) {
+  if (threadIdx.x < kMsCount) t.scalars[threadIdx.x] = 0;
+}
+
+__global__ void vtReduceSparseKernel(MotionTable t) {
+  if (*t.gate == 0) return;
+  const int n = t.scalars[kMsOccupied];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int slot = t.occupied[i];
+    if (t.deg[slot] == 0) continue;
+    const unsigned long long key = t.keys[slot];
+    const int root = ufFind(t.parent, slot);
+    const bool is_seed = t.flags[slot] & kMvSeed;
+    atomicAdd(&t.pix_total[root], static_cast<unsigned long long>(t.count[slot]) * static_cast<unsigned long long>(is_seed ? 1 : t.deg[slot]));
+    if (is_seed) atomicMin(&t.min_seed[root], key);
+    if (root == slot) {
+      const int r = atomicAdd(&t.scalars[kMsRoots], 1);
+      if (r < t.max_roots) t.roots[r] = slot;
+    }
+  }
+}
+
+__global__ void vtCleanupKernel(MotionTable t) {
+  if (*t.gate == 0) return;
+  const int n = t.scalars[kMsOccupied];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int slot = t.occupied[i];
+    t.keys[slot] = kVtEmpty;
+    t.count[slot] = 0;
+    t.flags[slot] = 0;
+    t.deg[slot] = 0;
+    t.pix_total[slot] = 0;
+    t.min_seed[slot] = ~0ull;
+    t.cluster_id[slot] = 0;
+  }
+}
+
 }  // namespace
+
+void launchMotionClusteringSparse(const MotionTable& t, const int3* gidx, const uint8_t* seed, int P, int conn, int D,
+                                  int min_size, int max_size, int32_t* image, bool table_dirty, cudaStream_t s) {
+  const int cap = static_cast<int>(t.mask) + 1;
+  if (table_dirty) vtInitFullKernel<<<(cap + 255) / 256, 256, 0, s>>>(t);  // someone else used the table: full reset once
+  else vtInitSparseKernel<<<1, 32, 0, s>>>(t);
+  vtInsertKernel<<<(P + 255) / 256, 256, 0, s>>>(t, gidx, seed, P);
+  vtLinkKernel<<<148 * 4, 256, 0, s>>>(t, conn);
+  if (D > 1) vtMergeNearKernel<<<148 * 4, 256, 0, s>>>(t, D);
+  vtReduceSparseKernel<<<148, 256, 0, s>>>(t);
+  vtRankKernel<<<1, 1024, 0, s>>>(t, min_size, max_size);
+  vtWriteImageKernel<<<(P + 255) / 256, 256, 0, s>>>(t, image, P);
+  vtCleanupKernel<<<148, 256, 0, s>>>(t);
+}
 
 void launchMotionClustering(const MotionTable& t, const int3* gidx, const uint8_t* seed, int P, int conn, int D,
                             int min_size, int max_size, int32_t* image, cudaStream_t s) {

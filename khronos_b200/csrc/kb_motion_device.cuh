@@ -33,4 +33,9 @@ struct MotionTable {
 void launchMotionClustering(const MotionTable& t, const int3* gidx, const uint8_t* seed, int P, int conn, int D,
                             int min_size, int max_size, int32_t* image, cudaStream_t s);
 
+// KB_MOTION_SPARSE experiment: same result; the table is reset slot by slot after use instead of wholesale before use
+// (table_dirty: another user — the object detector — left entries behind, do one full reset).
+void launchMotionClusteringSparse(const MotionTable& t, const int3* gidx, const uint8_t* seed, int P, int conn, int D,
+                                  int min_size, int max_size, int32_t* image, bool table_dirty, cudaStream_t s);
+
 }  // namespace kb

@@ -137,3 +137,36 @@ def test_narrowed_labels_fall_back_for_out_of_range_ids(oracle_lib, product_lib)
         hs.assert_blocks_equal(o.export_blocks(), g.export_blocks(), exact_float=True, what="narrowed labels")
     finally:
         os.environ.pop("KB_H2D_NARROW_LABELS", None)
+
+
+def test_motion_sparse_table_variant(oracle_lib, product_lib):
+    """KB_MOTION_SPARSE=1: the clustering table is reset slot by slot after each frame instead of wholesale before it; the
+    object detector (shared table memory) is interleaved on some frames to exercise the dirty -> full reset transition,
+    including frames without seeds right after it."""
+    os.environ["KB_MOTION_SPARSE"] = "1"
+    try:
+        import test_sharded_pipeline as tsp
+        from test_object_detection_oracle import OBJECTS
+        cam = hs.small_camera(4)
+        frames, poses, stamps = tsp.dynamic_scenario(cam, 28)
+        mot = capi.default_motion_config(min_cluster_size=5, min_separation_distance=2.0)
+        o = hs.make_handle(oracle_lib, "ko_", cam=cam, mot_cfg=mot)
+        g = hs.make_handle(product_lib, "kb_", cam=cam, mot_cfg=mot)
+        cfg = capi.default_object_detector_config(OBJECTS, use_3d=True, min_cluster_size=10)
+        dyn = 0
+        for i, ((d, l), T, st) in enumerate(zip(frames, poses, stamps)):
+            if i % 5 in (0, 1):  # object detection before the motion stage: leaves its entries in the shared table
+                io_, no_ = o.detect_objects(cfg, o.make_frame(d, T, st, label=l))
+                ig_, ng_ = g.detect_objects(cfg, g.make_frame(d, T, st, label=l))
+                assert no_ == ng_
+                np.testing.assert_array_equal(io_, ig_)
+            io, so, co = o.spin_once(o.make_frame(d, T, st, label=l))
+            ig, sg, cg = g.spin_once(g.make_frame(d, T, st, label=l))
+            assert (so, co) == (sg, cg), f"frame {i}"
+            np.testing.assert_array_equal(io, ig, err_msg=f"frame {i}")
+            assert len(o.get_motion_clusters()) == len(g.get_motion_clusters())
+            dyn += int((io > 0).sum())
+        assert dyn > 100
+        hs.assert_blocks_equal(o.export_blocks(), g.export_blocks(), exact_float=True, what="motion sparse")
+    finally:
+        os.environ.pop("KB_MOTION_SPARSE", None)
