@@ -375,6 +375,9 @@ def main_dynamic_sharded(args):
     h = kb.create_map(mc, ic, capi.default_tracking_config(), mot, device=local_rank)
     h.set_camera(cam)
     h.set_shard(rank, world)
+    # exchange buffers are shipped whole (no host round trip to learn the fill): size them for this workload — ~300 pending
+    # blocks per frame over all ranks, so <= 512 pending / 1024 published blocks per rank is > 2x headroom even at N = 2
+    h.set_shard_capacity(512, 1024)
     if args.exchange == "peers":
         win = kd.PeerShardedActiveWindow([h], kd.SymmMemPeers(device=dev), device=dev)
     else:
@@ -409,6 +412,8 @@ def main_dynamic_sharded(args):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dt = float(t.item())
     tot = h.get_totals()
+    if tot.capacity_exceeded:
+        raise SystemExit("bench.py: a shard exchange buffer / block pool overflowed (capacity_exceeded): results incomplete")
     blocks = torch.tensor([float(tot.total_blocks)], device=dev, dtype=torch.float64)
     dist.all_reduce(blocks)
     if rank == 0:
