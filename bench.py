@@ -375,9 +375,9 @@ def main_dynamic_sharded(args):
     h = kb.create_map(mc, ic, capi.default_tracking_config(), mot, device=local_rank)
     h.set_camera(cam)
     h.set_shard(rank, world)
-    # exchange buffers are shipped whole (no host round trip to learn the fill): size them for this workload — ~300 pending
-    # blocks per frame over all ranks, so <= 512 pending / 1024 published blocks per rank is > 2x headroom even at N = 2
-    h.set_shard_capacity(512, 1024)
+    # exchange buffers are shipped whole (no host round trip to learn the fill): size them for this workload. Counted on the
+    # emulated build at 640x480: ~172 pending blocks per frame over all ranks; published halo blocks per rank 147 (N = 2) / 42 (N = 8)
+    h.set_shard_capacity(256, 512)
     if args.exchange == "peers":
         win = kd.PeerShardedActiveWindow([h], kd.SymmMemPeers(device=dev), device=dev)
     else:
