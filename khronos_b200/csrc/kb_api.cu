@@ -94,6 +94,8 @@ struct kb_handle {
   bool cull_forced = false;  // kb_set_culling(2): cull even single frames (tests)
   int fuse_grid = 0;
   bool hwm_dirty = true;
+  size_t tombstones_ub = 0;      // upper bound on the tombstones in the block hash (removed blocks since the last rebuild)
+  size_t rehash_threshold = 0;   // rebuild the hash when the bound exceeds this (default: a quarter of the table)
   int hwm_cached = 0;
   // counters
   int* h_ctr = nullptr;  // pinned mirror
@@ -466,6 +468,8 @@ int kb_create(const kb_map_config* map, const kb_integrator_config* integ, const
     h->batch.items_per_block = m.V / 128;
     KB_CUDA(h, devAlloc(&h->item_fmask, S * h->batch.items_per_block, 0));
     if (const char* e = std::getenv("KB_FUSE_ITEM_LIST")) h->use_item_list = e[0] == '1';
+    h->rehash_threshold = (static_cast<size_t>(cap)) / 4;
+    if (const char* e = std::getenv("KB_REHASH_TOMBSTONES")) h->rehash_threshold = static_cast<size_t>(std::max(1, std::atoi(e)));  // tests
     if (const char* e = std::getenv("KB_MOTION_SPARSE")) h->motion_sparse = e[0] == '1';
     if (const char* e = std::getenv("KB_H2D_NARROW_LABELS")) h->narrow_labels = e[0] == '1';
     if (const char* e = std::getenv("KB_H2D_THREADS")) h->narrow_threads = std::max(1, std::atoi(e));
@@ -1140,6 +1144,13 @@ int kb_reset_inactive(kb_handle* h, int32_t* removed_xyz, int32_t max_removed, i
     return a.x != b.x ? a.x < b.x : (a.y != b.y ? a.y < b.y : a.z < b.z);
   });
   h->hwm_dirty = true;
+  // every removal leaves a tombstone; rebuild the table before they crowd out its empty entries
+  h->tombstones_ub += static_cast<size_t>(std::max(h->h_ctr[kCtrRemoved], 0));
+  if (h->tombstones_ub >= h->rehash_threshold) {
+    launchRehash(h->dm, nslots, h->stream);
+    KB_CUDA(h, cudaGetLastError());
+    h->tombstones_ub = 0;
+  }
   if (n_removed) *n_removed = static_cast<int32_t>(host.size());
   if (removed_xyz)
     for (int i = 0; i < std::min<int>(max_removed, host.size()); ++i) {

@@ -85,6 +85,7 @@ enum Counter {
   kCtrItemsB0 = 25,  //   run while the fuse kernel of batch i is still fetching
   kCtrItemsB1 = 26,
   kCtrItemsB2 = 27,
+  kCtrRehash = 28,   // number of hash-table rebuilds (tombstone garbage collection, kb_reset_inactive)
   kNumCounters = 32
 };
 

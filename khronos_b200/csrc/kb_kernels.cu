@@ -1345,6 +1345,23 @@ __global__ void __launch_bounds__(kThreads) resetInactiveKernel(const DeviceMap 
   }
 }
 
+// Tombstone garbage collection: the table was cleared; every live slot re-inserts its key (keys are unique).
+__global__ void rehashKernel(const DeviceMap m, int n) {
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot == 0) atomicAdd(&m.counters[kCtrRehash], 1);
+  if (slot >= n || !(m.block_flags[slot] & kFlagAllocated)) return;
+  const int3 bi = m.block_index[slot];
+  const unsigned long long key = packKey(bi.x, bi.y, bi.z);
+  uint32_t h = static_cast<uint32_t>(mix64(key)) & m.hash_mask;
+  for (uint32_t probe = 0; probe <= m.hash_mask; ++probe) {
+    if (atomicCAS(&m.hash_keys[h], kEmptyKey, key) == kEmptyKey) {
+      m.hash_vals[h] = slot;
+      return;
+    }
+    h = (h + 1) & m.hash_mask;
+  }
+}
+
 __global__ void markAllInactiveKernel(const DeviceMap m, int n) {
   const int slot = blockIdx.x * blockDim.x + threadIdx.x;
   if (slot < n && (m.block_flags[slot] & kFlagAllocated)) m.block_flags[slot] |= kFlagInactiveOverride;
@@ -1660,6 +1677,10 @@ void launchTrackingFinish(const DeviceMap& m, const TrackingParams& p, const Sha
 }
 void launchResetInactive(const DeviceMap& m, const TrackEval& ev, int n, int3* removed, int max_removed, cudaStream_t s) {
   if (n > 0) resetInactiveKernel<<<n, kThreads, 0, s>>>(m, ev, removed, max_removed);
+}
+void launchRehash(const DeviceMap& m, int n, cudaStream_t s) {
+  cudaMemsetAsync(m.hash_keys, 0xFF, (static_cast<size_t>(m.hash_mask) + 1) * sizeof(unsigned long long), s);
+  rehashKernel<<<(std::max(n, 1) + 255) / 256, 256, 0, s>>>(m, n);
 }
 void launchMarkAllInactive(const DeviceMap& m, int n, cudaStream_t s) {
   if (n > 0) markAllInactiveKernel<<<(n + 255) / 256, 256, 0, s>>>(m, n);

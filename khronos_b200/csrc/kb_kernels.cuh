@@ -132,6 +132,10 @@ void launchFuse(const DeviceMap& m, const BatchParams& p, int grid, cudaStream_t
 int fuseBlocksPerSm(int vps, int Lp);  // resident 128-thread CTAs per SM (occupancy API)
 void launchTrackingPass(const DeviceMap& m, const TrackingParams& p, int everfree_grid, cudaStream_t s);
 void launchResetInactive(const DeviceMap& m, const TrackEval& ev, int n_slots, int3* removed, int max_removed, cudaStream_t s);
+// Rebuilds the block hash from the live slots (drops the tombstones block removal leaves behind; without this the empty
+// entries of an open-addressed table only ever get fewer, and failed lookups — M1, K3 neighbours — degrade to full scans
+// on long runs with block turnover).
+void launchRehash(const DeviceMap& m, int n_slots, cudaStream_t s);
 void launchMarkAllInactive(const DeviceMap& m, int n_slots, cudaStream_t s);
 void launchClearUpdated(const DeviceMap& m, int n_slots, cudaStream_t s);
 void launchMotionLookup(const DeviceMap& m, const MotionParams& p, cudaStream_t s);

@@ -149,3 +149,33 @@ def test_f32_depth_with_u8_labels_in_one_frame(oracle_lib, product_lib):
                        want_stats=False)
     g.synchronize()
     hs.assert_blocks_equal(o.export_blocks(), g.export_blocks(), exact_float=True, what="f32 depth + u8 labels")
+
+
+def test_hash_rebuild_after_block_removal(oracle_lib, product_lib):
+    """Tombstone garbage collection: with KB_REHASH_TOMBSTONES=1 every kb_reset_inactive that removes a block rebuilds
+    the block hash from the live slots; lookups, re-allocation and every result must be unaffected."""
+    import os
+    os.environ["KB_REHASH_TOMBSTONES"] = "1"
+    try:
+        cam = hs.small_camera(4)
+        frames, poses, stamps = room_frames(cam, 14, laps=0.5, dt_ns=500_000_000)
+        frames, poses = frames + frames[:6], poses + poses[:6]   # come back: removed blocks are allocated again
+        stamps = stamps + [stamps[-1] + (k + 1) * 500_000_000 for k in range(6)]
+        mot = capi.default_motion_config(min_cluster_size=5, min_separation_distance=2.0, num_threads=4)
+        o, g = both(oracle_lib, product_lib, cam=cam, mot_cfg=mot)
+        removed = 0
+        for i, ((d, l), T, st) in enumerate(zip(frames, poses, stamps)):
+            io, so, co = o.spin_once(o.make_frame(d, T, st, label=l))
+            ig, sg, cg = g.spin_once(g.make_frame(d, T, st, label=l))
+            assert (so, co) == (sg, cg)
+            np.testing.assert_array_equal(io, ig)
+            if i % 3 == 2:
+                ro, rg = o.reset_inactive(), g.reset_inactive()
+                np.testing.assert_array_equal(ro, rg)
+                removed += len(ro)
+                hs.assert_blocks_equal(o.export_blocks(), g.export_blocks(), exact_float=True, what=f"after reset {i}")
+        assert removed > 0
+        assert int(g.get_debug_counters(32)[28]) >= 1, "the hash must have been rebuilt"
+        hs.assert_blocks_equal(o.export_blocks(), g.export_blocks(), exact_float=True, what="hash rebuild")
+    finally:
+        os.environ.pop("KB_REHASH_TOMBSTONES", None)
