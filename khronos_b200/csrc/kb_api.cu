@@ -663,6 +663,27 @@ static int integrateBatch(kb_handle* h, const kb_frame* frames, int n, int alloc
   const kb_camera& c = h->cam;
   const size_t px = static_cast<size_t>(c.width) * c.height;
   BatchParams& p = h->batch;  // persistent: camera / integrator fields are filled by kb_set_camera
+  if (allocate_blocks && n > 1) {
+    // K0 enumerates the union AABB of the batch's frusta, which assumes the frames are neighbours in space. Frames far
+    // apart (a jump in the stream, an extractor batch spanning a long track) would blow that box up: split such batches
+    // (results do not depend on how a frame sequence is cut into batches).
+    const double reach = static_cast<double>(c.max_range) + static_cast<double>(h->block_size) * 0.8660254;
+    const double inv = 1.0 / static_cast<double>(h->block_size);
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int b = 0; b < n; ++b)
+      for (int a = 0; a < 3; ++a) {
+        const double t = frames[b].world_T_sensor[a * 4 + 3];
+        lo[a] = std::min(lo[a], std::floor((t - reach) * inv));
+        hi[a] = std::max(hi[a], std::floor((t + reach) * inv));
+      }
+    const double single = std::pow(2.0 * reach * inv + 2.0, 3.0);
+    const double cells = (hi[0] - lo[0] + 1.0) * (hi[1] - lo[1] + 1.0) * (hi[2] - lo[2] + 1.0);
+    if (!(cells <= 8.0 * single)) {  // also catches NaN poses: they end up alone and fail the frustum test
+      int st = integrateBatch(h, frames, n / 2, allocate_blocks);
+      if (st != KB_OK) return st;
+      return integrateBatch(h, frames + n / 2, n - n / 2, allocate_blocks);
+    }
+  }
   p.n_frames = n;
   p.allocate = allocate_blocks ? 1 : 0;
   p.rank = h->rank;

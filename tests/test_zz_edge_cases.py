@@ -179,3 +179,24 @@ def test_hash_rebuild_after_block_removal(oracle_lib, product_lib):
         hs.assert_blocks_equal(o.export_blocks(), g.export_blocks(), exact_float=True, what="hash rebuild")
     finally:
         os.environ.pop("KB_REHASH_TOMBSTONES", None)
+
+
+def test_batch_with_frames_far_apart_is_split(oracle_lib, product_lib):
+    """A batch call whose frames jump hundreds of metres (the union candidate box of K0 would have ~10^8 cells) is cut
+    into spatially coherent sub-batches; results equal frame-by-frame integration."""
+    cam = hs.small_camera(4)
+    frames, poses, stamps = room_frames(cam, 12, laps=0.2)
+    far = []
+    for i, T in enumerate(poses):
+        T = np.array(T, dtype=np.float64)
+        if i % 4 >= 2:
+            T[:3, 3] += np.array([300.0 * (i % 3 + 1), -450.0, 20.0])   # outside the room: only allocation happens there
+        far.append(T)
+    o, g = both(oracle_lib, product_lib, cam=cam)
+    g.set_culling(2)
+    so = hs.run_fusion(o, frames, far, stamps)
+    s = g.integrate_frames([g.make_frame(d, T, st, label=l) for (d, l), T, st in zip(frames, far, stamps)]).as_dict()
+    want = {k: sum(x[k] for x in so) for k in s}
+    want["total_blocks"] = so[-1]["total_blocks"]
+    assert s == want
+    hs.assert_blocks_equal(o.export_blocks(), g.export_blocks(), exact_float=True, what="far-apart batch")
