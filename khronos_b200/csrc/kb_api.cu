@@ -925,8 +925,11 @@ int kb_integrate_frames(kb_handle* h, const kb_frame* frames, int32_t n_frames, 
                         kb_frame_stats* stats) {
   if (!h || !frames || n_frames < 0) return fail(h, KB_ERR_INVALID, "null frames");
   if (!h->has_cam) return fail(h, KB_ERR_STATE, "kb_set_camera must be called first");
-  for (int i = 0; i < n_frames; ++i)
+  for (int i = 0; i < n_frames; ++i) {
     if (!frames[i].depth && !frames[i].depth_u16) return fail(h, KB_ERR_INVALID, "frame without depth image");
+    for (int k = 0; k < 16; ++k)
+      if (!std::isfinite(frames[i].world_T_sensor[k])) return fail(h, KB_ERR_INVALID, "non-finite sensor pose");
+  }
   KB_CUDA(h, cudaSetDevice(h->device));
   int st;
   if (stats && h->ctr_dirty) {

@@ -200,3 +200,17 @@ def test_batch_with_frames_far_apart_is_split(oracle_lib, product_lib):
     want["total_blocks"] = so[-1]["total_blocks"]
     assert s == want
     hs.assert_blocks_equal(o.export_blocks(), g.export_blocks(), exact_float=True, what="far-apart batch")
+
+
+def test_non_finite_pose_is_rejected(product_lib):
+    import khronos_b200 as kb
+    cam = hs.small_camera(4)
+    frames, poses, stamps = room_frames(cam, 2)
+    g = hs.make_handle(product_lib, "kb_", cam=cam)
+    T = np.array(poses[0], dtype=np.float64)
+    T[0, 3] = np.nan
+    with pytest.raises(kb.KbError) as e:
+        g.integrate_frame(g.make_frame(frames[0][0], T, stamps[0], label=frames[0][1]))
+    assert e.value.status == 1
+    g.integrate_frame(g.make_frame(frames[1][0], poses[1], stamps[1], label=frames[1][1]))  # the handle stays usable
+    assert g.num_blocks() > 0
