@@ -1212,6 +1212,8 @@ int kb_allocate_box(kb_handle* h, const int32_t mn[3], const int32_t mx[3]) {
   const int3 lo = make_int3(mn[0], mn[1], mn[2]);
   const int3 dims = make_int3(mx[0] - mn[0] + 1, mx[1] - mn[1] + 1, mx[2] - mn[2] + 1);
   if (dims.x <= 0 || dims.y <= 0 || dims.z <= 0) return KB_OK;
+  if (static_cast<double>(dims.x) * dims.y * dims.z > static_cast<double>(h->dm.max_blocks) * (h->nranks > 1 ? 2.0 * h->nranks : 1.0))
+    return fail(h, KB_ERR_CAPACITY, "kb_allocate_box: the box holds more blocks than the pool");
   // blocks allocated now are seen by tracking passes with a frame index >= born
   const uint32_t last_idx = static_cast<uint32_t>(h->stamps.size() - 1);
   const uint32_t born = std::max(last_idx, h->pass.k_last + 1);
