@@ -114,6 +114,7 @@ struct kb_handle {
   bool motion_stale = false;   // cluster lists of the last detection not yet built on the host
   MotionHostParams motion_hp{};
   bool motion_have_image = false;
+  bool everfree_v2 = false;    // KB_EVERFREE_V2 experiment (vectorised halo fill)
   bool motion_sparse = false;  // KB_MOTION_SPARSE experiment (kb_motion_device.cu)
   bool mt_dirty = false;       // the shared table holds entries of another user (object detection / dense clustering)
   int3* d_removed = nullptr;
@@ -470,6 +471,7 @@ int kb_create(const kb_map_config* map, const kb_integrator_config* integ, const
     if (const char* e = std::getenv("KB_FUSE_ITEM_LIST")) h->use_item_list = e[0] == '1';
     h->rehash_threshold = (static_cast<size_t>(cap)) / 4;
     if (const char* e = std::getenv("KB_REHASH_TOMBSTONES")) h->rehash_threshold = static_cast<size_t>(std::max(1, std::atoi(e)));  // tests
+    if (const char* e = std::getenv("KB_EVERFREE_V2")) h->everfree_v2 = e[0] == '1';
     if (const char* e = std::getenv("KB_MOTION_SPARSE")) h->motion_sparse = e[0] == '1';
     if (const char* e = std::getenv("KB_H2D_NARROW_LABELS")) h->narrow_labels = e[0] == '1';
     if (const char* e = std::getenv("KB_H2D_THREADS")) h->narrow_threads = std::max(1, std::atoi(e));
@@ -1016,6 +1018,7 @@ static int trackingParams(kb_handle* h, uint64_t stamp_ns, TrackingParams* out) 
   p.pending = h->pending;
   p.rank = h->rank;
   p.nranks = h->nranks;
+  p.everfree_v2 = h->everfree_v2 ? 1 : 0;
   *out = p;
   return KB_OK;
 }

@@ -1113,6 +1113,93 @@ __global__ void __launch_bounds__(kThreads) everFreeKernel(const DeviceMap m, co
   }
 }
 
+// KB_EVERFREE_V2 (experiment, same results): the halo fill of everFreeKernel walks all (vps+2)^3 cells with one scalar byte
+// load each (23 dependent iterations per thread at vps 16). Here the block's own vps^3 flag bytes arrive as 16-byte vector
+// loads (one per thread at vps 16) and only the one-voxel shell taken from the 26 neighbour blocks (1736 of 5832 cells) is
+// gathered cell by cell.
+template <bool SHARD>
+__global__ void __launch_bounds__(kThreads) everFreeKernelV2(const DeviceMap m, const TrackingParams p) {
+  __shared__ int s_nbr[27];
+  __shared__ uint8_t s_free[18 * 18 * 18];
+  const int n = m.counters[kCtrPending];
+  const int vps = m.vps, V = m.V, hs = vps + 2;
+  const int planeA = hs * hs, planeB = vps * hs, planeC = vps * vps, n_shell = 2 * (planeA + planeB + planeC);
+  for (int w = blockIdx.x; w < n; w += gridDim.x) {
+    const int slot = p.pending[w];
+    __syncthreads();
+    if (threadIdx.x < 27) {
+      const int3 bi = m.block_index[slot];
+      const int dx = threadIdx.x % 3 - 1, dy = (threadIdx.x / 3) % 3 - 1, dz = threadIdx.x / 9 - 1;
+      int ns = (dx == 0 && dy == 0 && dz == 0) ? slot : hashLookup(m, bi.x + dx, bi.y + dy, bi.z + dz);
+      if (SHARD && ns < 0 && blockOwner(bi.x + dx, bi.y + dy, bi.z + dz, p.nranks) != p.rank) {
+        const int off = ghostLookup(p, bi.x + dx, bi.y + dy, bi.z + dz);
+        if (off >= 0) ns = -(2 + off);
+      }
+      s_nbr[threadIdx.x] = ns;
+    }
+    const size_t base = static_cast<size_t>(slot) * V;
+    // centre block: 16 flag bytes per vector load (does not need s_nbr)
+    for (int q = threadIdx.x; q < V / 16; q += kThreads) {
+      const uint4 f16 = *reinterpret_cast<const uint4*>(m.vflags + base + static_cast<size_t>(q) * 16);
+      const uint32_t wds[4] = {f16.x, f16.y, f16.z, f16.w};
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const uint8_t f = static_cast<uint8_t>((wds[k >> 2] >> (8 * (k & 3))) & 0xFFu);
+        const int lin = q * 16 + k;
+        const int vx = lin % vps, vy = (lin / vps) % vps, vz = lin / (vps * vps);
+        s_free[(vx + 1) + hs * ((vy + 1) + hs * (vz + 1))] =
+            static_cast<uint8_t>((voxelFreeNow(m, p.ev, base + lin, f) ? 1 : 0) | ((f & kVoxEverFree) ? 2 : 0));
+      }
+    }
+    __syncthreads();  // s_nbr complete
+    // one-voxel shell from the neighbour blocks: two z planes, two y slabs, two x slabs
+    for (int j = threadIdx.x; j < n_shell; j += kThreads) {
+      int x, y, z;
+      if (j < 2 * planeA) {
+        const int r = j % planeA;
+        x = r % hs - 1; y = r / hs - 1; z = (j / planeA) ? vps : -1;
+      } else if (j < 2 * (planeA + planeB)) {
+        const int jj = j - 2 * planeA, r = jj % planeB;
+        x = r % hs - 1; z = r / hs; y = (jj / planeB) ? vps : -1;
+      } else {
+        const int jj = j - 2 * (planeA + planeB), r = jj % planeC;
+        y = r % vps; z = r / vps; x = (jj / planeC) ? vps : -1;
+      }
+      const int cell = (x + 1) + hs * ((y + 1) + hs * (z + 1));
+      int bx = 1, by = 1, bz = 1;
+      if (x < 0) { x += vps; bx = 0; } else if (x >= vps) { x -= vps; bx = 2; }
+      if (y < 0) { y += vps; by = 0; } else if (y >= vps) { y -= vps; by = 2; }
+      if (z < 0) { z += vps; bz = 0; } else if (z >= vps) { z -= vps; bz = 2; }
+      const int ns = s_nbr[bx + 3 * by + 9 * bz];
+      uint8_t v = 0;  // missing neighbour block: blocks its neighbours (:198-202)
+      if (ns >= 0) {
+        const size_t idx = static_cast<size_t>(ns) * V + (x + vps * (y + vps * z));
+        const uint8_t f = m.vflags[idx];
+        v = (voxelFreeNow(m, p.ev, idx, f) ? 1 : 0) | ((f & kVoxEverFree) ? 2 : 0);
+      } else if (SHARD && ns <= -2) {
+        const int lin = x + vps * (y + vps * z);
+        v = (static_cast<uint32_t>(__ldg(&p.ghost_bits[(-ns - 2) + (lin >> 5)])) >> (lin & 31)) & 1u;
+      }
+      s_free[cell] = v;
+    }
+    __syncthreads();
+    for (int lin = threadIdx.x; lin < V; lin += kThreads) {
+      const int vx = lin % vps, vy = (lin / vps) % vps, vz = lin / (vps * vps);
+      const int c = (vx + 1) + hs * ((vy + 1) + hs * (vz + 1));
+      if (s_free[c] != 1) continue;
+      bool blocked = false;
+      for (int dz = -1; dz <= 1 && !blocked; ++dz)
+        for (int dy = -1; dy <= 1 && !blocked; ++dy)
+          for (int dx = -1; dx <= 1; ++dx) {
+            const int nnz = (dx != 0) + (dy != 0) + (dz != 0);
+            if (nnz == 0 || (p.connectivity == 6 && nnz > 1) || (p.connectivity == 18 && nnz > 2)) continue;
+            if (!(s_free[c + dx + hs * (dy + hs * dz)] & 1)) { blocked = true; break; }
+          }
+      if (!blocked) m.vflags[base + lin] |= kVoxEverFree;
+    }
+  }
+}
+
 // Resets the ever-free work counter after K3 (separate tiny launch: K3's CTAs all read it).
 __global__ void resetPendingKernel(const DeviceMap m) { m.counters[kCtrPending] = 0; }
 
@@ -1633,7 +1720,8 @@ void launchFuse(const DeviceMap& m, const BatchParams& p, int grid, cudaStream_t
 }
 void launchTrackingPass(const DeviceMap& m, const TrackingParams& p, int everfree_grid, cudaStream_t s) {
   trackingPassKernel<<<(std::max(p.n_slots, 1) + 255) / 256, 256, 0, s>>>(m, p);
-  everFreeKernel<false><<<everfree_grid, kThreads, 0, s>>>(m, p);
+  if (p.everfree_v2) everFreeKernelV2<false><<<everfree_grid, kThreads, 0, s>>>(m, p);
+  else everFreeKernel<false><<<everfree_grid, kThreads, 0, s>>>(m, p);
   resetPendingKernel<<<1, 1, 0, s>>>(m);
 }
 void launchTrackingBegin(const DeviceMap& m, const TrackingParams& p, const ShardExchange& x, int32_t* pending_out, cudaStream_t s) {
@@ -1672,7 +1760,8 @@ void launchTrackingFinish(const DeviceMap& m, const TrackingParams& p, const Sha
   cudaMemsetAsync(x.ghost_keys, 0xFF, (static_cast<size_t>(x.ghost_mask) + 1) * sizeof(unsigned long long), s);
   const int n = x.nranks * x.cap_halo;
   ghostBuildKernel<<<(n + 255) / 256, 256, 0, s>>>(m, x, all_pending, all_halo);
-  everFreeKernel<true><<<everfree_grid, kThreads, 0, s>>>(m, p);
+  if (p.everfree_v2) everFreeKernelV2<true><<<everfree_grid, kThreads, 0, s>>>(m, p);
+  else everFreeKernel<true><<<everfree_grid, kThreads, 0, s>>>(m, p);
   resetPendingKernel<<<1, 1, 0, s>>>(m);
 }
 void launchResetInactive(const DeviceMap& m, const TrackEval& ev, int n, int3* removed, int max_removed, cudaStream_t s) {

@@ -74,6 +74,7 @@ struct TrackingParams {
   int connectivity;         // 6 | 18 | 26
   int n_slots;              // pool slots to scan
   int* pending;             // [max_blocks] ever-free work list (slots whose TSDF was updated since the last pass)
+  int everfree_v2;          // KB_EVERFREE_V2 experiment: vectorised halo fill (everFreeKernelV2)
   // sharded pass only (everFreeKernel<true>): free masks of neighbour blocks owned by other ranks
   int rank, nranks;
   const int32_t* ghost_bits;             // the all-gathered halo buffers (see ShardExchange)

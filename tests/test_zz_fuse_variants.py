@@ -170,3 +170,28 @@ def test_motion_sparse_table_variant(oracle_lib, product_lib):
         hs.assert_blocks_equal(o.export_blocks(), g.export_blocks(), exact_float=True, what="motion sparse")
     finally:
         os.environ.pop("KB_MOTION_SPARSE", None)
+
+
+def test_everfree_v2_variant(oracle_lib, product_lib):
+    """KB_EVERFREE_V2=1: vectorised halo fill of the ever-free pass; all three connectivities."""
+    os.environ["KB_EVERFREE_V2"] = "1"
+    try:
+        import test_sharded_pipeline as tsp
+        cam = hs.small_camera(4)
+        frames, poses, stamps = tsp.dynamic_scenario(cam, 24)
+        for conn in (6, 18, 26):
+            trk = capi.default_tracking_config(num_threads=4)
+            trk.neighbor_connectivity = conn
+            mot = capi.default_motion_config(min_cluster_size=5, min_separation_distance=2.0, num_threads=4)
+            o = hs.make_handle(oracle_lib, "ko_", cam=cam, trk_cfg=trk, mot_cfg=mot)
+            g = hs.make_handle(product_lib, "kb_", cam=cam, trk_cfg=trk, mot_cfg=mot)
+            for i, ((d, l), T, st) in enumerate(zip(frames, poses, stamps)):
+                io, so, co = o.spin_once(o.make_frame(d, T, st, label=l))
+                ig, sg, cg = g.spin_once(g.make_frame(d, T, st, label=l))
+                assert (so, co) == (sg, cg)
+                np.testing.assert_array_equal(io, ig)
+            bo = o.export_blocks()
+            assert bo.ever_free.sum() > 1000
+            hs.assert_blocks_equal(bo, g.export_blocks(), exact_float=True, what=f"everfree v2 conn {conn}")
+    finally:
+        os.environ.pop("KB_EVERFREE_V2", None)

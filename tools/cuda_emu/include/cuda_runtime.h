@@ -36,6 +36,7 @@ struct dim3 {
 struct float2 { float x, y; };
 struct alignas(16) float4 { float x, y, z, w; };
 struct int3 { int x, y, z; };
+struct alignas(16) uint4 { unsigned x, y, z, w; };
 struct uchar3 { unsigned char x, y, z; };
 struct alignas(4) uchar4 { unsigned char x, y, z, w; };
 inline float2 make_float2(float x, float y) { return {x, y}; }

@@ -44,6 +44,8 @@ echo "== 3. per-frame pipeline (config[2]) on one GPU"
 timeout 200 python bench.py --workload dynamic --steps 4 --warmup 2 --no-cpu-baseline > gpurun_out/bench_dynamic.json 2> gpurun_out/bench_dynamic.err
 tail -c 600 gpurun_out/bench_dynamic.json
 timeout 200 python bench.py --workload dynamic --steps 4 --warmup 2 --no-cpu-baseline --force-cull > gpurun_out/bench_dynamic_cull.json 2> gpurun_out/bench_dynamic_cull.err
+KB_EVERFREE_V2=1 timeout 200 python bench.py --workload dynamic --steps 4 --warmup 2 --no-cpu-baseline > gpurun_out/bench_dynamic_efv2.json 2> gpurun_out/bench_dynamic_efv2.err
+python -c "import json;print('dynamic with KB_EVERFREE_V2', round(json.load(open('gpurun_out/bench_dynamic_efv2.json'))['value']), 'fps')"
 KB_MOTION_SPARSE=1 timeout 200 python bench.py --workload dynamic --steps 4 --warmup 2 --no-cpu-baseline > gpurun_out/bench_dynamic_sparse.json 2> gpurun_out/bench_dynamic_sparse.err
 python -c "import json;print('dynamic with KB_MOTION_SPARSE', round(json.load(open('gpurun_out/bench_dynamic_sparse.json'))['value']), 'fps')"
 python -c "import json;print('dynamic', round(json.load(open('gpurun_out/bench_dynamic.json'))['value']), 'fps; with single-frame culling', round(json.load(open('gpurun_out/bench_dynamic_cull.json'))['value']), 'fps')"
