@@ -126,6 +126,15 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
         rows = [(t, r) for t, r in list(self.rows) if len(r) >= 6]
+        late = False
+        if not rows:  # the sampler never produced a line (slow start): one synchronous query right after the region
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=20).stdout
+                rows = [(time.perf_counter(), [x.strip() for x in ln.split(",")]) for ln in out.splitlines() if ln.count(",") >= 5]
+                late = bool(rows)
+            except Exception:
+                rows = []
         inside = [r for t, r in rows if (t0 is None or t >= t0) and (t1 is None or t <= t1 + 0.5 * self.period_ms * 1e-3)]
         note = None
         if not inside and rows and t0 is not None:  # region shorter than the sampling period: nearest samples around it
@@ -142,6 +151,8 @@ class ClockSampler:
                     reasons.add(name)
         out = {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                "reasons": sorted(reasons), "samples": len(sm), "samples_total": len(rows)}
+        if late:
+            note = "sampler produced no line in time; one query taken right after the timed region"
         if note:
             out["note"] = note
         return out
