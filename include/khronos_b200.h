@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define KB_ABI_VERSION 3
+#define KB_ABI_VERSION 4
 
 typedef enum kb_status {
   KB_OK = 0,
@@ -283,6 +283,32 @@ int kb_detect_objects(kb_handle* h, const kb_object_detector_config* config, con
  * flat (u, v) pixel list in cluster order (order within a cluster unspecified). NULL pointers are skipped. */
 int kb_get_object_clusters(kb_handle* h, int32_t* id_semantic_count, int32_t* pixels_uv, int32_t* n_clusters,
                            int32_t* total_pixels);
+
+/* ---- track measurements (the step after the path) -------------------------------------------
+ * khronos::MaxIoUTracker in its shipped mode track_by = "voxels" (khronos_ros/config/mapper/uHumans2.yaml:72). The
+ * association itself (max_iou_tracker.cpp:216-448) is list bookkeeping and stays with the caller; this entry replaces
+ * what it loops over pixels and voxel sets for, for all clusters of one id image at once:
+ *   setupTrackMeasurementVoxels (max_iou_tracker.cpp:450-459)  cluster.voxels = { grid.toIndex(vertex_map(pixel)) } at
+ *                                                              Config::voxel_size (max_iou_tracker.h:95, default 0.1)
+ *   computeCentroid, voxel mode (:534-539)                     centroid = (voxel_sums / voxel_counts + 0.5) * voxel_size
+ *                                                              (the reference adds float voxel centres in the iteration
+ *                                                              order of an unordered_set; the integer sums are order free)
+ *   computeIoUVoxels (:551-562)                                intersections / iou against every track's last_voxels
+ * frame: depth (+ pose) or vertex_world, as for kb_detect_objects. id_image: H*W int32 in frame->memory space —
+ * FrameData::dynamic_image or object_image; a pixel value c in 1..max_id (max_id <= 1022) belongs to cluster c, anything
+ * else to none. Tracks: n_tracks lists of global voxel indices (x, y, z int64; Track::last_voxels, unique within a
+ * track), track t = track_voxels_xyz[3*track_offsets[t] .. 3*track_offsets[t+1]).
+ * Outputs (host, NULL = skipped): voxel_counts[max_id], voxel_sums[max_id*3], intersections[max_id*n_tracks] and
+ * iou[max_id*n_tracks] (row = id - 1), iou formed exactly like :562 (float inter / (float(size + size) - inter), so an
+ * empty cluster against an empty track is NaN as in the reference). Voxels further than 2^17 tracker voxels from the
+ * origin are dropped (13 km at 0.1 m). */
+int kb_track_measurements(kb_handle* h, const kb_frame* frame, const int32_t* id_image, int32_t max_id, float voxel_size,
+                          int32_t n_tracks, const int32_t* track_offsets, const int64_t* track_voxels_xyz,
+                          int32_t* voxel_counts, int64_t* voxel_sums, int32_t* intersections, float* iou);
+/* Voxel sets of the last kb_track_measurements call (what updateTrack stores as Track::last_voxels, :487-489):
+ * offsets[max_id + 1] and the flat (x, y, z) list, cluster ids ascending, voxels ascending in (z, y, x). Valid until the
+ * handle's next motion / object detection or track measurement. NULL pointers are skipped. */
+int kb_get_cluster_voxels(kb_handle* h, int32_t* offsets, int64_t* voxels_xyz, int32_t capacity, int32_t* total);
 
 /* ---- sharded per-frame pipeline (new in this build; SURVEY.md §8e exchange steps 1 and 2) -----------------------
  * With kb_set_shard(rank, nranks > 1) a handle holds only the blocks it owns. Fusion (K0/K1/K1b), K2, K2r and K4 are

@@ -415,6 +415,44 @@ class MapHandle:
             po += n
         return out
 
+    def track_measurements(self, frame: Frame, id_image, max_id: int, voxel_size: float = 0.1, tracks=()):
+        """kb_track_measurements (MaxIoUTracker, track_by = voxels). id_image: H x W int32 host array for host frames, or a device pointer (int) for
+        MEM_DEVICE frames. tracks: sequence of (n_i, 3) int64 arrays (Track::last_voxels). Returns a dict with
+        voxel_counts [max_id], voxel_sums [max_id, 3], intersections / iou [max_id, n_tracks]."""
+        if isinstance(id_image, int):  # raw pointer (device image of a MEM_DEVICE frame)
+            ids_ptr = C.c_void_p(id_image)
+        else:
+            ids = np.ascontiguousarray(id_image, np.int32)
+            ids_ptr = C.c_void_p(ids.ctypes.data)
+        tracks = [np.ascontiguousarray(t, np.int64).reshape(-1, 3) for t in tracks]
+        nt = len(tracks)
+        offsets = np.zeros(nt + 1, np.int32)
+        for i, t in enumerate(tracks):
+            offsets[i + 1] = offsets[i] + len(t)
+        flat = np.concatenate(tracks) if nt and offsets[-1] > 0 else np.zeros((1, 3), np.int64)
+        flat = np.ascontiguousarray(flat)
+        counts = np.zeros(max_id, np.int32)
+        sums = np.zeros((max_id, 3), np.int64)
+        inter = np.zeros((max_id, max(nt, 1)), np.int32)
+        iou = np.zeros((max_id, max(nt, 1)), np.float32)
+        self._check(self._fn("track_measurements")(
+            self._h, C.byref(frame), ids_ptr, C.c_int32(max_id), C.c_float(voxel_size), C.c_int32(nt),
+            C.c_void_p(offsets.ctypes.data) if nt else None, C.c_void_p(flat.ctypes.data) if nt else None,
+            C.c_void_p(counts.ctypes.data), C.c_void_p(sums.ctypes.data),
+            C.c_void_p(inter.ctypes.data) if nt else None, C.c_void_p(iou.ctypes.data) if nt else None))
+        return {"voxel_counts": counts, "voxel_sums": sums, "intersections": inter[:, :nt], "iou": iou[:, :nt]}
+
+    def get_cluster_voxels(self, max_id: int):
+        """kb_get_cluster_voxels: list of (n_c, 3) int64 arrays, one per id 1..max_id of the last track_measurements
+        call, voxels ascending in (z, y, x)."""
+        f = self._fn("get_cluster_voxels")
+        total = C.c_int32(0)
+        offsets = np.zeros(max_id + 1, np.int32)
+        self._check(f(self._h, C.c_void_p(offsets.ctypes.data), None, 0, C.byref(total)))
+        vox = np.zeros((max(total.value, 1), 3), np.int64)
+        self._check(f(self._h, C.c_void_p(offsets.ctypes.data), C.c_void_p(vox.ctypes.data), C.c_int32(total.value), C.byref(total)))
+        return [vox[offsets[i]:offsets[i + 1]].copy() for i in range(max_id)]
+
     def allocate_box(self, mn, mx):
         a = (C.c_int32 * 3)(*[int(v) for v in mn])
         b = (C.c_int32 * 3)(*[int(v) for v in mx])

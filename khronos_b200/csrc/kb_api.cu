@@ -16,6 +16,7 @@
 #include "kb_kernels.cuh"
 #include "kb_motion_device.cuh"
 #include "kb_objects_device.cuh"
+#include "kb_tracks_device.cuh"
 #include "kb_motion_host.h"
 
 using namespace kb;
@@ -127,6 +128,20 @@ struct kb_handle {
   size_t obj_pixels = 0;
   std::vector<int32_t> obj_image_host, obj_label_host;
   bool obj_have = false;
+  // track measurements (kb_track_measurements): staged id image, per-id accumulators, packed track voxels, results
+  int32_t* trk_ids = nullptr;
+  unsigned long long* trk_export = nullptr;
+  size_t trk_pixels = 0;
+  int* trk_counts = nullptr;
+  unsigned long long* trk_sums = nullptr;
+  int* trk_present = nullptr;
+  unsigned long long* trk_keys = nullptr;
+  int* trk_of = nullptr;
+  size_t trk_voxel_cap = 0;
+  int* trk_inter = nullptr;
+  size_t trk_inter_cap = 0;
+  std::vector<int32_t> trk_counts_host;
+  bool trk_have = false;
   // sharded per-frame pipeline (kb_tracking_begin / pack_halo / finish, kb_motion_lookup_local / cluster_global)
   ShardExchange xch{};
   int cap_pending = 1024, cap_halo = 2048;
@@ -208,6 +223,32 @@ int ensureObjectBuffers(kb_handle* h, size_t pixels) {
   KB_CUDA(h, devAlloc(&h->d_object, pixels, 0));
   if (!h->h_oscal) KB_CUDA(h, cudaMallocHost(reinterpret_cast<void**>(&h->h_oscal), sizeof(int) * kMsCount));
   h->obj_pixels = pixels;
+  return KB_OK;
+}
+
+int ensureTrackBuffers(kb_handle* h, size_t pixels, size_t track_voxels, size_t inter) {
+  if (h->trk_pixels < pixels) {
+    cudaFree(h->trk_ids); cudaFree(h->trk_export);
+    KB_CUDA(h, devAlloc(&h->trk_ids, pixels, 0));
+    KB_CUDA(h, devAlloc(&h->trk_export, pixels, 0));
+    h->trk_pixels = pixels;
+  }
+  if (!h->trk_counts) {
+    KB_CUDA(h, devAlloc(&h->trk_counts, static_cast<size_t>(kTrackMaxIds), 0));
+    KB_CUDA(h, devAlloc(&h->trk_sums, static_cast<size_t>(kTrackMaxIds) * 3, 0));
+    KB_CUDA(h, devAlloc(&h->trk_present, static_cast<size_t>(kTrackMaxIds), 0));
+  }
+  if (h->trk_voxel_cap < track_voxels) {
+    cudaFree(h->trk_keys); cudaFree(h->trk_of);
+    KB_CUDA(h, devAlloc(&h->trk_keys, track_voxels * 2, 0));
+    KB_CUDA(h, devAlloc(&h->trk_of, track_voxels * 2, 0));
+    h->trk_voxel_cap = track_voxels * 2;
+  }
+  if (h->trk_inter_cap < inter) {
+    cudaFree(h->trk_inter);
+    KB_CUDA(h, devAlloc(&h->trk_inter, inter * 2, 0));
+    h->trk_inter_cap = inter * 2;
+  }
   return KB_OK;
 }
 
@@ -532,6 +573,8 @@ int kb_destroy(kb_handle* h) {
   cudaFree(h->xch.halo_mark); cudaFree(h->xch.publish); cudaFree(h->xch.ghost_keys); cudaFree(h->xch.ghost_vals);
   cudaFree(h->obj_depth); cudaFree(h->obj_label); cudaFree(h->d_object); cudaFree(h->d_flags_local);
   if (h->h_oscal) cudaFreeHost(h->h_oscal);
+  cudaFree(h->trk_ids); cudaFree(h->trk_export); cudaFree(h->trk_counts); cudaFree(h->trk_sums); cudaFree(h->trk_present);
+  cudaFree(h->trk_keys); cudaFree(h->trk_of); cudaFree(h->trk_inter);
   cudaFree(h->stg_depth); cudaFree(h->stg_label); cudaFree(h->stg_mask); cudaFree(h->stg_object);
   cudaFree(h->stg_vertex); cudaFree(h->d_pixel_gidx); cudaFree(h->d_pixel_seed); cudaFree(h->d_removed);
   cudaFree(h->d_dynamic);
@@ -1302,6 +1345,7 @@ static int enqueueMotionLookup(kb_handle* h, const kb_frame* f, uint8_t* shard_f
 static int enqueueDeviceClustering(kb_handle* h) {
   const size_t px = static_cast<size_t>(h->cam.width) * h->cam.height;
   const int D = static_cast<int>(std::ceil(h->mot.min_separation_distance));
+  h->trk_have = false;  // the shared table is reused
   if (h->motion_sparse) {
     launchMotionClusteringSparse(h->mt, h->d_pixel_gidx, h->d_pixel_seed, static_cast<int>(px), h->mot.neighbor_connectivity, D,
                                  h->mot.min_cluster_size, h->mot.max_cluster_size, h->d_dynamic, h->mt_dirty, h->stream);
@@ -1454,6 +1498,7 @@ int kb_detect_objects(kb_handle* h, const kb_object_detector_config* cfg, const 
   if (cfg->use_3d) launchObjectClustering3D(h->mt, p, h->stream);
   else launchObjectClustering2D(h->mt, p, h->stream);
   h->mt_dirty = true;  // shared table memory
+  h->trk_have = false;
   KB_CUDA(h, cudaGetLastError());
   KB_CUDA(h, cudaMemcpyAsync(h->h_oscal, h->mt.scalars, sizeof(int) * kMsCount, cudaMemcpyDeviceToHost, h->stream));
   KB_CUDA(h, cudaMemcpyAsync(object_image_out, h->d_object, sizeof(int32_t) * px, cudaMemcpyDeviceToHost, h->stream));
@@ -1496,6 +1541,130 @@ int kb_get_object_clusters(kb_handle* h, int32_t* id_semantic_count, int32_t* pi
   }
   if (n_clusters) *n_clusters = nc;
   if (total_pixels) *total_pixels = static_cast<int32_t>(by_id.size());
+  return KB_OK;
+}
+
+int kb_track_measurements(kb_handle* h, const kb_frame* f, const int32_t* id_image, int32_t max_id, float voxel_size,
+                          int32_t n_tracks, const int32_t* track_offsets, const int64_t* track_voxels_xyz,
+                          int32_t* voxel_counts, int64_t* voxel_sums, int32_t* intersections, float* iou) {
+  if (!h || !f || !id_image || (!f->depth && !f->depth_u16 && !f->vertex_world)) return fail(h, KB_ERR_INVALID, "null argument");
+  if (!h->has_cam) return fail(h, KB_ERR_STATE, "kb_set_camera must be called first");
+  if (max_id < 1 || max_id > kTrackMaxIds) return fail(h, KB_ERR_INVALID, "max_id must be in 1..1022");
+  if (!(voxel_size > 0.f)) return fail(h, KB_ERR_INVALID, "voxel_size must be positive");
+  if (n_tracks < 0 || (n_tracks > 0 && (!track_offsets || !track_voxels_xyz))) return fail(h, KB_ERR_INVALID, "track lists missing");
+  if (n_tracks > 0 && (track_offsets[0] != 0)) return fail(h, KB_ERR_INVALID, "track_offsets[0] must be 0");
+  for (int t = 0; t < n_tracks; ++t)
+    if (track_offsets[t + 1] < track_offsets[t]) return fail(h, KB_ERR_INVALID, "track_offsets must be non-decreasing");
+  KB_CUDA(h, cudaSetDevice(h->device));
+  const kb_camera& c = h->cam;
+  const size_t px = static_cast<size_t>(c.width) * c.height;
+  const size_t ntv = n_tracks > 0 ? static_cast<size_t>(track_offsets[n_tracks]) : 0;
+  const size_t ninter = static_cast<size_t>(max_id) * static_cast<size_t>(std::max(n_tracks, 1));
+  int st;
+  if ((st = ensureObjectBuffers(h, px)) != KB_OK) return st;
+  if ((st = ensureTrackBuffers(h, px, std::max<size_t>(ntv, 1), ninter)) != KB_OK) return st;
+  h->trk_have = false;
+  TrackParams p{};
+  float R[9], t[3];
+  poseToFloat(f->world_T_sensor, R, t, p.Rw, p.tw);
+  p.W = c.width; p.H = c.height; p.fx = c.fx; p.fy = c.fy; p.cx = c.cx; p.cy = c.cy;
+  p.max_id = max_id;
+  p.inv_voxel = 1.f / voxel_size;
+  p.voxel_counts = h->trk_counts;
+  p.sums = h->trk_sums;
+  if ((st = stage(h, f->vertex_world, h->stg_vertex, px * 3, f->memory, &p.vertex)) != KB_OK) return st;
+  if (!p.vertex) {
+    if (f->depth_u16) {
+      const uint16_t* d16 = nullptr;
+      if ((st = stage(h, f->depth_u16, h->mot_depth16, px, f->memory, &d16)) != KB_OK) return st;
+      launchExpandDepth(d16, f->depth_u16_scale, h->obj_depth, static_cast<int>(px), h->stream);
+      p.depth = h->obj_depth;
+    } else if ((st = stage(h, f->depth, h->obj_depth, px, f->memory, &p.depth)) != KB_OK) {
+      return st;
+    }
+  }
+  if ((st = stage(h, id_image, h->trk_ids, px, f->memory, &p.ids)) != KB_OK) return st;
+  launchTrackVoxelize(h->mt, p, h->stream);
+  h->mt_dirty = true;  // shared table memory
+  KB_CUDA(h, cudaGetLastError());
+  h->trk_counts_host.assign(static_cast<size_t>(max_id), 0);
+  std::vector<unsigned long long> sums(static_cast<size_t>(max_id) * 3);
+  KB_CUDA(h, cudaMemcpyAsync(h->trk_counts_host.data(), h->trk_counts, sizeof(int) * max_id, cudaMemcpyDeviceToHost, h->stream));
+  KB_CUDA(h, cudaMemcpyAsync(sums.data(), h->trk_sums, sizeof(unsigned long long) * 3 * max_id, cudaMemcpyDeviceToHost, h->stream));
+  KB_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (voxel_counts) std::memcpy(voxel_counts, h->trk_counts_host.data(), sizeof(int32_t) * max_id);
+  if (voxel_sums)
+    for (size_t i = 0; i < sums.size(); ++i) voxel_sums[i] = static_cast<int64_t>(sums[i]);
+  h->trk_have = true;
+  if (n_tracks == 0 || (!intersections && !iou)) return KB_OK;
+  // computeIoUVoxels: probe every track voxel against the clusters that have voxels
+  std::vector<int> present;
+  for (int id = 1; id <= max_id; ++id)
+    if (h->trk_counts_host[id - 1] > 0) present.push_back(id);
+  std::vector<unsigned long long> keys;
+  std::vector<int> track_of;
+  keys.reserve(ntv); track_of.reserve(ntv);
+  for (int tr = 0; tr < n_tracks; ++tr)
+    for (int k = track_offsets[tr]; k < track_offsets[tr + 1]; ++k) {
+      unsigned long long key;  // a voxel outside the key range cannot be in any cluster of this frame
+      if (trackVoxelKey(track_voxels_xyz[3 * k], track_voxels_xyz[3 * k + 1], track_voxels_xyz[3 * k + 2], &key)) {
+        keys.push_back(key);
+        track_of.push_back(tr);
+      }
+    }
+  std::vector<int32_t> inter(static_cast<size_t>(max_id) * n_tracks, 0);
+  if (!present.empty() && !keys.empty()) {
+    KB_CUDA(h, cudaMemsetAsync(h->trk_inter, 0, sizeof(int) * inter.size(), h->stream));
+    KB_CUDA(h, cudaMemcpyAsync(h->trk_keys, keys.data(), sizeof(unsigned long long) * keys.size(), cudaMemcpyHostToDevice, h->stream));
+    KB_CUDA(h, cudaMemcpyAsync(h->trk_of, track_of.data(), sizeof(int) * keys.size(), cudaMemcpyHostToDevice, h->stream));
+    KB_CUDA(h, cudaMemcpyAsync(h->trk_present, present.data(), sizeof(int) * present.size(), cudaMemcpyHostToDevice, h->stream));
+    launchTrackIntersect(h->mt, h->trk_keys, h->trk_of, static_cast<int>(keys.size()), h->trk_present,
+                         static_cast<int>(present.size()), n_tracks, h->trk_inter, h->stream);
+    KB_CUDA(h, cudaGetLastError());
+    KB_CUDA(h, cudaMemcpyAsync(inter.data(), h->trk_inter, sizeof(int) * inter.size(), cudaMemcpyDeviceToHost, h->stream));
+    KB_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  for (int id = 1; id <= max_id; ++id)
+    for (int tr = 0; tr < n_tracks; ++tr) {
+      const size_t o = static_cast<size_t>(id - 1) * n_tracks + tr;
+      if (intersections) intersections[o] = inter[o];
+      if (iou) {
+        // max_iou_tracker.cpp:562: float intersection / (size_t + size_t - float intersection)
+        const float in = static_cast<float>(inter[o]);
+        const size_t sizes = static_cast<size_t>(h->trk_counts_host[id - 1]) +
+                             static_cast<size_t>(track_offsets[tr + 1] - track_offsets[tr]);
+        iou[o] = in / (static_cast<float>(sizes) - in);
+      }
+    }
+  return KB_OK;
+}
+
+int kb_get_cluster_voxels(kb_handle* h, int32_t* offsets, int64_t* voxels_xyz, int32_t capacity, int32_t* total) {
+  if (!h) return KB_ERR_INVALID;
+  if (!h->trk_have) return fail(h, KB_ERR_STATE, "no track measurement result");
+  KB_CUDA(h, cudaSetDevice(h->device));
+  const int max_id = static_cast<int>(h->trk_counts_host.size());
+  size_t n = 0;
+  for (int c : h->trk_counts_host) n += static_cast<size_t>(c);
+  if (total) *total = static_cast<int32_t>(n);
+  if (offsets) {
+    offsets[0] = 0;
+    for (int i = 0; i < max_id; ++i) offsets[i + 1] = offsets[i] + h->trk_counts_host[i];
+  }
+  if (!voxels_xyz) return KB_OK;
+  if (static_cast<size_t>(std::max(capacity, 0)) < n) return fail(h, KB_ERR_CAPACITY, "voxel buffer too small");
+  if (n == 0) return KB_OK;
+  std::vector<unsigned long long> keys(n);
+  launchTrackExportKeys(h->mt, h->trk_export, h->stream);
+  KB_CUDA(h, cudaGetLastError());
+  KB_CUDA(h, cudaMemcpyAsync(keys.data(), h->trk_export, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost, h->stream));
+  KB_CUDA(h, cudaStreamSynchronize(h->stream));
+  std::sort(keys.begin(), keys.end());  // order preserving keys: cluster id, then (z, y, x)
+  for (size_t i = 0; i < n; ++i) {
+    int id, x, y, z;
+    trackKeyDecode(keys[i], &id, &x, &y, &z);
+    voxels_xyz[3 * i] = x; voxels_xyz[3 * i + 1] = y; voxels_xyz[3 * i + 2] = z;
+  }
   return KB_OK;
 }
 

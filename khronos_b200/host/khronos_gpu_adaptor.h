@@ -252,6 +252,47 @@ class GpuConnectedSemantics {
   kb_object_detector_config config_;
 };
 
+// The measurement step of khronos::MaxIoUTracker with track_by = voxels (tracking/max_iou_tracker.cpp): what
+// setupTrackMeasurements (:450-459), computeCentroid (:534-539) and computeIoU (:551-562) compute for the clusters of one
+// id image (data.dynamic_image or data.object_image) against the voxel sets of the live tracks — one call per image and
+// frame instead of one set construction per cluster and one set probe loop per (cluster, track) pair. The greedy
+// association loops (:216-448) keep running on the host over these small matrices.
+struct TrackMeasurements {
+  int max_id = 0, n_tracks = 0;
+  std::vector<int32_t> voxel_counts;   // [max_id]              |cluster.voxels|
+  std::vector<int64_t> voxel_sums;     // [max_id * 3]          centroid = (sums / count + 0.5) * voxel_size
+  std::vector<int32_t> intersections;  // [max_id * n_tracks]
+  std::vector<float> iou;              // [max_id * n_tracks]   computeIoUVoxels
+  float iouOf(int cluster_id, int track) const { return iou[static_cast<size_t>(cluster_id - 1) * n_tracks + track]; }
+};
+
+inline TrackMeasurements measureTracks(GpuVolumetricMap& map, const khronos::FrameData& data, const cv::Mat& id_image,
+                                       int max_id, float tracker_voxel_size,
+                                       const std::vector<std::vector<int64_t>>& track_last_voxels_xyz) {
+  TrackMeasurements out;
+  out.max_id = max_id;
+  out.n_tracks = static_cast<int>(track_last_voxels_xyz.size());
+  std::vector<int32_t> offsets(1, 0);
+  std::vector<int64_t> flat;
+  for (const auto& t : track_last_voxels_xyz) {
+    flat.insert(flat.end(), t.begin(), t.end());
+    offsets.push_back(static_cast<int32_t>(flat.size() / 3));
+  }
+  if (flat.empty()) flat.resize(3);
+  out.voxel_counts.resize(static_cast<size_t>(max_id));
+  out.voxel_sums.resize(static_cast<size_t>(max_id) * 3);
+  out.intersections.resize(static_cast<size_t>(max_id) * out.n_tracks);
+  out.iou.resize(static_cast<size_t>(max_id) * out.n_tracks);
+  kb_frame f = makeFrame(data.input, nullptr, nullptr, 0);
+  map.setSensor(data.input.getSensor());
+  check(kb_track_measurements(map.handle(), &f, id_image.ptr<int32_t>(), max_id, tracker_voxel_size, out.n_tracks,
+                              out.n_tracks ? offsets.data() : nullptr, out.n_tracks ? flat.data() : nullptr,
+                              out.voxel_counts.data(), out.voxel_sums.data(),
+                              out.n_tracks ? out.intersections.data() : nullptr, out.n_tracks ? out.iou.data() : nullptr),
+        map.handle(), "kb_track_measurements");
+  return out;
+}
+
 // K4 wrapper for MeshObjectExtractor::extractStaticObject (mesh_object_extractor.cpp:246-264).
 inline int eraseLowConfidence(GpuVolumetricMap& map, float min_confidence, int min_observations) {
   int32_t n = 0;

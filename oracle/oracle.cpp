@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstring>
 #include <map>
+#include <set>
 #include <mutex>
 #include <thread>
 
@@ -955,6 +956,57 @@ void Oracle::detectObjects(const kb_object_detector_config& cfg, const kb_frame&
     }
   }
   if (clusters_out) *clusters_out = object_clusters_;
+}
+
+// ---- track measurements: MaxIoUTracker, track_by = voxels (tracking/max_iou_tracker.cpp, fully in-tree) --------
+
+void Oracle::trackMeasurements(const kb_frame& f, const int32_t* id_image, int max_id, float voxel_size, int n_tracks,
+                               const int32_t* track_offsets, const int64_t* track_voxels_xyz) {
+  track_result_ = TrackMeasurements{};
+  if (!has_cam_) { error_ = "camera not set"; return; }
+  const int W = cam_.width, H = cam_.height;
+  float R[9], t[3], Rw[9], tw[3];
+  invertPose(f.world_T_sensor, R, t, Rw, tw);
+  // spatial_hash::Grid(voxel_size) (max_iou_tracker.cpp:158): toIndex(p) = floor(p * voxel_size_inv), voxel_size_inv = 1.f / voxel_size
+  const float inv = 1.f / voxel_size;
+  // setupTrackMeasurementVoxels (:450-459) for every cluster: the set of voxels under the cluster's pixels
+  std::vector<std::set<GIdx, GIdxZyxLess>> sets(static_cast<size_t>(max_id));
+  for (int v = 0; v < H; ++v)
+    for (int u = 0; u < W; ++u) {
+      const size_t px = static_cast<size_t>(v) * W + u;
+      const int id = id_image[px];
+      if (id < 1 || id > max_id) continue;
+      float p[3];
+      if (f.vertex_world) {
+        p[0] = f.vertex_world[px * 3]; p[1] = f.vertex_world[px * 3 + 1]; p[2] = f.vertex_world[px * 3 + 2];
+      } else {
+        const float range = f.depth[px];
+        const float pC[3] = {(static_cast<float>(u) - cam_.cx) / cam_.fx * range,
+                             (static_cast<float>(v) - cam_.cy) / cam_.fy * range, range};
+        transform(Rw, tw, pC, p);
+      }
+      sets[id - 1].insert(GIdx{static_cast<int64_t>(std::floor(p[0] * inv)), static_cast<int64_t>(std::floor(p[1] * inv)),
+                               static_cast<int64_t>(std::floor(p[2] * inv))});
+    }
+  track_result_.voxels.resize(static_cast<size_t>(max_id));
+  for (int i = 0; i < max_id; ++i) track_result_.voxels[i].assign(sets[i].begin(), sets[i].end());
+  // computeIoUVoxels (:551-562) for every (cluster, track) pair
+  track_result_.intersections.assign(static_cast<size_t>(max_id) * n_tracks, 0);
+  track_result_.iou.assign(static_cast<size_t>(max_id) * n_tracks, 0.f);
+  for (int tr = 0; tr < n_tracks; ++tr) {
+    std::set<GIdx, GIdxZyxLess> last_voxels;
+    for (int k = track_offsets[tr]; k < track_offsets[tr + 1]; ++k)
+      last_voxels.insert(GIdx{track_voxels_xyz[3 * k], track_voxels_xyz[3 * k + 1], track_voxels_xyz[3 * k + 2]});
+    const size_t track_size = static_cast<size_t>(track_offsets[tr + 1] - track_offsets[tr]);  // Track::last_voxels.size()
+    for (int i = 0; i < max_id; ++i) {
+      float intersection = 0.f;
+      for (const GIdx& voxel : sets[i])
+        if (last_voxels.count(voxel)) intersection += 1.f;
+      const size_t o = static_cast<size_t>(i) * n_tracks + tr;
+      track_result_.intersections[o] = static_cast<int32_t>(intersection);
+      track_result_.iou[o] = intersection / (sets[i].size() + track_size - intersection);
+    }
+  }
 }
 
 // ---- E0 / K4 ----------------------------------------------------------------------------------------------

@@ -111,6 +111,18 @@ class Oracle {
                      std::vector<ObjectCluster>* clusters);
   const std::vector<ObjectCluster>& objectClusters() const { return object_clusters_; }
 
+  // Track measurements: khronos::MaxIoUTracker, track_by = voxels (tracking/max_iou_tracker.cpp:450-459, :534-539,
+  // :551-562) for every cluster id 1..max_id of an id image. Results: per id the voxel set (ordered z, y, x), and per
+  // (id, track) the intersection count and the IoU float of :562.
+  struct TrackMeasurements {
+    std::vector<std::vector<GIdx>> voxels;  // [max_id]
+    std::vector<int32_t> intersections;     // [max_id * n_tracks]
+    std::vector<float> iou;                 // [max_id * n_tracks]
+  };
+  void trackMeasurements(const kb_frame& f, const int32_t* id_image, int max_id, float voxel_size, int n_tracks,
+                         const int32_t* track_offsets, const int64_t* track_voxels_xyz);
+  const TrackMeasurements& trackResult() const { return track_result_; }
+
   // ---- block-hash sharded protocol (our multi-GPU design, not in the reference). The oracle
   // implements it on host buffers with the layouts of csrc/kb_kernels.cuh::ShardExchange so that world-size-2
   // gloo tests can prove "union of the shards == the unsharded map" on CPU.
@@ -177,6 +189,7 @@ class Oracle {
   std::vector<uint8_t> flags_scratch_;
   int rank_ = 0, nranks_ = 1;
   std::vector<ObjectCluster> object_clusters_;
+  TrackMeasurements track_result_;
   std::vector<Block*> open_pending_;       // ever-free work list between trackingBegin and trackingFinish
   uint64_t open_stamp_ = 0;
   std::string error_;

@@ -164,6 +164,51 @@ int ko_get_object_clusters(ko_handle* h, int32_t* id_semantic_count, int32_t* pi
   return KB_OK;
 }
 
+int ko_track_measurements(ko_handle* h, const kb_frame* f_in, const int32_t* id_image, int32_t max_id, float voxel_size,
+                          int32_t n_tracks, const int32_t* track_offsets, const int64_t* track_voxels_xyz,
+                          int32_t* voxel_counts, int64_t* voxel_sums, int32_t* intersections, float* iou) {
+  if (!h || !f_in || !id_image || (!f_in->depth && !f_in->depth_u16 && !f_in->vertex_world)) return KB_ERR_INVALID;
+  if (max_id < 1 || max_id > 1022 || !(voxel_size > 0.f) || n_tracks < 0) return KB_ERR_INVALID;
+  if (n_tracks > 0 && (!track_offsets || !track_voxels_xyz || track_offsets[0] != 0)) return KB_ERR_INVALID;
+  for (int t = 0; t < n_tracks; ++t)
+    if (track_offsets[t + 1] < track_offsets[t]) return KB_ERR_INVALID;
+  kb_frame tmp;
+  const kb_frame* f = expandCompact(h, f_in, &tmp);
+  h->o->trackMeasurements(*f, id_image, max_id, voxel_size, n_tracks, track_offsets, track_voxels_xyz);
+  if (!h->o->ok()) return fail(h, KB_ERR_STATE);
+  const auto& r = h->o->trackResult();
+  for (int i = 0; i < max_id; ++i) {
+    if (voxel_counts) voxel_counts[i] = static_cast<int32_t>(r.voxels[i].size());
+    if (voxel_sums) {
+      int64_t s[3] = {0, 0, 0};
+      for (const auto& g : r.voxels[i]) { s[0] += g.x; s[1] += g.y; s[2] += g.z; }
+      voxel_sums[3 * i] = s[0]; voxel_sums[3 * i + 1] = s[1]; voxel_sums[3 * i + 2] = s[2];
+    }
+  }
+  if (intersections) std::copy(r.intersections.begin(), r.intersections.end(), intersections);
+  if (iou) std::copy(r.iou.begin(), r.iou.end(), iou);
+  return KB_OK;
+}
+
+int ko_get_cluster_voxels(ko_handle* h, int32_t* offsets, int64_t* voxels_xyz, int32_t capacity, int32_t* total) {
+  if (!h) return KB_ERR_INVALID;
+  const auto& r = h->o->trackResult();
+  if (r.voxels.empty()) return fail(h, KB_ERR_STATE);
+  size_t n = 0;
+  for (const auto& v : r.voxels) n += v.size();
+  if (total) *total = static_cast<int32_t>(n);
+  if (offsets) {
+    offsets[0] = 0;
+    for (size_t i = 0; i < r.voxels.size(); ++i) offsets[i + 1] = offsets[i] + static_cast<int32_t>(r.voxels[i].size());
+  }
+  if (!voxels_xyz) return KB_OK;
+  if (static_cast<size_t>(std::max(capacity, 0)) < n) return fail(h, KB_ERR_CAPACITY);
+  size_t k = 0;
+  for (const auto& v : r.voxels)
+    for (const auto& g : v) { voxels_xyz[3 * k] = g.x; voxels_xyz[3 * k + 1] = g.y; voxels_xyz[3 * k + 2] = g.z; ++k; }
+  return KB_OK;
+}
+
 // ---- block-hash sharded protocol on host buffers (same layouts as the product's device buffers) ----------
 
 int ko_set_shard(ko_handle* h, int rank, int nranks) {
