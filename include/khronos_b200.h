@@ -295,18 +295,21 @@ int kb_get_object_clusters(kb_handle* h, int32_t* id_semantic_count, int32_t* pi
  *                                                              order of an unordered_set; the integer sums are order free)
  *   computeIoUVoxels (:551-562)                                intersections / iou against every track's last_voxels
  * frame: depth (+ pose) or vertex_world, as for kb_detect_objects. id_image: H*W int32 in frame->memory space —
- * FrameData::dynamic_image or object_image; a pixel value c in 1..max_id (max_id <= 1022) belongs to cluster c, anything
- * else to none. Tracks: n_tracks lists of global voxel indices (x, y, z int64; Track::last_voxels, unique within a
+ * FrameData::dynamic_image or object_image. Clusters: n_clusters <= 1022 rows; cluster_ids (host, strictly ascending
+ * pixel values, e.g. the ids of kb_get_object_clusters — the 2D detector keeps creation-order ids, which can be large)
+ * or NULL for the pixel values 1..n_clusters (dynamic images, 3D object images). Pixels with any other value belong
+ * to no cluster. Tracks: n_tracks lists of global voxel indices (x, y, z int64; Track::last_voxels, unique within a
  * track), track t = track_voxels_xyz[3*track_offsets[t] .. 3*track_offsets[t+1]).
- * Outputs (host, NULL = skipped): voxel_counts[max_id], voxel_sums[max_id*3], intersections[max_id*n_tracks] and
- * iou[max_id*n_tracks] (row = id - 1), iou formed exactly like :562 (float inter / (float(size + size) - inter), so an
- * empty cluster against an empty track is NaN as in the reference). Voxels further than 2^17 tracker voxels from the
- * origin are dropped (13 km at 0.1 m). */
-int kb_track_measurements(kb_handle* h, const kb_frame* frame, const int32_t* id_image, int32_t max_id, float voxel_size,
-                          int32_t n_tracks, const int32_t* track_offsets, const int64_t* track_voxels_xyz,
-                          int32_t* voxel_counts, int64_t* voxel_sums, int32_t* intersections, float* iou);
+ * Outputs (host, NULL = skipped): voxel_counts[n_clusters], voxel_sums[n_clusters*3], intersections[n_clusters*n_tracks]
+ * and iou[n_clusters*n_tracks] (row = position in cluster_ids, or id - 1), iou formed exactly like :562 (float inter /
+ * (float(size + size) - inter), so an empty cluster against an empty track is NaN as in the reference). Voxels further
+ * than 2^17 tracker voxels from the origin are dropped (13 km at 0.1 m). */
+int kb_track_measurements(kb_handle* h, const kb_frame* frame, const int32_t* id_image, int32_t n_clusters,
+                          const int32_t* cluster_ids, float voxel_size, int32_t n_tracks, const int32_t* track_offsets,
+                          const int64_t* track_voxels_xyz, int32_t* voxel_counts, int64_t* voxel_sums,
+                          int32_t* intersections, float* iou);
 /* Voxel sets of the last kb_track_measurements call (what updateTrack stores as Track::last_voxels, :487-489):
- * offsets[max_id + 1] and the flat (x, y, z) list, cluster ids ascending, voxels ascending in (z, y, x). Valid until the
+ * offsets[n_clusters + 1] and the flat (x, y, z) list, clusters in row order, voxels ascending in (z, y, x). Valid until the
  * handle's next motion / object detection or track measurement. NULL pointers are skipped. */
 int kb_get_cluster_voxels(kb_handle* h, int32_t* offsets, int64_t* voxels_xyz, int32_t capacity, int32_t* total);
 

@@ -415,15 +415,21 @@ class MapHandle:
             po += n
         return out
 
-    def track_measurements(self, frame: Frame, id_image, max_id: int, voxel_size: float = 0.1, tracks=()):
+    def track_measurements(self, frame: Frame, id_image, clusters, voxel_size: float = 0.1, tracks=()):
         """kb_track_measurements (MaxIoUTracker, track_by = voxels). id_image: H x W int32 host array for host frames, or a device pointer (int) for
-        MEM_DEVICE frames. tracks: sequence of (n_i, 3) int64 arrays (Track::last_voxels). Returns a dict with
-        voxel_counts [max_id], voxel_sums [max_id, 3], intersections / iou [max_id, n_tracks]."""
+        MEM_DEVICE frames. clusters: n (pixel values 1..n) or an ascending list of pixel values. tracks: sequence of
+        (n_i, 3) int64 arrays (Track::last_voxels). Returns a dict with voxel_counts [n], voxel_sums [n, 3],
+        intersections / iou [n, n_tracks]."""
         if isinstance(id_image, int):  # raw pointer (device image of a MEM_DEVICE frame)
             ids_ptr = C.c_void_p(id_image)
         else:
             ids = np.ascontiguousarray(id_image, np.int32)
             ids_ptr = C.c_void_p(ids.ctypes.data)
+        if isinstance(clusters, (int, np.integer)):   # pixel values 1..clusters
+            max_id, cid_ptr = int(clusters), None
+        else:                                          # ascending list of pixel values
+            cids = np.ascontiguousarray(clusters, np.int32)
+            max_id, cid_ptr = len(cids), C.c_void_p(cids.ctypes.data)
         tracks = [np.ascontiguousarray(t, np.int64).reshape(-1, 3) for t in tracks]
         nt = len(tracks)
         offsets = np.zeros(nt + 1, np.int32)
@@ -436,7 +442,7 @@ class MapHandle:
         inter = np.zeros((max_id, max(nt, 1)), np.int32)
         iou = np.zeros((max_id, max(nt, 1)), np.float32)
         self._check(self._fn("track_measurements")(
-            self._h, C.byref(frame), ids_ptr, C.c_int32(max_id), C.c_float(voxel_size), C.c_int32(nt),
+            self._h, C.byref(frame), ids_ptr, C.c_int32(max_id), cid_ptr, C.c_float(voxel_size), C.c_int32(nt),
             C.c_void_p(offsets.ctypes.data) if nt else None, C.c_void_p(flat.ctypes.data) if nt else None,
             C.c_void_p(counts.ctypes.data), C.c_void_p(sums.ctypes.data),
             C.c_void_p(inter.ctypes.data) if nt else None, C.c_void_p(iou.ctypes.data) if nt else None))

@@ -135,6 +135,7 @@ struct kb_handle {
   int* trk_counts = nullptr;
   unsigned long long* trk_sums = nullptr;
   int* trk_present = nullptr;
+  int* trk_idlist = nullptr;
   unsigned long long* trk_keys = nullptr;
   int* trk_of = nullptr;
   size_t trk_voxel_cap = 0;
@@ -237,6 +238,7 @@ int ensureTrackBuffers(kb_handle* h, size_t pixels, size_t track_voxels, size_t 
     KB_CUDA(h, devAlloc(&h->trk_counts, static_cast<size_t>(kTrackMaxIds), 0));
     KB_CUDA(h, devAlloc(&h->trk_sums, static_cast<size_t>(kTrackMaxIds) * 3, 0));
     KB_CUDA(h, devAlloc(&h->trk_present, static_cast<size_t>(kTrackMaxIds), 0));
+    KB_CUDA(h, devAlloc(&h->trk_idlist, static_cast<size_t>(kTrackMaxIds), 0));
   }
   if (h->trk_voxel_cap < track_voxels) {
     cudaFree(h->trk_keys); cudaFree(h->trk_of);
@@ -573,7 +575,7 @@ int kb_destroy(kb_handle* h) {
   cudaFree(h->xch.halo_mark); cudaFree(h->xch.publish); cudaFree(h->xch.ghost_keys); cudaFree(h->xch.ghost_vals);
   cudaFree(h->obj_depth); cudaFree(h->obj_label); cudaFree(h->d_object); cudaFree(h->d_flags_local);
   if (h->h_oscal) cudaFreeHost(h->h_oscal);
-  cudaFree(h->trk_ids); cudaFree(h->trk_export); cudaFree(h->trk_counts); cudaFree(h->trk_sums); cudaFree(h->trk_present);
+  cudaFree(h->trk_ids); cudaFree(h->trk_export); cudaFree(h->trk_counts); cudaFree(h->trk_sums); cudaFree(h->trk_present); cudaFree(h->trk_idlist);
   cudaFree(h->trk_keys); cudaFree(h->trk_of); cudaFree(h->trk_inter);
   cudaFree(h->stg_depth); cudaFree(h->stg_label); cudaFree(h->stg_mask); cudaFree(h->stg_object);
   cudaFree(h->stg_vertex); cudaFree(h->d_pixel_gidx); cudaFree(h->d_pixel_seed); cudaFree(h->d_removed);
@@ -1544,12 +1546,15 @@ int kb_get_object_clusters(kb_handle* h, int32_t* id_semantic_count, int32_t* pi
   return KB_OK;
 }
 
-int kb_track_measurements(kb_handle* h, const kb_frame* f, const int32_t* id_image, int32_t max_id, float voxel_size,
-                          int32_t n_tracks, const int32_t* track_offsets, const int64_t* track_voxels_xyz,
+int kb_track_measurements(kb_handle* h, const kb_frame* f, const int32_t* id_image, int32_t n_clusters,
+                          const int32_t* cluster_ids, float voxel_size, int32_t n_tracks, const int32_t* track_offsets, const int64_t* track_voxels_xyz,
                           int32_t* voxel_counts, int64_t* voxel_sums, int32_t* intersections, float* iou) {
   if (!h || !f || !id_image || (!f->depth && !f->depth_u16 && !f->vertex_world)) return fail(h, KB_ERR_INVALID, "null argument");
   if (!h->has_cam) return fail(h, KB_ERR_STATE, "kb_set_camera must be called first");
-  if (max_id < 1 || max_id > kTrackMaxIds) return fail(h, KB_ERR_INVALID, "max_id must be in 1..1022");
+  if (n_clusters < 1 || n_clusters > kTrackMaxIds) return fail(h, KB_ERR_INVALID, "n_clusters must be in 1..1022");
+  for (int i = 1; cluster_ids && i < n_clusters; ++i)
+    if (cluster_ids[i] <= cluster_ids[i - 1]) return fail(h, KB_ERR_INVALID, "cluster_ids must be strictly ascending");
+  const int max_id = n_clusters;  // rows
   if (!(voxel_size > 0.f)) return fail(h, KB_ERR_INVALID, "voxel_size must be positive");
   if (n_tracks < 0 || (n_tracks > 0 && (!track_offsets || !track_voxels_xyz))) return fail(h, KB_ERR_INVALID, "track lists missing");
   if (n_tracks > 0 && (track_offsets[0] != 0)) return fail(h, KB_ERR_INVALID, "track_offsets[0] must be 0");
@@ -1568,7 +1573,11 @@ int kb_track_measurements(kb_handle* h, const kb_frame* f, const int32_t* id_ima
   float R[9], t[3];
   poseToFloat(f->world_T_sensor, R, t, p.Rw, p.tw);
   p.W = c.width; p.H = c.height; p.fx = c.fx; p.fy = c.fy; p.cx = c.cx; p.cy = c.cy;
-  p.max_id = max_id;
+  p.n_ids = n_clusters;
+  if (cluster_ids) {
+    KB_CUDA(h, cudaMemcpyAsync(h->trk_idlist, cluster_ids, sizeof(int) * n_clusters, cudaMemcpyHostToDevice, h->stream));
+    p.id_list = h->trk_idlist;
+  }
   p.inv_voxel = 1.f / voxel_size;
   p.voxel_counts = h->trk_counts;
   p.sums = h->trk_sums;

@@ -5,7 +5,7 @@
 //
 //   T1  setupTrackMeasurementVoxels (khronos/src/active_window/tracking/max_iou_tracker.cpp:450-459): the voxels of a
 //       cluster are the set { grid.toIndex(vertex_map(pixel)) : pixel in cluster } at the tracker's own voxel size.
-//       Every pixel of the id image inserts (id, voxel) into an open-addressed table; the thread that creates an entry
+//       Every pixel of the id image inserts (cluster row + 1, voxel) into an open-addressed table; the thread that creates an entry
 //       adds it to the id's count and integer index sums (computeCentroid's voxel mode, :534-539, is the mean of the
 //       voxel centres = (sum / n + 0.5) * voxel_size; integer sums do not depend on the iteration order of the set).
 //   T2  computeIoUVoxels (:551-562): |cluster.voxels ∩ track.last_voxels| for every (cluster, track) pair: one thread
@@ -23,7 +23,7 @@ constexpr unsigned long long kTkEmpty = ~0ull;
 __global__ void tkInitKernel(MotionTable t, TrackParams p) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < kMsCount) t.scalars[i] = 0;
-  if (i < p.max_id) {
+  if (i < p.n_ids) {
     p.voxel_counts[i] = 0;
     p.sums[3 * i] = 0; p.sums[3 * i + 1] = 0; p.sums[3 * i + 2] = 0;
   }
@@ -33,8 +33,22 @@ __global__ void tkInitKernel(MotionTable t, TrackParams p) {
 __global__ void tkInsertKernel(MotionTable t, const __grid_constant__ TrackParams p) {
   const int px = blockIdx.x * blockDim.x + threadIdx.x;
   if (px >= p.W * p.H) return;
-  const int id = __ldg(&p.ids[px]);
-  if (id < 1 || id > p.max_id) return;
+  const int value = __ldg(&p.ids[px]);
+  int id;  // row + 1
+  if (p.id_list) {  // sparse ids (2D object images keep their creation-order ids): position in the ascending list
+    int lo = 0, hi = p.n_ids - 1;
+    id = 0;
+    while (lo <= hi) {
+      const int mid = (lo + hi) >> 1;
+      const int m = __ldg(&p.id_list[mid]);
+      if (m == value) { id = mid + 1; break; }
+      if (m < value) lo = mid + 1; else hi = mid - 1;
+    }
+    if (id == 0) return;
+  } else {
+    id = value;
+    if (id < 1 || id > p.n_ids) return;
+  }
   float wx, wy, wz;
   if (p.vertex) {
     wx = __ldg(&p.vertex[3 * px]); wy = __ldg(&p.vertex[3 * px + 1]); wz = __ldg(&p.vertex[3 * px + 2]);
@@ -104,7 +118,7 @@ __global__ void tkExportKernel(MotionTable t, unsigned long long* out) {
 
 void launchTrackVoxelize(const MotionTable& t, const TrackParams& p, cudaStream_t s) {
   const int slots = static_cast<int>(t.mask) + 1;
-  const int n_init = slots > p.max_id ? slots : p.max_id;
+  const int n_init = slots > p.n_ids ? slots : p.n_ids;
   tkInitKernel<<<(n_init + 255) / 256, 256, 0, s>>>(t, p);
   tkInsertKernel<<<(p.W * p.H + 255) / 256, 256, 0, s>>>(t, p);
 }

@@ -5,7 +5,7 @@
 
 namespace kb {
 
-constexpr int kTrackMaxIds = 1022;    // cluster ids 1..1022 (10 bits of the table key; 1023 is left out so no key is ~0)
+constexpr int kTrackMaxIds = 1022;    // clusters per call: row + 1 takes 10 bits of the table key (1023 is left out so no key is ~0)
 constexpr int kTrackCoordBits = 18;   // +-131072 tracker voxels per axis (13 km at the default 0.1 m)
 
 struct TrackParams {
@@ -15,18 +15,19 @@ struct TrackParams {
   const float* depth;          // device
   const float* vertex;         // device world-frame vertex map or null (computed from depth + pose)
   const int32_t* ids;          // device H*W cluster-id image (dynamic_image / object_image)
-  int max_id;                  // ids 1..max_id are clusters
+  int n_ids;                   // number of clusters (rows), <= kTrackMaxIds
+  const int* id_list;          // device, strictly ascending pixel values of the clusters, or null: values 1..n_ids
   float inv_voxel;             // 1 / MaxIoUTracker::Config::voxel_size
-  int* voxel_counts;           // device [max_id]   : |cluster.voxels|
-  unsigned long long* sums;    // device [max_id*3] : sum of the voxel indices (two's complement)
+  int* voxel_counts;           // device [n_ids]   : |cluster.voxels|
+  unsigned long long* sums;    // device [n_ids*3] : sum of the voxel indices (two's complement)
 };
 
-// T0-T1: fills the (shared) table with the unique (cluster id, voxel) pairs of the id image, per-id counts / index sums.
+// T0-T1: fills the (shared) table with the unique (cluster row + 1, voxel) pairs of the id image, per-id counts / index sums.
 // Leaves the number of entries in t.scalars[kMsOccupied] and the entry slots in t.occupied.
 void launchTrackVoxelize(const MotionTable& t, const TrackParams& p, cudaStream_t s);
 
-// T2: intersections[(id-1)*n_tracks + track] = |cluster(id).voxels ∩ track.last_voxels|. track_keys: one packed voxel key
-// per track voxel (trackVoxelKey), track_of: its track index; present_ids: the ids with voxel_counts > 0.
+// T2: intersections[row*n_tracks + track] = |cluster(row).voxels ∩ track.last_voxels|. track_keys: one packed voxel key
+// per track voxel (trackVoxelKey), track_of: its track index; present_ids: row + 1 of the clusters with voxel_counts > 0.
 void launchTrackIntersect(const MotionTable& t, const unsigned long long* track_keys, const int* track_of, int n_track_voxels,
                           const int* present_ids, int n_present, int n_tracks, int* intersections, cudaStream_t s);
 

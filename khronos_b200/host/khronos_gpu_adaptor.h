@@ -263,13 +263,16 @@ struct TrackMeasurements {
   std::vector<int64_t> voxel_sums;     // [max_id * 3]          centroid = (sums / count + 0.5) * voxel_size
   std::vector<int32_t> intersections;  // [max_id * n_tracks]
   std::vector<float> iou;              // [max_id * n_tracks]   computeIoUVoxels
-  float iouOf(int cluster_id, int track) const { return iou[static_cast<size_t>(cluster_id - 1) * n_tracks + track]; }
+  float iouOf(int row, int track) const { return iou[static_cast<size_t>(row) * n_tracks + track]; }  // row = position in cluster_ids, or id - 1
 };
 
+// cluster_ids: the MeasurementCluster::id values of the image's clusters, ascending (2D object images keep their
+// creation-order ids), or empty for ids 1..max_id (dynamic clusters, 3D object clusters).
 inline TrackMeasurements measureTracks(GpuVolumetricMap& map, const khronos::FrameData& data, const cv::Mat& id_image,
-                                       int max_id, float tracker_voxel_size,
+                                       int max_id, const std::vector<int32_t>& cluster_ids, float tracker_voxel_size,
                                        const std::vector<std::vector<int64_t>>& track_last_voxels_xyz) {
   TrackMeasurements out;
+  if (!cluster_ids.empty()) max_id = static_cast<int>(cluster_ids.size());
   out.max_id = max_id;
   out.n_tracks = static_cast<int>(track_last_voxels_xyz.size());
   std::vector<int32_t> offsets(1, 0);
@@ -285,7 +288,8 @@ inline TrackMeasurements measureTracks(GpuVolumetricMap& map, const khronos::Fra
   out.iou.resize(static_cast<size_t>(max_id) * out.n_tracks);
   kb_frame f = makeFrame(data.input, nullptr, nullptr, 0);
   map.setSensor(data.input.getSensor());
-  check(kb_track_measurements(map.handle(), &f, id_image.ptr<int32_t>(), max_id, tracker_voxel_size, out.n_tracks,
+  check(kb_track_measurements(map.handle(), &f, id_image.ptr<int32_t>(), max_id, cluster_ids.empty() ? nullptr : cluster_ids.data(),
+                              tracker_voxel_size, out.n_tracks,
                               out.n_tracks ? offsets.data() : nullptr, out.n_tracks ? flat.data() : nullptr,
                               out.voxel_counts.data(), out.voxel_sums.data(),
                               out.n_tracks ? out.intersections.data() : nullptr, out.n_tracks ? out.iou.data() : nullptr),

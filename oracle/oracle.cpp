@@ -960,7 +960,7 @@ void Oracle::detectObjects(const kb_object_detector_config& cfg, const kb_frame&
 
 // ---- track measurements: MaxIoUTracker, track_by = voxels (tracking/max_iou_tracker.cpp, fully in-tree) --------
 
-void Oracle::trackMeasurements(const kb_frame& f, const int32_t* id_image, int max_id, float voxel_size, int n_tracks,
+void Oracle::trackMeasurements(const kb_frame& f, const int32_t* id_image, int max_id, const int32_t* cluster_ids, float voxel_size, int n_tracks,
                                const int32_t* track_offsets, const int64_t* track_voxels_xyz) {
   track_result_ = TrackMeasurements{};
   if (!has_cam_) { error_ = "camera not set"; return; }
@@ -974,8 +974,14 @@ void Oracle::trackMeasurements(const kb_frame& f, const int32_t* id_image, int m
   for (int v = 0; v < H; ++v)
     for (int u = 0; u < W; ++u) {
       const size_t px = static_cast<size_t>(v) * W + u;
-      const int id = id_image[px];
-      if (id < 1 || id > max_id) continue;
+      int id = id_image[px];  // -> row + 1
+      if (cluster_ids) {
+        const int32_t* it = std::find(cluster_ids, cluster_ids + max_id, id);
+        if (it == cluster_ids + max_id) continue;
+        id = static_cast<int>(it - cluster_ids) + 1;
+      } else if (id < 1 || id > max_id) {
+        continue;
+      }
       float p[3];
       if (f.vertex_world) {
         p[0] = f.vertex_world[px * 3]; p[1] = f.vertex_world[px * 3 + 1]; p[2] = f.vertex_world[px * 3 + 2];

@@ -112,14 +112,14 @@ class Oracle {
   const std::vector<ObjectCluster>& objectClusters() const { return object_clusters_; }
 
   // Track measurements: khronos::MaxIoUTracker, track_by = voxels (tracking/max_iou_tracker.cpp:450-459, :534-539,
-  // :551-562) for every cluster id 1..max_id of an id image. Results: per id the voxel set (ordered z, y, x), and per
+  // :551-562) for the clusters of an id image (pixel values cluster_ids[0..max_id), or 1..max_id when cluster_ids is null). Results: per id the voxel set (ordered z, y, x), and per
   // (id, track) the intersection count and the IoU float of :562.
   struct TrackMeasurements {
     std::vector<std::vector<GIdx>> voxels;  // [max_id]
     std::vector<int32_t> intersections;     // [max_id * n_tracks]
     std::vector<float> iou;                 // [max_id * n_tracks]
   };
-  void trackMeasurements(const kb_frame& f, const int32_t* id_image, int max_id, float voxel_size, int n_tracks,
+  void trackMeasurements(const kb_frame& f, const int32_t* id_image, int max_id, const int32_t* cluster_ids, float voxel_size, int n_tracks,
                          const int32_t* track_offsets, const int64_t* track_voxels_xyz);
   const TrackMeasurements& trackResult() const { return track_result_; }
 

@@ -164,8 +164,8 @@ int ko_get_object_clusters(ko_handle* h, int32_t* id_semantic_count, int32_t* pi
   return KB_OK;
 }
 
-int ko_track_measurements(ko_handle* h, const kb_frame* f_in, const int32_t* id_image, int32_t max_id, float voxel_size,
-                          int32_t n_tracks, const int32_t* track_offsets, const int64_t* track_voxels_xyz,
+int ko_track_measurements(ko_handle* h, const kb_frame* f_in, const int32_t* id_image, int32_t max_id,
+                          const int32_t* cluster_ids, float voxel_size, int32_t n_tracks, const int32_t* track_offsets, const int64_t* track_voxels_xyz,
                           int32_t* voxel_counts, int64_t* voxel_sums, int32_t* intersections, float* iou) {
   if (!h || !f_in || !id_image || (!f_in->depth && !f_in->depth_u16 && !f_in->vertex_world)) return KB_ERR_INVALID;
   if (max_id < 1 || max_id > 1022 || !(voxel_size > 0.f) || n_tracks < 0) return KB_ERR_INVALID;
@@ -174,7 +174,9 @@ int ko_track_measurements(ko_handle* h, const kb_frame* f_in, const int32_t* id_
     if (track_offsets[t + 1] < track_offsets[t]) return KB_ERR_INVALID;
   kb_frame tmp;
   const kb_frame* f = expandCompact(h, f_in, &tmp);
-  h->o->trackMeasurements(*f, id_image, max_id, voxel_size, n_tracks, track_offsets, track_voxels_xyz);
+  for (int i = 1; cluster_ids && i < max_id; ++i)
+    if (cluster_ids[i] <= cluster_ids[i - 1]) return KB_ERR_INVALID;
+  h->o->trackMeasurements(*f, id_image, max_id, cluster_ids, voxel_size, n_tracks, track_offsets, track_voxels_xyz);
   if (!h->o->ok()) return fail(h, KB_ERR_STATE);
   const auto& r = h->o->trackResult();
   for (int i = 0; i < max_id; ++i) {

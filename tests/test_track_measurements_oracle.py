@@ -8,8 +8,12 @@ import harness as hs
 from test_object_detection_oracle import OBJECTS, scene_frame
 
 
-def numpy_measurements(cam, pose, depth, ids, max_id, voxel_size, tracks, vertex=None):
-    """Python sets, as the reference's GlobalIndexSet; fp32 arithmetic in the oracle's order."""
+def numpy_measurements(cam, pose, depth, ids, clusters, voxel_size, tracks, vertex=None):
+    """Python sets, as the reference's GlobalIndexSet; fp32 arithmetic in the oracle's order. clusters: n (pixel values
+    1..n) or the list of the clusters' pixel values."""
+    values = list(range(1, clusters + 1)) if isinstance(clusters, (int, np.integer)) else [int(c) for c in clusters]
+    row = {v: i for i, v in enumerate(values)}
+    max_id = len(values)
     H, W = ids.shape
     f32 = np.float32
     if vertex is None:
@@ -22,8 +26,8 @@ def numpy_measurements(cam, pose, depth, ids, max_id, voxel_size, tracks, vertex
     inv = f32(1.0) / f32(voxel_size)
     g = np.floor(vertex * inv).astype(np.int64)
     sets = [set() for _ in range(max_id)]
-    for vv, uu in zip(*np.nonzero((ids >= 1) & (ids <= max_id))):
-        sets[ids[vv, uu] - 1].add(tuple(g[vv, uu]))
+    for vv, uu in zip(*np.nonzero(np.isin(ids, values))):
+        sets[row[int(ids[vv, uu])]].add(tuple(g[vv, uu]))
     counts = np.array([len(s) for s in sets], np.int32)
     sums = np.array([np.sum(np.array(sorted(s), np.int64).reshape(-1, 3), 0) for s in sets], np.int64)
     inter = np.zeros((max_id, len(tracks)), np.int32)
@@ -49,8 +53,8 @@ def compare(res, lists, want):
         np.testing.assert_array_equal(a, b)
 
 
-def object_ids(h, d, l, pose, use_3d=True):
-    cfg = capi.default_object_detector_config(OBJECTS, use_3d=use_3d, min_cluster_size=10)
+def object_ids(h, d, l, pose, use_3d=True, min_size=10):
+    cfg = capi.default_object_detector_config(OBJECTS, use_3d=use_3d, min_cluster_size=min_size)
     img, n = h.detect_objects(cfg, h.make_frame(d, pose, 1_000_000_000, label=l))
     return img, n
 
@@ -109,6 +113,30 @@ def test_oracle_matches_numpy_on_object_clusters(oracle_lib):
     r = h.track_measurements(f, ids, n, 0.1, tracks)
     assert r["iou"][0, 0] == 1.0 and r["intersections"][0, 0] == len(lists[0])
     assert r["intersections"][2, 2] == len(lists[2][::2])
+
+
+def test_oracle_sparse_cluster_ids_of_the_2d_detector(oracle_lib):
+    """The 2D detector keeps creation-order ids (filterClusters does not renumber), so the surviving ids are sparse and
+    can be large: the caller passes them as a list and gets one row per list entry."""
+    cam, pose, d, l = scene_frame(scale=2, noise_seed=9)
+    h = hs.make_handle(oracle_lib, "ko_", cam=cam)
+    ids, n = object_ids(h, d, l, pose, use_3d=False, min_size=2)
+    cids = [c["id"] for c in h.get_object_clusters()]
+    assert len(cids) == n >= 2 and cids == sorted(cids) and cids[-1] > 1022   # sparse, beyond the dense id range
+    f = h.make_frame(d, pose, 1, label=l)
+    h.track_measurements(f, ids, cids, 0.1, [])
+    lists = h.get_cluster_voxels(n)
+    tracks = [lists[0], lists[-1][::3], np.array([[0, 0, 0]])]
+    r = h.track_measurements(f, ids, cids, 0.1, tracks)
+    compare(r, h.get_cluster_voxels(n), numpy_measurements(cam, pose, d, ids, cids, 0.1, tracks))
+    assert r["iou"][0, 0] == 1.0 and r["voxel_counts"].all()
+    # a sub-list: the other clusters' pixels belong to no row
+    sub = cids[1::2]
+    r = h.track_measurements(f, ids, sub, 0.1, tracks)
+    compare(r, h.get_cluster_voxels(len(sub)), numpy_measurements(cam, pose, d, ids, sub, 0.1, tracks))
+    import pytest
+    with pytest.raises(capi.KbError):
+        h.track_measurements(f, ids, cids[::-1], 0.1, tracks)   # not ascending
 
 
 def test_oracle_vertex_map_and_2d_ids(oracle_lib):

@@ -20,7 +20,8 @@ def check(o, g, fo, fg, ids, max_id, voxel_size, tracks, what, ids_g=None):
     for k in ("voxel_counts", "voxel_sums", "intersections"):
         np.testing.assert_array_equal(ro[k], rg[k], err_msg=f"{what}: {k}")
     np.testing.assert_array_equal(ro["iou"].view(np.uint32), rg["iou"].view(np.uint32), err_msg=f"{what}: iou")
-    lo, lg = o.get_cluster_voxels(max_id), g.get_cluster_voxels(max_id)
+    rows = max_id if isinstance(max_id, (int, np.integer)) else len(max_id)
+    lo, lg = o.get_cluster_voxels(rows), g.get_cluster_voxels(rows)
     for c, (a, b) in enumerate(zip(lo, lg)):
         np.testing.assert_array_equal(a, b, err_msg=f"{what}: voxels of cluster {c + 1}")
     return ro, lo
@@ -40,22 +41,27 @@ def test_track_measurements_match_oracle_on_object_clusters(oracle_lib, product_
     cam, pose, d, l = scene_frame(scale=2, noise_seed=5)
     o = hs.make_handle(oracle_lib, "ko_", cam=cam)
     g = hs.make_handle(product_lib, "kb_", cam=cam)
-    cfg = capi.default_object_detector_config(OBJECTS, use_3d=use_3d, min_cluster_size=10)
+    # 2D mode keeps creation-order ids (sparse, here beyond 1022): those clusters are named by an id list
+    cfg = capi.default_object_detector_config(OBJECTS, use_3d=use_3d, min_cluster_size=10 if use_3d else 2)
     ids, n = o.detect_objects(cfg, o.make_frame(d, pose, 1_000_000_000, label=l))
     ids_g, _ = g.detect_objects(cfg, g.make_frame(d, pose, 1_000_000_000, label=l))
     np.testing.assert_array_equal(ids, ids_g)
-    max_id = int(ids.max())
-    assert max_id >= 3
+    cids = [c["id"] for c in o.get_object_clusters()]
+    assert cids == [c["id"] for c in g.get_object_clusters()] and len(cids) == n >= 3
+    assert (cids == list(range(1, n + 1))) == use_3d and (use_3d or cids[-1] > 1022)
+    clusters = n if use_3d else cids
     fo, fg = o.make_frame(d, pose, 1_000_000_000, label=l), g.make_frame(d, pose, 1_000_000_000, label=l)
-    _, lists = check(o, g, fo, fg, ids, max_id, 0.1, [], "no tracks")
+    _, lists = check(o, g, fo, fg, ids, clusters, 0.1, [], "no tracks")
     tracks = make_tracks(lists, np.random.default_rng(2))
     for vs in (0.1, 0.07, 0.25):
-        r, _ = check(o, g, fo, fg, ids, max_id, vs, tracks, f"3d={use_3d} voxel_size={vs}")
-    r, lists = check(o, g, fo, fg, ids, max_id, 0.1, tracks, "again")
-    first = next(i for i, v in enumerate(lists) if len(v))
-    assert r["iou"][first, 0] == 1.0
-    # fewer ids than the image holds: the others are ignored
-    check(o, g, fo, fg, ids, 2, 0.1, tracks, "max_id 2")
+        r, _ = check(o, g, fo, fg, ids, clusters, vs, tracks, f"3d={use_3d} voxel_size={vs}")
+    r, lists = check(o, g, fo, fg, ids, clusters, 0.1, tracks, "again")
+    assert r["iou"][0, 0] == 1.0 and r["voxel_counts"].all()
+    # fewer clusters than the image holds: the other pixels belong to no row
+    check(o, g, fo, fg, ids, 2, 0.1, tracks, "ids 1..2")
+    check(o, g, fo, fg, ids, cids[1::2], 0.07, tracks, "id sub-list")
+    r1, _ = check(o, g, fo, fg, ids, cids, 0.1, tracks, "id list")
+    np.testing.assert_array_equal(r1["iou"].view(np.uint32), r["iou"].view(np.uint32))
 
 
 def test_track_measurements_full_resolution_device_frames_vertex_map_and_compact_depth(oracle_lib, product_lib):
@@ -132,6 +138,8 @@ def test_track_measurement_argument_errors_and_stale_results(product_lib):
             g.track_measurements(f, ids, bad, 0.1, [])
     with pytest.raises(capi.KbError):
         g.track_measurements(f, ids, 4, 0.0, [])
+    with pytest.raises(capi.KbError):
+        g.track_measurements(f, ids, [5, 3], 0.1, [])   # not ascending
     r = g.track_measurements(f, ids, 4, 0.1, [np.array([[1, 2, 3]])])   # no cluster pixel at all
     assert not r["voxel_counts"].any() and not r["intersections"].any()
     assert all(len(v) == 0 for v in g.get_cluster_voxels(4))

@@ -54,3 +54,6 @@ timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none --csv --lo
   -k regex:everFree\|halo\|ghost\|exportPending\|motionFinalize\|motionLookup\|os.*Kernel\|o2.*Kernel \
   python -m pytest "tests/test_sharded_pipeline.py::test_product_shards_equal_unsharded_oracle[2-2.0]" tests/test_zz_object_detection.py -m gpu -q -x -p no:cacheprovider \
   > gpurun_out/ncu_sharded.log 2>&1; tail -3 gpurun_out/ncu_sharded.log
+echo "== 5. track measurements (written after the round's GPU minutes were spent): parity on hardware + latency of the detector / tracker calls"
+timeout 300 python -m pytest tests/test_zz_track_measurements.py -m gpu -q --tb=short -p no:cacheprovider > gpurun_out/zz_tracks.log 2>&1; tail -3 gpurun_out/zz_tracks.log
+timeout 200 python tools/time_detectors.py > gpurun_out/time_detectors.log 2>&1; tail -2 gpurun_out/time_detectors.log
