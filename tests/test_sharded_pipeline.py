@@ -199,9 +199,3 @@ def test_oracle_shards_random_walk(oracle_lib, nshards, conn, seed):
 def test_oracle_shards_peer_memory_exchange(oracle_lib):
     """The peer-memory variants of the exchanges (producers store into every shard's buffers) give the same maps."""
     run_sharded_vs_unsharded(oracle_lib, oracle_lib, "ko_", 3, "cpu", scale=8, n=22, peers=True)
-
-
-@pytest.mark.gpu
-@pytest.mark.parametrize("nshards", [2, 4])
-def test_product_shards_peer_memory_exchange(oracle_lib, product_lib, nshards):
-    run_sharded_vs_unsharded(oracle_lib, product_lib, "kb_", nshards, "cuda", sep=2.0, peers=True)

@@ -5,7 +5,7 @@
 set -u
 mkdir -p gpurun_out
 echo "== 1. GPU tests not yet run on hardware (object detection, experimental fuse variants)"
-timeout 300 python -m pytest tests/test_zz_object_detection.py tests/test_zz_fuse_variants.py -m gpu -q --tb=short -p no:cacheprovider \
+timeout 300 python -m pytest tests/test_zz_edge_cases.py tests/test_zz_object_detection.py tests/test_zzy_peer_exchange.py tests/test_zzz_fuse_variants.py -m gpu -q --tb=short -p no:cacheprovider \
   > gpurun_out/zz_tests.log 2>&1; tail -5 gpurun_out/zz_tests.log
 echo "== 2. headline bench, default vs compacted heaviest-first item lists"
 timeout 200 python bench.py --no-e2e --no-cpu-baseline > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err
