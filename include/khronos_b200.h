@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define KB_ABI_VERSION 4
+#define KB_ABI_VERSION 5
 
 typedef enum kb_status {
   KB_OK = 0,
@@ -312,6 +312,45 @@ int kb_track_measurements(kb_handle* h, const kb_frame* frame, const int32_t* id
  * offsets[n_clusters + 1] and the flat (x, y, z) list, clusters in row order, voxels ascending in (z, y, x). Valid until the
  * handle's next motion / object detection or track measurement. NULL pointers are skipped. */
 int kb_get_cluster_voxels(kb_handle* h, int32_t* offsets, int64_t* voxels_xyz, int32_t capacity, int32_t* total);
+
+/* ---- ray index -------------------------------------------------------------------------------
+ * khronos::RayVerificator (khronos/include/khronos/backend/change_detection/ray_verificator.h:58-258,
+ * khronos/src/backend/change_detection/ray_verificator.cpp): the measurement rays of the scene graph (sensor position at
+ * a pose-graph node -> mesh vertex, with the stamp of the node) hashed into the coarse blocks they pass through, and the
+ * per-point query "which rays through this block saw the point / saw through it". Its own handle: it lives in the
+ * backend, independent of the active-window map. The scene-graph side (which vertex gets rays from which pose nodes,
+ * computeVertexSources :278-330, RayLookup) stays with the caller, who passes endpoints and stamps as arrays. */
+typedef struct kb_ray_index kb_ray_index;
+typedef struct kb_ray_config {   /* RayVerificator::Config (ray_verificator.h:68-100) */
+  float block_size;              /* m, default 1.0 */
+  float radial_tolerance;        /* m, default 0.1 */
+  float depth_tolerance;         /* m, default 0.1 */
+} kb_ray_config;
+int kb_rays_create(const kb_ray_config* config, int device, kb_ray_index** out);  /* all three must be > 0 (:56-61) */
+int kb_rays_destroy(kb_ray_index* h);
+const char* kb_rays_last_error(const kb_ray_index* h);
+int kb_rays_clear(kb_ray_index* h);                                               /* setDsg's reset (:150-166) */
+int kb_rays_size(kb_ray_index* h, int32_t* n_rays, int64_t* n_block_entries);
+/* addVertices' ray loop + addRayToHash (:264-273, :326-350) for n new rays (indices continue from the rays already
+ * held): sources / targets = lookup.getSource / getTarget (x, y, z float), timestamps = Ray::timestamp. Marches each
+ * ray in steps of block_size / 4 and adds it to every block entered. observed_blocks_xyz (optional, capacity
+ * max_observed blocks) receives the distinct blocks the NEW rays pass through (addVertices' return value, what
+ * updateDsg intersects with vertices_in_block_ / objects_in_block_ :176-189), ascending in (z, y, x); if it is too
+ * small the call fails with KB_ERR_CAPACITY, *n_observed holds the needed size and no ray is added. */
+int kb_rays_add(kb_ray_index* h, int32_t n, const float* sources_xyz, const float* targets_xyz, const uint64_t* timestamps,
+                int32_t* observed_blocks_xyz, int32_t max_observed, int32_t* n_observed);
+/* The rays are deformable: check() reads their endpoints from the current scene graph (:88-100) while the hash keeps
+ * the blocks computed when they were added. Replaces the endpoints of ALL rays (n_rays must match). */
+int kb_rays_set_endpoints(kb_ray_index* h, int32_t n_rays, const float* sources_xyz, const float* targets_xyz);
+int kb_rays_rehash(kb_ray_index* h);                                              /* recomputeHash (:314-324) */
+/* check (:66-146) for n_points points, each with its own [earliest, latest] stamp window: counts[2*i] = rays that saw
+ * through point i (CheckResult::absent), counts[2*i+1] = rays that ended at it (present); rays outside the window,
+ * further than radial_tolerance from the point or occluded before it count for neither. *total_stamps = sum of counts. */
+int kb_rays_check(kb_ray_index* h, int32_t n_points, const float* points_xyz, const uint64_t* earliest, const uint64_t* latest,
+                  int32_t* counts, int64_t* total_stamps);
+/* The stamps of the last kb_rays_check: for every point its absent stamps, then its present stamps, each ascending (the
+ * reference returns them in unordered_set iteration order; the consumers bucket them, ray_change_detector.cpp:72-81). */
+int kb_rays_get_stamps(kb_ray_index* h, uint64_t* stamps, int64_t capacity);
 
 /* ---- sharded per-frame pipeline (new in this build; SURVEY.md §8e exchange steps 1 and 2) -----------------------
  * With kb_set_shard(rank, nranks > 1) a handle holds only the blocks it owns. Fusion (K0/K1/K1b), K2, K2r and K4 are

@@ -17,6 +17,7 @@ import numpy as np
 KB_MAX_LABELS = 64
 KB_OK = 0
 KB_ERR_NO_DEVICE = 4
+KB_ERR_INVALID, KB_ERR_CUDA, KB_ERR_CAPACITY, KB_ERR_STATE = 1, 2, 3, 5
 INTERP_NEAREST, INTERP_BILINEAR, INTERP_ADAPTIVE = 0, 1, 2
 SEM_NONE, SEM_MLE, SEM_BINARY = 0, 1, 2
 MEM_HOST, MEM_DEVICE, MEM_HOST_ASYNC = 0, 1, 2
@@ -507,3 +508,102 @@ def load_product_library() -> C.CDLL:
             f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(nvcc, sm_100a). khronos_b200 has no CPU fallback.")
     return C.CDLL(path, mode=C.RTLD_GLOBAL)
+
+
+# ---- ray index (khronos::RayVerificator; include/khronos_b200.h "ray index") --------------------------------------------
+class RayConfig(C.Structure):
+    _fields_ = [("block_size", C.c_float), ("radial_tolerance", C.c_float), ("depth_tolerance", C.c_float)]
+
+
+def default_ray_config(block_size=1.0, radial_tolerance=0.1, depth_tolerance=0.1) -> RayConfig:
+    """RayVerificator::Config defaults (ray_verificator.h:68-100)."""
+    return RayConfig(block_size, radial_tolerance, depth_tolerance)
+
+
+class RayIndex:
+    """kb_rays_* (product, prefix "kb_") or ko_rays_* (oracle, prefix "ko_") through ctypes."""
+
+    def __init__(self, lib, prefix, cfg: RayConfig, device=0):
+        self._lib, self._p, self._h = lib, prefix, C.c_void_p()
+        st = self._fn("create")(C.byref(cfg), device, C.byref(self._h))
+        if st != KB_OK:
+            self._h = C.c_void_p()
+            raise KbError(st, "rays_create failed (no CUDA device?)" if st == KB_ERR_NO_DEVICE else "rays_create failed")
+
+    def _fn(self, name):
+        f = getattr(self._lib, self._p + "rays_" + name)
+        f.restype = C.c_int
+        return f
+
+    def _check(self, st):
+        if st != KB_OK:
+            e = getattr(self._lib, self._p + "rays_last_error")
+            e.restype = C.c_char_p
+            raise KbError(st, (e(self._h) or b"").decode())
+
+    def close(self):
+        if self._h:
+            self._fn("destroy")(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def clear(self):
+        self._check(self._fn("clear")(self._h))
+
+    def size(self):
+        n, e = C.c_int32(0), C.c_int64(0)
+        self._check(self._fn("size")(self._h, C.byref(n), C.byref(e)))
+        return n.value, e.value
+
+    def add(self, sources, targets, stamps, want_observed=True):
+        """Adds rays; returns the (k, 3) int32 array of blocks the new rays pass through (ascending z, y, x)."""
+        s = np.ascontiguousarray(sources, np.float32).reshape(-1, 3)
+        t = np.ascontiguousarray(targets, np.float32).reshape(-1, 3)
+        ts = np.ascontiguousarray(stamps, np.uint64)
+        n = len(s)
+        f = self._fn("add")
+        if not want_observed:
+            self._check(f(self._h, n, C.c_void_p(s.ctypes.data), C.c_void_p(t.ctypes.data), C.c_void_p(ts.ctypes.data), None, 0, None))
+            return None
+        cap, nobs = 64, C.c_int32(0)
+        while True:
+            obs = np.zeros((cap, 3), np.int32)
+            st = f(self._h, n, C.c_void_p(s.ctypes.data), C.c_void_p(t.ctypes.data), C.c_void_p(ts.ctypes.data),
+                   C.c_void_p(obs.ctypes.data), cap, C.byref(nobs))
+            if st == KB_ERR_CAPACITY and nobs.value > cap:
+                cap = nobs.value
+                continue
+            self._check(st)
+            return obs[:nobs.value].copy()
+
+    def set_endpoints(self, sources, targets):
+        s = np.ascontiguousarray(sources, np.float32).reshape(-1, 3)
+        t = np.ascontiguousarray(targets, np.float32).reshape(-1, 3)
+        self._check(self._fn("set_endpoints")(self._h, len(s), C.c_void_p(s.ctypes.data), C.c_void_p(t.ctypes.data)))
+
+    def rehash(self):
+        self._check(self._fn("rehash")(self._h))
+
+    def check(self, points, earliest=0, latest=2**64 - 1):
+        """Returns (counts (n, 2) int32 [absent, present], list of (absent stamps, present stamps) per point)."""
+        p = np.ascontiguousarray(points, np.float32).reshape(-1, 3)
+        n = len(p)
+        lo = np.ascontiguousarray(np.broadcast_to(np.asarray(earliest, np.uint64), (n,)))
+        hi = np.ascontiguousarray(np.broadcast_to(np.asarray(latest, np.uint64), (n,)))
+        counts = np.zeros((max(n, 1), 2), np.int32)
+        total = C.c_int64(0)
+        self._check(self._fn("check")(self._h, n, C.c_void_p(p.ctypes.data), C.c_void_p(lo.ctypes.data), C.c_void_p(hi.ctypes.data),
+                                      C.c_void_p(counts.ctypes.data), C.byref(total)))
+        stamps = np.zeros(max(total.value, 1), np.uint64)
+        self._check(self._fn("get_stamps")(self._h, C.c_void_p(stamps.ctypes.data), C.c_int64(total.value)))
+        out, o = [], 0
+        for i in range(n):
+            a, b = int(counts[i, 0]), int(counts[i, 1])
+            out.append((stamps[o:o + a].copy(), stamps[o + a:o + a + b].copy()))
+            o += a + b
+        return counts[:n], out

@@ -1,0 +1,81 @@
+"""GPU parity of the ray index (kb_rays_*: khronos::RayVerificator on the device) against the CPU
+oracle, which tests/test_ray_index_oracle.py pins against a numpy restatement of ray_verificator.cpp. Observed blocks,
+block-entry counts, per-point absent / present counts and the stamp lists must be identical (the classification is a
+chain of fp32 comparisons: any arithmetic difference would flip verdicts)."""
+import numpy as np
+import pytest
+
+from khronos_b200 import capi
+from test_ray_index_oracle import compare_checks, query_points, random_rays
+
+pytestmark = pytest.mark.gpu
+f32 = np.float32
+
+
+def both(oracle_lib, product_lib, cfg):
+    return capi.RayIndex(oracle_lib, "ko_", cfg), capi.RayIndex(product_lib, "kb_", cfg)
+
+
+def check_same(o, g, pts, lo=0, hi=2**64 - 1):
+    co, lo_ = o.check(pts, lo, hi)
+    cg, lg = g.check(pts, lo, hi)
+    np.testing.assert_array_equal(co, cg)
+    compare_checks((cg, lg), lo_)
+    return co
+
+
+@pytest.mark.parametrize("block_size,radial,depth_tol", [(1.0, 0.1, 0.1), (0.5, 0.05, 0.2), (2.0, 0.3, 0.05)])
+def test_ray_index_matches_oracle(oracle_lib, product_lib, block_size, radial, depth_tol):
+    rng = np.random.default_rng(8)
+    o, g = both(oracle_lib, product_lib, capi.default_ray_config(block_size, radial, depth_tol))
+    src, tgt, ts = random_rays(rng, 3000, n_poses=12)
+    for a, b in ((0, 1), (1, 700), (700, 3000)):   # incremental updates (updateDsg), buffers grow
+        np.testing.assert_array_equal(o.add(src[a:b], tgt[a:b], ts[a:b]), g.add(src[a:b], tgt[a:b], ts[a:b]))
+        assert o.size() == g.size()
+        pts = query_points(rng, src[:b], tgt[:b], 500)
+        check_same(o, g, pts)
+    pts = query_points(rng, src, tgt, 4000)
+    c = check_same(o, g, pts)
+    assert c[:, 0].sum() > 200 and c[:, 1].sum() > 200
+    lo = rng.integers(1_000_000_000, 5_000_000_000, len(pts)).astype(np.uint64)
+    check_same(o, g, pts, lo, lo + np.uint64(2_000_000_000))
+    # deformation (loop closure): endpoints move, the hash stays; then recomputeHash
+    src2 = src + rng.normal(0, 0.05, src.shape).astype(f32)
+    tgt2 = tgt + rng.normal(0, 0.15, tgt.shape).astype(f32)
+    o.set_endpoints(src2, tgt2); g.set_endpoints(src2, tgt2)
+    check_same(o, g, pts)
+    o.rehash(); g.rehash()
+    assert o.size() == g.size()
+    check_same(o, g, pts)
+    o.clear(); g.clear()
+    assert g.size() == (0, 0)
+    assert not check_same(o, g, pts[:50]).any()
+
+
+def test_ray_index_degenerate_inputs(oracle_lib, product_lib):
+    o, g = both(oracle_lib, product_lib, capi.default_ray_config())
+    pts = np.array([[1, 1, 1], [2, 2, 1], [3, 2, 1], [-4.5, -0.2, 0.3]], f32)
+    assert not check_same(o, g, pts).any()                       # no rays yet
+    s = np.array([[1, 1, 1], [2, 2, 1], [-0.5, -0.5, 0.5], [0, 0, 0]], f32)
+    t = np.array([[1, 1, 1], [5, 2, 1], [-7.5, 0.1, 0.2], [0, 0, 40.0]], f32)   # zero-length ray, negative blocks, long ray
+    np.testing.assert_array_equal(o.add(s, t, [5, 6, 7, 8]), g.add(s, t, [5, 6, 7, 8]))
+    assert o.size() == g.size()
+    check_same(o, g, pts)                                        # includes points at ray sources (depth 0 -> NaN tests)
+    check_same(o, g, np.zeros((0, 3), f32))
+    many = np.repeat(pts, 300, 0)                                # more points than warps in flight
+    check_same(o, g, many)
+    # many rays through one block: lists longer than a warp
+    rng = np.random.default_rng(0)
+    s = np.tile(np.array([[0.5, 0.5, 0.5]], f32), (200, 1))
+    t = s + rng.normal(0, 1, (200, 3)).astype(f32) * f32(3)
+    ts = rng.integers(1, 50, 200).astype(np.uint64)
+    np.testing.assert_array_equal(o.add(s, t, ts), g.add(s, t, ts))
+    q = (s + f32(0.8) * (t - s)).astype(f32)
+    c = check_same(o, g, q)
+    assert c.sum() > 100
+    with pytest.raises(capi.KbError):
+        g.add([[0, 0, np.nan]], [[1, 1, 1]], [1])
+    with pytest.raises(capi.KbError):
+        g.set_endpoints(s[:3], t[:3])
+    with pytest.raises(capi.KbError):
+        capi.RayIndex(product_lib, "kb_", capi.default_ray_config(radial_tolerance=0.0))

@@ -57,3 +57,5 @@ timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none --csv --lo
 echo "== 5. track measurements (written after the round's GPU minutes were spent): parity on hardware + latency of the detector / tracker calls"
 timeout 300 python -m pytest tests/test_zz_track_measurements.py -m gpu -q --tb=short -p no:cacheprovider > gpurun_out/zz_tracks.log 2>&1; tail -3 gpurun_out/zz_tracks.log
 timeout 200 python tools/time_detectors.py > gpurun_out/time_detectors.log 2>&1; tail -2 gpurun_out/time_detectors.log
+echo "== 6. ray index (RayVerificator on the device; written without GPU minutes): parity on hardware"
+timeout 300 python -m pytest tests/test_zz_ray_index.py -m gpu -q --tb=short -p no:cacheprovider > gpurun_out/zz_rays.log 2>&1; tail -3 gpurun_out/zz_rays.log
