@@ -173,7 +173,16 @@ class SymmMemPeers:
         t.zero_()
         hdl = self.symm_mem.rendezvous(t, self.group)
         self.handles.append(hdl)
-        return [t], [[int(p) for p in hdl.buffer_ptrs]]
+        # buffer_ptrs are allocation bases; a tensor carved out of a pool sits `offset` bytes into it. Resolve which
+        # convention this PyTorch build uses against the one pointer we know (our own) instead of assuming.
+        ptrs = [int(p) for p in hdl.buffer_ptrs]
+        off = int(getattr(hdl, "offset", 0) or 0)
+        own = ptrs[int(hdl.rank)]
+        if own + off == t.data_ptr():
+            ptrs = [p + off for p in ptrs]
+        elif own != t.data_ptr():
+            raise RuntimeError("symmetric memory: cannot relate buffer_ptrs to the tensor's data_ptr")
+        return [t], [ptrs]
 
     def barrier(self):
         self.handles[0].barrier()
