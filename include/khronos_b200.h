@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define KB_ABI_VERSION 5
+#define KB_ABI_VERSION 6
 
 typedef enum kb_status {
   KB_OK = 0,
@@ -339,6 +339,20 @@ int kb_rays_size(kb_ray_index* h, int32_t* n_rays, int64_t* n_block_entries);
  * small the call fails with KB_ERR_CAPACITY, *n_observed holds the needed size and no ray is added. */
 int kb_rays_add(kb_ray_index* h, int32_t n, const float* sources_xyz, const float* targets_xyz, const uint64_t* timestamps,
                 int32_t* observed_blocks_xyz, int32_t max_observed, int32_t* n_observed);
+/* RayVerificator::Config::RayPolicy (ray_verificator.h:84-92); kRandom / kRandom3 draw from rand_r and are not offered. */
+enum { KB_RAYS_FIRST = 0, KB_RAYS_LAST = 1, KB_RAYS_FIRST_AND_LAST = 2, KB_RAYS_MIDDLE = 3, KB_RAYS_ALL = 4 };
+/* addVertices (:222-276) for n_vertices new mesh vertices (global indices vertex_index_base + i): per vertex the pose
+ * nodes chosen by computeVertexSources (:278-330) from the ascending pose stamps (timestamps_) — upper_bound(first_seen),
+ * lower_bound(last_seen - active_window_duration), lower_bound of their mean, or all poses in between — each giving one
+ * ray pose position -> vertex with the pose's stamp; then kb_rays_add. The selection (binary searches) runs on the
+ * host, the march on the device. Rays are appended vertex by vertex, pose indices ascending within a vertex. */
+int kb_rays_add_vertices(kb_ray_index* h, int32_t policy, float active_window_duration, int32_t n_poses, const uint64_t* pose_stamps,
+                         const float* pose_positions_xyz, int32_t n_vertices, int32_t vertex_index_base, const float* vertices_xyz,
+                         const uint64_t* first_seen, const uint64_t* last_seen, int32_t* observed_blocks_xyz, int32_t max_observed,
+                         int32_t* n_observed, int32_t* n_rays_added);
+/* Ray::source_node (as index into the pose arrays), Ray::target_index and Ray::timestamp of all rays (-1 ids for rays
+ * added through kb_rays_add): what the caller gathers new endpoints with after a deformation. NULL pointers are skipped. */
+int kb_rays_get_ray_ids(kb_ray_index* h, int32_t* pose_index, int32_t* vertex_index, uint64_t* timestamps, int32_t capacity);
 /* The rays are deformable: check() reads their endpoints from the current scene graph (:88-100) while the hash keeps
  * the blocks computed when they were added. Replaces the endpoints of ALL rays (n_rays must match). */
 int kb_rays_set_endpoints(kb_ray_index* h, int32_t n_rays, const float* sources_xyz, const float* targets_xyz);

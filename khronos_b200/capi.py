@@ -520,6 +520,9 @@ def default_ray_config(block_size=1.0, radial_tolerance=0.1, depth_tolerance=0.1
     return RayConfig(block_size, radial_tolerance, depth_tolerance)
 
 
+RAYS_FIRST, RAYS_LAST, RAYS_FIRST_AND_LAST, RAYS_MIDDLE, RAYS_ALL = range(5)
+
+
 class RayIndex:
     """kb_rays_* (product, prefix "kb_") or ko_rays_* (oracle, prefix "ko_") through ctypes."""
 
@@ -580,6 +583,32 @@ class RayIndex:
                 continue
             self._check(st)
             return obs[:nobs.value].copy()
+
+    def add_vertices(self, policy, pose_stamps, pose_positions, vertices, first_seen, last_seen, vertex_index_base=0,
+                     active_window_duration=0.0):
+        """kb_rays_add_vertices; returns (observed blocks (k, 3), number of rays added)."""
+        ps = np.ascontiguousarray(pose_stamps, np.uint64)
+        pp = np.ascontiguousarray(pose_positions, np.float32).reshape(-1, 3)
+        vx = np.ascontiguousarray(vertices, np.float32).reshape(-1, 3)
+        fs, ls = np.ascontiguousarray(first_seen, np.uint64), np.ascontiguousarray(last_seen, np.uint64)
+        f = self._fn("add_vertices")
+        cap, nobs, nadd = 256, C.c_int32(0), C.c_int32(0)
+        while True:
+            obs = np.zeros((cap, 3), np.int32)
+            st = f(self._h, int(policy), C.c_float(active_window_duration), len(ps), C.c_void_p(ps.ctypes.data), C.c_void_p(pp.ctypes.data),
+                   len(vx), int(vertex_index_base), C.c_void_p(vx.ctypes.data), C.c_void_p(fs.ctypes.data), C.c_void_p(ls.ctypes.data),
+                   C.c_void_p(obs.ctypes.data), cap, C.byref(nobs), C.byref(nadd))
+            if st == KB_ERR_CAPACITY and nobs.value > cap:
+                cap = nobs.value
+                continue
+            self._check(st)
+            return obs[:nobs.value].copy(), nadd.value
+
+    def ray_ids(self):
+        n, _ = self.size()
+        pose, vert, ts = np.zeros(max(n, 1), np.int32), np.zeros(max(n, 1), np.int32), np.zeros(max(n, 1), np.uint64)
+        self._check(self._fn("get_ray_ids")(self._h, C.c_void_p(pose.ctypes.data), C.c_void_p(vert.ctypes.data), C.c_void_p(ts.ctypes.data), n))
+        return pose[:n], vert[:n], ts[:n]
 
     def set_endpoints(self, sources, targets):
         s = np.ascontiguousarray(sources, np.float32).reshape(-1, 3)

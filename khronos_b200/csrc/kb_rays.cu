@@ -246,6 +246,8 @@ struct kb_ray_index {
   float* d_points = nullptr; unsigned long long* d_early = nullptr; unsigned long long* d_late = nullptr;
   int* d_pt_counts = nullptr; long long* d_pt_offsets = nullptr; size_t cap_points = 0;
   unsigned long long* d_out = nullptr; size_t cap_out = 0;
+  // scene-graph ids of the rays added through kb_rays_add_vertices (Ray::source_node as pose index, Ray::target_index); -1 otherwise
+  std::vector<int32_t> ray_pose, ray_vertex;
   // last check
   std::vector<uint64_t> result_stamps;
   bool have_result = false;
@@ -354,6 +356,8 @@ int kb_rays_clear(kb_ray_index* h) {
   h->n_pairs = 0;
   h->csr_valid = false;
   h->have_result = false;
+  h->ray_pose.clear();
+  h->ray_vertex.clear();
   return KB_OK;
 }
 
@@ -438,6 +442,82 @@ int kb_rays_add(kb_ray_index* h, int32_t n, const float* sources_xyz, const floa
   h->n_pairs = run;
   h->csr_valid = false;
   h->have_result = false;
+  h->ray_pose.resize(total, -1);
+  h->ray_vertex.resize(total, -1);
+  return KB_OK;
+}
+
+int kb_rays_add_vertices(kb_ray_index* h, int32_t policy, float active_window_duration, int32_t n_poses, const uint64_t* pose_stamps,
+                         const float* pose_positions_xyz, int32_t n_vertices, int32_t vertex_index_base, const float* vertices_xyz,
+                         const uint64_t* first_seen, const uint64_t* last_seen, int32_t* observed_blocks_xyz, int32_t max_observed,
+                         int32_t* n_observed, int32_t* n_rays_added) {
+  if (!h || n_poses < 0 || n_vertices < 0 || (n_poses > 0 && (!pose_stamps || !pose_positions_xyz)) ||
+      (n_vertices > 0 && (!vertices_xyz || !first_seen || !last_seen)))
+    return rfail(h, KB_ERR_INVALID, "null argument");
+  if (policy < KB_RAYS_FIRST || policy > KB_RAYS_ALL) return rfail(h, KB_ERR_INVALID, "unsupported ray policy (the random policies are not reproducible)");
+  for (int i = 1; i < n_poses; ++i)
+    if (pose_stamps[i] < pose_stamps[i - 1]) return rfail(h, KB_ERR_INVALID, "pose stamps must be ascending");
+  if (n_observed) *n_observed = 0;
+  if (n_rays_added) *n_rays_added = 0;
+  // addVertices (:222-276): last_seen is shifted back by the active-window duration (:246-251), unsigned like the reference
+  const uint64_t offset_ns = active_window_duration > 0.f ? static_cast<uint64_t>(active_window_duration * 1e9) : 0ull;
+  const uint64_t* tb = pose_stamps;
+  const uint64_t* te = pose_stamps + n_poses;
+  std::vector<float> src, dst;
+  std::vector<uint64_t> ts;
+  std::vector<int32_t> pose_of, vertex_of;
+  std::vector<size_t> sources;
+  for (int v = 0; v < n_vertices; ++v) {
+    const uint64_t first = first_seen[v], last = last_seen[v] - offset_ns;
+    sources.clear();
+    // computeVertexSources (:278-330); the result set is listed ascending
+    if (policy == KB_RAYS_FIRST || policy == KB_RAYS_FIRST_AND_LAST) {
+      const uint64_t* it = std::upper_bound(tb, te, first);
+      if (it != te) sources.push_back(static_cast<size_t>(it - tb));
+    }
+    if (policy == KB_RAYS_LAST || policy == KB_RAYS_FIRST_AND_LAST) {
+      const uint64_t* it = std::lower_bound(tb, te, last);
+      if (it != te) sources.push_back(static_cast<size_t>(it - tb));
+    }
+    if (policy == KB_RAYS_MIDDLE) {
+      const uint64_t stamp = (last + first) / 2;
+      const uint64_t* it = std::lower_bound(tb, te, stamp);
+      if (it != te) sources.push_back(static_cast<size_t>(it - tb));
+    }
+    if (policy == KB_RAYS_ALL) {
+      const uint64_t* lo = std::upper_bound(tb, te, first);
+      const uint64_t* hi = std::lower_bound(tb, te, last);
+      for (const uint64_t* it = lo; it < hi; ++it) sources.push_back(static_cast<size_t>(it - tb));
+    }
+    std::sort(sources.begin(), sources.end());
+    sources.erase(std::unique(sources.begin(), sources.end()), sources.end());
+    for (size_t sidx : sources) {
+      for (int a = 0; a < 3; ++a) { src.push_back(pose_positions_xyz[3 * sidx + a]); dst.push_back(vertices_xyz[3 * static_cast<size_t>(v) + a]); }
+      ts.push_back(pose_stamps[sidx]);
+      pose_of.push_back(static_cast<int32_t>(sidx));
+      vertex_of.push_back(vertex_index_base + v);
+    }
+  }
+  const int n = static_cast<int>(ts.size());
+  const int before = h->n_rays;
+  const int st = kb_rays_add(h, n, src.data(), dst.data(), ts.data(), observed_blocks_xyz, max_observed, n_observed);
+  if (st != KB_OK) return st;
+  for (int i = 0; i < n; ++i) { h->ray_pose[before + i] = pose_of[i]; h->ray_vertex[before + i] = vertex_of[i]; }
+  if (n_rays_added) *n_rays_added = n;
+  return KB_OK;
+}
+
+int kb_rays_get_ray_ids(kb_ray_index* h, int32_t* pose_index, int32_t* vertex_index, uint64_t* timestamps, int32_t capacity) {
+  if (!h) return KB_ERR_INVALID;
+  if (capacity < h->n_rays) return rfail(h, KB_ERR_CAPACITY, "ray id buffer too small");
+  if (h->n_rays == 0) return KB_OK;
+  if (pose_index) std::memcpy(pose_index, h->ray_pose.data(), sizeof(int32_t) * h->n_rays);
+  if (vertex_index) std::memcpy(vertex_index, h->ray_vertex.data(), sizeof(int32_t) * h->n_rays);
+  if (timestamps) {
+    KR_CUDA(h, cudaSetDevice(h->device));
+    KR_CUDA(h, cudaMemcpyAsync(timestamps, h->d_stamps, sizeof(uint64_t) * h->n_rays, cudaMemcpyDeviceToHost, h->stream));
+    KR_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
   return KB_OK;
 }
 
@@ -465,8 +545,11 @@ int kb_rays_rehash(kb_ray_index* h) {
   KR_CUDA(h, cudaMemcpyAsync(dst.data(), h->d_dst, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, h->stream));
   KR_CUDA(h, cudaMemcpyAsync(ts.data(), h->d_stamps, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost, h->stream));
   KR_CUDA(h, cudaStreamSynchronize(h->stream));
+  std::vector<int32_t> pose = h->ray_pose, vertex = h->ray_vertex;
   kb_rays_clear(h);
-  return kb_rays_add(h, n, src.data(), dst.data(), ts.data(), nullptr, 0, nullptr);
+  const int st = kb_rays_add(h, n, src.data(), dst.data(), ts.data(), nullptr, 0, nullptr);
+  if (st == KB_OK) { h->ray_pose = pose; h->ray_vertex = vertex; }
+  return st;
 }
 
 int kb_rays_check(kb_ray_index* h, int32_t n_points, const float* points_xyz, const uint64_t* earliest, const uint64_t* latest,

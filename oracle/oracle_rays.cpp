@@ -40,6 +40,7 @@ struct ko_ray_index {
   std::vector<V3> src, dst;            // lookup.getSource / getTarget of every ray (current scene graph)
   std::vector<uint64_t> stamp;         // Ray::timestamp
   std::map<BIdx, std::set<size_t>> block_seen_by_rays;  // unordered in the reference; order does not matter
+  std::vector<int32_t> ray_pose, ray_vertex;  // Ray::source_node (pose index) / Ray::target_index, -1 for plain rays
   std::vector<uint64_t> result;
   bool have_result = false;
   int64_t entries = 0;
@@ -85,6 +86,7 @@ const char* ko_rays_last_error(const ko_ray_index*) { return ""; }
 int ko_rays_clear(ko_ray_index* h) {
   if (!h) return KB_ERR_INVALID;
   h->src.clear(); h->dst.clear(); h->stamp.clear(); h->block_seen_by_rays.clear(); h->entries = 0; h->have_result = false;
+  h->ray_pose.clear(); h->ray_vertex.clear();
   return KB_OK;
 }
 
@@ -124,9 +126,76 @@ int ko_rays_add(ko_ray_index* h, int32_t n, const float* s, const float* t, cons
     h->src.push_back({s[3 * i], s[3 * i + 1], s[3 * i + 2]});
     h->dst.push_back({t[3 * i], t[3 * i + 1], t[3 * i + 2]});
     h->stamp.push_back(ts[i]);
+    h->ray_pose.push_back(-1);
+    h->ray_vertex.push_back(-1);
     h->addRayToHash(h->src.size() - 1, nullptr);
   }
   h->have_result = false;
+  return KB_OK;
+}
+
+// addVertices (:222-276) + computeVertexSources (:278-330)
+int ko_rays_add_vertices(ko_ray_index* h, int32_t policy, float active_window_duration, int32_t n_poses, const uint64_t* pose_stamps,
+                         const float* pose_positions, int32_t n_vertices, int32_t vertex_index_base, const float* vertices,
+                         const uint64_t* first_seen_in, const uint64_t* last_seen_in, int32_t* observed_xyz, int32_t max_observed,
+                         int32_t* n_observed, int32_t* n_rays_added) {
+  if (!h || n_poses < 0 || n_vertices < 0 || policy < KB_RAYS_FIRST || policy > KB_RAYS_ALL) return KB_ERR_INVALID;
+  if ((n_poses > 0 && (!pose_stamps || !pose_positions)) || (n_vertices > 0 && (!vertices || !first_seen_in || !last_seen_in))) return KB_ERR_INVALID;
+  const std::vector<uint64_t> timestamps_(pose_stamps, pose_stamps + n_poses);
+  if (!std::is_sorted(timestamps_.begin(), timestamps_.end())) return KB_ERR_INVALID;
+  if (n_observed) *n_observed = 0;
+  if (n_rays_added) *n_rays_added = 0;
+  std::vector<uint64_t> last_seen(last_seen_in, last_seen_in + n_vertices);
+  if (active_window_duration > 0) {
+    const uint64_t offset_ns = active_window_duration * 1e9;   // :247
+    for (auto& stamp : last_seen) stamp -= offset_ns;
+  }
+  std::vector<float> s, t;
+  std::vector<uint64_t> ts;
+  std::vector<int32_t> pose_of, vertex_of;
+  for (int i = 0; i < n_vertices; ++i) {
+    const size_t first = first_seen_in[i], last = last_seen[i];
+    std::set<size_t> result;  // unordered_set in the reference
+    if (policy == KB_RAYS_FIRST || policy == KB_RAYS_FIRST_AND_LAST) {
+      const auto it = std::upper_bound(timestamps_.begin(), timestamps_.end(), first);
+      if (it != timestamps_.end()) result.insert(it - timestamps_.begin());
+    }
+    if (policy == KB_RAYS_LAST || policy == KB_RAYS_FIRST_AND_LAST) {
+      const auto it = std::lower_bound(timestamps_.begin(), timestamps_.end(), last);
+      if (it != timestamps_.end()) result.insert(it - timestamps_.begin());
+    }
+    if (policy == KB_RAYS_MIDDLE) {
+      const size_t stamp = (last + first) / 2;
+      const auto it = std::lower_bound(timestamps_.begin(), timestamps_.end(), stamp);
+      if (it != timestamps_.end()) result.insert(it - timestamps_.begin());
+    }
+    if (policy == KB_RAYS_ALL) {
+      const auto it_lower = std::upper_bound(timestamps_.begin(), timestamps_.end(), first);
+      const auto it_upper = std::lower_bound(timestamps_.begin(), timestamps_.end(), last);
+      for (auto it = it_lower; it < it_upper; ++it) result.insert(it - timestamps_.begin());
+    }
+    for (const size_t source_index : result) {
+      for (int a = 0; a < 3; ++a) { s.push_back(pose_positions[3 * source_index + a]); t.push_back(vertices[3 * static_cast<size_t>(i) + a]); }
+      ts.push_back(timestamps_[source_index]);
+      pose_of.push_back(static_cast<int32_t>(source_index));
+      vertex_of.push_back(vertex_index_base + i);
+    }
+  }
+  const size_t before = h->src.size();
+  const int st = ko_rays_add(h, static_cast<int32_t>(ts.size()), s.data(), t.data(), ts.data(), observed_xyz, max_observed, n_observed);
+  if (st != KB_OK) return st;
+  for (size_t k = 0; k < ts.size(); ++k) { h->ray_pose[before + k] = pose_of[k]; h->ray_vertex[before + k] = vertex_of[k]; }
+  if (n_rays_added) *n_rays_added = static_cast<int32_t>(ts.size());
+  return KB_OK;
+}
+
+int ko_rays_get_ray_ids(ko_ray_index* h, int32_t* pose_index, int32_t* vertex_index, uint64_t* timestamps, int32_t capacity) {
+  if (!h) return KB_ERR_INVALID;
+  const size_t n = h->src.size();
+  if (static_cast<size_t>(std::max(capacity, 0)) < n) return KB_ERR_CAPACITY;
+  if (pose_index) std::copy(h->ray_pose.begin(), h->ray_pose.end(), pose_index);
+  if (vertex_index) std::copy(h->ray_vertex.begin(), h->ray_vertex.end(), vertex_index);
+  if (timestamps) std::copy(h->stamp.begin(), h->stamp.end(), timestamps);
   return KB_OK;
 }
 

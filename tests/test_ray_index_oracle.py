@@ -162,3 +162,74 @@ def test_oracle_matches_numpy(oracle_lib, block_size, radial, depth_tol):
     np.testing.assert_array_equal(r2.add(s2, t2, [5, 6]), ref2.add(s2, t2, [5, 6]))
     p2 = np.array([[1, 1, 1], [2, 2, 1], [3, 2, 1]], f32)
     compare_checks(r2.check(p2), ref2.check(p2, 0, 2**64 - 1))
+
+
+def np_vertex_sources(policy, stamps, first, last):
+    """computeVertexSources (ray_verificator.cpp:278-330) with numpy's searchsorted (upper_bound = side 'right',
+    lower_bound = side 'left'); the resulting set ascending."""
+    n, out = len(stamps), set()
+    def take(i):
+        if i < n:
+            out.add(int(i))
+    if policy in (capi.RAYS_FIRST, capi.RAYS_FIRST_AND_LAST):
+        take(np.searchsorted(stamps, first, "right"))
+    if policy in (capi.RAYS_LAST, capi.RAYS_FIRST_AND_LAST):
+        take(np.searchsorted(stamps, last, "left"))
+    if policy == capi.RAYS_MIDDLE:
+        take(np.searchsorted(stamps, np.uint64((int(last) + int(first)) % 2**64 // 2), "left"))
+    if policy == capi.RAYS_ALL:
+        out.update(range(int(np.searchsorted(stamps, first, "right")), int(np.searchsorted(stamps, last, "left"))))
+    return sorted(out)
+
+
+def mesh_scenario(rng, n_poses=10, n_vertices=200):
+    stamps = (np.uint64(1_000_000_000) + np.arange(n_poses, dtype=np.uint64) * np.uint64(400_000_000))
+    poses = np.stack([np.linspace(2, 8, n_poses), np.linspace(3, 5, n_poses), np.full(n_poses, 1.2)], 1).astype(f32)
+    _, verts, _ = random_rays(rng, n_vertices)
+    first = rng.integers(500_000_000, 4_500_000_000, n_vertices).astype(np.uint64)
+    last = first + rng.integers(0, 2_000_000_000, n_vertices).astype(np.uint64)
+    first[::11] = stamps[rng.integers(0, n_poses, len(first[::11]))]     # exactly on a pose stamp: upper vs lower bound
+    last[::13] = stamps[rng.integers(0, n_poses, len(last[::13]))]
+    return stamps, poses, verts, first, last
+
+
+@pytest.mark.parametrize("policy", [capi.RAYS_FIRST, capi.RAYS_LAST, capi.RAYS_FIRST_AND_LAST, capi.RAYS_MIDDLE, capi.RAYS_ALL])
+@pytest.mark.parametrize("aw", [0.0, 0.75])
+def test_oracle_add_vertices_matches_numpy(oracle_lib, policy, aw):
+    rng = np.random.default_rng(policy)
+    stamps, poses, verts, first, last = mesh_scenario(rng)
+    cfg = capi.default_ray_config()
+    r, ref = capi.RayIndex(oracle_lib, "ko_", cfg), NumpyRays(cfg)
+    # first half of the mesh, then the rest (updateDsg), with more poses known by then
+    obs_all = []
+    for a, b, npz in ((0, 90, 7), (90, 200, 10)):
+        offset = np.uint64(int(np.float32(aw) * 1e9)) if aw > 0 else np.uint64(0)
+        want_s, want_t, want_ts, want_pose, want_vert = [], [], [], [], []
+        for v in range(a, b):
+            with np.errstate(over="ignore"):
+                shifted = np.uint64(last[v] - offset)
+            for k in np_vertex_sources(policy, stamps[:npz], first[v], shifted):
+                want_s.append(poses[k]); want_t.append(verts[v]); want_ts.append(stamps[k]); want_pose.append(k); want_vert.append(v)
+        obs, nadd = r.add_vertices(policy, stamps[:npz], poses[:npz], verts[a:b], first[a:b], last[a:b], vertex_index_base=a,
+                                   active_window_duration=aw)
+        assert nadd == len(want_ts)
+        want_obs = ref.add(np.array(want_s, f32).reshape(-1, 3), np.array(want_t, f32).reshape(-1, 3), want_ts)
+        np.testing.assert_array_equal(obs, want_obs)
+        obs_all.append((want_pose, want_vert, want_ts))
+    pose, vert, ts = r.ray_ids()
+    np.testing.assert_array_equal(pose, np.concatenate([np.array(o[0], np.int32) for o in obs_all]))
+    np.testing.assert_array_equal(vert, np.concatenate([np.array(o[1], np.int32) for o in obs_all]))
+    np.testing.assert_array_equal(ts, np.concatenate([np.array(o[2], np.uint64) for o in obs_all]))
+    assert len(ts) > 60
+    pts = query_points(rng, np.array(ref.src), np.array(ref.dst), 200)
+    compare_checks(r.check(pts), ref.check(pts, 0, 2**64 - 1))
+    # plain rays carry no ids; rehash keeps them
+    r.add([[0, 0, 0]], [[1, 1, 1]], [7])
+    r.rehash()
+    pose2, vert2, _ = r.ray_ids()
+    assert pose2[-1] == -1 and vert2[-1] == -1
+    np.testing.assert_array_equal(pose2[:-1], pose)
+    with pytest.raises(capi.KbError):
+        r.add_vertices(5, stamps, poses, verts, first, last)             # random policies are not offered
+    with pytest.raises(capi.KbError):
+        r.add_vertices(policy, stamps[::-1].copy(), poses, verts, first, last)

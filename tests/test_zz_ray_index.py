@@ -79,3 +79,32 @@ def test_ray_index_degenerate_inputs(oracle_lib, product_lib):
         g.set_endpoints(s[:3], t[:3])
     with pytest.raises(capi.KbError):
         capi.RayIndex(product_lib, "kb_", capi.default_ray_config(radial_tolerance=0.0))
+
+
+@pytest.mark.parametrize("policy", [capi.RAYS_FIRST_AND_LAST, capi.RAYS_MIDDLE, capi.RAYS_ALL])
+def test_ray_index_add_vertices_matches_oracle(oracle_lib, product_lib, policy):
+    """addVertices: rays chosen per mesh vertex from the pose stamps (computeVertexSources), then hashed."""
+    from test_ray_index_oracle import mesh_scenario
+    rng = np.random.default_rng(20 + policy)
+    stamps, poses, verts, first, last = mesh_scenario(rng, n_poses=14, n_vertices=1500)
+    o, g = both(oracle_lib, product_lib, capi.default_ray_config())
+    for a, b, npz, aw in ((0, 600, 9, 0.0), (600, 1500, 14, 0.5)):
+        ro = o.add_vertices(policy, stamps[:npz], poses[:npz], verts[a:b], first[a:b], last[a:b], a, aw)
+        rg = g.add_vertices(policy, stamps[:npz], poses[:npz], verts[a:b], first[a:b], last[a:b], a, aw)
+        np.testing.assert_array_equal(ro[0], rg[0])
+        assert ro[1] == rg[1] and o.size() == g.size()
+    for x, y in zip(o.ray_ids(), g.ray_ids()):
+        np.testing.assert_array_equal(x, y)
+    pose, vert, _ = g.ray_ids()
+    pts = (verts[rng.integers(0, len(verts), 2000)] + rng.normal(0, 0.03, (2000, 3))).astype(f32)
+    c = check_same(o, g, pts)
+    assert c.sum() > 300
+    # deformation through the ids: every pose / vertex moves, endpoints are re-gathered by the caller
+    poses2 = poses + rng.normal(0, 0.05, poses.shape).astype(f32)
+    verts2 = verts + rng.normal(0, 0.1, verts.shape).astype(f32)
+    o.set_endpoints(poses2[pose], verts2[vert]); g.set_endpoints(poses2[pose], verts2[vert])
+    check_same(o, g, pts)
+    g.rehash(); o.rehash()
+    for x, y in zip(o.ray_ids(), g.ray_ids()):
+        np.testing.assert_array_equal(x, y)
+    check_same(o, g, pts)
