@@ -491,4 +491,89 @@ inline void mirrorBack(GpuVolumetricMap& gmap, hydra::VolumetricMap& host, bool 
 inline void GpuActiveWindowCore::mirrorBackImpl(hydra::VolumetricMap& host_map) { mirrorBack(map_, host_map, /*updated_only=*/true); }
 #endif
 
+// khronos::RayVerificator's measurement store (backend/change_detection/ray_verificator.h:58-258) over a kb_ray_index:
+// same method names and result type; the scene-graph lookups (agent layer -> pose arrays, mesh -> vertex arrays) are done
+// by the caller, who passes plain arrays.
+class GpuRayVerificator {
+ public:
+  struct CheckResult {  // RayVerificator::CheckResult (:104-115)
+    std::vector<uint64_t> absent;
+    std::vector<uint64_t> present;
+    void merge(const CheckResult& other) {
+      absent.insert(absent.end(), other.absent.begin(), other.absent.end());
+      present.insert(present.end(), other.present.begin(), other.present.end());
+    }
+  };
+
+  explicit GpuRayVerificator(const kb_ray_config& config, int device = 0) {
+    const int st = kb_rays_create(&config, device, &h_);
+    if (st != KB_OK) throw std::runtime_error(st == KB_ERR_NO_DEVICE ? "GpuRayVerificator: no CUDA device" : "GpuRayVerificator: invalid config");
+  }
+  ~GpuRayVerificator() { kb_rays_destroy(h_); }
+  GpuRayVerificator(const GpuRayVerificator&) = delete;
+  GpuRayVerificator& operator=(const GpuRayVerificator&) = delete;
+
+  void clear() { rcheck(kb_rays_clear(h_), "kb_rays_clear"); }  // setDsg (:150-166)
+
+  // addVertices (:222-276) for the mesh vertices [first_vertex, first_vertex + n): returns the observed blocks (x, y, z triples).
+  std::vector<int32_t> addVertices(int policy, float active_window_duration, const std::vector<uint64_t>& pose_stamps,
+                                   const std::vector<float>& pose_positions_xyz, int first_vertex, int n, const float* vertices_xyz,
+                                   const uint64_t* first_seen, const uint64_t* last_seen) {
+    std::vector<int32_t> observed(3 * 1024);
+    int32_t n_obs = 0, n_added = 0;
+    for (;;) {
+      const int st = kb_rays_add_vertices(h_, policy, active_window_duration, static_cast<int32_t>(pose_stamps.size()), pose_stamps.data(),
+                                          pose_positions_xyz.data(), n, first_vertex, vertices_xyz, first_seen, last_seen, observed.data(),
+                                          static_cast<int32_t>(observed.size() / 3), &n_obs, &n_added);
+      if (st == KB_ERR_CAPACITY && static_cast<size_t>(n_obs) > observed.size() / 3) { observed.resize(3 * static_cast<size_t>(n_obs)); continue; }
+      rcheck(st, "kb_rays_add_vertices");
+      break;
+    }
+    observed.resize(3 * static_cast<size_t>(n_obs));
+    return observed;
+  }
+
+  // The rays' scene-graph ids, to gather deformed endpoints with; then setEndpoints (what RayLookup reads at :88-100).
+  void rayIds(std::vector<int32_t>* pose_index, std::vector<int32_t>* vertex_index) const {
+    int32_t n = 0;
+    kb_rays_size(h_, &n, nullptr);
+    pose_index->resize(n);
+    vertex_index->resize(n);
+    rcheck(kb_rays_get_ray_ids(h_, pose_index->data(), vertex_index->data(), nullptr, n), "kb_rays_get_ray_ids");
+  }
+  void setEndpoints(const std::vector<float>& sources_xyz, const std::vector<float>& targets_xyz) {
+    rcheck(kb_rays_set_endpoints(h_, static_cast<int32_t>(sources_xyz.size() / 3), sources_xyz.data(), targets_xyz.data()), "kb_rays_set_endpoints");
+  }
+  void recomputeHash() { rcheck(kb_rays_rehash(h_), "kb_rays_rehash"); }  // :314-324
+
+  // check (:66-146) for a batch of points, each with its own stamp window (the per-vertex loops of
+  // RayObjectChangeDetector :127-137 and RayBackgroundChangeDetector::checkVertex :90-93 in one call).
+  std::vector<CheckResult> check(const std::vector<float>& points_xyz, const std::vector<uint64_t>& earliest,
+                                 const std::vector<uint64_t>& latest) const {
+    const int32_t n = static_cast<int32_t>(points_xyz.size() / 3);
+    std::vector<int32_t> counts(2 * static_cast<size_t>(n));
+    int64_t total = 0;
+    rcheck(kb_rays_check(h_, n, points_xyz.data(), earliest.data(), latest.data(), counts.data(), &total), "kb_rays_check");
+    std::vector<uint64_t> stamps(static_cast<size_t>(total));
+    rcheck(kb_rays_get_stamps(h_, stamps.data(), total), "kb_rays_get_stamps");
+    std::vector<CheckResult> out(static_cast<size_t>(n));
+    size_t o = 0;
+    for (int32_t i = 0; i < n; ++i) {
+      out[i].absent.assign(stamps.begin() + o, stamps.begin() + o + counts[2 * i]);
+      o += counts[2 * i];
+      out[i].present.assign(stamps.begin() + o, stamps.begin() + o + counts[2 * i + 1]);
+      o += counts[2 * i + 1];
+    }
+    return out;
+  }
+
+  kb_ray_index* handle() const { return h_; }
+
+ private:
+  void rcheck(int st, const char* what) const {
+    if (st != KB_OK) throw std::runtime_error(std::string(what) + ": " + kb_rays_last_error(h_));
+  }
+  kb_ray_index* h_ = nullptr;
+};
+
 }  // namespace khronos_b200

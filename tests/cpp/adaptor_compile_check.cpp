@@ -68,6 +68,28 @@ int main(int argc, char** argv) {
       std::printf("core_frames=%zu core_outputs=%d core_blocks_after_finish=%zu core_archived=%zu ", core.numFramesProcessed(), outputs,
                   out_map.getTsdfLayer().numBlocks(), archived_total + archived.size());
     }
+    if (argc > 4) {  // fourth argument: tracker measurements + ray verificator (tests/test_zz_ray_index.py)
+      // the left half of the wall is cluster 1, the right half cluster 2; the only track holds cluster 1's voxels
+      khronos::FrameData fr = frame;
+      cv::Mat ids(48, 64, 4);
+      for (int i = 0; i < 48 * 64; ++i) ids.ptr<int32_t>()[i] = (i % 64) < 32 ? 1 : 2;
+      TrackMeasurements m0 = measureTracks(gmap, fr, ids, 2, {}, 0.1f, {});
+      int32_t offs[3]; int32_t total = 0;
+      kb_get_cluster_voxels(gmap.handle(), offs, nullptr, 0, &total);
+      std::vector<int64_t> vox(3 * static_cast<size_t>(total));
+      kb_get_cluster_voxels(gmap.handle(), offs, vox.data(), total, &total);
+      std::vector<int64_t> track(vox.begin(), vox.begin() + 3 * offs[1]);
+      TrackMeasurements m1 = measureTracks(gmap, fr, ids, 2, {}, 0.1f, {track});
+      std::printf("track_counts=%d,%d track_iou=%.3f,%.3f ", m0.voxel_counts[0], m0.voxel_counts[1], m1.iouOf(0, 0), m1.iouOf(1, 0));
+      // one ray from the camera to the wall centre: the hit is present, a point half way is absent, one behind is occluded
+      GpuRayVerificator rays(kb_ray_config{1.f, 0.1f, 0.1f});
+      const float vertex[3] = {0.f, 0.f, 2.f};
+      const uint64_t first_seen[1] = {900000000ull}, last_seen[1] = {1100000000ull};
+      auto observed = rays.addVertices(KB_RAYS_MIDDLE, 0.f, {1000000000ull}, {0.f, 0.f, 0.f}, 0, 1, vertex, first_seen, last_seen);
+      auto res = rays.check({0.f, 0.f, 2.f, 0.f, 0.f, 1.f, 0.f, 0.f, 2.5f}, {0, 0, 0}, {~0ull, ~0ull, ~0ull});
+      std::printf("ray_blocks=%zu ray_verdicts=%zu%zu,%zu%zu,%zu%zu ", observed.size() / 3, res[0].absent.size(), res[0].present.size(),
+                  res[1].absent.size(), res[1].present.size(), res[2].absent.size(), res[2].present.size());
+    }
     GpuConnectedSemantics object_detector(dc);
     if (argc > 2) {  // second argument: also run the object detector (tests/test_zz_object_detection.py)
       object_detector.processInput(gmap, frame);

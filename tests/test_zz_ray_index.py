@@ -108,3 +108,24 @@ def test_ray_index_add_vertices_matches_oracle(oracle_lib, product_lib, policy):
     for x, y in zip(o.ray_ids(), g.ray_ids()):
         np.testing.assert_array_equal(x, y)
     check_same(o, g, pts)
+
+
+def test_adaptor_track_measurements_and_ray_verificator(tmp_path):
+    """measureTracks and GpuRayVerificator through the C++ host adaptor (known answers on the flat-wall frame)."""
+    import os
+    import subprocess
+    from harness import ROOT
+    csrc = os.path.join(ROOT, "khronos_b200", "csrc")
+    exe = str(tmp_path / "adaptor_check")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", os.path.join(ROOT, "tests", "cpp", "adaptor_compile_check.cpp"),
+                           "-o", exe, "-L", csrc, "-lkhronos_b200", f"-Wl,-rpath,{csrc}"])
+    out = subprocess.run([exe, "require-gpu", "objects", "core", "rays"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    fields = dict(kv.split("=") for kv in out.stdout.split())
+    # wall at z = 2 m, 64 x 48 px at f = 32: 4 m x 3 m -> 40 x 30 voxels of 0.1 m, half of them per cluster
+    a, b = (int(v) for v in fields["track_counts"].split(","))
+    assert a == b == 20 * 30
+    assert fields["track_iou"] == "1.000,0.000"
+    # ray (0,0,0) -> (0,0,2), 1 m blocks, step 0.25: samples z = 0.25 .. 2.25 -> blocks z = 0, 1, 2
+    assert int(fields["ray_blocks"]) == 3
+    assert fields["ray_verdicts"] == "01,10,00"    # hit: present; half way: absent; 0.5 m behind: occluded
