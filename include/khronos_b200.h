@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define KB_ABI_VERSION 6
+#define KB_ABI_VERSION 7
 
 typedef enum kb_status {
   KB_OK = 0,
@@ -283,6 +283,13 @@ int kb_detect_objects(kb_handle* h, const kb_object_detector_config* config, con
  * flat (u, v) pixel list in cluster order (order within a cluster unspecified). NULL pointers are skipped. */
 int kb_get_object_clusters(kb_handle* h, int32_t* id_semantic_count, int32_t* pixels_uv, int32_t* n_clusters,
                            int32_t* total_pixels);
+
+/* Input conversion (first half): the world-frame vertex map that upstream parseInputPacket builds for
+ * FrameData (call site active_window.cpp:275; InputData::vertex_map, read e.g. at free_space_motion_detector.cpp:174-175,
+ * max_iou_tracker.cpp:456): p_W = R * ((u-cx)/fx*d, (v-cy)/fy*d, d) + t in fp32 for every pixel (no validity test; d = 0
+ * gives the sensor position). vertex_world_out: H*W*3 floats in frame->memory space. The entry points of this library
+ * compute these points themselves; this is for host code that still wants the map. */
+int kb_compute_vertex_map(kb_handle* h, const kb_frame* frame, float* vertex_world_out);
 
 /* ---- track measurements (the step after the path) -------------------------------------------
  * khronos::MaxIoUTracker in its shipped mode track_by = "voxels" (khronos_ros/config/mapper/uHumans2.yaml:72). The

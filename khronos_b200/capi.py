@@ -416,6 +416,16 @@ class MapHandle:
             po += n
         return out
 
+    def compute_vertex_map(self, frame: Frame, out_ptr=None):
+        """kb_compute_vertex_map: (H, W, 3) float32 world-frame vertex map (host frames), or written to the device pointer
+        out_ptr for MEM_DEVICE frames."""
+        if out_ptr is not None:
+            self._check(self._fn("compute_vertex_map")(self._h, C.byref(frame), C.c_void_p(out_ptr)))
+            return None
+        out = np.zeros((self._camera.height, self._camera.width, 3), np.float32)
+        self._check(self._fn("compute_vertex_map")(self._h, C.byref(frame), C.c_void_p(out.ctypes.data)))
+        return out
+
     def track_measurements(self, frame: Frame, id_image, clusters, voxel_size: float = 0.1, tracks=()):
         """kb_track_measurements (MaxIoUTracker, track_by = voxels). id_image: H x W int32 host array for host frames, or a device pointer (int) for
         MEM_DEVICE frames. clusters: n (pixel values 1..n) or an ascending list of pixel values. tracks: sequence of

@@ -1648,6 +1648,35 @@ int kb_track_measurements(kb_handle* h, const kb_frame* f, const int32_t* id_ima
   return KB_OK;
 }
 
+int kb_compute_vertex_map(kb_handle* h, const kb_frame* f, float* vertex_world_out) {
+  if (!h || !f || !vertex_world_out || (!f->depth && !f->depth_u16)) return fail(h, KB_ERR_INVALID, "null argument");
+  if (!h->has_cam) return fail(h, KB_ERR_STATE, "kb_set_camera must be called first");
+  KB_CUDA(h, cudaSetDevice(h->device));
+  const kb_camera& c = h->cam;
+  const size_t px = static_cast<size_t>(c.width) * c.height;
+  int st;
+  if ((st = ensureObjectBuffers(h, px)) != KB_OK) return st;
+  TrackParams p{};
+  float R[9], t[3];
+  poseToFloat(f->world_T_sensor, R, t, p.Rw, p.tw);
+  p.W = c.width; p.H = c.height; p.fx = c.fx; p.fy = c.fy; p.cx = c.cx; p.cy = c.cy;
+  if (f->depth_u16) {
+    const uint16_t* d16 = nullptr;
+    if ((st = stage(h, f->depth_u16, h->mot_depth16, px, f->memory, &d16)) != KB_OK) return st;
+    launchExpandDepth(d16, f->depth_u16_scale, h->obj_depth, static_cast<int>(px), h->stream);
+    p.depth = h->obj_depth;
+  } else if ((st = stage(h, f->depth, h->obj_depth, px, f->memory, &p.depth)) != KB_OK) {
+    return st;
+  }
+  const bool device_out = f->memory == KB_MEM_DEVICE;
+  float* out = device_out ? vertex_world_out : h->stg_vertex;
+  launchVertexMap(p, out, h->stream);
+  KB_CUDA(h, cudaGetLastError());
+  if (!device_out) KB_CUDA(h, cudaMemcpyAsync(vertex_world_out, out, sizeof(float) * 3 * px, cudaMemcpyDeviceToHost, h->stream));
+  KB_CUDA(h, cudaStreamSynchronize(h->stream));
+  return KB_OK;
+}
+
 int kb_get_cluster_voxels(kb_handle* h, int32_t* offsets, int64_t* voxels_xyz, int32_t capacity, int32_t* total) {
   if (!h) return KB_ERR_INVALID;
   if (!h->trk_have) return fail(h, KB_ERR_STATE, "no track measurement result");

@@ -87,6 +87,19 @@ __global__ void tkInsertKernel(MotionTable t, const __grid_constant__ TrackParam
   }
 }
 
+// Input conversion (upstream parseInputPacket, call site active_window.cpp:275): world-frame vertex map of a depth image.
+__global__ void vertexMapKernel(TrackParams p, float* __restrict__ out) {
+  const int px = blockIdx.x * blockDim.x + threadIdx.x;
+  if (px >= p.W * p.H) return;
+  const float range = __ldg(&p.depth[px]);
+  const int u = px % p.W, v = px / p.W;
+  const float cxn = (static_cast<float>(u) - p.cx) / p.fx * range;
+  const float cyn = (static_cast<float>(v) - p.cy) / p.fy * range;
+  out[3 * px] = ((p.Rw[0] * cxn + p.Rw[1] * cyn) + p.Rw[2] * range) + p.tw[0];
+  out[3 * px + 1] = ((p.Rw[3] * cxn + p.Rw[4] * cyn) + p.Rw[5] * range) + p.tw[1];
+  out[3 * px + 2] = ((p.Rw[6] * cxn + p.Rw[7] * cyn) + p.Rw[8] * range) + p.tw[2];
+}
+
 __global__ void tkIntersectKernel(MotionTable t, const unsigned long long* __restrict__ track_keys,
                                   const int* __restrict__ track_of, int n_track_voxels, const int* __restrict__ present_ids,
                                   int n_present, int n_tracks, int* intersections) {
@@ -129,6 +142,10 @@ void launchTrackIntersect(const MotionTable& t, const unsigned long long* track_
   const long long total = static_cast<long long>(n_track_voxels) * n_present;
   const int blocks = static_cast<int>(total / 256 + 1 < 148 * 8 ? total / 256 + 1 : 148 * 8);
   tkIntersectKernel<<<blocks, 256, 0, s>>>(t, track_keys, track_of, n_track_voxels, present_ids, n_present, n_tracks, intersections);
+}
+
+void launchVertexMap(const TrackParams& p, float* out, cudaStream_t s) {
+  vertexMapKernel<<<(p.W * p.H + 255) / 256, 256, 0, s>>>(p, out);
 }
 
 void launchTrackExportKeys(const MotionTable& t, unsigned long long* out, cudaStream_t s) {

@@ -31,6 +31,9 @@ void launchTrackVoxelize(const MotionTable& t, const TrackParams& p, cudaStream_
 void launchTrackIntersect(const MotionTable& t, const unsigned long long* track_keys, const int* track_of, int n_track_voxels,
                           const int* present_ids, int n_present, int n_tracks, int* intersections, cudaStream_t s);
 
+// World-frame vertex map (H*W*3 floats, device) of p.depth with p's camera and pose (the other fields are unused).
+void launchVertexMap(const TrackParams& p, float* out, cudaStream_t s);
+
 // T3: copies the occupied keys (id, z, y, x order preserving) to `out` (device, capacity = pixels); the caller sorts.
 void launchTrackExportKeys(const MotionTable& t, unsigned long long* out, cudaStream_t s);
 

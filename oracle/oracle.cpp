@@ -1015,6 +1015,20 @@ void Oracle::trackMeasurements(const kb_frame& f, const int32_t* id_image, int m
   }
 }
 
+bool Oracle::computeVertexMap(const kb_frame& f, float* out) {
+  if (!has_cam_) { error_ = "camera not set"; return false; }
+  float R[9], t[3], Rw[9], tw[3];
+  invertPose(f.world_T_sensor, R, t, Rw, tw);
+  for (int v = 0; v < cam_.height; ++v)
+    for (int u = 0; u < cam_.width; ++u) {
+      const size_t px = static_cast<size_t>(v) * cam_.width + u;
+      const float d = f.depth[px];
+      const float pC[3] = {(static_cast<float>(u) - cam_.cx) / cam_.fx * d, (static_cast<float>(v) - cam_.cy) / cam_.fy * d, d};
+      transform(Rw, tw, pC, &out[3 * px]);
+    }
+  return true;
+}
+
 // ---- E0 / K4 ----------------------------------------------------------------------------------------------
 
 void Oracle::allocateBox(const int32_t mn[3], const int32_t mx[3]) {

@@ -122,6 +122,8 @@ class Oracle {
   void trackMeasurements(const kb_frame& f, const int32_t* id_image, int max_id, const int32_t* cluster_ids, float voxel_size, int n_tracks,
                          const int32_t* track_offsets, const int64_t* track_voxels_xyz);
   const TrackMeasurements& trackResult() const { return track_result_; }
+  // World-frame vertex map of a depth image (upstream parseInputPacket; docs/ORACLE_SPEC.md §8 "vertex map").
+  bool computeVertexMap(const kb_frame& f, float* out);
 
   // ---- block-hash sharded protocol (our multi-GPU design, not in the reference). The oracle
   // implements it on host buffers with the layouts of csrc/kb_kernels.cuh::ShardExchange so that world-size-2

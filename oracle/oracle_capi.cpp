@@ -192,6 +192,13 @@ int ko_track_measurements(ko_handle* h, const kb_frame* f_in, const int32_t* id_
   return KB_OK;
 }
 
+int ko_compute_vertex_map(ko_handle* h, const kb_frame* f_in, float* out) {
+  if (!h || !f_in || !out || (!f_in->depth && !f_in->depth_u16)) return KB_ERR_INVALID;
+  kb_frame tmp;
+  const kb_frame* f = expandCompact(h, f_in, &tmp);
+  return h->o->computeVertexMap(*f, out) ? KB_OK : fail(h, KB_ERR_STATE);
+}
+
 int ko_get_cluster_voxels(ko_handle* h, int32_t* offsets, int64_t* voxels_xyz, int32_t capacity, int32_t* total) {
   if (!h) return KB_ERR_INVALID;
   const auto& r = h->o->trackResult();

@@ -26,7 +26,7 @@ def test_header_declares_expected_entry_points():
 def test_library_exports_every_declared_symbol(product_lib):
     for s in declared_symbols():
         assert hasattr(product_lib, s), f"libkhronos_b200.so does not export {s}"
-    assert product_lib.kb_abi_version() == 6
+    assert product_lib.kb_abi_version() == 7
 
 
 def test_oracle_mirrors_abi(oracle_lib):

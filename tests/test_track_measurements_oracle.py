@@ -151,3 +151,22 @@ def test_oracle_vertex_map_and_2d_ids(oracle_lib):
     f = h.make_frame(d, pose, 1, label=l, vertex_world=vw)
     r = h.track_measurements(f, ids, max_id, 0.1, tracks)
     compare(r, h.get_cluster_voxels(max_id), numpy_measurements(cam, pose, d, ids, max_id, 0.1, tracks, vertex=vw))
+
+
+def test_oracle_vertex_map_matches_numpy(oracle_lib):
+    """parseInputPacket's world-frame vertex map: p_W = R * ((u-cx)/fx*d, (v-cy)/fy*d, d) + t in fp32 (ORACLE_SPEC §8)."""
+    cam, pose, d, l = scene_frame(scale=4, noise_seed=2)
+    h = hs.make_handle(oracle_lib, "ko_", cam=cam)
+    got = h.compute_vertex_map(h.make_frame(d, pose, 1, label=l))
+    f32 = np.float32
+    T = np.asarray(pose, np.float64)
+    R, t = T[:3, :3].astype(f32), T[:3, 3].astype(f32)
+    v, u = np.meshgrid(np.arange(cam.height, dtype=f32), np.arange(cam.width, dtype=f32), indexing="ij")
+    x, y = (u - f32(cam.cx)) / f32(cam.fx) * d, (v - f32(cam.cy)) / f32(cam.fy) * d
+    want = np.stack([((R[a, 0] * x + R[a, 1] * y) + R[a, 2] * d) + t[a] for a in range(3)], -1).astype(f32)
+    np.testing.assert_array_equal(got.view(np.uint32), want.view(np.uint32))
+    # the map is what the detectors compute internally: feeding it back changes nothing
+    ids, n = object_ids(h, d, l, pose)
+    a = h.track_measurements(h.make_frame(d, pose, 1, label=l), ids, n, 0.1, [])
+    b = h.track_measurements(h.make_frame(d, pose, 1, label=l, vertex_world=got), ids, n, 0.1, [])
+    np.testing.assert_array_equal(a["voxel_sums"], b["voxel_sums"])

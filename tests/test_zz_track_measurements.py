@@ -148,3 +148,22 @@ def test_track_measurement_argument_errors_and_stale_results(product_lib):
     g.detect_objects(capi.default_object_detector_config(OBJECTS), f)   # reuses the table
     with pytest.raises(capi.KbError):
         g.get_cluster_voxels(4)
+
+
+def test_vertex_map_matches_oracle(oracle_lib, product_lib):
+    """kb_compute_vertex_map (input conversion): bit-identical to the oracle for host, compact-depth and device frames."""
+    import torch
+    cam, pose, d, l = scene_frame(scale=1, noise_seed=4)
+    o = hs.make_handle(oracle_lib, "ko_", cam=cam)
+    g = hs.make_handle(product_lib, "kb_", cam=cam)
+    want = o.compute_vertex_map(o.make_frame(d, pose, 1, label=l))
+    got = g.compute_vertex_map(g.make_frame(d, pose, 1, label=l))
+    np.testing.assert_array_equal(got.view(np.uint32), want.view(np.uint32))
+    d16 = np.clip(np.round(d * 1000.0), 0, 65535).astype(np.uint16)
+    np.testing.assert_array_equal(g.compute_vertex_map(g.make_frame(None, pose, 1, depth_u16=d16)).view(np.uint32),
+                                  o.compute_vertex_map(o.make_frame(None, pose, 1, depth_u16=d16)).view(np.uint32))
+    dd = torch.from_numpy(d).cuda()
+    out = torch.zeros(d.shape + (3,), dtype=torch.float32).cuda()
+    torch.cuda.synchronize()
+    g.compute_vertex_map(g.make_frame(dd, pose, 1, memory=capi.MEM_DEVICE), out_ptr=out.data_ptr())
+    np.testing.assert_array_equal(out.cpu().numpy().view(np.uint32), want.view(np.uint32))
