@@ -31,8 +31,12 @@ def build(verbose=False, asan=None):
     global OUT, LIB
     if asan is None:
         asan = os.environ.get("KB_EMU_ASAN") == "1"
-    if asan:
+    ubsan = not asan and os.environ.get("KB_EMU_UBSAN") == "1"   # UndefinedBehaviorSanitizer build in _build_ubsan/ (reports to stderr;
+    if asan:                                                        # run with LD_PRELOAD=$(g++ -print-file-name=libubsan.so))
         OUT = os.path.join(HERE, "_build_asan")
+        LIB = os.path.join(OUT, "libkhronos_b200_emu.so")
+    elif ubsan:
+        OUT = os.path.join(HERE, "_build_ubsan")
         LIB = os.path.join(OUT, "libkhronos_b200_emu.so")
     deps = [os.path.join(CSRC, n) for n in os.listdir(CSRC) if n.endswith((".cu", ".cuh", ".h", ".cpp"))]
     deps += [os.path.join(HERE, "emu_runtime.cpp"), os.path.join(HERE, "include", "cuda_runtime.h"), os.path.abspath(__file__),
@@ -56,6 +60,8 @@ def build(verbose=False, asan=None):
     cmd = ["g++", "-O1" if asan else "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-Wno-unknown-pragmas"]
     if asan:
         cmd += ["-fsanitize=address", "-fno-omit-frame-pointer"]
+    elif ubsan:
+        cmd += ["-fsanitize=undefined", "-fno-omit-frame-pointer"]
     cmd += [
            "-I", os.path.join(HERE, "include"), "-I", OUT, "-o", LIB, os.path.join(HERE, "emu_runtime.cpp")] + srcs
     if verbose:
