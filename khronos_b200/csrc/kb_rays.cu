@@ -8,7 +8,8 @@
 //       straight ray every coordinate of source + d * direction is monotone in d, so a ray never re-enters a block: "the
 //       index changed since the previous step" is exactly the reference's set insertion.
 //   R1  (after a host-side exclusive scan of the counts) the same march writes (block key, ray) pairs.
-//   B1-B3  CSR "block -> rays" over ALL pairs: open-addressed table of block keys with a count per slot, one-CTA
+//   B1-B3  CSR "block -> rays" over ALL pairs: open-addressed table of block keys (sized by the distinct blocks, grown 4x when
+//       the count pass finds it more than half full) with a count per slot, one-CTA
 //       exclusive scan over the slots, scatter of the ray indices (order within a block is unspecified, as in the
 //       reference's unordered_set<size_t>).
 //   C1  one warp per query point: table lookup of the point's block, lanes stride over the block's rays, classify each
@@ -121,7 +122,8 @@ __device__ __forceinline__ int tableFind(const RayTable& t, unsigned long long k
   return -1;
 }
 
-__global__ void tableCountKernel(RayTable t, const unsigned long long* __restrict__ pair_keys, long long n) {
+// flags[0] = number of distinct blocks inserted, flags[1] = set when a key found no slot (the host then retries with a larger table)
+__global__ void tableCountKernel(RayTable t, const unsigned long long* __restrict__ pair_keys, long long n, int* __restrict__ flags) {
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (i >= n) return;
   const unsigned long long key = pair_keys[i];
@@ -130,11 +132,12 @@ __global__ void tableCountKernel(RayTable t, const unsigned long long* __restric
     unsigned long long k = t.keys[h];
     if (k == kRaysEmpty) {
       k = atomicCAS(&t.keys[h], kRaysEmpty, key);
-      if (k == kRaysEmpty) k = key;
+      if (k == kRaysEmpty) { k = key; atomicAdd(&flags[0], 1); }
     }
     if (k == key) { atomicAdd(&t.count[h], 1); return; }
     h = (h + 1) & t.mask;
   }
+  flags[1] = 1;
 }
 
 // Exclusive scan of count[] into offset[] by one CTA of 1024 threads (contiguous chunks + a shared scan of the chunk sums).
@@ -240,6 +243,7 @@ struct kb_ray_index {
   int* d_block_rays = nullptr;
   RayTable table{};
   uint32_t table_cap = 0;
+  int* d_flags = nullptr;  // tableCountKernel: distinct blocks, overflow
   bool csr_valid = false;
   // scratch
   int* d_counts = nullptr; long long* d_offsets = nullptr; size_t cap_scratch = 0;
@@ -288,29 +292,42 @@ bool finite3(const float* p, size_t n) {
   return true;
 }
 
+int allocTable(kb_ray_index* h, uint32_t cap) {
+  cudaFree(h->table.keys); cudaFree(h->table.count); cudaFree(h->table.offset); cudaFree(h->table.cursor);
+  h->table = RayTable{};
+  h->table_cap = 0;
+  KR_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->table.keys), sizeof(unsigned long long) * cap));
+  KR_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->table.count), sizeof(int) * cap));
+  KR_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->table.offset), sizeof(int) * cap));
+  KR_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->table.cursor), sizeof(int) * cap));
+  h->table_cap = cap;
+  return KB_OK;
+}
+
+// The table is sized by the number of distinct blocks (usually thousands), not by the number of (block, ray) pairs
+// (millions): start small, and when the count pass reports a full or more than half-full table, grow 4x and redo it.
 int rebuildCsr(kb_ray_index* h) {
   if (h->csr_valid) return KB_OK;
-  uint32_t cap = 1024;
-  while (cap < 2ull * static_cast<unsigned long long>(std::max<long long>(h->n_pairs, 1))) cap <<= 1;
-  if (cap > h->table_cap) {
-    cudaFree(h->table.keys); cudaFree(h->table.count); cudaFree(h->table.offset); cudaFree(h->table.cursor);
-    h->table = RayTable{};
-    KR_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->table.keys), sizeof(unsigned long long) * cap));
-    KR_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->table.count), sizeof(int) * cap));
-    KR_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->table.offset), sizeof(int) * cap));
-    KR_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->table.cursor), sizeof(int) * cap));
-    h->table_cap = cap;
+  int st;
+  if (!h->d_flags) KR_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->d_flags), sizeof(int) * 2));
+  if (h->table_cap == 0 && (st = allocTable(h, 1u << 14)) != KB_OK) return st;
+  const unsigned blocks = static_cast<unsigned>((std::max<long long>(h->n_pairs, 1) + 255) / 256);
+  for (;;) {
+    h->table.mask = h->table_cap - 1;
+    tableClearKernel<<<(h->table_cap + 255) / 256, 256, 0, h->stream>>>(h->table);
+    if (h->n_pairs == 0) break;
+    KR_CUDA(h, cudaMemsetAsync(h->d_flags, 0, sizeof(int) * 2, h->stream));
+    tableCountKernel<<<blocks, 256, 0, h->stream>>>(h->table, h->d_pair_keys, h->n_pairs, h->d_flags);
+    KR_CUDA(h, cudaGetLastError());
+    int flags[2] = {0, 0};
+    KR_CUDA(h, cudaMemcpyAsync(flags, h->d_flags, sizeof(int) * 2, cudaMemcpyDeviceToHost, h->stream));
+    KR_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (!flags[1] && static_cast<uint32_t>(flags[0]) * 2u <= h->table_cap) break;
+    if (h->table_cap >= (1u << 30)) return rfail(h, KB_ERR_CAPACITY, "too many distinct blocks");
+    if ((st = allocTable(h, h->table_cap * 4u)) != KB_OK) return st;
   }
-  h->table.mask = h->table_cap - 1;
-  tableClearKernel<<<(h->table_cap + 255) / 256, 256, 0, h->stream>>>(h->table);
-  if (h->n_pairs > 0) {
-    const unsigned blocks = static_cast<unsigned>((h->n_pairs + 255) / 256);
-    tableCountKernel<<<blocks, 256, 0, h->stream>>>(h->table, h->d_pair_keys, h->n_pairs);
-    tableScanKernel<<<1, 1024, 0, h->stream>>>(h->table);
-    tableFillKernel<<<blocks, 256, 0, h->stream>>>(h->table, h->d_pair_keys, h->d_pair_rays, h->n_pairs, h->d_block_rays);
-  } else {
-    tableScanKernel<<<1, 1024, 0, h->stream>>>(h->table);
-  }
+  tableScanKernel<<<1, 1024, 0, h->stream>>>(h->table);
+  if (h->n_pairs > 0) tableFillKernel<<<blocks, 256, 0, h->stream>>>(h->table, h->d_pair_keys, h->d_pair_rays, h->n_pairs, h->d_block_rays);
   KR_CUDA(h, cudaGetLastError());
   h->csr_valid = true;
   return KB_OK;
@@ -343,7 +360,7 @@ int kb_rays_destroy(kb_ray_index* h) {
   cudaFree(h->d_src); cudaFree(h->d_dst); cudaFree(h->d_stamps); cudaFree(h->d_pair_keys); cudaFree(h->d_pair_rays);
   cudaFree(h->d_block_rays); cudaFree(h->table.keys); cudaFree(h->table.count); cudaFree(h->table.offset); cudaFree(h->table.cursor);
   cudaFree(h->d_counts); cudaFree(h->d_offsets); cudaFree(h->d_points); cudaFree(h->d_early); cudaFree(h->d_late);
-  cudaFree(h->d_pt_counts); cudaFree(h->d_pt_offsets); cudaFree(h->d_out);
+  cudaFree(h->d_pt_counts); cudaFree(h->d_pt_offsets); cudaFree(h->d_out); cudaFree(h->d_flags);
   delete h;
   return KB_OK;
 }

@@ -129,3 +129,19 @@ def test_adaptor_track_measurements_and_ray_verificator(tmp_path):
     # ray (0,0,0) -> (0,0,2), 1 m blocks, step 0.25: samples z = 0.25 .. 2.25 -> blocks z = 0, 1, 2
     assert int(fields["ray_blocks"]) == 3
     assert fields["ray_verdicts"] == "01,10,00"    # hit: present; half way: absent; 0.5 m behind: occluded
+
+
+def test_ray_index_table_growth(oracle_lib, product_lib):
+    """10 cm blocks: tens of thousands of distinct blocks, so the block table (sized by distinct blocks, starting at 2^14
+    slots) has to grow and the count pass is repeated."""
+    rng = np.random.default_rng(5)
+    o, g = both(oracle_lib, product_lib, capi.default_ray_config(0.1, 0.05, 0.05))
+    src, tgt, ts = random_rays(rng, 1500, n_poses=8)
+    np.testing.assert_array_equal(o.add(src, tgt, ts), g.add(src, tgt, ts))
+    assert o.size() == g.size() and g.size()[1] > 40_000
+    pts = query_points(rng, src, tgt, 1500)
+    c = check_same(o, g, pts)
+    assert c.sum() > 50
+    src2, tgt2, ts2 = random_rays(rng, 1500, n_poses=8)     # second update: grows again or reuses the grown table
+    np.testing.assert_array_equal(o.add(src2, tgt2, ts2), g.add(src2, tgt2, ts2))
+    check_same(o, g, pts)

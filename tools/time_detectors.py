@@ -51,6 +51,34 @@ def main(iters=50):
         out[name] = {"us": round((time.perf_counter() - t0) / iters * 1e6, 1), "clusters": max_id,
                      "cluster_voxels": int(r["voxel_counts"].sum()), "track_voxels": int(sum(len(t) for t in tr))}
     print(out)
+    time_rays(scale=1 if iters >= 10 else 0.01)
+
+
+def time_rays(scale=1.0):
+    """Ray index (kb_rays_*): rays hashed per second and points checked per second on a synthetic mesh: vertices on the
+    walls of a 40 x 30 x 4 m hall, 200 pose nodes along a sweep, ray policy kMiddle, 1 m blocks."""
+    rng = np.random.default_rng(0)
+    n_v, n_p, n_q = int(400_000 * scale), 200, int(200_000 * scale)
+    stamps = (np.uint64(1_000_000_000) + np.arange(n_p, dtype=np.uint64) * np.uint64(100_000_000))
+    poses = np.stack([np.linspace(5, 35, n_p), 15 + 8 * np.sin(np.linspace(0, 6, n_p)), np.full(n_p, 1.5)], 1).astype(np.float32)
+    verts = rng.uniform([0, 0, 0], [40, 30, 4], (n_v, 3)).astype(np.float32)
+    wall = rng.integers(0, 3, n_v)
+    for a, hi in enumerate((40.0, 30.0, 4.0)):
+        verts[wall == a, a] = np.where(rng.integers(0, 2, int((wall == a).sum())) == 1, hi, 0.0)
+    first = rng.integers(1_000_000_000, 20_000_000_000, n_v).astype(np.uint64)
+    last = first + rng.integers(0, 2_000_000_000, n_v).astype(np.uint64)
+    r = capi.RayIndex(kb.lib(), "kb_", capi.default_ray_config())
+    t0 = time.perf_counter()
+    _, n_rays = r.add_vertices(capi.RAYS_MIDDLE, stamps, poses, verts, first, last)
+    t_add = time.perf_counter() - t0
+    pts = (verts[rng.integers(0, n_v, n_q)] + rng.normal(0, 0.05, (n_q, 3))).astype(np.float32)
+    r.check(pts[:1000])                       # builds the CSR
+    t0 = time.perf_counter()
+    counts, _ = r.check(pts)
+    t_chk = time.perf_counter() - t0
+    print({"rays": n_rays, "block_entries": r.size()[1], "add_s": round(t_add, 4), "rays_per_s": round(n_rays / t_add),
+           "points": n_q, "check_s": round(t_chk, 4), "points_per_s": round(n_q / t_chk),
+           "verdicts": int(counts.sum()), "note": "host-side call latency incl. H2D/D2H and the Python unpacking of the stamp lists"})
 
 
 if __name__ == "__main__":
