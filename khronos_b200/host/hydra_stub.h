@@ -12,6 +12,8 @@
 #include <cstdint>
 #include <map>
 #include <memory>
+#include <chrono>
+#include <string>
 #include <vector>
 
 namespace cv {
@@ -123,5 +125,25 @@ inline Isometry3d InputData::getSensorPose() const {
     }
   return r;
 }
+
+// hydra::timing::ScopedTimer / ElapsedTimeRecorder stand-ins (khronos aliases `Timer`, common_types.h:130): the adaptor
+// opens the reference's timer names so timing/stats.csv keeps its rows.
+namespace timing {
+struct ElapsedTimeRecorder {
+  struct Entry { std::string name; uint64_t stamp; double seconds; };
+  std::vector<Entry> entries;
+  static ElapsedTimeRecorder& instance() { static ElapsedTimeRecorder r; return r; }
+};
+struct ScopedTimer {
+  ScopedTimer(const std::string& name, uint64_t stamp) : name_(name), stamp_(stamp), start_(std::chrono::steady_clock::now()) {}
+  ~ScopedTimer() {
+    const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - start_).count();
+    ElapsedTimeRecorder::instance().entries.push_back({name_, stamp_, s});
+  }
+  std::string name_;
+  uint64_t stamp_;
+  std::chrono::steady_clock::time_point start_;
+};
+}  // namespace timing
 
 }  // namespace hydra

@@ -111,6 +111,13 @@ int main(int argc, char** argv) {
     int32_t oblocks = 0;
     if (omap) kb_num_blocks(omap->handle(), KB_EXPORT_ALL, &oblocks);
     std::printf("object_blocks=%d erased=%d ", oblocks, erased);
+    {  // the reference's timer names were opened (timing/stats.csv rows)
+      int hits = 0;
+      for (const char* name : {"motion_detection/all", "active_window/update_map", "integration/tracking"})
+        for (const auto& e : hydra::timing::ElapsedTimeRecorder::instance().entries)
+          if (e.name == name) { ++hits; break; }
+      std::printf("timers=%d ", hits);
+    }
     std::printf("blocks=%zu distance=%.9g weight=%.9g label=%u\n", host.getTsdfLayer().numBlocks(), v.distance, v.weight,
                 host.getSemanticLayer()->getBlockPtr({0, 0, 2})->getVoxel(0 + 8 * (0 + 8 * 3)).semantic_label);
   } catch (const std::exception& e) {

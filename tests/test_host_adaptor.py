@@ -36,5 +36,6 @@ def test_adaptor_frame_matches_known_answer(adaptor_exe):
     assert float(fields["distance"]) == pytest.approx(0.05, abs=1e-6)
     assert float(fields["weight"]) == pytest.approx(32 * 32 * 0.01 / 1.95 ** 4, rel=1e-5)
     assert int(fields["label"]) == 3
+    assert int(fields["timers"]) == 3   # motion_detection/all, active_window/update_map, integration/tracking were opened
     # reconstructStaticObject: dense box allocated, 12 frames fused, some low-confidence voxels erased
     assert int(fields["object_blocks"]) > 100 and int(fields["erased"]) >= 0
