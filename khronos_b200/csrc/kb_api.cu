@@ -136,6 +136,7 @@ struct kb_handle {
   unsigned long long* trk_sums = nullptr;
   int* trk_present = nullptr;
   int* trk_idlist = nullptr;
+  uint32_t trk_mask = 0;        // table size the last track measurement used (<= mt.mask)
   unsigned long long* trk_keys = nullptr;
   int* trk_of = nullptr;
   size_t trk_voxel_cap = 0;
@@ -1593,7 +1594,18 @@ int kb_track_measurements(kb_handle* h, const kb_frame* f, const int32_t* id_ima
     }
   }
   if ((st = stage(h, id_image, h->trk_ids, px, f->memory, &p.ids)) != KB_OK) return st;
-  launchTrackVoxelize(h->mt, p, h->stream);
+  // The table needs 2 slots per cluster pixel at most. A host id image is counted on the way (a pass over 1.2 MB), so
+  // that only that part of the shared 2^20-slot table is reset and probed; device images use all of it.
+  MotionTable table = h->mt;
+  if (f->memory != KB_MEM_DEVICE) {
+    size_t cluster_pixels = 0;
+    for (size_t i = 0; i < px; ++i) cluster_pixels += id_image[i] != 0;
+    uint32_t cap = 1024;
+    while (cap < 2 * cluster_pixels) cap <<= 1;
+    if (cap - 1 < table.mask) table.mask = cap - 1;
+  }
+  h->trk_mask = table.mask;
+  launchTrackVoxelize(table, p, h->stream);
   h->mt_dirty = true;  // shared table memory
   KB_CUDA(h, cudaGetLastError());
   h->trk_counts_host.assign(static_cast<size_t>(max_id), 0);
@@ -1627,7 +1639,7 @@ int kb_track_measurements(kb_handle* h, const kb_frame* f, const int32_t* id_ima
     KB_CUDA(h, cudaMemcpyAsync(h->trk_keys, keys.data(), sizeof(unsigned long long) * keys.size(), cudaMemcpyHostToDevice, h->stream));
     KB_CUDA(h, cudaMemcpyAsync(h->trk_of, track_of.data(), sizeof(int) * keys.size(), cudaMemcpyHostToDevice, h->stream));
     KB_CUDA(h, cudaMemcpyAsync(h->trk_present, present.data(), sizeof(int) * present.size(), cudaMemcpyHostToDevice, h->stream));
-    launchTrackIntersect(h->mt, h->trk_keys, h->trk_of, static_cast<int>(keys.size()), h->trk_present,
+    launchTrackIntersect(table, h->trk_keys, h->trk_of, static_cast<int>(keys.size()), h->trk_present,
                          static_cast<int>(present.size()), n_tracks, h->trk_inter, h->stream);
     KB_CUDA(h, cudaGetLastError());
     KB_CUDA(h, cudaMemcpyAsync(inter.data(), h->trk_inter, sizeof(int) * inter.size(), cudaMemcpyDeviceToHost, h->stream));
