@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define KB_ABI_VERSION 7
+#define KB_ABI_VERSION 8
 
 typedef enum kb_status {
   KB_OK = 0,
@@ -202,6 +202,25 @@ int kb_set_culling(kb_handle* h, int enabled);
  * One 64 B device->host read + stream sync. Used for metrics
  * (SURVEY.md §5 "C-ABI returns counters") and for the bench's byte model. */
 int kb_get_totals(kb_handle* h, kb_frame_stats* totals);
+
+/* The same cumulative counters in 64 bits (the hydra::timing-style metrics a long run logs): they never
+ * wrap (voxels_updated passes 2^32 after ~36 k frames of a 640x480 stream). frames = distinct stamps seen so far;
+ * block_frame_pairs = (block, frame) pairs that survived the block-level culling. One device->host read + stream sync. */
+typedef struct kb_totals64 {
+  uint64_t blocks_in_frustum, blocks_allocated, blocks_updated;
+  uint64_t voxels_updated, voxels_in_band, voxels_semantic;
+  uint64_t block_frame_pairs, total_blocks, capacity_exceeded, frames;
+} kb_totals64;
+int kb_get_totals64(kb_handle* h, kb_totals64* totals);
+
+/* Order-independent checksum of the whole map, computed on the device (for self-verifying benchmarks and shard-count
+ * invariance: the sums of the shards of a sharded map add up to the unsharded map's). Every voxel of every allocated
+ * block contributes v = mix64(mix64(mix64(mix64(key ^ mix64(lin + 1)) ^ (distance bits | weight bits << 32)) ^ label) ^
+ * last_observed_ns), key = the 63-bit packed block index ((x + 2^20) | (y + 2^20) << 21 | (z + 2^20) << 42), lin = linear
+ * voxel index, label = semantic_label or 0xFFFFFFFF when empty, mix64 = the murmur3 finaliser:
+ * out[0] = sum of v mod 2^64, out[1] = xor of v, out[2] = allocated blocks, out[3] = voxels observed at least once.
+ * tests/harness.py::map_checksum is the same function over a kb_block_export (product or oracle). */
+int kb_map_checksum(kb_handle* h, uint64_t out[4]);
 
 /* K2+K3. Replaces TrackingIntegrator::updateBlocks (tracking_integrator.cpp:71-104). */
 int kb_update_tracking(kb_handle* h, uint64_t stamp_ns);

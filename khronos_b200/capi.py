@@ -85,6 +85,15 @@ class FrameStats(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+class Totals64(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in
+                ("blocks_in_frustum", "blocks_allocated", "blocks_updated", "voxels_updated", "voxels_in_band",
+                 "voxels_semantic", "block_frame_pairs", "total_blocks", "capacity_exceeded", "frames")]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
 class BlockExport(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in
                 ("block_index", "block_flags", "distance", "weight", "color", "last_observed",
@@ -288,6 +297,18 @@ class MapHandle:
         t = FrameStats()
         self._check(self._fn("get_totals")(self._h, C.byref(t)))
         return t
+
+    def get_totals64(self) -> Totals64:
+        """Cumulative counters since creation in 64 bits (never wrap)."""
+        t = Totals64()
+        self._check(self._fn("get_totals64")(self._h, C.byref(t)))
+        return t
+
+    def map_checksum(self):
+        """(sum, xor, blocks, observed voxels): order-independent checksum of the whole map (kb_map_checksum)."""
+        out = (C.c_uint64 * 4)()
+        self._check(self._fn("map_checksum")(self._h, out))
+        return tuple(int(x) for x in out)
 
     def update_tracking(self, stamp_ns: int):
         self._check(self._fn("update_tracking")(self._h, C.c_uint64(int(stamp_ns))))

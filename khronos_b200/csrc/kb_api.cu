@@ -367,7 +367,7 @@ int frameIndex(kb_handle* h, uint64_t stamp, uint32_t* idx) {
 }
 
 int readCounters(kb_handle* h) {
-  KB_CUDA(h, cudaMemcpyAsync(h->h_ctr, h->dm.counters, sizeof(int) * kNumCounters, cudaMemcpyDeviceToHost, h->stream));
+  KB_CUDA(h, cudaMemcpyAsync(h->h_ctr, h->dm.counters, sizeof(int) * kCounterInts, cudaMemcpyDeviceToHost, h->stream));
   KB_CUDA(h, cudaStreamSynchronize(h->stream));
   return KB_OK;
 }
@@ -478,7 +478,7 @@ int kb_create(const kb_map_config* map, const kb_integrator_config* integ, const
     const size_t S = m.max_blocks, V = m.V;
     KB_CUDA(h, devAlloc(&m.hash_keys, cap, 0xFF));
     KB_CUDA(h, devAlloc(&m.hash_vals, cap, 0xFF));
-    KB_CUDA(h, devAlloc(&m.counters, kNumCounters, 0));
+    KB_CUDA(h, devAlloc(&m.counters, kCounterInts, 0));
     KB_CUDA(h, devAlloc(&m.free_list, S, 0));
     KB_CUDA(h, devAlloc(&m.block_index, S, 0));
     KB_CUDA(h, devAlloc(&m.block_flags, S, 0));
@@ -500,8 +500,8 @@ int kb_create(const kb_map_config* map, const kb_integrator_config* integ, const
       KB_CUDA(h, devAlloc(&m.sem_label, Q * V, 0xFF));
       KB_CUDA(h, devAlloc(&m.sem_lik, Q * V * m.Lp, 0));
     }
-    KB_CUDA(h, cudaMallocHost(reinterpret_cast<void**>(&h->h_ctr), sizeof(int) * kNumCounters));
-    std::memset(h->h_ctr, 0, sizeof(int) * kNumCounters);
+    KB_CUDA(h, cudaMallocHost(reinterpret_cast<void**>(&h->h_ctr), sizeof(int) * kCounterInts));
+    std::memset(h->h_ctr, 0, sizeof(int) * kCounterInts);
     KB_CUDA(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) {
       KB_CUDA(h, cudaEventCreateWithFlags(&h->stg_ready[i], cudaEventDisableTiming));
@@ -1027,6 +1027,49 @@ int kb_get_totals(kb_handle* h, kb_frame_stats* t) {
   t->total_blocks = c[kCtrLiveBlocks];
   t->capacity_exceeded = c[kCtrCapacityExceeded];
   return KB_OK;
+}
+
+int kb_get_totals64(kb_handle* h, kb_totals64* t) {
+  if (!h || !t) return KB_ERR_INVALID;
+  KB_CUDA(h, cudaSetDevice(h->device));
+  int st = readCounters(h);
+  if (st != KB_OK) return st;
+  const unsigned long long* c = totals64(h->h_ctr);
+  t->blocks_in_frustum = c[kTotFrustum];
+  t->blocks_allocated = c[kTotAllocated];
+  t->blocks_updated = c[kTotBlocksUpdated];
+  t->voxels_updated = c[kTotVoxelsUpdated];
+  t->voxels_in_band = c[kTotVoxelsBand];
+  t->voxels_semantic = c[kTotVoxelsSemantic];
+  t->block_frame_pairs = c[kTotPairs];
+  t->total_blocks = static_cast<uint64_t>(std::max(h->h_ctr[kCtrLiveBlocks], 0));
+  t->capacity_exceeded = static_cast<uint64_t>(h->h_ctr[kCtrCapacityExceeded]);
+  t->frames = static_cast<uint64_t>(h->stamps.size() - 1);
+  return KB_OK;
+}
+
+int kb_map_checksum(kb_handle* h, uint64_t out[4]) {
+  if (!h || !out) return KB_ERR_INVALID;
+  KB_CUDA(h, cudaSetDevice(h->device));
+  int st, n = 0;
+  if ((st = slotHwm(h, &n)) != KB_OK) return st;
+  unsigned long long *d_stamps = nullptr, *d_out = nullptr;
+  auto body = [&]() -> int {
+    KB_CUDA(h, cudaMalloc(&d_stamps, sizeof(uint64_t) * h->stamps.size()));
+    KB_CUDA(h, cudaMalloc(&d_out, sizeof(uint64_t) * 4));
+    KB_CUDA(h, cudaMemcpyAsync(d_stamps, h->stamps.data(), sizeof(uint64_t) * h->stamps.size(), cudaMemcpyHostToDevice, h->stream));
+    KB_CUDA(h, cudaMemsetAsync(d_out, 0, sizeof(uint64_t) * 4, h->stream));
+    launchChecksum(h->dm, n, d_stamps, d_out, h->stream);
+    KB_CUDA(h, cudaGetLastError());
+    KB_CUDA(h, cudaMemcpyAsync(out, d_out, sizeof(uint64_t) * 4, cudaMemcpyDeviceToHost, h->stream));
+    KB_CUDA(h, cudaStreamSynchronize(h->stream));
+    return KB_OK;
+  };
+  st = body();
+  cudaFree(d_stamps);
+  cudaFree(d_out);
+  h->main_dirty = true;
+  return st;
 }
 
 // Parameters of the tracking pass at `stamp_ns` (no launch, no state change besides the stamp table).

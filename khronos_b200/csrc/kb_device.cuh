@@ -89,6 +89,24 @@ enum Counter {
   kNumCounters = 32
 };
 
+// 64-bit cumulative totals (kb_get_totals64): the int counters above wrap after ~36 k frames of the bench workload
+// (119 k voxel updates per frame). They live behind the int counters in the same allocation (8-byte aligned), so one
+// device->host copy reads both.
+enum Total64 {
+  kTotVoxelsUpdated = 0,
+  kTotVoxelsBand = 1,
+  kTotVoxelsSemantic = 2,
+  kTotFrustum = 3,
+  kTotPairs = 4,
+  kTotBlocksUpdated = 5,
+  kTotAllocated = 6,
+  kNumTotals = 8
+};
+constexpr int kCounterInts = kNumCounters + 2 * kNumTotals;  // ints in the counter allocation
+__host__ __device__ inline unsigned long long* totals64(int* counters) {
+  return reinterpret_cast<unsigned long long*>(counters + kNumCounters);
+}
+
 __host__ __device__ inline unsigned long long packKey(int x, int y, int z) {
   const unsigned long long o = 1ull << 20, m = (1ull << 21) - 1ull;
   return ((static_cast<unsigned long long>(x + static_cast<long long>(o)) & m)) |

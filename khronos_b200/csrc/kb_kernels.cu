@@ -362,7 +362,11 @@ __global__ void __launch_bounds__(128) selectBlocksKernel(const DeviceMap m, con
   }
   if (lane == 0) {
     atomicAdd(&m.counters[kCtrFrustum], __popc(mask));
-    if (created) atomicAdd(&m.counters[kCtrAllocated], 1);
+    atomicAdd(&totals64(m.counters)[kTotFrustum], static_cast<unsigned long long>(__popc(mask)));
+    if (created) {
+      atomicAdd(&m.counters[kCtrAllocated], 1);
+      atomicAdd(&totals64(m.counters)[kTotAllocated], 1ull);
+    }
   }
   if (p.cull) {
     // block-level culling, lane = frame: each lane tests the whole block against its own frame
@@ -383,6 +387,7 @@ __global__ void __launch_bounds__(128) selectBlocksKernel(const DeviceMap m, con
       m.block_sem[slot] = allocSlot(m.counters, kCtrSemHwm, kCtrSemFreeCount, m.sem_free_list, m.max_sem);
     }
     atomicAdd(&m.counters[kCtrPairs], __popc(mask));
+    atomicAdd(&totals64(m.counters)[kTotPairs], static_cast<unsigned long long>(__popc(mask)));
     i = atomicAdd(&m.counters[kCtrWork0 + p.parity], 1);
     if (i < p.max_work) {
       p.work_slots[i] = slot;
@@ -685,7 +690,10 @@ __global__ void __launch_bounds__(kFuseThreads, COLOR ? KB_FUSE_COLOR_MIN_BLOCKS
         if ((p.work_upd[wi] & upd_frames) != upd_frames) {
           const uint32_t prev = atomicOr(&p.work_upd[wi], upd_frames);
           const int fresh = __popc(upd_frames & ~prev);
-          if (fresh) atomicAdd(&m.counters[kCtrBlocksUpdated], fresh);
+          if (fresh) {
+            atomicAdd(&m.counters[kCtrBlocksUpdated], fresh);
+            atomicAdd(&totals64(m.counters)[kTotBlocksUpdated], static_cast<unsigned long long>(fresh));
+          }
         }
       }
     }
@@ -696,9 +704,17 @@ __global__ void __launch_bounds__(kFuseThreads, COLOR ? KB_FUSE_COLOR_MIN_BLOCKS
     n_band = warpSum(n_band);
     n_sem = warpSum(n_sem);
     if (lane == 0) {
+      unsigned long long* t64 = totals64(m.counters);
       atomicAdd(&m.counters[kCtrVoxelsUpdated], n_valid);
-      if (n_band) atomicAdd(&m.counters[kCtrVoxelsBand], n_band);
-      if (n_sem) atomicAdd(&m.counters[kCtrVoxelsSemantic], n_sem);
+      atomicAdd(&t64[kTotVoxelsUpdated], static_cast<unsigned long long>(n_valid));
+      if (n_band) {
+        atomicAdd(&m.counters[kCtrVoxelsBand], n_band);
+        atomicAdd(&t64[kTotVoxelsBand], static_cast<unsigned long long>(n_band));
+      }
+      if (n_sem) {
+        atomicAdd(&m.counters[kCtrVoxelsSemantic], n_sem);
+        atomicAdd(&t64[kTotVoxelsSemantic], static_cast<unsigned long long>(n_sem));
+      }
     }
   }
 }
@@ -987,7 +1003,10 @@ __global__ void __launch_bounds__(kFuseThreads, KB_FUSE_MLP_MIN_BLOCKS) fuseKern
         if ((p.work_upd[wi] & upd_frames) != upd_frames) {
           const uint32_t prev = atomicOr(&p.work_upd[wi], upd_frames);
           const int fresh = __popc(upd_frames & ~prev);
-          if (fresh) atomicAdd(&m.counters[kCtrBlocksUpdated], fresh);
+          if (fresh) {
+            atomicAdd(&m.counters[kCtrBlocksUpdated], fresh);
+            atomicAdd(&totals64(m.counters)[kTotBlocksUpdated], static_cast<unsigned long long>(fresh));
+          }
         }
       }
     }
@@ -997,9 +1016,17 @@ __global__ void __launch_bounds__(kFuseThreads, KB_FUSE_MLP_MIN_BLOCKS) fuseKern
     n_band = warpSum(n_band);
     n_sem = warpSum(n_sem);
     if (lane == 0) {
+      unsigned long long* t64 = totals64(m.counters);
       atomicAdd(&m.counters[kCtrVoxelsUpdated], n_valid);
-      if (n_band) atomicAdd(&m.counters[kCtrVoxelsBand], n_band);
-      if (n_sem) atomicAdd(&m.counters[kCtrVoxelsSemantic], n_sem);
+      atomicAdd(&t64[kTotVoxelsUpdated], static_cast<unsigned long long>(n_valid));
+      if (n_band) {
+        atomicAdd(&m.counters[kCtrVoxelsBand], n_band);
+        atomicAdd(&t64[kTotVoxelsBand], static_cast<unsigned long long>(n_band));
+      }
+      if (n_sem) {
+        atomicAdd(&m.counters[kCtrVoxelsSemantic], n_sem);
+        atomicAdd(&t64[kTotVoxelsSemantic], static_cast<unsigned long long>(n_sem));
+      }
     }
   }
 }
@@ -1811,5 +1838,57 @@ void launchGatherSemantic(const DeviceMap& m, const int* slots, int n, int L, ui
                           float* lik, cudaStream_t s) {
   if (n > 0) gatherSemanticKernel<<<n, 256, 0, s>>>(m, slots, L, label, empty, lik);
 }
+
+// ---- order-independent map checksum (kb_map_checksum) ----------------------------------------------------------
+// One CTA per pool slot; every voxel of every allocated block contributes
+//   v = mix64(mix64(mix64(mix64(packKey(block) ^ mix64(lin + 1)) ^ (distance bits | weight bits << 32)) ^ label) ^ stamp)
+// (label = semantic_label, 0xFFFFFFFF when empty / no semantic layer; stamp = last_observed in ns, 0 = never) to a
+// wrapping 64-bit sum and an xor; out[2] counts blocks, out[3] voxels observed at least once. The same function over
+// a kb_block_export is tests/harness.py::map_checksum.
+namespace {
+__global__ void __launch_bounds__(256) checksumKernel(const DeviceMap m, int n_slots, const unsigned long long* __restrict__ stamps,
+                                                      unsigned long long* __restrict__ out) {
+  const int slot = blockIdx.x;
+  if (slot >= n_slots || !(m.block_flags[slot] & kFlagAllocated)) return;
+  const int3 bi = m.block_index[slot];
+  const unsigned long long key = packKey(bi.x, bi.y, bi.z);
+  const int sem = m.block_sem[slot];
+  unsigned long long sum = 0, xr = 0, seen = 0;
+  for (int lin = threadIdx.x; lin < m.V; lin += blockDim.x) {
+    const size_t gi = static_cast<size_t>(slot) * m.V + lin;
+    const float2 st = m.tsdf[gi];
+    uint32_t label = 0xFFFFFFFFu;
+    if (sem >= 0 && m.sem_label) {
+      const uint16_t lb = m.sem_label[static_cast<size_t>(sem) * m.V + lin];
+      if (lb != kSemEmpty) label = lb;
+    }
+    const unsigned long long stamp = m.last_obs ? stamps[m.last_obs[gi]] : 0ull;
+    unsigned long long v = mix64(key ^ mix64(static_cast<unsigned long long>(lin) + 1ull));
+    v = mix64(v ^ (static_cast<unsigned long long>(__float_as_uint(st.x)) | (static_cast<unsigned long long>(__float_as_uint(st.y)) << 32)));
+    v = mix64(v ^ static_cast<unsigned long long>(label));
+    v = mix64(v ^ stamp);
+    sum += v;
+    xr ^= v;
+    seen += (stamp != 0ull || st.y > 0.f) ? 1ull : 0ull;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    xr ^= __shfl_xor_sync(0xffffffffu, xr, o);
+    seen += __shfl_xor_sync(0xffffffffu, seen, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&out[0], sum);
+    atomicXor(&out[1], xr);
+    atomicAdd(&out[3], seen);
+  }
+  if (threadIdx.x == 0) atomicAdd(&out[2], 1ull);
+}
+}  // namespace
+
+void launchChecksum(const DeviceMap& m, int n_slots, const unsigned long long* stamps, unsigned long long* out, cudaStream_t s) {
+  if (n_slots > 0) checksumKernel<<<n_slots, 256, 0, s>>>(m, n_slots, stamps, out);
+}
+
 
 }  // namespace kb

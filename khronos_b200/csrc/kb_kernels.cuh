@@ -172,4 +172,8 @@ void launchGatherColor(const DeviceMap& m, const int* slots, int n, uint8_t* rgb
 void launchGatherSemantic(const DeviceMap& m, const int* slots, int n, int L, uint32_t* label,
                           uint8_t* empty, float* lik, cudaStream_t s);
 
+// Order-independent checksum of the whole map (see checksumKernel): out[4] = {sum, xor, blocks, observed voxels}, zeroed by
+// the caller; stamps = the handle's frame index -> stamp table on the device.
+void launchChecksum(const DeviceMap& m, int n_slots, const unsigned long long* stamps, unsigned long long* out, cudaStream_t s);
+
 }  // namespace kb

@@ -12,6 +12,7 @@ struct ko_handle {
   Oracle* o;
   std::string last_error;
   kb_frame_stats totals{};
+  kb_totals64 totals64{};
   size_t pixels = 0;
   std::vector<float> depth_f;
   std::vector<int32_t> label_i;
@@ -99,6 +100,13 @@ int ko_integrate_frame(ko_handle* h, const kb_frame* f_in, int allocate_blocks, 
   h->totals.voxels_updated += local.voxels_updated;
   h->totals.voxels_in_band += local.voxels_in_band;
   h->totals.voxels_semantic += local.voxels_semantic;
+  h->totals64.blocks_in_frustum += static_cast<uint64_t>(local.blocks_in_frustum);
+  h->totals64.blocks_allocated += static_cast<uint64_t>(local.blocks_allocated);
+  h->totals64.blocks_updated += static_cast<uint64_t>(local.blocks_updated);
+  h->totals64.voxels_updated += static_cast<uint64_t>(local.voxels_updated);
+  h->totals64.voxels_in_band += static_cast<uint64_t>(local.voxels_in_band);
+  h->totals64.voxels_semantic += static_cast<uint64_t>(local.voxels_semantic);
+  h->totals64.frames += 1;
   if (stats) *stats = local;
   return h->o->ok() ? KB_OK : fail(h, KB_ERR_INVALID);
 }
@@ -126,6 +134,49 @@ int ko_get_totals(ko_handle* h, kb_frame_stats* t) {
   if (!h || !t) return KB_ERR_INVALID;
   *t = h->totals;
   t->total_blocks = static_cast<int32_t>(h->o->sortedBlocks(KB_EXPORT_ALL).size());
+  return KB_OK;
+}
+
+int ko_get_totals64(ko_handle* h, kb_totals64* t) {
+  if (!h || !t) return KB_ERR_INVALID;
+  *t = h->totals64;
+  t->block_frame_pairs = t->blocks_in_frustum;  // the oracle visits every selected block (no culling)
+  t->total_blocks = h->o->sortedBlocks(KB_EXPORT_ALL).size();
+  return KB_OK;
+}
+
+// kb_map_checksum restated on the oracle's blocks (definition: include/khronos_b200.h).
+static inline uint64_t koMix64(uint64_t k) {
+  k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
+  return k;
+}
+int ko_map_checksum(ko_handle* h, uint64_t out[4]) {
+  if (!h || !out) return KB_ERR_INVALID;
+  uint64_t sum = 0, xr = 0, nb = 0, seen = 0;
+  const uint64_t o = 1ull << 20, m = (1ull << 21) - 1ull;
+  const int V = h->o->V();
+  for (const ko::Block* b : h->o->sortedBlocks(KB_EXPORT_ALL)) {
+    const uint64_t key = ((static_cast<uint64_t>(static_cast<int64_t>(b->index.x) + static_cast<int64_t>(o)) & m)) |
+                         ((static_cast<uint64_t>(static_cast<int64_t>(b->index.y) + static_cast<int64_t>(o)) & m) << 21) |
+                         ((static_cast<uint64_t>(static_cast<int64_t>(b->index.z) + static_cast<int64_t>(o)) & m) << 42);
+    ++nb;
+    for (int lin = 0; lin < V; ++lin) {
+      uint32_t db, wb;
+      std::memcpy(&db, &b->distance[lin], 4);
+      std::memcpy(&wb, &b->weight[lin], 4);
+      const bool has_sem = !b->semantic_empty.empty() && !b->semantic_empty[lin];
+      const uint32_t label = has_sem ? b->semantic_label[lin] : 0xFFFFFFFFu;
+      const uint64_t stamp = b->last_observed.empty() ? 0ull : b->last_observed[lin];
+      uint64_t v = koMix64(key ^ koMix64(static_cast<uint64_t>(lin) + 1ull));
+      v = koMix64(v ^ (static_cast<uint64_t>(db) | (static_cast<uint64_t>(wb) << 32)));
+      v = koMix64(v ^ static_cast<uint64_t>(label));
+      v = koMix64(v ^ stamp);
+      sum += v;
+      xr ^= v;
+      seen += (stamp != 0ull || b->weight[lin] > 0.f) ? 1ull : 0ull;
+    }
+  }
+  out[0] = sum; out[1] = xr; out[2] = nb; out[3] = seen;
   return KB_OK;
 }
 

@@ -69,6 +69,45 @@ def assert_blocks_equal(a: capi.Blocks, b: capi.Blocks, rtol=1e-4, exact_float=F
                                    err_msg=f"{what} likelihoods")
 
 
+_M1, _M2 = np.uint64(0xff51afd7ed558ccd), np.uint64(0xc4ceb9fe1a85ec53)
+
+
+def _mix64(k):
+    k = k.astype(np.uint64, copy=True)
+    k ^= k >> np.uint64(33)
+    k *= _M1
+    k ^= k >> np.uint64(33)
+    k *= _M2
+    k ^= k >> np.uint64(33)
+    return k
+
+
+def map_checksum(b: capi.Blocks):
+    """kb_map_checksum (include/khronos_b200.h) restated in numpy over an exported map (product or oracle):
+    (sum mod 2^64, xor, blocks, voxels observed at least once)."""
+    if b.n == 0:
+        return (0, 0, 0, 0)
+    V = b.distance.shape[1] if b.distance.ndim == 2 else b.distance.size // b.n
+    bi = b.block_index.reshape(b.n, 3).astype(np.int64)
+    o, m = np.int64(1 << 20), np.uint64((1 << 21) - 1)
+    key = (((bi[:, 0] + o).astype(np.uint64) & m) | (((bi[:, 1] + o).astype(np.uint64) & m) << np.uint64(21)) |
+           (((bi[:, 2] + o).astype(np.uint64) & m) << np.uint64(42)))
+    lin = _mix64(np.arange(V, dtype=np.uint64) + np.uint64(1))
+    with np.errstate(over="ignore"):
+        v = _mix64(key[:, None] ^ lin[None, :])
+        d = np.ascontiguousarray(b.distance, np.float32).reshape(b.n, V).view(np.uint32).astype(np.uint64)
+        w = np.ascontiguousarray(b.weight, np.float32).reshape(b.n, V).view(np.uint32).astype(np.uint64)
+        v = _mix64(v ^ (d | (w << np.uint64(32))))
+        label = np.where(b.semantic_empty.reshape(b.n, V) != 0, np.uint64(0xFFFFFFFF), b.semantic_label.reshape(b.n, V).astype(np.uint64))
+        v = _mix64(v ^ label)
+        stamp = b.last_observed.reshape(b.n, V).astype(np.uint64)
+        v = _mix64(v ^ stamp)
+        total = int(np.add.reduce(v.ravel(), dtype=np.uint64))
+    xr = int(np.bitwise_xor.reduce(v.ravel()))
+    seen = int(((stamp != 0) | (b.weight.reshape(b.n, V) > 0)).sum())
+    return (total, xr, int(b.n), seen)
+
+
 def has_gpu():
     try:
         import torch

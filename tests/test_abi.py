@@ -26,7 +26,7 @@ def test_header_declares_expected_entry_points():
 def test_library_exports_every_declared_symbol(product_lib):
     for s in declared_symbols():
         assert hasattr(product_lib, s), f"libkhronos_b200.so does not export {s}"
-    assert product_lib.kb_abi_version() == 7
+    assert product_lib.kb_abi_version() == 8
 
 
 def test_oracle_mirrors_abi(oracle_lib):
@@ -40,14 +40,14 @@ def test_struct_sizes_match_header(tmp_path):
     """Compile a tiny C program against the header and compare sizeof() with the ctypes mirrors."""
     import subprocess
     src = tmp_path / "sz.c"
-    src.write_text('#include <stdio.h>\n#include "khronos_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n",'
+    src.write_text('#include <stdio.h>\n#include "khronos_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
                    'sizeof(kb_map_config),sizeof(kb_integrator_config),sizeof(kb_tracking_config),sizeof(kb_motion_config),'
-                   'sizeof(kb_camera),sizeof(kb_frame),sizeof(kb_frame_stats),sizeof(kb_block_export));return 0;}\n')
+                   'sizeof(kb_camera),sizeof(kb_frame),sizeof(kb_frame_stats),sizeof(kb_block_export),sizeof(kb_totals64));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
     want = [ctypes.sizeof(c) for c in (capi.MapConfig, capi.IntegratorConfig, capi.TrackingConfig, capi.MotionConfig,
-                                       capi.Camera, capi.Frame, capi.FrameStats, capi.BlockExport)]
+                                       capi.Camera, capi.Frame, capi.FrameStats, capi.BlockExport, capi.Totals64)]
     assert got == want
 
 

@@ -11,7 +11,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "khronos_b200", "csrc")
-OUT = os.path.join(HERE, "_build")
+# build artefacts (rewritten copies of the product sources) live outside the source tree
+BUILD_ROOT = os.environ.get("KB_EMU_BUILD_ROOT", "/tmp/khronos_b200_cuda_emu")
+OUT = os.path.join(BUILD_ROOT, "_build")
 LIB = os.path.join(OUT, "libkhronos_b200_emu.so")
 
 LAUNCH = re.compile(r"([A-Za-z_]\w*(?:<[^<>;()]*>)?)<<<(.+?)>>>\((.*?)\);")
@@ -33,10 +35,10 @@ def build(verbose=False, asan=None):
         asan = os.environ.get("KB_EMU_ASAN") == "1"
     ubsan = not asan and os.environ.get("KB_EMU_UBSAN") == "1"   # UndefinedBehaviorSanitizer build in _build_ubsan/ (reports to stderr;
     if asan:                                                        # run with LD_PRELOAD=$(g++ -print-file-name=libubsan.so))
-        OUT = os.path.join(HERE, "_build_asan")
+        OUT = os.path.join(BUILD_ROOT, "_build_asan")
         LIB = os.path.join(OUT, "libkhronos_b200_emu.so")
     elif ubsan:
-        OUT = os.path.join(HERE, "_build_ubsan")
+        OUT = os.path.join(BUILD_ROOT, "_build_ubsan")
         LIB = os.path.join(OUT, "libkhronos_b200_emu.so")
     deps = [os.path.join(CSRC, n) for n in os.listdir(CSRC) if n.endswith((".cu", ".cuh", ".h", ".cpp"))]
     deps += [os.path.join(HERE, "emu_runtime.cpp"), os.path.join(HERE, "include", "cuda_runtime.h"), os.path.abspath(__file__),
