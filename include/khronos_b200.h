@@ -173,6 +173,48 @@ int kb_set_shard(kb_handle* h, int rank, int nranks);
 /* Owner rank of a block index under the shard hash (pure function; usable without a device). */
 int kb_block_owner(int32_t bx, int32_t by, int32_t bz, int nranks);
 
+/* Spatial CELL sharding (new in this build): blocks are grouped into square cells of cell_blocks x cell_blocks blocks in
+ * x/y (all z); cell (cx, cy) belongs to rank ((cx mod grid_x) + grid_x * (cy mod grid_y)) mod nranks, a periodic tiling,
+ * so a camera frustum (a few metres across) touches 1-4 ranks instead of all of them and each rank needs only the frames
+ * that touch its cells. cell_blocks == 0 restores the per-block hash of kb_set_shard. Every sharded entry point (fusion,
+ * box allocation, the tracking / motion exchanges) uses the layout set last. grid_x * grid_y should be a multiple of
+ * nranks (e.g. 4 x 2 for 8 ranks). */
+int kb_set_shard_cells(kb_handle* h, int rank, int nranks, int cell_blocks, int grid_x, int grid_y);
+/* Owner of a block under the cell layout (pure function; usable without a device). */
+int kb_cell_owner(int32_t bx, int32_t by, int cell_blocks, int grid_x, int grid_y, int nranks);
+/* Which ranks need a frame: bit r of owner_mask[i] is set iff some block that hydra's findBlocksInViewFrustum would select
+ * for frames[i] (the candidates of K0: block centre inside the inflated view frustum, upstream ProjectiveIntegrator::
+ * updateMap; call site active_window.cpp:210) is owned by rank r under this handle's shard layout. Host arithmetic only
+ * (poses, camera, layout; the images are not touched): the scheduler of a sharded replay uses it to send each frame
+ * only where it is needed. Evaluated with a 1 mm larger inflation than K0, so the mask is a superset of the ranks on which
+ * the device finds work (an extra frame on a rank is a no-op). nranks <= 32. */
+int kb_frame_owners(kb_handle* h, const kb_frame* frames, int32_t n_frames, uint32_t* owner_mask);
+
+/* ---- peer-memory frame exchange (new in this build; csrc/kb_peer.cu) -----------------------------------------------
+ * The sharded replay keeps the stream striped over the GPUs' frame pools and every rank pulls the frames it needs out
+ * of its peers' pools over NVLink. Pools are plain device allocations shared through CUDA IPC: kb_peer_alloc +
+ * kb_peer_export on the owner, kb_peer_open (-> a pointer valid on `device`) on the readers. No handle, no collective:
+ * the pools are read-only while frames are being pulled. Errors: kb_peer_last_error() (thread-local). */
+int kb_peer_alloc(int device, size_t bytes, void** ptr);
+int kb_peer_free(int device, void* ptr);
+int kb_peer_export(int device, void* ptr, uint8_t handle[64]);
+int kb_peer_open(int device, const uint8_t handle[64], void** mapped);
+int kb_peer_close(int device, void* mapped);
+int kb_peer_enable_access(int device, int peer_device);  /* same-process multi-device use (tests) */
+const char* kb_peer_last_error(void);
+/* A gather plan = n contiguous ranges (src[i] -> dst[i], bytes[i]; 16-byte aligned and sized; src may be a peer
+ * mapping), uploaded once and run many times. Transports: */
+enum { KB_GATHER_CE = 0,    /* cudaMemcpyAsync per range (copy engines, no SM time) */
+       KB_GATHER_SM = 1,    /* persistent CTAs, 16 B loads / stores */
+       KB_GATHER_BULK = 2   /* single-warp CTAs driving a cp.async.bulk + mbarrier pipeline (TMA unit) */ };
+typedef struct kb_gather_plan kb_gather_plan;
+int kb_gather_plan_create(int device, int32_t n, const void* const* src, void* const* dst, const uint64_t* bytes,
+                          kb_gather_plan** out);
+int kb_gather_plan_destroy(kb_gather_plan* plan);
+uint64_t kb_gather_plan_bytes(const kb_gather_plan* plan);
+/* Enqueues the plan's copies on cuda_stream (max_ctas bounds the grid of the two kernel transports). */
+int kb_gather_run(kb_gather_plan* plan, int mode, int max_ctas, void* cuda_stream);
+
 /* ---- the hot path ----------------------------------------------------------------------------- */
 
 /* K0+K1. Replaces hydra::ProjectiveIntegrator::updateMap(data, map, allocate_blocks, mask)

@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["kb_kernels.cu", "kb_motion_device.cu", "kb_objects_device.cu", "kb_tracks_device.cu", "kb_rays.cu", "kb_api.cu", "kb_motion_host.cpp"]
+SOURCES = ["kb_kernels.cu", "kb_motion_device.cu", "kb_objects_device.cu", "kb_tracks_device.cu", "kb_rays.cu", "kb_peer.cu", "kb_api.cu", "kb_motion_host.cpp"]
 HEADERS = ["kb_device.cuh", "kb_kernels.cuh", "kb_motion_device.cuh", "kb_objects_device.cuh", "kb_tracks_device.cuh", "kb_unionfind.cuh", "kb_motion_host.h", os.path.join(ROOT, "include", "khronos_b200.h")]
 LIB = os.path.join(CSRC, "libkhronos_b200.so")
 

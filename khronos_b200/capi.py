@@ -252,6 +252,16 @@ class MapHandle:
         self._check(self._fn("set_shard")(self._h, rank, nranks))
 
     # ---- hot path
+    def set_shard_cells(self, rank: int, nranks: int, cell_blocks: int, grid_x: int, grid_y: int):
+        self._check(self._fn("set_shard_cells")(self._h, rank, nranks, cell_blocks, grid_x, grid_y))
+
+    def frame_owners(self, frames) -> np.ndarray:
+        """Bit mask of the ranks that need each frame (kb_frame_owners)."""
+        arr = frames if isinstance(frames, C.Array) else (Frame * len(frames))(*frames)
+        out = np.zeros(len(arr), np.uint32)
+        self._check(self._fn("frame_owners")(self._h, arr, len(arr), C.c_void_p(out.ctypes.data)))
+        return out
+
     @staticmethod
     def make_frame(depth, pose, stamp_ns, label=None, mask=None, object_image=None, color=None,
                    vertex_world=None, target_id=0, memory=MEM_HOST, depth_u16=None, label_u8=None,

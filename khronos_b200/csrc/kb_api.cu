@@ -64,10 +64,10 @@ struct kb_handle {
   uint32_t* item_fmask = nullptr;
   int* item_list = nullptr;    // KB_FUSE_ITEM_LIST experiment: compacted heaviest-first item lists (3 x item_list_cap)
   int item_list_cap = 0;
-  bool use_item_list = false;
+  bool use_item_list = true;   // default since round 2 (+7 % alone, +40 % with the pipeline; profiles/r2_ab1_summary.txt); KB_FUSE_ITEM_LIST=0 disables
   // KB_PIPELINE experiment: the prologue (tile pyramid, K0, K0b[, compaction]) of batch i+1 runs on its own stream while
   // the fuse kernel of batch i is still busy; work lists, tile pyramids and cursors exist twice (index = batch parity)
-  bool pipelined = false;
+  bool pipelined = true;       // default since round 2 (+31 %, profiles/r2_ab1_summary.txt); KB_PIPELINE=0 disables
   cudaStream_t pre_stream = nullptr;
   cudaEvent_t pre_done[2] = {nullptr, nullptr}, fuse_done[2] = {nullptr, nullptr}, main_front = nullptr;
   bool main_dirty = true;      // main-stream work other than fuse kernels was enqueued since the last prologue
@@ -115,8 +115,8 @@ struct kb_handle {
   bool motion_stale = false;   // cluster lists of the last detection not yet built on the host
   MotionHostParams motion_hp{};
   bool motion_have_image = false;
-  bool everfree_v2 = false;    // KB_EVERFREE_V2 experiment (vectorised halo fill)
-  bool motion_sparse = false;  // KB_MOTION_SPARSE experiment (kb_motion_device.cu)
+  bool everfree_v2 = true;     // vectorised halo fill of the ever-free pass (default since round 2; KB_EVERFREE_V2=0 disables)
+  bool motion_sparse = true;   // slot-wise reset of the clustering table (default since round 2; KB_MOTION_SPARSE=0 disables)
   bool mt_dirty = false;       // the shared table holds entries of another user (object detection / dense clustering)
   int3* d_removed = nullptr;
   int max_removed = 0;
@@ -703,6 +703,74 @@ int kb_set_shard(kb_handle* h, int rank, int nranks) {
   if (!h || nranks < 1 || rank < 0 || rank >= nranks) return fail(h, KB_ERR_INVALID, "invalid shard");
   h->rank = rank;
   h->nranks = nranks;
+  h->dm.shard_cell = 0;
+  h->dm.shard_gx = h->dm.shard_gy = 1;
+  return KB_OK;
+}
+
+int kb_set_shard_cells(kb_handle* h, int rank, int nranks, int cell_blocks, int grid_x, int grid_y) {
+  if (h) h->main_dirty = true;
+  if (!h || nranks < 1 || rank < 0 || rank >= nranks || cell_blocks < 0 || (cell_blocks > 0 && (grid_x < 1 || grid_y < 1)))
+    return fail(h, KB_ERR_INVALID, "invalid cell shard layout");
+  h->rank = rank;
+  h->nranks = nranks;
+  h->dm.shard_cell = cell_blocks;
+  h->dm.shard_gx = cell_blocks > 0 ? grid_x : 1;
+  h->dm.shard_gy = cell_blocks > 0 ? grid_y : 1;
+  return KB_OK;
+}
+
+int kb_cell_owner(int32_t bx, int32_t by, int cell_blocks, int grid_x, int grid_y, int nranks) {
+  if (nranks <= 1 || cell_blocks < 1 || grid_x < 1 || grid_y < 1) return 0;
+  return cellOwner(bx, by, cell_blocks, grid_x, grid_y, nranks);
+}
+
+// Host restatement of K0's candidate test (selectBlocksKernel: xform + inFrustum, same fp32 expressions; this
+// translation unit is compiled without FMA contraction like the device code) for the frame scheduler of a sharded replay.
+int kb_frame_owners(kb_handle* h, const kb_frame* frames, int32_t n_frames, uint32_t* owner_mask) {
+  if (!h || !frames || !owner_mask || n_frames < 0) return fail(h, KB_ERR_INVALID, "null argument");
+  if (!h->has_cam) return fail(h, KB_ERR_STATE, "kb_set_camera must be called first");
+  if (h->nranks > 32) return fail(h, KB_ERR_INVALID, "kb_frame_owners supports at most 32 ranks");
+  const BatchParams& p = h->batch;
+  const uint32_t all = h->nranks >= 32 ? 0xffffffffu : ((1u << h->nranks) - 1u);
+  const float infl = p.infl + 1e-3f;  // superset of the device's selection
+  for (int i = 0; i < n_frames; ++i) {
+    float R[9], t[3], Rw[9], tw[3];
+    for (int k = 0; k < 16; ++k)
+      if (!std::isfinite(frames[i].world_T_sensor[k])) return fail(h, KB_ERR_INVALID, "non-finite sensor pose");
+    poseToFloat(frames[i].world_T_sensor, R, t, Rw, tw);
+    uint32_t mask = 0;
+    if (h->nranks == 1) { owner_mask[i] = 1u; continue; }
+    const float reach = h->cam.max_range + infl;
+    const float inv = 1.f / h->block_size;
+    int lo[3], hi[3];
+    for (int a = 0; a < 3; ++a) {
+      lo[a] = static_cast<int>(std::floor((tw[a] - reach) * inv));
+      hi[a] = static_cast<int>(std::floor((tw[a] + reach) * inv));
+    }
+    for (int bz = lo[2]; bz <= hi[2] && mask != all; ++bz)
+      for (int by = lo[1]; by <= hi[1] && mask != all; ++by)
+        for (int bx = lo[0]; bx <= hi[0]; ++bx) {
+          const int owner = mapOwner(h->dm, bx, by, bz, h->nranks);
+          if ((mask >> owner) & 1u) continue;
+          const float cx = (static_cast<float>(bx) + 0.5f) * p.block_size;
+          const float cy = (static_cast<float>(by) + 0.5f) * p.block_size;
+          const float cz = (static_cast<float>(bz) + 0.5f) * p.block_size;
+          const float x = ((R[0] * cx + R[1] * cy) + R[2] * cz) + t[0];
+          const float y = ((R[3] * cx + R[4] * cy) + R[5] * cz) + t[1];
+          const float z = ((R[6] * cx + R[7] * cy) + R[8] * cz) + t[2];
+          if (z < -infl) continue;
+          const float r = std::sqrt((x * x + y * y) + z * z);
+          if (r < p.min_range - infl || r > p.max_range + infl) continue;
+          if (p.pl[0][0] * x + p.pl[0][1] * z < -infl) continue;
+          if (p.pl[1][0] * x + p.pl[1][1] * z < -infl) continue;
+          if (p.pl[2][0] * y + p.pl[2][1] * z < -infl) continue;
+          if (p.pl[3][0] * y + p.pl[3][1] * z < -infl) continue;
+          mask |= 1u << owner;
+          if (mask == all) break;
+        }
+    owner_mask[i] = mask;
+  }
   return KB_OK;
 }
 
@@ -739,7 +807,10 @@ static int integrateBatch(kb_handle* h, const kb_frame* frames, int n, int alloc
   p.parity = h->parity;
   h->parity ^= 1;
   const int par = p.parity;
-  const bool pipe = h->pipelined;
+  // Short calls (the per-frame pipeline: detect -> integrate -> track) gain nothing from a second stream: their prologue
+  // depends on the main-stream work right before it. They run entirely on the main stream with the first buffer set.
+  const bool pipe = h->pipelined && n >= 4;
+  if (!pipe) h->main_dirty = true;  // a later pipelined prologue must wait for this batch's main-stream kernels
   p.pipelined = pipe ? 1 : 0;
   p.fetch_ctr = (pipe && par) ? kCtrFetchB : kCtrFetch;
   p.items_ctr = (pipe && par) ? kCtrItemsB0 : kCtrItems0;

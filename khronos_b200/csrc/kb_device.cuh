@@ -53,6 +53,10 @@ struct DeviceMap {
   uint16_t* sem_label;
   float* sem_lik;
   uchar4* color;  // [S][V] TsdfVoxel::color (rgb, w unused); null until the first frame with a colour image
+  // Shard layout (kb_set_shard / kb_set_shard_cells). shard_cell == 0: per-block hash (blockOwner). shard_cell > 0:
+  // square cells of shard_cell x shard_cell blocks in x/y (all z), tiled periodically over a shard_gx x shard_gy grid
+  // of ranks, so spatially coherent frames touch few ranks (cellOwner).
+  int shard_cell, shard_gx, shard_gy;
 };
 
 // Cumulative device counters (never reset on the hot path; the host reports differences).
@@ -126,6 +130,17 @@ __host__ __device__ inline unsigned long long mix64(unsigned long long k) {
 // Shard owner of a block: upper hash bits, so it is independent of the table slot (lower bits).
 __host__ __device__ inline int blockOwner(int x, int y, int z, int nranks) {
   return static_cast<int>((mix64(packKey(x, y, z)) >> 40) % static_cast<unsigned long long>(nranks));
+}
+
+// Periodic cell tiling: cell (cx, cy) = floor(block / cell) belongs to rank ((cx mod gx) + gx * (cy mod gy)) mod nranks.
+__host__ __device__ inline int cellOwner(int x, int y, int cell, int gx, int gy, int nranks) {
+  const int cx = (x >= 0 ? x : x - cell + 1) / cell, cy = (y >= 0 ? y : y - cell + 1) / cell;  // floor division
+  const int mx = ((cx % gx) + gx) % gx, my = ((cy % gy) + gy) % gy;
+  return (mx + gx * my) % nranks;
+}
+// Owner rank of a block under the map's shard layout.
+__host__ __device__ inline int mapOwner(const DeviceMap& m, int x, int y, int z, int nranks) {
+  return m.shard_cell > 0 ? cellOwner(x, y, m.shard_cell, m.shard_gx, m.shard_gy, nranks) : blockOwner(x, y, z, nranks);
 }
 
 #ifdef __CUDACC__

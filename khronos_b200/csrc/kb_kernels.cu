@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(128) selectBlocksKernel(const DeviceMap m, con
     const float cy = (static_cast<float>(by) + 0.5f) * p.block_size;
     const float cz = (static_cast<float>(bz) + 0.5f) * p.block_size;
     // shard filter first: at N ranks (N-1)/N of the candidate warps retire here
-    if (p.nranks > 1 && blockOwner(bx, by, bz, p.nranks) != p.rank) return;
+    if (p.nranks > 1 && mapOwner(m, bx, by, bz, p.nranks) != p.rank) return;
     bool in = false;
     if (lane < p.n_frames) {
       float x, y, z;
@@ -1096,7 +1096,7 @@ __global__ void __launch_bounds__(kThreads) everFreeKernel(const DeviceMap m, co
       const int3 bi = m.block_index[slot];
       const int dx = threadIdx.x % 3 - 1, dy = (threadIdx.x / 3) % 3 - 1, dz = threadIdx.x / 9 - 1;
       int ns = (dx == 0 && dy == 0 && dz == 0) ? slot : hashLookup(m, bi.x + dx, bi.y + dy, bi.z + dz);
-      if (SHARD && ns < 0 && blockOwner(bi.x + dx, bi.y + dy, bi.z + dz, p.nranks) != p.rank) {
+      if (SHARD && ns < 0 && mapOwner(m, bi.x + dx, bi.y + dy, bi.z + dz, p.nranks) != p.rank) {
         const int off = ghostLookup(p, bi.x + dx, bi.y + dy, bi.z + dz);
         if (off >= 0) ns = -(2 + off);
       }
@@ -1158,7 +1158,7 @@ __global__ void __launch_bounds__(kThreads) everFreeKernelV2(const DeviceMap m, 
       const int3 bi = m.block_index[slot];
       const int dx = threadIdx.x % 3 - 1, dy = (threadIdx.x / 3) % 3 - 1, dz = threadIdx.x / 9 - 1;
       int ns = (dx == 0 && dy == 0 && dz == 0) ? slot : hashLookup(m, bi.x + dx, bi.y + dy, bi.z + dz);
-      if (SHARD && ns < 0 && blockOwner(bi.x + dx, bi.y + dy, bi.z + dz, p.nranks) != p.rank) {
+      if (SHARD && ns < 0 && mapOwner(m, bi.x + dx, bi.y + dy, bi.z + dz, p.nranks) != p.rank) {
         const int off = ghostLookup(p, bi.x + dx, bi.y + dy, bi.z + dz);
         if (off >= 0) ns = -(2 + off);
       }
@@ -1258,7 +1258,7 @@ __global__ void haloMarkKernel(const DeviceMap m, const ShardExchange x, const i
   const int32_t* __restrict__ buf = all_pending + static_cast<size_t>(r) * x.pending_stride();
   if (i >= buf[0]) return;
   const int bx = buf[4 + 3 * i] + (k % 3 - 1), by = buf[4 + 3 * i + 1] + ((k / 3) % 3 - 1), bz = buf[4 + 3 * i + 2] + (k / 9 - 1);
-  if (blockOwner(bx, by, bz, x.nranks) != x.rank) return;
+  if (mapOwner(m, bx, by, bz, x.nranks) != x.rank) return;
   const int slot = hashLookup(m, bx, by, bz);
   if (slot < 0) return;
   if (atomicExch(&x.halo_mark[slot], 1) != 0) return;
@@ -1561,7 +1561,7 @@ __global__ void allocateBoxKernel(const DeviceMap m, int3 lo, int3 dims, int ran
   const int bx = lo.x + c % dims.x;
   c /= dims.x;
   const int by = lo.y + c % dims.y, bz = lo.z + c / dims.y;
-  if (nranks > 1 && blockOwner(bx, by, bz, nranks) != rank) return;
+  if (nranks > 1 && mapOwner(m, bx, by, bz, nranks) != rank) return;
   int created;
   hashFindOrInsert(m, bx, by, bz, born, &created);
 }

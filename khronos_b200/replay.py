@@ -1,0 +1,168 @@
+"""Spatially sharded replay of a frame stream over the GPUs of one box (no counterpart in the reference).
+
+Layout. The map is sharded by CELLS (kb_set_shard_cells): square groups of cell x cell blocks, tiled periodically over
+a gx x gy grid of ranks, so a frame's frustum touches 1-4 ranks and each rank needs only the frames that touch its cells
+(kb_frame_owners). The stream is resident STRIPED over the ranks' frame pools (stripe = 32 consecutive frames per rank,
+round robin: what a host feeding each GPU over its own PCIe link produces). For every step each rank integrates, in
+stream order, the sub-sequence of frames it needs: frames of its own stripe are read in place, the others are PULLED out
+of the peers' pools over NVLink (kb_gather_*: CUDA IPC mappings + copy engines / a cp.async.bulk kernel) into a double
+buffered receive area while the previous step is being fused. Pools are read-only, so there is no collective and no
+cross-rank synchronisation inside a step; ranks run ahead of each other freely. Per voxel the sequence of updates is the
+stream order restricted to the frames that see its block, exactly as on one GPU, so the union of the shards is
+bit-identical to the unsharded map (kb_map_checksum sums add up).
+
+`StripedSchedule` is pure Python/numpy (tested on CPU); `PeerPools` wraps the kb_peer_* C ABI."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Sequence, Tuple
+
+import numpy as np
+
+
+def rank_grid(world: int) -> Tuple[int, int]:
+    """gx x gy = world with gx >= gy as square as possible (8 -> 4 x 2, 4 -> 2 x 2, 2 -> 2 x 1, 6 -> 3 x 2)."""
+    gy = int(np.floor(np.sqrt(world)))
+    while world % gy:
+        gy -= 1
+    return world // gy, gy
+
+
+@dataclass
+class StepPlan:
+    """One rank's share of a step: `mine` = (position in the step, global frame, slot) in stream order, slot >= 0 indexes
+    the receive buffer, slot < 0 encodes a frame of the rank's own pool as -(local index) - 1; `ranges` = contiguous
+    pulls (src rank, first local index on src, first receive slot, frame count)."""
+    mine: List[Tuple[int, int, int]]
+    ranges: List[Tuple[int, int, int, int]]
+    n_remote: int
+
+
+class StripedSchedule:
+    def __init__(self, world: int, rank: int, stripe: int = 32):
+        self.world, self.rank, self.stripe = int(world), int(rank), int(stripe)
+
+    def home(self, g: int) -> int:
+        return (g // self.stripe) % self.world
+
+    def local_index(self, g: int) -> int:
+        return (g // (self.stripe * self.world)) * self.stripe + g % self.stripe
+
+    def resident(self, lap: int) -> List[int]:
+        """Global frame numbers of a lap that live in this rank's pool, in local-index order."""
+        return [g for g in range(lap) if self.home(g) == self.rank]
+
+    def plan(self, step_frames: Sequence[int], owner_mask: np.ndarray) -> StepPlan:
+        """step_frames[j] = global frame of position j of the step; owner_mask[g] = kb_frame_owners bit mask."""
+        mine, ranges, slot = [], [], 0
+        for j, g in enumerate(step_frames):
+            if not (int(owner_mask[g]) >> self.rank) & 1:
+                continue
+            src = self.home(g)
+            li = self.local_index(g)
+            if src == self.rank:
+                mine.append((j, g, -li - 1))
+                continue
+            if ranges and ranges[-1][0] == src and ranges[-1][1] + ranges[-1][3] == li and ranges[-1][2] + ranges[-1][3] == slot:
+                r = ranges[-1]
+                ranges[-1] = (r[0], r[1], r[2], r[3] + 1)
+            else:
+                ranges.append((src, li, slot, 1))
+            mine.append((j, g, slot))
+            slot += 1
+        return StepPlan(mine, ranges, slot)
+
+
+class CudaArray:
+    """Raw device memory as a `__cuda_array_interface__` object: torch.as_tensor(CudaArray(...), device=...) is a
+    zero-copy view (the frame pools are cudaMalloc allocations of the library so that they can be shared by CUDA IPC)."""
+
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {"shape": tuple(int(x) for x in shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+class PeerPools:
+    """This rank's frame pool (depth f32 [n, H, W] followed by label i32 [n, H, W] in one allocation) and read-only
+    mappings of the other ranks' pools. `exchange` is a callable that all-gathers a 64-byte handle + pool size over the
+    ranks (torch.distributed in bench.py; a local list in single-process tests)."""
+
+    def __init__(self, lib, device: int, n_local: int, height: int, width: int):
+        self.lib, self.device = lib, int(device)
+        self.n, self.H, self.W = int(n_local), int(height), int(width)
+        self.P = self.H * self.W
+        self.bytes = max(self.n, 1) * self.P * 8
+        p = C.c_void_p()
+        self._check(lib.kb_peer_alloc(self.device, C.c_size_t(self.bytes), C.byref(p)), "kb_peer_alloc")
+        self.ptr = int(p.value)
+        self.peer_ptr = {}
+        self.peer_n = {}
+        self._opened = []
+
+    def _check(self, st, what):
+        if st != 0:
+            self.lib.kb_peer_last_error.restype = C.c_char_p
+            raise RuntimeError(f"{what} failed ({st}): {self.lib.kb_peer_last_error().decode()}")
+
+    def depth_ptr(self, base: int, n: int, i: int) -> int:
+        return base + i * self.P * 4
+
+    def label_ptr(self, base: int, n: int, i: int) -> int:
+        return base + max(n, 1) * self.P * 4 + i * self.P * 4
+
+    def views(self, torch, dev):
+        """(depth f32 [n, H, W], label i32 [n, H, W]) torch views of the local pool."""
+        n = max(self.n, 1)
+        d = torch.as_tensor(CudaArray(self.ptr, (n, self.H, self.W), "<f4"), device=dev)
+        l = torch.as_tensor(CudaArray(self.ptr + n * self.P * 4, (n, self.H, self.W), "<i4"), device=dev)
+        return d, l
+
+    def export_handle(self) -> bytes:
+        h = (C.c_uint8 * 64)()
+        self._check(self.lib.kb_peer_export(self.device, C.c_void_p(self.ptr), h), "kb_peer_export")
+        return bytes(h)
+
+    def open_peer(self, rank: int, handle: bytes, n_frames: int):
+        p = C.c_void_p()
+        hb = (C.c_uint8 * 64).from_buffer_copy(handle)
+        self._check(self.lib.kb_peer_open(self.device, hb, C.byref(p)), f"kb_peer_open(rank {rank})")
+        self.peer_ptr[rank], self.peer_n[rank] = int(p.value), int(n_frames)
+        self._opened.append(int(p.value))
+
+    def add_local_peer(self, rank: int, ptr: int, n_frames: int):
+        """Same-process peer (tests: several 'ranks' on one or more devices of one process)."""
+        self.peer_ptr[rank], self.peer_n[rank] = int(ptr), int(n_frames)
+
+    def gather_plan(self, ranges, rx_ptr: int, rx_capacity: int):
+        """kb_gather_plan for a StepPlan's ranges: per range one copy of the depth images and one of the label images
+        into the receive buffer (same layout as a pool: depth [cap, H, W] then label [cap, H, W])."""
+        src, dst, nbytes = [], [], []
+        for (r, li, slot, cnt) in ranges:
+            base, n = self.peer_ptr[r], self.peer_n[r]
+            assert li + cnt <= max(n, 1) and slot + cnt <= rx_capacity
+            src += [self.depth_ptr(base, n, li), self.label_ptr(base, n, li)]
+            dst += [self.depth_ptr(rx_ptr, rx_capacity, slot), self.label_ptr(rx_ptr, rx_capacity, slot)]
+            nbytes += [cnt * self.P * 4, cnt * self.P * 4]
+        k = len(src)
+        plan = C.c_void_p()
+        a_src = (C.c_void_p * max(k, 1))(*src)
+        a_dst = (C.c_void_p * max(k, 1))(*dst)
+        a_b = (C.c_uint64 * max(k, 1))(*nbytes)
+        self._check(self.lib.kb_gather_plan_create(self.device, k, a_src, a_dst, a_b, C.byref(plan)), "kb_gather_plan_create")
+        return plan
+
+    def run(self, plan, mode: int, max_ctas: int, stream: int):
+        self._check(self.lib.kb_gather_run(plan, int(mode), int(max_ctas), C.c_void_p(stream)), "kb_gather_run")
+
+    def plan_bytes(self, plan) -> int:
+        self.lib.kb_gather_plan_bytes.restype = C.c_uint64
+        return int(self.lib.kb_gather_plan_bytes(plan))
+
+    def close(self):
+        for p in self._opened:
+            self.lib.kb_peer_close(self.device, C.c_void_p(p))
+        self._opened = []
+        if self.ptr:
+            self.lib.kb_peer_free(self.device, C.c_void_p(self.ptr))
+            self.ptr = 0

@@ -270,6 +270,32 @@ static inline void transform(const float R[9], const float t[3], const float p[3
   out[2] = ((R[6] * p[0] + R[7] * p[1]) + R[8] * p[2]) + t[2];
 }
 
+// kb_frame_owners on the oracle: the exact frustum selection of integrateFrame (no safety inflation), reduced to the set
+// of owner ranks. The product's mask must be a superset.
+uint32_t Oracle::frameOwners(const kb_frame& f) const {
+  float R[9], t[3], Rw[9], tw[3];
+  invertPose(f.world_T_sensor, R, t, Rw, tw);
+  const float infl = block_size_ * 0.8660254f;
+  const float reach = cam_.max_range + infl;
+  int lo[3], hi[3];
+  for (int a = 0; a < 3; ++a) {
+    lo[a] = static_cast<int>(std::floor((tw[a] - reach) * block_size_inv_));
+    hi[a] = static_cast<int>(std::floor((tw[a] + reach) * block_size_inv_));
+  }
+  uint32_t mask = 0;
+  for (int bz = lo[2]; bz <= hi[2]; ++bz)
+    for (int by = lo[1]; by <= hi[1]; ++by)
+      for (int bx = lo[0]; bx <= hi[0]; ++bx) {
+        const float c[3] = {(static_cast<float>(bx) + 0.5f) * block_size_, (static_cast<float>(by) + 0.5f) * block_size_,
+                            (static_cast<float>(bz) + 0.5f) * block_size_};
+        float cC[3];
+        transform(R, t, c, cC);
+        if (!pointInFrustum(cC, infl)) continue;
+        mask |= 1u << (nranks_ > 1 ? owner(Idx3{bx, by, bz}) : 0);
+      }
+  return mask;
+}
+
 void Oracle::integrateFrame(const kb_frame& f, bool allocate_blocks, kb_frame_stats* stats) {
   if (!has_cam_) { error_ = "camera not set"; return; }
   if (f.stamp_ns == 0) { error_ = "stamp must be > 0"; return; }
@@ -298,7 +324,7 @@ void Oracle::integrateFrame(const kb_frame& f, bool allocate_blocks, kb_frame_st
           transform(R, t, c, cC);
           if (!pointInFrustum(cC, infl)) continue;
           const Idx3 idx{bx, by, bz};
-          if (nranks_ > 1 && blockOwner(idx, nranks_) != rank_) continue;  // block-hash shard (§8e)
+          if (nranks_ > 1 && owner(idx) != rank_) continue;  // block-hash / cell shard (§8e)
           if (!getBlock(idx)) ++n_new;
           todo.push_back(allocateBlock(idx));
         }
@@ -527,6 +553,15 @@ int Oracle::blockOwner(const Idx3& b, int nranks) {
   return static_cast<int>((shardMix64(key) >> 40) % static_cast<uint64_t>(nranks));
 }
 
+int Oracle::cellOwner(int bx, int by, int cell, int gx, int gy, int nranks) {
+  // restates csrc/kb_device.cuh cellOwner: floor division into cells, periodic gx x gy tiling
+  if (nranks <= 1 || cell < 1) return 0;
+  auto fdiv = [](int a, int b) { return (a >= 0 ? a : a - b + 1) / b; };
+  const int cx = fdiv(bx, cell), cy = fdiv(by, cell);
+  const int mx = ((cx % gx) + gx) % gx, my = ((cy % gy) + gy) % gy;
+  return (mx + gx * my) % nranks;
+}
+
 void Oracle::trackingBegin(uint64_t stamp, int32_t* out, int cap) {
   if (!has_trk_ || !map_.with_tracking) { error_ = "tracking not configured"; return; }
   open_pending_ = trackingPassLocal(stamp);
@@ -549,7 +584,7 @@ void Oracle::packHalo(const int32_t* all_pending, int cap_pending, int32_t* out,
       for (int k = 0; k < 27; ++k) {
         if (k == 13) continue;
         const Idx3 nb{buf[4 + 3 * i] + (k % 3 - 1), buf[4 + 3 * i + 1] + ((k / 3) % 3 - 1), buf[4 + 3 * i + 2] + (k / 9 - 1)};
-        if (blockOwner(nb, nranks_) != rank_) continue;
+        if (owner(nb) != rank_) continue;
         if (const Block* b = getBlock(nb)) publish.emplace(nb, b);
       }
   }
@@ -1035,7 +1070,7 @@ void Oracle::allocateBox(const int32_t mn[3], const int32_t mx[3]) {
   for (int x = mn[0]; x <= mx[0]; ++x)
     for (int y = mn[1]; y <= mx[1]; ++y)
       for (int z = mn[2]; z <= mx[2]; ++z) {
-        if (nranks_ > 1 && blockOwner(Idx3{x, y, z}, nranks_) != rank_) continue;
+        if (nranks_ > 1 && owner(Idx3{x, y, z}) != rank_) continue;
         allocateBlock(Idx3{x, y, z});
       }
 }

@@ -128,7 +128,13 @@ class Oracle {
   // ---- block-hash sharded protocol (our multi-GPU design, not in the reference). The oracle
   // implements it on host buffers with the layouts of csrc/kb_kernels.cuh::ShardExchange so that world-size-2
   // gloo tests can prove "union of the shards == the unsharded map" on CPU.
-  void setShard(int rank, int nranks) { rank_ = rank; nranks_ = nranks; }
+  void setShard(int rank, int nranks) { rank_ = rank; nranks_ = nranks; cell_ = 0; }
+  // kb_set_shard_cells: periodic tiling of cell x cell block cells (x/y) over a gx x gy grid of ranks.
+  void setShardCells(int rank, int nranks, int cell, int gx, int gy) { rank_ = rank; nranks_ = nranks; cell_ = cell; gx_ = gx; gy_ = gy; }
+  static int cellOwner(int bx, int by, int cell, int gx, int gy, int nranks);
+  int owner(const Idx3& b) const { return cell_ > 0 ? cellOwner(b.x, b.y, cell_, gx_, gy_, nranks_) : blockOwner(b, nranks_); }
+  // kb_frame_owners: ranks owning at least one block the frame's frustum test selects.
+  uint32_t frameOwners(const kb_frame& f) const;
   int rank() const { return rank_; }
   int nranks() const { return nranks_; }
   static int blockOwner(const Idx3& b, int nranks);
@@ -190,6 +196,7 @@ class Oracle {
   std::vector<PixKey> pix_keys_;
   std::vector<uint8_t> flags_scratch_;
   int rank_ = 0, nranks_ = 1;
+  int cell_ = 0, gx_ = 1, gy_ = 1;
   std::vector<ObjectCluster> object_clusters_;
   TrackMeasurements track_result_;
   std::vector<Block*> open_pending_;       // ever-free work list between trackingBegin and trackingFinish

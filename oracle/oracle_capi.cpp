@@ -277,6 +277,20 @@ int ko_set_shard(ko_handle* h, int rank, int nranks) {
   return KB_OK;
 }
 
+int ko_set_shard_cells(ko_handle* h, int rank, int nranks, int cell_blocks, int grid_x, int grid_y) {
+  if (!h || nranks < 1 || rank < 0 || rank >= nranks || cell_blocks < 0 || (cell_blocks > 0 && (grid_x < 1 || grid_y < 1))) return KB_ERR_INVALID;
+  if (cell_blocks == 0) h->o->setShard(rank, nranks); else h->o->setShardCells(rank, nranks, cell_blocks, grid_x, grid_y);
+  return KB_OK;
+}
+int ko_cell_owner(int32_t bx, int32_t by, int cell_blocks, int grid_x, int grid_y, int nranks) {
+  return Oracle::cellOwner(bx, by, cell_blocks, grid_x, grid_y, nranks);
+}
+int ko_frame_owners(ko_handle* h, const kb_frame* frames, int32_t n, uint32_t* owner_mask) {
+  if (!h || !frames || !owner_mask || n < 0 || h->o->nranks() > 32) return KB_ERR_INVALID;
+  for (int i = 0; i < n; ++i) owner_mask[i] = h->o->frameOwners(frames[i]);
+  return KB_OK;
+}
+
 int ko_block_owner(int32_t bx, int32_t by, int32_t bz, int nranks) { return Oracle::blockOwner(ko::Idx3{bx, by, bz}, nranks); }
 
 int ko_set_shard_capacity(ko_handle* h, int32_t pending_capacity, int32_t halo_capacity) {

@@ -1,0 +1,181 @@
+"""Spatially (cell-) sharded replay: khronos_b200/replay.py + kb_set_shard_cells / kb_frame_owners / kb_gather_*.
+CPU: the schedule (stripes, pulls, slots) on numpy pools, and the protocol between oracle shards — union of the shards ==
+the unsharded oracle map, checksum sums add up. GPU: product shards on one device ("virtual ranks", pools shared as
+same-process peers) with all three gather transports, bit-exact against the unsharded oracle."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from khronos_b200 import capi, synthetic as syn
+from khronos_b200.replay import PeerPools, StripedSchedule, rank_grid
+import harness as hs
+
+M64 = (1 << 64) - 1
+
+
+def _stream(n=48):
+    cam = hs.small_camera(4)
+    scene = syn.hall_scene(size=(20.0, 16.0, 6.0))
+    poses, stamps = syn.sweep_trajectory(n, size=(20.0, 16.0), margin=4.0, lanes=2, yaw_turns=2.0)
+    return cam, hs.render_frames(scene, cam, poses, stamps), poses, stamps
+
+
+def test_rank_grid():
+    assert [rank_grid(n) for n in (1, 2, 4, 6, 8)] == [(1, 1), (2, 1), (2, 2), (3, 2), (4, 2)]
+
+
+def test_cell_owner_tiling(oracle_lib):
+    seen = set()
+    for bx in range(-20, 20):
+        for by in range(-20, 20):
+            o = oracle_lib.ko_cell_owner(bx, by, 4, 4, 2, 8)
+            assert 0 <= o < 8
+            # all blocks of a cell share the owner; floor division for negative indices
+            assert o == oracle_lib.ko_cell_owner((bx // 4) * 4, (by // 4) * 4, 4, 4, 2, 8)
+            assert o == ((bx // 4) % 4) + 4 * ((by // 4) % 2)
+            seen.add(o)
+    assert seen == set(range(8))
+
+
+def test_schedule_moves_the_right_frames():
+    """Numpy pools: after executing the plan's pulls every frame a rank needs is where the plan says it is."""
+    world, stripe, lap, P = 3, 4, 50, 5
+    rng = np.random.default_rng(1)
+    owner_mask = rng.integers(1, 1 << world, size=lap).astype(np.uint32)
+    scheds = [StripedSchedule(world, r, stripe) for r in range(world)]
+    pools = []
+    for s in scheds:
+        res = s.resident(lap)
+        assert [s.local_index(g) for g in res] == list(range(len(res)))
+        pools.append(np.array([[g * 10 + k for k in range(P)] for g in res]))
+    assert sorted(g for s in scheds for g in s.resident(lap)) == list(range(lap))
+    step = [(7 + j) % lap for j in range(lap)]  # a step that wraps around the lap
+    for r, s in enumerate(scheds):
+        plan = s.plan(step, owner_mask)
+        rx = np.full((max(plan.n_remote, 1), P), -1)
+        for (src, li, slot, cnt) in plan.ranges:
+            assert src != r
+            rx[slot:slot + cnt] = pools[src][li:li + cnt]
+        want = [g for g in step if (owner_mask[g] >> r) & 1]
+        assert [g for _, g, _ in plan.mine] == want
+        assert [j for j, _, _ in plan.mine] == sorted(j for j, _, _ in plan.mine)
+        for j, g, slot in plan.mine:
+            row = rx[slot] if slot >= 0 else pools[r][-slot - 1]
+            assert row[0] == g * 10 and step[j] == g
+        assert plan.n_remote == sum(1 for g in want if s.home(g) != r)
+
+
+@pytest.mark.parametrize("world,cell", [(2, 10), (4, 8), (8, 5)])
+def test_oracle_cell_shards_equal_unsharded(oracle_lib, world, cell):
+    cam, frames, poses, stamps = _stream(40)
+    gx, gy = rank_grid(world)
+    ref = hs.make_handle(oracle_lib, "ko_", cam=cam)
+    hs.run_fusion(ref, frames, poses, stamps)
+    want = ref.map_checksum()
+    shards = []
+    for r in range(world):
+        h = hs.make_handle(oracle_lib, "ko_", cam=cam)
+        h.set_shard_cells(r, world, cell, gx, gy)
+        shards.append(h)
+    fr0 = [shards[0].make_frame(d, T, st, label=l) for (d, l), T, st in zip(frames, poses, stamps)]
+    masks = shards[0].frame_owners(fr0)
+    assert all(0 < int(m) < (1 << world) for m in masks)
+    assert any(bin(int(m)).count("1") < world for m in masks), "cell sharding should spare some ranks some frames"
+    total = [0, 0, 0, 0]
+    for r, h in enumerate(shards):
+        sched = StripedSchedule(world, r, stripe=8)
+        plan = sched.plan(list(range(len(frames))), masks)
+        for _, g, _ in plan.mine:  # each shard integrates only the frames it needs, in stream order
+            d, l = frames[g]
+            h.integrate_frame(h.make_frame(d, poses[g], stamps[g], label=l), want_stats=False)
+        c = h.map_checksum()
+        total = [(total[0] + c[0]) & M64, total[1] ^ c[1], total[2] + c[2], total[3] + c[3]]
+        # a frame the mask spares a rank would have found no owned block there
+        skipped = [g for g in range(len(frames)) if not (int(masks[g]) >> r) & 1]
+        for g in skipped[:3]:
+            d, l = frames[g]
+            probe = hs.make_handle(oracle_lib, "ko_", cam=cam)
+            probe.set_shard_cells(r, world, cell, gx, gy)
+            assert probe.integrate_frame(probe.make_frame(d, poses[g], stamps[g], label=l)).blocks_in_frustum == 0
+    assert tuple(total) == want
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_product_virtual_ranks_pull_and_fuse(oracle_lib, product_lib, mode):
+    """4 product shards on one device; every shard keeps a stripe of the stream in its own pool and pulls the rest through
+    a gather plan (mode 0 copy engines, 1 SM loads/stores, 2 cp.async.bulk pipeline). Union == unsharded oracle."""
+    import torch
+    world, cell, stripe = 4, 8, 8
+    cam, frames, poses, stamps = _stream(48)
+    n = len(frames)
+    gx, gy = rank_grid(world)
+    ref = hs.make_handle(oracle_lib, "ko_", cam=cam)
+    hs.run_fusion(ref, frames, poses, stamps)
+    want = ref.map_checksum()
+    dev = torch.device("cuda", 0)
+    H, W = cam.height, cam.width
+    scheds = [StripedSchedule(world, r, stripe) for r in range(world)]
+    pools = []
+    for r, s in enumerate(scheds):
+        res = s.resident(n)
+        pool = PeerPools(product_lib, 0, len(res), H, W)
+        dv, lv = pool.views(torch, dev)
+        for li, g in enumerate(res):
+            dv[li].copy_(torch.from_numpy(frames[g][0]))
+            lv[li].copy_(torch.from_numpy(frames[g][1]))
+        pools.append(pool)
+    torch.cuda.synchronize()
+    for r in range(world):
+        for q in range(world):
+            if q != r:
+                pools[r].add_local_peer(q, pools[q].ptr, pools[q].n)
+    handles = []
+    for r in range(world):
+        h = hs.make_handle(product_lib, "kb_", cam=cam)
+        h.set_shard_cells(r, world, cell, gx, gy)
+        handles.append(h)
+    fr0 = [handles[0].make_frame(None, T, st) for T, st in zip(poses, stamps)]
+    masks = handles[0].frame_owners(fr0)
+    fo = [ref.make_frame(d, T, st, label=l) for (d, l), T, st in zip(frames, poses, stamps)]
+    exact = hs.make_handle(oracle_lib, "ko_", cam=cam)
+    exact.set_shard_cells(0, world, cell, gx, gy)
+    exact_masks = exact.frame_owners(fo)
+    assert all(int(a) & int(b) == int(b) for a, b in zip(masks, exact_masks)), "kb_frame_owners must be a superset of the exact selection"
+    total = [0, 0, 0, 0]
+    stream = torch.cuda.current_stream().cuda_stream
+    for r, h in enumerate(handles):
+        plan = scheds[r].plan(list(range(n)), masks)
+        cap = max(plan.n_remote, 1)
+        rx = PeerPools(product_lib, 0, cap, H, W)
+        gp = pools[r].gather_plan(plan.ranges, rx.ptr, cap)
+        assert pools[r].plan_bytes(gp) == plan.n_remote * H * W * 8
+        pools[r].run(gp, mode, 8, stream)
+        torch.cuda.synchronize()
+        batch = []
+        for _, g, slot in plan.mine:
+            base, cnt, i = (rx.ptr, cap, slot) if slot >= 0 else (pools[r].ptr, pools[r].n, -slot - 1)
+            batch.append(h.make_frame(pools[r].depth_ptr(base, cnt, i), poses[g], stamps[g], label=pools[r].label_ptr(base, cnt, i),
+                                      memory=capi.MEM_DEVICE))
+        for b0 in range(0, len(batch), 32):
+            h.integrate_frames(batch[b0:b0 + 32], want_stats=False)
+        c = h.map_checksum()
+        total = [(total[0] + c[0]) & M64, total[1] ^ c[1], total[2] + c[2], total[3] + c[3]]
+        product_lib.kb_gather_plan_destroy(gp)
+        rx.close()
+    assert tuple(total) == want
+    # and block by block against the unsharded oracle
+    bo = ref.export_blocks()
+    parts = [h.export_blocks() for h in handles]
+    assert sum(p.n for p in parts) == bo.n
+    idx = {tuple(b): i for i, b in enumerate(bo.block_index.reshape(-1, 3).tolist())}
+    for p in parts:
+        for k, b in enumerate(p.block_index.reshape(-1, 3).tolist()):
+            i = idx[tuple(b)]
+            np.testing.assert_array_equal(p.distance[k].view(np.uint32), bo.distance[i].view(np.uint32))
+            np.testing.assert_array_equal(p.weight[k].view(np.uint32), bo.weight[i].view(np.uint32))
+            np.testing.assert_array_equal(p.semantic_label[k], bo.semantic_label[i])
+            np.testing.assert_array_equal(p.last_observed[k], bo.last_observed[i])
+    for p in pools:
+        p.close()

@@ -145,3 +145,87 @@ def test_world_size_2_gloo_sharded_pipeline():
                 p.kill()
     assert status == "ok", status
     assert sum(sizes) == n and min(sizes) > 0
+
+
+def _replay_worker(rank, world, port, q):
+    """Cell-sharded striped replay (khronos_b200/replay.py) over a real process group: every rank holds only its stripe
+    of the stream, computes the owner masks, pulls the frames it needs (the all-gathered pools stand in for the CUDA IPC
+    mappings the GPU build reads through) and integrates its sub-sequence with an oracle shard; the all-gathered
+    checksums must add up to the unsharded oracle map's."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    torch.set_num_threads(1)
+    import ctypes
+    from khronos_b200 import synthetic as syn
+    from khronos_b200.replay import StripedSchedule, rank_grid
+    import harness as hs
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        cam = hs.small_camera(8)
+        n, stripe, cell = 32, 4, 10
+        scene = syn.hall_scene(size=(20.0, 16.0, 6.0))
+        poses, stamps = syn.sweep_trajectory(n, size=(20.0, 16.0), margin=4.0, lanes=2, yaw_turns=1.5)
+        sched = StripedSchedule(world, rank, stripe)
+        res = sched.resident(n)
+        mine_rendered = hs.render_frames(scene, cam, [poses[g] for g in res], [stamps[g] for g in res])  # only the own stripe
+        pool_d = torch.from_numpy(np.stack([f[0] for f in mine_rendered]))
+        pool_l = torch.from_numpy(np.stack([f[1] for f in mine_rendered]))
+        sizes = [None] * world
+        dist.all_gather_object(sizes, len(res))
+        cap = max(sizes)
+        pad_d = torch.zeros((cap,) + pool_d.shape[1:], dtype=pool_d.dtype); pad_d[:len(res)] = pool_d
+        pad_l = torch.zeros((cap,) + pool_l.shape[1:], dtype=pool_l.dtype); pad_l[:len(res)] = pool_l
+        peers_d = [torch.zeros_like(pad_d) for _ in range(world)]
+        peers_l = [torch.zeros_like(pad_l) for _ in range(world)]
+        dist.all_gather(peers_d, pad_d)
+        dist.all_gather(peers_l, pad_l)
+        oracle = ctypes.CDLL(os.path.join(ROOT, "oracle", "liboracle.so"))
+        gx, gy = rank_grid(world)
+        h = hs.make_handle(oracle, "ko_", cam=cam)
+        h.set_shard_cells(rank, world, cell, gx, gy)
+        masks = h.frame_owners([h.make_frame(None, poses[g], stamps[g]) for g in range(n)])
+        plan = sched.plan(list(range(n)), masks)
+        rx_d = torch.zeros((max(plan.n_remote, 1),) + pool_d.shape[1:], dtype=pool_d.dtype)
+        rx_l = torch.zeros((max(plan.n_remote, 1),) + pool_l.shape[1:], dtype=pool_l.dtype)
+        for (src, li, slot, cnt) in plan.ranges:
+            rx_d[slot:slot + cnt] = peers_d[src][li:li + cnt]
+            rx_l[slot:slot + cnt] = peers_l[src][li:li + cnt]
+        for _, g, slot in plan.mine:
+            d, l = (rx_d[slot], rx_l[slot]) if slot >= 0 else (pool_d[-slot - 1], pool_l[-slot - 1])
+            h.integrate_frame(h.make_frame(d.numpy(), poses[g], stamps[g], label=l.numpy()), want_stats=False)
+        cs = [None] * world
+        dist.all_gather_object(cs, (h.map_checksum(), len(plan.mine), plan.n_remote))
+        if rank == 0:
+            ref = hs.make_handle(oracle, "ko_", cam=cam)
+            hs.run_fusion(ref, hs.render_frames(scene, cam, poses, stamps), poses, stamps)
+            want = ref.map_checksum()
+            M = (1 << 64) - 1
+            got = (sum(c[0][0] for c in cs) & M, cs[0][0][1] ^ cs[1][0][1], sum(c[0][2] for c in cs), sum(c[0][3] for c in cs))
+            ok = got == want and all(c[1] > 0 for c in cs) and sum(c[1] for c in cs) < world * n and any(c[2] > 0 for c in cs)
+            q.put(("ok" if ok else f"mismatch {got} vs {want}, frames {[c[1:] for c in cs]}", [c[1] for c in cs], n))
+    except Exception as e:  # pragma: no cover
+        import traceback
+        q.put(("error on rank %d: %r %s" % (rank, e, traceback.format_exc()[-400:]), [], 0))
+        os._exit(1)
+    dist.destroy_process_group()
+
+
+def test_world_size_2_gloo_cell_sharded_replay():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_replay_worker, args=(r, 2, port, q), daemon=True) for r in range(2)]
+    for p in procs:
+        p.start()
+    try:
+        status, sizes, n = q.get(timeout=240)
+    finally:
+        for p in procs:
+            p.join(timeout=20)
+        for p in procs:
+            if p.is_alive():
+                p.kill()
+    assert status == "ok", status
+    assert max(sizes) <= n and min(sizes) > 0

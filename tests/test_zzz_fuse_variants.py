@@ -1,4 +1,6 @@
-"""Experimental fuse-kernel variants (all off by default, selected by environment variables read in kb_create):
+"""Fuse-kernel variants, selected by environment variables read in kb_create. Since round 2 KB_PIPELINE, KB_FUSE_ITEM_LIST,
+KB_EVERFREE_V2 and KB_MOTION_SPARSE are ON by default (measured wins, profiles/r2_ab1_summary.txt), so the rest of the suite runs
+them and this file also runs the former defaults (=0); KB_FUSE_MLP and KB_H2D_NARROW_LABELS lost their A/Bs and stay off:
   KB_FUSE_ITEM_LIST=1  items come from compacted heaviest-first lists instead of the dense box range
   KB_PIPELINE=1        the prologue (tile pyramid, K0, K0b) of batch i+1 runs on its own stream while the fuse kernel of
                        batch i is busy; work lists, pyramids and cursors are double-buffered by batch parity
@@ -19,7 +21,8 @@ pytestmark = pytest.mark.gpu
 
 VARIANTS = [{"KB_FUSE_ITEM_LIST": "1"}, {"KB_FUSE_MLP": "2"}, {"KB_FUSE_MLP": "4"}, {"KB_FUSE_MLP": "4", "KB_FUSE_ITEM_LIST": "1"},
             {"KB_PIPELINE": "1"}, {"KB_PIPELINE": "1", "KB_FUSE_MLP": "4", "KB_FUSE_ITEM_LIST": "1", "KB_FUSE_CTAS_PER_SM": "3"},
-            {"KB_H2D_NARROW_LABELS": "1", "KB_H2D_THREADS": "3"}]
+            {"KB_H2D_NARROW_LABELS": "1", "KB_H2D_THREADS": "3"},
+            {"KB_PIPELINE": "0", "KB_FUSE_ITEM_LIST": "0"}, {"KB_PIPELINE": "0"}, {"KB_FUSE_ITEM_LIST": "0"}]
 
 
 @pytest.fixture(params=VARIANTS, ids=lambda v: "+".join(f"{k.replace('KB_', '').replace('FUSE_', '')}={x}" for k, x in v.items()))
@@ -139,11 +142,12 @@ def test_narrowed_labels_fall_back_for_out_of_range_ids(oracle_lib, product_lib)
         os.environ.pop("KB_H2D_NARROW_LABELS", None)
 
 
-def test_motion_sparse_table_variant(oracle_lib, product_lib):
+@pytest.mark.parametrize("sparse", ["1", "0"])
+def test_motion_sparse_table_variant(oracle_lib, product_lib, sparse):
     """KB_MOTION_SPARSE=1: the clustering table is reset slot by slot after each frame instead of wholesale before it; the
     object detector (shared table memory) is interleaved on some frames to exercise the dirty -> full reset transition,
     including frames without seeds right after it."""
-    os.environ["KB_MOTION_SPARSE"] = "1"
+    os.environ["KB_MOTION_SPARSE"] = sparse
     try:
         import test_sharded_pipeline as tsp
         from test_object_detection_oracle import OBJECTS
@@ -172,9 +176,10 @@ def test_motion_sparse_table_variant(oracle_lib, product_lib):
         os.environ.pop("KB_MOTION_SPARSE", None)
 
 
-def test_everfree_v2_variant(oracle_lib, product_lib):
+@pytest.mark.parametrize("v2", ["1", "0"])
+def test_everfree_v2_variant(oracle_lib, product_lib, v2):
     """KB_EVERFREE_V2=1: vectorised halo fill of the ever-free pass; all three connectivities."""
-    os.environ["KB_EVERFREE_V2"] = "1"
+    os.environ["KB_EVERFREE_V2"] = v2
     try:
         import test_sharded_pipeline as tsp
         cam = hs.small_camera(4)
