@@ -66,6 +66,18 @@ def parse_args():
                     help="f32 = depth f32 + label i32 (hydra::InputData, 8 B/pixel; the headline); compact = u16 millimetre "
                          "depth + u8 labels (3 B/pixel, expanded on the device): what crosses PCIe / NVLink; f32u8 (N > 1 only, "
                          "experiment): lossless 5 B/pixel broadcast, depth f32 + labels narrowed to u8 on the ingest rank")
+    ap.add_argument("--shard", default="cells", choices=["cells", "hash"],
+                    help="N > 1: 'cells' = spatial cell sharding, stream striped over the ranks' pools, frames pulled over NVLink "
+                         "only by the ranks whose cells they touch (khronos_b200/replay.py); 'hash' = round-1 design: per-block hash "
+                         "sharding, every frame broadcast to every rank from rank 0")
+    ap.add_argument("--cell-blocks", type=int, default=16, help="--shard cells: cell side in blocks (16 = 12.8 m at 5 cm voxels)")
+    ap.add_argument("--stripe", type=int, default=32, help="--shard cells: consecutive frames per rank in the striped pools")
+    ap.add_argument("--gather", default="ce", choices=["ce", "sm", "bulk"],
+                    help="--shard cells: transport of the NVLink pulls: copy engines, SM load/store kernel, cp.async.bulk kernel")
+    ap.add_argument("--gather-ctas", type=int, default=32)
+    ap.add_argument("--ingest", default="striped", choices=["striped", "rank0"],
+                    help="--shard cells: where the stream is resident: striped over all ranks' pools (default) or all on rank 0 "
+                         "(A/B: rank 0's NVLink egress then bounds the exchange)")
     ap.add_argument("--small", action="store_true", help="tiny configuration for functional checks")
     ap.add_argument("--workload", default="hall640", choices=["hall640", "hall1280", "dynamic"],
                     help="hall640 = BASELINE config[1] (fusion only, the headline, used for every --gpus N); hall1280 = "
@@ -468,6 +480,280 @@ def emit(obj):
     print(json.dumps(obj), flush=True)
 
 
+def load_capture():
+    """Per-launch DRAM traffic / issue utilisation of the dominant kernel from THIS round's `ncu --set full` capture
+    (profiles/r2_fuse_capture.json, written by tools/ncu_digest.py from the committed csv export). None if absent."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r2_fuse_capture.json")))
+    except Exception:
+        return None
+
+
+def hbm_peak():
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    except Exception:
+        return 6650.0, "fallback 6650 (of fallback)"
+
+
+def roofline_block(args, B, n_calls, gpu_ms, sampled_us, nv, nsem, nblk, n_frames, P, bpp, world=1):
+    """roofline of the dominant kernel group (one kb_integrate_frames call = tile pyramid + K0 + K0b + item lists + fuse
+    kernel for B frames). achieved = algorithmic bytes of the timed region / device time of the timed region (every
+    launch inside it belongs to such a group, and with the pipelined prologue the groups overlap, so the region average
+    is the only well-defined per-group duration); launch_us_sampled = CUDA events around individual calls."""
+    peak, src = hbm_peak()
+    total_bytes = algorithmic_bytes(nv, nsem, nblk, n_frames * P, bpp=bpp)
+    per_launch = total_bytes / max(n_calls, 1)
+    avg_us = gpu_ms * 1e3 / max(n_calls, 1)
+    achieved = total_bytes / (gpu_ms * 1e-3) / 1e9
+    cap = load_capture()
+    traffic = issue = None
+    if cap and cap.get("frames_per_launch") == B and args.workload == "hall640" and not args.small and world == 1:
+        traffic = cap.get("dram_bytes_per_launch_group")
+        issue = cap.get("fuse_issue_slot_utilization_pct")
+    out = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+           "kernel": "fuseKernel<16> + its prologue (tileMax, tilePyramid, selectBlocks, itemCull, itemCompact): one group per %d frames" % B,
+           "launch_us": avg_us, "launch_us_sampled": sampled_us, "algorithmic_bytes_per_launch": per_launch,
+           "peak_source": src,
+           "note": "the kernel is issue-bound, not HBM-bound (DRAM traffic is below the algorithmic bytes: the working set is L2 "
+                   "resident); frac_dram = measured DRAM bytes / time / peak, issue_slot_utilization from the same ncu capture"}
+    if traffic:
+        out["frac_dram"] = traffic / (avg_us * 1e-6) / 1e9 / peak
+    if issue is not None:
+        out["issue_slot_utilization_pct"] = issue
+    return out
+
+
+def combine_checksums(parts):
+    """parts: per-rank (sum, xor, blocks, observed) -> the unsharded map's checksum (sums wrap mod 2^64)."""
+    m = (1 << 64) - 1
+    x = 0
+    for p in parts:
+        x ^= int(p[1])
+    return {"sum": "%016x" % (sum(int(p[0]) for p in parts) & m), "xor": "%016x" % x,
+            "blocks": int(sum(int(p[2]) for p in parts)), "observed_voxels": int(sum(int(p[3]) for p in parts))}
+
+
+def main_hall_cells(args, world, rank, local_rank, dev):
+    """N > 1, --shard cells (khronos_b200/replay.py): cell-sharded map, stream striped over the ranks' frame pools, every
+    rank pulls the frames whose frustum touches its cells over NVLink (CUDA IPC peer mappings) and fuses its sub-sequence
+    in stream order, double buffered against the pulls of the next step. Returns None after printing the result line,
+    or a string (reason) when peer memory cannot be set up, in which case the caller falls back to --shard hash."""
+    import torch
+    import torch.distributed as dist
+    import khronos_b200 as kb
+    from khronos_b200 import capi, synthetic as syn
+    from khronos_b200.replay import PeerPools, StripedSchedule, rank_grid
+
+    lib = kb.lib()
+    F, K, Wm = args.frames_per_step, args.steps, args.warmup
+    if args.small:
+        F = min(F, 64)
+        args.lap_frames = min(args.lap_frames, 256)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    cam, scene, poses, stamps = workload(args)
+    lap, H, W = len(poses), cam.height, cam.width
+    P = H * W
+    bpp = BYTES_PER_PIXEL_IN
+    stripe = args.stripe if args.ingest == "striped" else lap * 2  # rank0 ingest = one stripe holding the whole lap
+    sched = StripedSchedule(world, rank, stripe)
+    res = sched.resident(lap)
+
+    # ---- this rank's stripe of the stream, rendered straight into its (IPC-shareable) pool
+    t_render = time.perf_counter()
+    note = None
+    try:
+        pool = PeerPools(lib, local_rank, len(res), H, W)
+        dv, lv = pool.views(torch, dev)
+        t0s = stamps[0]
+        for li, g in enumerate(res):
+            d, l = syn.render(scene, cam, poses[g], (stamps[g] - t0s) * 1e-9, device=dev, dtype=torch.float32)
+            dv[li].copy_(d)
+            lv[li].copy_(l)
+        torch.cuda.synchronize()
+        hb = torch.tensor(list(pool.export_handle()), dtype=torch.uint8, device=dev)
+        hs_all = [torch.empty_like(hb) for _ in range(world)]
+        dist.all_gather(hs_all, hb)
+        nres = torch.tensor([len(res)], dtype=torch.int64, device=dev)
+        n_all = [torch.empty_like(nres) for _ in range(world)]
+        dist.all_gather(n_all, nres)
+        for q in range(world):
+            if q != rank:
+                pool.open_peer(q, bytes(hs_all[q].cpu().tolist()), int(n_all[q].item()))
+    except Exception as e:  # noqa: BLE001 - any failure of the peer set-up selects the fallback on ALL ranks
+        note = "peer memory unavailable (%s)" % str(e)[:160]
+    flag = torch.tensor([1 if note else 0], device=dev)
+    dist.all_reduce(flag)
+    if int(flag.item()):
+        return note or "peer memory unavailable on another rank"
+    t_render = time.perf_counter() - t_render
+
+    mc, ic = map_configs(args)
+    h = kb.create_map(mc, ic, capi.default_tracking_config(), None, device=local_rank)
+    h.set_camera(cam)
+    if args.no_cull:
+        h.set_culling(False)
+    gx, gy = rank_grid(world)
+    h.set_shard_cells(rank, world, args.cell_blocks, gx, gy)
+    stream = torch.cuda.Stream(device=dev)
+    xstream = torch.cuda.Stream(device=dev)
+    h.set_stream(stream.cuda_stream)
+    B = max(1, min(args.batch, F))
+
+    def frame_index(step, j):
+        return (step * F + j) % lap
+
+    def stamp_of(step, j):
+        return 1_000_000_000 + (step * F + j) * 33_333_333
+
+    # ---- schedule: which frames this rank needs (pure pose arithmetic), pulls, frame descriptors — all outside the timed region
+    masks = h.frame_owners([h.make_frame(None, poses[g], stamps[g]) for g in range(lap)])
+    plans = {s: sched.plan([frame_index(s, j) for j in range(F)], masks) for s in range(Wm + K)}
+    cap = max(1, max(p.n_remote for p in plans.values()))
+    rx = [PeerPools(lib, local_rank, cap, H, W) for _ in range(2)]
+    mode = {"ce": 0, "sm": 1, "bulk": 2}[args.gather]
+    gplans = {s: pool.gather_plan(plans[s].ranges, rx[s % 2].ptr, cap) for s in plans}
+    calls = {}
+    for s, pl in plans.items():
+        fr = []
+        for j, g, slot in pl.mine:
+            base, cnt, i = (rx[s % 2].ptr, cap, slot) if slot >= 0 else (pool.ptr, pool.n, -slot - 1)
+            fr.append(h.make_frame(pool.depth_ptr(base, cnt, i), poses[g], stamp_of(s, j), label=pool.label_ptr(base, cnt, i),
+                                   memory=capi.MEM_DEVICE))
+        calls[s] = [((capi.Frame * len(fr[k:k + B]))(*fr[k:k + B]), len(fr[k:k + B])) for k in range(0, len(fr), B)]
+    integrate_n = h._fn("integrate_frames")
+    hptr = h._h
+    ready, gather_ev, buf_free, issued = {}, {}, [None, None], set()
+
+    def issue_gather(s):
+        b = s % 2
+        if buf_free[b] is not None:
+            xstream.wait_event(buf_free[b])  # the fusion of step s-2 no longer reads rx[b]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(xstream)
+        pool.run(gplans[s], mode, args.gather_ctas, xstream.cuda_stream)
+        e1.record(xstream)
+        gather_ev[s] = (e0, e1)
+        ready[s] = e1
+        issued.add(s)
+
+    def run_step(s, last_of_phase, samples=None):
+        if s not in issued:
+            issue_gather(s)
+        if not last_of_phase and (s + 1) in plans and (s + 1) not in issued:
+            issue_gather(s + 1)  # overlaps this step's fusion
+        stream.wait_event(ready[s])
+        with torch.cuda.stream(stream):
+            for k, (arr, n) in enumerate(calls[s]):
+                if samples is not None and k % 4 == 2 and n == B:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(stream)
+                    st = integrate_n(hptr, arr, n, 1, None)
+                    e1.record(stream)
+                    samples.append((e0, e1))
+                else:
+                    st = integrate_n(hptr, arr, n, 1, None)
+                if st != 0:
+                    raise RuntimeError(f"kb_integrate_frames failed: {st}")
+        ev = torch.cuda.Event()
+        ev.record(stream)
+        buf_free[s % 2] = ev
+
+    def barrier():
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    for s in range(Wm):
+        run_step(s, s == Wm - 1)
+    barrier()
+    t64_0 = h.get_totals64()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    samples = []
+    wall0 = time.perf_counter()
+    ev0.record(stream)
+    for s in range(Wm, Wm + K):
+        run_step(s, s == Wm + K - 1, samples)
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    busy_ms = ev0.elapsed_time(ev1)
+    dist.barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop(wall0, wall0 + wall) if rank == 0 else None
+    t = torch.tensor([busy_ms], device=dev, dtype=torch.float64)
+    all_busy = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(all_busy, t)
+    busy = [float(x.item()) for x in all_busy]
+    gpu_ms = max(busy)  # device time of the timed region, max over ranks
+    t64_1 = h.get_totals64()
+    if t64_1.capacity_exceeded:
+        raise SystemExit("bench.py: block pool exhausted (capacity_exceeded): results incomplete")
+    cs = h.map_checksum()
+    n_frames = K * F
+    my_frames = sum(len(plans[s].mine) for s in range(Wm, Wm + K))
+    my_remote = sum(plans[s].n_remote for s in range(Wm, Wm + K))
+    g_ms = sum(gather_ev[s][0].elapsed_time(gather_ev[s][1]) for s in range(Wm, Wm + K))
+    g_bytes = sum(pool.plan_bytes(gplans[s]) for s in range(Wm, Wm + K))
+    nv = t64_1.voxels_updated - t64_0.voxels_updated
+    nsem = t64_1.voxels_semantic - t64_0.voxels_semantic
+    nblk = t64_1.blocks_in_frustum - t64_0.blocks_in_frustum
+    stats = torch.tensor([float(nv), float(nsem), float(nblk), float(my_frames), float(my_remote), g_ms, float(g_bytes),
+                          float(t64_1.total_blocks)], device=dev, dtype=torch.float64)
+    all_stats = [torch.empty_like(stats) for _ in range(world)]
+    dist.all_gather(all_stats, stats)
+    cst = torch.tensor([int(c) - (1 << 64) if int(c) >= (1 << 63) else int(c) for c in cs], device=dev, dtype=torch.int64)
+    all_cs = [torch.empty_like(cst) for _ in range(world)]
+    dist.all_gather(all_cs, cst)
+
+    if rank == 0:
+        A = np.array([x.cpu().numpy() for x in all_stats])
+        parts = [[int(v) & ((1 << 64) - 1) for v in c.cpu().tolist()] for c in all_cs]
+        fps = n_frames / (gpu_ms * 1e-3)
+        full = [a.elapsed_time(b) for a, b in samples]
+        n_calls = sum(len(calls[s]) for s in range(Wm, Wm + K))
+        roof = roofline_block(args, B, n_calls, busy[0], float(np.mean(full) * 1e3) if full else None, nv, nsem, nblk,
+                              my_frames, P, bpp, world=world)
+        gbps = [float(A[r, 6] / (A[r, 5] * 1e-3) / 1e9) if A[r, 5] > 0 else 0.0 for r in range(world)]
+        out = {
+            "metric": "rgbd_frames_per_sec_integrated", "value": fps, "unit": "frames/s", "n_gpus": world,
+            "steps": K, "warmup": Wm, "ms_per_step": gpu_ms / K, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload if not args.small else "hall160-small", "image": [W, H], "voxel_size": mc.voxel_size,
+                       "voxels_per_side": 16, "truncation": mc.truncation_distance, "semantics": f"MLE L={L_LABELS}",
+                       "frames_per_step": F, "frames_per_call": B, "wire_format": "depth f32 + label i32 (8 B/px)", "lap_frames": lap,
+                       "live_blocks_all_ranks": int(A[:, 7].sum()),
+                       "l2": "inputs larger than L2: each step streams %.1f GB of frames" % (F * P * bpp / 1e9),
+                       "parallelism": "cell shard x%d (cells of %d x %d blocks = %.1f m, %d x %d rank tiling); stream resident %s; every rank pulls the "
+                                      "frames that touch its cells over NVLink (CUDA IPC peer mappings, transport: %s) and fuses them in stream order; "
+                                      "no collective in the data path" % (world, args.cell_blocks, args.cell_blocks, args.cell_blocks * mc.voxel_size * 16,
+                                                                       gx, gy, ("striped over the ranks' pools (%d-frame stripes)" % stripe) if args.ingest == "striped"
+                                                                       else "on rank 0", args.gather),
+                       "render_s": round(t_render, 1)},
+            "per_frame": {"voxels_updated": float(A[:, 0].sum()) / n_frames, "voxels_semantic": float(A[:, 1].sum()) / n_frames,
+                          "blocks_visited": float(A[:, 2].sum()) / n_frames, "frame_deliveries": float(A[:, 3].sum()) / n_frames},
+            "shards": {"frames_per_rank": [int(x) for x in A[:, 3]], "remote_frames_per_rank": [int(x) for x in A[:, 4]],
+                       "busy_ms_per_rank": [round(x, 2) for x in busy], "blocks_per_rank": [int(x) for x in A[:, 7]]},
+            "exchange": {"kind": "one-sided NVLink pull (kb_gather_run), overlapped with the previous step's fusion",
+                         "bytes_pulled_all_ranks": float(A[:, 6].sum()), "gbps_per_rank": [round(x, 1) for x in gbps],
+                         "gather_ms_per_rank": [round(float(x), 2) for x in A[:, 5]],
+                         "reference_gbps": 770.0, "reference": "measured peer copy per direction (B200_PROFILING.md)"},
+            "checksum": combine_checksums(parts),
+            "roofline": roof, "cpu_baseline": None, "e2e": None, "gpu_launches": 6 * n_calls, "clocks": clocks, "wall_s_timed": wall,
+        }
+        emit(out)
+    dist.barrier()
+    for s in gplans:
+        lib.kb_gather_plan_destroy(gplans[s])
+    h.close()
+    for r_ in rx:
+        r_.close()
+    pool.close()
+    return None
+
+
 def main():
     args = parse_args()
     quiet_stdout()
@@ -492,6 +778,13 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    shard_note = None
+    if world > 1 and args.shard == "cells":
+        shard_note = main_hall_cells(args, world, rank, local_rank, dev)
+        if shard_note is None:
+            dist.destroy_process_group()
+            return
+        # peer memory unavailable on this box: fall back to the round-1 design (hash shard + NCCL broadcast)
     F, K, Wm = args.frames_per_step, args.steps, args.warmup
     if args.small:
         F = min(F, 64)
@@ -672,8 +965,7 @@ def main():
     for s in range(Wm):
         run_step(s)
     barrier()
-    tot0 = h.get_totals()
-    dbg0 = h.get_debug_counters()
+    t64_0 = h.get_totals64()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     samples = []
     wall0 = time.perf_counter()
@@ -691,40 +983,33 @@ def main():
         t = torch.tensor([wall * 1e3], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         gpu_ms = float(t.item())
-    tot1 = h.get_totals()
-    dbg1 = h.get_debug_counters()
-    pairs = int((int(dbg1[17]) - int(dbg0[17])) & 0xFFFFFFFF)
-
-    def delta(name):
-        return (getattr(tot1, name) - getattr(tot0, name)) & 0xFFFFFFFF
-
+    t64_1 = h.get_totals64()
+    if t64_1.capacity_exceeded:
+        raise SystemExit("bench.py: block pool exhausted (capacity_exceeded): results incomplete")
+    # order-independent checksum of the map after the timed region (same value for every --gpus N: the bench verifies itself)
+    cs = h.map_checksum()
+    pairs = t64_1.block_frame_pairs - t64_0.block_frame_pairs
     n_frames = K * F
-    nv, nsem, nblk = delta("voxels_updated"), delta("voxels_semantic"), delta("blocks_in_frustum")
+    # 64-bit cumulative counters (kb_get_totals64): the 32-bit ones wrap after ~36 k frames of this workload
+    nv = t64_1.voxels_updated - t64_0.voxels_updated
+    nsem = t64_1.voxels_semantic - t64_0.voxels_semantic
+    nblk = t64_1.blocks_in_frustum - t64_0.blocks_in_frustum
     if world > 1:
         t = torch.tensor([nv, nsem, nblk], device=dev, dtype=torch.float64)
         dist.all_reduce(t)
         nv_all, nsem_all, nblk_all = [float(x) for x in t.tolist()]
+        cst = torch.tensor([int(c) - (1 << 64) if int(c) >= (1 << 63) else int(c) for c in cs], device=dev, dtype=torch.int64)
+        all_cs = [torch.empty_like(cst) for _ in range(world)]
+        dist.all_gather(all_cs, cst)
+        cs_parts = [[int(v) & ((1 << 64) - 1) for v in c.cpu().tolist()] for c in all_cs]
     else:
         nv_all, nsem_all, nblk_all = float(nv), float(nsem), float(nblk)
+        cs_parts = [cs]
     fps = n_frames / (gpu_ms * 1e-3)
     full = [(a.elapsed_time(b), n) for a, b, n in samples if n == B]
-    kern_us = float(np.mean([t for t, _ in full]) * 1e3) if full else None  # one K0+K1 launch pair (B frames)
+    kern_us = float(np.mean([t for t, _ in full]) * 1e3) if full else None  # main-stream time of one kb_integrate_frames call
     n_launch = sum(len(prebuilt[s]) for s in range(Wm, Wm + K))
-    bytes_per_launch = algorithmic_bytes(nv, nsem, nblk, n_frames * P, bpp=bpp) / n_frames * B  # this rank, per batch
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    achieved = bytes_per_launch / (kern_us * 1e-6) / 1e9 if kern_us else None
-    traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
-    try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_fuse_traffic.json")))
-        if B == tj["frames_per_launch"] and args.workload == "hall640" and not args.small:
-            traffic = tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"]
-    except Exception:
-        pass
+    roof = roofline_block(args, B, n_launch, gpu_ms, kern_us, nv, nsem, nblk, n_frames, P, bpp, world=world)
 
     # ---- e2e: host (pinned) images through the same C ABI, H2D inside the timed region (rank-local)
     e2e = None
@@ -812,18 +1097,15 @@ def main():
                                        "depth f32 + label i32 (8 B/px)"),
                        "lap_frames": lap, "live_blocks_rank0": total.total_blocks,
                        "l2": "inputs larger than L2: each step streams %.1f GB of frames" % (F * P * bpp / 1e9),
-                       "parallelism": ("block-hash shard x%d, %s frame broadcast" % (world, "NVLS multimem" if args.bcast == "multimem" else "NCCL")) if world > 1 else "single GPU",
+                       "parallelism": ("block-hash shard x%d, %s frame broadcast%s" % (world, "NVLS multimem" if args.bcast == "multimem" else "NCCL",
+                                                                                   (" (fallback: " + shard_note + ")") if shard_note else "")) if world > 1 else "single GPU",
                        "render_s": round(t_render, 1)},
             "per_frame": {"voxels_updated": nv_all / n_frames, "voxels_semantic": nsem_all / n_frames,
                           "blocks_visited": nblk_all / n_frames,
                           "block_frame_pairs_after_k0_culling_rank0": pairs / n_frames},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": traffic,
-                         "kernel": "fuseKernel<16> (+ its tileMax/selectBlocks prologue; one launch triple per %d frames)" % B,
-                         "launch_us": kern_us,
-                         "algorithmic_bytes_per_launch": bytes_per_launch,
-                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)"},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 3 * n_launch, "clocks": clocks,
+            "checksum": combine_checksums(cs_parts),
+            "roofline": roof,
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 6 * n_launch, "clocks": clocks,
             "wall_s_timed": wall,
         }
         emit(out)

@@ -485,6 +485,25 @@ int kb_motion_lookup_peers(kb_handle* h, const kb_frame* frame, uint8_t* const* 
  * it against the consumers with a barrier (e.g. _SymmetricMemory.barrier()). Untested on hardware in round 1. */
 int kb_multicast_copy(void* multicast_dst, const void* src, size_t bytes, void* cuda_stream);
 
+/* ---- mesh extraction ------------------------------------------------------------------------
+ * Replaces hydra::MeshIntegrator::generateMesh(map, only_mesh_updated_blocks, clear_updated_flag) (UPSTREAM; call sites
+ * active_window.cpp:223 with (true, true), mesh_object_extractor.cpp:267 with (true, false)): marching cubes over the
+ * TSDF of the blocks whose mesh_updated flag is set (or all blocks), on the device, so that an output tick moves the
+ * triangles to the host instead of every updated voxel block. Per block: the cubes inside the block (x-major), then
+ * the cubes on its max-x / max-y / max-z faces, which read the +x/+y/+z neighbour blocks (skipped when a neighbour is
+ * missing); a cube is meshed only if all 8 corner voxels have weight >= min_weight (hydra's MeshIntegratorConfig,
+ * default 1e-4); vertices are interpolated along the cube edges with a sign change; vertex colour / label are those of
+ * the nearer corner voxel. Vertices are not shared: triangle k is vertices (3k, 3k+1, 3k+2), so the face list of
+ * utils::combineMeshLayer (khronos/src/utils/geometry_utils.cpp:61-86) is the identity. Results stay on the device
+ * until kb_get_mesh. On a sharded map the cubes on a shard border miss their remote neighbour blocks (seams). */
+int kb_generate_mesh(kb_handle* h, int only_mesh_updated_blocks, int clear_updated_flag, float min_weight,
+                     int32_t* n_blocks, int64_t* n_vertices);
+/* Mesh of the last kb_generate_mesh: the processed blocks ascending in (x, y, z) (one hydra MeshBlock each, empty ones
+ * included), block_vertex_offsets[n_blocks + 1] into the concatenated vertex arrays (= combineMeshLayer's output plus
+ * the block boundaries), points in the world frame. NULL pointers are skipped; capacity_vertices must be >= n_vertices. */
+int kb_get_mesh(kb_handle* h, int32_t* block_index_xyz, int64_t* block_vertex_offsets, float* points_xyz,
+                uint8_t* colors_rgb, uint32_t* labels, int64_t capacity_vertices);
+
 /* ---- mirror-back / parity export ---------------------------------------------------------------- */
 
 enum { KB_EXPORT_ALL = 0, KB_EXPORT_UPDATED = 1 };

@@ -8,8 +8,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["kb_kernels.cu", "kb_motion_device.cu", "kb_objects_device.cu", "kb_tracks_device.cu", "kb_rays.cu", "kb_peer.cu", "kb_api.cu", "kb_motion_host.cpp"]
-HEADERS = ["kb_device.cuh", "kb_kernels.cuh", "kb_motion_device.cuh", "kb_objects_device.cuh", "kb_tracks_device.cuh", "kb_unionfind.cuh", "kb_motion_host.h", os.path.join(ROOT, "include", "khronos_b200.h")]
+SOURCES = ["kb_kernels.cu", "kb_motion_device.cu", "kb_objects_device.cu", "kb_tracks_device.cu", "kb_rays.cu", "kb_peer.cu", "kb_mesh.cu", "kb_api.cu", "kb_motion_host.cpp"]
+HEADERS = ["kb_device.cuh", "kb_kernels.cuh", "kb_motion_device.cuh", "kb_objects_device.cuh", "kb_tracks_device.cuh", "kb_unionfind.cuh", "kb_mesh.cuh", "kb_mc_tables.h", "kb_motion_host.h", os.path.join(ROOT, "include", "khronos_b200.h")]
 LIB = os.path.join(CSRC, "libkhronos_b200.so")
 
 NVCC_FLAGS = [
@@ -38,6 +38,19 @@ def build_product(force=False, verbose=False):
     return LIB
 
 
+# Tuning builds for A/B measurements (never loaded unless KB_PRODUCT_LIB_VARIANT names them): same sources, other -D flags.
+VARIANTS = {"mb12": ["-DKB_FUSE_MIN_BLOCKS=12"], "mb8": ["-DKB_FUSE_MIN_BLOCKS=8"]}
+
+
+def build_variant(name):
+    srcs = [os.path.join(CSRC, s) for s in SOURCES]
+    out = os.path.join(CSRC, f"libkhronos_b200_{name}.so")
+    cmd = ["nvcc"] + NVCC_FLAGS + VARIANTS[name] + ["-o", out] + srcs
+    print(" ".join(cmd), file=sys.stderr)
+    subprocess.check_call(cmd, cwd=CSRC)
+    return out
+
+
 def build_oracle():
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")])
     return os.path.join(ROOT, "oracle", "liboracle.so")
@@ -46,3 +59,6 @@ def build_oracle():
 if __name__ == "__main__":
     build_product(force="--force" in sys.argv, verbose="-v" in sys.argv)
     build_oracle()
+    for v in VARIANTS:
+        if ("--variant=" + v) in sys.argv:
+            build_variant(v)

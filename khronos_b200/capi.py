@@ -501,6 +501,22 @@ class MapHandle:
         self._check(f(self._h, C.c_void_p(offsets.ctypes.data), C.c_void_p(vox.ctypes.data), C.c_int32(total.value), C.byref(total)))
         return [vox[offsets[i]:offsets[i + 1]].copy() for i in range(max_id)]
 
+    def generate_mesh(self, only_mesh_updated=True, clear_updated_flag=True, min_weight=1e-4):
+        """hydra::MeshIntegrator::generateMesh on the map; returns (block_index (n,3), vertex offsets (n+1,), points (nv,3) f32,
+        colors (nv,3) u8, labels (nv,) u32); triangle k = vertices 3k..3k+2."""
+        nb, nv = C.c_int32(0), C.c_int64(0)
+        self._check(self._fn("generate_mesh")(self._h, int(only_mesh_updated), int(clear_updated_flag), C.c_float(min_weight),
+                                              C.byref(nb), C.byref(nv)))
+        n, v = nb.value, nv.value
+        bi = np.zeros((n, 3), np.int32)
+        off = np.zeros(n + 1, np.int64)
+        pts = np.zeros((v, 3), np.float32)
+        col = np.zeros((v, 3), np.uint8)
+        lab = np.zeros(v, np.uint32)
+        self._check(self._fn("get_mesh")(self._h, C.c_void_p(bi.ctypes.data), C.c_void_p(off.ctypes.data), C.c_void_p(pts.ctypes.data),
+                                         C.c_void_p(col.ctypes.data), C.c_void_p(lab.ctypes.data), C.c_int64(v)))
+        return bi, off, pts, col, lab
+
     def allocate_box(self, mn, mx):
         a = (C.c_int32 * 3)(*[int(v) for v in mn])
         b = (C.c_int32 * 3)(*[int(v) for v in mx])
@@ -543,7 +559,8 @@ class MapHandle:
 def load_product_library() -> C.CDLL:
     """Load the in-tree CUDA product library. Fails loudly if it is missing: there is no fallback."""
     here = os.path.dirname(os.path.abspath(__file__))
-    path = os.path.join(here, "csrc", "libkhronos_b200.so")
+    variant = os.environ.get("KB_PRODUCT_LIB_VARIANT")  # tuning builds (khronos_b200/build.py VARIANTS), A/B runs only
+    path = os.path.join(here, "csrc", f"libkhronos_b200_{variant}.so" if variant else "libkhronos_b200.so")
     if not os.path.exists(path):
         raise ImportError(
             f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "

@@ -14,6 +14,7 @@
 
 #include "../../include/khronos_b200.h"
 #include "kb_kernels.cuh"
+#include "kb_mesh.cuh"
 #include "kb_motion_device.cuh"
 #include "kb_objects_device.cuh"
 #include "kb_tracks_device.cuh"
@@ -152,6 +153,19 @@ struct kb_handle {
   TrackingParams open_pass{};   // parameters of the pass between kb_tracking_begin and kb_tracking_finish
   uint64_t open_pass_stamp = 0;
   int open_pass_state = 0;      // 0 none, 1 begun, 2 halo packed
+  // marching cubes (kb_generate_mesh): device results of the last call + host copies of the block list
+  int* mesh_slots = nullptr;
+  unsigned char* mesh_cases = nullptr;
+  int* mesh_tri_count = nullptr;
+  long long* mesh_tri_base = nullptr;
+  size_t mesh_block_cap = 0;
+  float* mesh_points = nullptr;
+  unsigned char* mesh_colors = nullptr;
+  unsigned int* mesh_labels = nullptr;
+  size_t mesh_tri_cap = 0;
+  std::vector<int3> mesh_index;
+  std::vector<long long> mesh_base;  // [n_blocks + 1] triangle offsets
+  bool mesh_have = false;
   std::string err;
 };
 
@@ -535,7 +549,7 @@ int kb_create(const kb_map_config* map, const kb_integrator_config* integ, const
     if (const char* e = std::getenv("KB_FUSE_MLP")) h->mlp_group = e[0] == '2' ? 2 : (e[0] == '4' ? 4 : 0);
     if (h->use_item_list) {  // experiment, off by default (results are identical either way: only the item order changes)
       h->item_list_cap = static_cast<int>(std::min<size_t>(S * h->batch.items_per_block, size_t(1) << 28));
-      KB_CUDA(h, devAlloc(&h->item_list, static_cast<size_t>(6) * h->item_list_cap, 0));  // 2 parities x 3 classes
+      KB_CUDA(h, devAlloc(&h->item_list, static_cast<size_t>(2 * kItemClasses) * h->item_list_cap, 0));  // 2 parities x classes
     }
     {
       cudaDeviceProp prop{};
@@ -599,6 +613,8 @@ int kb_destroy(kb_handle* h) {
   }
   if (h->main_front) cudaEventDestroy(h->main_front);
   cudaFree(h->work_slots2); cudaFree(h->work_masks2); cudaFree(h->work_upd2); cudaFree(h->item_fmask2);
+  cudaFree(h->mesh_slots); cudaFree(h->mesh_cases); cudaFree(h->mesh_tri_count); cudaFree(h->mesh_tri_base);
+  cudaFree(h->mesh_points); cudaFree(h->mesh_colors); cudaFree(h->mesh_labels);
   if (h->h_ctr) cudaFreeHost(h->h_ctr);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -835,7 +851,7 @@ static int integrateBatch(kb_handle* h, const kb_frame* frames, int n, int alloc
   p.has_color = any_color ? 1 : 0;
   // the compacted item lists pay for their extra launch only where items are many and uneven: long culled batches
   p.item_list = (h->use_item_list && p.cull && n >= 8 && !any_color)
-                    ? h->item_list + ((pipe && par) ? static_cast<size_t>(3) * h->item_list_cap : 0) : nullptr;
+                    ? h->item_list + ((pipe && par) ? static_cast<size_t>(kItemClasses) * h->item_list_cap : 0) : nullptr;
   p.item_list_cap = h->item_list_cap;
   p.mlp_group = h->mlp_group;
   if (any_color) {
@@ -1949,7 +1965,7 @@ int kb_get_motion_clusters(kb_handle* h, int32_t* counts, int32_t* pixels_uv, in
 // ---- export -------------------------------------------------------------------------------------------
 
 static int collectSlots(kb_handle* h, int which, std::vector<int>* slots, std::vector<int3>* index,
-                        std::vector<uint32_t>* flags) {
+                        std::vector<uint32_t>* flags, uint32_t need_flag = 0) {
   int st, n = 0;
   if ((st = slotHwm(h, &n)) != KB_OK) return st;
   std::vector<int3> bi(static_cast<size_t>(n));
@@ -1962,6 +1978,7 @@ static int collectSlots(kb_handle* h, int which, std::vector<int>* slots, std::v
   for (int s = 0; s < n; ++s) {
     if (!(bf[s] & kFlagAllocated)) continue;
     if (which == KB_EXPORT_UPDATED && !(bf[s] & KB_FLAG_UPDATED)) continue;
+    if (need_flag && !(bf[s] & need_flag)) continue;
     order.push_back(s);
   }
   std::sort(order.begin(), order.end(), [&](int a, int b) {
@@ -1970,6 +1987,91 @@ static int collectSlots(kb_handle* h, int which, std::vector<int>* slots, std::v
   });
   slots->clear(); index->clear(); flags->clear();
   for (int s : order) { slots->push_back(s); index->push_back(bi[s]); flags->push_back(bf[s]); }
+  return KB_OK;
+}
+
+int kb_generate_mesh(kb_handle* h, int only_mesh_updated, int clear_updated_flag, float min_weight, int32_t* n_blocks,
+                     int64_t* n_vertices) {
+  if (!h) return KB_ERR_INVALID;
+  h->main_dirty = true;
+  KB_CUDA(h, cudaSetDevice(h->device));
+  std::vector<int> slots; std::vector<uint32_t> flags;
+  int st = collectSlots(h, KB_EXPORT_ALL, &slots, &h->mesh_index, &flags, only_mesh_updated ? KB_FLAG_MESH_UPDATED : 0u);
+  if (st != KB_OK) return st;
+  const int n = static_cast<int>(slots.size());
+  h->mesh_base.assign(static_cast<size_t>(n) + 1, 0);
+  h->mesh_have = true;
+  if (n_blocks) *n_blocks = n;
+  if (n_vertices) *n_vertices = 0;
+  if (n == 0) return KB_OK;
+  const size_t V = h->dm.V;
+  if (h->mesh_block_cap < static_cast<size_t>(n)) {
+    KB_CUDA(h, cudaStreamSynchronize(h->stream));
+    cudaFree(h->mesh_slots); cudaFree(h->mesh_cases); cudaFree(h->mesh_tri_count); cudaFree(h->mesh_tri_base);
+    h->mesh_slots = nullptr; h->mesh_cases = nullptr; h->mesh_tri_count = nullptr; h->mesh_tri_base = nullptr;
+    h->mesh_block_cap = 0;
+    const size_t cap = static_cast<size_t>(n) + static_cast<size_t>(n) / 4 + 64;
+    KB_CUDA(h, cudaMalloc(&h->mesh_slots, sizeof(int) * cap));
+    KB_CUDA(h, cudaMalloc(&h->mesh_cases, cap * V));
+    KB_CUDA(h, cudaMalloc(&h->mesh_tri_count, sizeof(int) * cap));
+    KB_CUDA(h, cudaMalloc(&h->mesh_tri_base, sizeof(long long) * (cap + 1)));
+    h->mesh_block_cap = cap;
+  }
+  KB_CUDA(h, cudaMemcpyAsync(h->mesh_slots, slots.data(), sizeof(int) * n, cudaMemcpyHostToDevice, h->stream));
+  MeshParams p{};
+  p.slots = h->mesh_slots;
+  p.n_blocks = n;
+  p.voxel_size = h->map.voxel_size;
+  p.block_size = h->block_size;
+  p.min_weight = min_weight;
+  p.cases = h->mesh_cases;
+  p.tri_count = h->mesh_tri_count;
+  p.tri_base = h->mesh_tri_base;
+  p.clear_flag = clear_updated_flag ? 1 : 0;
+  launchMeshCount(h->dm, p, h->stream);
+  launchMeshScan(h->mesh_tri_count, h->mesh_tri_base, n, h->stream);
+  KB_CUDA(h, cudaGetLastError());
+  KB_CUDA(h, cudaMemcpyAsync(h->mesh_base.data(), h->mesh_tri_base, sizeof(long long) * (n + 1), cudaMemcpyDeviceToHost, h->stream));
+  KB_CUDA(h, cudaStreamSynchronize(h->stream));
+  const size_t tris = static_cast<size_t>(h->mesh_base[n]);
+  if (h->mesh_tri_cap < tris) {
+    cudaFree(h->mesh_points); cudaFree(h->mesh_colors); cudaFree(h->mesh_labels);
+    h->mesh_points = nullptr; h->mesh_colors = nullptr; h->mesh_labels = nullptr;
+    h->mesh_tri_cap = 0;
+    const size_t cap = tris + tris / 4 + 1024;
+    KB_CUDA(h, cudaMalloc(&h->mesh_points, sizeof(float) * 9 * cap));
+    KB_CUDA(h, cudaMalloc(&h->mesh_colors, 9 * cap));
+    KB_CUDA(h, cudaMalloc(&h->mesh_labels, sizeof(unsigned int) * 3 * cap));
+    h->mesh_tri_cap = cap;
+  }
+  p.points = h->mesh_points;
+  p.colors = h->mesh_colors;
+  p.labels = h->mesh_labels;
+  launchMeshEmit(h->dm, p, h->stream);
+  KB_CUDA(h, cudaGetLastError());
+  if (n_vertices) *n_vertices = static_cast<int64_t>(tris) * 3;
+  return KB_OK;
+}
+
+int kb_get_mesh(kb_handle* h, int32_t* block_index_xyz, int64_t* block_vertex_offsets, float* points_xyz, uint8_t* colors_rgb,
+                uint32_t* labels, int64_t capacity_vertices) {
+  if (!h) return KB_ERR_INVALID;
+  if (!h->mesh_have) return fail(h, KB_ERR_STATE, "kb_generate_mesh has not been called");
+  KB_CUDA(h, cudaSetDevice(h->device));
+  const size_t n = h->mesh_index.size();
+  const int64_t nv = static_cast<int64_t>(h->mesh_base[n]) * 3;
+  if ((points_xyz || colors_rgb || labels) && capacity_vertices < nv) return fail(h, KB_ERR_CAPACITY, "mesh output buffers too small");
+  for (size_t i = 0; i < n; ++i) {
+    if (block_index_xyz) { block_index_xyz[3 * i] = h->mesh_index[i].x; block_index_xyz[3 * i + 1] = h->mesh_index[i].y; block_index_xyz[3 * i + 2] = h->mesh_index[i].z; }
+    if (block_vertex_offsets) block_vertex_offsets[i] = static_cast<int64_t>(h->mesh_base[i]) * 3;
+  }
+  if (block_vertex_offsets) block_vertex_offsets[n] = nv;
+  if (nv > 0) {
+    if (points_xyz) KB_CUDA(h, cudaMemcpyAsync(points_xyz, h->mesh_points, sizeof(float) * 3 * nv, cudaMemcpyDeviceToHost, h->stream));
+    if (colors_rgb) KB_CUDA(h, cudaMemcpyAsync(colors_rgb, h->mesh_colors, 3 * nv, cudaMemcpyDeviceToHost, h->stream));
+    if (labels) KB_CUDA(h, cudaMemcpyAsync(labels, h->mesh_labels, sizeof(uint32_t) * nv, cudaMemcpyDeviceToHost, h->stream));
+  }
+  KB_CUDA(h, cudaStreamSynchronize(h->stream));
   return KB_OK;
 }
 

@@ -82,16 +82,14 @@ enum Counter {
   kCtrPending = 18,  // ever-free work list length of the current tracking pass
   kCtrFetch = 19,    // dynamic work cursor of the fuse kernel
   kCtrHalo = 20,     // sharded ever-free pass: locally owned blocks whose free masks are published this pass
-  kCtrItems0 = 21,   // KB_FUSE_ITEM_LIST: non-empty culling boxes of the batch in 3 weight classes (heavy first)
-  kCtrItems1 = 22,
-  kCtrItems2 = 23,
-  kCtrFetchB = 24,   // KB_PIPELINE: second work cursor / item-list counters, so that the prologue of batch i+1 can
-  kCtrItemsB0 = 25,  //   run while the fuse kernel of batch i is still fetching
-  kCtrItemsB1 = 26,
-  kCtrItemsB2 = 27,
+  kCtrFetchB = 24,   // pipelined batches: second work cursor, so that the prologue of batch i+1 can run while the fuse
+                     //   kernel of batch i is still fetching
   kCtrRehash = 28,   // number of hash-table rebuilds (tombstone garbage collection, kb_reset_inactive)
-  kNumCounters = 32
+  kCtrItems0 = 32,   // item lists: non-empty culling boxes of the batch in kItemClasses weight classes (heaviest first);
+  kCtrItemsB0 = 40,  //   second set for odd pipelined batches
+  kNumCounters = 48
 };
+constexpr int kItemClasses = 8;  // by frame count: 32..29, 28..25, ..., 4..1 frames
 
 // 64-bit cumulative totals (kb_get_totals64): the int counters above wrap after ~36 k frames of the bench workload
 // (119 k voxel updates per frame). They live behind the int counters in the same allocation (8-byte aligned), so one

@@ -442,28 +442,35 @@ __global__ void __launch_bounds__(128) itemCullKernel(const DeviceMap m, const _
 // cursor round trip. This pass lists the boxes whose frame mask is non-zero in three weight classes.
 template <int VPS, bool PB>
 __global__ void __launch_bounds__(256) itemCompactKernel(const DeviceMap m, const __grid_constant__ BatchParams p) {
-  constexpr int kItems = PB ? kCtrItemsB0 : kCtrItems0;  // PB: second counter set (odd batches of KB_PIPELINE)
+  constexpr int kItems = PB ? kCtrItemsB0 : kCtrItems0;  // PB: second counter set (odd pipelined batches)
   constexpr int BOXES = (VPS / 4) * (VPS / 8) * (VPS / 4);
   const int n = min(m.counters[kCtrWork0 + p.parity], p.max_work) * BOXES;
   const int lane = threadIdx.x & 31;
   for (int base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < n; base += gridDim.x * blockDim.x) {
     const int i = base + lane;
     const uint32_t fm = i < n ? p.item_fmask[i] : 0u;
-    const int c = __popc(fm);
-    const int cls = c >= 20 ? 0 : (c >= 8 ? 1 : 2);
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const unsigned vote = __ballot_sync(0xffffffffu, fm != 0u && cls == k);
-      if (!vote) continue;
-      int start = 0;
-      if (lane == __ffs(vote) - 1) start = atomicAdd(&m.counters[kItems + k], __popc(vote));
-      start = __shfl_sync(0xffffffffu, start, __ffs(vote) - 1);
-      if (fm != 0u && cls == k) {
-        const int idx = start + __popc(vote & ((1u << lane) - 1u));
-        if (idx < p.item_list_cap) p.item_list[static_cast<size_t>(k) * p.item_list_cap + idx] = i;
-      }
-    }
+    const int cls = fm ? (32 - __popc(fm)) >> 2 : -1;  // 0: 32..29 frames, ..., 7: 4..1 frames
+    // lanes of the same class aggregate their append into one atomic
+    const unsigned peers = __match_any_sync(0xffffffffu, cls);
+    if (cls < 0) continue;
+    const int leader = __ffs(peers) - 1;
+    int start = 0;
+    if (lane == leader) start = atomicAdd(&m.counters[kItems + cls], __popc(peers));
+    start = __shfl_sync(peers, start, leader);
+    const int idx = start + __popc(peers & ((1u << lane) - 1u));
+    if (idx < p.item_list_cap) p.item_list[static_cast<size_t>(cls) * p.item_list_cap + idx] = i;
   }
+}
+
+// Item j of the concatenated class lists -> box index.
+template <bool PB>
+__device__ __forceinline__ int listedBox(const BatchParams& p, const int (&n_cls)[kItemClasses], int j) {
+  int k = 0;
+#pragma unroll
+  for (int c = 0; c < kItemClasses - 1; ++c) {
+    if (k == c && j >= n_cls[c]) { j -= n_cls[c]; k = c + 1; }
+  }
+  return p.item_list[static_cast<size_t>(k) * p.item_list_cap + j];
 }
 
 // ---- K1: projective TSDF + semantic fusion ----------------------------------------------------------------
@@ -506,12 +513,16 @@ __global__ void __launch_bounds__(kFuseThreads, COLOR ? KB_FUSE_COLOR_MIN_BLOCKS
   // Short batches have little work per voxel, so an item then covers all NK layers of its box (amortising the
   // fetch); long batches use one layer per item for balance.
   constexpr int lpi = LPI, ipb = NK / LPI;  // layers per item, items per box
-  int n0 = 0, n1 = 0;  // LIST: sizes of the first two weight classes
+  int n_cls[kItemClasses] = {0};  // LIST: sizes of the weight classes
   int n_items;
   if constexpr (LIST) {
-    n0 = min(m.counters[kItems], p.item_list_cap);
-    n1 = min(m.counters[kItems + 1], p.item_list_cap);
-    n_items = (n0 + n1 + min(m.counters[kItems + 2], p.item_list_cap)) * ipb;
+    n_items = 0;
+#pragma unroll
+    for (int c = 0; c < kItemClasses; ++c) {
+      n_cls[c] = min(m.counters[kItems + c], p.item_list_cap);
+      n_items += n_cls[c];
+    }
+    n_items *= ipb;
   } else {
     n_items = min(m.counters[kCtrWork0 + p.parity], p.max_work) * BOXES * ipb;
   }
@@ -529,10 +540,7 @@ __global__ void __launch_bounds__(kFuseThreads, COLOR ? KB_FUSE_COLOR_MIN_BLOCKS
     if (lane == 0) pending = atomicAdd(&m.counters[kFetch], 1);
     int box = w / ipb;
     if constexpr (LIST) {
-      const int j = box;
-      box = j < n0 ? p.item_list[j]
-                   : (j < n0 + n1 ? p.item_list[static_cast<size_t>(p.item_list_cap) + (j - n0)]
-                                  : p.item_list[2 * static_cast<size_t>(p.item_list_cap) + (j - n0 - n1)]);
+      box = listedBox<PB>(p, n_cls, box);
     }
     const uint32_t fmask = p.item_fmask[box];
     if (!fmask) continue;
@@ -741,12 +749,16 @@ __global__ void __launch_bounds__(kFuseThreads, KB_FUSE_MLP_MIN_BLOCKS) fuseKern
   extern __shared__ float s_rows[];
   const int lane = threadIdx.x & 31;
   constexpr int lpi = LPI, ipb = NK / LPI;
-  int n0 = 0, n1 = 0;
+  int n_cls[kItemClasses] = {0};
   int n_items;
   if constexpr (LIST) {
-    n0 = min(m.counters[kItems], p.item_list_cap);
-    n1 = min(m.counters[kItems + 1], p.item_list_cap);
-    n_items = (n0 + n1 + min(m.counters[kItems + 2], p.item_list_cap)) * ipb;
+    n_items = 0;
+#pragma unroll
+    for (int c = 0; c < kItemClasses; ++c) {
+      n_cls[c] = min(m.counters[kItems + c], p.item_list_cap);
+      n_items += n_cls[c];
+    }
+    n_items *= ipb;
   } else {
     n_items = min(m.counters[kCtrWork0 + p.parity], p.max_work) * BOXES * ipb;
   }
@@ -763,10 +775,7 @@ __global__ void __launch_bounds__(kFuseThreads, KB_FUSE_MLP_MIN_BLOCKS) fuseKern
     if (lane == 0) pending = atomicAdd(&m.counters[kFetch], 1);
     int box = w / ipb;
     if constexpr (LIST) {
-      const int j = box;
-      box = j < n0 ? p.item_list[j]
-                   : (j < n0 + n1 ? p.item_list[static_cast<size_t>(p.item_list_cap) + (j - n0)]
-                                  : p.item_list[2 * static_cast<size_t>(p.item_list_cap) + (j - n0 - n1)]);
+      box = listedBox<PB>(p, n_cls, box);
     }
     const uint32_t fmask = p.item_fmask[box];
     if (!fmask) continue;
@@ -1680,7 +1689,7 @@ void launchSelectBlocks(const DeviceMap& m, const BatchParams& p, int cull_grid,
   }
   if (p.item_list) {
     const bool pb = p.fetch_ctr == kCtrFetchB;
-    cudaMemsetAsync(m.counters + (pb ? kCtrItemsB0 : kCtrItems0), 0, 3 * sizeof(int), s);
+    cudaMemsetAsync(m.counters + (pb ? kCtrItemsB0 : kCtrItems0), 0, kItemClasses * sizeof(int), s);
     if (m.vps == 16) { if (pb) itemCompactKernel<16, true><<<cull_grid, 256, 0, s>>>(m, p); else itemCompactKernel<16, false><<<cull_grid, 256, 0, s>>>(m, p); }
     else { if (pb) itemCompactKernel<8, true><<<cull_grid, 256, 0, s>>>(m, p); else itemCompactKernel<8, false><<<cull_grid, 256, 0, s>>>(m, p); }
   }

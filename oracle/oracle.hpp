@@ -144,6 +144,19 @@ class Oracle {
   void packHalo(const int32_t* all_pending, int cap_pending, int32_t* halo_out, int cap_halo);
   void trackingFinish(const int32_t* all_pending, int cap_pending, const int32_t* all_halo, int cap_halo);
 
+  // Marching cubes over the TSDF: hydra::MeshIntegrator::generateMesh(map, only_mesh_updated_blocks, clear_updated_flag)
+  // (UPSTREAM; call sites active_window.cpp:223, mesh_object_extractor.cpp:267; voxblox MeshIntegrator / MarchingCubes
+  // heritage, restated in docs/ORACLE_SPEC.md §10). One MeshBlock per processed block, blocks ascending (x, y, z);
+  // vertices are not shared: triangle k of a block is (points[3k], points[3k+1], points[3k+2]).
+  struct MeshBlock {
+    Idx3 index;
+    std::vector<float> points;     // 3 per vertex, world frame
+    std::vector<uint8_t> colors;   // 3 per vertex
+    std::vector<uint32_t> labels;  // 1 per vertex
+  };
+  void generateMesh(bool only_mesh_updated, bool clear_updated_flag, float min_weight);
+  const std::vector<MeshBlock>& mesh() const { return mesh_; }
+
   std::vector<const Block*> sortedBlocks(int which) const;
   int V() const { return V_; }
   int L() const { return L_; }
@@ -199,6 +212,7 @@ class Oracle {
   int cell_ = 0, gx_ = 1, gy_ = 1;
   std::vector<ObjectCluster> object_clusters_;
   TrackMeasurements track_result_;
+  std::vector<MeshBlock> mesh_;
   std::vector<Block*> open_pending_;       // ever-free work list between trackingBegin and trackingFinish
   uint64_t open_stamp_ = 0;
   std::string error_;

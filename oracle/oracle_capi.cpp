@@ -180,6 +180,36 @@ int ko_map_checksum(ko_handle* h, uint64_t out[4]) {
   return KB_OK;
 }
 
+int ko_generate_mesh(ko_handle* h, int only_mesh_updated, int clear_updated_flag, float min_weight, int32_t* n_blocks, int64_t* n_vertices) {
+  if (!h) return KB_ERR_INVALID;
+  h->o->generateMesh(only_mesh_updated != 0, clear_updated_flag != 0, min_weight);
+  int64_t nv = 0;
+  for (const auto& mb : h->o->mesh()) nv += static_cast<int64_t>(mb.labels.size());
+  if (n_blocks) *n_blocks = static_cast<int32_t>(h->o->mesh().size());
+  if (n_vertices) *n_vertices = nv;
+  return KB_OK;
+}
+
+int ko_get_mesh(ko_handle* h, int32_t* block_index_xyz, int64_t* block_vertex_offsets, float* points_xyz, uint8_t* colors_rgb,
+                uint32_t* labels, int64_t capacity_vertices) {
+  if (!h) return KB_ERR_INVALID;
+  int64_t off = 0;
+  size_t i = 0;
+  for (const auto& mb : h->o->mesh()) {
+    const int64_t n = static_cast<int64_t>(mb.labels.size());
+    if (off + n > capacity_vertices) return KB_ERR_CAPACITY;
+    if (block_index_xyz) { block_index_xyz[3 * i] = mb.index.x; block_index_xyz[3 * i + 1] = mb.index.y; block_index_xyz[3 * i + 2] = mb.index.z; }
+    if (block_vertex_offsets) block_vertex_offsets[i] = off;
+    if (points_xyz && n) std::memcpy(points_xyz + 3 * off, mb.points.data(), sizeof(float) * 3 * n);
+    if (colors_rgb && n) std::memcpy(colors_rgb + 3 * off, mb.colors.data(), 3 * n);
+    if (labels && n) std::memcpy(labels + off, mb.labels.data(), sizeof(uint32_t) * n);
+    off += n;
+    ++i;
+  }
+  if (block_vertex_offsets) block_vertex_offsets[i] = off;
+  return KB_OK;
+}
+
 int ko_update_tracking(ko_handle* h, uint64_t stamp_ns) {
   if (!h) return KB_ERR_INVALID;
   h->o->updateTracking(stamp_ns);
