@@ -62,6 +62,8 @@ def parse_args():
     ap.add_argument("--force-cull", action="store_true",
                     help="--workload dynamic: cull even single-frame calls (kb_set_culling(2)); results identical, 3 more launches per frame")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-legs", action="store_true", help="skip the secondary legs (output tick, per-frame pipeline on the hall stream, "
+                    "next rows) of the N = 1 run")
     ap.add_argument("--wire", default="f32", choices=["f32", "compact", "f32u8"],
                     help="f32 = depth f32 + label i32 (hydra::InputData, 8 B/pixel; the headline); compact = u16 millimetre "
                          "depth + u8 labels (3 B/pixel, expanded on the device): what crosses PCIe / NVLink; f32u8 (N > 1 only, "
@@ -1011,6 +1013,21 @@ def main():
     n_launch = sum(len(prebuilt[s]) for s in range(Wm, Wm + K))
     roof = roofline_block(args, B, n_launch, gpu_ms, kern_us, nv, nsem, nblk, n_frames, P, bpp, world=world)
 
+    # ---- secondary legs (N = 1): output tick on the benchmarked map (after the checksum: it integrates more frames)
+    legs = {}
+    if world == 1 and not args.no_legs and not compact and args.workload == "hall640":
+        import bench_legs
+        tick_step = Wm + K + 8
+
+        def tick_batch(t):
+            fr = [h.make_frame(depth[(t * 12 + j) % lap].data_ptr(), poses[(t * 12 + j) % lap], stamp_of(tick_step, t * 12 + j),
+                               label=label[(t * 12 + j) % lap].data_ptr(), memory=capi.MEM_DEVICE) for j in range(12)]
+            return (capi.Frame * 12)(*fr), 12
+        try:
+            legs["output_tick"] = bench_legs.leg_output_tick(h, tick_batch)
+        except Exception as e:  # noqa: BLE001 - a failing leg must not take the headline down; it is reported
+            legs["output_tick"] = {"error": str(e)[:300]}
+
     # ---- e2e: host (pinned) images through the same C ABI, H2D inside the timed region (rank-local)
     e2e = None
     if not args.no_e2e and world == 1:
@@ -1083,6 +1100,17 @@ def main():
                "sample": f"first {n_done} frames of the lap into an empty map, oracle port, {secs:.1f} s of integration, "
                          f"best of a thread-count sweep up to {os.cpu_count()} host threads"}
 
+    if world == 1 and not args.no_legs and not compact and args.workload == "hall640":
+        import bench_legs
+        nt_legs = locals().get("nt") or min(32, os.cpu_count() or 1)
+        for name, fn in (("dynamic", lambda: bench_legs.leg_dynamic_hall(args, cam, scene, poses, stamps, depth, label, dev, nt_legs,
+                                                                           n_timed=600 if not args.small else 24, small=args.small)),
+                         ("next_rows", lambda: bench_legs.leg_next_rows(dev, small=args.small, cpu=not args.no_cpu_baseline))):
+            try:
+                legs[name] = fn()
+            except Exception as e:  # noqa: BLE001
+                legs[name] = {"error": str(e)[:300]}
+
     if rank == 0:
         total = h.get_totals()
         out = {
@@ -1108,6 +1136,10 @@ def main():
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 6 * n_launch, "clocks": clocks,
             "wall_s_timed": wall,
         }
+        if legs:
+            out["configs"] = {"dynamic": legs.get("dynamic")}
+            out["output_tick"] = legs.get("output_tick")
+            out["next_rows"] = legs.get("next_rows")
         emit(out)
     if world > 1:
         dist.destroy_process_group()

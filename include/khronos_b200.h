@@ -345,6 +345,33 @@ int kb_detect_objects(kb_handle* h, const kb_object_detector_config* config, con
 int kb_get_object_clusters(kb_handle* h, int32_t* id_semantic_count, int32_t* pixels_uv, int32_t* n_clusters,
                            int32_t* total_pixels);
 
+/* khronos::InstanceForwarding (khronos/include/khronos/active_window/object_detection/instance_forwarding.h:62-86): the
+ * other shipped ObjectDetector — forwards the instance ids of an upstream segmenter instead of clustering class labels. */
+#define KB_MAX_INSTANCE_IDS 4096
+typedef struct kb_instance_forwarding_config {
+  float max_range;            /* m; 0 = infinite */
+  int32_t min_cluster_size;   /* pixels */
+  int32_t max_cluster_size;   /* pixels; <= 0 disables */
+  double min_object_volume;   /* m^3 of the cluster's world AABB; the volume filter runs if min > 0 or max > 0 (:68) */
+  double max_object_volume;   /* <= 0 disables the upper bound */
+} kb_instance_forwarding_config;
+/* Replaces InstanceForwarding::processInput / extractSemanticClusters (instance_forwarding.cpp:73-149). label = instance id
+ * image (ids 1 .. KB_MAX_INSTANCE_IDS - 1, 0 = none). id_is_background[id] != 0 (host, n_background entries, may be NULL)
+ * is the caller's per-id open-set decision "best background score > max_background_score" (:96-104: embeddings and prompts
+ * stay on the host; the decision only depends on the id). object_image_out (host, H*W) = the label image, as in the
+ * reference, where object_image shares the label image's buffer (:83) so that filtered pixels keep their id. A pixel
+ * belongs to its id's cluster if the id is not background and range <= max_range; clusters are then filtered by pixel
+ * count and by the volume of the world-frame bounding box of their vertices (:118-135). Cluster order: ascending id (a
+ * determinisation of the reference's unordered_map iteration). */
+int kb_forward_instances(kb_handle* h, const kb_instance_forwarding_config* config, const kb_frame* frame,
+                         const uint8_t* id_is_background, int32_t n_background, int32_t* object_image_out,
+                         int32_t* n_clusters);
+/* Clusters of the last kb_forward_instances: id_count[c*2+0..1] = id, #pixels; bbox_min_max[c*6..] = world AABB (min xyz,
+ * max xyz); pixels_uv = flat (u, v) lists in cluster order, pixels within a cluster in the reference's column-major scan
+ * order (u outer, v inner). NULL pointers are skipped. */
+int kb_get_instance_clusters(kb_handle* h, int32_t* id_count, float* bbox_min_max, int32_t* pixels_uv, int32_t* n_clusters,
+                             int32_t* total_pixels);
+
 /* Input conversion (first half): the world-frame vertex map that upstream parseInputPacket builds for
  * FrameData (call site active_window.cpp:275; InputData::vertex_map, read e.g. at free_space_motion_detector.cpp:174-175,
  * max_iou_tracker.cpp:456): p_W = R * ((u-cx)/fx*d, (v-cy)/fy*d, d) + t in fp32 for every pixel (no validity test; d = 0
@@ -371,7 +398,12 @@ int kb_compute_vertex_map(kb_handle* h, const kb_frame* frame, float* vertex_wor
  * Outputs (host, NULL = skipped): voxel_counts[n_clusters], voxel_sums[n_clusters*3], intersections[n_clusters*n_tracks]
  * and iou[n_clusters*n_tracks] (row = position in cluster_ids, or id - 1), iou formed exactly like :562 (float inter /
  * (float(size + size) - inter), so an empty cluster against an empty track is NaN as in the reference). Voxels further
- * than 2^17 tracker voxels from the origin are dropped (13 km at 0.1 m). */
+ * than 2^17 tracker voxels from the origin are dropped (13 km at 0.1 m).
+ * Precondition: the clusters are disjoint in the id image (one id per pixel). The reference's MeasurementCluster.pixels can
+ * put one pixel into two dynamic clusters when min_separation_distance == 0 (clusterDynamicVoxels has no closed-set check on
+ * absorbed neighbours) and its ids saturate at 255 (writeClustersToData); the image then keeps only the last id and the
+ * per-cluster rows differ from MaxIoUTracker's. With min_separation_distance > 0 (shipped: 2) and <= 254 dynamic clusters the
+ * image is exact. */
 int kb_track_measurements(kb_handle* h, const kb_frame* frame, const int32_t* id_image, int32_t n_clusters,
                           const int32_t* cluster_ids, float voxel_size, int32_t n_tracks, const int32_t* track_offsets,
                           const int64_t* track_voxels_xyz, int32_t* voxel_counts, int64_t* voxel_sums,

@@ -61,6 +61,11 @@ class ObjectDetectorConfig(C.Structure):
                 ("max_range", C.c_float), ("is_object", C.c_uint8 * KB_MAX_LABELS)]
 
 
+class InstanceForwardingConfig(C.Structure):
+    _fields_ = [("max_range", C.c_float), ("min_cluster_size", C.c_int32), ("max_cluster_size", C.c_int32),
+                ("min_object_volume", C.c_double), ("max_object_volume", C.c_double)]
+
+
 class Camera(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("fx", C.c_float), ("fy", C.c_float),
                 ("cx", C.c_float), ("cy", C.c_float), ("min_range", C.c_float),
@@ -432,6 +437,31 @@ class MapHandle:
         nc = C.c_int32(0)
         self._check(self._fn("detect_objects")(self._h, C.byref(cfg), C.byref(frame), C.c_void_p(img.ctypes.data), C.byref(nc)))
         return img, nc.value
+
+    def forward_instances(self, frame: Frame, max_range=0.0, min_cluster_size=0, max_cluster_size=-1, min_object_volume=0.0,
+                          max_object_volume=-1.0, background=None):
+        """kb_forward_instances (khronos::InstanceForwarding): returns (object image, clusters) with clusters =
+        [{"id", "pixels" (n, 2) in the reference's scan order, "bbox" (6,)}], ascending id."""
+        H, W = self._camera.height, self._camera.width
+        cfg = InstanceForwardingConfig(max_range, min_cluster_size, max_cluster_size, min_object_volume, max_object_volume)
+        img = np.zeros((H, W), np.int32)
+        nc = C.c_int32(0)
+        bg = None if background is None else np.ascontiguousarray(background, np.uint8)
+        self._check(self._fn("forward_instances")(self._h, C.byref(cfg), C.byref(frame), None if bg is None else C.c_void_p(bg.ctypes.data),
+                                                  0 if bg is None else int(bg.size), C.c_void_p(img.ctypes.data), C.byref(nc)))
+        n, tp = C.c_int32(0), C.c_int32(0)
+        f = self._fn("get_instance_clusters")
+        self._check(f(self._h, None, None, None, C.byref(n), C.byref(tp)))
+        info = np.zeros((max(n.value, 1), 2), np.int32)
+        bbox = np.zeros((max(n.value, 1), 6), np.float32)
+        px = np.zeros((max(tp.value, 1), 2), np.int32)
+        self._check(f(self._h, C.c_void_p(info.ctypes.data), C.c_void_p(bbox.ctypes.data), C.c_void_p(px.ctypes.data), C.byref(n), C.byref(tp)))
+        out, po = [], 0
+        for c in range(n.value):
+            k = int(info[c, 1])
+            out.append({"id": int(info[c, 0]), "pixels": px[po:po + k].copy(), "bbox": bbox[c].copy()})
+            po += k
+        return img, out
 
     def get_object_clusters(self):
         f = self._fn("get_object_clusters")

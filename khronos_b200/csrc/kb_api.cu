@@ -83,6 +83,7 @@ struct kb_handle {
   int narrow_threads = 8;
   uint8_t* pin_label8 = nullptr;
   size_t pin_label8_pixels = 0;
+  int fuse_prefetch = 0;       // KB_FUSE_PREFETCH: software-pipelined frame loop with L1 prefetch of the next frame's taps
   int mlp_group = 0;           // KB_FUSE_MLP experiment: 0 (off), 2 or 4 frames per memory-level-parallel group
   int cull_grid = 0;
   int parity = 0;
@@ -137,7 +138,6 @@ struct kb_handle {
   unsigned long long* trk_sums = nullptr;
   int* trk_present = nullptr;
   int* trk_idlist = nullptr;
-  uint32_t trk_mask = 0;        // table size the last track measurement used (<= mt.mask)
   unsigned long long* trk_keys = nullptr;
   int* trk_of = nullptr;
   size_t trk_voxel_cap = 0;
@@ -153,6 +153,17 @@ struct kb_handle {
   TrackingParams open_pass{};   // parameters of the pass between kb_tracking_begin and kb_tracking_finish
   uint64_t open_pass_stamp = 0;
   int open_pass_state = 0;      // 0 none, 1 begun, 2 halo packed
+  // InstanceForwarding (kb_forward_instances): per-id accumulators on the device, kept clusters + keep mask on the host
+  int* inst_counts = nullptr;
+  unsigned int* inst_bbox = nullptr;
+  uint8_t* inst_background = nullptr;
+  uint8_t* inst_keep = nullptr;
+  int* inst_bad = nullptr;
+  size_t inst_pixels = 0;
+  struct InstCluster { int id, count; float bbox[6]; };
+  std::vector<InstCluster> inst_clusters;
+  std::vector<uint8_t> inst_keep_host;
+  bool inst_have = false;
   // marching cubes (kb_generate_mesh): device results of the last call + host copies of the block list
   int* mesh_slots = nullptr;
   unsigned char* mesh_cases = nullptr;
@@ -546,6 +557,7 @@ int kb_create(const kb_map_config* map, const kb_integrator_config* integ, const
       KB_CUDA(h, devAlloc(&h->work_upd2, S, 0));
       KB_CUDA(h, devAlloc(&h->item_fmask2, S * h->batch.items_per_block, 0));
     }
+    if (const char* e = std::getenv("KB_FUSE_PREFETCH")) h->fuse_prefetch = std::max(0, std::min(2, std::atoi(e)));
     if (const char* e = std::getenv("KB_FUSE_MLP")) h->mlp_group = e[0] == '2' ? 2 : (e[0] == '4' ? 4 : 0);
     if (h->use_item_list) {  // experiment, off by default (results are identical either way: only the item order changes)
       h->item_list_cap = static_cast<int>(std::min<size_t>(S * h->batch.items_per_block, size_t(1) << 28));
@@ -613,6 +625,7 @@ int kb_destroy(kb_handle* h) {
   }
   if (h->main_front) cudaEventDestroy(h->main_front);
   cudaFree(h->work_slots2); cudaFree(h->work_masks2); cudaFree(h->work_upd2); cudaFree(h->item_fmask2);
+  cudaFree(h->inst_counts); cudaFree(h->inst_bbox); cudaFree(h->inst_background); cudaFree(h->inst_keep); cudaFree(h->inst_bad);
   cudaFree(h->mesh_slots); cudaFree(h->mesh_cases); cudaFree(h->mesh_tri_count); cudaFree(h->mesh_tri_base);
   cudaFree(h->mesh_points); cudaFree(h->mesh_colors); cudaFree(h->mesh_labels);
   if (h->h_ctr) cudaFreeHost(h->h_ctr);
@@ -854,6 +867,7 @@ static int integrateBatch(kb_handle* h, const kb_frame* frames, int n, int alloc
                     ? h->item_list + ((pipe && par) ? static_cast<size_t>(kItemClasses) * h->item_list_cap : 0) : nullptr;
   p.item_list_cap = h->item_list_cap;
   p.mlp_group = h->mlp_group;
+  p.prefetch = h->fuse_prefetch;
   if (any_color) {
     int st = ensureColorLayer(h);
     if (st == KB_OK && any_host_color) st = ensureColorStaging(h, px);
@@ -1644,6 +1658,143 @@ int kb_detect_objects(kb_handle* h, const kb_object_detector_config* cfg, const 
   return KB_OK;
 }
 
+int kb_forward_instances(kb_handle* h, const kb_instance_forwarding_config* cfg, const kb_frame* f, const uint8_t* id_is_background,
+                         int32_t n_background, int32_t* object_image_out, int32_t* n_clusters) {
+  if (!h || !cfg || !f || !object_image_out || (!f->depth && !f->depth_u16)) return fail(h, KB_ERR_INVALID, "null argument");
+  if (!h->has_cam) return fail(h, KB_ERR_STATE, "kb_set_camera must be called first");
+  KB_CUDA(h, cudaSetDevice(h->device));
+  h->main_dirty = true;
+  const kb_camera& c = h->cam;
+  const size_t px = static_cast<size_t>(c.width) * c.height;
+  int st;
+  if ((st = ensureObjectBuffers(h, px)) != KB_OK) return st;
+  h->inst_have = false;
+  h->inst_clusters.clear();
+  h->obj_label_host.assign(px, 0);
+  h->inst_keep_host.assign(px, 0);
+  if (!f->label && !f->label_u8) {
+    std::memset(object_image_out, 0, sizeof(int32_t) * px);
+    h->inst_have = true;
+    if (n_clusters) *n_clusters = 0;
+    return KB_OK;
+  }
+  if (!h->inst_counts) {
+    KB_CUDA(h, devAlloc(&h->inst_counts, KB_MAX_INSTANCE_IDS, 0));
+    KB_CUDA(h, devAlloc(&h->inst_bbox, static_cast<size_t>(KB_MAX_INSTANCE_IDS) * 6, 0));
+    KB_CUDA(h, devAlloc(&h->inst_background, KB_MAX_INSTANCE_IDS, 0));
+    KB_CUDA(h, devAlloc(&h->inst_bad, 1, 0));
+  }
+  if (h->inst_pixels < px) {
+    KB_CUDA(h, cudaStreamSynchronize(h->stream));
+    cudaFree(h->inst_keep);
+    h->inst_keep = nullptr;
+    KB_CUDA(h, devAlloc(&h->inst_keep, px, 0));
+    h->inst_pixels = px;
+  }
+  ObjectParams p{};
+  float R[9], t[3];
+  poseToFloat(f->world_T_sensor, R, t, p.Rw, p.tw);
+  p.W = c.width; p.H = c.height; p.fx = c.fx; p.fy = c.fy; p.cx = c.cx; p.cy = c.cy;
+  p.max_range = cfg->max_range;
+  if (f->depth_u16) {
+    const uint16_t* d16 = nullptr;
+    if ((st = stage(h, f->depth_u16, h->mot_depth16, px, f->memory, &d16)) != KB_OK) return st;
+    launchExpandDepth(d16, f->depth_u16_scale, h->obj_depth, static_cast<int>(px), h->stream);
+    p.depth = h->obj_depth;
+  } else if ((st = stage(h, f->depth, h->obj_depth, px, f->memory, &p.depth)) != KB_OK) {
+    return st;
+  }
+  if (f->label_u8) {
+    std::vector<uint8_t> tmp(px);
+    if (f->memory == KB_MEM_DEVICE) KB_CUDA(h, cudaMemcpy(tmp.data(), f->label_u8, px, cudaMemcpyDeviceToHost));
+    else std::memcpy(tmp.data(), f->label_u8, px);
+    for (size_t i = 0; i < px; ++i) h->obj_label_host[i] = tmp[i];
+    KB_CUDA(h, cudaMemcpyAsync(h->obj_label, h->obj_label_host.data(), sizeof(int) * px, cudaMemcpyHostToDevice, h->stream));
+    p.label = h->obj_label;
+  } else {
+    if ((st = stage(h, f->label, h->obj_label, px, f->memory, &p.label)) != KB_OK) return st;
+    if (f->memory == KB_MEM_DEVICE) KB_CUDA(h, cudaMemcpyAsync(h->obj_label_host.data(), f->label, sizeof(int) * px, cudaMemcpyDeviceToHost, h->stream));
+    else std::memcpy(h->obj_label_host.data(), f->label, sizeof(int) * px);
+  }
+  if ((st = stage(h, f->vertex_world, h->stg_vertex, px * 3, f->memory, &p.vertex)) != KB_OK) return st;
+  const uint8_t* bg = nullptr;
+  if (id_is_background && n_background > 0) {
+    std::vector<uint8_t> table(KB_MAX_INSTANCE_IDS, 0);
+    std::memcpy(table.data(), id_is_background, static_cast<size_t>(std::min<int32_t>(n_background, KB_MAX_INSTANCE_IDS)));
+    KB_CUDA(h, cudaMemcpyAsync(h->inst_background, table.data(), KB_MAX_INSTANCE_IDS, cudaMemcpyHostToDevice, h->stream));
+    KB_CUDA(h, cudaStreamSynchronize(h->stream));  // `table` is a local
+    bg = h->inst_background;
+  }
+  launchInstanceForward(p, bg, KB_MAX_INSTANCE_IDS, h->inst_counts, h->inst_bbox, h->inst_keep, h->inst_bad, h->stream);
+  KB_CUDA(h, cudaGetLastError());
+  std::vector<int> counts(KB_MAX_INSTANCE_IDS);
+  std::vector<unsigned int> bbox(static_cast<size_t>(KB_MAX_INSTANCE_IDS) * 6);
+  int bad = 0;
+  KB_CUDA(h, cudaMemcpyAsync(counts.data(), h->inst_counts, sizeof(int) * counts.size(), cudaMemcpyDeviceToHost, h->stream));
+  KB_CUDA(h, cudaMemcpyAsync(bbox.data(), h->inst_bbox, sizeof(unsigned int) * bbox.size(), cudaMemcpyDeviceToHost, h->stream));
+  KB_CUDA(h, cudaMemcpyAsync(h->inst_keep_host.data(), h->inst_keep, px, cudaMemcpyDeviceToHost, h->stream));
+  KB_CUDA(h, cudaMemcpyAsync(&bad, h->inst_bad, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  KB_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (bad) return fail(h, KB_ERR_INVALID, "instance id outside 0 .. KB_MAX_INSTANCE_IDS - 1");
+  std::memcpy(object_image_out, h->obj_label_host.data(), sizeof(int32_t) * px);  // object_image = label image (:83)
+  const bool filter_by_volume = cfg->min_object_volume > 0.0 || cfg->max_object_volume > 0.0;  // :68
+  auto decode = [](unsigned int o) {
+    const unsigned int b = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
+    float v;
+    std::memcpy(&v, &b, 4);
+    return v;
+  };
+  for (int id = 1; id < KB_MAX_INSTANCE_IDS; ++id) {
+    const int n = counts[id];
+    if (n == 0) continue;
+    if (n < cfg->min_cluster_size || (cfg->max_cluster_size > 0 && n > cfg->max_cluster_size)) continue;  // :119-122
+    kb_handle::InstCluster cl{};
+    cl.id = id;
+    cl.count = n;
+    for (int k = 0; k < 6; ++k) cl.bbox[k] = decode(bbox[static_cast<size_t>(id) * 6 + k]);
+    if (filter_by_volume) {  // :128-135, BoundingBox::volume() = product of the float dimensions
+      const float volume = (cl.bbox[3] - cl.bbox[0]) * (cl.bbox[4] - cl.bbox[1]) * (cl.bbox[5] - cl.bbox[2]);
+      if (volume < cfg->min_object_volume || (cfg->max_object_volume > 0.0 && volume > cfg->max_object_volume)) continue;
+    }
+    h->inst_clusters.push_back(cl);
+  }
+  h->inst_have = true;
+  if (n_clusters) *n_clusters = static_cast<int32_t>(h->inst_clusters.size());
+  return KB_OK;
+}
+
+int kb_get_instance_clusters(kb_handle* h, int32_t* id_count, float* bbox_min_max, int32_t* pixels_uv, int32_t* n_clusters,
+                             int32_t* total_pixels) {
+  if (!h) return KB_ERR_INVALID;
+  if (!h->inst_have) return fail(h, KB_ERR_STATE, "kb_forward_instances has not been called");
+  const int W = h->cam.width, H = h->cam.height;
+  int32_t total = 0;
+  std::vector<int> base(KB_MAX_INSTANCE_IDS, -1);
+  for (size_t c = 0; c < h->inst_clusters.size(); ++c) {
+    const auto& cl = h->inst_clusters[c];
+    if (id_count) { id_count[2 * c] = cl.id; id_count[2 * c + 1] = cl.count; }
+    if (bbox_min_max) std::memcpy(bbox_min_max + 6 * c, cl.bbox, sizeof(cl.bbox));
+    base[cl.id] = total;
+    total += cl.count;
+  }
+  if (pixels_uv && total > 0) {
+    std::vector<int> fill(KB_MAX_INSTANCE_IDS, 0);
+    for (int u = 0; u < W; ++u)      // the reference's scan order (:87-88)
+      for (int v = 0; v < H; ++v) {
+        const size_t px = static_cast<size_t>(v) * W + u;
+        if (!h->inst_keep_host[px]) continue;
+        const int id = h->obj_label_host[px];
+        if (id <= 0 || id >= KB_MAX_INSTANCE_IDS || base[id] < 0) continue;
+        const int k = base[id] + fill[id]++;
+        pixels_uv[2 * k] = u;
+        pixels_uv[2 * k + 1] = v;
+      }
+  }
+  if (n_clusters) *n_clusters = static_cast<int32_t>(h->inst_clusters.size());
+  if (total_pixels) *total_pixels = total;
+  return KB_OK;
+}
+
 int kb_get_object_clusters(kb_handle* h, int32_t* id_semantic_count, int32_t* pixels_uv, int32_t* n_clusters,
                            int32_t* total_pixels) {
   if (!h) return KB_ERR_INVALID;
@@ -1734,7 +1885,6 @@ int kb_track_measurements(kb_handle* h, const kb_frame* f, const int32_t* id_ima
     while (cap < 2 * cluster_pixels) cap <<= 1;
     if (cap - 1 < table.mask) table.mask = cap - 1;
   }
-  h->trk_mask = table.mask;
   launchTrackVoxelize(table, p, h->stream);
   h->mt_dirty = true;  // shared table memory
   KB_CUDA(h, cudaGetLastError());

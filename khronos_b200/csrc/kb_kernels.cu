@@ -568,17 +568,53 @@ __global__ void __launch_bounds__(kFuseThreads, COLOR ? KB_FUSE_COLOR_MIN_BLOCKS
     bool col_dirty = false;
 
     uint32_t rem = fmask;
+    // Software pipeline over the frames of the item (p.prefetch): the projection of the NEXT frame is computed one
+    // iteration early and the sectors its depth taps will hit are requested with prefetch.global.L1 (no destination
+    // register), so the taps of the next iteration find them in L1 instead of waiting an L2 round trip on the first use
+    // (the top long-scoreboard stall of the r2 capture). The carried (u, v, z) are the very values the iteration would
+    // compute itself, so results are unchanged.
+    float nu = 0.f, nv = 0.f, nz = -1.f;
+    auto project = [&](int b, float& u, float& v, float& z) {
+      const FrameView& f = p.f[b];
+      float x, y;
+      xform(f.R, f.t, wx, wy, wz, x, y, z);
+      if (z <= 0.f) return;
+      u = p.fx * x / z + p.cx;
+      v = p.fy * y / z + p.cy;
+      if (u < 0.f || u > static_cast<float>(p.W - 1) || v < 0.f || v > static_cast<float>(p.H - 1)) { z = -1.f; return; }
+      if (p.prefetch) {
+        const int u0 = static_cast<int>(floorf(u)), v0 = static_cast<int>(floorf(v));
+        const int i0 = v0 * p.W + u0;
+        const int i1 = min(v0 + 1, p.H - 1) * p.W + u0;
+        if constexpr (COMPACT) {
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(f.depth16 + i0));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(f.depth16 + i1));
+        } else {
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(f.depth + i0));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(f.depth + i1));
+          if (p.prefetch > 1 && f.label != nullptr) {
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(f.label + i0));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(f.label + i1));
+          }
+        }
+      }
+    };
+    if (p.prefetch && rem) project(__ffs(rem) - 1, nu, nv, nz);
     while (rem) {
       const int b = __ffs(rem) - 1;
       rem &= rem - 1;
       const FrameView& f = p.f[b];
       const bool has_label_img = L > 0 && (binary ? f.object_image != nullptr : (COMPACT ? f.label8 != nullptr : f.label != nullptr));
-      float x, y, z;
-      xform(f.R, f.t, wx, wy, wz, x, y, z);
+      float u, v, z;
+      if (p.prefetch) {
+        u = nu; v = nv; z = nz;
+        nz = -1.f;
+        if (rem) project(__ffs(rem) - 1, nu, nv, nz);
+      } else {
+        z = -1.f;
+        project(b, u, v, z);
+      }
       if (z <= 0.f) continue;
-      const float u = p.fx * x / z + p.cx;
-      const float v = p.fy * y / z + p.cy;
-      if (u < 0.f || u > static_cast<float>(p.W - 1) || v < 0.f || v > static_cast<float>(p.H - 1)) continue;
       float range = 0.f;
       const Taps taps = computeTaps<COMPACT>(p, f, u, v, range);
       if (!taps.valid) continue;

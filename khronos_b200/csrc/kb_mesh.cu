@@ -1,7 +1,7 @@
 // Marching cubes on the device: hydra::MeshIntegrator::generateMesh (UPSTREAM; call sites
 // khronos/src/active_window/active_window.cpp:223, khronos/src/active_window/object_extraction/mesh_object_extractor.cpp:267)
 // over the block pool, so that an output tick returns triangles instead of mirroring every updated block (68 KiB TSDF +
-// 328 KiB semantics each) back to a host hydra::VolumetricMap. Behaviour: docs/ORACLE_SPEC.md §10; parity oracle:
+// 328 KiB semantics each) back to a host hydra::VolumetricMap. Behaviour: docs/ORACLE_SPEC.md §13; parity oracle:
 // oracle/oracle_mesh.cpp.
 //
 // One CTA per block, two passes (count, emit) around a prefix sum, so that the vertex order is exactly the reference's

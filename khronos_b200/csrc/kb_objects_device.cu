@@ -9,7 +9,7 @@
 //     table (O1), one warp per occupied entry probes its neighbourhood and unions through a lock-free union-find (O2),
 //     per-root atomics accumulate pixel counts and the smallest key (O3), one CTA filters by size and ranks the kept
 //     roots by smallest key — semantic id ascending like the reference's std::map, then smallest voxel in (z,y,x)
-//     order (the determinisation of the unordered_map iteration, docs/ORACLE_SPEC.md §10) — into ids 1..N (O4), and
+//     order (the determinisation of the unordered_map iteration, docs/ORACLE_SPEC.md §13) — into ids 1..N (O4), and
 //     every pixel reads its root's id (O5).
 //   2D mode (semanticClustering2D :148-163 + growCluster2D :165-198 + filterClusters :200-217): union-find over the
 //     pixels in the reference's column-major scan order (index u*H + v, smaller index wins, so a component's root IS
@@ -309,6 +309,59 @@ __global__ void o2WriteKernel(MotionTable t, const __grid_constant__ ObjectParam
   p.image[v * p.W + u] = id;
 }
 
+// ---- InstanceForwarding (khronos/src/active_window/object_detection/instance_forwarding.cpp:80-149) -------------------
+// The detector that forwards instance ids of an upstream segmenter: per pixel a range / background test, per id a pixel
+// count and the world-frame bounding box of its vertices (for the volume filter). One pass over the image with per-id
+// atomics (ids < kMaxInstanceIds); floats are ordered through the usual sign-flip encoding so atomicMin / atomicMax apply.
+__device__ __forceinline__ unsigned int orderedBits(float f) {
+  const unsigned int b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+__global__ void instanceForwardKernel(const __grid_constant__ ObjectParams p, const uint8_t* __restrict__ background, int max_ids,
+                                      int* __restrict__ counts, unsigned int* __restrict__ bbox, uint8_t* __restrict__ keep,
+                                      int* __restrict__ bad_id) {
+  const int px = blockIdx.x * blockDim.x + threadIdx.x;
+  if (px >= p.W * p.H) return;
+  const int id = __ldg(&p.label[px]);
+  uint8_t k = 0;
+  if (id != 0) {
+    if (id < 0 || id >= max_ids) {
+      atomicExch(bad_id, 1);
+    } else {
+      const float range = __ldg(&p.depth[px]);
+      if (!(background && background[id]) && !(p.max_range > 0.f && range > p.max_range)) {
+        float wx, wy, wz;
+        if (p.vertex) {
+          wx = __ldg(&p.vertex[3 * px]); wy = __ldg(&p.vertex[3 * px + 1]); wz = __ldg(&p.vertex[3 * px + 2]);
+        } else {
+          const int u = px % p.W, v = px / p.W;
+          const float cxn = (static_cast<float>(u) - p.cx) / p.fx * range;
+          const float cyn = (static_cast<float>(v) - p.cy) / p.fy * range;
+          wx = ((p.Rw[0] * cxn + p.Rw[1] * cyn) + p.Rw[2] * range) + p.tw[0];
+          wy = ((p.Rw[3] * cxn + p.Rw[4] * cyn) + p.Rw[5] * range) + p.tw[1];
+          wz = ((p.Rw[6] * cxn + p.Rw[7] * cyn) + p.Rw[8] * range) + p.tw[2];
+        }
+        atomicAdd(&counts[id], 1);
+        unsigned int* b = bbox + static_cast<size_t>(id) * 6;
+        atomicMin(&b[0], orderedBits(wx)); atomicMin(&b[1], orderedBits(wy)); atomicMin(&b[2], orderedBits(wz));
+        atomicMax(&b[3], orderedBits(wx)); atomicMax(&b[4], orderedBits(wy)); atomicMax(&b[5], orderedBits(wz));
+        k = 1;
+      }
+    }
+  }
+  keep[px] = k;
+}
+
+__global__ void instanceInitKernel(int max_ids, int* __restrict__ counts, unsigned int* __restrict__ bbox, int* __restrict__ bad_id) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) *bad_id = 0;
+  if (i >= max_ids) return;
+  counts[i] = 0;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { bbox[static_cast<size_t>(i) * 6 + k] = 0xFFFFFFFFu; bbox[static_cast<size_t>(i) * 6 + 3 + k] = 0u; }
+}
+
 }  // namespace
 
 void launchObjectClustering3D(const MotionTable& t, const ObjectParams& p, cudaStream_t s) {
@@ -329,6 +382,13 @@ void launchObjectClustering2D(const MotionTable& t, const ObjectParams& p, cudaS
   o2ScanTilesKernel<<<tiles, 1024, 0, s>>>(t, P);
   o2ScanTotalsKernel<<<1, 1024, 0, s>>>(t, tiles);
   o2WriteKernel<<<(P + 255) / 256, 256, 0, s>>>(t, p);
+}
+
+void launchInstanceForward(const ObjectParams& p, const uint8_t* background, int max_ids, int* counts, unsigned int* bbox,
+                           uint8_t* keep, int* bad_id, cudaStream_t s) {
+  instanceInitKernel<<<(max_ids + 255) / 256, 256, 0, s>>>(max_ids, counts, bbox, bad_id);
+  const int P = p.W * p.H;
+  instanceForwardKernel<<<(P + 255) / 256, 256, 0, s>>>(p, background, max_ids, counts, bbox, keep, bad_id);
 }
 
 }  // namespace kb

@@ -24,4 +24,9 @@ struct ObjectParams {
 void launchObjectClustering3D(const MotionTable& t, const ObjectParams& p, cudaStream_t s);
 void launchObjectClustering2D(const MotionTable& t, const ObjectParams& p, cudaStream_t s);
 
+// InstanceForwarding: per-id pixel counts + world AABBs (ordered-bit encoded floats, min xyz then max xyz) of the pixels that
+// pass the range / background tests; keep[px] = 1 for those pixels. Uses ObjectParams' camera, pose, depth, label, vertex, max_range.
+void launchInstanceForward(const ObjectParams& p, const uint8_t* background, int max_ids, int* counts, unsigned int* bbox,
+                           uint8_t* keep, int* bad_id, cudaStream_t s);
+
 }  // namespace kb

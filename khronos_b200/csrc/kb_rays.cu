@@ -30,6 +30,7 @@
 #include <vector>
 
 #include <cuda_runtime.h>
+#include <cub/device/device_scan.cuh>
 
 #include "../../include/khronos_b200.h"
 #include "kb_device.cuh"
@@ -244,6 +245,8 @@ struct kb_ray_index {
   RayTable table{};
   uint32_t table_cap = 0;
   int* d_flags = nullptr;  // tableCountKernel: distinct blocks, overflow
+  void* scan_tmp = nullptr;  // cub::DeviceScan temporary storage (large tables)
+  size_t scan_tmp_bytes = 0;
   bool csr_valid = false;
   // scratch
   int* d_counts = nullptr; long long* d_offsets = nullptr; size_t cap_scratch = 0;
@@ -293,13 +296,20 @@ bool finite3(const float* p, size_t n) {
 }
 
 int allocTable(kb_ray_index* h, uint32_t cap) {
+  // allocate the new table first: an out-of-memory during growth must leave the old (valid) table in place
+  RayTable t{};
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&t.keys), sizeof(unsigned long long) * cap);
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&t.count), sizeof(int) * cap);
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&t.offset), sizeof(int) * cap);
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&t.cursor), sizeof(int) * cap);
+  if (e != cudaSuccess) {
+    cudaFree(t.keys); cudaFree(t.count); cudaFree(t.offset); cudaFree(t.cursor);
+    h->err = std::string("ray table allocation: ") + cudaGetErrorString(e);
+    return KB_ERR_CUDA;
+  }
+  cudaStreamSynchronize(h->stream);
   cudaFree(h->table.keys); cudaFree(h->table.count); cudaFree(h->table.offset); cudaFree(h->table.cursor);
-  h->table = RayTable{};
-  h->table_cap = 0;
-  KR_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->table.keys), sizeof(unsigned long long) * cap));
-  KR_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->table.count), sizeof(int) * cap));
-  KR_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->table.offset), sizeof(int) * cap));
-  KR_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->table.cursor), sizeof(int) * cap));
+  h->table = t;
   h->table_cap = cap;
   return KB_OK;
 }
@@ -326,7 +336,22 @@ int rebuildCsr(kb_ray_index* h) {
     if (h->table_cap >= (1u << 30)) return rfail(h, KB_ERR_CAPACITY, "too many distinct blocks");
     if ((st = allocTable(h, h->table_cap * 4u)) != KB_OK) return st;
   }
-  tableScanKernel<<<1, 1024, 0, h->stream>>>(h->table);
+  if (h->table_cap <= (1u << 16)) {
+    tableScanKernel<<<1, 1024, 0, h->stream>>>(h->table);  // small tables: one CTA is latency-optimal
+  } else {
+    // large tables (many distinct blocks): multi-CTA device scan, so a big map does not serialise on one SM
+    size_t tmp_bytes = 0;
+    KR_CUDA(h, cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, h->table.count, h->table.offset, static_cast<int>(h->table_cap), h->stream));
+    if (tmp_bytes > h->scan_tmp_bytes) {
+      KR_CUDA(h, cudaStreamSynchronize(h->stream));
+      cudaFree(h->scan_tmp);
+      h->scan_tmp = nullptr;
+      h->scan_tmp_bytes = 0;
+      KR_CUDA(h, cudaMalloc(&h->scan_tmp, tmp_bytes));
+      h->scan_tmp_bytes = tmp_bytes;
+    }
+    KR_CUDA(h, cub::DeviceScan::ExclusiveSum(h->scan_tmp, tmp_bytes, h->table.count, h->table.offset, static_cast<int>(h->table_cap), h->stream));
+  }
   if (h->n_pairs > 0) tableFillKernel<<<blocks, 256, 0, h->stream>>>(h->table, h->d_pair_keys, h->d_pair_rays, h->n_pairs, h->d_block_rays);
   KR_CUDA(h, cudaGetLastError());
   h->csr_valid = true;
@@ -360,7 +385,7 @@ int kb_rays_destroy(kb_ray_index* h) {
   cudaFree(h->d_src); cudaFree(h->d_dst); cudaFree(h->d_stamps); cudaFree(h->d_pair_keys); cudaFree(h->d_pair_rays);
   cudaFree(h->d_block_rays); cudaFree(h->table.keys); cudaFree(h->table.count); cudaFree(h->table.offset); cudaFree(h->table.cursor);
   cudaFree(h->d_counts); cudaFree(h->d_offsets); cudaFree(h->d_points); cudaFree(h->d_early); cudaFree(h->d_late);
-  cudaFree(h->d_pt_counts); cudaFree(h->d_pt_offsets); cudaFree(h->d_out); cudaFree(h->d_flags);
+  cudaFree(h->d_pt_counts); cudaFree(h->d_pt_offsets); cudaFree(h->d_out); cudaFree(h->d_flags); cudaFree(h->scan_tmp);
   delete h;
   return KB_OK;
 }
@@ -542,6 +567,10 @@ int kb_rays_set_endpoints(kb_ray_index* h, int32_t n_rays, const float* sources_
   if (!h || !sources_xyz || !targets_xyz) return rfail(h, KB_ERR_INVALID, "null argument");
   if (n_rays != h->n_rays) return rfail(h, KB_ERR_INVALID, "endpoint count differs from the number of rays");
   if (n_rays == 0) return KB_OK;
+  // same validation as kb_rays_add: a non-finite endpoint would make a later kb_rays_rehash drop rays (the reference's
+  // recomputeHash never does)
+  for (size_t i = 0; i < 3 * static_cast<size_t>(n_rays); ++i)
+    if (!std::isfinite(sources_xyz[i]) || !std::isfinite(targets_xyz[i])) return rfail(h, KB_ERR_INVALID, "non-finite ray endpoint");
   KR_CUDA(h, cudaSetDevice(h->device));
   KR_CUDA(h, cudaMemcpyAsync(h->d_src, sources_xyz, sizeof(float) * 3 * n_rays, cudaMemcpyHostToDevice, h->stream));
   KR_CUDA(h, cudaMemcpyAsync(h->d_dst, targets_xyz, sizeof(float) * 3 * n_rays, cudaMemcpyHostToDevice, h->stream));
@@ -562,10 +591,13 @@ int kb_rays_rehash(kb_ray_index* h) {
   KR_CUDA(h, cudaMemcpyAsync(dst.data(), h->d_dst, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, h->stream));
   KR_CUDA(h, cudaMemcpyAsync(ts.data(), h->d_stamps, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost, h->stream));
   KR_CUDA(h, cudaStreamSynchronize(h->stream));
+  // endpoints were validated when they were set (kb_rays_add / kb_rays_set_endpoints), so the re-add cannot reject rays
   std::vector<int32_t> pose = h->ray_pose, vertex = h->ray_vertex;
   kb_rays_clear(h);
   const int st = kb_rays_add(h, n, src.data(), dst.data(), ts.data(), nullptr, 0, nullptr);
-  if (st == KB_OK) { h->ray_pose = pose; h->ray_vertex = vertex; }
+  h->ray_pose = pose;  // the scene-graph ids survive either way; after a CUDA failure the index is empty and says so
+  h->ray_vertex = vertex;
+  if (st != KB_OK) { h->ray_pose.resize(static_cast<size_t>(h->n_rays)); h->ray_vertex.resize(static_cast<size_t>(h->n_rays)); }
   return st;
 }
 

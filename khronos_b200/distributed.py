@@ -231,6 +231,10 @@ class PeerShardedActiveWindow:
         self.peers.barrier()
         for h, ap, ah in zip(hs, self.all_pending, self.all_halo):
             h.tracking_finish(ap, ah)
+        # tracking_finish(k) reads this rank's all_pending / all_halo (ghost table, overflow words); a faster rank's
+        # tracking_begin_peers(k + 1) stores into them. Close the pass with a barrier so that back-to-back passes are safe
+        # without relying on spin_once's motion barrier for the ordering.
+        self.peers.barrier()
         if not with_motion_result:
             return None
         return [h.motion_result(want_image) for h in hs]

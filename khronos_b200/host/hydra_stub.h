@@ -126,6 +126,22 @@ inline Isometry3d InputData::getSensorPose() const {
   return r;
 }
 
+// hydra::MeshLayer stand-in (spark_dsg::Mesh per block: points, colors, labels, faces), what MeshIntegrator::generateMesh
+// fills and khronos::utils::combineMeshLayer (khronos/src/utils/geometry_utils.cpp:61-86) concatenates.
+struct MeshBlock {
+  BlockIndex index{0, 0, 0};
+  std::vector<std::array<float, 3>> points;
+  std::vector<std::array<uint8_t, 3>> colors;
+  std::vector<uint32_t> labels;
+  std::vector<std::array<size_t, 3>> faces;
+};
+struct MeshLayer {
+  std::map<BlockIndex, MeshBlock> blocks;
+  MeshBlock& allocateBlock(const BlockIndex& i) { auto& b = blocks[i]; b.index = i; return b; }
+  void removeBlock(const BlockIndex& i) { blocks.erase(i); }
+  size_t numBlocks() const { return blocks.size(); }
+};
+
 // hydra::timing::ScopedTimer / ElapsedTimeRecorder stand-ins (khronos aliases `Timer`, common_types.h:130): the adaptor
 // opens the reference's timer names so timing/stats.csv keeps its rows.
 namespace timing {

@@ -129,6 +129,46 @@ inline kb_frame makeFrame(const hydra::InputData& data, const cv::Mat* mask, con
   return f;
 }
 
+// hydra::MeshIntegrator stand-in (call sites active_window.cpp:223 `generateMesh(map_, true, true)`,
+// mesh_object_extractor.cpp:267 `generateMesh(map, true, false)`): marching cubes run on the device and only the
+// triangles of the processed blocks come back — the mesh blocks of `mesh_layer` are replaced block by block, exactly
+// what the reference's per-block `mesh_layer.allocateBlock(index)` + clear does. min_weight = hydra's
+// MeshIntegratorConfig::min_weight.
+class GpuMeshIntegrator {
+ public:
+  explicit GpuMeshIntegrator(float min_weight = 1e-4f) : min_weight_(min_weight) {}
+  // Returns the number of vertices written.
+  size_t generateMesh(GpuVolumetricMap& map, hydra::MeshLayer& mesh_layer, bool only_mesh_updated_blocks,
+                      bool clear_updated_flag) const {
+    Timer timer("active_window/generate_mesh", 0);
+    kb_handle* h = map.handle();
+    int32_t nb = 0;
+    int64_t nv = 0;
+    check(kb_generate_mesh(h, only_mesh_updated_blocks, clear_updated_flag, min_weight_, &nb, &nv), h, "kb_generate_mesh");
+    std::vector<int32_t> index(3 * static_cast<size_t>(nb));
+    std::vector<int64_t> off(static_cast<size_t>(nb) + 1);
+    std::vector<float> pts(3 * static_cast<size_t>(nv));
+    std::vector<uint8_t> rgb(3 * static_cast<size_t>(nv));
+    std::vector<uint32_t> lab(static_cast<size_t>(nv));
+    check(kb_get_mesh(h, index.data(), off.data(), pts.data(), rgb.data(), lab.data(), nv), h, "kb_get_mesh");
+    for (int32_t b = 0; b < nb; ++b) {
+      auto& blk = mesh_layer.allocateBlock({index[3 * b], index[3 * b + 1], index[3 * b + 2]});
+      const size_t n = static_cast<size_t>(off[b + 1] - off[b]), o = static_cast<size_t>(off[b]);
+      blk.points.resize(n); blk.colors.resize(n); blk.labels.resize(n); blk.faces.resize(n / 3);
+      for (size_t i = 0; i < n; ++i) {
+        blk.points[i] = {pts[3 * (o + i)], pts[3 * (o + i) + 1], pts[3 * (o + i) + 2]};
+        blk.colors[i] = {rgb[3 * (o + i)], rgb[3 * (o + i) + 1], rgb[3 * (o + i) + 2]};
+        blk.labels[i] = lab[o + i];
+      }
+      for (size_t f = 0; f < n / 3; ++f) blk.faces[f] = {3 * f, 3 * f + 1, 3 * f + 2};
+    }
+    return static_cast<size_t>(nv);
+  }
+
+ private:
+  float min_weight_;
+};
+
 // hydra::ProjectiveIntegrator stand-in. dynamic_image may be passed directly as the mask: the kernel
 // tests "!= 0", which is hydra::maskNonZero fused (active_window.cpp:209).
 class GpuProjectiveIntegrator {

@@ -111,6 +111,12 @@ class Oracle {
                      std::vector<ObjectCluster>* clusters);
   const std::vector<ObjectCluster>& objectClusters() const { return object_clusters_; }
 
+  // khronos::InstanceForwarding::extractSemanticClusters (object_detection/instance_forwarding.cpp:80-149).
+  struct InstanceCluster { int id = 0; std::vector<Pixel> pixels; float bbox[6] = {0, 0, 0, 0, 0, 0}; };
+  void forwardInstances(const kb_instance_forwarding_config& cfg, const kb_frame& f, const uint8_t* background, int n_background,
+                        int32_t* object_image);
+  const std::vector<InstanceCluster>& instanceClusters() const { return instance_clusters_; }
+
   // Track measurements: khronos::MaxIoUTracker, track_by = voxels (tracking/max_iou_tracker.cpp:450-459, :534-539,
   // :551-562) for the clusters of an id image (pixel values cluster_ids[0..max_id), or 1..max_id when cluster_ids is null). Results: per id the voxel set (ordered z, y, x), and per
   // (id, track) the intersection count and the IoU float of :562.
@@ -146,7 +152,7 @@ class Oracle {
 
   // Marching cubes over the TSDF: hydra::MeshIntegrator::generateMesh(map, only_mesh_updated_blocks, clear_updated_flag)
   // (UPSTREAM; call sites active_window.cpp:223, mesh_object_extractor.cpp:267; voxblox MeshIntegrator / MarchingCubes
-  // heritage, restated in docs/ORACLE_SPEC.md §10). One MeshBlock per processed block, blocks ascending (x, y, z);
+  // heritage, restated in docs/ORACLE_SPEC.md §13). One MeshBlock per processed block, blocks ascending (x, y, z);
   // vertices are not shared: triangle k of a block is (points[3k], points[3k+1], points[3k+2]).
   struct MeshBlock {
     Idx3 index;
@@ -213,6 +219,7 @@ class Oracle {
   std::vector<ObjectCluster> object_clusters_;
   TrackMeasurements track_result_;
   std::vector<MeshBlock> mesh_;
+  std::vector<InstanceCluster> instance_clusters_;
   std::vector<Block*> open_pending_;       // ever-free work list between trackingBegin and trackingFinish
   uint64_t open_stamp_ = 0;
   std::string error_;

@@ -180,6 +180,37 @@ int ko_map_checksum(ko_handle* h, uint64_t out[4]) {
   return KB_OK;
 }
 
+int ko_forward_instances(ko_handle* h, const kb_instance_forwarding_config* cfg, const kb_frame* f_in, const uint8_t* id_is_background,
+                         int32_t n_background, int32_t* object_image_out, int32_t* n_clusters) {
+  if (!h || !cfg || !f_in || !object_image_out || (!f_in->depth && !f_in->depth_u16)) return KB_ERR_INVALID;
+  kb_frame tmp;
+  const kb_frame* f = expandCompact(h, f_in, &tmp);
+  const size_t P = h->pixels;
+  if (f->label)
+    for (size_t i = 0; i < P; ++i)
+      if (f->label[i] < 0 || f->label[i] >= KB_MAX_INSTANCE_IDS) return KB_ERR_INVALID;
+  h->o->forwardInstances(*cfg, *f, id_is_background, n_background, object_image_out);
+  if (n_clusters) *n_clusters = static_cast<int32_t>(h->o->instanceClusters().size());
+  return h->o->ok() ? KB_OK : fail(h, KB_ERR_INVALID);
+}
+
+int ko_get_instance_clusters(ko_handle* h, int32_t* id_count, float* bbox_min_max, int32_t* pixels_uv, int32_t* n_clusters, int32_t* total_pixels) {
+  if (!h) return KB_ERR_INVALID;
+  int32_t total = 0;
+  size_t c = 0;
+  for (const auto& cl : h->o->instanceClusters()) {
+    if (id_count) { id_count[2 * c] = cl.id; id_count[2 * c + 1] = static_cast<int32_t>(cl.pixels.size()); }
+    if (bbox_min_max) std::memcpy(bbox_min_max + 6 * c, cl.bbox, sizeof(cl.bbox));
+    if (pixels_uv)
+      for (const auto& p : cl.pixels) { pixels_uv[2 * total] = p.u; pixels_uv[2 * total + 1] = p.v; ++total; }
+    else total += static_cast<int32_t>(cl.pixels.size());
+    ++c;
+  }
+  if (n_clusters) *n_clusters = static_cast<int32_t>(c);
+  if (total_pixels) *total_pixels = total;
+  return KB_OK;
+}
+
 int ko_generate_mesh(ko_handle* h, int only_mesh_updated, int clear_updated_flag, float min_weight, int32_t* n_blocks, int64_t* n_vertices) {
   if (!h) return KB_ERR_INVALID;
   h->o->generateMesh(only_mesh_updated != 0, clear_updated_flag != 0, min_weight);

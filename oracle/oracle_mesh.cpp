@@ -4,7 +4,7 @@
 // khronos/src/active_window/object_extraction/mesh_object_extractor.cpp:267 and concatenates the per-block meshes with
 // khronos/src/utils/geometry_utils.cpp:61-86). PARITY UNPINNED: restated from the published voxblox algorithm
 // (MeshIntegrator::extractMeshInsideBlock / extractMeshOnBorder, MarchingCubes::meshCube) it derives from; the frozen
-// behaviour is docs/ORACLE_SPEC.md §10.
+// behaviour is docs/ORACLE_SPEC.md §13.
 #include <algorithm>
 #include <cmath>
 
@@ -99,6 +99,49 @@ void Oracle::generateMesh(bool only_mesh_updated, bool clear_updated_flag, float
     for (int y = 0; y < m; ++y)
       for (int x = 0; x < m; ++x) cube(x, y, m);
     if (clear_updated_flag) b.mesh_updated = false;
+  }
+}
+
+// ---- InstanceForwarding (khronos/src/active_window/object_detection/instance_forwarding.cpp:80-149) ----------------------
+void Oracle::forwardInstances(const kb_instance_forwarding_config& cfg, const kb_frame& f, const uint8_t* background, int n_background,
+                              int32_t* object_image) {
+  instance_clusters_.clear();
+  const int W = cam_.width, H = cam_.height;
+  const size_t P = static_cast<size_t>(W) * H;
+  if (!f.label) { std::fill(object_image, object_image + P, 0); return; }
+  std::copy(f.label, f.label + P, object_image);  // :83 (shared buffer: filtered pixels keep their id)
+  std::vector<float> vertex;
+  const float* vm = f.vertex_world;
+  if (!vm) { vertex.resize(P * 3); computeVertexMap(f, vertex.data()); vm = vertex.data(); }
+  std::map<int32_t, std::vector<Pixel>> clusters;  // ascending id: determinisation of the unordered_map at :86
+  for (int u = 0; u < W; ++u)
+    for (int v = 0; v < H; ++v) {  // :87-88 column-major scan
+      const size_t px = static_cast<size_t>(v) * W + u;
+      const int32_t id = f.label[px];
+      if (id == 0) continue;                                                  // :90
+      if (background && id > 0 && id < n_background && background[id]) continue;  // :96-104, decided per id by the caller
+      if (cfg.max_range > 0.f && f.depth[px] > cfg.max_range) continue;       // :107-112
+      clusters[id].push_back(Pixel{u, v});                                    // :114
+    }
+  const bool filter_by_volume = cfg.min_object_volume > 0.0 || cfg.max_object_volume > 0.0;  // :68
+  for (const auto& kv : clusters) {
+    const int n = static_cast<int>(kv.second.size());
+    if (n < cfg.min_cluster_size || (cfg.max_cluster_size > 0 && n > cfg.max_cluster_size)) continue;  // :119-122
+    InstanceCluster cl;
+    cl.id = kv.first;
+    cl.pixels = kv.second;
+    for (int a = 0; a < 3; ++a) { cl.bbox[a] = 3.4e38f; cl.bbox[3 + a] = -3.4e38f; }
+    for (const Pixel& p : cl.pixels)
+      for (int a = 0; a < 3; ++a) {
+        const float x = vm[(static_cast<size_t>(p.v) * W + p.u) * 3 + a];
+        cl.bbox[a] = std::min(cl.bbox[a], x);
+        cl.bbox[3 + a] = std::max(cl.bbox[3 + a], x);
+      }
+    if (filter_by_volume) {  // :128-135
+      const float volume = (cl.bbox[3] - cl.bbox[0]) * (cl.bbox[4] - cl.bbox[1]) * (cl.bbox[5] - cl.bbox[2]);
+      if (volume < cfg.min_object_volume || (cfg.max_object_volume > 0.0 && volume > cfg.max_object_volume)) continue;
+    }
+    instance_clusters_.push_back(std::move(cl));
   }
 }
 

@@ -2,7 +2,9 @@
 // runs one flat-wall frame through GpuProjectiveIntegrator + GpuTrackingIntegrator + mirrorBack and
 // prints a few voxel values that tests/test_host_adaptor.py compares with the oracle.
 #include <cstdio>
+#include <cmath>
 #include <cstdlib>
+#include <algorithm>
 
 #include "../../khronos_b200/host/khronos_gpu_adaptor.h"
 
@@ -38,6 +40,14 @@ int main(int argc, char** argv) {
     auto blk = host.getTsdfLayer().getBlockPtr({0, 0, 2});
     if (!blk) { std::printf("missing block\n"); return 2; }
     const auto& v = blk->getVoxel(0 + 8 * (0 + 8 * 3));
+    // mesh of the fused wall (GpuMeshIntegrator = hydra::MeshIntegrator::generateMesh on the device): all vertices on z = 2
+    hydra::MeshLayer mesh_layer;
+    const size_t mesh_vertices = GpuMeshIntegrator().generateMesh(gmap, mesh_layer, true, true);
+    float mesh_err = 0.f;
+    for (const auto& kv : mesh_layer.blocks)
+      for (const auto& p : kv.second.points) mesh_err = std::max(mesh_err, std::fabs(p[2] - 2.f));
+    const size_t mesh_again = GpuMeshIntegrator().generateMesh(gmap, mesh_layer, true, true);  // flags were cleared
+    std::printf("mesh_vertices=%zu mesh_blocks=%zu mesh_err=%.4f mesh_again=%zu ", mesh_vertices, mesh_layer.numBlocks(), mesh_err, mesh_again);
     // object detector: the whole wall has label 3 -> one cluster when 3 is an object class
     kb_object_detector_config dc{};
     dc.use_full_connectivity = 1; dc.max_cluster_size = -1; dc.use_3d = 1; dc.grid_size = 0.1f; dc.is_object[3] = 1;

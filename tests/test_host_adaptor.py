@@ -37,5 +37,8 @@ def test_adaptor_frame_matches_known_answer(adaptor_exe):
     assert float(fields["weight"]) == pytest.approx(32 * 32 * 0.01 / 1.95 ** 4, rel=1e-5)
     assert int(fields["label"]) == 3
     assert int(fields["timers"]) == 3   # motion_detection/all, active_window/update_map, integration/tracking were opened
+    # GpuMeshIntegrator: the wall's mesh lies on z = 2, and the second tick finds no mesh_updated block
+    assert int(fields["mesh_vertices"]) > 300 and int(fields["mesh_blocks"]) > 5 and float(fields["mesh_err"]) < 2e-3
+    assert int(fields["mesh_again"]) == 0
     # reconstructStaticObject: dense box allocated, 12 frames fused, some low-confidence voxels erased
     assert int(fields["object_blocks"]) > 100 and int(fields["erased"]) >= 0

@@ -1,4 +1,4 @@
-"""Marching cubes (docs/ORACLE_SPEC.md §10): the case table and the oracle's mesher.
+"""Marching cubes (docs/ORACLE_SPEC.md §13): the case table and the oracle's mesher.
 The reference's mesher lives in un-vendored Hydra (parity unpinned); what can be pinned is pinned here:
   * both copies of the 256-case table (product + oracle) are identical, every row uses exactly the cube edges whose end
     points differ in sign, and meshes of random sign fields are closed, 2-manifold and consistently oriented;
@@ -70,7 +70,7 @@ def test_table_meshes_are_closed_manifold_and_oriented():
 
 
 def numpy_mesh(blocks: capi.Blocks, voxel_size, vps, min_weight=1e-4, only=None):
-    """Spec restatement (docs/ORACLE_SPEC.md §10) on an exported map: list of (block index, points (n,3) f32, labels)."""
+    """Spec restatement (docs/ORACLE_SPEC.md §13) on an exported map: list of (block index, points (n,3) f32, labels)."""
     f32 = np.float32
     V = vps ** 3
     idx = {tuple(b): i for i, b in enumerate(blocks.block_index.reshape(-1, 3).tolist())}

@@ -12,3 +12,6 @@ run mb12 KB_PRODUCT_LIB_VARIANT=mb12
 run default_ctas8 KB_FUSE_CTAS_PER_SM=8
 run nolist KB_FUSE_ITEM_LIST=0
 run default2 A=1
+echo "== full default bench with legs"
+timeout 600 python bench.py > $O/bench_full.json 2> $O/bench_full.err; echo "rc=$?"; python -c "
+import json;d=json.load(open('$O/bench_full.json'));print(round(d['value']),'fps; e2e',d['e2e'] and round(d['e2e']['value']));print('tick',d.get('output_tick'));print('dynamic',d.get('configs'));print('next',d.get('next_rows'))" || tail -5 $O/bench_full.err
