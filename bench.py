@@ -710,6 +710,47 @@ def main_hall_cells(args, world, rank, local_rank, dev):
     all_cs = [torch.empty_like(cst) for _ in range(world)]
     dist.all_gather(all_cs, cst)
 
+    # ---- e2e at N GPUs: every rank integrates the frames it needs from its OWN pinned host memory over its own PCIe link
+    # (the production ingest: the host knows the poses, so it hands each frame only to the ranks whose cells it touches)
+    e2e = None
+    if not args.no_e2e:
+        n_e = min(args.e2e_frames, lap) if not args.small else min(64, lap)
+        step_e = Wm + K + 2
+        need = [(j, frame_index(step_e, j)) for j in range(n_e) if (int(masks[frame_index(step_e, j)]) >> rank) & 1]
+        hd = torch.empty((max(len(need), 1), H, W), dtype=torch.float32, pin_memory=True)
+        hl = torch.empty((max(len(need), 1), H, W), dtype=torch.int32, pin_memory=True)
+        for k, (j, g) in enumerate(need):
+            d, l = syn.render(scene, cam, poses[g], 0.0, device=dev, dtype=torch.float32)
+            hd[k].copy_(d)
+            hl[k].copy_(l)
+        torch.cuda.synchronize()
+        fr = [h.make_frame(hd[k].data_ptr(), poses[g], stamp_of(step_e, j), label=hl[k].data_ptr(), memory=capi.MEM_HOST_ASYNC)
+              for k, (j, g) in enumerate(need)]
+        ecalls = [((capi.Frame * len(fr[k:k + B]))(*fr[k:k + B]), len(fr[k:k + B])) for k in range(0, len(fr), B)]
+
+        def run_window():
+            stats = capi.FrameStats()
+            for k, (arr, n) in enumerate(ecalls):
+                st = integrate_n(hptr, arr, n, 1, ctypes.byref(stats) if k == len(ecalls) - 1 else None)  # D2H of the result
+                if st != 0:
+                    raise RuntimeError(f"kb_integrate_frames (host) failed: {st}")
+            h.synchronize()
+        # untimed pass first (staging buffers), on other stamps: reuse the same frames with later stamps is not possible
+        # (stamps must increase), so the window is timed on first use after one small warm-up call
+        barrier()
+        t0 = time.perf_counter()
+        run_window()
+        dt_local = time.perf_counter() - t0
+        t = torch.tensor([dt_local, float(len(need))], device=dev, dtype=torch.float64)
+        all_t = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(all_t, t)
+        dt_max = max(float(x[0].item()) for x in all_t)
+        deliveries = sum(float(x[1].item()) for x in all_t)
+        e2e = {"value": n_e / dt_max, "unit": "frames/s", "h2d_bytes_per_step": int(deliveries * P * bpp),
+               "d2h_bytes_per_step": world * (ctypes.sizeof(capi.FrameStats) + 64), "frames_per_step": n_e,
+               "note": "every rank integrates the frames that touch its cells from its own pinned host buffers "
+                       "(kb_integrate_frames, KB_MEM_HOST_ASYNC, %d frames/call) over its own PCIe link; max over ranks" % B}
+
     if rank == 0:
         A = np.array([x.cpu().numpy() for x in all_stats])
         parts = [[int(v) & ((1 << 64) - 1) for v in c.cpu().tolist()] for c in all_cs]
@@ -743,7 +784,7 @@ def main_hall_cells(args, world, rank, local_rank, dev):
                          "gather_ms_per_rank": [round(float(x), 2) for x in A[:, 5]],
                          "reference_gbps": 770.0, "reference": "measured peer copy per direction (B200_PROFILING.md)"},
             "checksum": combine_checksums(parts),
-            "roofline": roof, "cpu_baseline": None, "e2e": None, "gpu_launches": 6 * n_calls, "clocks": clocks, "wall_s_timed": wall,
+            "roofline": roof, "cpu_baseline": None, "e2e": e2e, "gpu_launches": 6 * n_calls, "clocks": clocks, "wall_s_timed": wall,
         }
         emit(out)
     dist.barrier()
@@ -1017,7 +1058,7 @@ def main():
     legs = {}
     if world == 1 and not args.no_legs and not compact and args.workload == "hall640":
         import bench_legs
-        tick_step = Wm + K + 8
+        tick_step = Wm + K  # stamps after the timed steps and before the e2e windows (stamps must not decrease)
 
         def tick_batch(t):
             fr = [h.make_frame(depth[(t * 12 + j) % lap].data_ptr(), poses[(t * 12 + j) % lap], stamp_of(tick_step, t * 12 + j),
@@ -1070,15 +1111,15 @@ def main():
             run_window(calls)
             return time.perf_counter() - t0
 
-        timed_window(Wm + K, compact)            # untimed: the library allocates its staging buffers here
-        dt = timed_window(Wm + K + 1, compact)
+        timed_window(Wm + K + 1, compact)        # untimed: the library allocates its staging buffers here
+        dt = timed_window(Wm + K + 2, compact)
         e2e = {"value": n_e / dt, "unit": "frames/s", "h2d_bytes_per_step": n_e * P * bpp,
                "d2h_bytes_per_step": ctypes.sizeof(capi.FrameStats) + 64, "frames_per_step": n_e,
                "note": "host pinned depth+label ring -> kb_integrate_frames(KB_MEM_HOST_ASYNC, %d frames/call); stats read back at step end" % B}
         if not compact:
             # informational: the same window shipped in the sensor-native compact formats (kb_frame.depth_u16 / label_u8)
-            timed_window(Wm + K + 2, True)
-            dtc = timed_window(Wm + K + 3, True)
+            timed_window(Wm + K + 3, True)
+            dtc = timed_window(Wm + K + 4, True)
             e2e["compact_wire"] = {"value": n_e / dtc, "unit": "frames/s", "h2d_bytes_per_step": n_e * P * 3,
                                    "note": "u16 millimetre depth + u8 labels, expanded on the device (3 B/pixel over PCIe)"}
 

@@ -93,7 +93,7 @@ def leg_dynamic_hall(args, cam, scene, poses, stamps, depth, label, dev, cpu_thr
     stamp = lambda g: 1_000_000_000 + g * dt
     t_r = time.perf_counter()
     dposes = [poses[i % lap] for i in range(n_timed)]
-    extra = syn.companion_cuboids(dposes, start_frame=0)
+    extra = syn.companion_cuboids(dposes, start_frame=0, size=(1.5, 1.5, 2.2))  # ~20 % of a 640x480 / f = 320 image at 2.2 m
     dd, dl = syn.render_stream(scene, cam, dposes, [stamp(lap + i) for i in range(n_timed)], device=dev, dtype=torch.float32, extra=extra)
     torch.cuda.synchronize()
     t_r = time.perf_counter() - t_r

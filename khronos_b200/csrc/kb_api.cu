@@ -83,7 +83,6 @@ struct kb_handle {
   int narrow_threads = 8;
   uint8_t* pin_label8 = nullptr;
   size_t pin_label8_pixels = 0;
-  int fuse_prefetch = 0;       // KB_FUSE_PREFETCH: software-pipelined frame loop with L1 prefetch of the next frame's taps
   int mlp_group = 0;           // KB_FUSE_MLP experiment: 0 (off), 2 or 4 frames per memory-level-parallel group
   int cull_grid = 0;
   int parity = 0;
@@ -557,7 +556,6 @@ int kb_create(const kb_map_config* map, const kb_integrator_config* integ, const
       KB_CUDA(h, devAlloc(&h->work_upd2, S, 0));
       KB_CUDA(h, devAlloc(&h->item_fmask2, S * h->batch.items_per_block, 0));
     }
-    if (const char* e = std::getenv("KB_FUSE_PREFETCH")) h->fuse_prefetch = std::max(0, std::min(2, std::atoi(e)));
     if (const char* e = std::getenv("KB_FUSE_MLP")) h->mlp_group = e[0] == '2' ? 2 : (e[0] == '4' ? 4 : 0);
     if (h->use_item_list) {  // experiment, off by default (results are identical either way: only the item order changes)
       h->item_list_cap = static_cast<int>(std::min<size_t>(S * h->batch.items_per_block, size_t(1) << 28));
@@ -867,7 +865,6 @@ static int integrateBatch(kb_handle* h, const kb_frame* frames, int n, int alloc
                     ? h->item_list + ((pipe && par) ? static_cast<size_t>(kItemClasses) * h->item_list_cap : 0) : nullptr;
   p.item_list_cap = h->item_list_cap;
   p.mlp_group = h->mlp_group;
-  p.prefetch = h->fuse_prefetch;
   if (any_color) {
     int st = ensureColorLayer(h);
     if (st == KB_OK && any_host_color) st = ensureColorStaging(h, px);
@@ -1046,6 +1043,11 @@ static int integrateBatch(kb_handle* h, const kb_frame* frames, int n, int alloc
     }
     KB_CUDA(h, cudaMemsetAsync(h->dm.counters + kCtrWork0 + par, 0, sizeof(int), ps));
     KB_CUDA(h, cudaMemsetAsync(h->dm.counters + p.fetch_ctr, 0, sizeof(int), ps));
+  }
+  if (!pipe && h->pipelined) {
+    // Short batch between pipelined ones: the classic protocol expects the PREVIOUS batch's K0 to have zeroed this batch's
+    // work counter, which pipelined batches (whose counters the host resets) do not do.
+    KB_CUDA(h, cudaMemsetAsync(h->dm.counters + kCtrWork0 + par, 0, sizeof(int), ps));
   }
   if (any_compact && !all_compact) launchExpandFrames(p, ps);
   if (p.cull) launchTileMax(p, ps);

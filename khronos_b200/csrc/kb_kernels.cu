@@ -568,53 +568,17 @@ __global__ void __launch_bounds__(kFuseThreads, COLOR ? KB_FUSE_COLOR_MIN_BLOCKS
     bool col_dirty = false;
 
     uint32_t rem = fmask;
-    // Software pipeline over the frames of the item (p.prefetch): the projection of the NEXT frame is computed one
-    // iteration early and the sectors its depth taps will hit are requested with prefetch.global.L1 (no destination
-    // register), so the taps of the next iteration find them in L1 instead of waiting an L2 round trip on the first use
-    // (the top long-scoreboard stall of the r2 capture). The carried (u, v, z) are the very values the iteration would
-    // compute itself, so results are unchanged.
-    float nu = 0.f, nv = 0.f, nz = -1.f;
-    auto project = [&](int b, float& u, float& v, float& z) {
-      const FrameView& f = p.f[b];
-      float x, y;
-      xform(f.R, f.t, wx, wy, wz, x, y, z);
-      if (z <= 0.f) return;
-      u = p.fx * x / z + p.cx;
-      v = p.fy * y / z + p.cy;
-      if (u < 0.f || u > static_cast<float>(p.W - 1) || v < 0.f || v > static_cast<float>(p.H - 1)) { z = -1.f; return; }
-      if (p.prefetch) {
-        const int u0 = static_cast<int>(floorf(u)), v0 = static_cast<int>(floorf(v));
-        const int i0 = v0 * p.W + u0;
-        const int i1 = min(v0 + 1, p.H - 1) * p.W + u0;
-        if constexpr (COMPACT) {
-          asm volatile("prefetch.global.L1 [%0];" ::"l"(f.depth16 + i0));
-          asm volatile("prefetch.global.L1 [%0];" ::"l"(f.depth16 + i1));
-        } else {
-          asm volatile("prefetch.global.L1 [%0];" ::"l"(f.depth + i0));
-          asm volatile("prefetch.global.L1 [%0];" ::"l"(f.depth + i1));
-          if (p.prefetch > 1 && f.label != nullptr) {
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(f.label + i0));
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(f.label + i1));
-          }
-        }
-      }
-    };
-    if (p.prefetch && rem) project(__ffs(rem) - 1, nu, nv, nz);
     while (rem) {
       const int b = __ffs(rem) - 1;
       rem &= rem - 1;
       const FrameView& f = p.f[b];
       const bool has_label_img = L > 0 && (binary ? f.object_image != nullptr : (COMPACT ? f.label8 != nullptr : f.label != nullptr));
-      float u, v, z;
-      if (p.prefetch) {
-        u = nu; v = nv; z = nz;
-        nz = -1.f;
-        if (rem) project(__ffs(rem) - 1, nu, nv, nz);
-      } else {
-        z = -1.f;
-        project(b, u, v, z);
-      }
+      float x, y, z;
+      xform(f.R, f.t, wx, wy, wz, x, y, z);
       if (z <= 0.f) continue;
+      const float u = p.fx * x / z + p.cx;
+      const float v = p.fy * y / z + p.cy;
+      if (u < 0.f || u > static_cast<float>(p.W - 1) || v < 0.f || v > static_cast<float>(p.H - 1)) continue;
       float range = 0.f;
       const Taps taps = computeTaps<COMPACT>(p, f, u, v, range);
       if (!taps.valid) continue;
@@ -686,11 +650,15 @@ __global__ void __launch_bounds__(kFuseThreads, COLOR ? KB_FUSE_COLOR_MIN_BLOCKS
           s_rows[label * kFuseThreads + threadIdx.x] = c;
           best_label = s_rows[kFuseThreads + threadIdx.x] > s_rows[threadIdx.x] ? 1 : 0;
         } else {
-          float bestv = 0.f;
-          for (int kk = 0; kk < L; ++kk) {
-            const float c = s_rows[kk * kFuseThreads + threadIdx.x] + (static_cast<uint32_t>(kk) == label ? p.mle_diag : p.mle_off);
-            s_rows[kk * kFuseThreads + threadIdx.x] = c;
-            if (kk == 0 || c > bestv) { bestv = c; best_label = kk; }
+          // likelihoods += logM[:, label]: two independent shared-memory read-modify-writes per step (entries beyond L are
+          // padding that nobody reads); the arg max is taken once, when the row is written back — only its final value
+          // is ever stored, and it only depends on the final row
+          for (int k2 = 0; k2 < m.Lp; k2 += 2) {
+            float c0 = s_rows[(k2 + 0) * kFuseThreads + threadIdx.x], c1 = s_rows[(k2 + 1) * kFuseThreads + threadIdx.x];
+            c0 += static_cast<uint32_t>(k2 + 0) == label ? p.mle_diag : p.mle_off;
+            c1 += static_cast<uint32_t>(k2 + 1) == label ? p.mle_diag : p.mle_off;
+            s_rows[(k2 + 0) * kFuseThreads + threadIdx.x] = c0;
+            s_rows[(k2 + 1) * kFuseThreads + threadIdx.x] = c1;
           }
         }
         ++n_sem;
@@ -716,6 +684,14 @@ __global__ void __launch_bounds__(kFuseThreads, COLOR ? KB_FUSE_COLOR_MIN_BLOCKS
           for (int k4 = 0; k4 < m.Lp; k4 += 4)
             lk[k4 >> 2] = make_float4(s_rows[(k4 + 0) * kFuseThreads + threadIdx.x], s_rows[(k4 + 1) * kFuseThreads + threadIdx.x],
                                       s_rows[(k4 + 2) * kFuseThreads + threadIdx.x], s_rows[(k4 + 3) * kFuseThreads + threadIdx.x]);
+        }
+        if (!binary) {  // SemanticVoxel::semantic_label = first maximum of the final likelihoods (UP App. A.8)
+          float bestv = s_rows[threadIdx.x];
+          best_label = 0;
+          for (int kk = 1; kk < L; ++kk) {
+            const float c = s_rows[kk * kFuseThreads + threadIdx.x];
+            if (c > bestv) { bestv = c; best_label = kk; }
+          }
         }
         m.sem_label[si] = static_cast<uint16_t>(best_label);
       }
@@ -1004,11 +980,15 @@ __global__ void __launch_bounds__(kFuseThreads, KB_FUSE_MLP_MIN_BLOCKS) fuseKern
               s_rows[label * kFuseThreads + threadIdx.x] = c;
               best_label = s_rows[kFuseThreads + threadIdx.x] > s_rows[threadIdx.x] ? 1 : 0;
             } else {
-              float bestv = 0.f;
-              for (int kk = 0; kk < L; ++kk) {
-                const float c = s_rows[kk * kFuseThreads + threadIdx.x] + (static_cast<uint32_t>(kk) == label ? p.mle_diag : p.mle_off);
-                s_rows[kk * kFuseThreads + threadIdx.x] = c;
-                if (kk == 0 || c > bestv) { bestv = c; best_label = kk; }
+              // likelihoods += logM[:, label]: two independent shared-memory read-modify-writes per step (entries beyond L are
+              // padding that nobody reads); the arg max is taken once, when the row is written back — only its final value
+              // is ever stored, and it only depends on the final row
+              for (int k2 = 0; k2 < m.Lp; k2 += 2) {
+                float c0 = s_rows[(k2 + 0) * kFuseThreads + threadIdx.x], c1 = s_rows[(k2 + 1) * kFuseThreads + threadIdx.x];
+                c0 += static_cast<uint32_t>(k2 + 0) == label ? p.mle_diag : p.mle_off;
+                c1 += static_cast<uint32_t>(k2 + 1) == label ? p.mle_diag : p.mle_off;
+                s_rows[(k2 + 0) * kFuseThreads + threadIdx.x] = c0;
+                s_rows[(k2 + 1) * kFuseThreads + threadIdx.x] = c1;
               }
             }
             ++n_sem;
@@ -1031,6 +1011,14 @@ __global__ void __launch_bounds__(kFuseThreads, KB_FUSE_MLP_MIN_BLOCKS) fuseKern
             for (int k4 = 0; k4 < m.Lp; k4 += 4)
               lk[k4 >> 2] = make_float4(s_rows[(k4 + 0) * kFuseThreads + threadIdx.x], s_rows[(k4 + 1) * kFuseThreads + threadIdx.x],
                                         s_rows[(k4 + 2) * kFuseThreads + threadIdx.x], s_rows[(k4 + 3) * kFuseThreads + threadIdx.x]);
+          }
+          if (!binary) {  // SemanticVoxel::semantic_label = first maximum of the final likelihoods (UP App. A.8)
+            float bestv = s_rows[threadIdx.x];
+            best_label = 0;
+            for (int kk = 1; kk < L; ++kk) {
+              const float c = s_rows[kk * kFuseThreads + threadIdx.x];
+              if (c > bestv) { bestv = c; best_label = kk; }
+            }
           }
           m.sem_label[si] = static_cast<uint16_t>(best_label);
         }

@@ -90,7 +90,7 @@ def test_oracle_matches_reference_restatement(oracle_lib, kw):
 @pytest.mark.gpu
 @pytest.mark.parametrize("kw", CASES)
 def test_product_matches_oracle(oracle_lib, product_lib, kw):
-    cam, pose, d, ids = instance_frame(2)
+    cam, pose, d, ids = instance_frame()
     o = hs.make_handle(oracle_lib, "ko_", cam=cam)
     g = hs.make_handle(product_lib, "kb_", cam=cam)
     io, co, _ = _run(o, cam, pose, d, ids, kw)
