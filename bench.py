@@ -43,7 +43,9 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames-per-step", type=int, default=5000,
                     help="frames per step (default: one full lap, 12.3 GB of f32 input; 10 steps = ~0.4 s timed region)")
-    ap.add_argument("--batch", type=int, default=32, help="frames per kb_integrate_frames call (1 = per-frame calls)")
+    ap.add_argument("--batch", type=int, default=0,
+                    help="frames per kb_integrate_frames call; 0 (default) = the whole step in one call (the library fuses 32 frames "
+                         "per kernel group inside a call and pipelines the groups); 1 = per-frame calls")
     ap.add_argument("--lap-frames", type=int, default=5000, help="frames in one lap of the trajectory (pool in HBM)")
     ap.add_argument("--max-blocks", type=int, default=90000)
     ap.add_argument("--cpu-sample-frames", type=int, default=5000,
@@ -499,6 +501,13 @@ def hbm_peak():
         return 6650.0, "fallback 6650 (of fallback)"
 
 
+GROUP = 32  # frames fused per kernel group inside a kb_integrate_frames call (csrc/kb_kernels.cuh kMaxBatch)
+
+
+def n_groups(n):
+    return (n + GROUP - 1) // GROUP
+
+
 def roofline_block(args, B, n_calls, gpu_ms, sampled_us, nv, nsem, nblk, n_frames, P, bpp, world=1):
     """roofline of the dominant kernel group (one kb_integrate_frames call = tile pyramid + K0 + K0b + item lists + fuse
     kernel for B frames). achieved = algorithmic bytes of the timed region / device time of the timed region (every
@@ -603,7 +612,7 @@ def main_hall_cells(args, world, rank, local_rank, dev):
     stream = torch.cuda.Stream(device=dev)
     xstream = torch.cuda.Stream(device=dev)
     h.set_stream(stream.cuda_stream)
-    B = max(1, min(args.batch, F))
+    B = F if args.batch <= 0 else max(1, min(args.batch, F))  # frames per kb_integrate_frames call
 
     def frame_index(step, j):
         return (step * F + j) % lap
@@ -650,12 +659,12 @@ def main_hall_cells(args, world, rank, local_rank, dev):
         stream.wait_event(ready[s])
         with torch.cuda.stream(stream):
             for k, (arr, n) in enumerate(calls[s]):
-                if samples is not None and k % 4 == 2 and n == B:
+                if samples is not None and n >= GROUP:
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     e0.record(stream)
                     st = integrate_n(hptr, arr, n, 1, None)
                     e1.record(stream)
-                    samples.append((e0, e1))
+                    samples.append((e0, e1, n))
                 else:
                     st = integrate_n(hptr, arr, n, 1, None)
                 if st != 0:
@@ -755,9 +764,9 @@ def main_hall_cells(args, world, rank, local_rank, dev):
         A = np.array([x.cpu().numpy() for x in all_stats])
         parts = [[int(v) & ((1 << 64) - 1) for v in c.cpu().tolist()] for c in all_cs]
         fps = n_frames / (gpu_ms * 1e-3)
-        full = [a.elapsed_time(b) for a, b in samples]
-        n_calls = sum(len(calls[s]) for s in range(Wm, Wm + K))
-        roof = roofline_block(args, B, n_calls, busy[0], float(np.mean(full) * 1e3) if full else None, nv, nsem, nblk,
+        full = [a.elapsed_time(b) / n_groups(n) for a, b, n in samples]
+        n_calls = sum(n_groups(n) for s in range(Wm, Wm + K) for _, n in calls[s])
+        roof = roofline_block(args, GROUP, n_calls, busy[0], float(np.mean(full) * 1e3) if full else None, nv, nsem, nblk,
                               my_frames, P, bpp, world=world)
         gbps = [float(A[r, 6] / (A[r, 5] * 1e-3) / 1e9) if A[r, 5] > 0 else 0.0 for r in range(world)]
         out = {
@@ -766,7 +775,7 @@ def main_hall_cells(args, world, rank, local_rank, dev):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload if not args.small else "hall160-small", "image": [W, H], "voxel_size": mc.voxel_size,
                        "voxels_per_side": 16, "truncation": mc.truncation_distance, "semantics": f"MLE L={L_LABELS}",
-                       "frames_per_step": F, "frames_per_call": B, "wire_format": "depth f32 + label i32 (8 B/px)", "lap_frames": lap,
+                       "frames_per_step": F, "frames_per_call": B, "frames_per_kernel_group": GROUP, "wire_format": "depth f32 + label i32 (8 B/px)", "lap_frames": lap,
                        "live_blocks_all_ranks": int(A[:, 7].sum()),
                        "l2": "inputs larger than L2: each step streams %.1f GB of frames" % (F * P * bpp / 1e9),
                        "parallelism": "cell shard x%d (cells of %d x %d blocks = %.1f m, %d x %d rank tiling); stream resident %s; every rank pulls the "
@@ -920,7 +929,7 @@ def main():
         g = step * F + j
         return 1_000_000_000 + g * 33_333_333
 
-    B = max(1, min(args.batch, F))
+    B = F if args.batch <= 0 else max(1, min(args.batch, F))  # frames per kb_integrate_frames call
     integrate_n = h._fn("integrate_frames")
     hptr = h._h
 
@@ -987,7 +996,7 @@ def main():
             stream.wait_stream(cur)
         with torch.cuda.stream(stream):
             for j, (arr, n) in enumerate(prebuilt[step]):
-                if sample_events is not None and j % 4 == 2:
+                if sample_events is not None and n >= GROUP:
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     e0.record(stream)
                     st = integrate_n(hptr, arr, n, 1, None)
@@ -1049,10 +1058,10 @@ def main():
         nv_all, nsem_all, nblk_all = float(nv), float(nsem), float(nblk)
         cs_parts = [cs]
     fps = n_frames / (gpu_ms * 1e-3)
-    full = [(a.elapsed_time(b), n) for a, b, n in samples if n == B]
-    kern_us = float(np.mean([t for t, _ in full]) * 1e3) if full else None  # main-stream time of one kb_integrate_frames call
-    n_launch = sum(len(prebuilt[s]) for s in range(Wm, Wm + K))
-    roof = roofline_block(args, B, n_launch, gpu_ms, kern_us, nv, nsem, nblk, n_frames, P, bpp, world=world)
+    full = [a.elapsed_time(b) / n_groups(n) for a, b, n in samples]
+    kern_us = float(np.mean(full) * 1e3) if full else None  # main-stream time per 32-frame kernel group, from per-call events
+    n_launch = sum(n_groups(n) for s in range(Wm, Wm + K) for _, n in prebuilt[s])
+    roof = roofline_block(args, GROUP, n_launch, gpu_ms, kern_us, nv, nsem, nblk, n_frames, P, bpp, world=world)
 
     # ---- secondary legs (N = 1): output tick on the benchmarked map (after the checksum: it integrates more frames)
     legs = {}
@@ -1161,6 +1170,7 @@ def main():
             "config": {"workload": args.workload if not args.small else "hall160-small",
                        "image": [cam.width, cam.height], "voxel_size": mc.voxel_size, "voxels_per_side": 16,
                        "truncation": mc.truncation_distance, "semantics": f"MLE L={L_LABELS}", "frames_per_step": F, "frames_per_call": B,
+                       "frames_per_kernel_group": GROUP,
                        "wire_format": ("depth u16 mm + label u8 (3 B/px), expanded on device" if compact else
                                        "depth f32 + label u8 (5 B/px, lossless; labels widened on device)" if f32u8 else
                                        "depth f32 + label i32 (8 B/px)"),

@@ -161,7 +161,11 @@ int kb_destroy(kb_handle* h);
 const char* kb_last_error(const kb_handle* h);
 int kb_abi_version(void);
 
-/* Use an externally owned cudaStream_t (e.g. torch's current stream) for all work of this handle. */
+/* Use an externally owned cudaStream_t (e.g. torch's current stream) for all work of this handle. Stream order is honoured
+ * at CALL boundaries: work the caller enqueued on the stream before a call precedes everything the call does, and
+ * everything a call does precedes what the caller enqueues afterwards. Inside one kb_integrate_frames call the batches of
+ * 32 frames are pipelined over an internal stream (the block selection of batch i+1 overlaps the fusion of batch i), so
+ * hand a stream's frames over in large calls (a whole replay step), not 32 at a time. */
 int kb_set_stream(kb_handle* h, void* cuda_stream);
 int kb_synchronize(kb_handle* h);
 

@@ -1088,6 +1088,10 @@ int kb_integrate_frames(kb_handle* h, const kb_frame* frames, int32_t n_frames, 
     std::memcpy(h->prev_ctr, h->h_ctr, sizeof(h->prev_ctr));
     h->ctr_dirty = false;
   }
+  // Caller-owned stream (kb_set_stream): whatever the caller enqueued on it before this call (e.g. the copy / kernel that
+  // produces device-resident frames) must precede the call's work. The prologue of a pipelined batch runs on an internal
+  // stream, so the first batch of every call orders itself behind the caller's stream; the batches inside the call pipeline.
+  if (!h->own_stream) h->main_dirty = true;
   for (int i = 0; i < n_frames; i += kMaxBatch) {
     if ((st = integrateBatch(h, frames + i, std::min(kMaxBatch, n_frames - i), allocate_blocks)) != KB_OK) return st;
   }

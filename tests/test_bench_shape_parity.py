@@ -88,3 +88,33 @@ def test_totals64_do_not_wrap(product_lib):
         assert getattr(t64, k) == sum(s[k] for s in stats), k
         assert getattr(t64, k) & 0xFFFFFFFF == getattr(t32, k) & 0xFFFFFFFF, k
     assert t64.frames == 12 and t64.total_blocks == t32.total_blocks
+
+
+@pytest.mark.gpu
+def test_caller_stream_order_is_honoured_by_pipelined_batches(oracle_lib, product_lib):
+    """kb_set_stream contract: work enqueued on the caller's stream before kb_integrate_frames precedes the call — also for
+    the prologue of pipelined batches, which runs on an internal stream. The frames are produced on the stream by copies that
+    sit behind a long sleep kernel; nothing is synchronised before the call."""
+    import torch
+    cam = hs.small_camera(4)
+    scene = syn.hall_scene(size=(20.0, 16.0, 6.0))
+    poses, stamps = syn.sweep_trajectory(40, size=(20.0, 16.0), margin=4.0, lanes=2, yaw_turns=1.5)
+    frames = hs.render_frames(scene, cam, poses, stamps)
+    o = hs.make_handle(oracle_lib, "ko_", cam=cam)
+    hs.run_fusion(o, frames, poses, stamps)
+    g = hs.make_handle(product_lib, "kb_", cam=cam)
+    s = torch.cuda.Stream()
+    g.set_stream(s.cuda_stream)
+    hd = torch.from_numpy(np.stack([f[0] for f in frames])).pin_memory()
+    hl = torch.from_numpy(np.stack([f[1] for f in frames])).pin_memory()
+    dd = torch.full(hd.shape, 0.5, dtype=torch.float32, device="cuda")   # garbage until the copies land
+    dl = torch.zeros(hl.shape, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    with torch.cuda.stream(s):
+        torch.cuda._sleep(400_000_000)  # ~0.2 s: the call below returns long before the copies have run
+        dd.copy_(hd, non_blocking=True)
+        dl.copy_(hl, non_blocking=True)
+    fr = [g.make_frame(dd[i].data_ptr(), poses[i], stamps[i], label=dl[i].data_ptr(), memory=capi.MEM_DEVICE) for i in range(len(frames))]
+    g.integrate_frames(fr, want_stats=False)   # 40 frames: a pipelined 32-frame batch and a pipelined 8-frame batch
+    g.synchronize()
+    hs.assert_blocks_equal(o.export_blocks(), g.export_blocks(), exact_float=True, what="caller stream order")
