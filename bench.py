@@ -74,14 +74,20 @@ def parse_args():
                     help="N > 1: 'cells' = spatial cell sharding, stream striped over the ranks' pools, frames pulled over NVLink "
                          "only by the ranks whose cells they touch (khronos_b200/replay.py); 'hash' = round-1 design: per-block hash "
                          "sharding, every frame broadcast to every rank from rank 0")
-    ap.add_argument("--cell-blocks", type=int, default=16, help="--shard cells: cell side in blocks (16 = 12.8 m at 5 cm voxels)")
+    ap.add_argument("--cell-blocks", type=int, default=0,
+                    help="--shard cells: cell side in blocks (16 = 12.8 m at 5 cm voxels); 0 (default) = pick among 12/16/20/24 the layout "
+                         "with the fewest frames on the busiest rank for this trajectory (pose arithmetic only, kb_frame_owners)")
     ap.add_argument("--stripe", type=int, default=32, help="--shard cells: consecutive frames per rank in the striped pools")
     ap.add_argument("--gather", default="ce", choices=["ce", "sm", "bulk"],
                     help="--shard cells: transport of the NVLink pulls: copy engines, SM load/store kernel, cp.async.bulk kernel")
     ap.add_argument("--gather-ctas", type=int, default=32)
-    ap.add_argument("--ingest", default="striped", choices=["striped", "rank0"],
-                    help="--shard cells: where the stream is resident: striped over all ranks' pools (default) or all on rank 0 "
-                         "(A/B: rank 0's NVLink egress then bounds the exchange)")
+    ap.add_argument("--ingest", default="routed", choices=["routed", "striped", "rank0"],
+                    help="--shard cells: where the stream is resident. routed (default): the host, which knows the poses, hands every "
+                         "32-frame chunk to a rank whose cells it touches (one delivery per frame is local); striped: chunks dealt round "
+                         "robin; rank0: everything on rank 0 (its NVLink egress then bounds the exchange)")
+    ap.add_argument("--fuse-ctas-per-sm", type=int, default=0,
+                    help="N > 1: resident fusion CTAs per SM (KB_FUSE_CTAS_PER_SM; 0 = library default = full occupancy). Fewer CTAs leave "
+                         "registers for the next batch's block selection / culling kernels to run beside the fusion kernel")
     ap.add_argument("--small", action="store_true", help="tiny configuration for functional checks")
     ap.add_argument("--workload", default="hall640", choices=["hall640", "hall1280", "dynamic"],
                     help="hall640 = BASELINE config[1] (fusion only, the headline, used for every --gpus N); hall1280 = "
@@ -569,11 +575,38 @@ def main_hall_cells(args, world, rank, local_rank, dev):
     lap, H, W = len(poses), cam.height, cam.width
     P = H * W
     bpp = BYTES_PER_PIXEL_IN
-    stripe = args.stripe if args.ingest == "striped" else lap * 2  # rank0 ingest = one stripe holding the whole lap
-    sched = StripedSchedule(world, rank, stripe)
+    if args.fuse_ctas_per_sm > 0:
+        os.environ["KB_FUSE_CTAS_PER_SM"] = str(args.fuse_ctas_per_sm)  # read by kb_create
+    mc, ic = map_configs(args)
+    h = kb.create_map(mc, ic, capi.default_tracking_config(), None, device=local_rank)
+    h.set_camera(cam)
+    if args.no_cull:
+        h.set_culling(False)
+    gx, gy = rank_grid(world)
+    # which ranks need which frame: pure pose arithmetic (kb_frame_owners), identical on every rank. The per-batch cost of a
+    # rank is dominated by fixed work per frame it receives (tile pyramid, block selection, the critical path of the fusion
+    # kernel), so the layout with the fewest frames on the busiest rank wins (measured: profiles/r2_multigpu_summary.txt).
+    probe_frames = [h.make_frame(None, poses[g], stamps[g]) for g in range(lap)]
+    cell_choice = {}
+    for cb in ([args.cell_blocks] if args.cell_blocks > 0 else [12, 16, 20, 24]):
+        h.set_shard_cells(rank, world, cb, gx, gy)
+        m_ = h.frame_owners(probe_frames)
+        cell_choice[cb] = (max(int(((m_ >> r) & 1).sum()) for r in range(world)), m_)
+    args.cell_blocks = min(cell_choice, key=lambda cb: (cell_choice[cb][0], -cb))
+    masks = cell_choice[args.cell_blocks][1]
+    h.set_shard_cells(rank, world, args.cell_blocks, gx, gy)
+    stripe = args.stripe
+    if args.ingest == "rank0":
+        homes = np.zeros(lap, np.int32)
+    elif args.ingest == "routed":
+        from khronos_b200.replay import route_homes
+        homes = route_homes(masks, world, stripe)
+    else:
+        homes = None
+    sched = StripedSchedule(world, rank, stripe, homes=homes)
     res = sched.resident(lap)
 
-    # ---- this rank's stripe of the stream, rendered straight into its (IPC-shareable) pool
+    # ---- this rank's part of the stream, rendered straight into its (IPC-shareable) pool
     t_render = time.perf_counter()
     note = None
     try:
@@ -599,16 +632,10 @@ def main_hall_cells(args, world, rank, local_rank, dev):
     flag = torch.tensor([1 if note else 0], device=dev)
     dist.all_reduce(flag)
     if int(flag.item()):
+        h.close()
         return note or "peer memory unavailable on another rank"
     t_render = time.perf_counter() - t_render
 
-    mc, ic = map_configs(args)
-    h = kb.create_map(mc, ic, capi.default_tracking_config(), None, device=local_rank)
-    h.set_camera(cam)
-    if args.no_cull:
-        h.set_culling(False)
-    gx, gy = rank_grid(world)
-    h.set_shard_cells(rank, world, args.cell_blocks, gx, gy)
     stream = torch.cuda.Stream(device=dev)
     xstream = torch.cuda.Stream(device=dev)
     h.set_stream(stream.cuda_stream)
@@ -620,8 +647,7 @@ def main_hall_cells(args, world, rank, local_rank, dev):
     def stamp_of(step, j):
         return 1_000_000_000 + (step * F + j) * 33_333_333
 
-    # ---- schedule: which frames this rank needs (pure pose arithmetic), pulls, frame descriptors — all outside the timed region
-    masks = h.frame_owners([h.make_frame(None, poses[g], stamps[g]) for g in range(lap)])
+    # ---- schedule: pulls and frame descriptors — all outside the timed region
     plans = {s: sched.plan([frame_index(s, j) for j in range(F)], masks) for s in range(Wm + K)}
     cap = max(1, max(p.n_remote for p in plans.values()))
     rx = [PeerPools(lib, local_rank, cap, H, W) for _ in range(2)]
@@ -781,8 +807,9 @@ def main_hall_cells(args, world, rank, local_rank, dev):
                        "parallelism": "cell shard x%d (cells of %d x %d blocks = %.1f m, %d x %d rank tiling); stream resident %s; every rank pulls the "
                                       "frames that touch its cells over NVLink (CUDA IPC peer mappings, transport: %s) and fuses them in stream order; "
                                       "no collective in the data path" % (world, args.cell_blocks, args.cell_blocks, args.cell_blocks * mc.voxel_size * 16,
-                                                                       gx, gy, ("striped over the ranks' pools (%d-frame stripes)" % stripe) if args.ingest == "striped"
-                                                                       else "on rank 0", args.gather),
+                                                                       gx, gy, {"striped": "striped over the ranks' pools (%d-frame chunks, round robin)" % stripe,
+                                                                                "routed": "in the ranks' pools, every %d-frame chunk on a rank whose cells it touches (pose-aware ingest)" % stripe,
+                                                                                "rank0": "on rank 0"}[args.ingest], args.gather),
                        "render_s": round(t_render, 1)},
             "per_frame": {"voxels_updated": float(A[:, 0].sum()) / n_frames, "voxels_semantic": float(A[:, 1].sum()) / n_frames,
                           "blocks_visited": float(A[:, 2].sum()) / n_frames, "frame_deliveries": float(A[:, 3].sum()) / n_frames},

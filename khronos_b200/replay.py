@@ -39,14 +39,48 @@ class StepPlan:
     n_remote: int
 
 
+def route_homes(owner_mask: np.ndarray, world: int, stripe: int = 32) -> np.ndarray:
+    """Pose-aware placement of the stream: the ingest host knows the poses, so it can hand every chunk of `stripe`
+    consecutive frames to a rank that will integrate it (the rank most of the chunk's frames touch; ties go to the rank
+    holding the fewest frames so far) instead of dealing chunks round robin. One delivery per frame is then local and only
+    the frames' OTHER owners pull it over NVLink. Deterministic: every rank computes the same table from the same masks."""
+    n = len(owner_mask)
+    homes = np.zeros(n, np.int32)
+    held = np.zeros(world, np.int64)
+    for c0 in range(0, n, stripe):
+        chunk = owner_mask[c0:c0 + stripe]
+        votes = np.array([int(((chunk >> r) & 1).sum()) for r in range(world)])
+        best = votes.max()
+        cand = [r for r in range(world) if votes[r] == best]
+        r = min(cand, key=lambda q: (held[q], q))
+        homes[c0:c0 + stripe] = r
+        held[r] += len(chunk)
+    return homes
+
+
 class StripedSchedule:
-    def __init__(self, world: int, rank: int, stripe: int = 32):
+    """Where the frames of a lap live (`homes[g]`, default: chunks of `stripe` frames dealt round robin) and what each rank
+    pulls per step."""
+
+    def __init__(self, world: int, rank: int, stripe: int = 32, homes: np.ndarray = None):
         self.world, self.rank, self.stripe = int(world), int(rank), int(stripe)
+        self.homes = None if homes is None else np.asarray(homes, np.int32)
+        self._local = None
+        if self.homes is not None:  # local index = position among the frames of the same home, ascending frame number
+            self._local = np.zeros(len(self.homes), np.int64)
+            cnt = np.zeros(self.world, np.int64)
+            for g, r in enumerate(self.homes):
+                self._local[g] = cnt[r]
+                cnt[r] += 1
 
     def home(self, g: int) -> int:
+        if self.homes is not None:
+            return int(self.homes[g])
         return (g // self.stripe) % self.world
 
     def local_index(self, g: int) -> int:
+        if self._local is not None:
+            return int(self._local[g])
         return (g // (self.stripe * self.world)) * self.stripe + g % self.stripe
 
     def resident(self, lap: int) -> List[int]:

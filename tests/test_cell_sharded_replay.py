@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from khronos_b200 import capi, synthetic as syn
-from khronos_b200.replay import PeerPools, StripedSchedule, rank_grid
+from khronos_b200.replay import PeerPools, StripedSchedule, rank_grid, route_homes
 import harness as hs
 
 M64 = (1 << 64) - 1
@@ -64,6 +64,40 @@ def test_schedule_moves_the_right_frames():
             row = rx[slot] if slot >= 0 else pools[r][-slot - 1]
             assert row[0] == g * 10 and step[j] == g
         assert plan.n_remote == sum(1 for g in want if s.home(g) != r)
+
+
+def test_routed_homes_schedule():
+    """Pose-aware placement: chunks go to a rank that needs them; the schedule still delivers every needed frame."""
+    world, stripe, lap, P = 4, 4, 61, 3
+    rng = np.random.default_rng(2)
+    owner_mask = rng.integers(1, 1 << world, size=lap).astype(np.uint32)
+    homes = route_homes(owner_mask, world, stripe)
+    for c0 in range(0, lap, stripe):
+        assert len(set(homes[c0:c0 + stripe].tolist())) == 1
+        r = int(homes[c0])
+        votes = [int(((owner_mask[c0:c0 + stripe] >> q) & 1).sum()) for q in range(world)]
+        assert votes[r] == max(votes)
+    scheds = [StripedSchedule(world, r, stripe, homes=homes) for r in range(world)]
+    pools = []
+    for s in scheds:
+        res = s.resident(lap)
+        assert [s.local_index(g) for g in res] == list(range(len(res)))
+        pools.append(np.array([[g * 10 + k for k in range(P)] for g in res]).reshape(-1, P))
+    assert sorted(g for s in scheds for g in s.resident(lap)) == list(range(lap))
+    step = list(range(lap))
+    local = remote = 0
+    for r, s in enumerate(scheds):
+        plan = s.plan(step, owner_mask)
+        rx = np.full((max(plan.n_remote, 1), P), -1)
+        for (src, li, slot, cnt) in plan.ranges:
+            rx[slot:slot + cnt] = pools[src][li:li + cnt]
+        for j, g, slot in plan.mine:
+            row = rx[slot] if slot >= 0 else pools[r][-slot - 1]
+            assert row[0] == g * 10
+            local += slot < 0
+            remote += slot >= 0
+    rr = [StripedSchedule(world, r, stripe).plan(step, owner_mask).n_remote for r in range(world)]
+    assert remote < sum(rr), "routing must pull fewer frames than round-robin stripes"
 
 
 @pytest.mark.parametrize("world,cell", [(2, 10), (4, 8), (8, 5)])
