@@ -77,6 +77,10 @@ def parse_args():
     ap.add_argument("--cell-blocks", type=int, default=0,
                     help="--shard cells: cell side in blocks (16 = 12.8 m at 5 cm voxels); 0 (default) = pick among 12/16/20/24 the layout "
                          "with the fewest frames on the busiest rank for this trajectory (pose arithmetic only, kb_frame_owners)")
+    ap.add_argument("--layout", default="auto", choices=["auto", "tiling", "bisect"],
+                    help="--shard cells: 'tiling' = periodic tiling of square cells (--cell-blocks); 'bisect' = trajectory-aware table of "
+                         "contiguous regions (replay.bisect_layout over kb_frame_cells, kb_set_shard_table); 'auto' (default) = whichever "
+                         "puts the fewest frames on the busiest rank")
     ap.add_argument("--stripe", type=int, default=32, help="--shard cells: consecutive frames per rank in the striped pools")
     ap.add_argument("--gather", default="ce", choices=["ce", "sm", "bulk"],
                     help="--shard cells: transport of the NVLink pulls: copy engines, SM load/store kernel, cp.async.bulk kernel")
@@ -587,14 +591,39 @@ def main_hall_cells(args, world, rank, local_rank, dev):
     # rank is dominated by fixed work per frame it receives (tile pyramid, block selection, the critical path of the fusion
     # kernel), so the layout with the fewest frames on the busiest rank wins (measured: profiles/r2_multigpu_summary.txt).
     probe_frames = [h.make_frame(None, poses[g], stamps[g]) for g in range(lap)]
-    cell_choice = {}
-    for cb in ([args.cell_blocks] if args.cell_blocks > 0 else [12, 16, 20, 24]):
-        h.set_shard_cells(rank, world, cb, gx, gy)
+    frames_of = lambda m_: [int(((m_ >> r) & 1).sum()) for r in range(world)]
+    layouts = {}
+    if args.layout in ("auto", "tiling"):
+        for cb in ([args.cell_blocks] if args.cell_blocks > 0 else [12, 16, 20, 24]):
+            h.set_shard_cells(rank, world, cb, gx, gy)
+            m_ = h.frame_owners(probe_frames)
+            layouts[("tiling", cb)] = (max(frames_of(m_)), m_, None)
+    if args.layout in ("auto", "bisect"):
+        from khronos_b200.replay import bisect_layout
+        tcell = 4  # table granularity: 4 x 4 blocks (3.2 m at 5 cm voxels); regions are contiguous rectangles of such cells
+        bsz = mc.voxel_size * 16 * tcell
+        reach = cam.max_range + 2 * mc.voxel_size * 16
+        px = np.array([np.asarray(T, np.float64).reshape(4, 4)[0, 3] for T in poses])
+        py = np.array([np.asarray(T, np.float64).reshape(4, 4)[1, 3] for T in poses])
+        tox, toy = int(np.floor((px.min() - reach) / bsz)), int(np.floor((py.min() - reach) / bsz))
+        tw, th = int(np.floor((px.max() + reach) / bsz)) - tox + 1, int(np.floor((py.max() + reach) / bsz)) - toy + 1
+        touched = h.frame_cells(probe_frames, tcell, (tox, toy), tw, th)
+        table = bisect_layout(touched, world)
+        h.set_shard_table(rank, world, tcell, (tox, toy), table)
         m_ = h.frame_owners(probe_frames)
-        cell_choice[cb] = (max(int(((m_ >> r) & 1).sum()) for r in range(world)), m_)
-    args.cell_blocks = min(cell_choice, key=lambda cb: (cell_choice[cb][0], -cb))
-    masks = cell_choice[args.cell_blocks][1]
-    h.set_shard_cells(rank, world, args.cell_blocks, gx, gy)
+        layouts[("bisect", tcell)] = (max(frames_of(m_)), m_, ((tox, toy), table))
+    choice = min(layouts, key=lambda k: (layouts[k][0], k[0] != "bisect", -k[1]))
+    masks = layouts[choice][1]
+    if choice[0] == "bisect":
+        h.set_shard_table(rank, world, choice[1], layouts[choice][2][0], layouts[choice][2][1])
+        layout_desc = ("trajectory-aware table of %d contiguous regions (recursive bisection of %d x %d cells of %d x %d blocks = %.1f m by "
+                       "frames-per-region, kb_set_shard_table)" % (world, layouts[choice][2][1].shape[1], layouts[choice][2][1].shape[0],
+                                                                    choice[1], choice[1], choice[1] * mc.voxel_size * 16))
+    else:
+        h.set_shard_cells(rank, world, choice[1], gx, gy)
+        layout_desc = "cells of %d x %d blocks = %.1f m, %d x %d rank tiling" % (choice[1], choice[1], choice[1] * mc.voxel_size * 16, gx, gy)
+    args.cell_blocks = choice[1]
+    layout_proxy = {"%s-%d" % k: v[0] for k, v in layouts.items()}
     stripe = args.stripe
     if args.ingest == "rank0":
         homes = np.zeros(lap, np.int32)
@@ -804,13 +833,12 @@ def main_hall_cells(args, world, rank, local_rank, dev):
                        "frames_per_step": F, "frames_per_call": B, "frames_per_kernel_group": GROUP, "wire_format": "depth f32 + label i32 (8 B/px)", "lap_frames": lap,
                        "live_blocks_all_ranks": int(A[:, 7].sum()),
                        "l2": "inputs larger than L2: each step streams %.1f GB of frames" % (F * P * bpp / 1e9),
-                       "parallelism": "cell shard x%d (cells of %d x %d blocks = %.1f m, %d x %d rank tiling); stream resident %s; every rank pulls the "
+                       "parallelism": "cell shard x%d (%s); stream resident %s; every rank pulls the "
                                       "frames that touch its cells over NVLink (CUDA IPC peer mappings, transport: %s) and fuses them in stream order; "
-                                      "no collective in the data path" % (world, args.cell_blocks, args.cell_blocks, args.cell_blocks * mc.voxel_size * 16,
-                                                                       gx, gy, {"striped": "striped over the ranks' pools (%d-frame chunks, round robin)" % stripe,
+                                      "no collective in the data path" % (world, layout_desc, {"striped": "striped over the ranks' pools (%d-frame chunks, round robin)" % stripe,
                                                                                 "routed": "in the ranks' pools, every %d-frame chunk on a rank whose cells it touches (pose-aware ingest)" % stripe,
                                                                                 "rank0": "on rank 0"}[args.ingest], args.gather),
-                       "render_s": round(t_render, 1)},
+                       "layout_max_frames_per_rank": layout_proxy, "render_s": round(t_render, 1)},
             "per_frame": {"voxels_updated": float(A[:, 0].sum()) / n_frames, "voxels_semantic": float(A[:, 1].sum()) / n_frames,
                           "blocks_visited": float(A[:, 2].sum()) / n_frames, "frame_deliveries": float(A[:, 3].sum()) / n_frames},
             "shards": {"frames_per_rank": [int(x) for x in A[:, 3]], "remote_frames_per_rank": [int(x) for x in A[:, 4]],

@@ -184,6 +184,16 @@ int kb_block_owner(int32_t bx, int32_t by, int32_t bz, int nranks);
  * box allocation, the tracking / motion exchanges) uses the layout set last. grid_x * grid_y should be a multiple of
  * nranks (e.g. 4 x 2 for 8 ranks). */
 int kb_set_shard_cells(kb_handle* h, int rank, int nranks, int cell_blocks, int grid_x, int grid_y);
+/* The same cell sharding with an explicit cell -> rank table instead of the periodic tiling: owners[cy * width + cx] is the
+ * rank of cell (origin_cx + cx, origin_cy + cy) (cell index = floor(block index / cell_blocks)); cells outside the table
+ * fall back to the tiling. Lets a replay scheduler fit the layout to the trajectory (khronos_b200/replay.py::bisect_layout:
+ * contiguous regions with equal numbers of frames touching each). */
+int kb_set_shard_table(kb_handle* h, int rank, int nranks, int cell_blocks, int32_t origin_cx, int32_t origin_cy,
+                       int32_t width, int32_t height, const uint8_t* owners);
+/* touched[i * width * height + cy * width + cx] = 1 iff some block that K0 would select for frames[i] lies in cell
+ * (origin_cx + cx, origin_cy + cy): the per-cell counterpart of kb_frame_owners (host arithmetic on the poses only). */
+int kb_frame_cells(kb_handle* h, const kb_frame* frames, int32_t n_frames, int cell_blocks, int32_t origin_cx,
+                   int32_t origin_cy, int32_t width, int32_t height, uint8_t* touched);
 /* Owner of a block under the cell layout (pure function; usable without a device). */
 int kb_cell_owner(int32_t bx, int32_t by, int cell_blocks, int grid_x, int grid_y, int nranks);
 /* Which ranks need a frame: bit r of owner_mask[i] is set iff some block that hydra's findBlocksInViewFrustum would select

@@ -260,6 +260,19 @@ class MapHandle:
     def set_shard_cells(self, rank: int, nranks: int, cell_blocks: int, grid_x: int, grid_y: int):
         self._check(self._fn("set_shard_cells")(self._h, rank, nranks, cell_blocks, grid_x, grid_y))
 
+    def set_shard_table(self, rank: int, nranks: int, cell_blocks: int, origin, table: np.ndarray):
+        """kb_set_shard_table: table[cy, cx] (uint8, shape (height, width)) = rank of cell (origin[0] + cx, origin[1] + cy)."""
+        t = np.ascontiguousarray(table, np.uint8)
+        self._check(self._fn("set_shard_table")(self._h, rank, nranks, cell_blocks, int(origin[0]), int(origin[1]), int(t.shape[1]), int(t.shape[0]),
+                                                C.c_void_p(t.ctypes.data)))
+
+    def frame_cells(self, frames, cell_blocks: int, origin, width: int, height: int) -> np.ndarray:
+        """kb_frame_cells: (n_frames, height, width) uint8, 1 where the frame's frustum selection touches the cell."""
+        arr = frames if isinstance(frames, C.Array) else (Frame * len(frames))(*frames)
+        out = np.zeros((len(arr), height, width), np.uint8)
+        self._check(self._fn("frame_cells")(self._h, arr, len(arr), cell_blocks, int(origin[0]), int(origin[1]), width, height, C.c_void_p(out.ctypes.data)))
+        return out
+
     def frame_owners(self, frames) -> np.ndarray:
         """Bit mask of the ranks that need each frame (kb_frame_owners)."""
         arr = frames if isinstance(frames, C.Array) else (Frame * len(frames))(*frames)

@@ -83,6 +83,7 @@ struct kb_handle {
   int narrow_threads = 8;
   uint8_t* pin_label8 = nullptr;
   size_t pin_label8_pixels = 0;
+  int fuse_coop = 0;           // KB_FUSE_COOP: two-phase CTA-cooperative fuse kernel
   int mlp_group = 0;           // KB_FUSE_MLP experiment: 0 (off), 2 or 4 frames per memory-level-parallel group
   int cull_grid = 0;
   int parity = 0;
@@ -152,6 +153,8 @@ struct kb_handle {
   TrackingParams open_pass{};   // parameters of the pass between kb_tracking_begin and kb_tracking_finish
   uint64_t open_pass_stamp = 0;
   int open_pass_state = 0;      // 0 none, 1 begun, 2 halo packed
+  std::vector<uint8_t> shard_table_host;  // kb_set_shard_table: host copy (kb_frame_owners), device copy in dm.shard_table
+  uint8_t* shard_table_dev = nullptr;
   // InstanceForwarding (kb_forward_instances): per-id accumulators on the device, kept clusters + keep mask on the host
   int* inst_counts = nullptr;
   unsigned int* inst_bbox = nullptr;
@@ -556,6 +559,7 @@ int kb_create(const kb_map_config* map, const kb_integrator_config* integ, const
       KB_CUDA(h, devAlloc(&h->work_upd2, S, 0));
       KB_CUDA(h, devAlloc(&h->item_fmask2, S * h->batch.items_per_block, 0));
     }
+    if (const char* e = std::getenv("KB_FUSE_COOP")) h->fuse_coop = e[0] == '1' ? 1 : 0;
     if (const char* e = std::getenv("KB_FUSE_MLP")) h->mlp_group = e[0] == '2' ? 2 : (e[0] == '4' ? 4 : 0);
     if (h->use_item_list) {  // experiment, off by default (results are identical either way: only the item order changes)
       h->item_list_cap = static_cast<int>(std::min<size_t>(S * h->batch.items_per_block, size_t(1) << 28));
@@ -623,6 +627,7 @@ int kb_destroy(kb_handle* h) {
   }
   if (h->main_front) cudaEventDestroy(h->main_front);
   cudaFree(h->work_slots2); cudaFree(h->work_masks2); cudaFree(h->work_upd2); cudaFree(h->item_fmask2);
+  cudaFree(h->shard_table_dev);
   cudaFree(h->inst_counts); cudaFree(h->inst_bbox); cudaFree(h->inst_background); cudaFree(h->inst_keep); cudaFree(h->inst_bad);
   cudaFree(h->mesh_slots); cudaFree(h->mesh_cases); cudaFree(h->mesh_tri_count); cudaFree(h->mesh_tri_base);
   cudaFree(h->mesh_points); cudaFree(h->mesh_colors); cudaFree(h->mesh_labels);
@@ -732,6 +737,8 @@ int kb_set_shard(kb_handle* h, int rank, int nranks) {
   h->nranks = nranks;
   h->dm.shard_cell = 0;
   h->dm.shard_gx = h->dm.shard_gy = 1;
+  h->dm.shard_table = nullptr;
+  h->shard_table_host.clear();
   return KB_OK;
 }
 
@@ -744,6 +751,46 @@ int kb_set_shard_cells(kb_handle* h, int rank, int nranks, int cell_blocks, int 
   h->dm.shard_cell = cell_blocks;
   h->dm.shard_gx = cell_blocks > 0 ? grid_x : 1;
   h->dm.shard_gy = cell_blocks > 0 ? grid_y : 1;
+  h->dm.shard_table = nullptr;
+  h->shard_table_host.clear();
+  return KB_OK;
+}
+
+// Host-side owner of a block under the handle's layout (same function as the device's mapOwner, on the host copy of the table).
+static int hostOwner(const kb_handle* h, int x, int y, int z) {
+  const DeviceMap& m = h->dm;
+  if (m.shard_cell <= 0) return blockOwner(x, y, z, h->nranks);
+  if (!h->shard_table_host.empty())
+    return tableOwner(h->shard_table_host.data(), m.tab_ox, m.tab_oy, m.tab_w, m.tab_h, m.shard_cell, m.shard_gx, m.shard_gy, x, y, h->nranks);
+  return cellOwner(x, y, m.shard_cell, m.shard_gx, m.shard_gy, h->nranks);
+}
+
+int kb_set_shard_table(kb_handle* h, int rank, int nranks, int cell_blocks, int32_t origin_cx, int32_t origin_cy, int32_t width,
+                       int32_t height, const uint8_t* owners) {
+  if (h) h->main_dirty = true;
+  if (!h || nranks < 1 || nranks > 255 || rank < 0 || rank >= nranks || cell_blocks < 1 || width < 1 || height < 1 || !owners ||
+      static_cast<long long>(width) * height > (1 << 24))
+    return fail(h, KB_ERR_INVALID, "invalid cell table");
+  KB_CUDA(h, cudaSetDevice(h->device));
+  const size_t n = static_cast<size_t>(width) * height;
+  for (size_t i = 0; i < n; ++i)
+    if (owners[i] >= nranks) return fail(h, KB_ERR_INVALID, "cell table entry >= nranks");
+  KB_CUDA(h, cudaStreamSynchronize(h->stream));
+  cudaFree(h->shard_table_dev);
+  h->shard_table_dev = nullptr;
+  KB_CUDA(h, cudaMalloc(reinterpret_cast<void**>(&h->shard_table_dev), n));
+  KB_CUDA(h, cudaMemcpy(h->shard_table_dev, owners, n, cudaMemcpyHostToDevice));
+  h->shard_table_host.assign(owners, owners + n);
+  h->rank = rank;
+  h->nranks = nranks;
+  h->dm.shard_cell = cell_blocks;
+  // cells outside the table fall back to a periodic tiling of the ranks
+  int gy = static_cast<int>(std::floor(std::sqrt(static_cast<double>(nranks))));
+  while (nranks % gy) --gy;
+  h->dm.shard_gx = nranks / gy;
+  h->dm.shard_gy = gy;
+  h->dm.shard_table = h->shard_table_dev;
+  h->dm.tab_ox = origin_cx; h->dm.tab_oy = origin_cy; h->dm.tab_w = width; h->dm.tab_h = height;
   return KB_OK;
 }
 
@@ -778,7 +825,7 @@ int kb_frame_owners(kb_handle* h, const kb_frame* frames, int32_t n_frames, uint
     for (int bz = lo[2]; bz <= hi[2] && mask != all; ++bz)
       for (int by = lo[1]; by <= hi[1] && mask != all; ++by)
         for (int bx = lo[0]; bx <= hi[0]; ++bx) {
-          const int owner = mapOwner(h->dm, bx, by, bz, h->nranks);
+          const int owner = hostOwner(h, bx, by, bz);
           if ((mask >> owner) & 1u) continue;
           const float cx = (static_cast<float>(bx) + 0.5f) * p.block_size;
           const float cy = (static_cast<float>(by) + 0.5f) * p.block_size;
@@ -797,6 +844,58 @@ int kb_frame_owners(kb_handle* h, const kb_frame* frames, int32_t n_frames, uint
           if (mask == all) break;
         }
     owner_mask[i] = mask;
+  }
+  return KB_OK;
+}
+
+// Which cells of a cell grid a frame's candidate blocks fall into (the input of a trajectory-aware layout, kb_set_shard_table):
+// same candidate test as kb_frame_owners.
+int kb_frame_cells(kb_handle* h, const kb_frame* frames, int32_t n_frames, int cell_blocks, int32_t origin_cx, int32_t origin_cy,
+                   int32_t width, int32_t height, uint8_t* touched) {
+  if (!h || !frames || !touched || n_frames < 0 || cell_blocks < 1 || width < 1 || height < 1) return fail(h, KB_ERR_INVALID, "invalid argument");
+  if (!h->has_cam) return fail(h, KB_ERR_STATE, "kb_set_camera must be called first");
+  const BatchParams& p = h->batch;
+  const float infl = p.infl + 1e-3f;
+  const size_t cells = static_cast<size_t>(width) * height;
+  std::memset(touched, 0, cells * static_cast<size_t>(n_frames));
+  for (int i = 0; i < n_frames; ++i) {
+    float R[9], t[3], Rw[9], tw[3];
+    for (int k = 0; k < 16; ++k)
+      if (!std::isfinite(frames[i].world_T_sensor[k])) return fail(h, KB_ERR_INVALID, "non-finite sensor pose");
+    poseToFloat(frames[i].world_T_sensor, R, t, Rw, tw);
+    uint8_t* row = touched + cells * static_cast<size_t>(i);
+    const float reach = h->cam.max_range + infl;
+    const float inv = 1.f / h->block_size;
+    int lo[3], hi[3];
+    for (int a = 0; a < 3; ++a) {
+      lo[a] = static_cast<int>(std::floor((tw[a] - reach) * inv));
+      hi[a] = static_cast<int>(std::floor((tw[a] + reach) * inv));
+    }
+    for (int by = lo[1]; by <= hi[1]; ++by) {
+      const int cy = floorDiv(by, cell_blocks) - origin_cy;
+      if (cy < 0 || cy >= height) continue;
+      for (int bx = lo[0]; bx <= hi[0]; ++bx) {
+        const int cx = floorDiv(bx, cell_blocks) - origin_cx;
+        if (cx < 0 || cx >= width || row[cy * width + cx]) continue;
+        for (int bz = lo[2]; bz <= hi[2]; ++bz) {
+          const float px = (static_cast<float>(bx) + 0.5f) * p.block_size;
+          const float py = (static_cast<float>(by) + 0.5f) * p.block_size;
+          const float pz = (static_cast<float>(bz) + 0.5f) * p.block_size;
+          const float x = ((R[0] * px + R[1] * py) + R[2] * pz) + t[0];
+          const float y = ((R[3] * px + R[4] * py) + R[5] * pz) + t[1];
+          const float z = ((R[6] * px + R[7] * py) + R[8] * pz) + t[2];
+          if (z < -infl) continue;
+          const float r = std::sqrt((x * x + y * y) + z * z);
+          if (r < p.min_range - infl || r > p.max_range + infl) continue;
+          if (p.pl[0][0] * x + p.pl[0][1] * z < -infl) continue;
+          if (p.pl[1][0] * x + p.pl[1][1] * z < -infl) continue;
+          if (p.pl[2][0] * y + p.pl[2][1] * z < -infl) continue;
+          if (p.pl[3][0] * y + p.pl[3][1] * z < -infl) continue;
+          row[cy * width + cx] = 1;
+          break;
+        }
+      }
+    }
   }
   return KB_OK;
 }
@@ -865,6 +964,7 @@ static int integrateBatch(kb_handle* h, const kb_frame* frames, int n, int alloc
                     ? h->item_list + ((pipe && par) ? static_cast<size_t>(kItemClasses) * h->item_list_cap : 0) : nullptr;
   p.item_list_cap = h->item_list_cap;
   p.mlp_group = h->mlp_group;
+  p.coop = h->fuse_coop;
   if (any_color) {
     int st = ensureColorLayer(h);
     if (st == KB_OK && any_host_color) st = ensureColorStaging(h, px);

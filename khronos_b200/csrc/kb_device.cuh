@@ -57,6 +57,10 @@ struct DeviceMap {
   // square cells of shard_cell x shard_cell blocks in x/y (all z), tiled periodically over a shard_gx x shard_gy grid
   // of ranks, so spatially coherent frames touch few ranks (cellOwner).
   int shard_cell, shard_gx, shard_gy;
+  // Optional explicit cell -> rank table (kb_set_shard_table): cells (cx, cy) with cx - tab_ox in [0, tab_w) and cy - tab_oy
+  // in [0, tab_h) take their owner from the table (row-major, y outer); cells outside fall back to the periodic tiling.
+  const uint8_t* shard_table;
+  int tab_ox, tab_oy, tab_w, tab_h;
 };
 
 // Cumulative device counters (never reset on the hot path; the host reports differences).
@@ -136,9 +140,19 @@ __host__ __device__ inline int cellOwner(int x, int y, int cell, int gx, int gy,
   const int mx = ((cx % gx) + gx) % gx, my = ((cy % gy) + gy) % gy;
   return (mx + gx * my) % nranks;
 }
-// Owner rank of a block under the map's shard layout.
-__host__ __device__ inline int mapOwner(const DeviceMap& m, int x, int y, int z, int nranks) {
-  return m.shard_cell > 0 ? cellOwner(x, y, m.shard_cell, m.shard_gx, m.shard_gy, nranks) : blockOwner(x, y, z, nranks);
+__host__ __device__ inline int floorDiv(int a, int b) { return (a >= 0 ? a : a - b + 1) / b; }
+// Owner under an explicit cell table (`table` readable where this runs: device memory in kernels, a host copy on the host).
+__host__ __device__ inline int tableOwner(const uint8_t* table, int ox, int oy, int w, int h, int cell, int gx, int gy, int x, int y,
+                                          int nranks) {
+  const int cx = floorDiv(x, cell) - ox, cy = floorDiv(y, cell) - oy;
+  if (cx >= 0 && cx < w && cy >= 0 && cy < h) return table[cy * w + cx] % nranks;
+  return cellOwner(x, y, cell, gx, gy, nranks);
+}
+// Owner rank of a block under the map's shard layout (device side; the host uses kb_handle's copy of the table).
+__device__ inline int mapOwner(const DeviceMap& m, int x, int y, int z, int nranks) {
+  if (m.shard_cell <= 0) return blockOwner(x, y, z, nranks);
+  if (m.shard_table) return tableOwner(m.shard_table, m.tab_ox, m.tab_oy, m.tab_w, m.tab_h, m.shard_cell, m.shard_gx, m.shard_gy, x, y, nranks);
+  return cellOwner(x, y, m.shard_cell, m.shard_gx, m.shard_gy, nranks);
 }
 
 #ifdef __CUDACC__

@@ -777,6 +777,240 @@ __global__ void __launch_bounds__(kFuseThreads, COLOR ? KB_FUSE_COLOR_MIN_BLOCKS
   }
 }
 
+// ---- K1, CTA-cooperative two-phase variant (KB_FUSE_COOP) ----------------------------------------------------------
+// fuseKernel's unit of serial work is one warp walking up to 32 frames of its 32 voxels: ~280 instructions per frame, so
+// the dependency chain of a heavy item is about half the kernel and the SMs drain long before the last warp is done (r2
+// capture: SMs idle 26-36 % of the kernel). Only the last ~40 instructions of a frame depend on the voxel state. Here the
+// four warps of a CTA share one item: phase A — warp w computes the measurements (projection, taps, sdf, weight, label)
+// of the item's frames w, w+4, ... for all 32 voxels and parks them in shared memory; phase B — warp 0 folds them into
+// the voxel state in frame order (TSDF recurrence, likelihood row, bookkeeping). Same arithmetic in the same order per
+// voxel, so results are bit-identical; the chain per item shrinks to a quarter of the frames plus a short fold, and the
+// scheduling unit becomes the CTA (~15 items each instead of ~4 per warp).
+template <int VPS, bool COMPACT, bool PB>
+__global__ void __launch_bounds__(kFuseThreads, KB_FUSE_MIN_BLOCKS) fuseKernelCoop(const DeviceMap m, const __grid_constant__ BatchParams p) {
+  constexpr int kFetch = PB ? kCtrFetchB : kCtrFetch;
+  constexpr int kItems = PB ? kCtrItemsB0 : kCtrItems0;
+  constexpr int V = VPS * VPS * VPS;
+  constexpr int NK = 4;
+  constexpr int BOXES = (VPS / 4) * (VPS / 8) * (VPS / NK);
+  constexpr uint8_t kInvalid = 0xFE, kNoSem = 0xFF;
+  extern __shared__ float s_dyn[];
+  const int rows_floats = max(m.Lp, 2) * 32;
+  float* __restrict__ s_rows = s_dyn;                      // [Lp][32] likelihood rows of the item's 32 voxels
+  float* __restrict__ s_w = s_dyn + rows_floats;           // [32 frames][32 voxels] measurement weight
+  float* __restrict__ s_s = s_w + 32 * 32;                 // [32][32] sdf (unclamped)
+  uint8_t* __restrict__ s_l = reinterpret_cast<uint8_t*>(s_s + 32 * 32);  // [32][32] label | kNoSem | kInvalid
+  __shared__ int s_item;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int n_cls[kItemClasses];
+  int n_items = 0;
+#pragma unroll
+  for (int c = 0; c < kItemClasses; ++c) {
+    n_cls[c] = min(m.counters[kItems + c], p.item_list_cap);
+    n_items += n_cls[c];
+  }
+  n_items *= NK;
+  const bool binary = p.sem_mode == KB_SEMANTICS_BINARY;
+  const int L = p.L;
+  int n_valid = 0, n_band = 0, n_sem = 0;
+  int pending = 0;
+  if (threadIdx.x == 0) pending = atomicAdd(&m.counters[kFetch], 1);
+  for (;;) {
+    if (threadIdx.x == 0) s_item = pending;
+    __syncthreads();  // item index visible; the previous item's fold is done, its records may be overwritten
+    const int w = s_item;
+    if (w >= n_items) break;
+    if (threadIdx.x == 0) pending = atomicAdd(&m.counters[kFetch], 1);  // next item: the round trip overlaps this one
+    const int box = listedBox<PB>(p, n_cls, w / NK);
+    const uint32_t fmask = p.item_fmask[box];
+    const int wi = box / BOXES, it = box % BOXES;
+    const int slot = p.work_slots[wi];
+    const int3 bi = m.block_index[slot];
+    const int sem = L > 0 ? m.block_sem[slot] : -1;
+    int x0, y0, z0;
+    itemOrigin<VPS>(it, x0, y0, z0);
+    const int vx = x0 + (lane & 3), vy = y0 + (lane >> 2), vz = z0 + (w % NK);
+    const int lin = vx + VPS * (vy + VPS * vz);
+    const size_t gi = static_cast<size_t>(slot) * V + lin;
+    const float wx = static_cast<float>(bi.x) * p.block_size + (static_cast<float>(vx) + 0.5f) * p.voxel_size;
+    const float wy = static_cast<float>(bi.y) * p.block_size + (static_cast<float>(vy) + 0.5f) * p.voxel_size;
+    const float wz = static_cast<float>(bi.z) * p.block_size + (static_cast<float>(vz) + 0.5f) * p.voxel_size;
+    const int nf = __popc(fmask);
+    // ---- phase A: measurements of frames (rank r among the item's frames) r = warp, warp + 4, ...
+    for (int r = warp; r < nf; r += 4) {
+      const int b = __fns(fmask, 0, r + 1);
+      const FrameView& f = p.f[b];
+      const bool has_label_img = L > 0 && (binary ? f.object_image != nullptr : (COMPACT ? f.label8 != nullptr : f.label != nullptr));
+      uint8_t tag = kInvalid;
+      float sdf = 0.f, wm = 0.f;
+      float x, y, z;
+      xform(f.R, f.t, wx, wy, wz, x, y, z);
+      if (z > 0.f) {
+        const float u = p.fx * x / z + p.cx;
+        const float v = p.fy * y / z + p.cy;
+        if (!(u < 0.f || u > static_cast<float>(p.W - 1) || v < 0.f || v > static_cast<float>(p.H - 1))) {
+          float range = 0.f;
+          const Taps taps = computeTaps<COMPACT>(p, f, u, v, range);
+          if (taps.valid) {
+            sdf = range - z;
+            if (!(sdf < -p.trunc)) {
+              bool ok = true;
+              uint32_t label = 0;
+              const bool in_band = fabsf(sdf) < p.trunc;
+              if (in_band) {
+                const int ti = tapIndex(p, taps);
+                if (f.mask != nullptr && __ldg(&f.mask[ti]) != 0) ok = false;
+                if (ok && has_label_img) {
+                  if (binary) {
+                    label = __ldg(&f.object_image[ti]) == f.target_id ? 1u : 0u;
+                  } else {
+                    label = static_cast<uint32_t>(labelAt<COMPACT>(f, ti));
+                    if (label < static_cast<uint32_t>(KB_MAX_LABELS) && ((p.blocked_mask >> label) & 1ull)) ok = false;
+                  }
+                }
+              }
+              if (ok) {
+                wm = measurementWeight(p, z, sdf);
+                tag = (in_band && sem >= 0 && has_label_img && label < static_cast<uint32_t>(L)) ? static_cast<uint8_t>(label) : kNoSem;
+              }
+            }
+          }
+        }
+      }
+      s_w[r * 32 + lane] = wm;
+      s_s[r * 32 + lane] = sdf;
+      s_l[r * 32 + lane] = tag;
+    }
+    __syncthreads();  // all measurements of the item are in shared memory
+    // ---- phase B: warp 0 folds the frames into the voxel state, in frame order
+    if (warp == 0) {
+      float2 st = make_float2(0.f, 0.f);
+      uint32_t lobs = 0, vfl = 0, upd_frames = 0;
+      bool have = false, row_resident = false;
+      int best_label = 0;
+      uint32_t rem = fmask;
+      int r = 0;
+      while (rem) {
+        const int b = __ffs(rem) - 1;
+        rem &= rem - 1;
+        const uint8_t tag = s_l[r * 32 + lane];
+        const float wm = s_w[r * 32 + lane], sdf = s_s[r * 32 + lane];
+        ++r;
+        if (tag == kInvalid) continue;
+        if (!have) {
+          st = m.tsdf[gi];
+          have = true;
+          if (p.with_tracking) vfl = trackingFold(m, p.trk, m.born_frame[slot], gi);
+        }
+        const float sdf_c = fminf(fmaxf(sdf, -p.trunc), p.trunc);
+        const float2 old = st;
+        st.x = (old.x * old.y + sdf_c * wm) / (old.y + wm);
+        st.y = fminf(old.y + wm, p.max_weight);
+        lobs = p.f[b].frame_idx;
+        upd_frames |= 1u << b;
+        ++n_valid;
+        if (!(fabsf(sdf) < p.trunc)) continue;
+        ++n_band;
+        if (tag == kNoSem) continue;
+        const uint32_t label = tag;
+        const size_t si = static_cast<size_t>(sem) * V + lin;
+        if (!row_resident) {
+          row_resident = true;
+          const bool empty = m.sem_label[si] == kSemEmpty;
+          if (binary) {
+            const float2 c = empty ? make_float2(0.f, 0.f) : *reinterpret_cast<const float2*>(m.sem_lik + si * 2);
+            s_rows[lane] = c.x;
+            s_rows[32 + lane] = c.y;
+          } else {
+            const float4* __restrict__ lk = reinterpret_cast<const float4*>(m.sem_lik + si * m.Lp);
+            for (int k4 = 0; k4 < m.Lp; k4 += 4) {
+              const float4 c = empty ? make_float4(p.mle_init, p.mle_init, p.mle_init, p.mle_init) : lk[k4 >> 2];
+              s_rows[(k4 + 0) * 32 + lane] = c.x;
+              s_rows[(k4 + 1) * 32 + lane] = c.y;
+              s_rows[(k4 + 2) * 32 + lane] = c.z;
+              s_rows[(k4 + 3) * 32 + lane] = c.w;
+            }
+          }
+        }
+        if (binary) {
+          s_rows[label * 32 + lane] = s_rows[label * 32 + lane] + 1.f;
+          best_label = s_rows[32 + lane] > s_rows[lane] ? 1 : 0;
+        } else {
+          for (int k2 = 0; k2 < m.Lp; k2 += 2) {
+            float c0 = s_rows[(k2 + 0) * 32 + lane], c1 = s_rows[(k2 + 1) * 32 + lane];
+            c0 += static_cast<uint32_t>(k2 + 0) == label ? p.mle_diag : p.mle_off;
+            c1 += static_cast<uint32_t>(k2 + 1) == label ? p.mle_diag : p.mle_off;
+            s_rows[(k2 + 0) * 32 + lane] = c0;
+            s_rows[(k2 + 1) * 32 + lane] = c1;
+          }
+        }
+        ++n_sem;
+      }
+      if (have) {
+        m.tsdf[gi] = st;
+        if (p.with_tracking) {
+          m.last_obs[gi] = lobs;
+          m.vflags[gi] = static_cast<uint8_t>(vfl | (st.x < p.occ_thr ? 0 : kVoxNotOccupied));
+        }
+        if (row_resident) {
+          const size_t si = static_cast<size_t>(sem) * V + lin;
+          if (binary) {
+            *reinterpret_cast<float2*>(m.sem_lik + si * 2) = make_float2(s_rows[lane], s_rows[32 + lane]);
+          } else {
+            float4* __restrict__ lk = reinterpret_cast<float4*>(m.sem_lik + si * m.Lp);
+            for (int k4 = 0; k4 < m.Lp; k4 += 4)
+              lk[k4 >> 2] = make_float4(s_rows[(k4 + 0) * 32 + lane], s_rows[(k4 + 1) * 32 + lane], s_rows[(k4 + 2) * 32 + lane],
+                                        s_rows[(k4 + 3) * 32 + lane]);
+            float bestv = s_rows[lane];
+            best_label = 0;
+            for (int kk = 1; kk < L; ++kk) {
+              const float c = s_rows[kk * 32 + lane];
+              if (c > bestv) { bestv = c; best_label = kk; }
+            }
+          }
+          m.sem_label[si] = static_cast<uint16_t>(best_label);
+        }
+      }
+      if (__any_sync(0xffffffffu, have)) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) upd_frames |= __shfl_xor_sync(0xffffffffu, upd_frames, o);
+        if (lane == 0) {
+          const uint32_t all = KB_FLAG_UPDATED | KB_FLAG_MESH_UPDATED | KB_FLAG_ESDF_UPDATED | KB_FLAG_TRACKING_UPDATED;
+          if ((m.block_flags[slot] & all) != all) atomicOr(&m.block_flags[slot], all);
+          if ((p.work_upd[wi] & upd_frames) != upd_frames) {
+            const uint32_t prev = atomicOr(&p.work_upd[wi], upd_frames);
+            const int fresh = __popc(upd_frames & ~prev);
+            if (fresh) {
+              atomicAdd(&m.counters[kCtrBlocksUpdated], fresh);
+              atomicAdd(&totals64(m.counters)[kTotBlocksUpdated], static_cast<unsigned long long>(fresh));
+            }
+          }
+        }
+      }
+    }
+  }
+  if (warp == 0) {
+    n_valid = warpSum(n_valid);
+    if (n_valid) {
+      n_band = warpSum(n_band);
+      n_sem = warpSum(n_sem);
+      if (lane == 0) {
+        unsigned long long* t64 = totals64(m.counters);
+        atomicAdd(&m.counters[kCtrVoxelsUpdated], n_valid);
+        atomicAdd(&t64[kTotVoxelsUpdated], static_cast<unsigned long long>(n_valid));
+        if (n_band) {
+          atomicAdd(&m.counters[kCtrVoxelsBand], n_band);
+          atomicAdd(&t64[kTotVoxelsBand], static_cast<unsigned long long>(n_band));
+        }
+        if (n_sem) {
+          atomicAdd(&m.counters[kCtrVoxelsSemantic], n_sem);
+          atomicAdd(&t64[kTotVoxelsSemantic], static_cast<unsigned long long>(n_sem));
+        }
+      }
+    }
+  }
+}
+
 // ---- K1, memory-level-parallel variant (experiment, KB_FUSE_MLP=G; off by default) -------------------------------
 // fuseKernel walks an item's frames one at a time: projection -> 4 depth taps -> label/mask tap -> update, i.e. two
 // to three dependent memory round trips per frame and voxel, with ~26 resident warps per SM to hide them (ncu: issue
@@ -1802,6 +2036,18 @@ void launchFuse(const DeviceMap& m, const BatchParams& p, int grid, cudaStream_t
     if (p.mlp_group == 2) KB_FUSE_MLP_G(V, LP, C, 2);                                                                \
     else KB_FUSE_MLP_G(V, LP, C, 4);                                                                                 \
   } while (0)
+  if (p.coop && p.item_list && one && !col && p.mlp_group == 0) {  // CTA-cooperative two-phase items (long listed batches)
+    const size_t csmem = static_cast<size_t>(std::max(m.Lp, 2)) * 32 * sizeof(float) + 2 * 32 * 32 * sizeof(float) + 32 * 32;
+#define KB_COOP(V, C)                                                                   \
+  do {                                                                                  \
+    if (pb) fuseKernelCoop<V, C, true><<<grid, kFuseThreads, csmem, s>>>(m, p);         \
+    else fuseKernelCoop<V, C, false><<<grid, kFuseThreads, csmem, s>>>(m, p);           \
+  } while (0)
+    if (m.vps == 16) { if (c) KB_COOP(16, true); else KB_COOP(16, false); }
+    else { if (c) KB_COOP(8, true); else KB_COOP(8, false); }
+#undef KB_COOP
+    return;
+  }
   if (p.mlp_group != 0 && !col) {  // experiment: memory-level-parallel variant (same results)
     if (m.vps == 16) {
       if (one) { if (c) KB_FUSE_MLP(16, 1, true); else KB_FUSE_MLP(16, 1, false); }

@@ -59,6 +59,7 @@ struct BatchParams {
   int pipelined;         // KB_PIPELINE: the host resets this batch's counters itself (K0 must not touch the other batch's)
   int fetch_ctr;         // counter index of this batch's work cursor (kCtrFetch, or kCtrFetchB for odd pipelined batches)
   int items_ctr;         // first of the 3 item-list counters of this batch (kCtrItems0 / kCtrItemsB0)
+  int coop;              // KB_FUSE_COOP: CTA-cooperative two-phase fuse kernel for long listed batches (fuseKernelCoop)
   int mlp_group;         // optional (KB_FUSE_MLP = 2 | 4): frames per memory-level-parallel group of fuseKernelMlp; 0 = fuseKernel
   int* item_list;        // optional (KB_FUSE_ITEM_LIST): 3 segments of item_list_cap box indices, non-empty boxes by
   int item_list_cap;     //   descending frame count (>= 20, >= 8, the rest): no empty fetches, heavy items start first

@@ -58,6 +58,46 @@ def route_homes(owner_mask: np.ndarray, world: int, stripe: int = 32) -> np.ndar
     return homes
 
 
+def bisect_layout(touched: np.ndarray, world: int) -> np.ndarray:
+    """Trajectory-aware cell -> rank table (kb_set_shard_table). touched[f, cy, cx] != 0 iff frame f's frustum touches cell
+    (cx, cy) (kb_frame_cells). Recursive bisection of the cell rectangle: a rectangle that gets k ranks is cut, along x or
+    y, where the busier side's frames-per-rank is smallest — the load of a side is the number of frames that touch ANY of
+    its cells (a frame on the cut counts on both sides, so cuts avoid busy places) — until every rectangle has one rank.
+    Regions are contiguous, so a frustum touches few of them, and equally busy, which is what bounds a sharded replay
+    (the per-batch cost of a rank hardly depends on how many of its blocks a frame holds)."""
+    t = np.asarray(touched) != 0
+    F, H, W = t.shape
+    table = np.zeros((H, W), np.uint8)
+
+    def load(x0, x1, y0, y1):
+        return int(t[:, y0:y1, x0:x1].any(axis=(1, 2)).sum())
+
+    def split(x0, x1, y0, y1, base, k):
+        if k == 1 or (x1 - x0 <= 1 and y1 - y0 <= 1):
+            table[y0:y1, x0:x1] = base  # (more ranks than cells: the surplus ranks stay idle)
+            return
+        k1 = k // 2
+        k2 = k - k1
+        best = None
+        for axis, lo, hi in (("x", x0, x1), ("y", y0, y1)):
+            for c in range(lo + 1, hi):
+                a = load(x0, c, y0, y1) if axis == "x" else load(x0, x1, y0, c)
+                b = load(c, x1, y0, y1) if axis == "x" else load(x0, x1, c, y1)
+                cost = max(a / k1, b / k2)
+                if best is None or cost < best[0]:
+                    best = (cost, axis, c)
+        _, axis, c = best
+        if axis == "x":
+            split(x0, c, y0, y1, base, k1)
+            split(c, x1, y0, y1, base + k1, k2)
+        else:
+            split(x0, x1, y0, c, base, k1)
+            split(x0, x1, c, y1, base + k1, k2)
+
+    split(0, W, 0, H, 0, int(world))
+    return table
+
+
 class StripedSchedule:
     """Where the frames of a lap live (`homes[g]`, default: chunks of `stripe` frames dealt round robin) and what each rank
     pulls per step."""

@@ -270,6 +270,49 @@ static inline void transform(const float R[9], const float t[3], const float p[3
   out[2] = ((R[6] * p[0] + R[7] * p[1]) + R[8] * p[2]) + t[2];
 }
 
+int Oracle::owner(const Idx3& b) const {
+  if (cell_ <= 0) return blockOwner(b, nranks_);
+  if (!table_.empty()) {
+    auto fdiv = [](int a, int c) { return (a >= 0 ? a : a - c + 1) / c; };
+    const int cx = fdiv(b.x, cell_) - tab_ox_, cy = fdiv(b.y, cell_) - tab_oy_;
+    if (cx >= 0 && cx < tab_w_ && cy >= 0 && cy < tab_h_) return table_[static_cast<size_t>(cy) * tab_w_ + cx] % nranks_;
+  }
+  return cellOwner(b.x, b.y, cell_, gx_, gy_, nranks_);
+}
+
+void Oracle::setShardTable(int rank, int nranks, int cell, int ox, int oy, int w, int h, const uint8_t* owners) {
+  rank_ = rank; nranks_ = nranks; cell_ = cell;
+  int gy = 1;
+  for (int g = 1; g * g <= nranks; ++g) if (nranks % g == 0) gy = g;  // same fallback tiling as the product
+  gy_ = gy; gx_ = nranks / gy;
+  table_.assign(owners, owners + static_cast<size_t>(w) * h);
+  tab_ox_ = ox; tab_oy_ = oy; tab_w_ = w; tab_h_ = h;
+}
+
+void Oracle::frameCells(const kb_frame& f, int cell, int ox, int oy, int w, int h, uint8_t* touched) const {
+  float R[9], t[3], Rw[9], tw[3];
+  invertPose(f.world_T_sensor, R, t, Rw, tw);
+  const float infl = block_size_ * 0.8660254f;
+  const float reach = cam_.max_range + infl;
+  int lo[3], hi[3];
+  for (int a = 0; a < 3; ++a) {
+    lo[a] = static_cast<int>(std::floor((tw[a] - reach) * block_size_inv_));
+    hi[a] = static_cast<int>(std::floor((tw[a] + reach) * block_size_inv_));
+  }
+  auto fdiv = [](int a, int c) { return (a >= 0 ? a : a - c + 1) / c; };
+  for (int bz = lo[2]; bz <= hi[2]; ++bz)
+    for (int by = lo[1]; by <= hi[1]; ++by)
+      for (int bx = lo[0]; bx <= hi[0]; ++bx) {
+        const int cx = fdiv(bx, cell) - ox, cy = fdiv(by, cell) - oy;
+        if (cx < 0 || cx >= w || cy < 0 || cy >= h || touched[static_cast<size_t>(cy) * w + cx]) continue;
+        const float c[3] = {(static_cast<float>(bx) + 0.5f) * block_size_, (static_cast<float>(by) + 0.5f) * block_size_,
+                            (static_cast<float>(bz) + 0.5f) * block_size_};
+        float cC[3];
+        transform(R, t, c, cC);
+        if (pointInFrustum(cC, infl)) touched[static_cast<size_t>(cy) * w + cx] = 1;
+      }
+}
+
 // kb_frame_owners on the oracle: the exact frustum selection of integrateFrame (no safety inflation), reduced to the set
 // of owner ranks. The product's mask must be a superset.
 uint32_t Oracle::frameOwners(const kb_frame& f) const {

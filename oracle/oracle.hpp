@@ -134,11 +134,15 @@ class Oracle {
   // ---- block-hash sharded protocol (our multi-GPU design, not in the reference). The oracle
   // implements it on host buffers with the layouts of csrc/kb_kernels.cuh::ShardExchange so that world-size-2
   // gloo tests can prove "union of the shards == the unsharded map" on CPU.
-  void setShard(int rank, int nranks) { rank_ = rank; nranks_ = nranks; cell_ = 0; }
+  void setShard(int rank, int nranks) { rank_ = rank; nranks_ = nranks; cell_ = 0; table_.clear(); }
   // kb_set_shard_cells: periodic tiling of cell x cell block cells (x/y) over a gx x gy grid of ranks.
-  void setShardCells(int rank, int nranks, int cell, int gx, int gy) { rank_ = rank; nranks_ = nranks; cell_ = cell; gx_ = gx; gy_ = gy; }
+  void setShardCells(int rank, int nranks, int cell, int gx, int gy) { rank_ = rank; nranks_ = nranks; cell_ = cell; gx_ = gx; gy_ = gy; table_.clear(); }
   static int cellOwner(int bx, int by, int cell, int gx, int gy, int nranks);
-  int owner(const Idx3& b) const { return cell_ > 0 ? cellOwner(b.x, b.y, cell_, gx_, gy_, nranks_) : blockOwner(b, nranks_); }
+  // kb_set_shard_table: explicit cell -> rank table over [ox, ox + w) x [oy, oy + h) cells, periodic tiling outside.
+  void setShardTable(int rank, int nranks, int cell, int ox, int oy, int w, int h, const uint8_t* owners);
+  // kb_frame_cells: cells touched by the frame's frustum selection.
+  void frameCells(const kb_frame& f, int cell, int ox, int oy, int w, int h, uint8_t* touched) const;
+  int owner(const Idx3& b) const;
   // kb_frame_owners: ranks owning at least one block the frame's frustum test selects.
   uint32_t frameOwners(const kb_frame& f) const;
   int rank() const { return rank_; }
@@ -216,6 +220,8 @@ class Oracle {
   std::vector<uint8_t> flags_scratch_;
   int rank_ = 0, nranks_ = 1;
   int cell_ = 0, gx_ = 1, gy_ = 1;
+  std::vector<uint8_t> table_;
+  int tab_ox_ = 0, tab_oy_ = 0, tab_w_ = 0, tab_h_ = 0;
   std::vector<ObjectCluster> object_clusters_;
   TrackMeasurements track_result_;
   std::vector<MeshBlock> mesh_;

@@ -343,6 +343,22 @@ int ko_set_shard_cells(ko_handle* h, int rank, int nranks, int cell_blocks, int 
   if (cell_blocks == 0) h->o->setShard(rank, nranks); else h->o->setShardCells(rank, nranks, cell_blocks, grid_x, grid_y);
   return KB_OK;
 }
+int ko_set_shard_table(ko_handle* h, int rank, int nranks, int cell_blocks, int32_t origin_cx, int32_t origin_cy, int32_t width,
+                       int32_t height, const uint8_t* owners) {
+  if (!h || nranks < 1 || nranks > 255 || rank < 0 || rank >= nranks || cell_blocks < 1 || width < 1 || height < 1 || !owners) return KB_ERR_INVALID;
+  for (size_t i = 0; i < static_cast<size_t>(width) * height; ++i)
+    if (owners[i] >= nranks) return KB_ERR_INVALID;
+  h->o->setShardTable(rank, nranks, cell_blocks, origin_cx, origin_cy, width, height, owners);
+  return KB_OK;
+}
+int ko_frame_cells(ko_handle* h, const kb_frame* frames, int32_t n, int cell_blocks, int32_t origin_cx, int32_t origin_cy, int32_t width,
+                   int32_t height, uint8_t* touched) {
+  if (!h || !frames || !touched || n < 0 || cell_blocks < 1 || width < 1 || height < 1) return KB_ERR_INVALID;
+  const size_t cells = static_cast<size_t>(width) * height;
+  std::memset(touched, 0, cells * static_cast<size_t>(n));
+  for (int i = 0; i < n; ++i) h->o->frameCells(frames[i], cell_blocks, origin_cx, origin_cy, width, height, touched + cells * i);
+  return KB_OK;
+}
 int ko_cell_owner(int32_t bx, int32_t by, int cell_blocks, int grid_x, int grid_y, int nranks) {
   return Oracle::cellOwner(bx, by, cell_blocks, grid_x, grid_y, nranks);
 }

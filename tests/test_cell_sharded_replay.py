@@ -213,3 +213,94 @@ def test_product_virtual_ranks_pull_and_fuse(oracle_lib, product_lib, mode):
             np.testing.assert_array_equal(p.last_observed[k], bo.last_observed[i])
     for p in pools:
         p.close()
+
+
+def _cell_grid(h, frames, cell):
+    """Bounding cell rectangle of a stream (generous) and the per-frame touched cells."""
+    ox, oy, w, hgt = -4, -4, 16, 14
+    return (ox, oy), h.frame_cells(frames, cell, (ox, oy), w, hgt)
+
+
+def test_bisect_layout_properties():
+    from khronos_b200.replay import bisect_layout
+    rng = np.random.default_rng(5)
+    F, H, W = 400, 9, 12
+    t = np.zeros((F, H, W), np.uint8)
+    for f in range(F):  # a 2 x 2 footprint walking along a serpentine
+        cx = int(f * (W - 2) / F) if (f // 100) % 2 == 0 else int((F - f) * (W - 2) / F)
+        cy = min(H - 2, 2 * (f // 100))
+        t[f, cy:cy + 2, cx:cx + 2] = 1
+    for world in (2, 4, 8):
+        tab = bisect_layout(t, world)
+        assert tab.shape == (H, W) and set(np.unique(tab)) <= set(range(world))
+        loads = [int(((t != 0) & (tab[None] == r)).any(axis=(1, 2)).sum()) for r in range(world)]
+        assert min(loads) > 0, loads
+        assert max(loads) <= 2.2 * (sum(loads) / world), loads
+        for r in range(world):  # every region is a rectangle
+            ys, xs = np.nonzero(tab == r)
+            assert (tab[ys.min():ys.max() + 1, xs.min():xs.max() + 1] == r).all()
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_oracle_table_shards_equal_unsharded(oracle_lib, world):
+    """kb_set_shard_table layout from bisect_layout on oracle shards: union == unsharded, masks consistent with the cells."""
+    from khronos_b200.replay import bisect_layout
+    cam, frames, poses, stamps = _stream(40)
+    ref = hs.make_handle(oracle_lib, "ko_", cam=cam)
+    hs.run_fusion(ref, frames, poses, stamps)
+    want = ref.map_checksum()
+    probe = hs.make_handle(oracle_lib, "ko_", cam=cam)
+    fr0 = [probe.make_frame(d, T, st, label=l) for (d, l), T, st in zip(frames, poses, stamps)]
+    cell = 4
+    origin, touched = _cell_grid(probe, fr0, cell)
+    assert touched.any(axis=(1, 2)).all()
+    table = bisect_layout(touched, world)
+    shards = []
+    for r in range(world):
+        h = hs.make_handle(oracle_lib, "ko_", cam=cam)
+        h.set_shard_table(r, world, cell, origin, table)
+        shards.append(h)
+    masks = shards[0].frame_owners(fr0)
+    # the owner mask of a frame = the ranks of the cells it touches
+    for g in range(len(frames)):
+        ranks = set(np.unique(table[touched[g] != 0]).tolist())
+        assert ranks == {r for r in range(world) if (int(masks[g]) >> r) & 1}, g
+    total = [0, 0, 0, 0]
+    for r, h in enumerate(shards):
+        for g in range(len(frames)):
+            if (int(masks[g]) >> r) & 1:
+                d, l = frames[g]
+                h.integrate_frame(h.make_frame(d, poses[g], stamps[g], label=l), want_stats=False)
+        c = h.map_checksum()
+        total = [(total[0] + c[0]) & M64, total[1] ^ c[1], total[2] + c[2], total[3] + c[3]]
+    assert tuple(total) == want
+
+
+@pytest.mark.gpu
+def test_product_table_layout_matches_oracle_masks_and_map(oracle_lib, product_lib):
+    """The explicit cell table on the device: kb_frame_cells / kb_frame_owners agree with (or contain) the oracle's, and
+    product shards under the table reproduce the unsharded oracle map."""
+    from khronos_b200.replay import bisect_layout
+    world, cell = 4, 4
+    cam, frames, poses, stamps = _stream(40)
+    ref = hs.make_handle(oracle_lib, "ko_", cam=cam)
+    hs.run_fusion(ref, frames, poses, stamps)
+    want = ref.map_checksum()
+    g0 = hs.make_handle(product_lib, "kb_", cam=cam)
+    fr0 = [g0.make_frame(None, T, st) for T, st in zip(poses, stamps)]
+    origin, touched = _cell_grid(g0, fr0, cell)
+    fo = [ref.make_frame(d, T, st, label=l) for (d, l), T, st in zip(frames, poses, stamps)]
+    _, touched_o = _cell_grid(ref, fo, cell)
+    assert ((touched != 0) | (touched_o == 0)).all(), "kb_frame_cells must contain the oracle's exact selection"
+    table = bisect_layout(touched, world)
+    total = [0, 0, 0, 0]
+    for r in range(world):
+        h = hs.make_handle(product_lib, "kb_", cam=cam)
+        h.set_shard_table(r, world, cell, origin, table)
+        masks = h.frame_owners(fr0)
+        batch = [h.make_frame(d, poses[g], stamps[g], label=l) for g, (d, l) in enumerate(frames) if (int(masks[g]) >> r) & 1]
+        for b0 in range(0, len(batch), 32):
+            h.integrate_frames(batch[b0:b0 + 32], want_stats=False)
+        c = h.map_checksum()
+        total = [(total[0] + c[0]) & M64, total[1] ^ c[1], total[2] + c[2], total[3] + c[3]]
+    assert tuple(total) == want

@@ -1,6 +1,6 @@
 """Fuse-kernel variants, selected by environment variables read in kb_create. Since round 2 KB_PIPELINE, KB_FUSE_ITEM_LIST,
 KB_EVERFREE_V2 and KB_MOTION_SPARSE are ON by default (measured wins, profiles/r2_ab1_summary.txt), so the rest of the suite runs
-them and this file also runs the former defaults (=0); KB_FUSE_MLP and KB_H2D_NARROW_LABELS lost their A/Bs and stay off:
+them and this file also runs the former defaults (=0); KB_FUSE_MLP and KB_H2D_NARROW_LABELS lost their A/Bs and stay off; KB_FUSE_COOP selects the CTA-cooperative two-phase fuse kernel:
   KB_FUSE_ITEM_LIST=1  items come from compacted heaviest-first lists instead of the dense box range
   KB_PIPELINE=1        the prologue (tile pyramid, K0, K0b) of batch i+1 runs on its own stream while the fuse kernel of
                        batch i is busy; work lists, pyramids and cursors are double-buffered by batch parity
@@ -22,7 +22,8 @@ pytestmark = pytest.mark.gpu
 VARIANTS = [{"KB_FUSE_ITEM_LIST": "1"}, {"KB_FUSE_MLP": "2"}, {"KB_FUSE_MLP": "4"}, {"KB_FUSE_MLP": "4", "KB_FUSE_ITEM_LIST": "1"},
             {"KB_PIPELINE": "1"}, {"KB_PIPELINE": "1", "KB_FUSE_MLP": "4", "KB_FUSE_ITEM_LIST": "1", "KB_FUSE_CTAS_PER_SM": "3"},
             {"KB_H2D_NARROW_LABELS": "1", "KB_H2D_THREADS": "3"},
-            {"KB_PIPELINE": "0", "KB_FUSE_ITEM_LIST": "0"}, {"KB_PIPELINE": "0"}, {"KB_FUSE_ITEM_LIST": "0"}]
+            {"KB_PIPELINE": "0", "KB_FUSE_ITEM_LIST": "0"}, {"KB_PIPELINE": "0"}, {"KB_FUSE_ITEM_LIST": "0"},
+            {"KB_FUSE_COOP": "1"}, {"KB_FUSE_COOP": "1", "KB_PIPELINE": "0"}, {"KB_FUSE_COOP": "0"}]
 
 
 @pytest.fixture(params=VARIANTS, ids=lambda v: "+".join(f"{k.replace('KB_', '').replace('FUSE_', '')}={x}" for k, x in v.items()))

@@ -11,6 +11,10 @@ timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>
 echo "== full default bench"
 timeout 600 python bench.py > $O/bench_full.json 2> $O/bench_full.err; echo "rc=$?"; python -c "
 import json;d=json.load(open('$O/bench_full.json'));print(round(d['value']),'fps; e2e',d['e2e'] and round(d['e2e']['value']), 'cpu', d['cpu_baseline'] and round(d['cpu_baseline']['value']), d['checksum'], 'frac', d['roofline']['frac'], d['clocks']);print('tick',d['output_tick']['mesh_tick_ms'], d['output_tick']['mirror_back_tick_ms']);print('dynamic',d['configs']['dynamic']['value'], d['configs']['dynamic']['flagged_pixel_fraction_last_frame'], d['configs']['dynamic'].get('cpu_baseline'))" || tail -5 $O/bench_full.err
+echo "== CTA-cooperative fuse kernel (KB_FUSE_COOP=1): parity + A/B"
+KB_FUSE_COOP=1 timeout 600 python -m pytest tests/test_parity_gpu.py tests/test_bench_shape_parity.py tests/test_golden.py -m gpu -q -p no:cacheprovider > $O/gpu_tests_coop.log 2>&1; echo "rc=$?"; tail -4 $O/gpu_tests_coop.log
+for v in 1 0; do KB_FUSE_COOP=$v timeout 200 python bench.py --no-e2e --no-cpu-baseline --no-legs > $O/bench_coop$v.json 2> $O/bench_coop$v.err; python -c "
+import json;d=json.load(open('$O/bench_coop$v.json'));print('coop=$v',round(d['value']),'fps',d['checksum']['sum'],round(d['roofline']['launch_us'],1),'us/group')" || tail -3 $O/bench_coop$v.err; done
 echo "== reference arm"
 timeout 300 python bench.py --impl reference > $O/bench_ref.json 2> $O/bench_ref.err; echo "rc=$?"; head -c 300 $O/bench_ref.json; echo
 K='regex:fuseKernel|selectBlocks|itemCull|itemCompact|tileMax|tilePyramid'
