@@ -303,6 +303,50 @@ class GpuConnectedSemantics {
   kb_object_detector_config config_;
 };
 
+// khronos::InstanceForwarding stand-in (object_detection/instance_forwarding.cpp:73-149; registered "GpuInstanceForwarding",
+// selected by `type:` like the reference's "InstanceForwarding"): object_image = the instance id image, one semantic
+// cluster per id that passes the range / background / size / volume filters. `id_is_background` is the host's per-id open-set
+// decision (the reference asks an EmbeddingGroup, :96-104); empty = closed set.
+class GpuInstanceForwarding {
+ public:
+  explicit GpuInstanceForwarding(const kb_instance_forwarding_config& config) : config_(config) {}
+  void processInput(GpuVolumetricMap& map, khronos::FrameData& data, const std::vector<uint8_t>& id_is_background = {}) const {
+    Timer timer("object_detection/all", data.input.timestamp_ns);  // instance_forwarding.cpp:75
+    kb_frame f = makeFrame(data.input, nullptr, nullptr, 0);
+    map.setSensor(data.input.getSensor());
+    if (data.object_image.empty()) data.object_image = cv::Mat(data.input.depth_image.rows, data.input.depth_image.cols, 4);
+    int32_t n = 0;
+    if (kb_forward_instances(map.handle(), &config_, &f, id_is_background.empty() ? nullptr : id_is_background.data(),
+                             static_cast<int32_t>(id_is_background.size()), data.object_image.ptr<int32_t>(), &n) != KB_OK) {
+      std::fprintf(stderr, "[GpuInstanceForwarding] %s\n", kb_last_error(map.handle()));
+      return;
+    }
+    data.semantic_clusters.clear();
+    if (n == 0) return;
+    int32_t nc = 0, tp = 0;
+    kb_get_instance_clusters(map.handle(), nullptr, nullptr, nullptr, &nc, &tp);
+    std::vector<int32_t> info(2 * static_cast<size_t>(nc)), px(2 * static_cast<size_t>(tp));
+    std::vector<float> bbox(6 * static_cast<size_t>(nc));
+    kb_get_instance_clusters(map.handle(), info.data(), bbox.data(), px.data(), &nc, &tp);
+    size_t po = 0;
+    for (int c = 0; c < nc; ++c) {
+      khronos::MeasurementCluster cl;
+      cl.id = info[2 * c];
+#ifndef KB_HAVE_HYDRA
+      cl.semantic_id = info[2 * c];  // closed set: SemanticClusterInfo(id) (:138-140)
+      for (int a = 0; a < 3; ++a) { cl.bbox_min[a] = bbox[6 * c + a]; cl.bbox_max[a] = bbox[6 * c + 3 + a]; }
+#else
+      cl.semantics = khronos::SemanticClusterInfo(info[2 * c]);
+#endif
+      for (int i = 0; i < info[2 * c + 1]; ++i, ++po) cl.pixels.push_back({px[2 * po], px[2 * po + 1]});
+      data.semantic_clusters.push_back(std::move(cl));
+    }
+  }
+
+ private:
+  kb_instance_forwarding_config config_;
+};
+
 // The measurement step of khronos::MaxIoUTracker with track_by = voxels (tracking/max_iou_tracker.cpp): what
 // setupTrackMeasurements (:450-459), computeCentroid (:534-539) and computeIoU (:551-562) compute for the clusters of one
 // id image (data.dynamic_image or data.object_image) against the voxel sets of the live tracks — one call per image and

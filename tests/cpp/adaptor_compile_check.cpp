@@ -101,6 +101,8 @@ int main(int argc, char** argv) {
                   res[1].absent.size(), res[1].present.size(), res[2].absent.size(), res[2].present.size());
     }
     GpuConnectedSemantics object_detector(dc);
+    const GpuInstanceForwarding instance_forwarding(kb_instance_forwarding_config{0.f, 0, -1, 0.0, -1.0});  // compiled, not run here
+    (void)instance_forwarding;
     if (argc > 2) {  // second argument: also run the object detector (tests/test_zz_object_detection.py)
       object_detector.processInput(gmap, frame);
       std::printf("semantic_clusters=%zu cluster_pixels=%zu ", frame.semantic_clusters.size(),
