@@ -90,9 +90,21 @@ def colour_case(lib):
     return out
 
 
+def mesh_case(lib):
+    """Marching cubes (kb_generate_mesh) over the map of the fusion fixture: inputs are read from fusion.npz, the fixture
+    stores the mesh of all blocks and the map checksum."""
+    g = np.load(os.path.join(HERE, "fusion.npz"))
+    h = hs.make_handle(lib, "ko_", cam=golden_camera())
+    frames = [(np.ascontiguousarray(d), np.ascontiguousarray(l)) for d, l in zip(g["depth"], g["label"])]
+    hs.run_fusion(h, frames, list(g["poses"]), [int(s) for s in g["stamps"]], tracking=True)
+    bi, off, pts, col, lab = h.generate_mesh(False, False)
+    return {"block_index": bi, "offsets": off, "points_bits": pts.view(np.uint32), "labels": lab.astype(np.uint8),
+            "checksum": np.array(h.map_checksum(), np.uint64)}
+
+
 if __name__ == "__main__":
     lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "liboracle.so"))
-    cases = (("fusion", fusion_case), ("dynamic", dynamic_case), ("colour", colour_case))
+    cases = (("fusion", fusion_case), ("dynamic", dynamic_case), ("colour", colour_case), ("mesh", mesh_case))
     for name, fn in cases:
         if len(sys.argv) > 1 and name not in sys.argv[1:]:
             continue

@@ -63,6 +63,24 @@ def run_colour_case(lib, prefix):
     np.testing.assert_array_equal(g["b_color"], b.color)
 
 
+def run_mesh_case(lib, prefix):
+    """Mesh + map checksum of the fusion fixture's map (tests/golden/mesh.npz)."""
+    g, m = np.load(os.path.join(GOLD, "fusion.npz")), np.load(os.path.join(GOLD, "mesh.npz"))
+    h = hs.make_handle(lib, prefix, cam=golden_camera())
+    frames = [(np.ascontiguousarray(d), np.ascontiguousarray(l)) for d, l in zip(g["depth"], g["label"])]
+    hs.run_fusion(h, frames, list(g["poses"]), [int(s) for s in g["stamps"]], tracking=True)
+    assert tuple(int(x) for x in m["checksum"]) == h.map_checksum()
+    bi, off, pts, col, lab = h.generate_mesh(False, False)
+    np.testing.assert_array_equal(m["block_index"], bi)
+    np.testing.assert_array_equal(m["offsets"], off)
+    np.testing.assert_array_equal(m["points_bits"], pts.view(np.uint32))
+    np.testing.assert_array_equal(m["labels"], lab.astype(np.uint8))
+
+
+def test_oracle_matches_golden_mesh(oracle_lib):
+    run_mesh_case(oracle_lib, "ko_")
+
+
 def test_oracle_matches_golden_fusion(oracle_lib):
     run_fusion_case(oracle_lib, "ko_")
 
@@ -84,6 +102,11 @@ def test_oracle_is_thread_count_invariant(oracle_lib):
     frames = [(np.ascontiguousarray(d), np.ascontiguousarray(l)) for d, l in zip(g["depth"], g["label"])]
     hs.run_fusion(h, frames, list(g["poses"]), [int(s) for s in g["stamps"]], tracking=True)
     check_blocks(g, h.export_blocks())
+
+
+@pytest.mark.gpu
+def test_product_matches_golden_mesh(product_lib):
+    run_mesh_case(product_lib, "kb_")
 
 
 @pytest.mark.gpu
