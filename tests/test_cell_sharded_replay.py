@@ -304,3 +304,32 @@ def test_product_table_layout_matches_oracle_masks_and_map(oracle_lib, product_l
         c = h.map_checksum()
         total = [(total[0] + c[0]) & M64, total[1] ^ c[1], total[2] + c[2], total[3] + c[3]]
     assert tuple(total) == want
+
+
+@pytest.mark.parametrize("world", [1, 3, 5, 6, 7])
+def test_layouts_for_any_rank_count(world):
+    """bisect_layout / route_homes / rank_grid for rank counts that are not powers of two (and the trivial one)."""
+    from khronos_b200.replay import bisect_layout
+    rng = np.random.default_rng(world)
+    F, H, W = 300, 7, 9
+    t = np.zeros((F, H, W), np.uint8)
+    for f in range(F):
+        cx, cy = int(rng.integers(0, W - 1)), int(rng.integers(0, H - 1))
+        t[f, cy:cy + 2, cx:cx + 2] = 1
+    tab = bisect_layout(t, world)
+    assert set(np.unique(tab)) == set(range(world))
+    masks = np.zeros(F, np.uint32)
+    for f in range(F):
+        for r in np.unique(tab[t[f] != 0]):
+            masks[f] |= np.uint32(1 << int(r))
+    homes = route_homes(masks, world, 16)
+    assert homes.min() >= 0 and homes.max() < world
+    gx, gy = rank_grid(world)
+    assert gx * gy == world and gx >= gy
+    total = 0
+    for r in range(world):
+        s = StripedSchedule(world, r, 16, homes=homes)
+        plan = s.plan(list(range(F)), masks)
+        total += len(plan.mine)
+        assert all(src != r for src, _, _, _ in plan.ranges)
+    assert total == int(sum(bin(int(m)).count("1") for m in masks))
