@@ -194,6 +194,19 @@ int kb_set_shard_table(kb_handle* h, int rank, int nranks, int cell_blocks, int3
  * (origin_cx + cx, origin_cy + cy): the per-cell counterpart of kb_frame_owners (host arithmetic on the poses only). */
 int kb_frame_cells(kb_handle* h, const kb_frame* frames, int32_t n_frames, int cell_blocks, int32_t origin_cx,
                    int32_t origin_cy, int32_t width, int32_t height, uint8_t* touched);
+/* Handle-free variants of kb_frame_owners / kb_frame_cells (need no GPU): the scheduler of a sharded replay may run on a host
+ * without a device. The layout is passed explicitly: cell_blocks == 0 = per-block hash (kb_set_shard); table == NULL = periodic
+ * tiling (kb_set_shard_cells); otherwise the table of kb_set_shard_table. Same arithmetic as the handle-based calls. */
+typedef struct kb_shard_layout {
+  int32_t nranks, cell_blocks, grid_x, grid_y;
+  int32_t table_origin_cx, table_origin_cy, table_width, table_height;
+  const uint8_t* table;
+} kb_shard_layout;
+int kb_frame_owners_host(const kb_camera* camera, float voxel_size, int32_t voxels_per_side, const kb_shard_layout* layout,
+                         const kb_frame* frames, int32_t n_frames, uint32_t* owner_mask);
+int kb_frame_cells_host(const kb_camera* camera, float voxel_size, int32_t voxels_per_side, const kb_frame* frames,
+                        int32_t n_frames, int cell_blocks, int32_t origin_cx, int32_t origin_cy, int32_t width, int32_t height,
+                        uint8_t* touched);
 /* Owner of a block under the cell layout (pure function; usable without a device). */
 int kb_cell_owner(int32_t bx, int32_t by, int cell_blocks, int grid_x, int grid_y, int nranks);
 /* Which ranks need a frame: bit r of owner_mask[i] is set iff some block that hydra's findBlocksInViewFrustum would select

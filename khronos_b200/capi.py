@@ -66,6 +66,36 @@ class InstanceForwardingConfig(C.Structure):
                 ("min_object_volume", C.c_double), ("max_object_volume", C.c_double)]
 
 
+class ShardLayout(C.Structure):
+    _fields_ = [("nranks", C.c_int32), ("cell_blocks", C.c_int32), ("grid_x", C.c_int32), ("grid_y", C.c_int32),
+                ("table_origin_cx", C.c_int32), ("table_origin_cy", C.c_int32), ("table_width", C.c_int32),
+                ("table_height", C.c_int32), ("table", C.c_void_p)]
+
+
+def frame_owners_host(lib, prefix, cam, voxel_size, vps, frames, nranks, cell_blocks=0, grid=(1, 1), origin=(0, 0), table=None):
+    """kb_frame_owners_host / ko_frame_owners_host: owner masks without a handle (no GPU needed)."""
+    arr = frames if isinstance(frames, C.Array) else (Frame * len(frames))(*frames)
+    t = None if table is None else np.ascontiguousarray(table, np.uint8)
+    lay = ShardLayout(nranks, cell_blocks, grid[0], grid[1], int(origin[0]), int(origin[1]), 0 if t is None else t.shape[1],
+                      0 if t is None else t.shape[0], None if t is None else t.ctypes.data)
+    out = np.zeros(len(arr), np.uint32)
+    st = getattr(lib, prefix + "frame_owners_host")(C.byref(cam), C.c_float(voxel_size), vps, C.byref(lay), arr, len(arr), C.c_void_p(out.ctypes.data))
+    if st != KB_OK:
+        raise KbError(st, "frame_owners_host failed")
+    return out
+
+
+def frame_cells_host(lib, prefix, cam, voxel_size, vps, frames, cell_blocks, origin, width, height):
+    """kb_frame_cells_host / ko_frame_cells_host: (n, height, width) touched cells without a handle."""
+    arr = frames if isinstance(frames, C.Array) else (Frame * len(frames))(*frames)
+    out = np.zeros((len(arr), height, width), np.uint8)
+    st = getattr(lib, prefix + "frame_cells_host")(C.byref(cam), C.c_float(voxel_size), vps, arr, len(arr), cell_blocks, int(origin[0]), int(origin[1]),
+                                                   width, height, C.c_void_p(out.ctypes.data))
+    if st != KB_OK:
+        raise KbError(st, "frame_cells_host failed")
+    return out
+
+
 class Camera(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("fx", C.c_float), ("fy", C.c_float),
                 ("cx", C.c_float), ("cy", C.c_float), ("min_range", C.c_float),

@@ -756,15 +756,6 @@ int kb_set_shard_cells(kb_handle* h, int rank, int nranks, int cell_blocks, int 
   return KB_OK;
 }
 
-// Host-side owner of a block under the handle's layout (same function as the device's mapOwner, on the host copy of the table).
-static int hostOwner(const kb_handle* h, int x, int y, int z) {
-  const DeviceMap& m = h->dm;
-  if (m.shard_cell <= 0) return blockOwner(x, y, z, h->nranks);
-  if (!h->shard_table_host.empty())
-    return tableOwner(h->shard_table_host.data(), m.tab_ox, m.tab_oy, m.tab_w, m.tab_h, m.shard_cell, m.shard_gx, m.shard_gy, x, y, h->nranks);
-  return cellOwner(x, y, m.shard_cell, m.shard_gx, m.shard_gy, h->nranks);
-}
-
 int kb_set_shard_table(kb_handle* h, int rank, int nranks, int cell_blocks, int32_t origin_cx, int32_t origin_cy, int32_t width,
                        int32_t height, const uint8_t* owners) {
   if (h) h->main_dirty = true;
@@ -799,47 +790,89 @@ int kb_cell_owner(int32_t bx, int32_t by, int cell_blocks, int grid_x, int grid_
   return cellOwner(bx, by, cell_blocks, grid_x, grid_y, nranks);
 }
 
-// Host restatement of K0's candidate test (selectBlocksKernel: xform + inFrustum, same fp32 expressions; this
-// translation unit is compiled without FMA contraction like the device code) for the frame scheduler of a sharded replay.
-int kb_frame_owners(kb_handle* h, const kb_frame* frames, int32_t n_frames, uint32_t* owner_mask) {
-  if (!h || !frames || !owner_mask || n_frames < 0) return fail(h, KB_ERR_INVALID, "null argument");
-  if (!h->has_cam) return fail(h, KB_ERR_STATE, "kb_set_camera must be called first");
-  if (h->nranks > 32) return fail(h, KB_ERR_INVALID, "kb_frame_owners supports at most 32 ranks");
+// ---- host-side frame scheduling arithmetic (kb_frame_owners / kb_frame_cells and their handle-free _host variants) --------
+// A restatement of K0's candidate test (selectBlocksKernel: xform + inFrustum, same fp32 expressions; this translation unit is
+// compiled without FMA contraction like the device code), evaluated with a 1 mm larger inflation so that the result is a
+// superset of the device's selection.
+namespace {
+struct HostFrustum { float pl[4][2]; float infl, min_range, max_range, block_size; };
+struct HostLayout { int nranks, cell, gx, gy; const uint8_t* table; int ox, oy, w, h; };
+
+// The frustum side planes / inflation of a camera: the expressions of kb_set_camera.
+void hostFrustum(const kb_camera& c, float block_size, HostFrustum* f) {
+  const float xl = (0.f - c.cx) / c.fx, xr = (static_cast<float>(c.width - 1) - c.cx) / c.fx;
+  const float yt = (0.f - c.cy) / c.fy, yb = (static_cast<float>(c.height - 1) - c.cy) / c.fy;
+  const float il = 1.f / std::sqrt(1.f + xl * xl), ir = 1.f / std::sqrt(1.f + xr * xr);
+  const float it = 1.f / std::sqrt(1.f + yt * yt), ib = 1.f / std::sqrt(1.f + yb * yb);
+  f->pl[0][0] = il;  f->pl[0][1] = -xl * il;
+  f->pl[1][0] = -ir; f->pl[1][1] = xr * ir;
+  f->pl[2][0] = it;  f->pl[2][1] = -yt * it;
+  f->pl[3][0] = -ib; f->pl[3][1] = yb * ib;
+  f->infl = block_size * 0.8660254f;
+  f->min_range = c.min_range;
+  f->max_range = c.max_range;
+  f->block_size = block_size;
+}
+
+void handleFrustum(const kb_handle* h, HostFrustum* f) {  // the values the kernels use
   const BatchParams& p = h->batch;
-  const uint32_t all = h->nranks >= 32 ? 0xffffffffu : ((1u << h->nranks) - 1u);
-  const float infl = p.infl + 1e-3f;  // superset of the device's selection
+  std::memcpy(f->pl, p.pl, sizeof(f->pl));
+  f->infl = p.infl; f->min_range = p.min_range; f->max_range = p.max_range; f->block_size = p.block_size;
+}
+
+int layoutOwner(const HostLayout& L, int x, int y, int z) {
+  if (L.cell <= 0) return blockOwner(x, y, z, L.nranks);
+  if (L.table) return tableOwner(L.table, L.ox, L.oy, L.w, L.h, L.cell, L.gx, L.gy, x, y, L.nranks);
+  return cellOwner(x, y, L.cell, L.gx, L.gy, L.nranks);
+}
+
+inline bool candidateSelected(const HostFrustum& f, float infl, const float R[9], const float t[3], int bx, int by, int bz) {
+  const float cx = (static_cast<float>(bx) + 0.5f) * f.block_size;
+  const float cy = (static_cast<float>(by) + 0.5f) * f.block_size;
+  const float cz = (static_cast<float>(bz) + 0.5f) * f.block_size;
+  const float x = ((R[0] * cx + R[1] * cy) + R[2] * cz) + t[0];
+  const float y = ((R[3] * cx + R[4] * cy) + R[5] * cz) + t[1];
+  const float z = ((R[6] * cx + R[7] * cy) + R[8] * cz) + t[2];
+  if (z < -infl) return false;
+  const float r = std::sqrt((x * x + y * y) + z * z);
+  if (r < f.min_range - infl || r > f.max_range + infl) return false;
+  if (f.pl[0][0] * x + f.pl[0][1] * z < -infl) return false;
+  if (f.pl[1][0] * x + f.pl[1][1] * z < -infl) return false;
+  if (f.pl[2][0] * y + f.pl[2][1] * z < -infl) return false;
+  if (f.pl[3][0] * y + f.pl[3][1] * z < -infl) return false;
+  return true;
+}
+
+// returns false on a non-finite pose
+bool frameBox(const HostFrustum& f, float infl, const kb_frame& fr, float R[9], float t[3], int lo[3], int hi[3]) {
+  float Rw[9], tw[3];
+  for (int k = 0; k < 16; ++k)
+    if (!std::isfinite(fr.world_T_sensor[k])) return false;
+  poseToFloat(fr.world_T_sensor, R, t, Rw, tw);
+  const float reach = f.max_range + infl;
+  const float inv = 1.f / f.block_size;
+  for (int a = 0; a < 3; ++a) {
+    lo[a] = static_cast<int>(std::floor((tw[a] - reach) * inv));
+    hi[a] = static_cast<int>(std::floor((tw[a] + reach) * inv));
+  }
+  return true;
+}
+
+int frameOwnersImpl(const HostFrustum& f, const HostLayout& L, const kb_frame* frames, int32_t n_frames, uint32_t* owner_mask) {
+  const uint32_t all = L.nranks >= 32 ? 0xffffffffu : ((1u << L.nranks) - 1u);
+  const float infl = f.infl + 1e-3f;  // superset of the device's selection
   for (int i = 0; i < n_frames; ++i) {
-    float R[9], t[3], Rw[9], tw[3];
-    for (int k = 0; k < 16; ++k)
-      if (!std::isfinite(frames[i].world_T_sensor[k])) return fail(h, KB_ERR_INVALID, "non-finite sensor pose");
-    poseToFloat(frames[i].world_T_sensor, R, t, Rw, tw);
-    uint32_t mask = 0;
-    if (h->nranks == 1) { owner_mask[i] = 1u; continue; }
-    const float reach = h->cam.max_range + infl;
-    const float inv = 1.f / h->block_size;
+    float R[9], t[3];
     int lo[3], hi[3];
-    for (int a = 0; a < 3; ++a) {
-      lo[a] = static_cast<int>(std::floor((tw[a] - reach) * inv));
-      hi[a] = static_cast<int>(std::floor((tw[a] + reach) * inv));
-    }
+    if (!frameBox(f, infl, frames[i], R, t, lo, hi)) return KB_ERR_INVALID;
+    if (L.nranks == 1) { owner_mask[i] = 1u; continue; }
+    uint32_t mask = 0;
     for (int bz = lo[2]; bz <= hi[2] && mask != all; ++bz)
       for (int by = lo[1]; by <= hi[1] && mask != all; ++by)
         for (int bx = lo[0]; bx <= hi[0]; ++bx) {
-          const int owner = hostOwner(h, bx, by, bz);
+          const int owner = layoutOwner(L, bx, by, bz);
           if ((mask >> owner) & 1u) continue;
-          const float cx = (static_cast<float>(bx) + 0.5f) * p.block_size;
-          const float cy = (static_cast<float>(by) + 0.5f) * p.block_size;
-          const float cz = (static_cast<float>(bz) + 0.5f) * p.block_size;
-          const float x = ((R[0] * cx + R[1] * cy) + R[2] * cz) + t[0];
-          const float y = ((R[3] * cx + R[4] * cy) + R[5] * cz) + t[1];
-          const float z = ((R[6] * cx + R[7] * cy) + R[8] * cz) + t[2];
-          if (z < -infl) continue;
-          const float r = std::sqrt((x * x + y * y) + z * z);
-          if (r < p.min_range - infl || r > p.max_range + infl) continue;
-          if (p.pl[0][0] * x + p.pl[0][1] * z < -infl) continue;
-          if (p.pl[1][0] * x + p.pl[1][1] * z < -infl) continue;
-          if (p.pl[2][0] * y + p.pl[2][1] * z < -infl) continue;
-          if (p.pl[3][0] * y + p.pl[3][1] * z < -infl) continue;
+          if (!candidateSelected(f, infl, R, t, bx, by, bz)) continue;
           mask |= 1u << owner;
           if (mask == all) break;
         }
@@ -848,56 +881,77 @@ int kb_frame_owners(kb_handle* h, const kb_frame* frames, int32_t n_frames, uint
   return KB_OK;
 }
 
-// Which cells of a cell grid a frame's candidate blocks fall into (the input of a trajectory-aware layout, kb_set_shard_table):
-// same candidate test as kb_frame_owners.
-int kb_frame_cells(kb_handle* h, const kb_frame* frames, int32_t n_frames, int cell_blocks, int32_t origin_cx, int32_t origin_cy,
+int frameCellsImpl(const HostFrustum& f, const kb_frame* frames, int32_t n_frames, int cell_blocks, int32_t origin_cx, int32_t origin_cy,
                    int32_t width, int32_t height, uint8_t* touched) {
-  if (!h || !frames || !touched || n_frames < 0 || cell_blocks < 1 || width < 1 || height < 1) return fail(h, KB_ERR_INVALID, "invalid argument");
-  if (!h->has_cam) return fail(h, KB_ERR_STATE, "kb_set_camera must be called first");
-  const BatchParams& p = h->batch;
-  const float infl = p.infl + 1e-3f;
+  const float infl = f.infl + 1e-3f;
   const size_t cells = static_cast<size_t>(width) * height;
   std::memset(touched, 0, cells * static_cast<size_t>(n_frames));
   for (int i = 0; i < n_frames; ++i) {
-    float R[9], t[3], Rw[9], tw[3];
-    for (int k = 0; k < 16; ++k)
-      if (!std::isfinite(frames[i].world_T_sensor[k])) return fail(h, KB_ERR_INVALID, "non-finite sensor pose");
-    poseToFloat(frames[i].world_T_sensor, R, t, Rw, tw);
-    uint8_t* row = touched + cells * static_cast<size_t>(i);
-    const float reach = h->cam.max_range + infl;
-    const float inv = 1.f / h->block_size;
+    float R[9], t[3];
     int lo[3], hi[3];
-    for (int a = 0; a < 3; ++a) {
-      lo[a] = static_cast<int>(std::floor((tw[a] - reach) * inv));
-      hi[a] = static_cast<int>(std::floor((tw[a] + reach) * inv));
-    }
+    if (!frameBox(f, infl, frames[i], R, t, lo, hi)) return KB_ERR_INVALID;
+    uint8_t* row = touched + cells * static_cast<size_t>(i);
     for (int by = lo[1]; by <= hi[1]; ++by) {
       const int cy = floorDiv(by, cell_blocks) - origin_cy;
       if (cy < 0 || cy >= height) continue;
       for (int bx = lo[0]; bx <= hi[0]; ++bx) {
         const int cx = floorDiv(bx, cell_blocks) - origin_cx;
         if (cx < 0 || cx >= width || row[cy * width + cx]) continue;
-        for (int bz = lo[2]; bz <= hi[2]; ++bz) {
-          const float px = (static_cast<float>(bx) + 0.5f) * p.block_size;
-          const float py = (static_cast<float>(by) + 0.5f) * p.block_size;
-          const float pz = (static_cast<float>(bz) + 0.5f) * p.block_size;
-          const float x = ((R[0] * px + R[1] * py) + R[2] * pz) + t[0];
-          const float y = ((R[3] * px + R[4] * py) + R[5] * pz) + t[1];
-          const float z = ((R[6] * px + R[7] * py) + R[8] * pz) + t[2];
-          if (z < -infl) continue;
-          const float r = std::sqrt((x * x + y * y) + z * z);
-          if (r < p.min_range - infl || r > p.max_range + infl) continue;
-          if (p.pl[0][0] * x + p.pl[0][1] * z < -infl) continue;
-          if (p.pl[1][0] * x + p.pl[1][1] * z < -infl) continue;
-          if (p.pl[2][0] * y + p.pl[2][1] * z < -infl) continue;
-          if (p.pl[3][0] * y + p.pl[3][1] * z < -infl) continue;
-          row[cy * width + cx] = 1;
-          break;
-        }
+        for (int bz = lo[2]; bz <= hi[2]; ++bz)
+          if (candidateSelected(f, infl, R, t, bx, by, bz)) { row[cy * width + cx] = 1; break; }
       }
     }
   }
   return KB_OK;
+}
+
+HostLayout handleLayout(const kb_handle* h) {
+  const DeviceMap& m = h->dm;
+  return HostLayout{h->nranks, m.shard_cell, m.shard_gx, m.shard_gy, h->shard_table_host.empty() ? nullptr : h->shard_table_host.data(),
+                    m.tab_ox, m.tab_oy, m.tab_w, m.tab_h};
+}
+}  // namespace
+
+int kb_frame_owners(kb_handle* h, const kb_frame* frames, int32_t n_frames, uint32_t* owner_mask) {
+  if (!h || !frames || !owner_mask || n_frames < 0) return fail(h, KB_ERR_INVALID, "null argument");
+  if (!h->has_cam) return fail(h, KB_ERR_STATE, "kb_set_camera must be called first");
+  if (h->nranks > 32) return fail(h, KB_ERR_INVALID, "kb_frame_owners supports at most 32 ranks");
+  HostFrustum f;
+  handleFrustum(h, &f);
+  const int st = frameOwnersImpl(f, handleLayout(h), frames, n_frames, owner_mask);
+  return st == KB_OK ? KB_OK : fail(h, st, "non-finite sensor pose");
+}
+
+int kb_frame_cells(kb_handle* h, const kb_frame* frames, int32_t n_frames, int cell_blocks, int32_t origin_cx, int32_t origin_cy,
+                   int32_t width, int32_t height, uint8_t* touched) {
+  if (!h || !frames || !touched || n_frames < 0 || cell_blocks < 1 || width < 1 || height < 1) return fail(h, KB_ERR_INVALID, "invalid argument");
+  if (!h->has_cam) return fail(h, KB_ERR_STATE, "kb_set_camera must be called first");
+  HostFrustum f;
+  handleFrustum(h, &f);
+  const int st = frameCellsImpl(f, frames, n_frames, cell_blocks, origin_cx, origin_cy, width, height, touched);
+  return st == KB_OK ? KB_OK : fail(h, st, "non-finite sensor pose");
+}
+
+// Handle-free variants (need no GPU): the scheduler of a sharded replay can run on a host without a device.
+int kb_frame_owners_host(const kb_camera* camera, float voxel_size, int32_t voxels_per_side, const kb_shard_layout* layout,
+                         const kb_frame* frames, int32_t n_frames, uint32_t* owner_mask) {
+  if (!camera || !layout || !frames || !owner_mask || n_frames < 0 || !(voxel_size > 0.f) || voxels_per_side < 1 || layout->nranks < 1 ||
+      layout->nranks > 32 || layout->cell_blocks < 0 || (layout->cell_blocks > 0 && (layout->grid_x < 1 || layout->grid_y < 1)))
+    return KB_ERR_INVALID;
+  HostFrustum f;
+  hostFrustum(*camera, voxel_size * static_cast<float>(voxels_per_side), &f);
+  const HostLayout L{layout->nranks, layout->cell_blocks, layout->grid_x, layout->grid_y, layout->table, layout->table_origin_cx,
+                     layout->table_origin_cy, layout->table_width, layout->table_height};
+  return frameOwnersImpl(f, L, frames, n_frames, owner_mask);
+}
+
+int kb_frame_cells_host(const kb_camera* camera, float voxel_size, int32_t voxels_per_side, const kb_frame* frames, int32_t n_frames,
+                        int cell_blocks, int32_t origin_cx, int32_t origin_cy, int32_t width, int32_t height, uint8_t* touched) {
+  if (!camera || !frames || !touched || n_frames < 0 || !(voxel_size > 0.f) || voxels_per_side < 1 || cell_blocks < 1 || width < 1 || height < 1)
+    return KB_ERR_INVALID;
+  HostFrustum f;
+  hostFrustum(*camera, voxel_size * static_cast<float>(voxels_per_side), &f);
+  return frameCellsImpl(f, frames, n_frames, cell_blocks, origin_cx, origin_cy, width, height, touched);
 }
 
 // Fuses up to kMaxBatch frames with one K0 + one K1 launch (plus one tile-max launch when culling).

@@ -359,6 +359,40 @@ int ko_frame_cells(ko_handle* h, const kb_frame* frames, int32_t n, int cell_blo
   for (int i = 0; i < n; ++i) h->o->frameCells(frames[i], cell_blocks, origin_cx, origin_cy, width, height, touched + cells * i);
   return KB_OK;
 }
+// Handle-free mirrors: a throw-away oracle carries the camera and the layout.
+static Oracle* layoutOracle(const kb_camera* camera, float voxel_size, int32_t vps, const kb_shard_layout* layout) {
+  kb_map_config mc{};
+  mc.voxel_size = voxel_size; mc.voxels_per_side = vps; mc.truncation_distance = 3.f * voxel_size; mc.max_blocks = 1;
+  kb_integrator_config ic{};
+  ic.max_weight = 1e5f; ic.interpolation_method = KB_INTERP_ADAPTIVE; ic.adaptive_max_depth_difference = 0.2f; ic.num_threads = 1;
+  Oracle* o = new Oracle(mc, ic, nullptr, nullptr);
+  o->setCamera(*camera);
+  if (layout) {
+    if (layout->cell_blocks <= 0) o->setShard(0, layout->nranks);
+    else if (layout->table) o->setShardTable(0, layout->nranks, layout->cell_blocks, layout->table_origin_cx, layout->table_origin_cy,
+                                             layout->table_width, layout->table_height, layout->table);
+    else o->setShardCells(0, layout->nranks, layout->cell_blocks, layout->grid_x, layout->grid_y);
+  }
+  return o;
+}
+int ko_frame_owners_host(const kb_camera* camera, float voxel_size, int32_t voxels_per_side, const kb_shard_layout* layout,
+                         const kb_frame* frames, int32_t n, uint32_t* owner_mask) {
+  if (!camera || !layout || !frames || !owner_mask || n < 0 || layout->nranks < 1 || layout->nranks > 32) return KB_ERR_INVALID;
+  Oracle* o = layoutOracle(camera, voxel_size, voxels_per_side, layout);
+  for (int i = 0; i < n; ++i) owner_mask[i] = o->frameOwners(frames[i]);
+  delete o;
+  return KB_OK;
+}
+int ko_frame_cells_host(const kb_camera* camera, float voxel_size, int32_t voxels_per_side, const kb_frame* frames, int32_t n,
+                        int cell_blocks, int32_t origin_cx, int32_t origin_cy, int32_t width, int32_t height, uint8_t* touched) {
+  if (!camera || !frames || !touched || n < 0 || cell_blocks < 1 || width < 1 || height < 1) return KB_ERR_INVALID;
+  Oracle* o = layoutOracle(camera, voxel_size, voxels_per_side, nullptr);
+  const size_t cells = static_cast<size_t>(width) * height;
+  std::memset(touched, 0, cells * static_cast<size_t>(n));
+  for (int i = 0; i < n; ++i) o->frameCells(frames[i], cell_blocks, origin_cx, origin_cy, width, height, touched + cells * i);
+  delete o;
+  return KB_OK;
+}
 int ko_cell_owner(int32_t bx, int32_t by, int cell_blocks, int grid_x, int grid_y, int nranks) {
   return Oracle::cellOwner(bx, by, cell_blocks, grid_x, grid_y, nranks);
 }
