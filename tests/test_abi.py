@@ -13,7 +13,7 @@ from harness import ROOT, has_gpu
 
 def declared_symbols():
     src = open(os.path.join(ROOT, "include", "khronos_b200.h")).read()
-    return sorted(set(re.findall(r"^(?:int|const char\*)\s+(kb_\w+)\s*\(", src, flags=re.M)))
+    return sorted(set(re.findall(r"^(?:int|const char\*|uint64_t)\s+(kb_\w+)\s*\(", src, flags=re.M)))
 
 
 def test_header_declares_expected_entry_points():
